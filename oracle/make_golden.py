@@ -1,0 +1,222 @@
+"""Generate golden traces by running the UNMODIFIED reference (`/root/reference`) on CPU.
+
+TEST INFRASTRUCTURE ONLY (never imported by the product).  Runs in the build container, where the
+reference tree exists; the GPU box only ever sees the committed `.npz` fixtures in `tests/golden/`.
+
+    python oracle/make_golden.py            # regenerate every fixture
+    python oracle/make_golden.py c2_year    # one case
+
+The reference needs two pure-Python packages that are absent from this image (`gymnasium`,
+`simplejson`); `oracle/shims/` holds minimal stand-ins.  The dataset cache is
+seeded from `/root/reference/data/misc` so that `DataSet()` never touches the network
+(`citylearn/citylearn.py:2055-2057`).
+
+Fixture format (one `.npz` per case): `config` (JSON: dataset, overrides, reward), `actions`
+[K, sum(A_b)] float32 fed as exact Python floats, `steps` (indices of recorded steps), per-step arrays
+`obs` [n, L], `reward` [n, R], `district` [n, 3], per-building internals `trace` [n, B, NTRACE] in
+`TRACE_NAMES` order, plus `meta` (JSON: names, spaces, resolved device parameters).
+"""
+import json
+import logging
+import os
+import shutil
+import sys
+from pathlib import Path
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+REF = Path('/root/reference')
+DATASETS = REF / 'data' / 'datasets'
+OUT = HERE.parent / 'tests' / 'golden'
+
+TRACE_NAMES = [
+    'electrical_storage_soc', 'electrical_storage_energy_balance', 'electrical_storage_electricity_consumption',
+    'electrical_storage_efficiency', 'electrical_storage_degraded_capacity',
+    'non_shiftable_load_electricity_consumption', 'cooling_electricity_consumption', 'heating_electricity_consumption',
+    'dhw_electricity_consumption', 'cooling_storage_soc', 'heating_storage_soc', 'dhw_storage_soc',
+    'cooling_storage_energy_balance', 'heating_storage_energy_balance', 'dhw_storage_energy_balance',
+    'net_electricity_consumption', 'net_electricity_consumption_cost', 'net_electricity_consumption_emission',
+    'indoor_dry_bulb_temperature', 'cooling_demand', 'heating_demand', 'energy_from_cooling_device',
+    'energy_from_dhw_device', 'power_outage',
+]
+
+
+def import_reference():
+    sys.path.insert(0, str(HERE / 'shims'))
+    sys.path.insert(0, str(REF))
+    from platformdirs import user_cache_dir
+    d = user_cache_dir(appname='citylearn', appauthor='intelligent-environments-lab', version='v2.4.2')
+    os.makedirs(d + '/misc', exist_ok=True)
+    for f in ('battery_choices.yaml', 'lbl-tracking_the_sun-res-pv.csv'):
+        if not os.path.isfile(d + '/misc/' + f):
+            shutil.copy(REF / 'data' / 'misc' / f, d + '/misc/' + f)
+    logging.getLogger().setLevel(logging.WARNING)
+    from citylearn.citylearn import CityLearnEnv
+    return CityLearnEnv
+
+
+def make_env(CityLearnEnv, dataset, overrides=None, reward=None):
+    overrides = dict(overrides or {})
+    root = DATASETS / dataset
+    schema = json.load(open(root / 'schema.json'))
+    schema['root_directory'] = str(root)
+    if reward is not None:   # set in the schema dict so that schema attributes do not leak
+        schema['reward_function'] = {'type': reward['type'], 'attributes': reward.get('attributes', {})}
+    return CityLearnEnv(schema, **overrides)
+
+
+def unit_trace(b, t):
+    es = b.electrical_storage
+    def at(a):
+        return float(a[t])
+    return [
+        at(es.soc), at(es.energy_balance), at(es.electricity_consumption), float(es.efficiency_history[min(t + 1, len(es.efficiency_history) - 1)]),
+        float(es.capacity_history[min(t + 1, len(es.capacity_history) - 1)]),
+        at(b.non_shiftable_load_device.electricity_consumption), at(b.cooling_device.electricity_consumption),
+        at(b.heating_device.electricity_consumption), at(b.dhw_device.electricity_consumption),
+        at(b.cooling_storage.soc), at(b.heating_storage.soc), at(b.dhw_storage.soc),
+        at(b.cooling_storage.energy_balance), at(b.heating_storage.energy_balance), at(b.dhw_storage.energy_balance),
+        at(b.net_electricity_consumption), at(b.net_electricity_consumption_cost), at(b.net_electricity_consumption_emission),
+        at(b.energy_simulation.indoor_dry_bulb_temperature), at(b.energy_simulation.cooling_demand),
+        at(b.energy_simulation.heating_demand), at(b.energy_from_cooling_device), at(b.energy_from_dhw_device),
+        float(b.power_outage_signal[t]),
+    ]
+
+
+def device_meta(d):
+    out = {}
+    for k, v in d.get_metadata().items():
+        if isinstance(v, np.ndarray):
+            out[k] = v.tolist()
+        elif isinstance(v, (int, float, str, bool)) or v is None:
+            out[k] = v
+        elif isinstance(v, np.generic):
+            out[k] = v.item()
+    out['class'] = type(d).__name__
+    return out
+
+
+def env_meta(env):
+    meta = {
+        'observation_names': env.observation_names, 'action_names': env.action_names,
+        'observation_low': [s.low.tolist() for s in env.observation_space],
+        'observation_high': [s.high.tolist() for s in env.observation_space],
+        'action_low': [s.low.tolist() for s in env.action_space], 'action_high': [s.high.tolist() for s in env.action_space],
+        'central_agent': env.central_agent, 'shared_observations': env.shared_observations,
+        'time_steps': env.time_steps, 'seconds_per_time_step': env.seconds_per_time_step, 'random_seed': env.random_seed,
+        'buildings': [],
+    }
+    for b in env.buildings:
+        meta['buildings'].append({
+            'name': b.name, 'active_observations': b.active_observations, 'active_actions': b.active_actions,
+            'observation_low': b.observation_space.low.tolist(), 'observation_high': b.observation_space.high.tolist(),
+            'action_low': b.action_space.low.tolist(), 'action_high': b.action_space.high.tolist(),
+            **{dn: device_meta(getattr(b, dn)) for dn in ('cooling_device', 'heating_device', 'dhw_device', 'cooling_storage',
+                                                            'heating_storage', 'dhw_storage', 'electrical_storage', 'pv')},
+            'time_step_ratio': b.time_step_ratio,
+        })
+    return meta
+
+
+def flat(list_of_lists):
+    return np.array([float(v) for row in list_of_lists for v in (row if isinstance(row, (list, tuple, np.ndarray)) else [row])], dtype='float64')
+
+
+def run_case(CityLearnEnv, name, dataset, overrides=None, reward=None, steps=None, seed=0, record=None, episodes=1, resets_with_seed=None):
+    env = make_env(CityLearnEnv, dataset, overrides, reward)
+    meta = env_meta(env)
+    lo = np.concatenate([np.asarray(b.action_space.low, dtype='float64') for b in env.buildings])
+    hi = np.concatenate([np.asarray(b.action_space.high, dtype='float64') for b in env.buildings])
+    sizes = [b.action_space.shape[0] for b in env.buildings]
+    rng = np.random.RandomState(seed)
+    out = {'obs': [], 'reward': [], 'district': [], 'trace': [], 'steps': [], 'episode': [], 'reset_obs': [], 'episode_window': [],
+           'terminated': []}
+    all_actions = []
+    for ep in range(episodes):
+        obs, _ = env.reset()
+        out['reset_obs'].append(flat(obs))
+        out['episode_window'].append([env.episode_tracker.episode_start_time_step, env.episode_tracker.episode_end_time_step])
+        K = env.time_steps - 1 if steps is None else min(steps, env.time_steps - 1)
+        u = rng.uniform(0.0, 1.0, size=(K, len(lo)))
+        actions = (lo + u * (hi - lo)).astype('float32')
+        all_actions.append(actions)
+        rec = set(range(K)) if record is None else set(record(K))
+        for k in range(K):
+            a = [float(x) for x in actions[k]]
+            if env.central_agent:
+                act = [a]
+            else:
+                act, o = [], 0
+                for s in sizes:
+                    act.append(a[o:o + s])
+                    o += s
+            obs, rew, term, trunc, _ = env.step(act)
+            if k in rec:
+                out['steps'].append(k)
+                out['episode'].append(ep)
+                out['obs'].append(flat(obs))
+                out['reward'].append(flat(rew))
+                out['district'].append([float(env.net_electricity_consumption[k]), float(env.net_electricity_consumption_cost[k]),
+                                        float(env.net_electricity_consumption_emission[k])])
+                out['trace'].append([unit_trace(b, k) for b in env.buildings])
+                out['terminated'].append(bool(term))
+    arrays = {
+        'actions': np.concatenate(all_actions, axis=0) if episodes == 1 else np.stack(all_actions, axis=0),
+        'steps': np.array(out['steps'], dtype='int32'), 'episode': np.array(out['episode'], dtype='int32'),
+        'obs': np.array(out['obs'], dtype='float32'), 'reward': np.array(out['reward'], dtype='float32'),
+        'district': np.array(out['district'], dtype='float32'), 'trace': np.array(out['trace'], dtype='float32'),
+        'reset_obs': np.array(out['reset_obs'], dtype='float32'), 'episode_window': np.array(out['episode_window'], dtype='int32'),
+        'terminated': np.array(out['terminated'], dtype='bool'),
+    }
+    if env.episode_rewards:
+        er = env.episode_rewards[-1]
+        arrays['episode_reward_sum'] = np.array(er['sum'], dtype='float64')
+        arrays['episode_reward_min'] = np.array(er['min'], dtype='float64')
+        arrays['episode_reward_max'] = np.array(er['max'], dtype='float64')
+    config = {'dataset': dataset, 'overrides': overrides or {}, 'reward': reward, 'seed': seed, 'episodes': episodes,
+              'trace_names': TRACE_NAMES, 'numpy': np.__version__}
+    arrays['config'] = np.frombuffer(json.dumps(config).encode(), dtype='uint8')
+    arrays['meta'] = np.frombuffer(json.dumps(meta).encode(), dtype='uint8')
+    OUT.mkdir(parents=True, exist_ok=True)
+    np.savez_compressed(OUT / f'{name}.npz', **arrays)
+    print(name, {k: v.shape for k, v in arrays.items() if k not in ('config', 'meta')}, (OUT / f'{name}.npz').stat().st_size)
+
+
+def sparse(K):
+    return sorted(set(list(range(0, 48)) + list(range(0, K, 41)) + list(range(K - 48, K))))
+
+
+P1 = 'citylearn_challenge_2022_phase_1'
+PALL = 'citylearn_challenge_2022_phase_all'
+C23 = 'citylearn_challenge_2023_phase_2_local_evaluation'
+MARL = {'type': 'citylearn.reward_function.MARL', 'attributes': {}}
+
+CASES = {
+    # C1: 5 buildings, decentralised, default reward (BASELINE.json configs[0])
+    'c1_phase1_300': dict(dataset=P1, steps=300),
+    'c1_phase1_central': dict(dataset=P1, overrides={'central_agent': True}, steps=60),
+    # C2 schema: 17 buildings, full year, sparse recording + episode reward sums (SURVEY.md Appendix D.2 uses its own actions)
+    'c2_year': dict(dataset=PALL, steps=None, record=sparse),
+    'c2_marl': dict(dataset=PALL, reward=MARL, steps=120),
+    'c2_isac': dict(dataset=PALL, reward={'type': 'citylearn.reward_function.IndependentSACReward', 'attributes': {}}, steps=60),
+    'c2_solar_penalty': dict(dataset=PALL, reward={'type': 'citylearn.reward_function.SolarPenaltyReward', 'attributes': {}}, steps=120),
+    'c2_central_exp2': dict(dataset=PALL, overrides={'central_agent': True},
+                            reward={'type': 'citylearn.reward_function.RewardFunction', 'attributes': {'exponent': 2.0}}, steps=60),
+    # episode windows: consecutive splits inside a sub-range, two episodes
+    'c1_episodes': dict(dataset=P1, overrides={'simulation_start_time_step': 100, 'simulation_end_time_step': 1299,
+                                               'episode_time_steps': 240}, episodes=3, seed=3),
+    # C3 schema: 3 LSTM buildings, outages, decentralised MARL (BASELINE.json configs[2]) and the schema default
+    'c3_marl': dict(dataset=C23, overrides={'central_agent': False}, reward=MARL, steps=None, seed=1),
+    'c3_default_central_comfort': dict(dataset=C23, steps=None, seed=2),
+    'c3_solar_comfort': dict(dataset=C23, overrides={'central_agent': False},
+                             reward={'type': 'citylearn.reward_function.SolarPenaltyAndComfortReward',
+                                     'attributes': {'band': 1.0, 'lower_exponent': 2.0, 'higher_exponent': 3.0, 'coefficients': [1.0, 2.0]}},
+                             steps=200, seed=4),
+}
+
+if __name__ == '__main__':
+    CityLearnEnv = import_reference()
+    todo = sys.argv[1:] or list(CASES)
+    for n in todo:
+        run_case(CityLearnEnv, n, **CASES[n])
