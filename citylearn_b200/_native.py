@@ -1,0 +1,170 @@
+"""ctypes binding of `libcitylearn_b200.so` (C ABI in `include/citylearn_b200.h`).
+
+The CUDA library is the only compute path of this package: if it is missing or cannot be loaded this
+module raises - there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from pathlib import Path
+
+import numpy as np
+
+from . import schema as S
+
+_LIB_NAME = 'libcitylearn_b200.so'
+_lib = None
+
+
+class NativeLibraryError(RuntimeError):
+    pass
+
+
+class DistrictDesc(ctypes.Structure):
+    _fields_ = [
+        ('abi_version', ctypes.c_int32), ('n_buildings', ctypes.c_int32), ('n_envs', ctypes.c_int32),
+        ('n_rows', ctypes.c_int32), ('n_cols', ctypes.c_int32), ('action_dim', ctypes.c_int32),
+        ('obs_dim', ctypes.c_int32), ('central_agent', ctypes.c_int32), ('reward_id', ctypes.c_int32),
+        ('precision', ctypes.c_int32), ('stale_observations', ctypes.c_int32), ('lstm_weight_count', ctypes.c_int32),
+        ('reward_params', ctypes.c_double * 8),
+        ('table', ctypes.c_void_p), ('params', ctypes.c_void_p), ('iparams', ctypes.c_void_p),
+        ('obs_desc', ctypes.c_void_p), ('lstm_weights', ctypes.c_void_p),
+    ]
+
+
+ABI_VERSION = 1
+PRECISION = {'fp32': 0, 'fp64': 1}
+
+
+def library_path() -> Path:
+    return Path(__file__).resolve().parent / _LIB_NAME
+
+
+def load():
+    """Load the CUDA library once; raises `NativeLibraryError` when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = library_path()
+    if not path.is_file():
+        raise NativeLibraryError(
+            f'{path} not found: the CUDA extension has not been built. Run `python -c "import __graft_entry__ as g; g.build()"` '
+            f'(or `make -C {path.parent / "csrc"}`) - citylearn_b200 has no CPU fallback.')
+    try:
+        lib = ctypes.CDLL(str(path))
+    except OSError as e:  # pragma: no cover
+        raise NativeLibraryError(f'cannot load {path}: {e}') from e
+    vp, i32, i64p = ctypes.c_void_p, ctypes.c_int32, ctypes.POINTER(ctypes.c_int64)
+    lib.cl_abi_version.restype = ctypes.c_int
+    lib.cl_last_error.restype = ctypes.c_char_p
+    lib.cl_create.argtypes = [ctypes.POINTER(DistrictDesc), ctypes.POINTER(vp)]
+    lib.cl_destroy.argtypes = [vp]
+    lib.cl_set_outage.argtypes = [vp, vp, i32, vp]
+    lib.cl_reset.argtypes = [vp, vp, i32, i32, vp, vp]
+    lib.cl_step.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+    lib.cl_rollout.argtypes = [vp, i32, vp, vp, vp, vp, vp]
+    lib.cl_time_step.argtypes = [vp, ctypes.POINTER(ctypes.c_int32)]
+    lib.cl_state_size.argtypes = [vp, ctypes.POINTER(ctypes.c_size_t)]
+    lib.cl_get_state.argtypes = [vp, vp, vp]
+    lib.cl_set_state.argtypes = [vp, vp, i32, vp]
+    lib.cl_launch_count.argtypes = [vp, i64p]
+    for name in ('cl_create', 'cl_destroy', 'cl_set_outage', 'cl_reset', 'cl_step', 'cl_rollout', 'cl_time_step',
+                 'cl_state_size', 'cl_get_state', 'cl_set_state', 'cl_launch_count'):
+        getattr(lib, name).restype = ctypes.c_int
+    if lib.cl_abi_version() != ABI_VERSION:
+        raise NativeLibraryError(f'{path}: ABI version {lib.cl_abi_version()} != {ABI_VERSION}; rebuild the extension')
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = ''):
+    if rc != 0:
+        msg = load().cl_last_error().decode(errors='replace')
+        exc = {1: ValueError, 3: NotImplementedError}.get(rc, RuntimeError)
+        raise exc(f'{what}: {msg}' if what else msg)
+
+
+class Handle:
+    """Owns one `cl_env*`."""
+
+    def __init__(self, spec: S.DistrictSpec, num_envs: int, obs_desc: np.ndarray, central_agent: bool, reward_id: int,
+                 reward_params, precision: str = 'fp64', stale_observations: bool = True):
+        self.lib = load()
+        # keep the host arrays alive for the duration of cl_create
+        table = np.ascontiguousarray(spec.table, dtype='float32')
+        params = np.ascontiguousarray(spec.params.T, dtype='float64')      # [NPARAM][B]
+        iparams = np.ascontiguousarray(spec.iparams.T, dtype='int32')      # [NIPARAM][B]
+        desc_arr = np.ascontiguousarray(obs_desc, dtype='int32')
+        weights = np.ascontiguousarray(spec.lstm_weights, dtype='float32')
+        d = DistrictDesc()
+        d.abi_version = ABI_VERSION
+        d.n_buildings = spec.n_buildings
+        d.n_envs = int(num_envs)
+        d.n_rows, d.n_cols = table.shape
+        d.action_dim = spec.action_dim
+        d.obs_dim = desc_arr.shape[0]
+        d.central_agent = int(bool(central_agent))
+        d.reward_id = int(reward_id)
+        d.precision = PRECISION[precision]
+        d.stale_observations = int(bool(stale_observations))
+        d.lstm_weight_count = int(weights.size)
+        rp = list(reward_params) + [0.0] * (8 - len(reward_params))
+        for i in range(8):
+            d.reward_params[i] = float(rp[i])
+        d.table = table.ctypes.data
+        d.params = params.ctypes.data
+        d.iparams = iparams.ctypes.data
+        d.obs_desc = desc_arr.ctypes.data
+        d.lstm_weights = weights.ctypes.data if weights.size else None
+        out = ctypes.c_void_p()
+        check(self.lib.cl_create(ctypes.byref(d), ctypes.byref(out)), 'cl_create')
+        self.ptr = out
+
+    def close(self):
+        if getattr(self, 'ptr', None):
+            self.lib.cl_destroy(self.ptr)
+            self.ptr = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_outage(self, signals, stream: int):
+        if signals is None:
+            check(self.lib.cl_set_outage(self.ptr, None, 0, stream), 'cl_set_outage')
+        else:
+            s = np.ascontiguousarray(signals, dtype='float32')
+            check(self.lib.cl_set_outage(self.ptr, s.ctypes.data, s.shape[1], stream), 'cl_set_outage')
+
+    def reset(self, start_ptr, uniform_start: int, episode_time_steps: int, obs_ptr, stream: int):
+        check(self.lib.cl_reset(self.ptr, start_ptr, int(uniform_start), int(episode_time_steps), obs_ptr, stream), 'cl_reset')
+
+    def step(self, actions_ptr, obs_ptr, reward_ptr, district_ptr, trace_ptr, stream: int):
+        check(self.lib.cl_step(self.ptr, actions_ptr, obs_ptr, reward_ptr, district_ptr, trace_ptr, stream), 'cl_step')
+
+    def rollout(self, n_steps: int, actions_ptr, obs_ptr, reward_ptr, district_ptr, stream: int):
+        check(self.lib.cl_rollout(self.ptr, int(n_steps), actions_ptr, obs_ptr, reward_ptr, district_ptr, stream), 'cl_rollout')
+
+    def time_step(self) -> int:
+        t = ctypes.c_int32()
+        check(self.lib.cl_time_step(self.ptr, ctypes.byref(t)))
+        return t.value
+
+    def state_size(self) -> int:
+        n = ctypes.c_size_t()
+        check(self.lib.cl_state_size(self.ptr, ctypes.byref(n)))
+        return n.value
+
+    def get_state(self, dst_ptr, stream: int):
+        check(self.lib.cl_get_state(self.ptr, dst_ptr, stream), 'cl_get_state')
+
+    def set_state(self, src_ptr, time_step: int, stream: int):
+        check(self.lib.cl_set_state(self.ptr, src_ptr, int(time_step), stream), 'cl_set_state')
+
+    def launch_count(self) -> int:
+        n = ctypes.c_int64()
+        check(self.lib.cl_launch_count(self.ptr, ctypes.byref(n)))
+        return n.value

@@ -1,0 +1,818 @@
+// citylearn_b200.cu - sm_100a kernels + C ABI of the CityLearn step path (see include/citylearn_b200.h).
+//
+// Data layout in HBM (all per cl_env handle, i.e. per GPU shard of E envs):
+//   table    float  [n_rows][Wp]      one row per dataset time step, Wp = W rounded up to 4 floats (16 B) so that the
+//                                     rows of step t and t+1 are ONE contiguous, 16B-aligned span -> a single TMA bulk copy
+//   params   float / double [CL_NPARAM][B]   parameter-major so that the B buildings of a warp read consecutive words
+//   iparams  int32  [CL_NIPARAM][B]
+//   obs_desc int4   [L]
+//   outage   float  [B][T]            power-outage signal of the running episode
+//   start    int32  [E]               table row of time step 0 of every env
+//   state    float  [6][E*B]  (+ double [2][E*B] in CL_PRECISION_FP64)   unit index u = e * B + b (building fastest)
+//
+// Thread mapping: one thread per unit; a block owns `envs_per_block` consecutive envs x all B buildings, so its slice of
+// actions [E][A], rewards [E][B], state [.][E*B] and observations [E][L] is one contiguous range each (coalesced), and the
+// district sums of an env never leave the block (shared memory, summed in building order like the reference's sum()).
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "unit_physics.cuh"
+
+namespace cl {
+
+// ------------------------------------------------------------------------------------------------------------------
+// device-side district description (passed by value to kernels)
+// ------------------------------------------------------------------------------------------------------------------
+struct Dev {
+    int B, E, U, n_rows, W, Wp, A, L, T;
+    int central, reward_id, stale, envs_per_block, uniform_start, start0, has_outage, any_dynamics;
+    float rp[8];
+    const float* table;
+    const float* pf;       // [NPARAM][B]
+    const double* pd;      // [NPARAM][B]
+    const int32_t* ip;     // [NIPARAM][B]
+    const int4* desc;      // [L]
+    const float* outage;   // [B][T] or nullptr
+    const int32_t* start;  // [E]
+    float* st;             // [6][U]
+    double* dst;           // [2][U] (fp64 mode)
+};
+
+enum { ST_SOC_B = 0, ST_CAP_DEG = 1, ST_EFF_B = 2, ST_SOC_CS = 3, ST_SOC_HS = 4, ST_SOC_DS = 5, ST_N = 6 };
+
+template <typename R> struct PSel;
+template <> struct PSel<float> { static __device__ __forceinline__ const float* p(const Dev& d) { return d.pf; } };
+template <> struct PSel<double> { static __device__ __forceinline__ const double* p(const Dev& d) { return d.pd; } };
+
+template <typename R, bool THERMAL>
+__device__ __forceinline__ void load_params(const Dev& d, int b, BuildingParams<R>& p) {
+    const auto* P = PSel<R>::p(d);
+    const int B = d.B;
+#define LD(k) ((R)__ldg(P + (k) * B + b))
+    p.bat_capacity = LD(CL_P_BAT_CAPACITY); p.bat_pnom = LD(CL_P_BAT_NOMINAL_POWER); p.bat_loss = LD(CL_P_BAT_LOSS);
+    p.bat_clc = LD(CL_P_BAT_CLC); p.bat_dod = LD(CL_P_BAT_DOD);
+    p.ratio = LD(CL_P_TIME_STEP_RATIO); p.hours = LD(CL_P_HOURS_PER_STEP);
+    p.flags = __ldg(d.ip + CL_IP_FLAGS * B + b);
+    p.pe_n = __ldg(d.ip + CL_IP_PE_N * B + b);
+    p.cp_n = __ldg(d.ip + CL_IP_CP_N * B + b);
+    if (THERMAL) {
+        p.cd_pnom = LD(CL_P_CD_NOMINAL_POWER); p.cd_cop_num = LD(CL_P_CD_COP_NUM); p.cd_target = LD(CL_P_CD_TARGET);
+        p.hd_pnom = LD(CL_P_HD_NOMINAL_POWER); p.hd_cop_num = LD(CL_P_HD_COP_NUM); p.hd_target = LD(CL_P_HD_TARGET); p.hd_eff = LD(CL_P_HD_EFFICIENCY);
+        p.dd_pnom = LD(CL_P_DD_NOMINAL_POWER); p.dd_cop_num = LD(CL_P_DD_COP_NUM); p.dd_target = LD(CL_P_DD_TARGET); p.dd_eff = LD(CL_P_DD_EFFICIENCY);
+        p.cs.capacity = LD(CL_P_CS_CAPACITY); p.cs.efficiency = LD(CL_P_CS_EFFICIENCY); p.cs.loss = LD(CL_P_CS_LOSS);
+        p.cs.max_in = LD(CL_P_CS_MAX_IN); p.cs.max_out = LD(CL_P_CS_MAX_OUT);
+        p.cs.has_max_in = p.flags & CL_F_CS_HAS_MAX_IN; p.cs.has_max_out = p.flags & CL_F_CS_HAS_MAX_OUT;
+        p.hs.capacity = LD(CL_P_HS_CAPACITY); p.hs.efficiency = LD(CL_P_HS_EFFICIENCY); p.hs.loss = LD(CL_P_HS_LOSS);
+        p.hs.max_in = LD(CL_P_HS_MAX_IN); p.hs.max_out = LD(CL_P_HS_MAX_OUT);
+        p.hs.has_max_in = p.flags & CL_F_HS_HAS_MAX_IN; p.hs.has_max_out = p.flags & CL_F_HS_HAS_MAX_OUT;
+        p.ds.capacity = LD(CL_P_DS_CAPACITY); p.ds.efficiency = LD(CL_P_DS_EFFICIENCY); p.ds.loss = LD(CL_P_DS_LOSS);
+        p.ds.max_in = LD(CL_P_DS_MAX_IN); p.ds.max_out = LD(CL_P_DS_MAX_OUT);
+        p.ds.has_max_in = p.flags & CL_F_DS_HAS_MAX_IN; p.ds.has_max_out = p.flags & CL_F_DS_HAS_MAX_OUT;
+    }
+#undef LD
+}
+
+template <typename R, bool THERMAL>
+__device__ __forceinline__ void load_state(const Dev& d, int u, UnitState<R>& s) {
+    const int U = d.U;
+    s.soc_b = (R)d.st[ST_SOC_B * U + u];
+    if (sizeof(R) == 8) { s.cap_deg = (R)d.dst[u]; s.eff_b = (R)d.dst[U + u]; }
+    else { s.cap_deg = (R)d.st[ST_CAP_DEG * U + u]; s.eff_b = (R)d.st[ST_EFF_B * U + u]; }
+    if (THERMAL) { s.soc_cs = (R)d.st[ST_SOC_CS * U + u]; s.soc_hs = (R)d.st[ST_SOC_HS * U + u]; s.soc_ds = (R)d.st[ST_SOC_DS * U + u]; }
+    else { s.soc_cs = s.soc_hs = s.soc_ds = (R)0; }
+}
+
+template <typename R, bool THERMAL>
+__device__ __forceinline__ void store_state(const Dev& d, int u, const UnitState<R>& s) {
+    const int U = d.U;
+    d.st[ST_SOC_B * U + u] = (float)s.soc_b;
+    if (sizeof(R) == 8) { d.dst[u] = (double)s.cap_deg; d.dst[U + u] = (double)s.eff_b; }
+    else { d.st[ST_CAP_DEG * U + u] = (float)s.cap_deg; d.st[ST_EFF_B * U + u] = (float)s.eff_b; }
+    if (THERMAL) { d.st[ST_SOC_CS * U + u] = (float)s.soc_cs; d.st[ST_SOC_HS * U + u] = (float)s.soc_hs; d.st[ST_SOC_DS * U + u] = (float)s.soc_ds; }
+}
+
+// exogenous inputs of unit (e, b) at time step t; `row` points at the time row (shared or global memory)
+template <typename R, bool THERMAL>
+__device__ __forceinline__ void load_inputs(const Dev& d, const float* row, int b, int t, UnitInputs<R>& in) {
+    const int B = d.B;
+    const int32_t* ip = d.ip;
+    const auto* P = PSel<R>::p(d);
+#define COL(k) row[__ldg(ip + (k) * B + b)]
+    in.nsl = (R)COL(CL_IP_C_NSL);
+    const R pv = (R)__ldg(P + CL_P_PV_NOMINAL_POWER * B + b);
+    in.solar = -(pv * (R)COL(CL_IP_C_SOLAR) / (R)1000);            // building.py:2554, energy_model.py:488
+    in.price = (R)COL(CL_IP_C_PRICE);
+    in.carbon = (R)COL(CL_IP_C_CARBON);
+    if (THERMAL) {
+        in.dhw_demand = (R)COL(CL_IP_C_DHW_DEMAND); in.cooling_demand = (R)COL(CL_IP_C_COOLING_DEMAND);
+        in.heating_demand = (R)COL(CL_IP_C_HEATING_DEMAND); in.t_out = (R)COL(CL_IP_C_T_OUT);
+        in.hvac_mode = (int32_t)COL(CL_IP_C_HVAC_MODE);
+    } else {
+        in.dhw_demand = in.cooling_demand = in.heating_demand = (R)0; in.t_out = (R)0; in.hvac_mode = 0;
+    }
+#undef COL
+    const int flags = __ldg(ip + CL_IP_FLAGS * B + b);
+    in.outage = d.has_outage && (flags & CL_F_SIMULATE_OUTAGE) && __ldg(d.outage + b * d.T + t) > 0.f;
+    in.control_cooling_demand = false;
+    in.control_heating_demand = false;
+}
+
+template <typename R, bool THERMAL>
+__device__ __forceinline__ void load_actions(const Dev& d, const float* act_row, int b, UnitInputs<R>& in) {
+    const int B = d.B;
+    const int32_t* ip = d.ip;
+    auto slot = [&](int k) { return __ldg(ip + k * B + b); };
+    const int s_es = slot(CL_IP_A_ELECTRICAL_STORAGE);
+    in.a_es = s_es >= 0 ? (R)act_row[s_es] : (R)0;
+    in.a_cooling_device = in.a_heating_device = (R)NAN;
+    in.a_cs = in.a_hs = in.a_ds = (R)0;
+    if (THERMAL) {
+        const int s_cd = slot(CL_IP_A_COOLING_DEVICE), s_hd = slot(CL_IP_A_HEATING_DEVICE), s_coh = slot(CL_IP_A_COOLING_OR_HEATING_DEVICE);
+        if (s_cd >= 0) in.a_cooling_device = (R)act_row[s_cd];
+        if (s_hd >= 0) in.a_heating_device = (R)act_row[s_hd];
+        if (s_coh >= 0) {   // building.py:1550-1553
+            const R v = (R)act_row[s_coh];
+            in.a_cooling_device = fabs(rmin(v, (R)0));
+            in.a_heating_device = fabs(rmax(v, (R)0));
+        }
+        const int s_cs = slot(CL_IP_A_COOLING_STORAGE), s_hs = slot(CL_IP_A_HEATING_STORAGE), s_ds = slot(CL_IP_A_DHW_STORAGE);
+        if (s_cs >= 0) in.a_cs = (R)act_row[s_cs];
+        if (s_hs >= 0) in.a_hs = (R)act_row[s_hs];
+        if (s_ds >= 0) in.a_ds = (R)act_row[s_ds];
+    }
+}
+
+// dyn values of a unit (cl_dyn order) from a step / time-0 result
+template <typename R>
+__device__ __forceinline__ void fill_dyn(const BuildingParams<R>& p, const UnitState<R>& s, const UnitResult<R>& o, R t_in, float* dyn) {
+    using N = Num<R>;
+    dyn[CL_DYN_ELECTRICAL_STORAGE_SOC] = (float)s.soc_b;
+    dyn[CL_DYN_COOLING_STORAGE_SOC] = (float)s.soc_cs;
+    dyn[CL_DYN_HEATING_STORAGE_SOC] = (float)s.soc_hs;
+    dyn[CL_DYN_DHW_STORAGE_SOC] = (float)s.soc_ds;
+    dyn[CL_DYN_NET_ELECTRICITY_CONSUMPTION] = (float)o.net;
+    dyn[CL_DYN_COOLING_DEMAND] = (float)(o.e_from_cool + fabs(rmin(o.eb_cs, (R)0)));
+    dyn[CL_DYN_HEATING_DEMAND] = (float)(o.e_from_heat + fabs(rmin(o.eb_hs, (R)0)));
+    dyn[CL_DYN_DHW_DEMAND] = (float)(o.e_from_dhw + fabs(rmin(o.eb_ds, (R)0)));
+    dyn[CL_DYN_COOLING_ELECTRICITY_CONSUMPTION] = (float)(o.ec_cool * p.ratio);
+    dyn[CL_DYN_HEATING_ELECTRICITY_CONSUMPTION] = (float)(o.ec_heat * p.ratio);
+    dyn[CL_DYN_DHW_ELECTRICITY_CONSUMPTION] = (float)(o.ec_dhw * p.ratio);
+    dyn[CL_DYN_COOLING_STORAGE_ELECTRICITY_CONSUMPTION] = (float)N::div32(o.eb_cs, o.eff_cool);
+    dyn[CL_DYN_HEATING_STORAGE_ELECTRICITY_CONSUMPTION] = (float)N::div32(o.eb_hs, o.eff_heat);
+    dyn[CL_DYN_DHW_STORAGE_ELECTRICITY_CONSUMPTION] = (float)N::div32(o.eb_ds, o.eff_dhw);
+    dyn[CL_DYN_ELECTRICAL_STORAGE_ELECTRICITY_CONSUMPTION] = (float)(o.ec_bat * p.ratio);
+    dyn[CL_DYN_INDOOR_DRY_BULB_TEMPERATURE] = (float)t_in;
+    dyn[CL_DYN_NON_SHIFTABLE_LOAD_ELECTRICITY_CONSUMPTION] = (float)(o.ec_nsl * p.ratio);
+    dyn[CL_DYN_ELECTRICAL_STORAGE_ENERGY_BALANCE] = (float)o.eb_bat;
+    dyn[CL_DYN_COOLING_STORAGE_ENERGY_BALANCE] = (float)o.eb_cs;
+    dyn[CL_DYN_HEATING_STORAGE_ENERGY_BALANCE] = (float)o.eb_hs;
+    dyn[CL_DYN_DHW_STORAGE_ENERGY_BALANCE] = (float)o.eb_ds;
+    dyn[CL_DYN_NET_ELECTRICITY_CONSUMPTION_COST] = (float)o.cost;
+    dyn[CL_DYN_NET_ELECTRICITY_CONSUMPTION_EMISSION] = (float)o.emission;
+    dyn[CL_DYN_ELECTRICAL_STORAGE_DEGRADED_CAPACITY] = (float)s.cap_deg;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// reward functions (citylearn/reward_function.py); observation values are np.float32 there -> float arithmetic,
+// except MARL which converts to float64 (np.array(..., dtype=float)).
+// ------------------------------------------------------------------------------------------------------------------
+struct RewardIn {
+    float net, soc_b, soc_cs, soc_hs, soc_ds, cool_dem, heat_dem, t_in, cool_sp, heat_sp, band_series;
+    float cap_b, cap_cs, cap_hs, cap_ds;
+    int hvac_mode;
+    float district_net;
+};
+
+__device__ __forceinline__ float comfort_reward(const RewardIn& r, const float* rp) {
+    const float band = isnan(rp[0]) ? r.band_series : rp[0];
+    const float lo_e = rp[1], hi_e = rp[2];
+    const bool heating = r.heat_dem > r.cool_dem;
+    const float T = r.t_in;
+    if (r.hvac_mode == 1 || r.hvac_mode == 2) {
+        const float sp = r.hvac_mode == 1 ? r.cool_sp : r.heat_sp;
+        const float lower = sp - band, upper = sp + band;
+        const float delta = fabsf(T - sp);
+        if (T < lower) return -powf(delta, r.hvac_mode == 2 ? lo_e : hi_e);
+        if (lower <= T && T < sp) return heating ? 0.f : -delta;
+        if (sp <= T && T <= upper) return heating ? -delta : 0.f;
+        return -powf(delta, heating ? hi_e : lo_e);
+    }
+    const float lower = r.heat_sp - band, upper = r.cool_sp + band;
+    const float cd = T - r.cool_sp, hd = T - r.heat_sp;
+    if (T < lower) return -powf(fabsf(hd), !heating ? hi_e : lo_e);
+    if (lower <= T && T < r.heat_sp) return -fabsf(hd);
+    if (r.heat_sp <= T && T <= r.cool_sp) return 0.f;
+    if (r.cool_sp < T && T < upper) return -fabsf(cd);
+    return -powf(fabsf(cd), heating ? hi_e : lo_e);
+}
+
+__device__ __forceinline__ float sgnf(float x) { return x > 0.f ? 1.f : (x < 0.f ? -1.f : (x == 0.f ? 0.f : x)); }
+
+__device__ __forceinline__ float solar_penalty_reward(const RewardIn& r) {
+    const float e = r.net;
+    float reward = 0.f;
+    if (r.cap_cs > (float)kEps) reward += -(1.0f + sgnf(e) * r.soc_cs) * fabsf(e);
+    if (r.cap_hs > (float)kEps) reward += -(1.0f + sgnf(e) * r.soc_hs) * fabsf(e);
+    if (r.cap_ds > (float)kEps) reward += -(1.0f + sgnf(e) * r.soc_ds) * fabsf(e);
+    if (r.cap_b > (float)kEps) reward += -(1.0f + sgnf(e) * r.soc_b) * fabsf(e);
+    return reward;
+}
+
+__device__ __forceinline__ float unit_reward(int reward_id, const float* rp, const RewardIn& r) {
+    switch (reward_id) {
+        case CL_REWARD_DEFAULT: {
+            const float m = fmaxf(r.net, 0.f);
+            return rp[0] == 1.0f ? -m : -powf(m, rp[0]);
+        }
+        case CL_REWARD_MARL: {
+            const double be = -(double)r.net;
+            const double sg = be > 0 ? 1.0 : (be < 0 ? -1.0 : 0.0);
+            return (float)(sg * 0.01 * (be * be) * fmax(0.0, (double)r.district_net));
+        }
+        case CL_REWARD_INDEPENDENT_SAC: return fminf(-r.net, 0.f);   // v * -1 ** 3 == -v (reward_function.py:161)
+        case CL_REWARD_SOLAR_PENALTY: return solar_penalty_reward(r);
+        case CL_REWARD_COMFORT: return comfort_reward(r, rp);
+        case CL_REWARD_SOLAR_PENALTY_AND_COMFORT:
+            return (float)((double)solar_penalty_reward(r) * (double)rp[3] + (double)comfort_reward(r, rp) * (double)rp[4]);
+        default: return 0.f;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// TMA (cp.async.bulk) staging of the time rows t and t+1 into shared memory
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(phase)
+        : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// observation writer: rows of the block's envs are one contiguous span obs[e0*L .. (e0+n)*L)
+// ------------------------------------------------------------------------------------------------------------------
+// general path: any descriptor kind, per-env start rows, DYN values from shared memory (or zero)
+__device__ __forceinline__ void write_obs_general(const Dev& d, float* obs, int e0, int n_env, int t_obs,
+                                                   const float* dynbuf /* [n_env*B][CL_NDYN] or nullptr */) {
+    const int L = d.L, nt = blockDim.x;
+    const int total = n_env * L;
+    int j = threadIdx.x;
+    int e_l = j / L, k = j - e_l * L;
+    const int de = nt / L, dk = nt - de * L;
+    for (; j < total; j += nt) {
+        const int4 ds = __ldg(d.desc + k);
+        float v;
+        if (ds.x == CL_OBS_TS) {
+            const int row = __ldg(d.start + e0 + e_l) + t_obs;
+            v = __ldg(d.table + (size_t)row * d.Wp + ds.y);
+        } else if (ds.x == CL_OBS_DYN) {
+            v = dynbuf ? dynbuf[(e_l * d.B + ds.w) * CL_NDYN + ds.y] : 0.f;
+        } else {
+            v = d.has_outage ? __ldg(d.outage + ds.w * d.T + t_obs) : 0.f;
+        }
+        obs[(size_t)e0 * L + j] = v;
+        e_l += de; k += dk;
+        if (k >= L) { k -= L; e_l += 1; }
+    }
+}
+
+// fast path (uniform start rows, no DYN values needed): every env row equals the template row built once per block
+__device__ __forceinline__ void build_obs_template(const Dev& d, const float* row_next, int t_obs, float* tmpl) {
+    for (int k = threadIdx.x; k < d.L; k += blockDim.x) {
+        const int4 ds = __ldg(d.desc + k);
+        float v;
+        if (ds.x == CL_OBS_TS) v = row_next[ds.y];
+        else if (ds.x == CL_OBS_DYN) v = 0.f;
+        else v = d.has_outage ? __ldg(d.outage + ds.w * d.T + t_obs) : 0.f;
+        tmpl[k] = v;
+    }
+}
+
+__device__ __forceinline__ void write_obs_template(const Dev& d, float* obs, int e0, int n_env, const float* tmpl) {
+    const int L = d.L, nt = blockDim.x;
+    float* out = obs + (size_t)e0 * L;
+    if ((L & 3) == 0) {   // 16-byte vector stores: a row never straddles a float4 because L % 4 == 0
+        const int L4 = L >> 2, total4 = n_env * L4;
+        const float4* t4 = reinterpret_cast<const float4*>(tmpl);
+        float4* o4 = reinterpret_cast<float4*>(out);
+        int j = threadIdx.x;
+        int k = j % L4;
+        const int dk = nt % L4;
+        for (; j < total4; j += nt) {
+            __stcs(o4 + j, t4[k]);   // streaming store: written once, read by the consumer later
+            k += dk;
+            if (k >= L4) k -= L4;
+        }
+    } else {
+        const int total = n_env * L;
+        int j = threadIdx.x;
+        int k = j % L;
+        const int dk = nt % L;
+        for (; j < total; j += nt) {
+            __stcs(out + j, tmpl[k]);
+            k += dk;
+            if (k >= L) k -= L;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// shared memory carve-up (dynamic): [mbarrier 16B][rows 2*Wp][tmpl Lp][red 4*nthreads][dsum 4*epb][dynbuf (optional)]
+// ------------------------------------------------------------------------------------------------------------------
+struct Smem {
+    uint64_t* bar;
+    float* rows;
+    float* tmpl;
+    float* red;     // [3][nthreads] net, cost, emission (+ [nthreads] reward when central)
+    float* dsum;    // [epb][4]
+    float* dynbuf;  // [nthreads][CL_NDYN]
+};
+__device__ __forceinline__ Smem carve(const Dev& d, unsigned char* base, int nthreads) {
+    Smem s;
+    s.bar = reinterpret_cast<uint64_t*>(base);
+    float* f = reinterpret_cast<float*>(base + 16);
+    s.rows = f; f += 2 * d.Wp;
+    s.tmpl = f; f += (d.L + 3) & ~3;
+    s.red = f; f += 4 * nthreads;
+    s.dsum = f; f += 4 * d.envs_per_block;
+    s.dynbuf = f;
+    return s;
+}
+static size_t smem_bytes(const Dev& d, int nthreads, bool with_dyn) {
+    size_t n = 16 + sizeof(float) * (2 * (size_t)d.Wp + ((d.L + 3) & ~3) + 4 * (size_t)nthreads + 4 * (size_t)d.envs_per_block);
+    if (with_dyn) n += sizeof(float) * (size_t)nthreads * CL_NDYN;
+    return n;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// step kernel
+// ------------------------------------------------------------------------------------------------------------------
+template <typename R, bool THERMAL, int MAXT>
+__global__ void __launch_bounds__(MAXT) step_kernel(Dev d, int t, const float* __restrict__ actions, float* __restrict__ obs,
+                                                     float* __restrict__ reward, float* __restrict__ district, float* __restrict__ trace) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int nt = blockDim.x, tid = threadIdx.x;
+    Smem sm = carve(d, smem_raw, nt);
+    const int B = d.B, epb = d.envs_per_block;
+    const int e0 = blockIdx.x * epb;
+    const int n_env = min(epb, d.E - e0);
+    const int n_units = n_env * B;
+    const bool active = tid < n_units;
+    const int e_l = tid / B, b = tid - e_l * B;
+    const int e = e0 + e_l, u = e * B + b;
+    const bool want_dyn = (!d.stale && obs != nullptr);
+
+    // stage the time rows of t and t+1 (contiguous) with one TMA bulk copy
+    if (d.uniform_start) {
+        if (tid == 0) {
+            mbar_init(sm.bar, 1);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            const uint32_t bytes = 2u * d.Wp * sizeof(float);
+            mbar_expect_tx(sm.bar, bytes);
+            tma_load_1d(sm.rows, d.table + (size_t)(d.start0 + t) * d.Wp, bytes, sm.bar);
+        }
+        __syncthreads();
+        mbar_wait(sm.bar, 0);
+    }
+
+    UnitResult<R> o;
+    UnitState<R> s;
+    BuildingParams<R> p;
+    UnitInputs<R> in;
+    float t_in = 0.f;
+    if (active) {
+        load_params<R, THERMAL>(d, b, p);
+        const float* row = d.uniform_start ? sm.rows : d.table + (size_t)(__ldg(d.start + e) + t) * d.Wp;
+        load_inputs<R, THERMAL>(d, row, b, t, in);
+        load_actions<R, THERMAL>(d, actions + (size_t)e * d.A, b, in);
+        load_state<R, THERMAL>(d, u, s);
+        const auto* curves = PSel<R>::p(d) + CL_P_PE_X0 * B + b;
+        unit_step<R, THERMAL>(p, curves, B, t, in, s, o);
+        store_state<R, THERMAL>(d, u, s);
+        t_in = row[__ldg(d.ip + CL_IP_C_T_IN * B + b)];
+        sm.red[tid] = (float)o.net;
+        sm.red[nt + tid] = (float)o.cost;
+        sm.red[2 * nt + tid] = (float)o.emission;
+        if (trace != nullptr || want_dyn) {
+            float dyn[CL_NDYN];
+            fill_dyn<R>(p, s, o, (R)t_in, dyn);
+            if (trace != nullptr) {
+#pragma unroll
+                for (int k = 0; k < CL_NDYN; ++k) trace[(size_t)u * CL_NDYN + k] = dyn[k];
+            }
+            if (want_dyn) {
+#pragma unroll
+                for (int k = 0; k < CL_NDYN; ++k) sm.dynbuf[tid * CL_NDYN + k] = dyn[k];
+            }
+        }
+    }
+    __syncthreads();
+    // district sums in building order, like the reference's sum() over buildings (citylearn.py:1908-1918)
+    if (tid < n_env) {
+        float sn = 0.f, sc = 0.f, se = 0.f;
+        for (int k = 0; k < B; ++k) {
+            sn += sm.red[tid * B + k];
+            sc += sm.red[nt + tid * B + k];
+            se += sm.red[2 * nt + tid * B + k];
+        }
+        sm.dsum[tid * 4 + 0] = sn; sm.dsum[tid * 4 + 1] = sc; sm.dsum[tid * 4 + 2] = se;
+        if (district != nullptr) {
+            district[(size_t)(e0 + tid) * 3 + 0] = sn;
+            district[(size_t)(e0 + tid) * 3 + 1] = sc;
+            district[(size_t)(e0 + tid) * 3 + 2] = se;
+        }
+    }
+    __syncthreads();
+    if (reward != nullptr && d.reward_id >= 0) {
+        float r = 0.f;
+        if (active) {
+            RewardIn ri;
+            ri.net = (float)o.net; ri.district_net = sm.dsum[e_l * 4];
+            ri.soc_b = (float)s.soc_b; ri.soc_cs = (float)s.soc_cs; ri.soc_hs = (float)s.soc_hs; ri.soc_ds = (float)s.soc_ds;
+            ri.cap_b = (float)p.bat_capacity;
+            if (THERMAL) {
+                ri.cap_cs = (float)p.cs.capacity; ri.cap_hs = (float)p.hs.capacity; ri.cap_ds = (float)p.ds.capacity;
+                ri.cool_dem = (float)(o.e_from_cool + fabs(rmin(o.eb_cs, (R)0)));
+                ri.heat_dem = (float)(o.e_from_heat + fabs(rmin(o.eb_hs, (R)0)));
+            } else { ri.cap_cs = ri.cap_hs = ri.cap_ds = 0.f; ri.cool_dem = ri.heat_dem = 0.f; }
+            ri.hvac_mode = in.hvac_mode;
+            ri.t_in = t_in;
+            if (d.reward_id == CL_REWARD_COMFORT || d.reward_id == CL_REWARD_SOLAR_PENALTY_AND_COMFORT) {
+                const float* row = d.uniform_start ? sm.rows : d.table + (size_t)(__ldg(d.start + e) + t) * d.Wp;
+                ri.cool_sp = row[__ldg(d.ip + CL_IP_C_COOL_SP * B + b)];
+                ri.heat_sp = row[__ldg(d.ip + CL_IP_C_HEAT_SP * B + b)];
+                ri.band_series = row[__ldg(d.ip + CL_IP_C_COMFORT_BAND * B + b)];
+                ri.hvac_mode = (int)row[__ldg(d.ip + CL_IP_C_HVAC_MODE * B + b)];
+            } else { ri.cool_sp = ri.heat_sp = ri.band_series = 0.f; }
+            r = unit_reward(d.reward_id, d.rp, ri);
+        }
+        if (d.central) {
+            sm.red[3 * nt + tid] = r;
+            __syncthreads();
+            if (tid < n_env) {
+                float sr = 0.f;
+                if (d.reward_id == CL_REWARD_MARL || d.reward_id == CL_REWARD_SOLAR_PENALTY_AND_COMFORT) {
+                    double acc = 0.0;   // these rewards are float64 in the reference
+                    for (int k = 0; k < B; ++k) acc += (double)sm.red[3 * nt + tid * B + k];
+                    sr = (float)acc;
+                } else {
+                    for (int k = 0; k < B; ++k) sr += sm.red[3 * nt + tid * B + k];
+                }
+                reward[e0 + tid] = sr;
+            }
+        } else if (active) {
+            reward[u] = r;
+        }
+    }
+    // observations at t + 1
+    if (obs != nullptr) {
+        if (d.uniform_start && d.stale) {
+            build_obs_template(d, sm.rows + d.Wp, t + 1, sm.tmpl);
+            __syncthreads();
+            write_obs_template(d, obs, e0, n_env, sm.tmpl);
+        } else {
+            write_obs_general(d, obs, e0, n_env, t + 1, want_dyn ? sm.dynbuf : nullptr);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// reset kernel: state <- initial values; obs <- observation at t = 0 (citylearn.py:1829-1886, building.py:2526-2564)
+// ------------------------------------------------------------------------------------------------------------------
+template <typename R, bool THERMAL, int MAXT>
+__global__ void __launch_bounds__(MAXT) reset_kernel(Dev d, float* __restrict__ obs) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int nt = blockDim.x, tid = threadIdx.x;
+    Smem sm = carve(d, smem_raw, nt);
+    const int B = d.B, epb = d.envs_per_block;
+    const int e0 = blockIdx.x * epb;
+    const int n_env = min(epb, d.E - e0);
+    const int n_units = n_env * B;
+    const int e_l = tid / B, b = tid - e_l * B;
+    const int e = e0 + e_l, u = e * B + b;
+    if (tid < n_units) {
+        const auto* P = PSel<R>::p(d);
+        BuildingParams<R> p;
+        load_params<R, THERMAL>(d, b, p);
+        UnitState<R> s;
+        s.soc_b = Num<R>::r32((R)__ldg(P + CL_P_BAT_INITIAL_SOC * B + b));
+        s.cap_deg = p.bat_capacity;
+        s.eff_b = (R)__ldg(P + CL_P_BAT_EFFICIENCY0 * B + b);
+        s.soc_cs = Num<R>::r32((R)__ldg(P + CL_P_CS_INITIAL_SOC * B + b));
+        s.soc_hs = Num<R>::r32((R)__ldg(P + CL_P_HS_INITIAL_SOC * B + b));
+        s.soc_ds = Num<R>::r32((R)__ldg(P + CL_P_DS_INITIAL_SOC * B + b));
+        store_state<R, true>(d, u, s);
+        if (obs != nullptr) {
+            const float* row = d.table + (size_t)__ldg(d.start + e) * d.Wp;
+            UnitInputs<R> in;
+            load_inputs<R, THERMAL>(d, row, b, 0, in);
+            UnitResult<R> o;
+            unit_time0<R, THERMAL>(p, in, o);
+            const float t_in = row[__ldg(d.ip + CL_IP_C_T_IN * B + b)];
+            fill_dyn<R>(p, s, o, (R)t_in, sm.dynbuf + tid * CL_NDYN);
+        }
+    }
+    if (obs != nullptr) {
+        __syncthreads();
+        write_obs_general(d, obs, e0, n_env, 0, sm.dynbuf);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CUDA_TRY(x)                                                                                        \
+    do {                                                                                                   \
+        cudaError_t e_ = (x);                                                                              \
+        if (e_ != cudaSuccess) return fail(CL_ERR_CUDA, std::string(#x) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+
+}  // namespace cl
+
+struct cl_env {
+    cl::Dev d;
+    int precision = 0;
+    bool thermal = false;
+    int t = -1;              // -1: not reset
+    int T = 0;
+    int threads = 0, blocks = 0;
+    int64_t launches = 0;
+    std::vector<void*> allocs;
+    float* outage_dev = nullptr;
+    int outage_T = 0;
+    size_t st_floats = 0, dst_doubles = 0;
+};
+
+using namespace cl;
+
+template <typename T> static int dev_copy(cl_env* env, const T* host, size_t n, T** out) {
+    void* p = nullptr;
+    CUDA_TRY(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)));
+    env->allocs.push_back(p);
+    if (n) CUDA_TRY(cudaMemcpy(p, host, n * sizeof(T), cudaMemcpyHostToDevice));
+    *out = static_cast<T*>(p);
+    return CL_OK;
+}
+
+extern "C" int cl_abi_version(void) { return CL_ABI_VERSION; }
+extern "C" const char* cl_last_error(void) { return g_err.c_str(); }
+
+extern "C" int cl_create(const cl_district_desc* desc, cl_env** out) {
+    if (!desc || !out) return fail(CL_ERR_INVALID, "cl_create: null argument");
+    if (desc->abi_version != CL_ABI_VERSION) return fail(CL_ERR_INVALID, "cl_create: ABI version mismatch");
+    if (desc->n_buildings < 1 || desc->n_envs < 1 || desc->n_rows < 2 || desc->n_cols < 1 || desc->obs_dim < 1)
+        return fail(CL_ERR_INVALID, "cl_create: empty district");
+    if (desc->n_buildings > 1024) return fail(CL_ERR_UNSUPPORTED, "cl_create: more than 1024 buildings per district not supported yet");
+    if (!desc->table || !desc->params || !desc->iparams || !desc->obs_desc) return fail(CL_ERR_INVALID, "cl_create: null table/params");
+    if (desc->precision != CL_PRECISION_FP32 && desc->precision != CL_PRECISION_FP64) return fail(CL_ERR_INVALID, "cl_create: bad precision");
+    cl_env* env = new (std::nothrow) cl_env();
+    if (!env) return fail(CL_ERR_INVALID, "cl_create: out of host memory");
+    Dev& d = env->d;
+    std::memset(&d, 0, sizeof(d));
+    const int B = desc->n_buildings;
+    d.B = B; d.E = desc->n_envs; d.U = d.B * d.E; d.n_rows = desc->n_rows; d.W = desc->n_cols; d.Wp = (desc->n_cols + 3) & ~3;
+    d.A = desc->action_dim; d.L = desc->obs_dim; d.central = desc->central_agent; d.reward_id = desc->reward_id;
+    d.stale = desc->stale_observations;
+    for (int i = 0; i < 8; ++i) d.rp[i] = (float)desc->reward_params[i];
+    env->precision = desc->precision;
+    int any_thermal = 0, any_dyn = 0;
+    for (int b = 0; b < B; ++b) {
+        const int f = desc->iparams[CL_IP_FLAGS * B + b];
+        any_thermal |= (f & CL_F_HAS_THERMAL);
+        any_dyn |= (f & CL_F_DYNAMICS);
+    }
+    env->thermal = any_thermal != 0;
+    d.any_dynamics = any_dyn != 0;
+    if (any_dyn) { delete env; return fail(CL_ERR_UNSUPPORTED, "cl_create: LSTM dynamics buildings are not supported by this build"); }
+    // padded table
+    {
+        std::vector<float> padded((size_t)d.n_rows * d.Wp, 0.f);
+        for (int r = 0; r < d.n_rows; ++r) std::memcpy(&padded[(size_t)r * d.Wp], desc->table + (size_t)r * d.W, sizeof(float) * d.W);
+        float* p = nullptr;
+        int rc = dev_copy(env, padded.data(), padded.size(), &p);
+        if (rc) { cl_destroy(env); return rc; }
+        d.table = p;
+    }
+    {
+        std::vector<float> pf((size_t)CL_NPARAM * B);
+        for (size_t i = 0; i < pf.size(); ++i) pf[i] = (float)desc->params[i];
+        float* p = nullptr; double* q = nullptr; int32_t* ip = nullptr; int4* ds = nullptr;
+        int rc = dev_copy(env, pf.data(), pf.size(), &p);
+        if (!rc) rc = dev_copy(env, desc->params, (size_t)CL_NPARAM * B, &q);
+        if (!rc) rc = dev_copy(env, desc->iparams, (size_t)CL_NIPARAM * B, &ip);
+        if (!rc) rc = dev_copy(env, reinterpret_cast<const int4*>(desc->obs_desc), (size_t)d.L, &ds);
+        if (rc) { cl_destroy(env); return rc; }
+        d.pf = p; d.pd = q; d.ip = ip; d.desc = ds;
+    }
+    {
+        void* p = nullptr;
+        env->st_floats = (size_t)ST_N * d.U;
+        if (cudaMalloc(&p, env->st_floats * sizeof(float)) != cudaSuccess) { cl_destroy(env); return fail(CL_ERR_CUDA, "cl_create: state allocation failed"); }
+        env->allocs.push_back(p); d.st = static_cast<float*>(p);
+        cudaMemset(p, 0, env->st_floats * sizeof(float));
+        env->dst_doubles = env->precision == CL_PRECISION_FP64 ? (size_t)2 * d.U : 0;
+        if (env->dst_doubles) {
+            if (cudaMalloc(&p, env->dst_doubles * sizeof(double)) != cudaSuccess) { cl_destroy(env); return fail(CL_ERR_CUDA, "cl_create: state allocation failed"); }
+            env->allocs.push_back(p); d.dst = static_cast<double*>(p);
+            cudaMemset(p, 0, env->dst_doubles * sizeof(double));
+        }
+        if (cudaMalloc(&p, (size_t)d.E * sizeof(int32_t)) != cudaSuccess) { cl_destroy(env); return fail(CL_ERR_CUDA, "cl_create: start allocation failed"); }
+        env->allocs.push_back(p); d.start = static_cast<int32_t*>(p);
+    }
+    // launch geometry: as many whole envs per block as fit ~256 threads
+    int epb = 256 / B;
+    if (epb < 1) epb = 1;
+    if (epb > d.E) epb = d.E;
+    d.envs_per_block = epb;
+    env->threads = ((epb * B + 31) / 32) * 32;
+    env->blocks = (d.E + epb - 1) / epb;
+    // opt in to large dynamic shared memory once (both kernels, all instantiations)
+    const size_t smem = smem_bytes(d, env->threads, true);
+    if (smem > 200 * 1024) { cl_destroy(env); return fail(CL_ERR_UNSUPPORTED, "cl_create: district too wide for the shared-memory staging"); }
+#define OPTIN(K) cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+#define OPTIN4(K, M) OPTIN((K<float, false, M>)); OPTIN((K<float, true, M>)); OPTIN((K<double, false, M>)); OPTIN((K<double, true, M>))
+    OPTIN4(step_kernel, 512); OPTIN4(step_kernel, 1024); OPTIN4(reset_kernel, 512); OPTIN4(reset_kernel, 1024);
+#undef OPTIN4
+#undef OPTIN
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { cl_destroy(env); return fail(CL_ERR_CUDA, std::string("cl_create: ") + cudaGetErrorString(e)); }
+    *out = env;
+    return CL_OK;
+}
+
+extern "C" int cl_destroy(cl_env* env) {
+    if (!env) return CL_OK;
+    for (void* p : env->allocs) cudaFree(p);
+    if (env->outage_dev) cudaFree(env->outage_dev);
+    delete env;
+    return CL_OK;
+}
+
+extern "C" int cl_set_outage(cl_env* env, const float* signals, int32_t episode_time_steps, cl_stream stream) {
+    if (!env) return fail(CL_ERR_INVALID, "cl_set_outage: null env");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (!signals) { env->d.has_outage = 0; env->d.outage = nullptr; return CL_OK; }
+    if (episode_time_steps < 1) return fail(CL_ERR_INVALID, "cl_set_outage: bad episode_time_steps");
+    const size_t n = (size_t)env->d.B * episode_time_steps;
+    if (!env->outage_dev || env->outage_T != episode_time_steps) {
+        if (env->outage_dev) { CUDA_TRY(cudaStreamSynchronize(st)); cudaFree(env->outage_dev); env->outage_dev = nullptr; }
+        CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&env->outage_dev), n * sizeof(float)));
+        env->outage_T = episode_time_steps;
+    }
+    CUDA_TRY(cudaMemcpyAsync(env->outage_dev, signals, n * sizeof(float), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaStreamSynchronize(st));   // `signals` is a host buffer the caller may free right away
+    env->d.outage = env->outage_dev;
+    env->d.has_outage = 1;
+    return CL_OK;
+}
+
+// blocks of up to 512 threads get the 128-register budget; only very wide districts (B > 512) use 1024-thread blocks
+template <typename R, bool TH>
+static void launch_reset(cl_env* env, float* obs, cudaStream_t st) {
+    const size_t smem = smem_bytes(env->d, env->threads, true);
+    if (env->threads <= 512) reset_kernel<R, TH, 512><<<env->blocks, env->threads, smem, st>>>(env->d, obs);
+    else reset_kernel<R, TH, 1024><<<env->blocks, env->threads, smem, st>>>(env->d, obs);
+}
+template <typename R, bool TH>
+static void launch_step(cl_env* env, const float* actions, float* obs, float* reward, float* district, float* trace, cudaStream_t st) {
+    const bool want_dyn = !env->d.stale && obs != nullptr;
+    const size_t smem = smem_bytes(env->d, env->threads, want_dyn);
+    if (env->threads <= 512) step_kernel<R, TH, 512><<<env->blocks, env->threads, smem, st>>>(env->d, env->t, actions, obs, reward, district, trace);
+    else step_kernel<R, TH, 1024><<<env->blocks, env->threads, smem, st>>>(env->d, env->t, actions, obs, reward, district, trace);
+}
+
+__global__ void fill_start_kernel(int32_t* start, int n, int v) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) start[i] = v;
+}
+
+extern "C" int cl_reset(cl_env* env, const int32_t* episode_start, int32_t uniform_start, int32_t episode_time_steps, float* obs,
+                        cl_stream stream) {
+    if (!env) return fail(CL_ERR_INVALID, "cl_reset: null env");
+    Dev& d = env->d;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (episode_time_steps < 2) return fail(CL_ERR_INVALID, "cl_reset: episode_time_steps must be >= 2");
+    if (d.has_outage && env->outage_T < episode_time_steps) return fail(CL_ERR_STATE, "cl_reset: outage signal shorter than the episode");
+    if (episode_start == nullptr) {
+        if (uniform_start < 0 || uniform_start + episode_time_steps > d.n_rows) return fail(CL_ERR_INVALID, "cl_reset: episode window outside the table");
+        fill_start_kernel<<<(d.E + 255) / 256, 256, 0, st>>>(const_cast<int32_t*>(d.start), d.E, uniform_start);
+        env->launches++;
+        d.uniform_start = 1; d.start0 = uniform_start;
+    } else {
+        CUDA_TRY(cudaMemcpyAsync(const_cast<int32_t*>(d.start), episode_start, sizeof(int32_t) * d.E, cudaMemcpyDeviceToDevice, st));
+        d.uniform_start = 0; d.start0 = 0;
+    }
+    d.T = episode_time_steps;
+    env->T = episode_time_steps;
+    if (env->precision == CL_PRECISION_FP64) { if (env->thermal) launch_reset<double, true>(env, obs, st); else launch_reset<double, false>(env, obs, st); }
+    else { if (env->thermal) launch_reset<float, true>(env, obs, st); else launch_reset<float, false>(env, obs, st); }
+    env->launches++;
+    CUDA_TRY(cudaGetLastError());
+    env->t = 0;
+    return CL_OK;
+}
+
+extern "C" int cl_step(cl_env* env, const float* actions, float* obs, float* reward, float* district, float* trace, cl_stream stream) {
+    if (!env || !actions) return fail(CL_ERR_INVALID, "cl_step: null argument");
+    if (env->t < 0) return fail(CL_ERR_STATE, "cl_step: call cl_reset first");
+    if (env->t >= env->T - 1) return fail(CL_ERR_STATE, "cl_step: episode has ended (terminated); call cl_reset");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (env->precision == CL_PRECISION_FP64) {
+        if (env->thermal) launch_step<double, true>(env, actions, obs, reward, district, trace, st);
+        else launch_step<double, false>(env, actions, obs, reward, district, trace, st);
+    } else {
+        if (env->thermal) launch_step<float, true>(env, actions, obs, reward, district, trace, st);
+        else launch_step<float, false>(env, actions, obs, reward, district, trace, st);
+    }
+    env->launches++;
+    CUDA_TRY(cudaGetLastError());
+    env->t += 1;
+    return CL_OK;
+}
+
+extern "C" int cl_rollout(cl_env* env, int32_t n_steps, const float* actions, float* obs, float* reward, float* district, cl_stream stream) {
+    if (!env || !actions) return fail(CL_ERR_INVALID, "cl_rollout: null argument");
+    if (n_steps < 1) return fail(CL_ERR_INVALID, "cl_rollout: n_steps must be >= 1");
+    if (env->t < 0) return fail(CL_ERR_STATE, "cl_rollout: call cl_reset first");
+    if (env->t + n_steps > env->T - 1) return fail(CL_ERR_STATE, "cl_rollout: block runs past the end of the episode");
+    const Dev& d = env->d;
+    const int R_ = d.central ? 1 : d.B;
+    for (int k = 0; k < n_steps; ++k) {   // first version: K launches (a fused persistent kernel replaces this loop)
+        int rc = cl_step(env, actions + (size_t)k * d.E * d.A, obs ? obs + (size_t)k * d.E * d.L : nullptr,
+                         reward ? reward + (size_t)k * d.E * R_ : nullptr, district ? district + (size_t)k * d.E * 3 : nullptr, nullptr, stream);
+        if (rc) return rc;
+    }
+    return CL_OK;
+}
+
+extern "C" int cl_time_step(const cl_env* env, int32_t* t) {
+    if (!env || !t) return fail(CL_ERR_INVALID, "cl_time_step: null argument");
+    *t = env->t;
+    return CL_OK;
+}
+
+extern "C" int cl_state_size(const cl_env* env, size_t* bytes) {
+    if (!env || !bytes) return fail(CL_ERR_INVALID, "cl_state_size: null argument");
+    *bytes = env->st_floats * sizeof(float) + env->dst_doubles * sizeof(double);
+    return CL_OK;
+}
+
+extern "C" int cl_get_state(cl_env* env, void* dst_dev, cl_stream stream) {
+    if (!env || !dst_dev) return fail(CL_ERR_INVALID, "cl_get_state: null argument");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    char* p = static_cast<char*>(dst_dev);
+    if (env->dst_doubles) {   // doubles first keeps them 8-byte aligned inside the blob
+        CUDA_TRY(cudaMemcpyAsync(p, env->d.dst, env->dst_doubles * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        p += env->dst_doubles * sizeof(double);
+    }
+    CUDA_TRY(cudaMemcpyAsync(p, env->d.st, env->st_floats * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return CL_OK;
+}
+
+extern "C" int cl_set_state(cl_env* env, const void* src_dev, int32_t time_step, cl_stream stream) {
+    if (!env || !src_dev) return fail(CL_ERR_INVALID, "cl_set_state: null argument");
+    if (env->T < 2 || time_step < 0 || time_step > env->T - 1) return fail(CL_ERR_STATE, "cl_set_state: time step outside the current episode (reset first)");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const char* p = static_cast<const char*>(src_dev);
+    if (env->dst_doubles) {
+        CUDA_TRY(cudaMemcpyAsync(env->d.dst, p, env->dst_doubles * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        p += env->dst_doubles * sizeof(double);
+    }
+    CUDA_TRY(cudaMemcpyAsync(env->d.st, p, env->st_floats * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    env->t = time_step;
+    return CL_OK;
+}
+
+extern "C" int cl_launch_count(const cl_env* env, int64_t* n) {
+    if (!env || !n) return fail(CL_ERR_INVALID, "cl_launch_count: null argument");
+    *n = env->launches;
+    return CL_OK;
+}

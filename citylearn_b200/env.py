@@ -1,0 +1,456 @@
+"""`CityLearnEnv`: the reference's Gymnasium surface over the fused CUDA step path.
+
+Drop-in contract (reference `citylearn/citylearn.py`):
+  * `CityLearnEnv(schema, **overrides)` with the same override keywords (`:133-142`, precedence `:2006-2051`);
+  * `reset(seed=None, options=None) -> (observations, info)` (`:1829-1886`);
+  * `step(actions) -> (observations, reward, terminated, truncated, info)` (`:978-1056`);
+  * `observation_space`, `action_space`, `observation_names`, `action_names`, `buildings`, `time_step`, `time_steps`,
+    `terminated`, `truncated`, `episode_rewards`, `episode_tracker`, `get_metadata()`, `unwrapped` (`:384-538, :946-953`).
+
+With `num_envs=1` and list actions the return values have the reference's shapes (lists of lists).  New keywords:
+`num_envs` (parallel environments held as CUDA tensors), `device`, `precision` ('fp64': the reference's own
+float64-intermediate / float32-storage arithmetic, bit-exact physics; 'fp32': float arithmetic), `stale_observations`
+(True = reference parity: action-dependent entries of the observation returned by `step` are the zero-initialised
+values at t+1; False = they carry the post-action values of step t).
+
+Batched mode (`num_envs > 1`, or tensor / ndarray actions): `actions` is `[E, sum(A_b)]` (district vector: buildings in
+order, active actions in schema order) or a list of per-building `[E, A_b]`; `step` returns `obs [E, L]`, `reward [E, B]`
+(or `[E, 1]` with a central agent) as CUDA tensors that are overwritten by the next step, and Python bools for
+terminated / truncated (all envs advance in lock-step).
+"""
+from __future__ import annotations
+
+import importlib
+import math
+from typing import Any, Dict, List, Mapping, Optional, Sequence, Tuple, Union
+
+import numpy as np
+import torch
+
+from . import _native
+from . import reward_function as rf_mod
+from . import schema as S
+from .spaces import Box
+
+_REFERENCE_REWARD_MODULES = ('citylearn.reward_function', 'citylearn_b200.reward_function')
+
+
+def _resolve_reward_class(spec_type):
+    if isinstance(spec_type, type):
+        # a reference class object (citylearn.reward_function.X) maps to the class of the same name here
+        if spec_type.__module__ in _REFERENCE_REWARD_MODULES and hasattr(rf_mod, spec_type.__name__):
+            return getattr(rf_mod, spec_type.__name__)
+        return spec_type
+    module_name, _, class_name = str(spec_type).rpartition('.')
+    if module_name in _REFERENCE_REWARD_MODULES and hasattr(rf_mod, class_name):
+        return getattr(rf_mod, class_name)
+    return getattr(importlib.import_module(module_name), class_name)
+
+
+class BuildingProxy:
+    """Light stand-in for `citylearn.building.Building`: the attributes wrappers / agents read."""
+
+    def __init__(self, env: 'CityLearnEnv', spec: S.BuildingSpec):
+        self._env = env
+        self._spec = spec
+        self.name = spec.name
+        self.observation_metadata = dict(spec.observation_metadata)
+        self.action_metadata = dict(spec.action_metadata)
+        self.observation_space = Box(low=spec.observation_low, high=spec.observation_high, dtype=np.float32)
+        self.action_space = Box(low=spec.action_low, high=spec.action_high, dtype=np.float32)
+        self.time_step_ratio = spec.time_step_ratio
+        self.seconds_per_time_step = spec.seconds_per_time_step
+
+    @property
+    def active_observations(self) -> List[str]:
+        return self._spec.active_observations
+
+    @property
+    def active_actions(self) -> List[str]:
+        return self._spec.active_actions
+
+    def get_metadata(self) -> Mapping[str, Any]:
+        dv = self._spec.devices
+        s = self._spec.series
+        n_years = max(1, self._env.time_steps * self.seconds_per_time_step / (8760 * 3600))
+
+        def device(d):
+            out = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in d.items() if k not in ('type', 'class', 'absent')}
+            if 'efficiency' in d and d['type'] in ('StorageTank', 'Battery'):
+                out['round_trip_efficiency'] = d['efficiency'] ** 0.5
+            return out
+
+        return {
+            'name': self.name, 'observation_metadata': self.observation_metadata, 'action_metadata': self.action_metadata,
+            **{k: device(dv[k]) for k in ('cooling_device', 'heating_device', 'dhw_device', 'cooling_storage', 'heating_storage',
+                                          'dhw_storage', 'electrical_storage', 'pv')},
+            'annual_cooling_demand_estimate': float(s['cooling_demand'].sum() / n_years),
+            'annual_heating_demand_estimate': float(s['heating_demand'].sum() / n_years),
+            'annual_dhw_demand_estimate': float(s['dhw_demand'].sum() / n_years),
+            'annual_non_shiftable_load_estimate': float(s['non_shiftable_load'].sum() / n_years),
+            'annual_solar_generation_estimate': float(S.pv_generation(self._spec, s['solar_generation']).sum() / n_years),
+        }
+
+
+class CityLearnEnv:
+    metadata: Dict[str, Any] = {}
+    render_mode = None
+
+    def __init__(self, schema, num_envs: int = 1, device: Union[str, torch.device, None] = None, precision: str = 'fp64',
+                 stale_observations: bool = True, track_episode_rewards: Optional[bool] = None, debug_trace: bool = False, **kwargs):
+        self.spec = S.load(schema, **kwargs)
+        self.schema = self.spec.schema
+        self.num_envs = int(num_envs)
+        if self.num_envs < 1:
+            raise ValueError('num_envs must be >= 1')
+        if not torch.cuda.is_available():
+            raise RuntimeError('citylearn_b200 needs a CUDA device (B200 / sm_100a); there is no CPU fallback.')
+        self.device = torch.device('cuda' if device is None else device)
+        if self.device.type != 'cuda':
+            raise RuntimeError("citylearn_b200 runs on CUDA devices only (device='cuda[:i]'); there is no CPU fallback.")
+        if self.device.index is None:
+            self.device = torch.device('cuda', torch.cuda.current_device())
+        self.precision = precision
+        self.stale_observations = bool(stale_observations)
+        spec = self.spec
+        self.central_agent = spec.central_agent
+        self.shared_observations = spec.shared_observations
+        self.random_seed = spec.random_seed
+        self.seconds_per_time_step = spec.seconds_per_time_step
+        self.time_step_ratio = spec.time_step_ratio
+        self.episode_time_steps = spec.episode_time_steps
+        self.rolling_episode_split = spec.rolling_episode_split
+        self.random_episode_split = spec.random_episode_split
+        self.episode_tracker = S.EpisodeTracker(spec.simulation_start_time_step, spec.simulation_end_time_step)
+        self.buildings = [BuildingProxy(self, b) for b in spec.buildings]
+        self._entries, self._desc = S.observation_layout(spec, self.central_agent, self.stale_observations)
+        self._obs_dim = len(self._entries)
+        self._sizes_obs = [len(b.active_observations) for b in spec.buildings]
+        self._sizes_act = [len(b.active_actions) for b in spec.buildings]
+        self._track = (self.num_envs == 1) if track_episode_rewards is None else bool(track_episode_rewards)
+        # reward function (citylearn/citylearn.py:2100-2163)
+        self.reward_function = self._make_reward_function()
+        rid, rparams = self._fused_reward()
+        self._reward_id = rid
+        self._reward_dim = 1 if self.central_agent else spec.n_buildings
+        with torch.cuda.device(self.device):
+            self._h = _native.Handle(spec, self.num_envs, self._desc, self.central_agent, rid, rparams, precision, self.stale_observations)
+            E = self.num_envs
+            self._obs = torch.zeros((E, self._obs_dim), dtype=torch.float32, device=self.device)
+            self._reward = torch.zeros((E, self._reward_dim), dtype=torch.float32, device=self.device)
+            self._district = torch.zeros((E, 3), dtype=torch.float32, device=self.device)
+            self._trace = (torch.zeros((E, spec.n_buildings, S.NDYN), dtype=torch.float32, device=self.device)
+                           if (rid < 0 or debug_trace) else None)
+            self._act = torch.zeros((E, max(spec.action_dim, 1)), dtype=torch.float32, device=self.device)
+            self._act_pinned = torch.zeros((E, max(spec.action_dim, 1)), dtype=torch.float32).pin_memory()
+            self._obs_pinned = torch.zeros((E, self._obs_dim), dtype=torch.float32).pin_memory()
+            self._reward_pinned = torch.zeros((E, self._reward_dim), dtype=torch.float32).pin_memory()
+        self._table_dev = None
+        self.time_step = 0
+        self._episode_rewards: List[Mapping[str, Any]] = []
+        self._rsum = self._rmin = self._rmax = None
+        self.reset()
+        self.episode_tracker.reset_episode_index()       # citylearn/citylearn.py:237-240
+        self.reward_function.env_metadata = self.get_metadata()
+        self._episode_rewards = []
+
+    # ---------------------------------------------------------------------------------------------
+    # reward plumbing
+    # ---------------------------------------------------------------------------------------------
+    def _make_reward_function(self):
+        spec = self.spec
+        rt, attrs = spec.reward_type, spec.reward_attributes
+        if isinstance(rt, dict):   # per-building reward functions (citylearn/citylearn.py:2106-2141)
+            default_type = rt.get('default') or (next(iter(rt.values())) if rt else None)
+            default_attrs = (attrs or {}).get('default')
+            if default_attrs is None and attrs:
+                default_attrs = next(iter(attrs.values()))
+            fns = {}
+            for b in spec.buildings:
+                r_type = rt.get(b.name, default_type)
+                if r_type is None:
+                    raise ValueError(f"No reward function defined for building '{b.name}' and no default provided")
+                fns[b.name] = _resolve_reward_class(r_type)(None, **((attrs or {}).get(b.name, default_attrs) or {}))
+            return rf_mod.MultiBuildingRewardFunction(None, fns)
+        if isinstance(rt, rf_mod.RewardFunction):
+            return rt
+        return _resolve_reward_class(rt)(None, **(attrs or {}))
+
+    def _fused_reward(self) -> Tuple[int, List[float]]:
+        r = self.reward_function
+        rid = rf_mod.BUILTIN_REWARD_IDS.get(type(r), -1)
+        if rid == 0:
+            return rid, [float(r.exponent)]
+        if rid == 4:
+            return rid, [float('nan') if r.band is None else float(r.band), float(r.lower_exponent), float(r.higher_exponent)]
+        if rid == 5:
+            c = r._functions[1]
+            return rid, [float('nan') if c.band is None else float(c.band), float(c.lower_exponent), float(c.higher_exponent),
+                         float(r.coefficients[0]), float(r.coefficients[1])]
+        return rid, []
+
+    def _reward_observations(self) -> List[Dict[str, torch.Tensor]]:
+        """Per-building dicts of `Tensor[E]` at step t for Python reward functions (citylearn/citylearn.py:1022)."""
+        spec = self.spec
+        if self._table_dev is None:
+            self._table_dev = torch.as_tensor(spec.table, device=self.device)
+        rows = self._start_dev.long() + (self.time_step)
+        out = []
+        for bi, b in enumerate(spec.buildings):
+            d: Dict[str, torch.Tensor] = {}
+            for key, col in spec.columns.items():
+                if isinstance(key, tuple) and len(key) == 2 and key[0] == bi and isinstance(key[1], str) and not key[1].startswith('C_'):
+                    d[key[1]] = self._table_dev[rows, col]
+            for name, slot in S.DYN.items():
+                d[name] = self._trace[:, bi, slot]
+            d['power_outage'] = torch.full((self.num_envs,), float(self._outage[bi, self.time_step]), device=self.device)
+            out.append(d)
+        return out
+
+    # ---------------------------------------------------------------------------------------------
+    # Gymnasium surface
+    # ---------------------------------------------------------------------------------------------
+    @property
+    def unwrapped(self):
+        return self
+
+    @property
+    def time_steps(self) -> int:
+        return self.episode_tracker.episode_time_steps
+
+    @property
+    def terminated(self) -> bool:
+        return self.time_step == self.time_steps - 1     # citylearn/citylearn.py:372-376
+
+    @property
+    def truncated(self) -> bool:
+        return False
+
+    @property
+    def episode_rewards(self):
+        return self._episode_rewards
+
+    @property
+    def observation_space(self) -> List[Box]:
+        if self.central_agent:
+            lo, hi = [], []
+            flat_lo = {(bi, n): v for bi, b in enumerate(self.spec.buildings) for n, v in zip(b.active_observations, b.observation_low)}
+            flat_hi = {(bi, n): v for bi, b in enumerate(self.spec.buildings) for n, v in zip(b.active_observations, b.observation_high)}
+            for key in self._entries:
+                lo.append(flat_lo[key])
+                hi.append(flat_hi[key])
+            return [Box(low=np.array(lo, dtype='float32'), high=np.array(hi, dtype='float32'), dtype=np.float32)]
+        return [b.observation_space for b in self.buildings]
+
+    @property
+    def action_space(self) -> List[Box]:
+        if self.central_agent:
+            lo = [v for b in self.spec.buildings for v in b.action_low]
+            hi = [v for b in self.spec.buildings for v in b.action_high]
+            return [Box(low=np.array(lo, dtype='float32'), high=np.array(hi, dtype='float32'), dtype=np.float32)]
+        return [b.action_space for b in self.buildings]
+
+    @property
+    def observation_names(self) -> List[List[str]]:
+        if self.central_agent:
+            return [[n for _, n in self._entries]]
+        return [list(b.active_observations) for b in self.spec.buildings]
+
+    @property
+    def action_names(self) -> List[List[str]]:
+        if self.central_agent:
+            return [[n for b in self.spec.buildings for n in b.active_actions]]
+        return [list(b.active_actions) for b in self.spec.buildings]
+
+    @property
+    def observations(self):
+        """Current observation: reference-shaped lists for num_envs == 1, else the `[E, L]` CUDA tensor."""
+        return self._shape_obs(self._obs) if self.num_envs == 1 else self._obs
+
+    def get_metadata(self) -> Mapping[str, Any]:
+        return {
+            'random_seed': self.random_seed, 'simulation_time_steps': self.episode_tracker.simulation_time_steps,
+            'seconds_per_time_step': self.seconds_per_time_step, 'time_step_ratio': self.time_step_ratio,
+            'buildings': [b.get_metadata() for b in self.buildings], 'central_agent': self.central_agent,
+            'shared_observations': self.shared_observations, 'num_envs': self.num_envs,
+        }
+
+    def get_info(self) -> Mapping[Any, Any]:
+        return {}
+
+    def close(self):
+        self._h.close()
+
+    # ---------------------------------------------------------------------------------------------
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _shape_obs(self, obs: torch.Tensor):
+        row = obs[0].tolist()
+        if self.central_agent:
+            return [row]
+        out, o = [], 0
+        for n in self._sizes_obs:
+            out.append(row[o:o + n])
+            o += n
+        return out
+
+    def reset(self, seed: int = None, options: Mapping[str, Any] = None):
+        """Start the next episode (citylearn/citylearn.py:1829-1886). `options={'episode_start': Tensor[E] int32}` gives every
+        env its own window start (same length) instead of the tracker's."""
+        if seed is not None:
+            self.random_seed = seed
+        ets = self.episode_time_steps if self.episode_time_steps is not None else self.episode_tracker.simulation_time_steps
+        self.episode_tracker.next_episode(ets, self.rolling_episode_split, self.random_episode_split, self.random_seed)
+        start = self.episode_tracker.episode_start_time_step
+        T = self.episode_tracker.episode_time_steps
+        self._outage = S.outage_signals(self.spec, T, start)
+        self.time_step = 0
+        with torch.cuda.device(self.device):
+            stream = self._stream()
+            self._h.set_outage(self._outage if any(b.simulate_power_outage for b in self.spec.buildings) else None, stream)
+            per_env = None if not options else options.get('episode_start')
+            if per_env is not None:
+                self._start_dev = torch.as_tensor(per_env, dtype=torch.int32, device=self.device).contiguous()
+                assert self._start_dev.shape == (self.num_envs,)
+                self._h.reset(self._start_dev.data_ptr(), 0, T, self._obs.data_ptr(), stream)
+            else:
+                self._start_dev = torch.full((self.num_envs,), start, dtype=torch.int32, device=self.device)
+                self._h.reset(None, start, T, self._obs.data_ptr(), stream)
+        self.reward_function.reset()
+        self._rsum = self._rmin = self._rmax = None
+        if self.num_envs == 1:
+            return self._shape_obs(self._obs), self.get_info()
+        return self._obs, self.get_info()
+
+    def _parse_actions(self, actions) -> Tuple[torch.Tensor, bool]:
+        """-> (device tensor [E, A], reference_shaped)."""
+        E, A = self.num_envs, self.spec.action_dim
+        if isinstance(actions, torch.Tensor):
+            a = actions.reshape(E, A)
+            if a.device != self.device or a.dtype != torch.float32 or not a.is_contiguous():
+                a = a.to(device=self.device, dtype=torch.float32, non_blocking=True).contiguous()
+            return a, False
+        if isinstance(actions, np.ndarray):
+            self._act_pinned.copy_(torch.from_numpy(np.ascontiguousarray(actions, dtype=np.float32).reshape(E, A)))
+            self._act.copy_(self._act_pinned, non_blocking=True)
+            return self._act, False
+        actions = list(actions)
+        if len(actions) and isinstance(actions[0], torch.Tensor):      # per-building [E, A_b]
+            a = torch.cat([x.reshape(E, -1).to(self.device, torch.float32) for x in actions], dim=1).contiguous()
+            assert a.shape[1] == A
+            return a, False
+        # reference-style nested lists (citylearn/citylearn.py:1063-1134)
+        if E != 1:
+            raise ValueError('nested-list actions are only accepted with num_envs == 1; pass an [E, A] tensor or ndarray')
+        if self.central_agent:
+            flat = [float(v) for v in actions[0]]
+            assert len(flat) == A, f'Expected {A} actions but {len(flat)} were parsed to env.step.'
+        else:
+            flat = []
+            for b, a in zip(self.spec.buildings, actions):
+                a = list(a)
+                assert len(a) == len(b.active_actions), f'Expected {len(b.active_actions)} for {b.name} but {len(a)} actions were provided.'
+                flat += [float(v) for v in a]
+        self._act_pinned[0, :A] = torch.tensor(flat, dtype=torch.float32)
+        self._act.copy_(self._act_pinned, non_blocking=True)
+        return self._act, True
+
+    def step(self, actions):
+        if self.terminated:
+            raise RuntimeError('step() called after the episode terminated; call reset().')
+        with torch.cuda.device(self.device):
+            a, ref_shaped = self._parse_actions(actions)
+            stream = self._stream()
+            fused = self._reward_id >= 0
+            self._h.step(a.data_ptr(), self._obs.data_ptr(), self._reward.data_ptr() if fused else None, self._district.data_ptr(),
+                         None if self._trace is None else self._trace.data_ptr(), stream)
+            if not fused:
+                self._python_reward()
+            self.time_step += 1
+            if self._track:
+                self._accumulate_rewards()
+        terminated = self.terminated
+        if terminated and self._track:
+            self._finish_episode_rewards()
+        if ref_shaped:
+            rew = self._reward[0].tolist()
+            return self._shape_obs(self._obs), rew, terminated, False, self.get_info()
+        return self._obs, self._reward, terminated, False, self.get_info()
+
+    def step_host(self, actions: np.ndarray) -> Tuple[np.ndarray, np.ndarray, bool]:
+        """End-to-end host path: host ndarray actions in, host ndarrays out (pinned staging, one sync)."""
+        obs, rew, terminated, _, _ = self.step(np.asarray(actions, dtype=np.float32))
+        self._obs_pinned.copy_(obs, non_blocking=True)
+        self._reward_pinned.copy_(rew, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return self._obs_pinned.numpy(), self._reward_pinned.numpy(), terminated
+
+    def rollout(self, actions: torch.Tensor, obs: Optional[torch.Tensor] = None, reward: Optional[torch.Tensor] = None,
+                district: Optional[torch.Tensor] = None):
+        """K steps with pre-resident actions `[K, E, A]` (device). Fills `obs [K, E, L]`, `reward [K, E, R]`, `district [K, E, 3]`."""
+        if self._reward_id < 0:
+            raise NotImplementedError('rollout needs a built-in (fused) reward function')
+        K = actions.shape[0]
+        assert actions.is_cuda and actions.dtype == torch.float32 and actions.is_contiguous()
+        with torch.cuda.device(self.device):
+            self._h.rollout(K, actions.data_ptr(), None if obs is None else obs.data_ptr(), None if reward is None else reward.data_ptr(),
+                            None if district is None else district.data_ptr(), self._stream())
+        self.time_step += K
+        return obs, reward, self.terminated
+
+    # ---------------------------------------------------------------------------------------------
+    def _python_reward(self):
+        obs = self._reward_observations()
+        r = self.reward_function.calculate(obs)
+        flat = []
+        for v in r:
+            v = v[0] if isinstance(v, (list, tuple)) else v     # MultiBuildingRewardFunction returns 1-element lists
+            v = v if isinstance(v, torch.Tensor) else torch.as_tensor(v, dtype=torch.float32, device=self.device)
+            flat.append(v.to(self.device, torch.float32).reshape(-1).expand(self.num_envs))
+        self._reward.copy_(torch.stack(flat, dim=1))
+
+    def _accumulate_rewards(self):
+        r = self._reward
+        if self._rsum is None:
+            self._rsum, self._rmin, self._rmax, self._rcount = r.clone(), r.clone(), r.clone(), 1
+        else:
+            self._rsum += r
+            torch.minimum(self._rmin, r, out=self._rmin)
+            torch.maximum(self._rmax, r, out=self._rmax)
+            self._rcount += 1
+
+    def _finish_episode_rewards(self):
+        # citylearn/citylearn.py:1034-1040 (float32 min / max / sum / mean over the episode's steps)
+        def shape(x):
+            return x[0].tolist() if self.num_envs == 1 else x.clone()
+        self._episode_rewards.append({'min': shape(self._rmin), 'max': shape(self._rmax), 'sum': shape(self._rsum),
+                                      'mean': shape(self._rsum / self._rcount)})
+
+    # ---------------------------------------------------------------------------------------------
+    def state_dict(self) -> Dict[str, Any]:
+        """Checkpoint of the mutable simulation state."""
+        n = self._h.state_size()
+        buf = torch.empty(n, dtype=torch.uint8, device=self.device)
+        self._h.get_state(buf.data_ptr(), self._stream())
+        return {'state': buf, 'time_step': self.time_step, 'episode': self.episode_tracker.episode,
+                'episode_start': self._start_dev.clone(), 'obs': self._obs.clone()}
+
+    def load_state_dict(self, sd: Mapping[str, Any]):
+        self._h.set_state(sd['state'].data_ptr(), int(sd['time_step']), self._stream())
+        self.time_step = int(sd['time_step'])
+        self._obs.copy_(sd['obs'])
+
+    @property
+    def trace(self) -> Optional[torch.Tensor]:
+        """`[E, B, CL_NDYN]` per-unit values of the last step (only with `debug_trace=True` or a Python reward function)."""
+        return self._trace
+
+    @property
+    def district(self) -> torch.Tensor:
+        """`[E, 3]` district net electricity consumption, cost and emission of the last step (citylearn.py:1908-1918)."""
+        return self._district
+
+    @property
+    def gpu_launches(self) -> int:
+        return self._h.launch_count()

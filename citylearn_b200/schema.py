@@ -58,6 +58,7 @@ P = {name: i for i, name in enumerate([
     'CP_Y0', 'CP_Y1', 'CP_Y2', 'CP_Y3', 'CP_Y4', 'CP_Y5', 'CP_Y6', 'CP_Y7',
     # LSTM output de-normalisation for indoor_dry_bulb_temperature (citylearn/building.py:3031-3037)
     'DYN_TIN_MIN', 'DYN_TIN_MAX', 'DYN_CDEM_MIN', 'DYN_CDEM_MAX',
+    'PV_NOMINAL_POWER',
 ])}
 NPARAM = len(P)
 MAX_CURVE = 8
@@ -964,7 +965,7 @@ def finalize(spec: DistrictSpec) -> None:
         p = params[bi]
         physics = {
             'C_NSL': s['non_shiftable_load'], 'C_DHW_DEMAND': s['dhw_demand'], 'C_COOLING_DEMAND': s['cooling_demand'],
-            'C_HEATING_DEMAND': s['heating_demand'], 'C_SOLAR': derived_series(b, 'solar_neg'),
+            'C_HEATING_DEMAND': s['heating_demand'], 'C_SOLAR': s['solar_generation'],
             'C_T_OUT': s['outdoor_dry_bulb_temperature'], 'C_PRICE': s['electricity_pricing'], 'C_CARBON': s['carbon_intensity'],
             'C_HVAC_MODE': s['hvac_mode'], 'C_T_IN': s['indoor_dry_bulb_temperature'],
             'C_COOL_SP': s['indoor_dry_bulb_temperature_cooling_set_point'],
@@ -1032,6 +1033,7 @@ def finalize(spec: DistrictSpec) -> None:
                 p[P[f'{pre}_EFFICIENCY']] = d['efficiency']
         # quirk kept: at t == 0 a heater-type heating device is billed with the DHW heater's efficiency (building.py:2632)
         p[P['TIME_STEP_RATIO']] = b.time_step_ratio
+        p[P['PV_NOMINAL_POWER']] = dv['pv']['nominal_power']
         p[P['HOURS_PER_STEP']] = spec.seconds_per_time_step / 3600
         thermal = (s['cooling_demand'].any() or s['heating_demand'].any() or s['dhw_demand'].any()
                    or any(dv[k]['capacity'] > 0 for k in ('cooling_storage', 'heating_storage', 'dhw_storage'))

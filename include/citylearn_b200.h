@@ -1,0 +1,210 @@
+/*
+ * citylearn_b200.h - C ABI of the B200-native CityLearn step path.
+ *
+ * The reference (intelligent-environments-lab/CityLearn v2.4.2) is pure Python and has no FFI; the entry
+ * points below are what a binding for its hot path would call.  Each one names the reference
+ * interface it replaces (file:line relative to the reference tree):
+ *
+ *   cl_create   <- CityLearnEnv.__init__ / _load ............ citylearn/citylearn.py:133-271, 1973-2170
+ *                  (the schema is parsed on the host by citylearn_b200/schema.py; the descriptor carries
+ *                   the flattened result: parameters, the time-series table, the observation layout)
+ *   cl_reset    <- CityLearnEnv.reset ...................... citylearn/citylearn.py:1829-1886
+ *                  Building.reset .......................... citylearn/building.py:2526-2564
+ *   cl_step     <- CityLearnEnv.step ....................... citylearn/citylearn.py:978-1056
+ *                  Building.apply_actions .................. citylearn/building.py:1500-1634
+ *                  Building.update_variables ............... citylearn/building.py:2615-2703
+ *                  CityLearnEnv.update_variables ........... citylearn/citylearn.py:1888-1918
+ *                  RewardFunction.calculate (built-ins) .... citylearn/reward_function.py:65-386
+ *                  CityLearnEnv.observations ............... citylearn/citylearn.py:451-485
+ *   cl_rollout  <- the caller's `while not env.terminated: env.step(a)` loop
+ *                  (citylearn/agents/base.py:155-176) for open-loop action blocks
+ *   cl_get_state / cl_set_state <- (no reference equivalent; checkpoint / resume of the mutable state)
+ *   cl_set_outage <- Building.reset_power_outage_signal ..... citylearn/building.py:2566-2594
+ *
+ * Conventions: every pointer marked "dev" is device memory owned by the caller (e.g. torch tensors'
+ * data_ptr()); "host" pointers are only read during the call.  All entry points enqueue work on the
+ * given CUDA stream and return without synchronising.  Return value: CL_OK or an error code; the
+ * message of the last error of the calling thread is available from cl_last_error().
+ * One cl_env must not be used from two streams at once; distinct handles are independent.
+ */
+#ifndef CITYLEARN_B200_H
+#define CITYLEARN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CL_ABI_VERSION 1
+
+typedef enum cl_status {
+    CL_OK = 0,
+    CL_ERR_INVALID = 1,      /* bad argument / descriptor */
+    CL_ERR_CUDA = 2,         /* CUDA runtime error (message has the cudaError string) */
+    CL_ERR_UNSUPPORTED = 3,  /* feature outside the accelerated path */
+    CL_ERR_STATE = 4         /* call sequence error (e.g. step before reset, step after the episode end) */
+} cl_status;
+
+/* ---- per-building float parameters: column k of params[CL_NPARAM][B] (host, double) ------------- */
+enum cl_building_param {
+    CL_P_BAT_CAPACITY = 0, CL_P_BAT_NOMINAL_POWER, CL_P_BAT_EFFICIENCY0, CL_P_BAT_LOSS, CL_P_BAT_CLC, CL_P_BAT_DOD,
+    CL_P_BAT_INITIAL_SOC,
+    CL_P_CS_CAPACITY, CL_P_CS_EFFICIENCY, CL_P_CS_LOSS, CL_P_CS_INITIAL_SOC, CL_P_CS_MAX_IN, CL_P_CS_MAX_OUT,
+    CL_P_HS_CAPACITY, CL_P_HS_EFFICIENCY, CL_P_HS_LOSS, CL_P_HS_INITIAL_SOC, CL_P_HS_MAX_IN, CL_P_HS_MAX_OUT,
+    CL_P_DS_CAPACITY, CL_P_DS_EFFICIENCY, CL_P_DS_LOSS, CL_P_DS_INITIAL_SOC, CL_P_DS_MAX_IN, CL_P_DS_MAX_OUT,
+    CL_P_CD_NOMINAL_POWER, CL_P_CD_COP_NUM, CL_P_CD_TARGET,
+    CL_P_HD_NOMINAL_POWER, CL_P_HD_COP_NUM, CL_P_HD_TARGET, CL_P_HD_EFFICIENCY,
+    CL_P_DD_NOMINAL_POWER, CL_P_DD_COP_NUM, CL_P_DD_TARGET, CL_P_DD_EFFICIENCY,
+    CL_P_TIME_STEP_RATIO, CL_P_HOURS_PER_STEP,
+    CL_P_PE_X0, CL_P_PE_X1, CL_P_PE_X2, CL_P_PE_X3, CL_P_PE_X4, CL_P_PE_X5, CL_P_PE_X6, CL_P_PE_X7,
+    CL_P_PE_Y0, CL_P_PE_Y1, CL_P_PE_Y2, CL_P_PE_Y3, CL_P_PE_Y4, CL_P_PE_Y5, CL_P_PE_Y6, CL_P_PE_Y7,
+    CL_P_CP_X0, CL_P_CP_X1, CL_P_CP_X2, CL_P_CP_X3, CL_P_CP_X4, CL_P_CP_X5, CL_P_CP_X6, CL_P_CP_X7,
+    CL_P_CP_Y0, CL_P_CP_Y1, CL_P_CP_Y2, CL_P_CP_Y3, CL_P_CP_Y4, CL_P_CP_Y5, CL_P_CP_Y6, CL_P_CP_Y7,
+    CL_P_DYN_TIN_MIN, CL_P_DYN_TIN_MAX, CL_P_DYN_CDEM_MIN, CL_P_DYN_CDEM_MAX,
+    CL_P_PV_NOMINAL_POWER,   /* C_SOLAR is the raw inverter series [W/kW]; solar_generation = -(P * s / 1000), building.py:2554 */
+    CL_NPARAM
+};
+#define CL_MAX_CURVE 8
+
+/* ---- per-building int parameters: column k of iparams[CL_NIPARAM][B] (host, int32) -------------- */
+enum cl_building_iparam {
+    CL_IP_FLAGS = 0, CL_IP_PE_N, CL_IP_CP_N,
+    CL_IP_A_COOLING_DEVICE, CL_IP_A_HEATING_DEVICE, CL_IP_A_COOLING_OR_HEATING_DEVICE,
+    CL_IP_A_COOLING_STORAGE, CL_IP_A_HEATING_STORAGE, CL_IP_A_DHW_STORAGE, CL_IP_A_ELECTRICAL_STORAGE,
+    CL_IP_C_NSL, CL_IP_C_DHW_DEMAND, CL_IP_C_COOLING_DEMAND, CL_IP_C_HEATING_DEMAND, CL_IP_C_SOLAR, CL_IP_C_T_OUT,
+    CL_IP_C_PRICE, CL_IP_C_CARBON, CL_IP_C_HVAC_MODE, CL_IP_C_T_IN, CL_IP_C_COOL_SP, CL_IP_C_HEAT_SP,
+    CL_IP_C_COMFORT_BAND, CL_IP_C_OCCUPANT,
+    CL_IP_DYN_C_INPUTS, CL_IP_DYN_N_INPUTS, CL_IP_DYN_SLOT_TIN, CL_IP_DYN_SLOT_CDEM, CL_IP_DYN_W_OFFSET,
+    CL_IP_DYN_LOOKBACK, CL_IP_DYN_HIDDEN,
+    CL_NIPARAM
+};
+
+/* CL_IP_FLAGS bits */
+#define CL_F_HEATING_IS_HEAT_PUMP (1 << 0)
+#define CL_F_DHW_IS_HEAT_PUMP     (1 << 1)
+#define CL_F_SIMULATE_OUTAGE      (1 << 2)
+#define CL_F_DYNAMICS             (1 << 3)
+#define CL_F_HAS_THERMAL          (1 << 4)
+#define CL_F_CS_HAS_MAX_IN        (1 << 5)
+#define CL_F_CS_HAS_MAX_OUT       (1 << 6)
+#define CL_F_HS_HAS_MAX_IN        (1 << 7)
+#define CL_F_HS_HAS_MAX_OUT       (1 << 8)
+#define CL_F_DS_HAS_MAX_IN        (1 << 9)
+#define CL_F_DS_HAS_MAX_OUT       (1 << 10)
+
+/* ---- per-unit dynamic values at time step t (trace output, DYN observation slots) --------------- */
+enum cl_dyn {
+    CL_DYN_ELECTRICAL_STORAGE_SOC = 0, CL_DYN_COOLING_STORAGE_SOC, CL_DYN_HEATING_STORAGE_SOC, CL_DYN_DHW_STORAGE_SOC,
+    CL_DYN_NET_ELECTRICITY_CONSUMPTION, CL_DYN_COOLING_DEMAND, CL_DYN_HEATING_DEMAND, CL_DYN_DHW_DEMAND,
+    CL_DYN_COOLING_ELECTRICITY_CONSUMPTION, CL_DYN_HEATING_ELECTRICITY_CONSUMPTION, CL_DYN_DHW_ELECTRICITY_CONSUMPTION,
+    CL_DYN_COOLING_STORAGE_ELECTRICITY_CONSUMPTION, CL_DYN_HEATING_STORAGE_ELECTRICITY_CONSUMPTION,
+    CL_DYN_DHW_STORAGE_ELECTRICITY_CONSUMPTION, CL_DYN_ELECTRICAL_STORAGE_ELECTRICITY_CONSUMPTION,
+    CL_DYN_INDOOR_DRY_BULB_TEMPERATURE, CL_DYN_NON_SHIFTABLE_LOAD_ELECTRICITY_CONSUMPTION,
+    CL_DYN_ELECTRICAL_STORAGE_ENERGY_BALANCE, CL_DYN_COOLING_STORAGE_ENERGY_BALANCE, CL_DYN_HEATING_STORAGE_ENERGY_BALANCE,
+    CL_DYN_DHW_STORAGE_ENERGY_BALANCE, CL_DYN_NET_ELECTRICITY_CONSUMPTION_COST, CL_DYN_NET_ELECTRICITY_CONSUMPTION_EMISSION,
+    CL_DYN_ELECTRICAL_STORAGE_DEGRADED_CAPACITY,
+    CL_NDYN
+};
+
+/* ---- observation descriptor: obs_desc[L][4] = (kind, a, b, building) ----------------------------- */
+enum cl_obs_kind {
+    CL_OBS_TS = 0,          /* a = table column: value of the series at the observed time step            */
+    CL_OBS_DYN = 1,         /* a = cl_dyn slot of `building`; zero after a step in reference-parity mode  */
+    CL_OBS_OUTAGE = 2,      /* power-outage signal of `building` at the observed time step                */
+    CL_OBS_TS_MINUS_TS = 3  /* reserved                                                                    */
+};
+
+/* ---- built-in reward functions (citylearn/reward_function.py) ------------------------------------ */
+enum cl_reward_id {
+    CL_REWARD_DEFAULT = 0,            /* RewardFunction :65-88   p[0] = exponent                          */
+    CL_REWARD_MARL = 1,               /* MARL :132-143                                                     */
+    CL_REWARD_INDEPENDENT_SAC = 2,    /* IndependentSACReward :159-168                                     */
+    CL_REWARD_SOLAR_PENALTY = 3,      /* SolarPenaltyReward :189-214                                       */
+    CL_REWARD_COMFORT = 4,            /* ComfortReward :269-334  p[0]=band (NaN: series) p[1]=lower p[2]=higher exponent */
+    CL_REWARD_SOLAR_PENALTY_AND_COMFORT = 5, /* :381-386         p[3], p[4] = coefficients                 */
+    CL_REWARD_NONE = -1               /* rewards are computed by the caller from the trace (custom RewardFunction) */
+};
+
+enum cl_precision {
+    CL_PRECISION_FP32 = 0,  /* float arithmetic (north-star contract: <= 1e-5 scaled-relative of the reference)      */
+    CL_PRECISION_FP64 = 1   /* the reference's own float64-intermediate / float32-storage flow (bit-exact physics)    */
+};
+
+typedef struct cl_district_desc {
+    int32_t abi_version;         /* CL_ABI_VERSION */
+    int32_t n_buildings;         /* B */
+    int32_t n_envs;              /* E parallel environments held by this handle (this GPU's shard) */
+    int32_t n_rows;              /* rows of the time-series table (dataset length) */
+    int32_t n_cols;              /* W columns per row */
+    int32_t action_dim;          /* sum of active actions over buildings */
+    int32_t obs_dim;             /* L values per env observation row */
+    int32_t central_agent;       /* 1: reward is the district sum [E,1]; 0: [E,B] */
+    int32_t reward_id;           /* cl_reward_id */
+    int32_t precision;           /* cl_precision */
+    int32_t stale_observations;  /* 1: reference parity (DYN observations read 0 after a step) */
+    int32_t lstm_weight_count;   /* floats in lstm_weights (0: no dynamics) */
+    double reward_params[8];
+    const float* table;          /* host [n_rows][n_cols] */
+    const double* params;        /* host [CL_NPARAM][B] */
+    const int32_t* iparams;      /* host [CL_NIPARAM][B] */
+    const int32_t* obs_desc;     /* host [L][4] */
+    const float* lstm_weights;   /* host, per-building blocks at iparams[CL_IP_DYN_W_OFFSET] */
+} cl_district_desc;
+
+typedef struct cl_env cl_env;    /* opaque */
+typedef void* cl_stream;         /* cudaStream_t */
+
+/* Build the device-side district: copies the table, parameters and layouts to the current CUDA device. */
+int cl_create(const cl_district_desc* desc, cl_env** out);
+int cl_destroy(cl_env* env);
+
+/* Power-outage signals of the coming episode: host [B][episode_time_steps] float 0/1 (NULL: no outages). */
+int cl_set_outage(cl_env* env, const float* signals, int32_t episode_time_steps, cl_stream stream);
+
+/*
+ * Start an episode.  episode_start: dev [E] int32 table row of time step 0 of every env, or NULL with
+ * `uniform_start` used for all envs.  episode_time_steps: T (the episode has T-1 steps, citylearn.py:372-376).
+ * obs: dev [E][L] observation at t = 0 (may be NULL).
+ */
+int cl_reset(cl_env* env, const int32_t* episode_start, int32_t uniform_start, int32_t episode_time_steps,
+             float* obs, cl_stream stream);
+
+/*
+ * Advance every env by one time step.
+ *   actions  dev [E][action_dim]      (district action vector: buildings in order, active actions in schema order)
+ *   obs      dev [E][L]               observation at t+1                        (NULL: not materialised)
+ *   reward   dev [E][B] or [E][1]     reward of step t                          (NULL allowed)
+ *   district dev [E][3]               sum over buildings of net, cost, emission (NULL allowed)
+ *   trace    dev [E][B][CL_NDYN]      per-unit values at t                      (NULL allowed)
+ */
+int cl_step(cl_env* env, const float* actions, float* obs, float* reward, float* district, float* trace,
+            cl_stream stream);
+
+/*
+ * K consecutive steps in ONE launch with pre-resident actions (open-loop block / on-device policy output).
+ *   actions dev [K][E][action_dim]; obs dev [K][E][L]; reward dev [K][E][R]; district dev [K][E][3] (NULL allowed each
+ *   except actions).  Equivalent to K calls of cl_step.
+ */
+int cl_rollout(cl_env* env, int32_t n_steps, const float* actions, float* obs, float* reward, float* district,
+               cl_stream stream);
+
+/* Current time step t of the handle (host value; steps done since the last reset). */
+int cl_time_step(const cl_env* env, int32_t* t);
+
+/* Mutable state as an opaque float blob (checkpoint / resume).  cl_state_size returns the number of bytes. */
+int cl_state_size(const cl_env* env, size_t* bytes);
+int cl_get_state(cl_env* env, void* dst_dev, cl_stream stream);
+int cl_set_state(cl_env* env, const void* src_dev, int32_t time_step, cl_stream stream);
+
+/* Number of kernels this library has launched on behalf of `env` since creation (bench.py's gpu_launches). */
+int cl_launch_count(const cl_env* env, int64_t* n);
+
+const char* cl_last_error(void);
+int cl_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CITYLEARN_B200_H */

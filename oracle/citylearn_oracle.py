@@ -173,8 +173,9 @@ class OracleEnv:
         ec_cool = self.col32('C_COOLING_DEMAND', 0) / cop_c
         # quirk: heater-type heating device uses dhw_device.get_input_power (building.py:2632)
         hd_eff = np.where(self.flag(S.F_HEATING_IS_HEAT_PUMP), self.eff_heat('heating', T), self.eff_heat('dhw', T))
-        ec_heat = self.col32('C_HEATING_DEMAND', 0) / hd_eff
-        ec_dhw = self.col32('C_DHW_DEMAND', 0) / self.eff_heat('dhw', T)
+        # np.array(float32) / python-float efficiency and float32 / float32 COP are both float32 divisions
+        ec_heat = self.col32('C_HEATING_DEMAND', 0) / w32(hd_eff)
+        ec_dhw = self.col32('C_DHW_DEMAND', 0) / w32(self.eff_heat('dhw', T))
         ec_nsl = self.col32('C_NSL', 0)
         return [np.broadcast_to(x, (self.E, self.B)).astype(np.float32) for x in (ec_cool, ec_heat, ec_dhw, ec_nsl)]
 

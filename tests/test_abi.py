@@ -1,0 +1,82 @@
+"""The C header, the Python constants and the built library must agree (no GPU needed: nothing is launched)."""
+import ctypes
+import re
+from pathlib import Path
+
+import pytest
+
+from citylearn_b200 import schema as S
+
+ROOT = Path(__file__).resolve().parents[1]
+HEADER = (ROOT / 'include' / 'citylearn_b200.h').read_text()
+
+
+def enum_members(name):
+    body = re.search(r'enum\s+' + name + r'\s*\{(.*?)\}', HEADER, re.S).group(1)
+    body = re.sub(r'/\*.*?\*/', '', body, flags=re.S)
+    out, value = {}, 0
+    for item in body.split(','):
+        item = item.strip()
+        if not item:
+            continue
+        if '=' in item:
+            k, v = [x.strip() for x in item.split('=')]
+            value = int(v, 0)
+        else:
+            k = item
+        out[k] = value
+        value += 1
+    return out
+
+
+def test_param_enums_match_python():
+    p = enum_members('cl_building_param')
+    assert p['CL_NPARAM'] == S.NPARAM
+    for k, v in S.P.items():
+        assert p['CL_P_' + k] == v, k
+    ip = enum_members('cl_building_iparam')
+    assert ip['CL_NIPARAM'] == S.NIPARAM
+    for k, v in S.IP.items():
+        assert ip['CL_IP_' + k] == v, k
+    dyn = enum_members('cl_dyn')
+    assert dyn['CL_NDYN'] == S.NDYN
+    for k, v in S.DYN.items():
+        assert dyn['CL_DYN_' + k.upper()] == v, k
+    kinds = enum_members('cl_obs_kind')
+    assert (kinds['CL_OBS_TS'], kinds['CL_OBS_DYN'], kinds['CL_OBS_OUTAGE']) == (S.OBS_TS, S.OBS_DYN, S.OBS_OUTAGE)
+    assert int(re.search(r'#define CL_MAX_CURVE (\d+)', HEADER).group(1)) == S.MAX_CURVE
+
+
+def test_flag_bits_match_python():
+    for name in ('HEATING_IS_HEAT_PUMP', 'DHW_IS_HEAT_PUMP', 'SIMULATE_OUTAGE', 'DYNAMICS', 'HAS_THERMAL', 'CS_HAS_MAX_IN',
+                 'CS_HAS_MAX_OUT', 'HS_HAS_MAX_IN', 'HS_HAS_MAX_OUT', 'DS_HAS_MAX_IN', 'DS_HAS_MAX_OUT'):
+        shift = int(re.search(r'#define CL_F_' + name + r'\s+\(1 << (\d+)\)', HEADER).group(1))
+        assert getattr(S, 'F_' + name) == 1 << shift
+
+
+def test_library_exports_every_declared_symbol():
+    """`libcitylearn_b200.so` loads on a CPU-only box and exports every entry point the header declares."""
+    from citylearn_b200 import _native, build
+    build.build()
+    lib = ctypes.CDLL(str(_native.library_path()))
+    declared = re.findall(r'^\s*(?:int|const char\*)\s+(cl_\w+)\s*\(', HEADER, re.M)
+    assert len(declared) >= 12
+    for sym in declared:
+        assert hasattr(lib, sym), sym
+    lib.cl_abi_version.restype = ctypes.c_int
+    assert lib.cl_abi_version() == _native.ABI_VERSION
+
+
+def test_descriptor_struct_layout():
+    from citylearn_b200._native import DistrictDesc
+    # 12 int32 + 8 double + 5 pointers, no padding surprises
+    assert ctypes.sizeof(DistrictDesc) == 12 * 4 + 8 * 8 + 5 * 8
+
+
+def test_product_fails_loudly_without_cuda():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('CUDA present')
+    from citylearn_b200 import CityLearnEnv
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        CityLearnEnv('citylearn_challenge_2022_phase_1')

@@ -1,0 +1,238 @@
+"""GPU parity tests (run on the B200 box: `pytest -m gpu`).  Everything goes through the C ABI (ctypes -> libcitylearn_b200.so).
+
+* fp64 precision (default): bit-exact physics vs the golden traces recorded from the unmodified reference and vs the oracle;
+* fp32 precision: within 1e-4 scaled-relative of the oracle (DESIGN.md 'Numerics');
+* size-independent properties at BASELINE.json's full size (17 x 4096): env independence, determinism, rollout == steps.
+"""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip('torch')
+
+from citylearn_b200 import schema as S                      # noqa: E402
+from citylearn_b200.schema import DYN                       # noqa: E402
+from helpers import (TRACE_TO_DYN, actions_of, load_golden, max_abs_diff, observation_scales, schema_for,  # noqa: E402
+                     within_scaled_tolerance)
+
+pytestmark = pytest.mark.gpu
+
+NON_LSTM_CASES = ['c1_phase1_300', 'c1_phase1_central', 'c1_episodes', 'c2_marl', 'c2_isac', 'c2_solar_penalty', 'c2_central_exp2', 'c2_year']
+
+
+def make_env(cfg, **kw):
+    from citylearn_b200 import CityLearnEnv
+    sch, src, ov = schema_for(cfg)
+    return CityLearnEnv(sch, data_source=src, **ov, **kw)
+
+
+@pytest.mark.parametrize('case', NON_LSTM_CASES)
+def test_single_env_matches_reference_traces(case):
+    """num_envs=1, nested-list actions, fp64 flow: observations / district / physics identical to the reference run."""
+    z, cfg, meta = load_golden(case)
+    env = make_env(cfg, num_envs=1, debug_trace=True)
+    tn = cfg['trace_names']
+    acts = actions_of(z)
+    sizes = [len(b.active_actions) for b in env.spec.buildings]
+    gi = 0
+    for ep in range(cfg['episodes']):
+        obs, _ = env.reset()
+        assert [env.episode_tracker.episode_start_time_step, env.episode_tracker.episode_end_time_step] == z['episode_window'][ep].tolist()
+        flat = np.array([v for row in obs for v in row], dtype='float32')
+        assert max_abs_diff(flat, z['reset_obs'][ep]) == 0.0
+        K = acts.shape[1]
+        for k in range(K):
+            a = [float(x) for x in acts[ep, k]]
+            if env.central_agent:
+                nested = [a]
+            else:
+                nested, o = [], 0
+                for s in sizes:
+                    nested.append(a[o:o + s])
+                    o += s
+            obs, rew, term, trunc, info = env.step(nested)
+            if gi < len(z['steps']) and z['steps'][gi] == k and z['episode'][gi] == ep:
+                flat = np.array([v for row in obs for v in row], dtype='float32')
+                assert max_abs_diff(flat, z['obs'][gi]) == 0.0, f'obs step {k}'
+                r = np.array(rew, dtype='float32')
+                ok, w = within_scaled_tolerance(r, z['reward'][gi], 1.0, rtol=2e-7)
+                assert ok, f'reward step {k}: {w}'
+                assert max_abs_diff(env.district[0].cpu().numpy(), z['district'][gi]) == 0.0, f'district step {k}'
+                tr = env.trace[0].cpu().numpy()
+                for gn, dn in TRACE_TO_DYN.items():
+                    tol = 3e-7 if gn == 'electrical_storage_degraded_capacity' else 0.0
+                    assert max_abs_diff(tr[:, DYN[dn]], z['trace'][gi, :, tn.index(gn)]) <= tol, f'{gn} step {k}'
+                assert term == bool(z['terminated'][gi])
+                gi += 1
+        assert env.terminated == (K == env.time_steps - 1)
+    assert gi == len(z['steps'])
+    if 'episode_reward_sum' in z.files and cfg['episodes'] == 1:
+        np.testing.assert_allclose(env.episode_rewards[-1]['sum'], z['episode_reward_sum'], rtol=2e-5)
+    assert env.gpu_launches > 0
+
+
+@pytest.mark.parametrize('precision,rtol', [('fp64', 0.0), ('fp32', 1e-4)])
+def test_batched_distinct_actions_match_oracle(precision, rtol):
+    """64 envs x 17 buildings with different action sequences vs the vectorised oracle, 150 steps."""
+    from citylearn_b200 import CityLearnEnv
+    from citylearn_oracle import OracleEnv
+    E, K = 64, 150
+    env = CityLearnEnv('citylearn_challenge_2022_phase_all', num_envs=E, precision=precision, debug_trace=True)
+    oracle = OracleEnv(env.spec, E)
+    obs0 = oracle.reset()
+    o, _ = env.reset()
+    assert max_abs_diff(o.cpu().numpy(), obs0.astype('float32')) == 0.0
+    rng = np.random.RandomState(11)
+    scales = observation_scales(env.spec, env._entries)
+    worst = 0.0
+    for k in range(K):
+        a = rng.uniform(-1, 1, size=(E, env.spec.action_dim)).astype('float32')
+        obs, rew, term, _, _ = env.step(torch.from_numpy(a).cuda())
+        oobs, orew, odist, odyn = oracle.step(a)
+        assert max_abs_diff(obs.cpu().numpy(), oobs) == 0.0           # stale observations are exogenous: always exact
+        tr = env.trace.cpu().numpy()
+        if rtol == 0.0:
+            assert np.array_equal(rew.cpu().numpy(), orew)
+            assert np.array_equal(env.district.cpu().numpy(), odist)
+            for n in ('electrical_storage_soc', 'electrical_storage_energy_balance', 'net_electricity_consumption',
+                      'net_electricity_consumption_cost', 'net_electricity_consumption_emission'):
+                assert np.array_equal(tr[..., DYN[n]], odyn[..., DYN[n]].astype('float32')), (n, k)
+        else:
+            for n, sc in (('electrical_storage_soc', 1.0), ('net_electricity_consumption', 20.0), ('electrical_storage_energy_balance', 10.0)):
+                ok, w = within_scaled_tolerance(tr[..., DYN[n]], odyn[..., DYN[n]], sc, rtol)
+                worst = max(worst, w)
+                assert ok, (n, k, w)
+            ok, w = within_scaled_tolerance(rew.cpu().numpy(), orew, 20.0, rtol)
+            assert ok, ('reward', k, w)
+
+
+def test_full_size_envs_are_independent_and_deterministic():
+    """BASELINE configs[1] size (17 x 4096): identical actions -> identical envs; interleaved distinct envs unaffected; repeatable."""
+    from citylearn_b200 import CityLearnEnv
+    E, K = 4096, 40
+    z, cfg, _ = load_golden('c2_year')
+    acts = actions_of(z)[0][:K]
+    env = CityLearnEnv('citylearn_challenge_2022_phase_all', num_envs=E, debug_trace=True)
+    rng = np.random.RandomState(3)
+    odd = rng.uniform(-1, 1, size=(K, E // 2, env.spec.action_dim)).astype('float32')
+    results = []
+    for rep in range(2):
+        env.reset()
+        rsum = torch.zeros((E, 17), device='cuda')
+        gi = 0
+        for k in range(K):
+            a = np.repeat(acts[k][None], E, axis=0)
+            a[1::2] = odd[k]                       # odd envs get their own actions, even envs replay the golden sequence
+            obs, rew, term, _, _ = env.step(torch.from_numpy(a).cuda())
+            rsum += rew
+            even = rew[0::2]
+            assert torch.equal(even, even[0:1].expand_as(even))
+            if z['steps'][gi] == k:
+                ok, w = within_scaled_tolerance(rew[0].cpu().numpy(), z['reward'][gi], 1.0, rtol=2e-7)
+                assert ok
+                assert max_abs_diff(obs[0].cpu().numpy(), z['obs'][gi]) == 0.0
+                assert max_abs_diff(env.district[0].cpu().numpy(), z['district'][gi]) == 0.0
+                gi += 1
+        results.append(rsum.cpu().numpy())
+    assert np.array_equal(results[0], results[1])
+    assert not np.array_equal(results[0][0], results[0][1])
+
+
+def test_per_env_episode_start_matches_oracle():
+    from citylearn_b200 import CityLearnEnv
+    from citylearn_oracle import OracleEnv
+    E, K = 8, 60
+    env = CityLearnEnv('citylearn_challenge_2022_phase_1', num_envs=E, debug_trace=True, simulation_start_time_step=0,
+                       simulation_end_time_step=4999, episode_time_steps=500)
+    starts = np.array([0, 500, 1000, 1500, 24, 2500, 3000, 4500], dtype='int32')
+    oracle = OracleEnv(env.spec, E)
+    oobs = oracle.reset(starts, 500)
+    obs, _ = env.reset(options={'episode_start': torch.from_numpy(starts)})
+    assert max_abs_diff(obs.cpu().numpy(), oobs.astype('float32')) == 0.0
+    rng = np.random.RandomState(2)
+    for k in range(K):
+        a = rng.uniform(-1, 1, size=(E, env.spec.action_dim)).astype('float32')
+        obs, rew, _, _, _ = env.step(a)
+        oobs, orew, odist, odyn = oracle.step(a)
+        assert max_abs_diff(obs.cpu().numpy(), oobs) == 0.0
+        assert np.array_equal(rew.cpu().numpy(), orew)
+
+
+def test_fresh_observations_mode_carries_post_action_values():
+    from citylearn_b200 import CityLearnEnv
+    from citylearn_oracle import OracleEnv
+    E = 4
+    env = CityLearnEnv('citylearn_challenge_2022_phase_1', num_envs=E, stale_observations=False)
+    oracle = OracleEnv(env.spec, E, stale_observations=False)
+    oracle.reset()
+    env.reset()
+    rng = np.random.RandomState(4)
+    names = [n for _, n in env._entries]
+    j = names.index('electrical_storage_soc')
+    for k in range(20):
+        a = rng.uniform(-1, 1, size=(E, env.spec.action_dim)).astype('float32')
+        obs, _, _, _, _ = env.step(a)
+        oobs, _, _, _ = oracle.step(a)
+        assert max_abs_diff(obs.cpu().numpy(), oobs) == 0.0
+    assert float(obs[:, j].abs().sum()) > 0.0
+
+
+def test_rollout_equals_steps_and_checkpoint_roundtrip():
+    from citylearn_b200 import CityLearnEnv
+    E, K = 256, 24
+    env = CityLearnEnv('citylearn_challenge_2022_phase_all', num_envs=E)
+    g = torch.Generator(device='cuda').manual_seed(0)
+    acts = torch.rand((K, E, env.spec.action_dim), device='cuda', generator=g) * 2 - 1
+    env.reset()
+    for k in range(5):
+        env.step(acts[k])
+    sd = env.state_dict()
+    step_obs, step_rew = [], []
+    for k in range(5, K):
+        o, r, _, _, _ = env.step(acts[k])
+        step_obs.append(o.clone())
+        step_rew.append(r.clone())
+    env.load_state_dict(sd)
+    assert env.time_step == 5
+    obs = torch.empty((K - 5, E, env._obs_dim), device='cuda')
+    rew = torch.empty((K - 5, E, 17), device='cuda')
+    dist = torch.empty((K - 5, E, 3), device='cuda')
+    env.rollout(acts[5:].contiguous(), obs, rew, dist)
+    assert env.time_step == K
+    assert torch.equal(obs, torch.stack(step_obs))
+    assert torch.equal(rew, torch.stack(step_rew))
+
+
+def test_host_path_and_python_reward_fallback():
+    from citylearn_b200 import CityLearnEnv
+    from citylearn_b200.reward_function import RewardFunction
+
+    class MyReward(RewardFunction):          # same formula as the default, but a subclass -> Python tensor path
+        def calculate(self, observations):
+            return [-torch.clamp(o['net_electricity_consumption'], min=0.0) for o in observations]
+
+    E = 32
+    fused = CityLearnEnv('citylearn_challenge_2022_phase_1', num_envs=E)
+    custom = CityLearnEnv('citylearn_challenge_2022_phase_1', num_envs=E, reward_function=MyReward)
+    assert custom._reward_id == -1 and fused._reward_id == 0
+    fused.reset(); custom.reset()
+    rng = np.random.RandomState(9)
+    for k in range(10):
+        a = rng.uniform(-1, 1, size=(E, 5)).astype('float32')
+        o1, r1, t1 = fused.step_host(a)
+        o2, r2, _, _, _ = custom.step(a)
+        assert np.array_equal(o1, o2.cpu().numpy())
+        assert np.array_equal(r1, r2.cpu().numpy())
+
+
+def test_error_paths():
+    from citylearn_b200 import CityLearnEnv
+    env = CityLearnEnv('citylearn_challenge_2022_phase_1', num_envs=2, simulation_end_time_step=9)
+    env.reset()
+    for _ in range(9):
+        env.step(np.zeros((2, 5), dtype='float32'))
+    assert env.terminated
+    with pytest.raises(RuntimeError):
+        env.step(np.zeros((2, 5), dtype='float32'))
+    with pytest.raises(ValueError):
+        env.reset()
+        env.step([[0.0]] * 5)      # nested lists need num_envs == 1

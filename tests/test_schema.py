@@ -1,0 +1,72 @@
+"""Host loader vs metadata recorded from the unmodified reference (tests/golden/*.npz 'meta')."""
+import numpy as np
+import pytest
+
+from citylearn_b200 import schema as S
+from helpers import golden_cases, load_golden, spec_for
+
+
+@pytest.mark.parametrize('case', golden_cases())
+def test_names_spaces_and_devices_match_reference(case):
+    z, cfg, meta = load_golden(case)
+    spec = spec_for(cfg)
+    entries, desc = S.observation_layout(spec)
+    assert [n for _, n in entries] == [n for row in meta['observation_names'] for n in row]
+    assert spec.central_agent == meta['central_agent']
+    assert spec.shared_observations == meta['shared_observations']
+    for b, mb in zip(spec.buildings, meta['buildings']):
+        assert b.name == mb['name']
+        assert b.active_observations == mb['active_observations']
+        assert b.active_actions == mb['active_actions']
+        np.testing.assert_allclose(b.observation_low, mb['observation_low'], rtol=1e-6, equal_nan=True)
+        np.testing.assert_allclose(b.observation_high, mb['observation_high'], rtol=1e-6, equal_nan=True)
+        np.testing.assert_allclose(b.action_low, mb['action_low'], rtol=1e-6)
+        np.testing.assert_allclose(b.action_high, mb['action_high'], rtol=1e-6)
+        bat, mbat = b.devices['electrical_storage'], mb['electrical_storage']
+        # md5-seeded stochastic defaults (citylearn/citylearn.py:2364-2378, energy_model.py:977-1003)
+        np.testing.assert_allclose(bat['power_efficiency_curve'], mbat['power_efficiency_curve'], rtol=1e-13)
+        np.testing.assert_allclose(bat['capacity_power_curve'], mbat['capacity_power_curve'], rtol=1e-13)
+        for k in ('capacity', 'nominal_power', 'depth_of_discharge', 'capacity_loss_coefficient', 'initial_soc'):
+            assert bat[k] == pytest.approx(mbat[k], rel=1e-13)
+        for dn in ('cooling_storage', 'heating_storage', 'dhw_storage', 'cooling_device', 'heating_device', 'dhw_device'):
+            if b.devices[dn].get('absent'):
+                continue          # absent devices get unreproducible random parameters in the reference
+            for k, v in b.devices[dn].items():
+                if k in mb[dn] and isinstance(v, float):
+                    assert v == pytest.approx(mb[dn][k], rel=1e-13), (dn, k)
+
+
+def test_device_seed_known_answer():
+    # 2022 Building_1 battery, schema seed 2022 -> 135823784 -> u = 0.5803480936676708
+    seed = S.device_random_seed('Building_1', 'citylearn.citylearn.Building', 'electrical_storage', 'citylearn.energy_model.Battery', 2022)
+    assert seed == 135823784
+    assert np.random.RandomState(seed).uniform() == pytest.approx(0.5803480936676708, rel=1e-15)
+
+
+def test_episode_windows_match_reference():
+    z, cfg, meta = load_golden('c1_episodes')
+    spec = spec_for(cfg)
+    tr = S.EpisodeTracker(spec.simulation_start_time_step, spec.simulation_end_time_step)
+    for ep in range(cfg['episodes']):
+        tr.next_episode(spec.episode_time_steps, spec.rolling_episode_split, spec.random_episode_split, spec.random_seed)
+        assert [tr.episode_start_time_step, tr.episode_end_time_step] == z['episode_window'][ep].tolist()
+
+
+def test_unsupported_features_fail_loudly():
+    from citylearn_b200.data import DataSet
+    src = DataSet.get_source('citylearn_challenge_2022_phase_1')
+    sch = src.schema()
+    sch['buildings']['Building_1']['chargers'] = {'c1': {}}
+    with pytest.raises(S.UnsupportedSchemaError):
+        S.load(sch, data_source=src)
+    with pytest.raises(S.UnknownSchemaError):
+        S.load('no_such_dataset')
+
+
+def test_table_layout():
+    spec = S.load('citylearn_challenge_2022_phase_all')
+    assert spec.table.dtype == np.float32 and spec.table.shape[0] == 8760
+    assert spec.params.shape == (17, S.NPARAM) and spec.iparams.shape == (17, S.NIPARAM)
+    assert spec.action_dim == 17
+    # shared weather / pricing series are stored once
+    assert spec.columns[(0, 'outdoor_dry_bulb_temperature')] == spec.columns[(16, 'outdoor_dry_bulb_temperature')]
