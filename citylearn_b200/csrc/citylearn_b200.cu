@@ -16,6 +16,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -343,7 +344,8 @@ __device__ __forceinline__ void write_obs_template(const Dev& d, float* obs, int
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// shared memory carve-up (dynamic): [mbarrier 16B][rows 2*Wp][tmpl Lp][red 4*nthreads][dsum 4*epb][dynbuf (optional)]
+// shared memory carve-up (dynamic): [mbarriers 32B][rows 3*Wp][tmpl Lp][red 4*nthreads][dsum 4*epb][dynbuf (optional)]
+// (the step kernel uses rows[0..1] and one barrier; the rollout kernel uses a 3-row ring with one barrier per slot)
 // ------------------------------------------------------------------------------------------------------------------
 struct Smem {
     uint64_t* bar;
@@ -356,8 +358,8 @@ struct Smem {
 __device__ __forceinline__ Smem carve(const Dev& d, unsigned char* base, int nthreads) {
     Smem s;
     s.bar = reinterpret_cast<uint64_t*>(base);
-    float* f = reinterpret_cast<float*>(base + 16);
-    s.rows = f; f += 2 * d.Wp;
+    float* f = reinterpret_cast<float*>(base + 32);
+    s.rows = f; f += 3 * d.Wp;
     s.tmpl = f; f += (d.L + 3) & ~3;
     s.red = f; f += 4 * nthreads;
     s.dsum = f; f += 4 * d.envs_per_block;
@@ -365,7 +367,7 @@ __device__ __forceinline__ Smem carve(const Dev& d, unsigned char* base, int nth
     return s;
 }
 static size_t smem_bytes(const Dev& d, int nthreads, bool with_dyn) {
-    size_t n = 16 + sizeof(float) * (2 * (size_t)d.Wp + ((d.L + 3) & ~3) + 4 * (size_t)nthreads + 4 * (size_t)d.envs_per_block);
+    size_t n = 32 + sizeof(float) * (3 * (size_t)d.Wp + ((d.L + 3) & ~3) + 4 * (size_t)nthreads + 4 * (size_t)d.envs_per_block);
     if (with_dyn) n += sizeof(float) * (size_t)nthreads * CL_NDYN;
     return n;
 }
@@ -500,6 +502,155 @@ __global__ void __launch_bounds__(MAXT) step_kernel(Dev d, int t, const float* _
             write_obs_general(d, obs, e0, n_env, t + 1, want_dyn ? sm.dynbuf : nullptr);
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// rollout kernel: K consecutive steps in one launch.  State and parameters live in registers for the whole block of
+// steps; per step a thread reads its action(s), the block reduces the district sums in shared memory and streams out the
+// reward and observation slabs.  The time rows ride a 3-slot TMA ring (row t+2 is prefetched while step t computes).
+// ------------------------------------------------------------------------------------------------------------------
+template <typename R, bool THERMAL>
+__device__ __forceinline__ void reward_inputs(const Dev& d, const BuildingParams<R>& p, const UnitState<R>& s, const UnitResult<R>& o,
+                                              const UnitInputs<R>& in, const float* row, int b, float t_in, float district_net, RewardIn& ri) {
+    const int B = d.B;
+    ri.net = (float)o.net; ri.district_net = district_net;
+    ri.soc_b = (float)s.soc_b; ri.soc_cs = (float)s.soc_cs; ri.soc_hs = (float)s.soc_hs; ri.soc_ds = (float)s.soc_ds;
+    ri.cap_b = (float)p.bat_capacity;
+    if (THERMAL) {
+        ri.cap_cs = (float)p.cs.capacity; ri.cap_hs = (float)p.hs.capacity; ri.cap_ds = (float)p.ds.capacity;
+        ri.cool_dem = (float)(o.e_from_cool + fabs(rmin(o.eb_cs, (R)0)));
+        ri.heat_dem = (float)(o.e_from_heat + fabs(rmin(o.eb_hs, (R)0)));
+    } else { ri.cap_cs = ri.cap_hs = ri.cap_ds = 0.f; ri.cool_dem = ri.heat_dem = 0.f; }
+    ri.hvac_mode = in.hvac_mode;
+    ri.t_in = t_in;
+    if (d.reward_id == CL_REWARD_COMFORT || d.reward_id == CL_REWARD_SOLAR_PENALTY_AND_COMFORT) {
+        ri.cool_sp = row[__ldg(d.ip + CL_IP_C_COOL_SP * B + b)];
+        ri.heat_sp = row[__ldg(d.ip + CL_IP_C_HEAT_SP * B + b)];
+        ri.band_series = row[__ldg(d.ip + CL_IP_C_COMFORT_BAND * B + b)];
+        ri.hvac_mode = (int)row[__ldg(d.ip + CL_IP_C_HVAC_MODE * B + b)];
+    } else { ri.cool_sp = ri.heat_sp = ri.band_series = 0.f; }
+}
+
+template <typename R, bool THERMAL, int MAXT>
+__global__ void __launch_bounds__(MAXT) rollout_kernel(Dev d, int t0, int K, const float* __restrict__ actions, float* __restrict__ obs,
+                                                        float* __restrict__ reward, float* __restrict__ district) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int nt = blockDim.x, tid = threadIdx.x;
+    Smem sm = carve(d, smem_raw, nt);
+    const int B = d.B, epb = d.envs_per_block, Wp = d.Wp;
+    const int e0 = blockIdx.x * epb;
+    const int n_env = min(epb, d.E - e0);
+    const int n_units = n_env * B;
+    const bool active = tid < n_units;
+    const int e_l = tid / B, b = tid - e_l * B;
+    const int e = e0 + e_l, u = e * B + b;
+    const bool uniform = d.uniform_start != 0;
+    const bool want_dyn = (!d.stale && obs != nullptr);
+    const int Rdim = d.central ? 1 : B;
+    const uint32_t row_bytes = (uint32_t)Wp * sizeof(float);
+
+    if (uniform && tid == 0) {
+        for (int i = 0; i < 3; ++i) mbar_init(sm.bar + i, 1);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        for (int i = 0; i < 3 && i <= K; ++i) {     // rows t0 .. t0+2 (row t0+K is the last one any step needs)
+            mbar_expect_tx(sm.bar + i, row_bytes);
+            tma_load_1d(sm.rows + i * Wp, d.table + (size_t)(d.start0 + t0 + i) * Wp, row_bytes, sm.bar + i);
+        }
+    }
+    BuildingParams<R> p;
+    UnitState<R> s;
+    const auto* curves = PSel<R>::p(d) + CL_P_PE_X0 * B + (active ? b : 0);
+    int start_e = 0;
+    if (active) {
+        load_params<R, THERMAL>(d, b, p);
+        load_state<R, THERMAL>(d, u, s);
+        start_e = __ldg(d.start + e);
+    }
+    __syncthreads();   // barriers initialised before anyone waits on them
+
+    for (int k = 0; k < K; ++k) {
+        const int t = t0 + k;
+        const int slot_t = k % 3, slot_n = (k + 1) % 3;
+        const float* row;
+        const float* row_next = nullptr;
+        if (uniform) {
+            mbar_wait(sm.bar + slot_t, (uint32_t)((k / 3) & 1));
+            mbar_wait(sm.bar + slot_n, (uint32_t)(((k + 1) / 3) & 1));
+            row = sm.rows + slot_t * Wp;
+            row_next = sm.rows + slot_n * Wp;
+        } else {
+            row = d.table + (size_t)(start_e + t) * Wp;
+        }
+        UnitResult<R> o;
+        UnitInputs<R> in;
+        float t_in = 0.f;
+        if (active) {
+            load_inputs<R, THERMAL>(d, row, b, t, in);
+            load_actions<R, THERMAL>(d, actions + ((size_t)k * d.E + e) * d.A, b, in);
+            unit_step<R, THERMAL>(p, curves, B, t, in, s, o);
+            t_in = row[__ldg(d.ip + CL_IP_C_T_IN * B + b)];
+            sm.red[tid] = (float)o.net;
+            sm.red[nt + tid] = (float)o.cost;
+            sm.red[2 * nt + tid] = (float)o.emission;
+            if (want_dyn) fill_dyn<R>(p, s, o, (R)t_in, sm.dynbuf + tid * CL_NDYN);
+        }
+        __syncthreads();                                                       // S1
+        if (uniform && tid == 0 && k >= 1 && k + 2 <= K) {
+            // every thread has left step k-1: its row slot ((k-1) % 3) is free -> prefetch row t0 + k + 2 into it
+            const int sl = (k + 2) % 3;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_expect_tx(sm.bar + sl, row_bytes);
+            tma_load_1d(sm.rows + sl * Wp, d.table + (size_t)(d.start0 + t0 + k + 2) * Wp, row_bytes, sm.bar + sl);
+        }
+        if (tid < n_env) {
+            float sn = 0.f, sc = 0.f, se = 0.f;
+            for (int j = 0; j < B; ++j) {
+                sn += sm.red[tid * B + j];
+                sc += sm.red[nt + tid * B + j];
+                se += sm.red[2 * nt + tid * B + j];
+            }
+            sm.dsum[tid * 4 + 0] = sn;
+            if (district != nullptr) {
+                float* dp = district + ((size_t)k * d.E + e0 + tid) * 3;
+                dp[0] = sn; dp[1] = sc; dp[2] = se;
+            }
+        }
+        const bool tmpl_path = obs != nullptr && uniform && d.stale;
+        if (tmpl_path) build_obs_template(d, row_next, t + 1, sm.tmpl);
+        __syncthreads();                                                       // S2
+        if (reward != nullptr && d.reward_id >= 0) {
+            float r = 0.f;
+            if (active) {
+                RewardIn ri;
+                reward_inputs<R, THERMAL>(d, p, s, o, in, row, b, t_in, sm.dsum[e_l * 4], ri);
+                r = unit_reward(d.reward_id, d.rp, ri);
+            }
+            float* rk = reward + (size_t)k * d.E * Rdim;
+            if (d.central) {
+                sm.red[3 * nt + tid] = r;
+                __syncthreads();
+                if (tid < n_env) {
+                    float sr = 0.f;
+                    if (d.reward_id == CL_REWARD_MARL || d.reward_id == CL_REWARD_SOLAR_PENALTY_AND_COMFORT) {
+                        double acc = 0.0;
+                        for (int j = 0; j < B; ++j) acc += (double)sm.red[3 * nt + tid * B + j];
+                        sr = (float)acc;
+                    } else {
+                        for (int j = 0; j < B; ++j) sr += sm.red[3 * nt + tid * B + j];
+                    }
+                    rk[e0 + tid] = sr;
+                }
+            } else if (active) {
+                rk[u] = r;
+            }
+        }
+        if (obs != nullptr) {
+            float* ok = obs + (size_t)k * d.E * d.L;
+            if (tmpl_path) write_obs_template(d, ok, e0, n_env, sm.tmpl);
+            else write_obs_general(d, ok, e0, n_env, t + 1, want_dyn ? sm.dynbuf : nullptr);
+        }
+    }
+    if (active) store_state<R, THERMAL>(d, u, s);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -647,8 +798,12 @@ extern "C" int cl_create(const cl_district_desc* desc, cl_env** out) {
         if (cudaMalloc(&p, (size_t)d.E * sizeof(int32_t)) != cudaSuccess) { cl_destroy(env); return fail(CL_ERR_CUDA, "cl_create: start allocation failed"); }
         env->allocs.push_back(p); d.start = static_cast<int32_t*>(p);
     }
-    // launch geometry: as many whole envs per block as fit ~256 threads
-    int epb = 256 / B;
+    // launch geometry: as many whole envs per block as fit the target block size.  The step path is latency-bound at the
+    // benchmark sizes (a few warps per scheduler), so SMALL blocks win: one warp per block turns the block barriers into
+    // warp barriers and lets idle lanes buy more resident warps (profiles/README.md).  CL_B200_BLOCK_THREADS overrides.
+    int target = 32;
+    if (const char* ev = std::getenv("CL_B200_BLOCK_THREADS")) { const int v = std::atoi(ev); if (v >= 32 && v <= 1024) target = v; }
+    int epb = target / B;
     if (epb < 1) epb = 1;
     if (epb > d.E) epb = d.E;
     d.envs_per_block = epb;
@@ -660,6 +815,7 @@ extern "C" int cl_create(const cl_district_desc* desc, cl_env** out) {
 #define OPTIN(K) cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
 #define OPTIN4(K, M) OPTIN((K<float, false, M>)); OPTIN((K<float, true, M>)); OPTIN((K<double, false, M>)); OPTIN((K<double, true, M>))
     OPTIN4(step_kernel, 512); OPTIN4(step_kernel, 1024); OPTIN4(reset_kernel, 512); OPTIN4(reset_kernel, 1024);
+    OPTIN4(rollout_kernel, 512); OPTIN4(rollout_kernel, 1024);
 #undef OPTIN4
 #undef OPTIN
     cudaError_t e = cudaGetLastError();
@@ -707,6 +863,14 @@ static void launch_step(cl_env* env, const float* actions, float* obs, float* re
     const size_t smem = smem_bytes(env->d, env->threads, want_dyn);
     if (env->threads <= 512) step_kernel<R, TH, 512><<<env->blocks, env->threads, smem, st>>>(env->d, env->t, actions, obs, reward, district, trace);
     else step_kernel<R, TH, 1024><<<env->blocks, env->threads, smem, st>>>(env->d, env->t, actions, obs, reward, district, trace);
+}
+
+template <typename R, bool TH>
+static void launch_rollout(cl_env* env, int K, const float* actions, float* obs, float* reward, float* district, cudaStream_t st) {
+    const bool want_dyn = !env->d.stale && obs != nullptr;
+    const size_t smem = smem_bytes(env->d, env->threads, want_dyn);
+    if (env->threads <= 512) rollout_kernel<R, TH, 512><<<env->blocks, env->threads, smem, st>>>(env->d, env->t, K, actions, obs, reward, district);
+    else rollout_kernel<R, TH, 1024><<<env->blocks, env->threads, smem, st>>>(env->d, env->t, K, actions, obs, reward, district);
 }
 
 __global__ void fill_start_kernel(int32_t* start, int n, int v) {
@@ -763,13 +927,17 @@ extern "C" int cl_rollout(cl_env* env, int32_t n_steps, const float* actions, fl
     if (n_steps < 1) return fail(CL_ERR_INVALID, "cl_rollout: n_steps must be >= 1");
     if (env->t < 0) return fail(CL_ERR_STATE, "cl_rollout: call cl_reset first");
     if (env->t + n_steps > env->T - 1) return fail(CL_ERR_STATE, "cl_rollout: block runs past the end of the episode");
-    const Dev& d = env->d;
-    const int R_ = d.central ? 1 : d.B;
-    for (int k = 0; k < n_steps; ++k) {   // first version: K launches (a fused persistent kernel replaces this loop)
-        int rc = cl_step(env, actions + (size_t)k * d.E * d.A, obs ? obs + (size_t)k * d.E * d.L : nullptr,
-                         reward ? reward + (size_t)k * d.E * R_ : nullptr, district ? district + (size_t)k * d.E * 3 : nullptr, nullptr, stream);
-        if (rc) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (env->precision == CL_PRECISION_FP64) {
+        if (env->thermal) launch_rollout<double, true>(env, n_steps, actions, obs, reward, district, st);
+        else launch_rollout<double, false>(env, n_steps, actions, obs, reward, district, st);
+    } else {
+        if (env->thermal) launch_rollout<float, true>(env, n_steps, actions, obs, reward, district, st);
+        else launch_rollout<float, false>(env, n_steps, actions, obs, reward, district, st);
     }
+    env->launches++;
+    CUDA_TRY(cudaGetLastError());
+    env->t += n_steps;
     return CL_OK;
 }
 
