@@ -5,11 +5,13 @@
 //                                     rows of step t and t+1 are ONE contiguous, 16B-aligned span -> a single TMA bulk copy
 //   params   float / double [CL_NPARAM][B]   parameter-major so that the B buildings of a warp read consecutive words
 //   iparams  int32  [CL_NIPARAM][B]
-//   obs_desc int4   [L]
+//   obs_desc int4   [L]  (+ tcol int32 [L]: the same layout compiled to "template columns" for the fast path)
 //   outage   float  [B][T]            power-outage signal of the running episode
 //   start    int32  [E]               table row of time step 0 of every env
 //   state    float  [6][E*B]  (+ double [2][E*B] in CL_PRECISION_FP64)   unit index u = e * B + b (building fastest)
 //
+// Kernels: `advance_kernel` (K >= 1 consecutive time steps in one launch: cl_step is K = 1, cl_rollout any K) and
+// `reset_kernel`.
 // Thread mapping: one thread per unit; a block owns `envs_per_block` consecutive envs x all B buildings, so its slice of
 // actions [E][A], rewards [E][B], state [.][E*B] and observations [E][L] is one contiguous range each (coalesced), and the
 // district sums of an env never leave the block (shared memory, summed in building order like the reference's sum()).
@@ -38,29 +40,47 @@ struct Dev {
     const double* pd;      // [NPARAM][B]
     const int32_t* ip;     // [NIPARAM][B]
     const int4* desc;      // [L]
+    const int32_t* tcol;   // [L] >= 0: table column, -1: zero (stale DYN slot), <= -2: outage signal of building (-2 - tcol)
     const float* outage;   // [B][T] or nullptr
     const int32_t* start;  // [E]
     float* st;             // [6][U]
     double* dst;           // [2][U] (fp64 mode)
 };
 
-enum { ST_SOC_B = 0, ST_CAP_DEG = 1, ST_EFF_B = 2, ST_SOC_CS = 3, ST_SOC_HS = 4, ST_SOC_DS = 5, ST_N = 6 };
+enum { ST_SOC_B = 0, ST_CAP_DEG = 1, ST_RTE_B = 2, ST_SOC_CS = 3, ST_SOC_HS = 4, ST_SOC_DS = 5, ST_N = 6 };
 
 template <typename R> struct PSel;
 template <> struct PSel<float> { static __device__ __forceinline__ const float* p(const Dev& d) { return d.pf; } };
 template <> struct PSel<double> { static __device__ __forceinline__ const double* p(const Dev& d) { return d.pd; } };
 
+// per-thread launch constants: the unit's building parameters, table columns and action slots (registers)
+template <typename R> struct UnitCtx {
+    BuildingParams<R> p;
+    R pv;
+    int c_nsl, c_solar, c_price, c_carbon, c_tin;
+    int a_es;
+    int c_dhw, c_cool, c_heat, c_tout, c_hvac;
+    int a_cd, a_hd, a_coh, a_cs, a_hs, a_ds;
+    int c_coolsp, c_heatsp, c_band;
+};
+
 template <typename R, bool THERMAL>
-__device__ __forceinline__ void load_params(const Dev& d, int b, BuildingParams<R>& p) {
+__device__ __forceinline__ void load_ctx(const Dev& d, int b, UnitCtx<R>& c) {
     const auto* P = PSel<R>::p(d);
     const int B = d.B;
+    BuildingParams<R>& p = c.p;
 #define LD(k) ((R)__ldg(P + (k) * B + b))
+#define LDI(k) (__ldg(d.ip + (k) * B + b))
     p.bat_capacity = LD(CL_P_BAT_CAPACITY); p.bat_pnom = LD(CL_P_BAT_NOMINAL_POWER); p.bat_loss = LD(CL_P_BAT_LOSS);
     p.bat_clc = LD(CL_P_BAT_CLC); p.bat_dod = LD(CL_P_BAT_DOD);
     p.ratio = LD(CL_P_TIME_STEP_RATIO); p.hours = LD(CL_P_HOURS_PER_STEP);
-    p.flags = __ldg(d.ip + CL_IP_FLAGS * B + b);
-    p.pe_n = __ldg(d.ip + CL_IP_PE_N * B + b);
-    p.cp_n = __ldg(d.ip + CL_IP_CP_N * B + b);
+    p.flags = LDI(CL_IP_FLAGS); p.pe_n = LDI(CL_IP_PE_N); p.cp_n = LDI(CL_IP_CP_N);
+    c.pv = LD(CL_P_PV_NOMINAL_POWER);
+    c.c_nsl = LDI(CL_IP_C_NSL); c.c_solar = LDI(CL_IP_C_SOLAR); c.c_price = LDI(CL_IP_C_PRICE); c.c_carbon = LDI(CL_IP_C_CARBON);
+    c.c_tin = LDI(CL_IP_C_T_IN);
+    c.a_es = LDI(CL_IP_A_ELECTRICAL_STORAGE);
+    c.c_coolsp = LDI(CL_IP_C_COOL_SP); c.c_heatsp = LDI(CL_IP_C_HEAT_SP); c.c_band = LDI(CL_IP_C_COMFORT_BAND);
+    c.c_hvac = LDI(CL_IP_C_HVAC_MODE);
     if (THERMAL) {
         p.cd_pnom = LD(CL_P_CD_NOMINAL_POWER); p.cd_cop_num = LD(CL_P_CD_COP_NUM); p.cd_target = LD(CL_P_CD_TARGET);
         p.hd_pnom = LD(CL_P_HD_NOMINAL_POWER); p.hd_cop_num = LD(CL_P_HD_COP_NUM); p.hd_target = LD(CL_P_HD_TARGET); p.hd_eff = LD(CL_P_HD_EFFICIENCY);
@@ -74,16 +94,21 @@ __device__ __forceinline__ void load_params(const Dev& d, int b, BuildingParams<
         p.ds.capacity = LD(CL_P_DS_CAPACITY); p.ds.efficiency = LD(CL_P_DS_EFFICIENCY); p.ds.loss = LD(CL_P_DS_LOSS);
         p.ds.max_in = LD(CL_P_DS_MAX_IN); p.ds.max_out = LD(CL_P_DS_MAX_OUT);
         p.ds.has_max_in = p.flags & CL_F_DS_HAS_MAX_IN; p.ds.has_max_out = p.flags & CL_F_DS_HAS_MAX_OUT;
+        c.c_dhw = LDI(CL_IP_C_DHW_DEMAND); c.c_cool = LDI(CL_IP_C_COOLING_DEMAND); c.c_heat = LDI(CL_IP_C_HEATING_DEMAND);
+        c.c_tout = LDI(CL_IP_C_T_OUT);
+        c.a_cd = LDI(CL_IP_A_COOLING_DEVICE); c.a_hd = LDI(CL_IP_A_HEATING_DEVICE); c.a_coh = LDI(CL_IP_A_COOLING_OR_HEATING_DEVICE);
+        c.a_cs = LDI(CL_IP_A_COOLING_STORAGE); c.a_hs = LDI(CL_IP_A_HEATING_STORAGE); c.a_ds = LDI(CL_IP_A_DHW_STORAGE);
     }
 #undef LD
+#undef LDI
 }
 
 template <typename R, bool THERMAL>
 __device__ __forceinline__ void load_state(const Dev& d, int u, UnitState<R>& s) {
     const int U = d.U;
     s.soc_b = (R)d.st[ST_SOC_B * U + u];
-    if (sizeof(R) == 8) { s.cap_deg = (R)d.dst[u]; s.eff_b = (R)d.dst[U + u]; }
-    else { s.cap_deg = (R)d.st[ST_CAP_DEG * U + u]; s.eff_b = (R)d.st[ST_EFF_B * U + u]; }
+    if (sizeof(R) == 8) { s.cap_deg = (R)d.dst[u]; s.rte_b = (R)d.dst[U + u]; }
+    else { s.cap_deg = (R)d.st[ST_CAP_DEG * U + u]; s.rte_b = (R)d.st[ST_RTE_B * U + u]; }
     if (THERMAL) { s.soc_cs = (R)d.st[ST_SOC_CS * U + u]; s.soc_hs = (R)d.st[ST_SOC_HS * U + u]; s.soc_ds = (R)d.st[ST_SOC_DS * U + u]; }
     else { s.soc_cs = s.soc_hs = s.soc_ds = (R)0; }
 }
@@ -92,59 +117,45 @@ template <typename R, bool THERMAL>
 __device__ __forceinline__ void store_state(const Dev& d, int u, const UnitState<R>& s) {
     const int U = d.U;
     d.st[ST_SOC_B * U + u] = (float)s.soc_b;
-    if (sizeof(R) == 8) { d.dst[u] = (double)s.cap_deg; d.dst[U + u] = (double)s.eff_b; }
-    else { d.st[ST_CAP_DEG * U + u] = (float)s.cap_deg; d.st[ST_EFF_B * U + u] = (float)s.eff_b; }
+    if (sizeof(R) == 8) { d.dst[u] = (double)s.cap_deg; d.dst[U + u] = (double)s.rte_b; }
+    else { d.st[ST_CAP_DEG * U + u] = (float)s.cap_deg; d.st[ST_RTE_B * U + u] = (float)s.rte_b; }
     if (THERMAL) { d.st[ST_SOC_CS * U + u] = (float)s.soc_cs; d.st[ST_SOC_HS * U + u] = (float)s.soc_hs; d.st[ST_SOC_DS * U + u] = (float)s.soc_ds; }
 }
 
-// exogenous inputs of unit (e, b) at time step t; `row` points at the time row (shared or global memory)
+// exogenous inputs of a unit at time step t; `row` points at the time row (shared or global memory)
 template <typename R, bool THERMAL>
-__device__ __forceinline__ void load_inputs(const Dev& d, const float* row, int b, int t, UnitInputs<R>& in) {
-    const int B = d.B;
-    const int32_t* ip = d.ip;
-    const auto* P = PSel<R>::p(d);
-#define COL(k) row[__ldg(ip + (k) * B + b)]
-    in.nsl = (R)COL(CL_IP_C_NSL);
-    const R pv = (R)__ldg(P + CL_P_PV_NOMINAL_POWER * B + b);
-    in.solar = -(pv * (R)COL(CL_IP_C_SOLAR) / (R)1000);            // building.py:2554, energy_model.py:488
-    in.price = (R)COL(CL_IP_C_PRICE);
-    in.carbon = (R)COL(CL_IP_C_CARBON);
+__device__ __forceinline__ void load_inputs(const Dev& d, const UnitCtx<R>& c, const float* row, int b, int t, UnitInputs<R>& in) {
+    in.nsl = (R)row[c.c_nsl];
+    in.solar = -(c.pv * (R)row[c.c_solar] / (R)1000);            // building.py:2554, energy_model.py:488
+    in.price = (R)row[c.c_price];
+    in.carbon = (R)row[c.c_carbon];
     if (THERMAL) {
-        in.dhw_demand = (R)COL(CL_IP_C_DHW_DEMAND); in.cooling_demand = (R)COL(CL_IP_C_COOLING_DEMAND);
-        in.heating_demand = (R)COL(CL_IP_C_HEATING_DEMAND); in.t_out = (R)COL(CL_IP_C_T_OUT);
-        in.hvac_mode = (int32_t)COL(CL_IP_C_HVAC_MODE);
+        in.dhw_demand = (R)row[c.c_dhw]; in.cooling_demand = (R)row[c.c_cool]; in.heating_demand = (R)row[c.c_heat];
+        in.t_out = (R)row[c.c_tout]; in.hvac_mode = (int32_t)row[c.c_hvac];
     } else {
         in.dhw_demand = in.cooling_demand = in.heating_demand = (R)0; in.t_out = (R)0; in.hvac_mode = 0;
     }
-#undef COL
-    const int flags = __ldg(ip + CL_IP_FLAGS * B + b);
-    in.outage = d.has_outage && (flags & CL_F_SIMULATE_OUTAGE) && __ldg(d.outage + b * d.T + t) > 0.f;
+    in.outage = d.has_outage && (c.p.flags & CL_F_SIMULATE_OUTAGE) && __ldg(d.outage + b * d.T + t) > 0.f;
     in.control_cooling_demand = false;
     in.control_heating_demand = false;
 }
 
 template <typename R, bool THERMAL>
-__device__ __forceinline__ void load_actions(const Dev& d, const float* act_row, int b, UnitInputs<R>& in) {
-    const int B = d.B;
-    const int32_t* ip = d.ip;
-    auto slot = [&](int k) { return __ldg(ip + k * B + b); };
-    const int s_es = slot(CL_IP_A_ELECTRICAL_STORAGE);
-    in.a_es = s_es >= 0 ? (R)act_row[s_es] : (R)0;
+__device__ __forceinline__ void load_actions(const UnitCtx<R>& c, const float* act_row, UnitInputs<R>& in) {
+    in.a_es = c.a_es >= 0 ? (R)__ldg(act_row + c.a_es) : (R)0;
     in.a_cooling_device = in.a_heating_device = (R)NAN;
     in.a_cs = in.a_hs = in.a_ds = (R)0;
     if (THERMAL) {
-        const int s_cd = slot(CL_IP_A_COOLING_DEVICE), s_hd = slot(CL_IP_A_HEATING_DEVICE), s_coh = slot(CL_IP_A_COOLING_OR_HEATING_DEVICE);
-        if (s_cd >= 0) in.a_cooling_device = (R)act_row[s_cd];
-        if (s_hd >= 0) in.a_heating_device = (R)act_row[s_hd];
-        if (s_coh >= 0) {   // building.py:1550-1553
-            const R v = (R)act_row[s_coh];
+        if (c.a_cd >= 0) in.a_cooling_device = (R)__ldg(act_row + c.a_cd);
+        if (c.a_hd >= 0) in.a_heating_device = (R)__ldg(act_row + c.a_hd);
+        if (c.a_coh >= 0) {   // building.py:1550-1553
+            const R v = (R)__ldg(act_row + c.a_coh);
             in.a_cooling_device = fabs(rmin(v, (R)0));
             in.a_heating_device = fabs(rmax(v, (R)0));
         }
-        const int s_cs = slot(CL_IP_A_COOLING_STORAGE), s_hs = slot(CL_IP_A_HEATING_STORAGE), s_ds = slot(CL_IP_A_DHW_STORAGE);
-        if (s_cs >= 0) in.a_cs = (R)act_row[s_cs];
-        if (s_hs >= 0) in.a_hs = (R)act_row[s_hs];
-        if (s_ds >= 0) in.a_ds = (R)act_row[s_ds];
+        if (c.a_cs >= 0) in.a_cs = (R)__ldg(act_row + c.a_cs);
+        if (c.a_hs >= 0) in.a_hs = (R)__ldg(act_row + c.a_hs);
+        if (c.a_ds >= 0) in.a_ds = (R)__ldg(act_row + c.a_ds);
     }
 }
 
@@ -276,7 +287,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// observation writer: rows of the block's envs are one contiguous span obs[e0*L .. (e0+n)*L)
+// observation writers: the rows of a block's envs are one contiguous span obs[e0*L .. (e0+n)*L)
 // ------------------------------------------------------------------------------------------------------------------
 // general path: any descriptor kind, per-env start rows, DYN values from shared memory (or zero)
 __device__ __forceinline__ void write_obs_general(const Dev& d, float* obs, int e0, int n_env, int t_obs,
@@ -303,217 +314,81 @@ __device__ __forceinline__ void write_obs_general(const Dev& d, float* obs, int 
     }
 }
 
-// fast path (uniform start rows, no DYN values needed): every env row equals the template row built once per block
-__device__ __forceinline__ void build_obs_template(const Dev& d, const float* row_next, int t_obs, float* tmpl) {
+// fast path (uniform start rows, reference-parity observations): every env row equals the template row of the step
+__device__ __forceinline__ void build_obs_template(const Dev& d, const int32_t* tcol, const float* row_next, int t_obs, float* tmpl) {
     for (int k = threadIdx.x; k < d.L; k += blockDim.x) {
-        const int4 ds = __ldg(d.desc + k);
+        const int c = tcol[k];
         float v;
-        if (ds.x == CL_OBS_TS) v = row_next[ds.y];
-        else if (ds.x == CL_OBS_DYN) v = 0.f;
-        else v = d.has_outage ? __ldg(d.outage + ds.w * d.T + t_obs) : 0.f;
+        if (c >= 0) v = row_next[c];
+        else if (c == -1) v = 0.f;
+        else v = d.has_outage ? __ldg(d.outage + (-2 - c) * d.T + t_obs) : 0.f;
         tmpl[k] = v;
     }
 }
 
 __device__ __forceinline__ void write_obs_template(const Dev& d, float* obs, int e0, int n_env, const float* tmpl) {
-    const int L = d.L, nt = blockDim.x;
+    const int L = d.L;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     float* out = obs + (size_t)e0 * L;
-    if ((L & 3) == 0) {   // 16-byte vector stores: a row never straddles a float4 because L % 4 == 0
-        const int L4 = L >> 2, total4 = n_env * L4;
+    if ((L & 3) == 0) {   // 16-byte vector stores; one warp streams one env row at a time: no index arithmetic in the loop
+        const int L4 = L >> 2;
         const float4* t4 = reinterpret_cast<const float4*>(tmpl);
-        float4* o4 = reinterpret_cast<float4*>(out);
-        int j = threadIdx.x;
-        int k = j % L4;
-        const int dk = nt % L4;
-        for (; j < total4; j += nt) {
-            __stcs(o4 + j, t4[k]);   // streaming store: written once, read by the consumer later
-            k += dk;
-            if (k >= L4) k -= L4;
+        for (int le = warp; le < n_env; le += nwarps) {
+            float4* o4 = reinterpret_cast<float4*>(out + (size_t)le * L);
+            for (int k = lane; k < L4; k += 32) __stcs(o4 + k, t4[k]);   // streaming store: written once, read by the consumer later
         }
     } else {
-        const int total = n_env * L;
-        int j = threadIdx.x;
-        int k = j % L;
-        const int dk = nt % L;
-        for (; j < total; j += nt) {
-            __stcs(out + j, tmpl[k]);
-            k += dk;
-            if (k >= L) k -= L;
+        for (int le = warp; le < n_env; le += nwarps) {
+            float* o = out + (size_t)le * L;
+            for (int k = lane; k < L; k += 32) __stcs(o + k, tmpl[k]);
         }
     }
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// shared memory carve-up (dynamic): [mbarriers 32B][rows 3*Wp][tmpl Lp][red 4*nthreads][dsum 4*epb][dynbuf (optional)]
-// (the step kernel uses rows[0..1] and one barrier; the rollout kernel uses a 3-row ring with one barrier per slot)
+// shared memory carve-up (dynamic)
+//   [mbarriers 32 B][rows 3*Wp][tcol Lp (int)][tmpl 2*Lp][red 2*3*nt][rsum nt][dsum 2*epb][curves B*32 (R)][dynbuf nt*NDYN (opt)]
+// red / tmpl / dsum are double-buffered by step parity so that a step needs ONE block barrier (see advance_kernel).
 // ------------------------------------------------------------------------------------------------------------------
 struct Smem {
     uint64_t* bar;
     float* rows;
-    float* tmpl;
-    float* red;     // [3][nthreads] net, cost, emission (+ [nthreads] reward when central)
-    float* dsum;    // [epb][4]
-    float* dynbuf;  // [nthreads][CL_NDYN]
+    int32_t* tcol;
+    float* tmpl;    // [2][Lp]
+    float* red;     // [2][3][nt]  net, cost, emission
+    float* rsum;    // [nt]        per-unit rewards (central agent)
+    float* dsum;    // [2][epb]
+    void* curves;   // R [B][32]
+    float* dynbuf;  // [nt][CL_NDYN]
+    int Lp;
 };
-__device__ __forceinline__ Smem carve(const Dev& d, unsigned char* base, int nthreads) {
+__device__ __forceinline__ Smem carve(const Dev& d, unsigned char* base, int nt, int rsize) {
     Smem s;
+    s.Lp = (d.L + 3) & ~3;
     s.bar = reinterpret_cast<uint64_t*>(base);
     float* f = reinterpret_cast<float*>(base + 32);
     s.rows = f; f += 3 * d.Wp;
-    s.tmpl = f; f += (d.L + 3) & ~3;
-    s.red = f; f += 4 * nthreads;
-    s.dsum = f; f += 4 * d.envs_per_block;
+    s.tcol = reinterpret_cast<int32_t*>(f); f += s.Lp;
+    s.tmpl = f; f += 2 * s.Lp;
+    s.red = f; f += 6 * nt;
+    s.rsum = f; f += nt;
+    s.dsum = f; f += (2 * d.envs_per_block + 3) & ~3;
+    s.curves = f; f += (size_t)d.B * 32 * (rsize / 4);
     s.dynbuf = f;
     return s;
 }
-static size_t smem_bytes(const Dev& d, int nthreads, bool with_dyn) {
-    size_t n = 32 + sizeof(float) * (3 * (size_t)d.Wp + ((d.L + 3) & ~3) + 4 * (size_t)nthreads + 4 * (size_t)d.envs_per_block);
-    if (with_dyn) n += sizeof(float) * (size_t)nthreads * CL_NDYN;
+static size_t smem_bytes(const Dev& d, int nt, bool with_dyn, int rsize) {
+    const size_t Lp = (d.L + 3) & ~3;
+    size_t n = 32 + sizeof(float) * (3 * (size_t)d.Wp + 3 * Lp + 7 * (size_t)nt + ((2 * (size_t)d.envs_per_block + 3) & ~3) + (size_t)d.B * 32 * (rsize / 4));
+    if (with_dyn) n += sizeof(float) * (size_t)nt * CL_NDYN;
     return n;
 }
 
-// ------------------------------------------------------------------------------------------------------------------
-// step kernel
-// ------------------------------------------------------------------------------------------------------------------
-template <typename R, bool THERMAL, int MAXT>
-__global__ void __launch_bounds__(MAXT) step_kernel(Dev d, int t, const float* __restrict__ actions, float* __restrict__ obs,
-                                                     float* __restrict__ reward, float* __restrict__ district, float* __restrict__ trace) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int nt = blockDim.x, tid = threadIdx.x;
-    Smem sm = carve(d, smem_raw, nt);
-    const int B = d.B, epb = d.envs_per_block;
-    const int e0 = blockIdx.x * epb;
-    const int n_env = min(epb, d.E - e0);
-    const int n_units = n_env * B;
-    const bool active = tid < n_units;
-    const int e_l = tid / B, b = tid - e_l * B;
-    const int e = e0 + e_l, u = e * B + b;
-    const bool want_dyn = (!d.stale && obs != nullptr);
-
-    // stage the time rows of t and t+1 (contiguous) with one TMA bulk copy
-    if (d.uniform_start) {
-        if (tid == 0) {
-            mbar_init(sm.bar, 1);
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            const uint32_t bytes = 2u * d.Wp * sizeof(float);
-            mbar_expect_tx(sm.bar, bytes);
-            tma_load_1d(sm.rows, d.table + (size_t)(d.start0 + t) * d.Wp, bytes, sm.bar);
-        }
-        __syncthreads();
-        mbar_wait(sm.bar, 0);
-    }
-
-    UnitResult<R> o;
-    UnitState<R> s;
-    BuildingParams<R> p;
-    UnitInputs<R> in;
-    float t_in = 0.f;
-    if (active) {
-        load_params<R, THERMAL>(d, b, p);
-        const float* row = d.uniform_start ? sm.rows : d.table + (size_t)(__ldg(d.start + e) + t) * d.Wp;
-        load_inputs<R, THERMAL>(d, row, b, t, in);
-        load_actions<R, THERMAL>(d, actions + (size_t)e * d.A, b, in);
-        load_state<R, THERMAL>(d, u, s);
-        const auto* curves = PSel<R>::p(d) + CL_P_PE_X0 * B + b;
-        unit_step<R, THERMAL>(p, curves, B, t, in, s, o);
-        store_state<R, THERMAL>(d, u, s);
-        t_in = row[__ldg(d.ip + CL_IP_C_T_IN * B + b)];
-        sm.red[tid] = (float)o.net;
-        sm.red[nt + tid] = (float)o.cost;
-        sm.red[2 * nt + tid] = (float)o.emission;
-        if (trace != nullptr || want_dyn) {
-            float dyn[CL_NDYN];
-            fill_dyn<R>(p, s, o, (R)t_in, dyn);
-            if (trace != nullptr) {
-#pragma unroll
-                for (int k = 0; k < CL_NDYN; ++k) trace[(size_t)u * CL_NDYN + k] = dyn[k];
-            }
-            if (want_dyn) {
-#pragma unroll
-                for (int k = 0; k < CL_NDYN; ++k) sm.dynbuf[tid * CL_NDYN + k] = dyn[k];
-            }
-        }
-    }
-    __syncthreads();
-    // district sums in building order, like the reference's sum() over buildings (citylearn.py:1908-1918)
-    if (tid < n_env) {
-        float sn = 0.f, sc = 0.f, se = 0.f;
-        for (int k = 0; k < B; ++k) {
-            sn += sm.red[tid * B + k];
-            sc += sm.red[nt + tid * B + k];
-            se += sm.red[2 * nt + tid * B + k];
-        }
-        sm.dsum[tid * 4 + 0] = sn; sm.dsum[tid * 4 + 1] = sc; sm.dsum[tid * 4 + 2] = se;
-        if (district != nullptr) {
-            district[(size_t)(e0 + tid) * 3 + 0] = sn;
-            district[(size_t)(e0 + tid) * 3 + 1] = sc;
-            district[(size_t)(e0 + tid) * 3 + 2] = se;
-        }
-    }
-    __syncthreads();
-    if (reward != nullptr && d.reward_id >= 0) {
-        float r = 0.f;
-        if (active) {
-            RewardIn ri;
-            ri.net = (float)o.net; ri.district_net = sm.dsum[e_l * 4];
-            ri.soc_b = (float)s.soc_b; ri.soc_cs = (float)s.soc_cs; ri.soc_hs = (float)s.soc_hs; ri.soc_ds = (float)s.soc_ds;
-            ri.cap_b = (float)p.bat_capacity;
-            if (THERMAL) {
-                ri.cap_cs = (float)p.cs.capacity; ri.cap_hs = (float)p.hs.capacity; ri.cap_ds = (float)p.ds.capacity;
-                ri.cool_dem = (float)(o.e_from_cool + fabs(rmin(o.eb_cs, (R)0)));
-                ri.heat_dem = (float)(o.e_from_heat + fabs(rmin(o.eb_hs, (R)0)));
-            } else { ri.cap_cs = ri.cap_hs = ri.cap_ds = 0.f; ri.cool_dem = ri.heat_dem = 0.f; }
-            ri.hvac_mode = in.hvac_mode;
-            ri.t_in = t_in;
-            if (d.reward_id == CL_REWARD_COMFORT || d.reward_id == CL_REWARD_SOLAR_PENALTY_AND_COMFORT) {
-                const float* row = d.uniform_start ? sm.rows : d.table + (size_t)(__ldg(d.start + e) + t) * d.Wp;
-                ri.cool_sp = row[__ldg(d.ip + CL_IP_C_COOL_SP * B + b)];
-                ri.heat_sp = row[__ldg(d.ip + CL_IP_C_HEAT_SP * B + b)];
-                ri.band_series = row[__ldg(d.ip + CL_IP_C_COMFORT_BAND * B + b)];
-                ri.hvac_mode = (int)row[__ldg(d.ip + CL_IP_C_HVAC_MODE * B + b)];
-            } else { ri.cool_sp = ri.heat_sp = ri.band_series = 0.f; }
-            r = unit_reward(d.reward_id, d.rp, ri);
-        }
-        if (d.central) {
-            sm.red[3 * nt + tid] = r;
-            __syncthreads();
-            if (tid < n_env) {
-                float sr = 0.f;
-                if (d.reward_id == CL_REWARD_MARL || d.reward_id == CL_REWARD_SOLAR_PENALTY_AND_COMFORT) {
-                    double acc = 0.0;   // these rewards are float64 in the reference
-                    for (int k = 0; k < B; ++k) acc += (double)sm.red[3 * nt + tid * B + k];
-                    sr = (float)acc;
-                } else {
-                    for (int k = 0; k < B; ++k) sr += sm.red[3 * nt + tid * B + k];
-                }
-                reward[e0 + tid] = sr;
-            }
-        } else if (active) {
-            reward[u] = r;
-        }
-    }
-    // observations at t + 1
-    if (obs != nullptr) {
-        if (d.uniform_start && d.stale) {
-            build_obs_template(d, sm.rows + d.Wp, t + 1, sm.tmpl);
-            __syncthreads();
-            write_obs_template(d, obs, e0, n_env, sm.tmpl);
-        } else {
-            write_obs_general(d, obs, e0, n_env, t + 1, want_dyn ? sm.dynbuf : nullptr);
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------------------------------
-// rollout kernel: K consecutive steps in one launch.  State and parameters live in registers for the whole block of
-// steps; per step a thread reads its action(s), the block reduces the district sums in shared memory and streams out the
-// reward and observation slabs.  The time rows ride a 3-slot TMA ring (row t+2 is prefetched while step t computes).
-// ------------------------------------------------------------------------------------------------------------------
 template <typename R, bool THERMAL>
-__device__ __forceinline__ void reward_inputs(const Dev& d, const BuildingParams<R>& p, const UnitState<R>& s, const UnitResult<R>& o,
-                                              const UnitInputs<R>& in, const float* row, int b, float t_in, float district_net, RewardIn& ri) {
-    const int B = d.B;
-    ri.net = (float)o.net; ri.district_net = district_net;
+__device__ __forceinline__ void reward_inputs(const Dev& d, const UnitCtx<R>& c, const UnitState<R>& s, const UnitResult<R>& o,
+                                              const float* row, RewardIn& ri) {
+    const BuildingParams<R>& p = c.p;
+    ri.net = (float)o.net; ri.district_net = 0.f;
     ri.soc_b = (float)s.soc_b; ri.soc_cs = (float)s.soc_cs; ri.soc_hs = (float)s.soc_hs; ri.soc_ds = (float)s.soc_ds;
     ri.cap_b = (float)p.bat_capacity;
     if (THERMAL) {
@@ -521,22 +396,28 @@ __device__ __forceinline__ void reward_inputs(const Dev& d, const BuildingParams
         ri.cool_dem = (float)(o.e_from_cool + fabs(rmin(o.eb_cs, (R)0)));
         ri.heat_dem = (float)(o.e_from_heat + fabs(rmin(o.eb_hs, (R)0)));
     } else { ri.cap_cs = ri.cap_hs = ri.cap_ds = 0.f; ri.cool_dem = ri.heat_dem = 0.f; }
-    ri.hvac_mode = in.hvac_mode;
-    ri.t_in = t_in;
+    ri.t_in = row[c.c_tin];
     if (d.reward_id == CL_REWARD_COMFORT || d.reward_id == CL_REWARD_SOLAR_PENALTY_AND_COMFORT) {
-        ri.cool_sp = row[__ldg(d.ip + CL_IP_C_COOL_SP * B + b)];
-        ri.heat_sp = row[__ldg(d.ip + CL_IP_C_HEAT_SP * B + b)];
-        ri.band_series = row[__ldg(d.ip + CL_IP_C_COMFORT_BAND * B + b)];
-        ri.hvac_mode = (int)row[__ldg(d.ip + CL_IP_C_HVAC_MODE * B + b)];
-    } else { ri.cool_sp = ri.heat_sp = ri.band_series = 0.f; }
+        ri.cool_sp = row[c.c_coolsp]; ri.heat_sp = row[c.c_heatsp]; ri.band_series = row[c.c_band];
+        ri.hvac_mode = (int)row[c.c_hvac];
+    } else { ri.cool_sp = ri.heat_sp = ri.band_series = 0.f; ri.hvac_mode = 0; }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// advance kernel: K consecutive time steps in one launch (cl_step: K = 1, cl_rollout: any K).
+// Parameters, table columns and the unit state stay in registers for the whole launch; per step a thread gathers its inputs
+// from the TMA-staged time row, reads its action(s), runs the physics, and the block reduces the district sums in shared
+// memory and streams out the reward and observation slabs.  The time rows ride a 3-slot TMA ring: the row of step t+3 is
+// requested as soon as every thread is done with the row of step t.  One block barrier per step (two when a reward needs the
+// district sum, three for central-agent sums): `red`, `tmpl` and `dsum` are double-buffered by step parity.
+// ------------------------------------------------------------------------------------------------------------------
 template <typename R, bool THERMAL, int MAXT>
-__global__ void __launch_bounds__(MAXT) rollout_kernel(Dev d, int t0, int K, const float* __restrict__ actions, float* __restrict__ obs,
-                                                        float* __restrict__ reward, float* __restrict__ district) {
+__global__ void __launch_bounds__(MAXT) advance_kernel(Dev d, int t0, int K, const float* __restrict__ actions, float* __restrict__ obs,
+                                                        float* __restrict__ reward, float* __restrict__ district, float* __restrict__ trace) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int nt = blockDim.x, tid = threadIdx.x;
-    Smem sm = carve(d, smem_raw, nt);
+    Smem sm = carve(d, smem_raw, nt, (int)sizeof(R));
+    R* scurves = reinterpret_cast<R*>(sm.curves);
     const int B = d.B, epb = d.envs_per_block, Wp = d.Wp;
     const int e0 = blockIdx.x * epb;
     const int n_env = min(epb, d.E - e0);
@@ -546,6 +427,9 @@ __global__ void __launch_bounds__(MAXT) rollout_kernel(Dev d, int t0, int K, con
     const int e = e0 + e_l, u = e * B + b;
     const bool uniform = d.uniform_start != 0;
     const bool want_dyn = (!d.stale && obs != nullptr);
+    const bool tmpl_path = obs != nullptr && uniform && d.stale;
+    const bool need_dsum = d.reward_id == CL_REWARD_MARL && reward != nullptr;
+    const bool fused_reward = reward != nullptr && d.reward_id >= 0;
     const int Rdim = d.central ? 1 : B;
     const uint32_t row_bytes = (uint32_t)Wp * sizeof(float);
 
@@ -557,19 +441,26 @@ __global__ void __launch_bounds__(MAXT) rollout_kernel(Dev d, int t0, int K, con
             tma_load_1d(sm.rows + i * Wp, d.table + (size_t)(d.start0 + t0 + i) * Wp, row_bytes, sm.bar + i);
         }
     }
-    BuildingParams<R> p;
+    // block-wide staging: template columns and the battery curves of every building (dynamic indexing -> shared memory)
+    if (tmpl_path) for (int k = tid; k < d.L; k += nt) sm.tcol[k] = __ldg(d.tcol + k);
+    {
+        const auto* P = PSel<R>::p(d) + CL_P_PE_X0 * B;
+        for (int i = tid; i < B * 32; i += nt) { const int bb = i >> 5, j = i & 31; scurves[i] = (R)__ldg(P + j * B + bb); }
+    }
+    UnitCtx<R> c;
     UnitState<R> s;
-    const auto* curves = PSel<R>::p(d) + CL_P_PE_X0 * B + (active ? b : 0);
     int start_e = 0;
     if (active) {
-        load_params<R, THERMAL>(d, b, p);
+        load_ctx<R, THERMAL>(d, b, c);
         load_state<R, THERMAL>(d, u, s);
         start_e = __ldg(d.start + e);
     }
-    __syncthreads();   // barriers initialised before anyone waits on them
+    const R* curves = scurves + (active ? b : 0) * 32;
+    __syncthreads();   // barriers initialised, curves / tcol staged
 
     for (int k = 0; k < K; ++k) {
         const int t = t0 + k;
+        const int pb = k & 1;
         const int slot_t = k % 3, slot_n = (k + 1) % 3;
         const float* row;
         const float* row_next = nullptr;
@@ -581,62 +472,73 @@ __global__ void __launch_bounds__(MAXT) rollout_kernel(Dev d, int t0, int K, con
         } else {
             row = d.table + (size_t)(start_e + t) * Wp;
         }
+        float* red = sm.red + pb * 3 * nt;
+        float* tmpl = sm.tmpl + pb * sm.Lp;
         UnitResult<R> o;
-        UnitInputs<R> in;
-        float t_in = 0.f;
+        RewardIn ri;
         if (active) {
-            load_inputs<R, THERMAL>(d, row, b, t, in);
-            load_actions<R, THERMAL>(d, actions + ((size_t)k * d.E + e) * d.A, b, in);
-            unit_step<R, THERMAL>(p, curves, B, t, in, s, o);
-            t_in = row[__ldg(d.ip + CL_IP_C_T_IN * B + b)];
-            sm.red[tid] = (float)o.net;
-            sm.red[nt + tid] = (float)o.cost;
-            sm.red[2 * nt + tid] = (float)o.emission;
-            if (want_dyn) fill_dyn<R>(p, s, o, (R)t_in, sm.dynbuf + tid * CL_NDYN);
+            UnitInputs<R> in;
+            load_inputs<R, THERMAL>(d, c, row, b, t, in);
+            load_actions<R, THERMAL>(c, actions + ((size_t)k * d.E + e) * d.A, in);
+            unit_step<R, THERMAL>(c.p, curves, 1, t, in, s, o);
+            red[tid] = (float)o.net;
+            red[nt + tid] = (float)o.cost;
+            red[2 * nt + tid] = (float)o.emission;
+            if (fused_reward) reward_inputs<R, THERMAL>(d, c, s, o, row, ri);     // everything the reward needs from row t
+            if (trace != nullptr || want_dyn) {
+                float dyn[CL_NDYN];
+                fill_dyn<R>(c.p, s, o, (R)row[c.c_tin], dyn);
+                if (trace != nullptr) {
+#pragma unroll
+                    for (int j = 0; j < CL_NDYN; ++j) trace[(size_t)u * CL_NDYN + j] = dyn[j];
+                }
+                if (want_dyn) {
+#pragma unroll
+                    for (int j = 0; j < CL_NDYN; ++j) sm.dynbuf[tid * CL_NDYN + j] = dyn[j];
+                }
+            }
         }
-        __syncthreads();                                                       // S1
-        if (uniform && tid == 0 && k >= 1 && k + 2 <= K) {
-            // every thread has left step k-1: its row slot ((k-1) % 3) is free -> prefetch row t0 + k + 2 into it
-            const int sl = (k + 2) % 3;
+        if (tmpl_path) build_obs_template(d, sm.tcol, row_next, t + 1, tmpl);
+        __syncthreads();                                                       // S1: red / tmpl / dynbuf of step k complete
+        if (uniform && tid == 0 && k + 3 <= K) {
+            // nobody reads row t any more (reward inputs were captured above): its slot takes the row of step t + 3
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            mbar_expect_tx(sm.bar + sl, row_bytes);
-            tma_load_1d(sm.rows + sl * Wp, d.table + (size_t)(d.start0 + t0 + k + 2) * Wp, row_bytes, sm.bar + sl);
+            mbar_expect_tx(sm.bar + slot_t, row_bytes);
+            tma_load_1d(sm.rows + slot_t * Wp, d.table + (size_t)(d.start0 + t + 3) * Wp, row_bytes, sm.bar + slot_t);
         }
-        if (tid < n_env) {
-            float sn = 0.f, sc = 0.f, se = 0.f;
-            for (int j = 0; j < B; ++j) {
-                sn += sm.red[tid * B + j];
-                sc += sm.red[nt + tid * B + j];
-                se += sm.red[2 * nt + tid * B + j];
-            }
-            sm.dsum[tid * 4 + 0] = sn;
-            if (district != nullptr) {
-                float* dp = district + ((size_t)k * d.E + e0 + tid) * 3;
-                dp[0] = sn; dp[1] = sc; dp[2] = se;
-            }
+        // district sums in building order, like the reference's sum() over buildings (citylearn.py:1908-1918);
+        // one thread per (quantity, env)
+        for (int idx = tid; idx < 3 * n_env; idx += nt) {
+            const int q = idx / n_env, le = idx - q * n_env;
+            if (q > 0 && district == nullptr) continue;
+            const float* src = red + q * nt + le * B;
+            float acc = 0.f;
+            int j = 0;
+            for (; j + 4 <= B; j += 4) { acc += src[j]; acc += src[j + 1]; acc += src[j + 2]; acc += src[j + 3]; }   // same left-to-right order
+            for (; j < B; ++j) acc += src[j];
+            if (q == 0) sm.dsum[pb * epb + le] = acc;
+            if (district != nullptr) district[((size_t)k * d.E + e0 + le) * 3 + q] = acc;
         }
-        const bool tmpl_path = obs != nullptr && uniform && d.stale;
-        if (tmpl_path) build_obs_template(d, row_next, t + 1, sm.tmpl);
-        __syncthreads();                                                       // S2
-        if (reward != nullptr && d.reward_id >= 0) {
+        if (need_dsum) __syncthreads();                                        // S2 only when a reward reads the district sum
+        if (fused_reward) {
             float r = 0.f;
             if (active) {
-                RewardIn ri;
-                reward_inputs<R, THERMAL>(d, p, s, o, in, row, b, t_in, sm.dsum[e_l * 4], ri);
+                if (need_dsum) ri.district_net = sm.dsum[pb * epb + e_l];
                 r = unit_reward(d.reward_id, d.rp, ri);
             }
             float* rk = reward + (size_t)k * d.E * Rdim;
             if (d.central) {
-                sm.red[3 * nt + tid] = r;
+                if (k > 0) __syncthreads();                                    // previous step's rsum readers are done
+                sm.rsum[tid] = r;
                 __syncthreads();
                 if (tid < n_env) {
                     float sr = 0.f;
                     if (d.reward_id == CL_REWARD_MARL || d.reward_id == CL_REWARD_SOLAR_PENALTY_AND_COMFORT) {
-                        double acc = 0.0;
-                        for (int j = 0; j < B; ++j) acc += (double)sm.red[3 * nt + tid * B + j];
+                        double acc = 0.0;   // these rewards are float64 in the reference
+                        for (int j = 0; j < B; ++j) acc += (double)sm.rsum[tid * B + j];
                         sr = (float)acc;
                     } else {
-                        for (int j = 0; j < B; ++j) sr += sm.red[3 * nt + tid * B + j];
+                        for (int j = 0; j < B; ++j) sr += sm.rsum[tid * B + j];
                     }
                     rk[e0 + tid] = sr;
                 }
@@ -646,8 +548,11 @@ __global__ void __launch_bounds__(MAXT) rollout_kernel(Dev d, int t0, int K, con
         }
         if (obs != nullptr) {
             float* ok = obs + (size_t)k * d.E * d.L;
-            if (tmpl_path) write_obs_template(d, ok, e0, n_env, sm.tmpl);
-            else write_obs_general(d, ok, e0, n_env, t + 1, want_dyn ? sm.dynbuf : nullptr);
+            if (tmpl_path) write_obs_template(d, ok, e0, n_env, tmpl);
+            else {
+                write_obs_general(d, ok, e0, n_env, t + 1, want_dyn ? sm.dynbuf : nullptr);
+                if (want_dyn && k + 1 < K) __syncthreads();                     // dynbuf is single-buffered
+            }
         }
     }
     if (active) store_state<R, THERMAL>(d, u, s);
@@ -660,7 +565,7 @@ template <typename R, bool THERMAL, int MAXT>
 __global__ void __launch_bounds__(MAXT) reset_kernel(Dev d, float* __restrict__ obs) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int nt = blockDim.x, tid = threadIdx.x;
-    Smem sm = carve(d, smem_raw, nt);
+    Smem sm = carve(d, smem_raw, nt, (int)sizeof(R));
     const int B = d.B, epb = d.envs_per_block;
     const int e0 = blockIdx.x * epb;
     const int n_env = min(epb, d.E - e0);
@@ -669,12 +574,12 @@ __global__ void __launch_bounds__(MAXT) reset_kernel(Dev d, float* __restrict__ 
     const int e = e0 + e_l, u = e * B + b;
     if (tid < n_units) {
         const auto* P = PSel<R>::p(d);
-        BuildingParams<R> p;
-        load_params<R, THERMAL>(d, b, p);
+        UnitCtx<R> c;
+        load_ctx<R, THERMAL>(d, b, c);
         UnitState<R> s;
         s.soc_b = Num<R>::r32((R)__ldg(P + CL_P_BAT_INITIAL_SOC * B + b));
-        s.cap_deg = p.bat_capacity;
-        s.eff_b = (R)__ldg(P + CL_P_BAT_EFFICIENCY0 * B + b);
+        s.cap_deg = c.p.bat_capacity;
+        s.rte_b = Num<R>::sqrt_((R)__ldg(P + CL_P_BAT_EFFICIENCY0 * B + b));
         s.soc_cs = Num<R>::r32((R)__ldg(P + CL_P_CS_INITIAL_SOC * B + b));
         s.soc_hs = Num<R>::r32((R)__ldg(P + CL_P_HS_INITIAL_SOC * B + b));
         s.soc_ds = Num<R>::r32((R)__ldg(P + CL_P_DS_INITIAL_SOC * B + b));
@@ -682,11 +587,10 @@ __global__ void __launch_bounds__(MAXT) reset_kernel(Dev d, float* __restrict__ 
         if (obs != nullptr) {
             const float* row = d.table + (size_t)__ldg(d.start + e) * d.Wp;
             UnitInputs<R> in;
-            load_inputs<R, THERMAL>(d, row, b, 0, in);
+            load_inputs<R, THERMAL>(d, c, row, b, 0, in);
             UnitResult<R> o;
-            unit_time0<R, THERMAL>(p, in, o);
-            const float t_in = row[__ldg(d.ip + CL_IP_C_T_IN * B + b)];
-            fill_dyn<R>(p, s, o, (R)t_in, sm.dynbuf + tid * CL_NDYN);
+            unit_time0<R, THERMAL>(c.p, in, o);
+            fill_dyn<R>(c.p, s, o, (R)row[c.c_tin], sm.dynbuf + tid * CL_NDYN);
         }
     }
     if (obs != nullptr) {
@@ -780,8 +684,18 @@ extern "C" int cl_create(const cl_district_desc* desc, cl_env** out) {
         if (!rc) rc = dev_copy(env, desc->params, (size_t)CL_NPARAM * B, &q);
         if (!rc) rc = dev_copy(env, desc->iparams, (size_t)CL_NIPARAM * B, &ip);
         if (!rc) rc = dev_copy(env, reinterpret_cast<const int4*>(desc->obs_desc), (size_t)d.L, &ds);
+        std::vector<int32_t> tcol((size_t)d.L);
+        for (int k = 0; k < d.L; ++k) {
+            const int32_t* e4 = desc->obs_desc + 4 * (size_t)k;
+            if (e4[3] < 0 || e4[3] >= B) { cl_destroy(env); return fail(CL_ERR_INVALID, "cl_create: observation descriptor names a building outside the district"); }
+            tcol[k] = e4[0] == CL_OBS_TS ? e4[1] : (e4[0] == CL_OBS_DYN ? -1 : -2 - e4[3]);
+            if (e4[0] == CL_OBS_TS && (e4[1] < 0 || e4[1] >= d.W)) { cl_destroy(env); return fail(CL_ERR_INVALID, "cl_create: observation column outside the table"); }
+            if (e4[0] == CL_OBS_DYN && (e4[1] < 0 || e4[1] >= CL_NDYN)) { cl_destroy(env); return fail(CL_ERR_INVALID, "cl_create: bad DYN slot"); }
+        }
+        int32_t* tc = nullptr;
+        if (!rc) rc = dev_copy(env, tcol.data(), tcol.size(), &tc);
         if (rc) { cl_destroy(env); return rc; }
-        d.pf = p; d.pd = q; d.ip = ip; d.desc = ds;
+        d.pf = p; d.pd = q; d.ip = ip; d.desc = ds; d.tcol = tc;
     }
     {
         void* p = nullptr;
@@ -798,10 +712,10 @@ extern "C" int cl_create(const cl_district_desc* desc, cl_env** out) {
         if (cudaMalloc(&p, (size_t)d.E * sizeof(int32_t)) != cudaSuccess) { cl_destroy(env); return fail(CL_ERR_CUDA, "cl_create: start allocation failed"); }
         env->allocs.push_back(p); d.start = static_cast<int32_t*>(p);
     }
-    // launch geometry: as many whole envs per block as fit the target block size.  The step path is latency-bound at the
-    // benchmark sizes (a few warps per scheduler), so SMALL blocks win: one warp per block turns the block barriers into
-    // warp barriers and lets idle lanes buy more resident warps (profiles/README.md).  CL_B200_BLOCK_THREADS overrides.
-    int target = 32;
+    // launch geometry: as many whole envs per block as fit the target block size.  Measured on B200 at 17 x 4096
+    // (profiles/README.md): 128-thread blocks are best (more, smaller blocks balance the 148 SMs; below 128 the per-block
+    // template / TMA work dominates).  CL_B200_BLOCK_THREADS overrides for experiments.
+    int target = 128;
     if (const char* ev = std::getenv("CL_B200_BLOCK_THREADS")) { const int v = std::atoi(ev); if (v >= 32 && v <= 1024) target = v; }
     int epb = target / B;
     if (epb < 1) epb = 1;
@@ -810,12 +724,11 @@ extern "C" int cl_create(const cl_district_desc* desc, cl_env** out) {
     env->threads = ((epb * B + 31) / 32) * 32;
     env->blocks = (d.E + epb - 1) / epb;
     // opt in to large dynamic shared memory once (both kernels, all instantiations)
-    const size_t smem = smem_bytes(d, env->threads, true);
+    const size_t smem = smem_bytes(d, env->threads, true, 8);
     if (smem > 200 * 1024) { cl_destroy(env); return fail(CL_ERR_UNSUPPORTED, "cl_create: district too wide for the shared-memory staging"); }
 #define OPTIN(K) cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
 #define OPTIN4(K, M) OPTIN((K<float, false, M>)); OPTIN((K<float, true, M>)); OPTIN((K<double, false, M>)); OPTIN((K<double, true, M>))
-    OPTIN4(step_kernel, 512); OPTIN4(step_kernel, 1024); OPTIN4(reset_kernel, 512); OPTIN4(reset_kernel, 1024);
-    OPTIN4(rollout_kernel, 512); OPTIN4(rollout_kernel, 1024);
+    OPTIN4(advance_kernel, 512); OPTIN4(advance_kernel, 1024); OPTIN4(reset_kernel, 512); OPTIN4(reset_kernel, 1024);
 #undef OPTIN4
 #undef OPTIN
     cudaError_t e = cudaGetLastError();
@@ -853,24 +766,26 @@ extern "C" int cl_set_outage(cl_env* env, const float* signals, int32_t episode_
 // blocks of up to 512 threads get the 128-register budget; only very wide districts (B > 512) use 1024-thread blocks
 template <typename R, bool TH>
 static void launch_reset(cl_env* env, float* obs, cudaStream_t st) {
-    const size_t smem = smem_bytes(env->d, env->threads, true);
+    const size_t smem = smem_bytes(env->d, env->threads, true, (int)sizeof(R));
     if (env->threads <= 512) reset_kernel<R, TH, 512><<<env->blocks, env->threads, smem, st>>>(env->d, obs);
     else reset_kernel<R, TH, 1024><<<env->blocks, env->threads, smem, st>>>(env->d, obs);
 }
 template <typename R, bool TH>
-static void launch_step(cl_env* env, const float* actions, float* obs, float* reward, float* district, float* trace, cudaStream_t st) {
+static void launch_advance(cl_env* env, int K, const float* actions, float* obs, float* reward, float* district, float* trace, cudaStream_t st) {
     const bool want_dyn = !env->d.stale && obs != nullptr;
-    const size_t smem = smem_bytes(env->d, env->threads, want_dyn);
-    if (env->threads <= 512) step_kernel<R, TH, 512><<<env->blocks, env->threads, smem, st>>>(env->d, env->t, actions, obs, reward, district, trace);
-    else step_kernel<R, TH, 1024><<<env->blocks, env->threads, smem, st>>>(env->d, env->t, actions, obs, reward, district, trace);
+    const size_t smem = smem_bytes(env->d, env->threads, want_dyn, (int)sizeof(R));
+    if (env->threads <= 512) advance_kernel<R, TH, 512><<<env->blocks, env->threads, smem, st>>>(env->d, env->t, K, actions, obs, reward, district, trace);
+    else advance_kernel<R, TH, 1024><<<env->blocks, env->threads, smem, st>>>(env->d, env->t, K, actions, obs, reward, district, trace);
 }
-
-template <typename R, bool TH>
-static void launch_rollout(cl_env* env, int K, const float* actions, float* obs, float* reward, float* district, cudaStream_t st) {
-    const bool want_dyn = !env->d.stale && obs != nullptr;
-    const size_t smem = smem_bytes(env->d, env->threads, want_dyn);
-    if (env->threads <= 512) rollout_kernel<R, TH, 512><<<env->blocks, env->threads, smem, st>>>(env->d, env->t, K, actions, obs, reward, district);
-    else rollout_kernel<R, TH, 1024><<<env->blocks, env->threads, smem, st>>>(env->d, env->t, K, actions, obs, reward, district);
+static void dispatch_advance(cl_env* env, int K, const float* actions, float* obs, float* reward, float* district, float* trace, cudaStream_t st) {
+    if (env->precision == CL_PRECISION_FP64) {
+        if (env->thermal) launch_advance<double, true>(env, K, actions, obs, reward, district, trace, st);
+        else launch_advance<double, false>(env, K, actions, obs, reward, district, trace, st);
+    } else {
+        if (env->thermal) launch_advance<float, true>(env, K, actions, obs, reward, district, trace, st);
+        else launch_advance<float, false>(env, K, actions, obs, reward, district, trace, st);
+    }
+    env->launches++;
 }
 
 __global__ void fill_start_kernel(int32_t* start, int n, int v) {
@@ -908,15 +823,7 @@ extern "C" int cl_step(cl_env* env, const float* actions, float* obs, float* rew
     if (!env || !actions) return fail(CL_ERR_INVALID, "cl_step: null argument");
     if (env->t < 0) return fail(CL_ERR_STATE, "cl_step: call cl_reset first");
     if (env->t >= env->T - 1) return fail(CL_ERR_STATE, "cl_step: episode has ended (terminated); call cl_reset");
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (env->precision == CL_PRECISION_FP64) {
-        if (env->thermal) launch_step<double, true>(env, actions, obs, reward, district, trace, st);
-        else launch_step<double, false>(env, actions, obs, reward, district, trace, st);
-    } else {
-        if (env->thermal) launch_step<float, true>(env, actions, obs, reward, district, trace, st);
-        else launch_step<float, false>(env, actions, obs, reward, district, trace, st);
-    }
-    env->launches++;
+    dispatch_advance(env, 1, actions, obs, reward, district, trace, static_cast<cudaStream_t>(stream));
     CUDA_TRY(cudaGetLastError());
     env->t += 1;
     return CL_OK;
@@ -927,15 +834,7 @@ extern "C" int cl_rollout(cl_env* env, int32_t n_steps, const float* actions, fl
     if (n_steps < 1) return fail(CL_ERR_INVALID, "cl_rollout: n_steps must be >= 1");
     if (env->t < 0) return fail(CL_ERR_STATE, "cl_rollout: call cl_reset first");
     if (env->t + n_steps > env->T - 1) return fail(CL_ERR_STATE, "cl_rollout: block runs past the end of the episode");
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (env->precision == CL_PRECISION_FP64) {
-        if (env->thermal) launch_rollout<double, true>(env, n_steps, actions, obs, reward, district, st);
-        else launch_rollout<double, false>(env, n_steps, actions, obs, reward, district, st);
-    } else {
-        if (env->thermal) launch_rollout<float, true>(env, n_steps, actions, obs, reward, district, st);
-        else launch_rollout<float, false>(env, n_steps, actions, obs, reward, district, st);
-    }
-    env->launches++;
+    dispatch_advance(env, n_steps, actions, obs, reward, district, nullptr, static_cast<cudaStream_t>(stream));
     CUDA_TRY(cudaGetLastError());
     env->t += n_steps;
     return CL_OK;

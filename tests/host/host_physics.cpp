@@ -31,7 +31,7 @@ static void load_params_host(const double* P, const int32_t* ip, int B, int b, B
 #undef LD
 }
 
-// state: double [6][U] (soc_b, cap_deg, eff_b, soc_cs, soc_hs, soc_ds); dyn out: float [U][CL_NDYN]
+// state: double [6][U] (soc_b, cap_deg, rte_b = sqrt(efficiency), soc_cs, soc_hs, soc_ds); dyn out: float [U][CL_NDYN]
 template <typename R>
 static void step_impl(int B, int E, int W, const double* P, const int32_t* ip, const float* table, const int32_t* start, int t,
                       const float* outage, int T, const float* actions, int A, double* state, float* dyn_out,
@@ -67,11 +67,11 @@ static void step_impl(int B, int E, int W, const double* P, const int32_t* ip, c
             in.control_cooling_demand = control_cool && control_cool[u];
             in.control_heating_demand = false;
             UnitState<R> s;
-            s.soc_b = (R)state[0 * U + u]; s.cap_deg = (R)state[1 * U + u]; s.eff_b = (R)state[2 * U + u];
+            s.soc_b = (R)state[0 * U + u]; s.cap_deg = (R)state[1 * U + u]; s.rte_b = (R)state[2 * U + u];
             s.soc_cs = (R)state[3 * U + u]; s.soc_hs = (R)state[4 * U + u]; s.soc_ds = (R)state[5 * U + u];
             UnitResult<R> o;
             unit_step<R, true, R>(p, curves.data() + b, B, t, in, s, o);
-            state[0 * U + u] = (double)s.soc_b; state[1 * U + u] = (double)s.cap_deg; state[2 * U + u] = (double)s.eff_b;
+            state[0 * U + u] = (double)s.soc_b; state[1 * U + u] = (double)s.cap_deg; state[2 * U + u] = (double)s.rte_b;
             state[3 * U + u] = (double)s.soc_cs; state[4 * U + u] = (double)s.soc_hs; state[5 * U + u] = (double)s.soc_ds;
             float* d = dyn_out + (size_t)u * CL_NDYN;
             d[CL_DYN_ELECTRICAL_STORAGE_SOC] = (float)s.soc_b; d[CL_DYN_COOLING_STORAGE_SOC] = (float)s.soc_cs;

@@ -44,7 +44,7 @@ def run_host(hostlib, spec, acts, precision, E=1):
     tile = lambda v: np.tile(v, E)   # noqa: E731
     state[0] = tile(np.float32(spec.params[:, P['BAT_INITIAL_SOC']]))
     state[1] = tile(spec.params[:, P['BAT_CAPACITY']])
-    state[2] = tile(spec.params[:, P['BAT_EFFICIENCY0']])
+    state[2] = tile(np.sqrt(spec.params[:, P['BAT_EFFICIENCY0']]))
     state[3] = tile(np.float32(spec.params[:, P['CS_INITIAL_SOC']]))
     state[4] = tile(np.float32(spec.params[:, P['HS_INITIAL_SOC']]))
     state[5] = tile(np.float32(spec.params[:, P['DS_INITIAL_SOC']]))
