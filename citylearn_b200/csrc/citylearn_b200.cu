@@ -9,6 +9,7 @@
 //   outage   float  [B][T]            power-outage signal of the running episode
 //   start    int32  [E]               table row of time step 0 of every env
 //   state    float  [6][E*B]  (+ double [2][E*B] in CL_PRECISION_FP64)   unit index u = e * B + b (building fastest)
+//   lstm     float  [90][E*B]         h, c of both layers and the two fed-back input windows (LSTM dynamics districts)
 //
 // Kernels: `advance_kernel` (K >= 1 consecutive time steps in one launch: cl_step is K = 1, cl_rollout any K) and
 // `reset_kernel`.
@@ -43,6 +44,8 @@ struct Dev {
     const int32_t* tcol;   // [L] >= 0: table column, -1: zero (stale DYN slot), <= -2: outage signal of building (-2 - tcol)
     const float* outage;   // [B][T] or nullptr
     const int32_t* start;  // [E]
+    const float* lstm_w;   // packed LSTM weights [B][kLstmStride] (buildings without dynamics: zeros)
+    float* lst;            // LSTM state [kLstmStateFloats][U] (dynamics districts only)
     float* st;             // [6][U]
     double* dst;           // [2][U] (fp64 mode)
 };
@@ -62,6 +65,9 @@ template <typename R> struct UnitCtx {
     int c_dhw, c_cool, c_heat, c_tout, c_hvac;
     int a_cd, a_hd, a_coh, a_cs, a_hs, a_ds;
     int c_coolsp, c_heatsp, c_band;
+    // LSTM dynamics
+    int dyn_c_inputs, dyn_n_inputs, dyn_slot_tin, dyn_slot_cdem, dyn_lookback;
+    float tin_min, tin_range, cdem_min, cdem_range;
 };
 
 template <typename R, bool THERMAL>
@@ -98,6 +104,12 @@ __device__ __forceinline__ void load_ctx(const Dev& d, int b, UnitCtx<R>& c) {
         c.c_tout = LDI(CL_IP_C_T_OUT);
         c.a_cd = LDI(CL_IP_A_COOLING_DEVICE); c.a_hd = LDI(CL_IP_A_HEATING_DEVICE); c.a_coh = LDI(CL_IP_A_COOLING_OR_HEATING_DEVICE);
         c.a_cs = LDI(CL_IP_A_COOLING_STORAGE); c.a_hs = LDI(CL_IP_A_HEATING_STORAGE); c.a_ds = LDI(CL_IP_A_DHW_STORAGE);
+        c.dyn_c_inputs = LDI(CL_IP_DYN_C_INPUTS); c.dyn_n_inputs = LDI(CL_IP_DYN_N_INPUTS); c.dyn_slot_tin = LDI(CL_IP_DYN_SLOT_TIN);
+        c.dyn_slot_cdem = LDI(CL_IP_DYN_SLOT_CDEM); c.dyn_lookback = LDI(CL_IP_DYN_LOOKBACK);
+        // normalisation constants: (float32 - python min) / (python max - python min) is float32 arithmetic (building.py:3070-3078)
+        const double tmin = __ldg(d.pd + CL_P_DYN_TIN_MIN * B + b), tmax = __ldg(d.pd + CL_P_DYN_TIN_MAX * B + b);
+        const double cmin = __ldg(d.pd + CL_P_DYN_CDEM_MIN * B + b), cmax = __ldg(d.pd + CL_P_DYN_CDEM_MAX * B + b);
+        c.tin_min = (float)tmin; c.tin_range = (float)(tmax - tmin); c.cdem_min = (float)cmin; c.cdem_range = (float)(cmax - cmin);
     }
 #undef LD
 #undef LDI
@@ -386,7 +398,7 @@ static size_t smem_bytes(const Dev& d, int nt, bool with_dyn, int rsize) {
 
 template <typename R, bool THERMAL>
 __device__ __forceinline__ void reward_inputs(const Dev& d, const UnitCtx<R>& c, const UnitState<R>& s, const UnitResult<R>& o,
-                                              const float* row, RewardIn& ri) {
+                                              const float* row, float t_in, RewardIn& ri) {
     const BuildingParams<R>& p = c.p;
     ri.net = (float)o.net; ri.district_net = 0.f;
     ri.soc_b = (float)s.soc_b; ri.soc_cs = (float)s.soc_cs; ri.soc_hs = (float)s.soc_hs; ri.soc_ds = (float)s.soc_ds;
@@ -396,11 +408,62 @@ __device__ __forceinline__ void reward_inputs(const Dev& d, const UnitCtx<R>& c,
         ri.cool_dem = (float)(o.e_from_cool + fabs(rmin(o.eb_cs, (R)0)));
         ri.heat_dem = (float)(o.e_from_heat + fabs(rmin(o.eb_hs, (R)0)));
     } else { ri.cap_cs = ri.cap_hs = ri.cap_ds = 0.f; ri.cool_dem = ri.heat_dem = 0.f; }
-    ri.t_in = row[c.c_tin];
+    ri.t_in = t_in;
     if (d.reward_id == CL_REWARD_COMFORT || d.reward_id == CL_REWARD_SOLAR_PENALTY_AND_COMFORT) {
         ri.cool_sp = row[c.c_coolsp]; ri.heat_sp = row[c.c_heatsp]; ri.band_series = row[c.c_band];
         ri.hvac_mode = (int)row[c.c_hvac];
     } else { ri.cool_sp = ri.heat_sp = ri.band_series = 0.f; ri.hvac_mode = 0; }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// LSTM dynamics of one unit after its physics at step t (building.py:2935-2942, 3000-3078).
+// The two action-dependent inputs (cooling demand, indoor temperature) live in per-unit ring windows indexed by time step;
+// the exogenous inputs come pre-normalised from the table.  Returns the indoor temperature of step t (prediction once the
+// window is full, else the dataset value).
+// ------------------------------------------------------------------------------------------------------------------
+template <typename R>
+__device__ __forceinline__ float lstm_update(const Dev& d, const UnitCtx<R>& c, const float* W, int u, int t, int row0 /* table row of step 0 */,
+                                             float obs_cool_dem, float t_in_dataset) {
+    const int U = d.U;
+    const int L = c.dyn_lookback, ring = L + 1;
+    float* lst = d.lst;
+    float* win_c = lst + (size_t)(4 * kLstmH) * U + u;                     // [ring][U]
+    float* win_t = lst + (size_t)(4 * kLstmH + kLstmMaxLookback + 1) * U + u;
+    // _update_dynamics_input: append the normalised observation of step t (float32 arithmetic)
+    if (c.dyn_slot_cdem >= 0) win_c[(size_t)(t % ring) * U] = (obs_cool_dem - c.cdem_min) / c.cdem_range;
+    win_t[(size_t)(t % ring) * U] = (t_in_dataset - c.tin_min) / c.tin_range;
+    if (t < L) return t_in_dataset;                                         // window not full yet (building.py:2996-2998)
+    float h0[kLstmH], h1[kLstmH], c0[kLstmH], c1[kLstmH];
+#pragma unroll
+    for (int j = 0; j < kLstmH; ++j) {
+        h0[j] = lst[(size_t)j * U + u]; h1[j] = lst[(size_t)(kLstmH + j) * U + u];
+        c0[j] = lst[(size_t)(2 * kLstmH + j) * U + u]; c1[j] = lst[(size_t)(3 * kLstmH + j) * U + u];
+    }
+#pragma unroll 1
+    for (int sidx = 0; sidx < L; ++sidx) {
+        const int tau = t - (L - 1) + sidx;                                 // time step of the non-fed-back inputs
+        const float* row = d.table + (size_t)(row0 + tau) * d.Wp + c.dyn_c_inputs;
+        float x[kLstmIn];
+#pragma unroll
+        for (int i = 0; i < kLstmIn; ++i) x[i] = i < c.dyn_n_inputs ? __ldg(row + i) : 0.f;
+        const float xc = c.dyn_slot_cdem >= 0 ? win_c[(size_t)(tau % ring) * U] : 0.f;
+        const float xt = win_t[(size_t)((tau - 1) % ring) * U];             // indoor temperature is lagged by one step (building.py:3044-3049)
+#pragma unroll
+        for (int i = 0; i < kLstmIn; ++i) { if (i == c.dyn_slot_cdem) x[i] = xc; if (i == c.dyn_slot_tin) x[i] = xt; }
+        lstm_cell(W, x, h0, c0);
+        lstm_cell(W + kLstmLayerStride, h0, h1, c1);
+    }
+    const float* wl = W + 2 * kLstmLayerStride;
+    float y = wl[16];
+#pragma unroll
+    for (int j = 0; j < kLstmH; ++j) y = fmaf(wl[j], h1[j], y);
+#pragma unroll
+    for (int j = 0; j < kLstmH; ++j) {
+        lst[(size_t)j * U + u] = h0[j]; lst[(size_t)(kLstmH + j) * U + u] = h1[j];
+        lst[(size_t)(2 * kLstmH + j) * U + u] = c0[j]; lst[(size_t)(3 * kLstmH + j) * U + u] = c1[j];
+    }
+    win_t[(size_t)(t % ring) * U] = y;                                       // the prediction replaces the slot (building.py:3027-3028)
+    return y * c.tin_range + c.tin_min;                                      // de-normalised (building.py:3031-3037)
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -411,7 +474,7 @@ __device__ __forceinline__ void reward_inputs(const Dev& d, const UnitCtx<R>& c,
 // requested as soon as every thread is done with the row of step t.  One block barrier per step (two when a reward needs the
 // district sum, three for central-agent sums): `red`, `tmpl` and `dsum` are double-buffered by step parity.
 // ------------------------------------------------------------------------------------------------------------------
-template <typename R, bool THERMAL, int MAXT>
+template <typename R, bool THERMAL, bool DYNAMICS, int MAXT>
 __global__ void __launch_bounds__(MAXT) advance_kernel(Dev d, int t0, int K, const float* __restrict__ actions, float* __restrict__ obs,
                                                         float* __restrict__ reward, float* __restrict__ district, float* __restrict__ trace) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -456,6 +519,7 @@ __global__ void __launch_bounds__(MAXT) advance_kernel(Dev d, int t0, int K, con
         start_e = __ldg(d.start + e);
     }
     const R* curves = scurves + (active ? b : 0) * 32;
+    const float* lstm_w = DYNAMICS ? d.lstm_w + (size_t)(active ? b : 0) * kLstmStride : nullptr;
     __syncthreads();   // barriers initialised, curves / tcol staged
 
     for (int k = 0; k < K; ++k) {
@@ -480,14 +544,24 @@ __global__ void __launch_bounds__(MAXT) advance_kernel(Dev d, int t0, int K, con
             UnitInputs<R> in;
             load_inputs<R, THERMAL>(d, c, row, b, t, in);
             load_actions<R, THERMAL>(c, actions + ((size_t)k * d.E + e) * d.A, in);
+            if (DYNAMICS && (c.p.flags & CL_F_DYNAMICS) && t > c.dyn_lookback) {
+                // partial-load control is live once the input window is full (building.py:3108, 3144)
+                in.control_cooling_demand = (c.a_cd >= 0 || c.a_coh >= 0);
+                in.control_heating_demand = (c.a_hd >= 0 || c.a_coh >= 0);
+            }
             unit_step<R, THERMAL>(c.p, curves, 1, t, in, s, o);
+            float t_in = row[c.c_tin];
+            if (DYNAMICS && (c.p.flags & CL_F_DYNAMICS)) {
+                const float cd = (float)(o.e_from_cool + fabs(rmin(o.eb_cs, (R)0)));
+                t_in = lstm_update<R>(d, c, lstm_w, u, t, start_e, cd, t_in);
+            }
             red[tid] = (float)o.net;
             red[nt + tid] = (float)o.cost;
             red[2 * nt + tid] = (float)o.emission;
-            if (fused_reward) reward_inputs<R, THERMAL>(d, c, s, o, row, ri);     // everything the reward needs from row t
+            if (fused_reward) reward_inputs<R, THERMAL>(d, c, s, o, row, t_in, ri);     // everything the reward needs from row t
             if (trace != nullptr || want_dyn) {
                 float dyn[CL_NDYN];
-                fill_dyn<R>(c.p, s, o, (R)row[c.c_tin], dyn);
+                fill_dyn<R>(c.p, s, o, (R)t_in, dyn);
                 if (trace != nullptr) {
 #pragma unroll
                     for (int j = 0; j < CL_NDYN; ++j) trace[(size_t)u * CL_NDYN + j] = dyn[j];
@@ -584,6 +658,9 @@ __global__ void __launch_bounds__(MAXT) reset_kernel(Dev d, float* __restrict__ 
         s.soc_hs = Num<R>::r32((R)__ldg(P + CL_P_HS_INITIAL_SOC * B + b));
         s.soc_ds = Num<R>::r32((R)__ldg(P + CL_P_DS_INITIAL_SOC * B + b));
         store_state<R, true>(d, u, s);
+        if (d.lst != nullptr) {
+            for (int j = 0; j < kLstmStateFloats; ++j) d.lst[(size_t)j * d.U + u] = 0.f;   // dynamics.py:112-127
+        }
         if (obs != nullptr) {
             const float* row = d.table + (size_t)__ldg(d.start + e) * d.Wp;
             UnitInputs<R> in;
@@ -623,7 +700,8 @@ struct cl_env {
     std::vector<void*> allocs;
     float* outage_dev = nullptr;
     int outage_T = 0;
-    size_t st_floats = 0, dst_doubles = 0;
+    size_t st_floats = 0, dst_doubles = 0, lst_floats = 0;
+    bool dynamics = false;
 };
 
 using namespace cl;
@@ -666,7 +744,43 @@ extern "C" int cl_create(const cl_district_desc* desc, cl_env** out) {
     }
     env->thermal = any_thermal != 0;
     d.any_dynamics = any_dyn != 0;
-    if (any_dyn) { delete env; return fail(CL_ERR_UNSUPPORTED, "cl_create: LSTM dynamics buildings are not supported by this build"); }
+    env->dynamics = any_dyn != 0;
+    if (any_dyn) {
+        // repack every building's LSTM block (schema.py order: W_ih0 [64,nin], W_hh0 [64,16], b_ih0, b_hh0, W_ih1 [64,16], W_hh1, b_ih1,
+        // b_hh1, w_lin [16], b_lin) into the padded device layout of unit_physics.cuh
+        if (!desc->lstm_weights) { delete env; return fail(CL_ERR_INVALID, "cl_create: dynamics buildings without lstm_weights"); }
+        std::vector<float> packed((size_t)B * kLstmStride, 0.f);
+        for (int b = 0; b < B; ++b) {
+            if (!(desc->iparams[CL_IP_FLAGS * B + b] & CL_F_DYNAMICS)) continue;
+            const int nin = desc->iparams[CL_IP_DYN_N_INPUTS * B + b], H = desc->iparams[CL_IP_DYN_HIDDEN * B + b];
+            const int L = desc->iparams[CL_IP_DYN_LOOKBACK * B + b], off = desc->iparams[CL_IP_DYN_W_OFFSET * B + b];
+            if (H != kLstmH || nin < 1 || nin > kLstmIn || L < 1 || L > kLstmMaxLookback) {
+                delete env;
+                return fail(CL_ERR_UNSUPPORTED, "cl_create: LSTM dynamics supports hidden_size 16, <= 16 inputs, lookback <= 12, 2 layers");
+            }
+            const size_t need = (size_t)64 * nin + 64 * 16 + 128 + 2 * 64 * 16 + 128 + 16 + 1;
+            if (off < 0 || (size_t)off + need > (size_t)desc->lstm_weight_count) { delete env; return fail(CL_ERR_INVALID, "cl_create: lstm_weights block out of range"); }
+            const float* w = desc->lstm_weights + off;
+            float* o = &packed[(size_t)b * kLstmStride];
+            const float* wih0 = w; const float* whh0 = wih0 + 64 * nin; const float* bih0 = whh0 + 64 * 16; const float* bhh0 = bih0 + 64;
+            const float* wih1 = bhh0 + 64; const float* whh1 = wih1 + 64 * 16; const float* bih1 = whh1 + 64 * 16; const float* bhh1 = bih1 + 64;
+            const float* wl = bhh1 + 64; const float* bl = wl + 16;
+            for (int r = 0; r < 64; ++r) {
+                for (int i = 0; i < nin; ++i) o[r * 16 + i] = wih0[r * nin + i];
+                for (int i = 0; i < 16; ++i) o[64 * 16 + r * 16 + i] = whh0[r * 16 + i];
+                o[64 * 32 + r] = bih0[r] + bhh0[r];
+                for (int i = 0; i < 16; ++i) o[kLstmLayerStride + r * 16 + i] = wih1[r * 16 + i];
+                for (int i = 0; i < 16; ++i) o[kLstmLayerStride + 64 * 16 + r * 16 + i] = whh1[r * 16 + i];
+                o[kLstmLayerStride + 64 * 32 + r] = bih1[r] + bhh1[r];
+            }
+            for (int i = 0; i < 16; ++i) o[2 * kLstmLayerStride + i] = wl[i];
+            o[2 * kLstmLayerStride + 16] = bl[0];
+        }
+        float* pw = nullptr;
+        int rc = dev_copy(env, packed.data(), packed.size(), &pw);
+        if (rc) { cl_destroy(env); return rc; }
+        d.lstm_w = pw;
+    }
     // padded table
     {
         std::vector<float> padded((size_t)d.n_rows * d.Wp, 0.f);
@@ -709,6 +823,12 @@ extern "C" int cl_create(const cl_district_desc* desc, cl_env** out) {
             env->allocs.push_back(p); d.dst = static_cast<double*>(p);
             cudaMemset(p, 0, env->dst_doubles * sizeof(double));
         }
+        env->lst_floats = any_dyn ? (size_t)kLstmStateFloats * d.U : 0;
+        if (env->lst_floats) {
+            if (cudaMalloc(&p, env->lst_floats * sizeof(float)) != cudaSuccess) { cl_destroy(env); return fail(CL_ERR_CUDA, "cl_create: LSTM state allocation failed"); }
+            env->allocs.push_back(p); d.lst = static_cast<float*>(p);
+            cudaMemset(p, 0, env->lst_floats * sizeof(float));
+        }
         if (cudaMalloc(&p, (size_t)d.E * sizeof(int32_t)) != cudaSuccess) { cl_destroy(env); return fail(CL_ERR_CUDA, "cl_create: start allocation failed"); }
         env->allocs.push_back(p); d.start = static_cast<int32_t*>(p);
     }
@@ -728,7 +848,10 @@ extern "C" int cl_create(const cl_district_desc* desc, cl_env** out) {
     if (smem > 200 * 1024) { cl_destroy(env); return fail(CL_ERR_UNSUPPORTED, "cl_create: district too wide for the shared-memory staging"); }
 #define OPTIN(K) cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
 #define OPTIN4(K, M) OPTIN((K<float, false, M>)); OPTIN((K<float, true, M>)); OPTIN((K<double, false, M>)); OPTIN((K<double, true, M>))
-    OPTIN4(advance_kernel, 512); OPTIN4(advance_kernel, 1024); OPTIN4(reset_kernel, 512); OPTIN4(reset_kernel, 1024);
+#define OPTINA(M) OPTIN((advance_kernel<float, false, false, M>)); OPTIN((advance_kernel<float, true, false, M>)); OPTIN((advance_kernel<float, true, true, M>)); \
+    OPTIN((advance_kernel<double, false, false, M>)); OPTIN((advance_kernel<double, true, false, M>)); OPTIN((advance_kernel<double, true, true, M>))
+    OPTINA(512); OPTINA(1024); OPTIN4(reset_kernel, 512); OPTIN4(reset_kernel, 1024);
+#undef OPTINA
 #undef OPTIN4
 #undef OPTIN
     cudaError_t e = cudaGetLastError();
@@ -770,20 +893,22 @@ static void launch_reset(cl_env* env, float* obs, cudaStream_t st) {
     if (env->threads <= 512) reset_kernel<R, TH, 512><<<env->blocks, env->threads, smem, st>>>(env->d, obs);
     else reset_kernel<R, TH, 1024><<<env->blocks, env->threads, smem, st>>>(env->d, obs);
 }
-template <typename R, bool TH>
+template <typename R, bool TH, bool DY>
 static void launch_advance(cl_env* env, int K, const float* actions, float* obs, float* reward, float* district, float* trace, cudaStream_t st) {
     const bool want_dyn = !env->d.stale && obs != nullptr;
     const size_t smem = smem_bytes(env->d, env->threads, want_dyn, (int)sizeof(R));
-    if (env->threads <= 512) advance_kernel<R, TH, 512><<<env->blocks, env->threads, smem, st>>>(env->d, env->t, K, actions, obs, reward, district, trace);
-    else advance_kernel<R, TH, 1024><<<env->blocks, env->threads, smem, st>>>(env->d, env->t, K, actions, obs, reward, district, trace);
+    if (env->threads <= 512) advance_kernel<R, TH, DY, 512><<<env->blocks, env->threads, smem, st>>>(env->d, env->t, K, actions, obs, reward, district, trace);
+    else advance_kernel<R, TH, DY, 1024><<<env->blocks, env->threads, smem, st>>>(env->d, env->t, K, actions, obs, reward, district, trace);
 }
 static void dispatch_advance(cl_env* env, int K, const float* actions, float* obs, float* reward, float* district, float* trace, cudaStream_t st) {
     if (env->precision == CL_PRECISION_FP64) {
-        if (env->thermal) launch_advance<double, true>(env, K, actions, obs, reward, district, trace, st);
-        else launch_advance<double, false>(env, K, actions, obs, reward, district, trace, st);
+        if (env->dynamics) launch_advance<double, true, true>(env, K, actions, obs, reward, district, trace, st);
+        else if (env->thermal) launch_advance<double, true, false>(env, K, actions, obs, reward, district, trace, st);
+        else launch_advance<double, false, false>(env, K, actions, obs, reward, district, trace, st);
     } else {
-        if (env->thermal) launch_advance<float, true>(env, K, actions, obs, reward, district, trace, st);
-        else launch_advance<float, false>(env, K, actions, obs, reward, district, trace, st);
+        if (env->dynamics) launch_advance<float, true, true>(env, K, actions, obs, reward, district, trace, st);
+        else if (env->thermal) launch_advance<float, true, false>(env, K, actions, obs, reward, district, trace, st);
+        else launch_advance<float, false, false>(env, K, actions, obs, reward, district, trace, st);
     }
     env->launches++;
 }
@@ -848,7 +973,7 @@ extern "C" int cl_time_step(const cl_env* env, int32_t* t) {
 
 extern "C" int cl_state_size(const cl_env* env, size_t* bytes) {
     if (!env || !bytes) return fail(CL_ERR_INVALID, "cl_state_size: null argument");
-    *bytes = env->st_floats * sizeof(float) + env->dst_doubles * sizeof(double);
+    *bytes = env->st_floats * sizeof(float) + env->dst_doubles * sizeof(double) + env->lst_floats * sizeof(float);
     return CL_OK;
 }
 
@@ -861,6 +986,8 @@ extern "C" int cl_get_state(cl_env* env, void* dst_dev, cl_stream stream) {
         p += env->dst_doubles * sizeof(double);
     }
     CUDA_TRY(cudaMemcpyAsync(p, env->d.st, env->st_floats * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    p += env->st_floats * sizeof(float);
+    if (env->lst_floats) CUDA_TRY(cudaMemcpyAsync(p, env->d.lst, env->lst_floats * sizeof(float), cudaMemcpyDeviceToDevice, st));
     return CL_OK;
 }
 
@@ -874,6 +1001,8 @@ extern "C" int cl_set_state(cl_env* env, const void* src_dev, int32_t time_step,
         p += env->dst_doubles * sizeof(double);
     }
     CUDA_TRY(cudaMemcpyAsync(env->d.st, p, env->st_floats * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    p += env->st_floats * sizeof(float);
+    if (env->lst_floats) CUDA_TRY(cudaMemcpyAsync(env->d.lst, p, env->lst_floats * sizeof(float), cudaMemcpyDeviceToDevice, st));
     env->t = time_step;
     return CL_OK;
 }

@@ -17,6 +17,8 @@ from helpers import (TRACE_TO_DYN, actions_of, load_golden, max_abs_diff, observ
 pytestmark = pytest.mark.gpu
 
 NON_LSTM_CASES = ['c1_phase1_300', 'c1_phase1_central', 'c1_episodes', 'c2_marl', 'c2_isac', 'c2_solar_penalty', 'c2_central_exp2', 'c2_year']
+# 2023 schema: heat pump + electric heater + DHW tank + battery + outages + LSTM indoor-temperature dynamics (BASELINE configs[2])
+LSTM_CASES = ['c3_marl', 'c3_default_central_comfort', 'c3_solar_comfort']
 
 
 def make_env(cfg, **kw):
@@ -25,10 +27,11 @@ def make_env(cfg, **kw):
     return CityLearnEnv(sch, data_source=src, **ov, **kw)
 
 
-@pytest.mark.parametrize('case', NON_LSTM_CASES)
+@pytest.mark.parametrize('case', NON_LSTM_CASES + LSTM_CASES)
 def test_single_env_matches_reference_traces(case):
     """num_envs=1, nested-list actions, fp64 flow: observations / district / physics identical to the reference run."""
     z, cfg, meta = load_golden(case)
+    lstm = case in LSTM_CASES      # torch's float32 GEMM order is not reproducible: the predicted temperature gets a tolerance
     env = make_env(cfg, num_envs=1, debug_trace=True)
     tn = cfg['trace_names']
     acts = actions_of(z)
@@ -54,19 +57,19 @@ def test_single_env_matches_reference_traces(case):
                 flat = np.array([v for row in obs for v in row], dtype='float32')
                 assert max_abs_diff(flat, z['obs'][gi]) == 0.0, f'obs step {k}'
                 r = np.array(rew, dtype='float32')
-                ok, w = within_scaled_tolerance(r, z['reward'][gi], 1.0, rtol=2e-7)
+                ok, w = within_scaled_tolerance(r, z['reward'][gi], 1.0, rtol=1e-5 if lstm else 2e-7)
                 assert ok, f'reward step {k}: {w}'
                 assert max_abs_diff(env.district[0].cpu().numpy(), z['district'][gi]) == 0.0, f'district step {k}'
                 tr = env.trace[0].cpu().numpy()
                 for gn, dn in TRACE_TO_DYN.items():
-                    tol = 3e-7 if gn == 'electrical_storage_degraded_capacity' else 0.0
+                    tol = 3e-7 if gn == 'electrical_storage_degraded_capacity' else (3e-5 if (lstm and gn == 'indoor_dry_bulb_temperature') else 0.0)
                     assert max_abs_diff(tr[:, DYN[dn]], z['trace'][gi, :, tn.index(gn)]) <= tol, f'{gn} step {k}'
                 assert term == bool(z['terminated'][gi])
                 gi += 1
         assert env.terminated == (K == env.time_steps - 1)
     assert gi == len(z['steps'])
     if 'episode_reward_sum' in z.files and cfg['episodes'] == 1:
-        np.testing.assert_allclose(env.episode_rewards[-1]['sum'], z['episode_reward_sum'], rtol=2e-5)
+        np.testing.assert_allclose(env.episode_rewards[-1]['sum'], z['episode_reward_sum'], rtol=1e-4 if lstm else 2e-5)
     assert env.gpu_launches > 0
 
 
@@ -236,3 +239,33 @@ def test_error_paths():
     with pytest.raises(ValueError):
         env.reset()
         env.step([[0.0]] * 5)      # nested lists need num_envs == 1
+
+
+def test_lstm_district_batched_matches_oracle():
+    """2023 schema, 3 LSTM buildings x 48 envs with distinct actions, fp64 flow vs the vectorised oracle (200 steps incl. outages)."""
+    from citylearn_b200 import CityLearnEnv
+    from citylearn_b200.data import DataSet
+    from citylearn_oracle import OracleEnv
+    src = DataSet.get_source('citylearn_challenge_2023_phase_2_local_evaluation')
+    sch = src.schema()
+    sch['reward_function'] = {'type': 'citylearn.reward_function.MARL', 'attributes': {}}
+    E, K = 48, 200
+    env = CityLearnEnv(sch, data_source=src, central_agent=False, num_envs=E, debug_trace=True)
+    oracle = OracleEnv(env.spec, E)
+    o0 = oracle.reset()
+    obs, _ = env.reset()
+    assert max_abs_diff(obs.cpu().numpy(), o0.astype('float32')) == 0.0
+    rng = np.random.RandomState(21)
+    lo = np.concatenate([b.action_low for b in env.spec.buildings])
+    hi = np.concatenate([b.action_high for b in env.spec.buildings])
+    for k in range(K):
+        a = (lo + rng.uniform(0, 1, size=(E, env.spec.action_dim)) * (hi - lo)).astype('float32')
+        obs, rew, _, _, _ = env.step(a)
+        oobs, orew, odist, odyn = oracle.step(a)
+        assert max_abs_diff(obs.cpu().numpy(), oobs) == 0.0
+        tr = env.trace.cpu().numpy()
+        for n in ('electrical_storage_soc', 'dhw_storage_soc', 'net_electricity_consumption', 'cooling_electricity_consumption',
+                  'dhw_electricity_consumption', 'cooling_demand'):
+            assert np.array_equal(tr[..., DYN[n]], odyn[..., DYN[n]].astype('float32')), (n, k)
+        assert max_abs_diff(tr[..., DYN['indoor_dry_bulb_temperature']], odyn[..., DYN['indoor_dry_bulb_temperature']]) < 3e-5
+        assert np.array_equal(rew.cpu().numpy(), orew)          # MARL does not read the temperature
