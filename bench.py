@@ -75,9 +75,35 @@ class ClockSampler:
             self.ok = True
         except Exception:
             self.ok = False
-            return
+            return self._start_smi()
         self.thread = threading.Thread(target=self._run, daemon=True)
         self.thread.start()
+
+    def _start_smi(self):
+        """Fallback: the nvidia-smi line of B200_PROFILING.md at a low rate."""
+        q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+             'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--id={self.index}', f'--query-gpu={q}', '--format=csv,noheader,nounits', '-lms', '250'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            return
+
+        def read():
+            for line in self.proc.stdout:
+                r = [x.strip() for x in line.split(',')]
+                try:
+                    self.sm.append(float(r[0]))
+                    self.max_mhz = float(r[1])
+                    for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[2:6]):
+                        if v.lower().startswith('active'):
+                            self.reasons.add(name)
+                except Exception:
+                    pass
+        self.thread = threading.Thread(target=read, daemon=True)
+        self.thread.start()
+        self.ok = True
+        self.smi = True
 
     def _run(self):
         nv = self.nv
@@ -104,6 +130,8 @@ class ClockSampler:
         if not self.ok:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['unavailable']}
         self._stop.set()
+        if getattr(self, 'smi', False):
+            self.proc.terminate()
         self.thread.join(timeout=2)
         sm = sorted(self.sm)
         return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': self.max_mhz, 'reasons': sorted(self.reasons), 'samples': len(sm)}
