@@ -50,7 +50,7 @@ class ClockSampler:
     """SM clocks / throttle reasons sampled DURING the timed regions through NVML in a background thread
     (same fields as the nvidia-smi line in B200_PROFILING.md, without spawning a process that perturbs the host loop)."""
 
-    def __init__(self, index: int, period_s: float = 0.05):
+    def __init__(self, index: int, period_s: float = 0.1):
         self.index, self.period = index, period_s
         self.sm, self.reasons, self.max_mhz = [], set(), None
         self._stop = threading.Event()
@@ -155,6 +155,29 @@ def cpu_oracle_rate(n_envs: int, steps: int, seed: int = 0):
     return spec.n_buildings * n_envs * steps / dt, dt
 
 
+def effective_cpus() -> int:
+    """Host cores this process may really use: min(affinity, cgroup CPU quota)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    for path in ('/sys/fs/cgroup/cpu.max', '/sys/fs/cgroup/cpu/cpu.cfs_quota_us'):
+        try:
+            txt = open(path).read().split()
+            if path.endswith('cpu.max'):
+                if txt[0] != 'max':
+                    n = min(n, max(1, int(float(txt[0]) / float(txt[1]))))
+            else:
+                q = int(txt[0])
+                if q > 0:
+                    per = int(open('/sys/fs/cgroup/cpu/cpu.cfs_period_us').read())
+                    n = min(n, max(1, q // per))
+            break
+        except Exception:
+            continue
+    return n
+
+
 def _ref_worker(args):
     n_envs, steps, seed = args
     os.environ.setdefault('OMP_NUM_THREADS', '1')
@@ -167,8 +190,7 @@ def run_reference(args):
     if rank != 0:
         return
     import multiprocessing as mp
-    cores = os.cpu_count() or 1
-    procs = max(1, min(cores, 32))
+    procs = max(1, min(effective_cpus(), 128))
     per = max(1, ENVS_PER_GPU // procs)
     steps, warm = args.steps, args.warmup
     ctx = mp.get_context('fork')
@@ -303,9 +325,9 @@ def main():
         pass
     cpu = None
     if not args.no_cpu_baseline:
-        rate, dt = cpu_oracle_rate(256, 40)
+        rate, dt = cpu_oracle_rate(512, 1200)      # ~10-20 s of single-core NumPy work
         cpu = {'value': rate, 'unit': UNIT, 'cores': 1, 'kind': 'port',
-               'sample': f'NumPy oracle, 17 buildings x 256 envs x 40 steps in {dt:.1f}s on 1 core '
+               'sample': f'NumPy oracle, 17 buildings x 512 envs x 1200 steps in {dt:.1f}s on 1 core '
                          f'(reference itself: 871.7 building-steps/s/core, BASELINE.md)'}
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': K, 'warmup': W, 'ms_per_step': ms_max / K,

@@ -359,39 +359,31 @@ __device__ __forceinline__ void write_obs_template(const Dev& d, float* obs, int
 
 // ------------------------------------------------------------------------------------------------------------------
 // shared memory carve-up (dynamic)
-//   [mbarriers 32 B][rows 3*Wp][tcol Lp (int)][tmpl 2*Lp][red 2*3*nt][rsum nt][dsum 2*epb][curves B*32 (R)][dynbuf nt*NDYN (opt)]
+//   [mbarriers 32 B][curves B*32 (R)][rows 3*Wp][tcol Lp (int)][tmpl 2*Lp][red 2*3*nt][rsum nt][dsum 2*epb][dynbuf nt*NDYN (opt)]
 // red / tmpl / dsum are double-buffered by step parity so that a step needs ONE block barrier (see advance_kernel).
 // ------------------------------------------------------------------------------------------------------------------
-struct Smem {
-    uint64_t* bar;
-    float* rows;
-    int32_t* tcol;
-    float* tmpl;    // [2][Lp]
-    float* red;     // [2][3][nt]  net, cost, emission
-    float* rsum;    // [nt]        per-unit rewards (central agent)
-    float* dsum;    // [2][epb]
-    void* curves;   // R [B][32]
-    float* dynbuf;  // [nt][CL_NDYN]
-    int Lp;
+// offsets in floats from the start of the dynamic shared memory (kept as plain ints so that every access is derived
+// directly from the `extern __shared__` array and compiles to LDS/STS with 32-bit addressing, not generic loads)
+struct SmemLayout {
+    int curves, rows, tcol, tmpl, red, rsum, dsum, dynbuf, Lp;
 };
-__device__ __forceinline__ Smem carve(const Dev& d, unsigned char* base, int nt, int rsize) {
-    Smem s;
-    s.Lp = (d.L + 3) & ~3;
-    s.bar = reinterpret_cast<uint64_t*>(base);
-    float* f = reinterpret_cast<float*>(base + 32);
-    s.rows = f; f += 3 * d.Wp;
-    s.tcol = reinterpret_cast<int32_t*>(f); f += s.Lp;
-    s.tmpl = f; f += 2 * s.Lp;
-    s.red = f; f += 6 * nt;
-    s.rsum = f; f += nt;
-    s.dsum = f; f += (2 * d.envs_per_block + 3) & ~3;
-    s.curves = f; f += (size_t)d.B * 32 * (rsize / 4);
-    s.dynbuf = f;
-    return s;
+__host__ __device__ __forceinline__ SmemLayout smem_layout(int B, int Wp, int L, int epb, int nt, int rsize) {
+    SmemLayout o;
+    o.Lp = (L + 3) & ~3;
+    int f = 8;                                   // 32 bytes of mbarriers
+    o.curves = f; f += B * 32 * (rsize / 4);     // first: keeps doubles 8-byte aligned
+    o.rows = f; f += 3 * Wp;
+    o.tcol = f; f += o.Lp;
+    o.tmpl = f; f += 2 * o.Lp;
+    o.red = f; f += 6 * nt;
+    o.rsum = f; f += nt;
+    o.dsum = f; f += (2 * epb + 3) & ~3;
+    o.dynbuf = f;
+    return o;
 }
 static size_t smem_bytes(const Dev& d, int nt, bool with_dyn, int rsize) {
-    const size_t Lp = (d.L + 3) & ~3;
-    size_t n = 32 + sizeof(float) * (3 * (size_t)d.Wp + 3 * Lp + 7 * (size_t)nt + ((2 * (size_t)d.envs_per_block + 3) & ~3) + (size_t)d.B * 32 * (rsize / 4));
+    const SmemLayout o = smem_layout(d.B, d.Wp, d.L, d.envs_per_block, nt, rsize);
+    size_t n = sizeof(float) * (size_t)o.dynbuf;
     if (with_dyn) n += sizeof(float) * (size_t)nt * CL_NDYN;
     return n;
 }
@@ -477,11 +469,17 @@ __device__ __forceinline__ float lstm_update(const Dev& d, const UnitCtx<R>& c, 
 template <typename R, bool THERMAL, bool DYNAMICS, int MAXT>
 __global__ void __launch_bounds__(MAXT) advance_kernel(Dev d, int t0, int K, const float* __restrict__ actions, float* __restrict__ obs,
                                                         float* __restrict__ reward, float* __restrict__ district, float* __restrict__ trace) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(16) float smf[];
     const int nt = blockDim.x, tid = threadIdx.x;
-    Smem sm = carve(d, smem_raw, nt, (int)sizeof(R));
-    R* scurves = reinterpret_cast<R*>(sm.curves);
     const int B = d.B, epb = d.envs_per_block, Wp = d.Wp;
+    const SmemLayout lo = smem_layout(B, Wp, d.L, epb, nt, (int)sizeof(R));
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(smf);
+    R* scurves = reinterpret_cast<R*>(smf + lo.curves);
+    float* s_rows = smf + lo.rows;
+    int32_t* s_tcol = reinterpret_cast<int32_t*>(smf + lo.tcol);
+    float* s_dsum = smf + lo.dsum;
+    float* s_rsum = smf + lo.rsum;
+    float* s_dynbuf = smf + lo.dynbuf;
     const int e0 = blockIdx.x * epb;
     const int n_env = min(epb, d.E - e0);
     const int n_units = n_env * B;
@@ -497,15 +495,15 @@ __global__ void __launch_bounds__(MAXT) advance_kernel(Dev d, int t0, int K, con
     const uint32_t row_bytes = (uint32_t)Wp * sizeof(float);
 
     if (uniform && tid == 0) {
-        for (int i = 0; i < 3; ++i) mbar_init(sm.bar + i, 1);
+        for (int i = 0; i < 3; ++i) mbar_init(s_bar + i, 1);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         for (int i = 0; i < 3 && i <= K; ++i) {     // rows t0 .. t0+2 (row t0+K is the last one any step needs)
-            mbar_expect_tx(sm.bar + i, row_bytes);
-            tma_load_1d(sm.rows + i * Wp, d.table + (size_t)(d.start0 + t0 + i) * Wp, row_bytes, sm.bar + i);
+            mbar_expect_tx(s_bar + i, row_bytes);
+            tma_load_1d(s_rows + i * Wp, d.table + (size_t)(d.start0 + t0 + i) * Wp, row_bytes, s_bar + i);
         }
     }
     // block-wide staging: template columns and the battery curves of every building (dynamic indexing -> shared memory)
-    if (tmpl_path) for (int k = tid; k < d.L; k += nt) sm.tcol[k] = __ldg(d.tcol + k);
+    if (tmpl_path) for (int k = tid; k < d.L; k += nt) s_tcol[k] = __ldg(d.tcol + k);
     {
         const auto* P = PSel<R>::p(d) + CL_P_PE_X0 * B;
         for (int i = tid; i < B * 32; i += nt) { const int bb = i >> 5, j = i & 31; scurves[i] = (R)__ldg(P + j * B + bb); }
@@ -529,15 +527,15 @@ __global__ void __launch_bounds__(MAXT) advance_kernel(Dev d, int t0, int K, con
         const float* row;
         const float* row_next = nullptr;
         if (uniform) {
-            mbar_wait(sm.bar + slot_t, (uint32_t)((k / 3) & 1));
-            mbar_wait(sm.bar + slot_n, (uint32_t)(((k + 1) / 3) & 1));
-            row = sm.rows + slot_t * Wp;
-            row_next = sm.rows + slot_n * Wp;
+            mbar_wait(s_bar + slot_t, (uint32_t)((k / 3) & 1));
+            mbar_wait(s_bar + slot_n, (uint32_t)(((k + 1) / 3) & 1));
+            row = s_rows + slot_t * Wp;
+            row_next = s_rows + slot_n * Wp;
         } else {
             row = d.table + (size_t)(start_e + t) * Wp;
         }
-        float* red = sm.red + pb * 3 * nt;
-        float* tmpl = sm.tmpl + pb * sm.Lp;
+        float* red = smf + lo.red + pb * 3 * nt;
+        float* tmpl = smf + lo.tmpl + pb * lo.Lp;
         UnitResult<R> o;
         RewardIn ri;
         if (active) {
@@ -568,17 +566,17 @@ __global__ void __launch_bounds__(MAXT) advance_kernel(Dev d, int t0, int K, con
                 }
                 if (want_dyn) {
 #pragma unroll
-                    for (int j = 0; j < CL_NDYN; ++j) sm.dynbuf[tid * CL_NDYN + j] = dyn[j];
+                    for (int j = 0; j < CL_NDYN; ++j) s_dynbuf[tid * CL_NDYN + j] = dyn[j];
                 }
             }
         }
-        if (tmpl_path) build_obs_template(d, sm.tcol, row_next, t + 1, tmpl);
+        if (tmpl_path) build_obs_template(d, s_tcol, row_next, t + 1, tmpl);
         __syncthreads();                                                       // S1: red / tmpl / dynbuf of step k complete
         if (uniform && tid == 0 && k + 3 <= K) {
             // nobody reads row t any more (reward inputs were captured above): its slot takes the row of step t + 3
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            mbar_expect_tx(sm.bar + slot_t, row_bytes);
-            tma_load_1d(sm.rows + slot_t * Wp, d.table + (size_t)(d.start0 + t + 3) * Wp, row_bytes, sm.bar + slot_t);
+            mbar_expect_tx(s_bar + slot_t, row_bytes);
+            tma_load_1d(s_rows + slot_t * Wp, d.table + (size_t)(d.start0 + t + 3) * Wp, row_bytes, s_bar + slot_t);
         }
         // district sums in building order, like the reference's sum() over buildings (citylearn.py:1908-1918);
         // one thread per (quantity, env)
@@ -590,29 +588,29 @@ __global__ void __launch_bounds__(MAXT) advance_kernel(Dev d, int t0, int K, con
             int j = 0;
             for (; j + 4 <= B; j += 4) { acc += src[j]; acc += src[j + 1]; acc += src[j + 2]; acc += src[j + 3]; }   // same left-to-right order
             for (; j < B; ++j) acc += src[j];
-            if (q == 0) sm.dsum[pb * epb + le] = acc;
+            if (q == 0) s_dsum[pb * epb + le] = acc;
             if (district != nullptr) district[((size_t)k * d.E + e0 + le) * 3 + q] = acc;
         }
         if (need_dsum) __syncthreads();                                        // S2 only when a reward reads the district sum
         if (fused_reward) {
             float r = 0.f;
             if (active) {
-                if (need_dsum) ri.district_net = sm.dsum[pb * epb + e_l];
+                if (need_dsum) ri.district_net = s_dsum[pb * epb + e_l];
                 r = unit_reward(d.reward_id, d.rp, ri);
             }
             float* rk = reward + (size_t)k * d.E * Rdim;
             if (d.central) {
                 if (k > 0) __syncthreads();                                    // previous step's rsum readers are done
-                sm.rsum[tid] = r;
+                s_rsum[tid] = r;
                 __syncthreads();
                 if (tid < n_env) {
                     float sr = 0.f;
                     if (d.reward_id == CL_REWARD_MARL || d.reward_id == CL_REWARD_SOLAR_PENALTY_AND_COMFORT) {
                         double acc = 0.0;   // these rewards are float64 in the reference
-                        for (int j = 0; j < B; ++j) acc += (double)sm.rsum[tid * B + j];
+                        for (int j = 0; j < B; ++j) acc += (double)s_rsum[tid * B + j];
                         sr = (float)acc;
                     } else {
-                        for (int j = 0; j < B; ++j) sr += sm.rsum[tid * B + j];
+                        for (int j = 0; j < B; ++j) sr += s_rsum[tid * B + j];
                     }
                     rk[e0 + tid] = sr;
                 }
@@ -624,7 +622,7 @@ __global__ void __launch_bounds__(MAXT) advance_kernel(Dev d, int t0, int K, con
             float* ok = obs + (size_t)k * d.E * d.L;
             if (tmpl_path) write_obs_template(d, ok, e0, n_env, tmpl);
             else {
-                write_obs_general(d, ok, e0, n_env, t + 1, want_dyn ? sm.dynbuf : nullptr);
+                write_obs_general(d, ok, e0, n_env, t + 1, want_dyn ? s_dynbuf : nullptr);
                 if (want_dyn && k + 1 < K) __syncthreads();                     // dynbuf is single-buffered
             }
         }
@@ -637,10 +635,11 @@ __global__ void __launch_bounds__(MAXT) advance_kernel(Dev d, int t0, int K, con
 // ------------------------------------------------------------------------------------------------------------------
 template <typename R, bool THERMAL, int MAXT>
 __global__ void __launch_bounds__(MAXT) reset_kernel(Dev d, float* __restrict__ obs) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(16) float smf[];
     const int nt = blockDim.x, tid = threadIdx.x;
-    Smem sm = carve(d, smem_raw, nt, (int)sizeof(R));
     const int B = d.B, epb = d.envs_per_block;
+    const SmemLayout lo = smem_layout(B, d.Wp, d.L, epb, nt, (int)sizeof(R));
+    float* s_dynbuf = smf + lo.dynbuf;
     const int e0 = blockIdx.x * epb;
     const int n_env = min(epb, d.E - e0);
     const int n_units = n_env * B;
@@ -667,12 +666,12 @@ __global__ void __launch_bounds__(MAXT) reset_kernel(Dev d, float* __restrict__ 
             load_inputs<R, THERMAL>(d, c, row, b, 0, in);
             UnitResult<R> o;
             unit_time0<R, THERMAL>(c.p, in, o);
-            fill_dyn<R>(c.p, s, o, (R)row[c.c_tin], sm.dynbuf + tid * CL_NDYN);
+            fill_dyn<R>(c.p, s, o, (R)row[c.c_tin], s_dynbuf + tid * CL_NDYN);
         }
     }
     if (obs != nullptr) {
         __syncthreads();
-        write_obs_general(d, obs, e0, n_env, 0, sm.dynbuf);
+        write_obs_general(d, obs, e0, n_env, 0, s_dynbuf);
     }
 }
 

@@ -136,15 +136,20 @@ class CityLearnEnv:
         with torch.cuda.device(self.device):
             self._h = _native.Handle(spec, self.num_envs, self._desc, self.central_agent, rid, rparams, precision, self.stale_observations)
             E = self.num_envs
-            self._obs = torch.zeros((E, self._obs_dim), dtype=torch.float32, device=self.device)
-            self._reward = torch.zeros((E, self._reward_dim), dtype=torch.float32, device=self.device)
+            # observations and rewards share one allocation so that the host path needs ONE device->host copy per step
+            self._out = torch.zeros(E * (self._obs_dim + self._reward_dim), dtype=torch.float32, device=self.device)
+            self._obs = self._out[:E * self._obs_dim].view(E, self._obs_dim)
+            self._reward = self._out[E * self._obs_dim:].view(E, self._reward_dim)
             self._district = torch.zeros((E, 3), dtype=torch.float32, device=self.device)
             self._trace = (torch.zeros((E, spec.n_buildings, S.NDYN), dtype=torch.float32, device=self.device)
                            if (rid < 0 or debug_trace) else None)
             self._act = torch.zeros((E, max(spec.action_dim, 1)), dtype=torch.float32, device=self.device)
             self._act_pinned = torch.zeros((E, max(spec.action_dim, 1)), dtype=torch.float32).pin_memory()
-            self._obs_pinned = torch.zeros((E, self._obs_dim), dtype=torch.float32).pin_memory()
-            self._reward_pinned = torch.zeros((E, self._reward_dim), dtype=torch.float32).pin_memory()
+            self._act_host = self._act_pinned.numpy()      # same memory; filled with np.copyto (single-threaded memcpy)
+            self._out_pinned = torch.zeros(E * (self._obs_dim + self._reward_dim), dtype=torch.float32).pin_memory()
+            self._obs_pinned = self._out_pinned[:E * self._obs_dim].view(E, self._obs_dim)
+            self._reward_pinned = self._out_pinned[E * self._obs_dim:].view(E, self._reward_dim)
+            self._obs_host, self._reward_host = self._obs_pinned.numpy(), self._reward_pinned.numpy()
         self._table_dev = None
         self.time_step = 0
         self._episode_rewards: List[Mapping[str, Any]] = []
@@ -332,7 +337,9 @@ class CityLearnEnv:
                 a = a.to(device=self.device, dtype=torch.float32, non_blocking=True).contiguous()
             return a, False
         if isinstance(actions, np.ndarray):
-            self._act_pinned.copy_(torch.from_numpy(np.ascontiguousarray(actions, dtype=np.float32).reshape(E, A)))
+            # plain memcpy into the pinned staging buffer: a torch CPU copy_ would fan out over the intra-op thread pool, and
+            # the spinning pool threads can exhaust a container's CPU quota (observed: 70 ms cgroup throttling stalls)
+            np.copyto(self._act_host[:, :A], actions.reshape(E, A), casting='same_kind')
             self._act.copy_(self._act_pinned, non_blocking=True)
             return self._act, False
         actions = list(actions)
@@ -379,12 +386,12 @@ class CityLearnEnv:
         return self._obs, self._reward, terminated, False, self.get_info()
 
     def step_host(self, actions: np.ndarray) -> Tuple[np.ndarray, np.ndarray, bool]:
-        """End-to-end host path: host ndarray actions in, host ndarrays out (pinned staging, one sync)."""
-        obs, rew, terminated, _, _ = self.step(np.asarray(actions, dtype=np.float32))
-        self._obs_pinned.copy_(obs, non_blocking=True)
-        self._reward_pinned.copy_(rew, non_blocking=True)
+        """End-to-end host path: host ndarray actions in, host ndarrays out (pinned staging, one H2D + one D2H copy, one sync).
+        The returned arrays are views of a pinned buffer that the next call overwrites."""
+        _, _, terminated, _, _ = self.step(np.asarray(actions, dtype=np.float32))
+        self._out_pinned.copy_(self._out, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
-        return self._obs_pinned.numpy(), self._reward_pinned.numpy(), terminated
+        return self._obs_host, self._reward_host, terminated
 
     def rollout(self, actions: torch.Tensor, obs: Optional[torch.Tensor] = None, reward: Optional[torch.Tensor] = None,
                 district: Optional[torch.Tensor] = None):
