@@ -38,7 +38,8 @@ PRECISION = {'fp32': 0, 'fp64': 1}
 
 
 def library_path() -> Path:
-    return Path(__file__).resolve().parent / _LIB_NAME
+    override = os.environ.get('CL_B200_LIB')      # debug builds (e.g. tools/phase_timing.py)
+    return Path(override) if override else Path(__file__).resolve().parent / _LIB_NAME
 
 
 def load():

@@ -136,9 +136,11 @@ __device__ __forceinline__ void store_state(const Dev& d, int u, const UnitState
 
 // exogenous inputs of a unit at time step t; `row` points at the time row (shared or global memory)
 template <typename R, bool THERMAL>
-__device__ __forceinline__ void load_inputs(const Dev& d, const UnitCtx<R>& c, const float* row, int b, int t, UnitInputs<R>& in) {
+__device__ __forceinline__ void load_inputs(const Dev& d, const UnitCtx<R>& c, const float* row, int b, int t, UnitInputs<R>& in,
+                                            bool solar_from_block = false) {
     in.nsl = (R)row[c.c_nsl];
-    in.solar = -(c.pv * (R)row[c.c_solar] / (R)1000);            // building.py:2554, energy_model.py:488
+    // building.py:2554, energy_model.py:488; with lock-step rows the helper warp computes it once per building
+    in.solar = solar_from_block ? (R)0 : -dvd(c.pv * (R)row[c.c_solar], (R)1000);
     in.price = (R)row[c.c_price];
     in.carbon = (R)row[c.c_carbon];
     if (THERMAL) {
@@ -152,22 +154,38 @@ __device__ __forceinline__ void load_inputs(const Dev& d, const UnitCtx<R>& c, c
     in.control_heating_demand = false;
 }
 
+// raw action values of one unit for one step (registers); fetched ONE STEP AHEAD so that the HBM latency of the read hides
+// behind the physics of the current step
+struct RawActions { float es, cd, hd, coh, cs, hs, ds; };
+
 template <typename R, bool THERMAL>
-__device__ __forceinline__ void load_actions(const UnitCtx<R>& c, const float* act_row, UnitInputs<R>& in) {
-    in.a_es = c.a_es >= 0 ? (R)__ldg(act_row + c.a_es) : (R)0;
+__device__ __forceinline__ void fetch_actions(const UnitCtx<R>& c, const float* act_row, RawActions& a) {
+    a.es = c.a_es >= 0 ? __ldg(act_row + c.a_es) : 0.f;
+    if (THERMAL) {
+        a.cd = c.a_cd >= 0 ? __ldg(act_row + c.a_cd) : 0.f;
+        a.hd = c.a_hd >= 0 ? __ldg(act_row + c.a_hd) : 0.f;
+        a.coh = c.a_coh >= 0 ? __ldg(act_row + c.a_coh) : 0.f;
+        a.cs = c.a_cs >= 0 ? __ldg(act_row + c.a_cs) : 0.f;
+        a.hs = c.a_hs >= 0 ? __ldg(act_row + c.a_hs) : 0.f;
+        a.ds = c.a_ds >= 0 ? __ldg(act_row + c.a_ds) : 0.f;
+    }
+}
+
+// inactive storage actions are 0, inactive device actions NaN (building.py:1555-1564)
+template <typename R, bool THERMAL>
+__device__ __forceinline__ void apply_actions(const UnitCtx<R>& c, const RawActions& a, UnitInputs<R>& in) {
+    in.a_es = (R)a.es;
     in.a_cooling_device = in.a_heating_device = (R)NAN;
     in.a_cs = in.a_hs = in.a_ds = (R)0;
     if (THERMAL) {
-        if (c.a_cd >= 0) in.a_cooling_device = (R)__ldg(act_row + c.a_cd);
-        if (c.a_hd >= 0) in.a_heating_device = (R)__ldg(act_row + c.a_hd);
+        if (c.a_cd >= 0) in.a_cooling_device = (R)a.cd;
+        if (c.a_hd >= 0) in.a_heating_device = (R)a.hd;
         if (c.a_coh >= 0) {   // building.py:1550-1553
-            const R v = (R)__ldg(act_row + c.a_coh);
+            const R v = (R)a.coh;
             in.a_cooling_device = fabs(rmin(v, (R)0));
             in.a_heating_device = fabs(rmax(v, (R)0));
         }
-        if (c.a_cs >= 0) in.a_cs = (R)__ldg(act_row + c.a_cs);
-        if (c.a_hs >= 0) in.a_hs = (R)__ldg(act_row + c.a_hs);
-        if (c.a_ds >= 0) in.a_ds = (R)__ldg(act_row + c.a_ds);
+        in.a_cs = (R)a.cs; in.a_hs = (R)a.hs; in.a_ds = (R)a.ds;
     }
 }
 
@@ -298,15 +316,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
         : "memory");
 }
 
+__device__ __forceinline__ void tma_store_1d(void* gdst, const void* ssrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+template <int N> __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
+
 // ------------------------------------------------------------------------------------------------------------------
 // observation writers: the rows of a block's envs are one contiguous span obs[e0*L .. (e0+n)*L)
 // ------------------------------------------------------------------------------------------------------------------
 // general path: any descriptor kind, per-env start rows, DYN values from shared memory (or zero)
 __device__ __forceinline__ void write_obs_general(const Dev& d, float* obs, int e0, int n_env, int t_obs,
-                                                   const float* dynbuf /* [n_env*B][CL_NDYN] or nullptr */) {
-    const int L = d.L, nt = blockDim.x;
+                                                   const float* dynbuf /* [n_env*B][CL_NDYN] or nullptr */, int tid, int nt) {
+    const int L = d.L;
     const int total = n_env * L;
-    int j = threadIdx.x;
+    int j = tid;
     int e_l = j / L, k = j - e_l * L;
     const int de = nt / L, dk = nt - de * L;
     for (; j < total; j += nt) {
@@ -326,55 +351,25 @@ __device__ __forceinline__ void write_obs_general(const Dev& d, float* obs, int 
     }
 }
 
-// fast path (uniform start rows, reference-parity observations): every env row equals the template row of the step
-__device__ __forceinline__ void build_obs_template(const Dev& d, const int32_t* tcol, const float* row_next, int t_obs, float* tmpl) {
-    for (int k = threadIdx.x; k < d.L; k += blockDim.x) {
-        const int c = tcol[k];
-        float v;
-        if (c >= 0) v = row_next[c];
-        else if (c == -1) v = 0.f;
-        else v = d.has_outage ? __ldg(d.outage + (-2 - c) * d.T + t_obs) : 0.f;
-        tmpl[k] = v;
-    }
-}
-
-__device__ __forceinline__ void write_obs_template(const Dev& d, float* obs, int e0, int n_env, const float* tmpl) {
-    const int L = d.L;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    float* out = obs + (size_t)e0 * L;
-    if ((L & 3) == 0) {   // 16-byte vector stores; one warp streams one env row at a time: no index arithmetic in the loop
-        const int L4 = L >> 2;
-        const float4* t4 = reinterpret_cast<const float4*>(tmpl);
-        for (int le = warp; le < n_env; le += nwarps) {
-            float4* o4 = reinterpret_cast<float4*>(out + (size_t)le * L);
-            for (int k = lane; k < L4; k += 32) __stcs(o4 + k, t4[k]);   // streaming store: written once, read by the consumer later
-        }
-    } else {
-        for (int le = warp; le < n_env; le += nwarps) {
-            float* o = out + (size_t)le * L;
-            for (int k = lane; k < L; k += 32) __stcs(o + k, tmpl[k]);
-        }
-    }
-}
-
 // ------------------------------------------------------------------------------------------------------------------
 // shared memory carve-up (dynamic)
-//   [mbarriers 32 B][curves B*32 (R)][rows 3*Wp][tcol Lp (int)][tmpl 2*Lp][red 2*3*nt][rsum nt][dsum 2*epb][dynbuf nt*NDYN (opt)]
-// red / tmpl / dsum are double-buffered by step parity so that a step needs ONE block barrier (see advance_kernel).
+//   [mbarriers 32 B][curves B*32 (R)][bsolar 2*B (R)][rows 3*Wp][tcol Lp (int)][tmpl 2*Lp][red 2*3*nt][rsum nt][dsum 2*epb][dynbuf nt*NDYN (opt)]
+// red / dsum / bsolar are double-buffered by step parity so that a step needs ONE block barrier (see advance_kernel).
 // ------------------------------------------------------------------------------------------------------------------
 // offsets in floats from the start of the dynamic shared memory (kept as plain ints so that every access is derived
 // directly from the `extern __shared__` array and compiles to LDS/STS with 32-bit addressing, not generic loads)
 struct SmemLayout {
-    int curves, rows, tcol, tmpl, red, rsum, dsum, dynbuf, Lp;
+    int curves, bsolar, rows, tcol, tmpl, red, rsum, dsum, dynbuf, Lp;
 };
 __host__ __device__ __forceinline__ SmemLayout smem_layout(int B, int Wp, int L, int epb, int nt, int rsize) {
     SmemLayout o;
     o.Lp = (L + 3) & ~3;
     int f = 8;                                   // 32 bytes of mbarriers
     o.curves = f; f += B * 32 * (rsize / 4);     // first: keeps doubles 8-byte aligned
+    o.bsolar = f; f += ((2 * B * (rsize / 4)) + 3) & ~3;
     o.rows = f; f += 3 * Wp;
     o.tcol = f; f += o.Lp;
-    o.tmpl = f; f += 2 * o.Lp;
+    o.tmpl = f; f += 2 * o.Lp;                   // observation row of the step, source of the TMA bulk stores (double-buffered)
     o.red = f; f += 6 * nt;
     o.rsum = f; f += nt;
     o.dsum = f; f += (2 * epb + 3) & ~3;
@@ -460,21 +455,34 @@ __device__ __forceinline__ float lstm_update(const Dev& d, const UnitCtx<R>& c, 
 
 // ------------------------------------------------------------------------------------------------------------------
 // advance kernel: K consecutive time steps in one launch (cl_step: K = 1, cl_rollout: any K).
-// Parameters, table columns and the unit state stay in registers for the whole launch; per step a thread gathers its inputs
-// from the TMA-staged time row, reads its action(s), runs the physics, and the block reduces the district sums in shared
-// memory and streams out the reward and observation slabs.  The time rows ride a 3-slot TMA ring: the row of step t+3 is
-// requested as soon as every thread is done with the row of step t.  One block barrier per step (two when a reward needs the
-// district sum, three for central-agent sums): `red`, `tmpl` and `dsum` are double-buffered by step parity.
+//
+// Block = P "physics" warps (one thread per unit: building x env, whole envs per block) + ONE helper warp.
+//  * physics threads keep parameters, table columns and the unit state in registers for the whole launch; per step they
+//    gather their inputs from the TMA-staged time row, take the (prefetched) action, run `unit_step`, publish net / cost /
+//    emission to shared memory, pass ONE block barrier, and write rewards (district sums: one thread per (quantity, env), in
+//    building order like the reference's sum()).
+//  * the helper warp works one step ahead of / behind them: before the barrier of step k it prepares the per-building inputs
+//    of step k+1 that do not depend on the env (PV generation: an fp64 division per unit otherwise); after the barrier it
+//    streams the observation slab of step k (reference-parity observations are env-independent rows) with
+//    16-byte st.global.cs stores WHILE the physics warps already compute step k+1 - the store phase of one step overlaps the
+//    arithmetic phase of the next instead of alternating with it.
+// The time rows ride a 3-slot TMA ring (cp.async.bulk + mbarrier): the row of step t+3 is requested right after the barrier
+// of step t.  `red`, `dsum` and the per-building buffers are double-buffered by step parity, so one barrier per step suffices
+// (two when a reward needs the district sum, more for central-agent sums).
 // ------------------------------------------------------------------------------------------------------------------
 template <typename R, bool THERMAL, bool DYNAMICS, int MAXT>
 __global__ void __launch_bounds__(MAXT) advance_kernel(Dev d, int t0, int K, const float* __restrict__ actions, float* __restrict__ obs,
                                                         float* __restrict__ reward, float* __restrict__ district, float* __restrict__ trace) {
     extern __shared__ __align__(16) float smf[];
     const int nt = blockDim.x, tid = threadIdx.x;
+    const int np_ = nt - 32;                       // physics threads; the last warp is the helper
+    const bool is_helper = tid >= np_;
+    const int lane = tid & 31;
     const int B = d.B, epb = d.envs_per_block, Wp = d.Wp;
     const SmemLayout lo = smem_layout(B, Wp, d.L, epb, nt, (int)sizeof(R));
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(smf);
     R* scurves = reinterpret_cast<R*>(smf + lo.curves);
+    R* s_bsolar = reinterpret_cast<R*>(smf + lo.bsolar);          // [2][B] PV generation of the step, per building
     float* s_rows = smf + lo.rows;
     int32_t* s_tcol = reinterpret_cast<int32_t*>(smf + lo.tcol);
     float* s_dsum = smf + lo.dsum;
@@ -491,6 +499,7 @@ __global__ void __launch_bounds__(MAXT) advance_kernel(Dev d, int t0, int K, con
     const bool tmpl_path = obs != nullptr && uniform && d.stale;
     const bool need_dsum = d.reward_id == CL_REWARD_MARL && reward != nullptr;
     const bool fused_reward = reward != nullptr && d.reward_id >= 0;
+    const bool central_sync = fused_reward && d.central;
     const int Rdim = d.central ? 1 : B;
     const uint32_t row_bytes = (uint32_t)Wp * sizeof(float);
 
@@ -511,18 +520,43 @@ __global__ void __launch_bounds__(MAXT) advance_kernel(Dev d, int t0, int K, con
     UnitCtx<R> c;
     UnitState<R> s;
     int start_e = 0;
+    RawActions act_next = {};
     if (active) {
         load_ctx<R, THERMAL>(d, b, c);
         load_state<R, THERMAL>(d, u, s);
         start_e = __ldg(d.start + e);
+        fetch_actions<R, THERMAL>(c, actions + (size_t)e * d.A, act_next);
     }
     const R* curves = scurves + (active ? b : 0) * 32;
     const float* lstm_w = DYNAMICS ? d.lstm_w + (size_t)(active ? b : 0) * kLstmStride : nullptr;
-    __syncthreads();   // barriers initialised, curves / tcol staged
+    __syncthreads();   // mbarriers initialised (visible to every waiter), curves / tcol staged
 
+    // per-building PV generation of time row `rowp` -> dst[b]  (building.py:2554; the same value for every env of the block)
+    auto building_inputs = [&](const float* rowp, R* dst) {
+        const auto* P = PSel<R>::p(d);
+        for (int bb = lane; bb < B; bb += 32) {
+            const R pv = (R)__ldg(P + CL_P_PV_NOMINAL_POWER * B + bb);
+            dst[bb] = -dvd(pv * (R)rowp[__ldg(d.ip + CL_IP_C_SOLAR * B + bb)], (R)1000);
+        }
+    };
+    if (uniform) {
+        if (is_helper) {
+            mbar_wait(s_bar + 0, 0u);
+            building_inputs(s_rows, s_bsolar);
+        }
+        __syncthreads();
+    }
+
+#ifdef CL_PHASE_TIMING
+#define CL_STAMP(i) do { if (blockIdx.x == 1 && tid == 32 && trace) trace[k * 8 + (i)] = (float)(clock64() - clk0); } while (0)
+    const long long clk0 = clock64();
+#else
+#define CL_STAMP(i)
+#endif
     for (int k = 0; k < K; ++k) {
         const int t = t0 + k;
         const int pb = k & 1;
+        CL_STAMP(0);
         const int slot_t = k % 3, slot_n = (k + 1) % 3;
         const float* row;
         const float* row_next = nullptr;
@@ -534,20 +568,67 @@ __global__ void __launch_bounds__(MAXT) advance_kernel(Dev d, int t0, int K, con
         } else {
             row = d.table + (size_t)(start_e + t) * Wp;
         }
+        CL_STAMP(1);
         float* red = smf + lo.red + pb * 3 * nt;
-        float* tmpl = smf + lo.tmpl + pb * lo.Lp;
+
+        if (is_helper) {
+            // ---------------- helper warp ----------------
+            if (uniform && k + 1 < K) building_inputs(row_next, s_bsolar + ((k + 1) & 1) * B);
+            __syncthreads();                                                   // S1
+            if (need_dsum) __syncthreads();                                    // S2
+            if (central_sync) { if (k > 0) __syncthreads(); __syncthreads(); }
+            if (tmpl_path) {
+                // observation slab of step k: every env row of the block equals the row gathered from time row t+1
+                float* ok = obs + (size_t)k * d.E * d.L + (size_t)e0 * d.L;
+                const int L = d.L;
+                auto gather = [&](int j) -> float {
+                    const int cc = s_tcol[j];
+                    if (cc >= 0) return row_next[cc];
+                    if (cc == -1) return 0.f;
+                    return d.has_outage ? __ldg(d.outage + (-2 - cc) * d.T + t + 1) : 0.f;
+                };
+                if ((L & 3) == 0) {
+                    // build the row once in shared memory, then one TMA bulk store (cp.async.bulk shared -> global) per env row:
+                    // the copy engine moves the slab, the SM's load/store path stays free for the physics warps
+                    float* tmpl = smf + lo.tmpl + pb * lo.Lp;
+                    tma_store_wait_read<1>();                                   // the stores issued two steps ago have read this buffer
+                    for (int j = lane; j < L; j += 32) tmpl[j] = gather(j);
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // generic-proxy writes -> visible to the async proxy
+                    __syncwarp();
+                    if (lane == 0) {
+                        const uint32_t bytes = (uint32_t)L * sizeof(float);
+                        for (int le = 0; le < n_env; ++le) tma_store_1d(ok + (size_t)le * L, tmpl, bytes);
+                        tma_store_commit();
+                    }
+                } else {
+                    for (int j = lane; j < L; j += 32) {
+                        const float v = gather(j);
+                        for (int le = 0; le < n_env; ++le) __stcs(ok + (size_t)le * L + j, v);
+                    }
+                }
+            } else if (obs != nullptr && want_dyn && k + 1 < K) {
+                __syncthreads();
+            }
+            continue;
+        }
+
+        // ---------------- physics warps ----------------
         UnitResult<R> o;
         RewardIn ri;
         if (active) {
             UnitInputs<R> in;
-            load_inputs<R, THERMAL>(d, c, row, b, t, in);
-            load_actions<R, THERMAL>(c, actions + ((size_t)k * d.E + e) * d.A, in);
+            load_inputs<R, THERMAL>(d, c, row, b, t, in, uniform);
+            if (uniform) in.solar = s_bsolar[pb * B + b];
+            apply_actions<R, THERMAL>(c, act_next, in);
+            if (k + 1 < K) fetch_actions<R, THERMAL>(c, actions + ((size_t)(k + 1) * d.E + e) * d.A, act_next);   // prefetch
             if (DYNAMICS && (c.p.flags & CL_F_DYNAMICS) && t > c.dyn_lookback) {
                 // partial-load control is live once the input window is full (building.py:3108, 3144)
                 in.control_cooling_demand = (c.a_cd >= 0 || c.a_coh >= 0);
                 in.control_heating_demand = (c.a_hd >= 0 || c.a_coh >= 0);
             }
+            CL_STAMP(2);
             unit_step<R, THERMAL>(c.p, curves, 1, t, in, s, o);
+            CL_STAMP(3);
             float t_in = row[c.c_tin];
             if (DYNAMICS && (c.p.flags & CL_F_DYNAMICS)) {
                 const float cd = (float)(o.e_from_cool + fabs(rmin(o.eb_cs, (R)0)));
@@ -557,21 +638,28 @@ __global__ void __launch_bounds__(MAXT) advance_kernel(Dev d, int t0, int K, con
             red[nt + tid] = (float)o.cost;
             red[2 * nt + tid] = (float)o.emission;
             if (fused_reward) reward_inputs<R, THERMAL>(d, c, s, o, row, t_in, ri);     // everything the reward needs from row t
+#ifdef CL_PHASE_TIMING
+            if (want_dyn) {
+#else
             if (trace != nullptr || want_dyn) {
+#endif
                 float dyn[CL_NDYN];
                 fill_dyn<R>(c.p, s, o, (R)t_in, dyn);
+#ifndef CL_PHASE_TIMING
                 if (trace != nullptr) {
 #pragma unroll
                     for (int j = 0; j < CL_NDYN; ++j) trace[(size_t)u * CL_NDYN + j] = dyn[j];
                 }
+#endif
                 if (want_dyn) {
 #pragma unroll
                     for (int j = 0; j < CL_NDYN; ++j) s_dynbuf[tid * CL_NDYN + j] = dyn[j];
                 }
             }
         }
-        if (tmpl_path) build_obs_template(d, s_tcol, row_next, t + 1, tmpl);
-        __syncthreads();                                                       // S1: red / tmpl / dynbuf of step k complete
+        CL_STAMP(4);
+        __syncthreads();                                                       // S1: red / dynbuf / next-step building inputs complete
+        CL_STAMP(5);
         if (uniform && tid == 0 && k + 3 <= K) {
             // nobody reads row t any more (reward inputs were captured above): its slot takes the row of step t + 3
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -580,7 +668,7 @@ __global__ void __launch_bounds__(MAXT) advance_kernel(Dev d, int t0, int K, con
         }
         // district sums in building order, like the reference's sum() over buildings (citylearn.py:1908-1918);
         // one thread per (quantity, env)
-        for (int idx = tid; idx < 3 * n_env; idx += nt) {
+        for (int idx = tid; idx < 3 * n_env; idx += np_) {
             const int q = idx / n_env, le = idx - q * n_env;
             if (q > 0 && district == nullptr) continue;
             const float* src = red + q * nt + le * B;
@@ -618,16 +706,17 @@ __global__ void __launch_bounds__(MAXT) advance_kernel(Dev d, int t0, int K, con
                 rk[u] = r;
             }
         }
-        if (obs != nullptr) {
-            float* ok = obs + (size_t)k * d.E * d.L;
-            if (tmpl_path) write_obs_template(d, ok, e0, n_env, tmpl);
-            else {
-                write_obs_general(d, ok, e0, n_env, t + 1, want_dyn ? s_dynbuf : nullptr);
-                if (want_dyn && k + 1 < K) __syncthreads();                     // dynbuf is single-buffered
-            }
+        CL_STAMP(6);
+        if (obs != nullptr && !tmpl_path) {
+            write_obs_general(d, obs + (size_t)k * d.E * d.L, e0, n_env, t + 1, want_dyn ? s_dynbuf : nullptr, tid, np_);
+            if (want_dyn && k + 1 < K) __syncthreads();                         // dynbuf is single-buffered
         }
     }
-    if (active) store_state<R, THERMAL>(d, u, s);
+#ifdef CL_PHASE_TIMING
+    { const int k = K - 1; CL_STAMP(7); }
+#endif
+    if (is_helper) tma_store_wait_all<0>();
+    if (active && !is_helper) store_state<R, THERMAL>(d, u, s);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -671,7 +760,7 @@ __global__ void __launch_bounds__(MAXT) reset_kernel(Dev d, float* __restrict__ 
     }
     if (obs != nullptr) {
         __syncthreads();
-        write_obs_general(d, obs, e0, n_env, 0, s_dynbuf);
+        write_obs_general(d, obs, e0, n_env, 0, s_dynbuf, tid, nt);
     }
 }
 
@@ -722,7 +811,7 @@ extern "C" int cl_create(const cl_district_desc* desc, cl_env** out) {
     if (desc->abi_version != CL_ABI_VERSION) return fail(CL_ERR_INVALID, "cl_create: ABI version mismatch");
     if (desc->n_buildings < 1 || desc->n_envs < 1 || desc->n_rows < 2 || desc->n_cols < 1 || desc->obs_dim < 1)
         return fail(CL_ERR_INVALID, "cl_create: empty district");
-    if (desc->n_buildings > 1024) return fail(CL_ERR_UNSUPPORTED, "cl_create: more than 1024 buildings per district not supported yet");
+    if (desc->n_buildings > 992) return fail(CL_ERR_UNSUPPORTED, "cl_create: more than 992 buildings per district not supported yet (one env per block + helper warp)");
     if (!desc->table || !desc->params || !desc->iparams || !desc->obs_desc) return fail(CL_ERR_INVALID, "cl_create: null table/params");
     if (desc->precision != CL_PRECISION_FP32 && desc->precision != CL_PRECISION_FP64) return fail(CL_ERR_INVALID, "cl_create: bad precision");
     cl_env* env = new (std::nothrow) cl_env();
@@ -831,11 +920,49 @@ extern "C" int cl_create(const cl_district_desc* desc, cl_env** out) {
         if (cudaMalloc(&p, (size_t)d.E * sizeof(int32_t)) != cudaSuccess) { cl_destroy(env); return fail(CL_ERR_CUDA, "cl_create: start allocation failed"); }
         env->allocs.push_back(p); d.start = static_cast<int32_t*>(p);
     }
-    // launch geometry: as many whole envs per block as fit the target block size.  Measured on B200 at 17 x 4096
-    // (profiles/README.md): 128-thread blocks are best (more, smaller blocks balance the 148 SMs; below 128 the per-block
-    // template / TMA work dominates).  CL_B200_BLOCK_THREADS overrides for experiments.
-    int target = 128;
-    if (const char* ev = std::getenv("CL_B200_BLOCK_THREADS")) { const int v = std::atoi(ev); if (v >= 32 && v <= 1024) target = v; }
+    // launch geometry.  A block = whole envs x all B buildings (physics threads, rounded up to warps) + one helper warp.
+    // Every block must be RESIDENT for the whole launch to run in one wave (the kernel is register-heavy: ~100-128 registers
+    // per thread), so the block size is chosen per (E, B, device): among a few candidate sizes pick the one that minimises
+    // waves x resident threads per SM.  On B200 at 17 x 4096 this selects one 512-thread block per SM (147 blocks on 148 SMs;
+    // profiles/README.md has the sweep).  CL_B200_BLOCK_THREADS overrides for experiments.
+    int n_sm = 148;
+    {
+        int dev = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+        if (n_sm < 1) n_sm = 148;
+    }
+    int regs = 128;
+    {
+        cudaFuncAttributes fa;
+        const void* fn = env->precision == CL_PRECISION_FP64
+            ? (any_dyn ? (const void*)advance_kernel<double, true, true, 512> : (any_thermal ? (const void*)advance_kernel<double, true, false, 512> : (const void*)advance_kernel<double, false, false, 512>))
+            : (any_dyn ? (const void*)advance_kernel<float, true, true, 512> : (any_thermal ? (const void*)advance_kernel<float, true, false, 512> : (const void*)advance_kernel<float, false, false, 512>));
+        if (cudaFuncGetAttributes(&fa, fn) == cudaSuccess && fa.numRegs > 0) regs = fa.numRegs;
+        cudaGetLastError();
+    }
+    int target = 0;
+    if (const char* ev = std::getenv("CL_B200_BLOCK_THREADS")) { const int v = std::atoi(ev); if (v >= 32 && v <= 992) target = v; }
+    if (target == 0) {
+        const int cand[] = {96, 128, 224, 352, 480};
+        double best = 1e30;
+        for (int ci = 0; ci < 5; ++ci) {
+            int epb_c = cand[ci] / B;
+            if (epb_c < 1) epb_c = 1;
+            if (epb_c > d.E) epb_c = d.E;
+            const int thr = ((epb_c * B + 31) / 32) * 32 + 32;
+            if (thr > 512 && ci > 0) continue;
+            const int regs_alloc = ((regs + 7) / 8) * 8;
+            int bps = 65536 / (regs_alloc * thr);
+            if (bps > 2048 / thr) bps = 2048 / thr;
+            if (bps < 1) bps = 1;
+            const long blocks = (d.E + epb_c - 1) / epb_c;
+            const long waves = (blocks + (long)n_sm * bps - 1) / ((long)n_sm * bps);
+            const long resident = blocks < (long)n_sm * bps ? (blocks + n_sm - 1) / n_sm : bps;   // blocks per SM actually resident
+            const double cost = (double)waves * (double)resident * thr;
+            if (cost < best - 1e-9) { best = cost; target = cand[ci]; }
+        }
+        if (target == 0) target = 128;
+    }
     int epb = target / B;
     if (epb < 1) epb = 1;
     if (epb > d.E) epb = d.E;
@@ -843,7 +970,7 @@ extern "C" int cl_create(const cl_district_desc* desc, cl_env** out) {
     env->threads = ((epb * B + 31) / 32) * 32;
     env->blocks = (d.E + epb - 1) / epb;
     // opt in to large dynamic shared memory once (both kernels, all instantiations)
-    const size_t smem = smem_bytes(d, env->threads, true, 8);
+    const size_t smem = smem_bytes(d, env->threads + 32, true, 8);
     if (smem > 200 * 1024) { cl_destroy(env); return fail(CL_ERR_UNSUPPORTED, "cl_create: district too wide for the shared-memory staging"); }
 #define OPTIN(K) cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
 #define OPTIN4(K, M) OPTIN((K<float, false, M>)); OPTIN((K<float, true, M>)); OPTIN((K<double, false, M>)); OPTIN((K<double, true, M>))
@@ -895,9 +1022,10 @@ static void launch_reset(cl_env* env, float* obs, cudaStream_t st) {
 template <typename R, bool TH, bool DY>
 static void launch_advance(cl_env* env, int K, const float* actions, float* obs, float* reward, float* district, float* trace, cudaStream_t st) {
     const bool want_dyn = !env->d.stale && obs != nullptr;
-    const size_t smem = smem_bytes(env->d, env->threads, want_dyn, (int)sizeof(R));
-    if (env->threads <= 512) advance_kernel<R, TH, DY, 512><<<env->blocks, env->threads, smem, st>>>(env->d, env->t, K, actions, obs, reward, district, trace);
-    else advance_kernel<R, TH, DY, 1024><<<env->blocks, env->threads, smem, st>>>(env->d, env->t, K, actions, obs, reward, district, trace);
+    const int nthreads = env->threads + 32;          // + the helper warp
+    const size_t smem = smem_bytes(env->d, nthreads, want_dyn, (int)sizeof(R));
+    if (nthreads <= 512) advance_kernel<R, TH, DY, 512><<<env->blocks, nthreads, smem, st>>>(env->d, env->t, K, actions, obs, reward, district, trace);
+    else advance_kernel<R, TH, DY, 1024><<<env->blocks, nthreads, smem, st>>>(env->d, env->t, K, actions, obs, reward, district, trace);
 }
 static void dispatch_advance(cl_env* env, int K, const float* actions, float* obs, float* reward, float* district, float* trace, cudaStream_t st) {
     if (env->precision == CL_PRECISION_FP64) {
@@ -958,7 +1086,11 @@ extern "C" int cl_rollout(cl_env* env, int32_t n_steps, const float* actions, fl
     if (n_steps < 1) return fail(CL_ERR_INVALID, "cl_rollout: n_steps must be >= 1");
     if (env->t < 0) return fail(CL_ERR_STATE, "cl_rollout: call cl_reset first");
     if (env->t + n_steps > env->T - 1) return fail(CL_ERR_STATE, "cl_rollout: block runs past the end of the episode");
+#ifdef CL_PHASE_TIMING
+    dispatch_advance(env, n_steps, actions, obs, reward, nullptr, district, static_cast<cudaStream_t>(stream));   // `district` receives the stamps
+#else
     dispatch_advance(env, n_steps, actions, obs, reward, district, nullptr, static_cast<cudaStream_t>(stream));
+#endif
     CUDA_TRY(cudaGetLastError());
     env->t += n_steps;
     return CL_OK;

@@ -50,7 +50,7 @@ static void step_impl(int B, int E, int W, const double* P, const int32_t* ip, c
             auto col = [&](int k) { return row[ip[k * B + b]]; };
             in.nsl = (R)col(CL_IP_C_NSL);
             const R pv = (R)(sizeof(R) == 4 ? (double)(float)P[CL_P_PV_NOMINAL_POWER * B + b] : P[CL_P_PV_NOMINAL_POWER * B + b]);
-            in.solar = -(pv * (R)col(CL_IP_C_SOLAR) / (R)1000);
+            in.solar = -dvd(pv * (R)col(CL_IP_C_SOLAR), (R)1000);
             in.price = (R)col(CL_IP_C_PRICE); in.carbon = (R)col(CL_IP_C_CARBON);
             in.dhw_demand = (R)col(CL_IP_C_DHW_DEMAND); in.cooling_demand = (R)col(CL_IP_C_COOLING_DEMAND);
             in.heating_demand = (R)col(CL_IP_C_HEATING_DEMAND); in.t_out = (R)col(CL_IP_C_T_OUT);
