@@ -206,6 +206,8 @@ CASES = {
     # episode windows: consecutive splits inside a sub-range, two episodes
     'c1_episodes': dict(dataset=P1, overrides={'simulation_start_time_step': 100, 'simulation_end_time_step': 1299,
                                                'episode_time_steps': 240}, episodes=3, seed=3),
+    # sub-hour control step on an hourly dataset: time_step_ratio = 0.5 (tests/unit/test_subhour_scaling.py in the reference)
+    'c1_subhour': dict(dataset=P1, overrides={'seconds_per_time_step': 1800}, steps=120, seed=5),
     # C3 schema: 3 LSTM buildings, outages, decentralised MARL (BASELINE.json configs[2]) and the schema default
     'c3_marl': dict(dataset=C23, overrides={'central_agent': False}, reward=MARL, steps=None, seed=1),
     'c3_default_central_comfort': dict(dataset=C23, steps=None, seed=2),

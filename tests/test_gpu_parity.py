@@ -16,7 +16,7 @@ from helpers import (TRACE_TO_DYN, actions_of, load_golden, max_abs_diff, observ
 
 pytestmark = pytest.mark.gpu
 
-NON_LSTM_CASES = ['c1_phase1_300', 'c1_phase1_central', 'c1_episodes', 'c2_marl', 'c2_isac', 'c2_solar_penalty', 'c2_central_exp2', 'c2_year']
+NON_LSTM_CASES = ['c1_phase1_300', 'c1_phase1_central', 'c1_episodes', 'c1_subhour', 'c2_marl', 'c2_isac', 'c2_solar_penalty', 'c2_central_exp2', 'c2_year']
 # 2023 schema: heat pump + electric heater + DHW tank + battery + outages + LSTM indoor-temperature dynamics (BASELINE configs[2])
 LSTM_CASES = ['c3_marl', 'c3_default_central_comfort', 'c3_solar_comfort']
 
@@ -269,3 +269,29 @@ def test_lstm_district_batched_matches_oracle():
             assert np.array_equal(tr[..., DYN[n]], odyn[..., DYN[n]].astype('float32')), (n, k)
         assert max_abs_diff(tr[..., DYN['indoor_dry_bulb_temperature']], odyn[..., DYN['indoor_dry_bulb_temperature']]) < 3e-5
         assert np.array_equal(rew.cpu().numpy(), orew)          # MARL does not read the temperature
+
+
+def test_full_size_component_identity_and_bounds():
+    """Size-independent properties at 17 x 4096 (reference tests/unit/test_alignment.py, test_battery.py): net == sum of components,
+    0 <= soc <= 1, district == sum over buildings, checked on the GPU trace for every unit."""
+    from citylearn_b200 import CityLearnEnv
+    E = 4096
+    env = CityLearnEnv('citylearn_challenge_2022_phase_all', num_envs=E, debug_trace=True)
+    env.reset()
+    g = torch.Generator(device='cuda').manual_seed(5)
+    table = torch.as_tensor(env.spec.table, device='cuda')
+    pv = torch.as_tensor(env.spec.params[:, S.P['PV_NOMINAL_POWER']], device='cuda', dtype=torch.float64)
+    c_solar = torch.as_tensor(env.spec.iparams[:, S.IP['C_SOLAR']], device='cuda').long()
+    for k in range(25):
+        a = torch.rand((E, 17), device='cuda', generator=g) * 2 - 1
+        obs, rew, _, _, _ = env.step(a)
+        tr = env.trace.double()
+        solar = -(pv * table[k, c_solar].double() / 1000.0)
+        comp = (tr[..., DYN['cooling_electricity_consumption']] + tr[..., DYN['heating_electricity_consumption']]
+                + tr[..., DYN['dhw_electricity_consumption']] + tr[..., DYN['non_shiftable_load_electricity_consumption']]
+                + tr[..., DYN['electrical_storage_electricity_consumption']] + solar[None, :])
+        assert float((comp - tr[..., DYN['net_electricity_consumption']]).abs().max()) < 1e-4
+        soc = tr[..., DYN['electrical_storage_soc']]
+        assert float(soc.min()) >= 0.0 and float(soc.max()) <= 1.0 + 1e-6
+        assert float((tr[..., DYN['net_electricity_consumption']].sum(dim=1) - env.district[:, 0].double()).abs().max()) < 1e-3
+        assert torch.equal(rew, -torch.clamp(env.trace[..., DYN['net_electricity_consumption']], min=0.0))
