@@ -34,7 +34,7 @@ namespace cl {
 // ------------------------------------------------------------------------------------------------------------------
 struct Dev {
     int B, E, U, n_rows, W, Wp, A, L, T;
-    int central, reward_id, stale, envs_per_block, uniform_start, start0, has_outage, any_dynamics;
+    int central, reward_id, stale, envs_per_block, uniform_start, start0, has_outage, any_dynamics, lstm_smem;
     float rp[8];
     const float* table;
     const float* pf;       // [NPARAM][B]
@@ -359,9 +359,9 @@ __device__ __forceinline__ void write_obs_general(const Dev& d, float* obs, int 
 // offsets in floats from the start of the dynamic shared memory (kept as plain ints so that every access is derived
 // directly from the `extern __shared__` array and compiles to LDS/STS with 32-bit addressing, not generic loads)
 struct SmemLayout {
-    int curves, bsolar, rows, tcol, tmpl, red, rsum, dsum, dynbuf, Lp;
+    int curves, bsolar, rows, tcol, tmpl, red, rsum, dsum, lstm, dynbuf, Lp;
 };
-__host__ __device__ __forceinline__ SmemLayout smem_layout(int B, int Wp, int L, int epb, int nt, int rsize) {
+__host__ __device__ __forceinline__ SmemLayout smem_layout(int B, int Wp, int L, int epb, int nt, int rsize, int lstm_smem = 0) {
     SmemLayout o;
     o.Lp = (L + 3) & ~3;
     int f = 8;                                   // 32 bytes of mbarriers
@@ -373,11 +373,12 @@ __host__ __device__ __forceinline__ SmemLayout smem_layout(int B, int Wp, int L,
     o.red = f; f += 6 * nt;
     o.rsum = f; f += nt;
     o.dsum = f; f += (2 * epb + 3) & ~3;
+    o.lstm = f; f += lstm_smem ? B * kLstmStride : 0;      // kLstmStride is a multiple of 4 floats: 16-byte aligned rows
     o.dynbuf = f;
     return o;
 }
 static size_t smem_bytes(const Dev& d, int nt, bool with_dyn, int rsize) {
-    const SmemLayout o = smem_layout(d.B, d.Wp, d.L, d.envs_per_block, nt, rsize);
+    const SmemLayout o = smem_layout(d.B, d.Wp, d.L, d.envs_per_block, nt, rsize, d.lstm_smem);
     size_t n = sizeof(float) * (size_t)o.dynbuf;
     if (with_dyn) n += sizeof(float) * (size_t)nt * CL_NDYN;
     return n;
@@ -479,7 +480,7 @@ __global__ void __launch_bounds__(MAXT) advance_kernel(Dev d, int t0, int K, con
     const bool is_helper = tid >= np_;
     const int lane = tid & 31;
     const int B = d.B, epb = d.envs_per_block, Wp = d.Wp;
-    const SmemLayout lo = smem_layout(B, Wp, d.L, epb, nt, (int)sizeof(R));
+    const SmemLayout lo = smem_layout(B, Wp, d.L, epb, nt, (int)sizeof(R), DYNAMICS ? d.lstm_smem : 0);
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(smf);
     R* scurves = reinterpret_cast<R*>(smf + lo.curves);
     R* s_bsolar = reinterpret_cast<R*>(smf + lo.bsolar);          // [2][B] PV generation of the step, per building
@@ -492,7 +493,11 @@ __global__ void __launch_bounds__(MAXT) advance_kernel(Dev d, int t0, int K, con
     const int n_env = min(epb, d.E - e0);
     const int n_units = n_env * B;
     const bool active = tid < n_units;
-    const int e_l = tid / B, b = tid - e_l * B;
+    // thread -> unit: env-major (building fastest: coalesced state / action / reward slices) except for LSTM districts, where
+    // building-major keeps the lanes of a warp on ONE building so that its LSTM weights are broadcast loads
+    const int b = DYNAMICS ? tid / n_env : tid % B;
+    const int e_l = DYNAMICS ? tid - b * n_env : tid / B;
+    const int ul = e_l * B + b;                    // unit slot inside the block's shared-memory arrays (always env-major)
     const int e = e0 + e_l, u = e * B + b;
     const bool uniform = d.uniform_start != 0;
     const bool want_dyn = (!d.stale && obs != nullptr);
@@ -528,8 +533,18 @@ __global__ void __launch_bounds__(MAXT) advance_kernel(Dev d, int t0, int K, con
         fetch_actions<R, THERMAL>(c, actions + (size_t)e * d.A, act_next);
     }
     const R* curves = scurves + (active ? b : 0) * 32;
-    const float* lstm_w = DYNAMICS ? d.lstm_w + (size_t)(active ? b : 0) * kLstmStride : nullptr;
-    __syncthreads();   // mbarriers initialised (visible to every waiter), curves / tcol staged
+    const float* lstm_w = nullptr;
+    if (DYNAMICS) {
+        if (d.lstm_smem) {                            // stage every building's packed LSTM weights in shared memory (16-byte copies)
+            float4* dst = reinterpret_cast<float4*>(smf + lo.lstm);
+            const float4* src = reinterpret_cast<const float4*>(d.lstm_w);
+            for (int i = tid; i < B * (kLstmStride / 4); i += nt) dst[i] = __ldg(src + i);
+            lstm_w = smf + lo.lstm + (size_t)(active ? b : 0) * kLstmStride;
+        } else {
+            lstm_w = d.lstm_w + (size_t)(active ? b : 0) * kLstmStride;
+        }
+    }
+    __syncthreads();   // mbarriers initialised (visible to every waiter), curves / tcol / LSTM weights staged
 
     // per-building PV generation of time row `rowp` -> dst[b]  (building.py:2554; the same value for every env of the block)
     auto building_inputs = [&](const float* rowp, R* dst) {
@@ -634,9 +649,9 @@ __global__ void __launch_bounds__(MAXT) advance_kernel(Dev d, int t0, int K, con
                 const float cd = (float)(o.e_from_cool + fabs(rmin(o.eb_cs, (R)0)));
                 t_in = lstm_update<R>(d, c, lstm_w, u, t, start_e, cd, t_in);
             }
-            red[tid] = (float)o.net;
-            red[nt + tid] = (float)o.cost;
-            red[2 * nt + tid] = (float)o.emission;
+            red[ul] = (float)o.net;
+            red[nt + ul] = (float)o.cost;
+            red[2 * nt + ul] = (float)o.emission;
             if (fused_reward) reward_inputs<R, THERMAL>(d, c, s, o, row, t_in, ri);     // everything the reward needs from row t
 #ifdef CL_PHASE_TIMING
             if (want_dyn) {
@@ -653,7 +668,7 @@ __global__ void __launch_bounds__(MAXT) advance_kernel(Dev d, int t0, int K, con
 #endif
                 if (want_dyn) {
 #pragma unroll
-                    for (int j = 0; j < CL_NDYN; ++j) s_dynbuf[tid * CL_NDYN + j] = dyn[j];
+                    for (int j = 0; j < CL_NDYN; ++j) s_dynbuf[ul * CL_NDYN + j] = dyn[j];
                 }
             }
         }
@@ -689,7 +704,7 @@ __global__ void __launch_bounds__(MAXT) advance_kernel(Dev d, int t0, int K, con
             float* rk = reward + (size_t)k * d.E * Rdim;
             if (d.central) {
                 if (k > 0) __syncthreads();                                    // previous step's rsum readers are done
-                s_rsum[tid] = r;
+                s_rsum[ul] = r;
                 __syncthreads();
                 if (tid < n_env) {
                     float sr = 0.f;
@@ -868,6 +883,7 @@ extern "C" int cl_create(const cl_district_desc* desc, cl_env** out) {
         int rc = dev_copy(env, packed.data(), packed.size(), &pw);
         if (rc) { cl_destroy(env); return rc; }
         d.lstm_w = pw;
+        d.lstm_smem = ((size_t)B * kLstmStride * sizeof(float) <= 120 * 1024) ? 1 : 0;
     }
     // padded table
     {
