@@ -217,6 +217,9 @@ __device__ __forceinline__ void fill_dyn(const BuildingParams<R>& p, const UnitS
     dyn[CL_DYN_NET_ELECTRICITY_CONSUMPTION_COST] = (float)o.cost;
     dyn[CL_DYN_NET_ELECTRICITY_CONSUMPTION_EMISSION] = (float)o.emission;
     dyn[CL_DYN_ELECTRICAL_STORAGE_DEGRADED_CAPACITY] = (float)s.cap_deg;
+    dyn[CL_DYN_ENERGY_TO_NON_SHIFTABLE_LOAD] = (float)o.e_to_nsl;
+    dyn[CL_DYN_COOLING_DEMAND_SERIES] = (float)o.cool_dem;
+    dyn[CL_DYN_HEATING_DEMAND_SERIES] = (float)o.heat_dem;
 }
 
 // ------------------------------------------------------------------------------------------------------------------

@@ -97,7 +97,8 @@ class CityLearnEnv:
     render_mode = None
 
     def __init__(self, schema, num_envs: int = 1, device: Union[str, torch.device, None] = None, precision: str = 'fp64',
-                 stale_observations: bool = True, track_episode_rewards: Optional[bool] = None, debug_trace: bool = False, **kwargs):
+                 stale_observations: bool = True, track_episode_rewards: Optional[bool] = None, debug_trace: bool = False,
+                 record_history: Optional[bool] = None, history_env: int = 0, **kwargs):
         self.spec = S.load(schema, **kwargs)
         self.schema = self.spec.schema
         self.num_envs = int(num_envs)
@@ -128,6 +129,12 @@ class CityLearnEnv:
         self._sizes_obs = [len(b.active_observations) for b in spec.buildings]
         self._sizes_act = [len(b.active_actions) for b in spec.buildings]
         self._track = (self.num_envs == 1) if track_episode_rewards is None else bool(track_episode_rewards)
+        # per-step history of ONE env for evaluate() (the reference keeps full series for its single env)
+        self._record = (self.num_envs == 1) if record_history is None else bool(record_history)
+        self._history_env = int(history_env)
+        if not 0 <= self._history_env < self.num_envs:
+            raise ValueError('history_env out of range')
+        debug_trace = debug_trace or self._record
         # reward function (citylearn/citylearn.py:2100-2163)
         self.reward_function = self._make_reward_function()
         rid, rparams = self._fused_reward()
@@ -324,6 +331,10 @@ class CityLearnEnv:
                 self._h.reset(None, start, T, self._obs.data_ptr(), stream)
         self.reward_function.reset()
         self._rsum = self._rmin = self._rmax = None
+        if self._record:
+            self._hist_dyn = torch.zeros((T - 1, self.spec.n_buildings, S.NDYN), dtype=torch.float32, device=self.device)
+            self._hist_district = torch.zeros((T - 1, 3), dtype=torch.float32, device=self.device)
+            self._hist_valid = True
         if self.num_envs == 1:
             return self._shape_obs(self._obs), self.get_info()
         return self._obs, self.get_info()
@@ -374,6 +385,9 @@ class CityLearnEnv:
                          None if self._trace is None else self._trace.data_ptr(), stream)
             if not fused:
                 self._python_reward()
+            if self._record:
+                self._hist_dyn[self.time_step].copy_(self._trace[self._history_env])
+                self._hist_district[self.time_step].copy_(self._district[self._history_env])
             self.time_step += 1
             if self._track:
                 self._accumulate_rewards()
@@ -404,6 +418,7 @@ class CityLearnEnv:
             self._h.rollout(K, actions.data_ptr(), None if obs is None else obs.data_ptr(), None if reward is None else reward.data_ptr(),
                             None if district is None else district.data_ptr(), self._stream())
         self.time_step += K
+        self._hist_valid = False          # rollouts do not produce the per-unit trace evaluate() needs
         return obs, reward, self.terminated
 
     # ---------------------------------------------------------------------------------------------
@@ -433,6 +448,18 @@ class CityLearnEnv:
             return x[0].tolist() if self.num_envs == 1 else x.clone()
         self._episode_rewards.append({'min': shape(self._rmin), 'max': shape(self._rmax), 'sum': shape(self._rsum),
                                       'mean': shape(self._rsum / self._rcount)})
+
+    def evaluate(self, control_condition=None, baseline_condition=None, comfort_band: float = None):
+        """KPI table of the recorded env (`citylearn/citylearn.py:1136-1323`): ratios of control vs baseline cost functions per building
+        and for the district, as a DataFrame with columns cost_function / value / name / level.  Needs `record_history=True`
+        (the default for num_envs == 1) and steps taken through `step()`."""
+        from .evaluate import History, evaluate
+        if not self._record or not getattr(self, '_hist_valid', False):
+            raise RuntimeError('evaluate() needs record_history=True and an episode advanced with step() (not rollout())')
+        k = self.time_step
+        h = History(self._hist_dyn[:k].cpu().numpy(), self._hist_district[:k].cpu().numpy(), int(self._start_dev[self._history_env].item()),
+                    self._outage)
+        return evaluate(self.spec, h, control_condition, baseline_condition, comfort_band)
 
     # ---------------------------------------------------------------------------------------------
     def state_dict(self) -> Dict[str, Any]:

@@ -101,6 +101,7 @@ DYN = {name: i for i, name in enumerate([
     'electrical_storage_energy_balance', 'cooling_storage_energy_balance', 'heating_storage_energy_balance',
     'dhw_storage_energy_balance', 'net_electricity_consumption_cost', 'net_electricity_consumption_emission',
     'electrical_storage_degraded_capacity',
+    'energy_to_non_shiftable_load', 'cooling_demand_series', 'heating_demand_series',
 ])}
 NDYN = len(DYN)
 

@@ -105,6 +105,8 @@ enum cl_dyn {
     CL_DYN_ELECTRICAL_STORAGE_ENERGY_BALANCE, CL_DYN_COOLING_STORAGE_ENERGY_BALANCE, CL_DYN_HEATING_STORAGE_ENERGY_BALANCE,
     CL_DYN_DHW_STORAGE_ENERGY_BALANCE, CL_DYN_NET_ELECTRICITY_CONSUMPTION_COST, CL_DYN_NET_ELECTRICITY_CONSUMPTION_EMISSION,
     CL_DYN_ELECTRICAL_STORAGE_DEGRADED_CAPACITY,
+    /* series needed by the KPI table (CityLearnEnv.evaluate, citylearn.py:1136-1323) */
+    CL_DYN_ENERGY_TO_NON_SHIFTABLE_LOAD, CL_DYN_COOLING_DEMAND_SERIES, CL_DYN_HEATING_DEMAND_SERIES,
     CL_NDYN
 };
 

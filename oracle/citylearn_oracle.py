@@ -213,6 +213,9 @@ class OracleEnv:
         dyn[..., DYN['net_electricity_consumption_cost']] = r32(net64 * self.col('C_PRICE', 0))
         dyn[..., DYN['net_electricity_consumption_emission']] = r32(np.maximum(0.0, net64 * self.col('C_CARBON', 0)))
         dyn[..., DYN['electrical_storage_degraded_capacity']] = self.cap_deg
+        dyn[..., DYN['energy_to_non_shiftable_load']] = self.col('C_NSL', 0)
+        dyn[..., DYN['cooling_demand_series']] = self.col('C_COOLING_DEMAND', 0)
+        dyn[..., DYN['heating_demand_series']] = self.col('C_HEATING_DEMAND', 0)
         return dyn
 
     # -- storage primitives ----------------------------------------------------------------------
@@ -508,6 +511,9 @@ class OracleEnv:
         dyn[..., DYN['net_electricity_consumption_cost']] = cost
         dyn[..., DYN['net_electricity_consumption_emission']] = emission
         dyn[..., DYN['electrical_storage_degraded_capacity']] = self.cap_deg
+        dyn[..., DYN['energy_to_non_shiftable_load']] = e_to_nsl32
+        dyn[..., DYN['cooling_demand_series']] = dem32['cool']
+        dyn[..., DYN['heating_demand_series']] = dem32['heat']
         self.last_aux = {'cooling_demand_series': dem32['cool'], 'heating_demand_series': dem32['heat'],
                          'energy_from_cooling_device': e_from['cool'], 'energy_from_dhw_device': e_from['dhw'],
                          'efficiency': self.eff_b.copy(), 'outage': outage}

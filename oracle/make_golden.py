@@ -57,6 +57,13 @@ def import_reference():
 
 
 def make_env(CityLearnEnv, dataset, overrides=None, reward=None):
+    # `EnergySimulation.__init__(..., time_step_ratios=[])` is a mutable default shared by every env of the process and indexed by
+    # building position (citylearn/data.py:403,454): a second env in the same process silently reuses the FIRST env's ratios.
+    # Clear it so that every fixture is what a fresh process would produce.
+    from citylearn.data import EnergySimulation
+    for dflt in (EnergySimulation.__init__.__defaults__ or ()):
+        if isinstance(dflt, list):
+            dflt.clear()
     overrides = dict(overrides or {})
     root = DATASETS / dataset
     schema = json.load(open(root / 'schema.json'))
@@ -174,6 +181,14 @@ def run_case(CityLearnEnv, name, dataset, overrides=None, reward=None, steps=Non
         arrays['episode_reward_sum'] = np.array(er['sum'], dtype='float64')
         arrays['episode_reward_min'] = np.array(er['min'], dtype='float64')
         arrays['episode_reward_max'] = np.array(er['max'], dtype='float64')
+    try:      # KPI table at the point where the run stopped (citylearn.py:1136-1323), for tests/test_evaluate.py
+        ev = env.evaluate()
+        records = [{'cost_function': r['cost_function'], 'name': r['name'], 'level': r['level'],
+                    'value': None if r['value'] is None or (isinstance(r['value'], float) and np.isnan(r['value'])) else float(r['value'])}
+                   for r in ev.to_dict('records')]
+    except Exception as e:   # pragma: no cover
+        records = [{'error': repr(e)}]
+    arrays['evaluate'] = np.frombuffer(json.dumps(records).encode(), dtype='uint8')
     config = {'dataset': dataset, 'overrides': overrides or {}, 'reward': reward, 'seed': seed, 'episodes': episodes,
               'trace_names': TRACE_NAMES, 'numpy': np.__version__}
     arrays['config'] = np.frombuffer(json.dumps(config).encode(), dtype='uint8')

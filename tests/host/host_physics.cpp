@@ -89,6 +89,8 @@ static void step_impl(int B, int E, int W, const double* P, const int32_t* ip, c
             d[CL_DYN_HEATING_STORAGE_ENERGY_BALANCE] = (float)o.eb_hs; d[CL_DYN_DHW_STORAGE_ENERGY_BALANCE] = (float)o.eb_ds;
             d[CL_DYN_NET_ELECTRICITY_CONSUMPTION_COST] = (float)o.cost; d[CL_DYN_NET_ELECTRICITY_CONSUMPTION_EMISSION] = (float)o.emission;
             d[CL_DYN_ELECTRICAL_STORAGE_DEGRADED_CAPACITY] = (float)s.cap_deg;
+            d[CL_DYN_ENERGY_TO_NON_SHIFTABLE_LOAD] = (float)o.e_to_nsl; d[CL_DYN_COOLING_DEMAND_SERIES] = (float)o.cool_dem;
+            d[CL_DYN_HEATING_DEMAND_SERIES] = (float)o.heat_dem;
         }
     }
 }

@@ -1,0 +1,67 @@
+"""KPI table (`CityLearnEnv.evaluate`, reference citylearn.py:1136-1323 + cost_function.py) vs tables recorded from the reference.
+
+CPU: the history comes from the oracle (same `cl_dyn` slots as the kernel's trace).  The GPU variant is in test_gpu_parity.py.
+"""
+import json
+
+import numpy as np
+import pytest
+
+from citylearn_b200 import schema as S
+from citylearn_b200.evaluate import History, evaluate
+from citylearn_oracle import OracleEnv
+from helpers import actions_of, golden_cases, load_golden, spec_for
+
+
+def golden_table(z):
+    recs = json.loads(bytes(z['evaluate']).decode())
+    return {(r['name'], r['cost_function']): r['value'] for r in recs}
+
+
+def oracle_history(spec, acts):
+    env = OracleEnv(spec, 1)
+    env.reset()
+    dyn, dist = [], []
+    for k in range(len(acts)):
+        _, _, d, dy = env.step(acts[k][None])
+        dyn.append(dy[0].astype('float32'))
+        dist.append(d[0])
+    return History(np.stack(dyn), np.stack(dist), int(env.start[0]), env.outage)
+
+
+def compare(table, ref, lstm):
+    assert set(table) == set(ref)
+    for key, v in ref.items():
+        got = table[key]
+        if v is None:
+            assert got is None or (isinstance(got, float) and np.isnan(got)), key
+        else:
+            tol = 2e-4 if lstm and 'discomfort' in key[1] or lstm and 'resilience' in key[1] else 2e-6
+            assert got == pytest.approx(v, rel=tol, abs=1e-9), (key, got, v)
+
+
+@pytest.mark.parametrize('case', [c for c in golden_cases() if c not in ('c1_episodes',)])
+def test_kpis_match_reference(case):
+    z, cfg, _ = load_golden(case)
+    if 'evaluate' not in z.files:
+        pytest.skip('fixture without KPI table')
+    spec = spec_for(cfg)
+    h = oracle_history(spec, actions_of(z)[0])
+    recs = evaluate(spec, h, as_dataframe=False)
+    table = {(r['name'], r['cost_function']): r['value'] for r in recs}
+    compare(table, golden_table(z), any(b.dynamics for b in spec.buildings))
+
+
+def test_cost_function_primitives():
+    from citylearn_b200.cost_function import CostFunction as C
+    x = [1.0, 3.0, 2.0, -1.0, 4.0]
+    assert np.isnan(C.ramping(x)[0]) and C.ramping(x)[-1] == pytest.approx(2.0 + 5.0)
+    assert C.ramping(x, down_ramp=True)[-1] == pytest.approx(2 + 1 + 3 + 5)
+    assert C.electricity_consumption(x)[-1] == 10.0 and C.zero_net_energy(x)[-1] == 9.0
+    assert C.peak(x, window=2) == pytest.approx([3.0, 2.5, (3 + 2 + 4) / 3])
+    lf = C.one_minus_load_factor(x, window=2)
+    assert lf[0] == pytest.approx(1 - 2.0 / 3.0) and lf[1] == pytest.approx(((1 - 2 / 3) + (1 - 0.5 / 2)) / 2)
+    d = C.discomfort([20, 25, 30], [24, 24, 24], [20, 20, 20], band=2.0, occupant_count=[1, 1, 0])
+    assert d[0][-1] == 0.0 and d[7][-1] == 1.0      # never outside the band while occupied; hot delta max = 1
+    u = C.normalized_unserved_energy([2, 2, 2], [2, 1, 0], power_outage=[0, 1, 1])
+    assert u[-1] == pytest.approx(3.0 / 4.0)

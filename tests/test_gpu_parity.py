@@ -295,3 +295,27 @@ def test_full_size_component_identity_and_bounds():
         assert float(soc.min()) >= 0.0 and float(soc.max()) <= 1.0 + 1e-6
         assert float((tr[..., DYN['net_electricity_consumption']].sum(dim=1) - env.district[:, 0].double()).abs().max()) < 1e-3
         assert torch.equal(rew, -torch.clamp(env.trace[..., DYN['net_electricity_consumption']], min=0.0))
+
+
+@pytest.mark.parametrize('case', ['c1_phase1_300', 'c2_marl', 'c3_marl', 'c3_default_central_comfort'])
+def test_evaluate_matches_reference_kpi_table(case):
+    """env.evaluate() (history recorded from the kernel's trace) vs the KPI table of the reference's own evaluate()."""
+    import json
+    z, cfg, meta = load_golden(case)
+    env = make_env(cfg, num_envs=1)
+    env.reset()
+    acts = actions_of(z)[0]
+    for k in range(len(acts)):
+        env.step(acts[k][None])
+    df = env.evaluate()
+    got = {(r['name'], r['cost_function']): r['value'] for r in df.to_dict('records')}
+    ref = {(r['name'], r['cost_function']): r['value'] for r in json.loads(bytes(z['evaluate']).decode())}
+    assert set(got) == set(ref)
+    lstm = case in LSTM_CASES
+    for key, v in ref.items():
+        g = got[key]
+        if v is None:
+            assert g is None or np.isnan(g), key
+        else:
+            tol = 2e-4 if (lstm and ('discomfort' in key[1] or 'resilience' in key[1])) else 2e-6
+            assert g == pytest.approx(v, rel=tol, abs=1e-9), (key, g, v)
