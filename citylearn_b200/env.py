@@ -151,8 +151,14 @@ class CityLearnEnv:
             self._trace = (torch.zeros((E, spec.n_buildings, S.NDYN), dtype=torch.float32, device=self.device)
                            if (rid < 0 or debug_trace) else None)
             self._act = torch.zeros((E, max(spec.action_dim, 1)), dtype=torch.float32, device=self.device)
-            self._act_pinned = torch.zeros((E, max(spec.action_dim, 1)), dtype=torch.float32).pin_memory()
-            self._act_host = self._act_pinned.numpy()      # same memory; filled with np.copyto (single-threaded memcpy)
+            # host -> device action staging: a small ring of pinned buffers, each guarded by a CUDA event, because the H2D copy is
+            # asynchronous - the host must not refill a buffer before the copy that reads it has executed
+            self._stage_n = 4
+            self._stage_pinned = [torch.zeros((E, max(spec.action_dim, 1)), dtype=torch.float32).pin_memory() for _ in range(self._stage_n)]
+            self._stage_host = [t.numpy() for t in self._stage_pinned]      # same memory; filled with np.copyto (single-threaded memcpy)
+            self._stage_event = [torch.cuda.Event() for _ in range(self._stage_n)]
+            self._stage_used = [False] * self._stage_n
+            self._stage_i = 0
             self._out_pinned = torch.zeros(E * (self._obs_dim + self._reward_dim), dtype=torch.float32).pin_memory()
             self._obs_pinned = self._out_pinned[:E * self._obs_dim].view(E, self._obs_dim)
             self._reward_pinned = self._out_pinned[E * self._obs_dim:].view(E, self._reward_dim)
@@ -350,8 +356,7 @@ class CityLearnEnv:
         if isinstance(actions, np.ndarray):
             # plain memcpy into the pinned staging buffer: a torch CPU copy_ would fan out over the intra-op thread pool, and
             # the spinning pool threads can exhaust a container's CPU quota (observed: 70 ms cgroup throttling stalls)
-            np.copyto(self._act_host[:, :A], actions.reshape(E, A), casting='same_kind')
-            self._act.copy_(self._act_pinned, non_blocking=True)
+            self._upload(lambda host: np.copyto(host[:, :A], actions.reshape(E, A), casting='same_kind'))
             return self._act, False
         actions = list(actions)
         if len(actions) and isinstance(actions[0], torch.Tensor):      # per-building [E, A_b]
@@ -370,9 +375,19 @@ class CityLearnEnv:
                 a = list(a)
                 assert len(a) == len(b.active_actions), f'Expected {len(b.active_actions)} for {b.name} but {len(a)} actions were provided.'
                 flat += [float(v) for v in a]
-        self._act_pinned[0, :A] = torch.tensor(flat, dtype=torch.float32)
-        self._act.copy_(self._act_pinned, non_blocking=True)
+        self._upload(lambda host: host.__setitem__((0, slice(0, A)), np.asarray(flat, dtype=np.float32)))
         return self._act, True
+
+    def _upload(self, fill):
+        """Fill the next pinned staging buffer on the host and enqueue its H2D copy into `self._act`."""
+        i = self._stage_i
+        self._stage_i = (i + 1) % self._stage_n
+        if self._stage_used[i]:
+            self._stage_event[i].synchronize()          # the copy that last read this buffer has finished
+        fill(self._stage_host[i])
+        self._act.copy_(self._stage_pinned[i], non_blocking=True)
+        self._stage_event[i].record(torch.cuda.current_stream(self.device))
+        self._stage_used[i] = True
 
     def step(self, actions):
         if self.terminated:

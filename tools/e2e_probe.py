@@ -25,12 +25,10 @@ env.reset()
 print('step_host                       us', timeit(lambda i: env.step_host(host[i])))
 print('D2H obs only + sync             us', timeit(lambda i: (env._obs_pinned.copy_(env._obs, non_blocking=True), torch.cuda.synchronize())))
 print('D2H reward only + sync          us', timeit(lambda i: (env._reward_pinned.copy_(env._reward, non_blocking=True), torch.cuda.synchronize())))
-print('host memcpy act->pinned         us', timeit(lambda i: env._act_pinned.copy_(torch.from_numpy(host[i]))))
-print('H2D act + sync                  us', timeit(lambda i: (env._act.copy_(env._act_pinned, non_blocking=True), torch.cuda.synchronize())))
 big = torch.empty((E, env._obs_dim)).pin_memory()
 print('D2H obs into fresh pinned       us', timeit(lambda i: (big.copy_(env._obs, non_blocking=True), torch.cuda.synchronize())))
 import ctypes
-print('pinned? ', env._obs_pinned.is_pinned(), env._act_pinned.is_pinned(), big.is_pinned())
+print('pinned? ', env._obs_pinned.is_pinned(), big.is_pinned())
 print('D2H fused out (obs+reward) + sync us', timeit(lambda i: (env._out_pinned.copy_(env._out, non_blocking=True), torch.cuda.synchronize())))
 n = env._out.numel()
 p2 = torch.empty(n, dtype=torch.float32, pin_memory=True)
