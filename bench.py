@@ -320,7 +320,11 @@ def main():
     achieved = bytes_per_launch / avg_launch_s / 1e9
     traffic = None
     try:
-        traffic = json.loads((ROOT / 'profiles' / 'step_kernel_traffic.json').read_text()).get(args.precision)
+        # measured DRAM bytes (ncu --set full: dram__bytes_read.sum + dram__bytes_write.sum) per step of the same workload, scaled to
+        # the steps of one launch like `achieved`; only valid for the default workload the capture was taken on
+        rec = json.loads((ROOT / 'profiles' / 'step_kernel_traffic.json').read_text()).get(args.precision)
+        if rec and args.envs == ENVS_PER_GPU:
+            traffic = (rec['dram_read_bytes_per_step'] + rec['dram_write_bytes_per_step']) * steps_per_launch
     except Exception:
         pass
     cpu = None
@@ -339,7 +343,7 @@ def main():
                    'l2': f'every step writes its own obs/reward slab: {K} x {bpu * units_per_step / 1e6:.1f} MB > 126 MB L2',
                    'envs_sharded_across_gpus': True, 'collectives_on_step_path': 0},
         'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic,
-                     'kernel': 'rollout_kernel', 'bytes_per_unit': bpu, 'bytes_per_step': bpu * units_per_step, 'bytes_per_launch': bytes_per_launch, 'steps_per_launch': steps_per_launch,
+                     'kernel': 'advance_kernel', 'bytes_per_unit': bpu, 'bytes_per_step': bpu * units_per_step, 'bytes_per_launch': bytes_per_launch, 'steps_per_launch': steps_per_launch,
                      'avg_launch_us': avg_launch_s * 1e6, 'peak_source': 'MEASURED_PEAKS.json hbm_gbs' if peaks else 'fallback 6650'},
         'cpu_baseline': cpu,
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': E * A * 4, 'd2h_bytes_per_step': E * L * 4 + E * B * 4,

@@ -860,26 +860,32 @@ extern "C" int cl_create(const cl_district_desc* desc, cl_env** out) {
             if (!(desc->iparams[CL_IP_FLAGS * B + b] & CL_F_DYNAMICS)) continue;
             const int nin = desc->iparams[CL_IP_DYN_N_INPUTS * B + b], H = desc->iparams[CL_IP_DYN_HIDDEN * B + b];
             const int L = desc->iparams[CL_IP_DYN_LOOKBACK * B + b], off = desc->iparams[CL_IP_DYN_W_OFFSET * B + b];
-            if (H != kLstmH || nin < 1 || nin > kLstmIn || L < 1 || L > kLstmMaxLookback) {
+            if (H < 1 || H > kLstmH || nin < 1 || nin > kLstmIn || L < 1 || L > kLstmMaxLookback) {
                 delete env;
-                return fail(CL_ERR_UNSUPPORTED, "cl_create: LSTM dynamics supports hidden_size 16, <= 16 inputs, lookback <= 12, 2 layers");
+                return fail(CL_ERR_UNSUPPORTED, "cl_create: LSTM dynamics supports hidden_size <= 16, <= 16 inputs, lookback <= 12, 2 layers");
             }
-            const size_t need = (size_t)64 * nin + 64 * 16 + 128 + 2 * 64 * 16 + 128 + 16 + 1;
+            // source blocks have their natural sizes ([4H, nin], [4H, H], [4H] ...); the device layout is padded to 16 hidden
+            // units / 16 inputs.  Padded hidden units have zero weights and biases: their cell and output stay exactly 0.
+            const int G = 4 * H;
+            const size_t need = (size_t)G * nin + (size_t)G * H + 2 * G + 2 * (size_t)G * H + 2 * G + H + 1;
             if (off < 0 || (size_t)off + need > (size_t)desc->lstm_weight_count) { delete env; return fail(CL_ERR_INVALID, "cl_create: lstm_weights block out of range"); }
             const float* w = desc->lstm_weights + off;
             float* o = &packed[(size_t)b * kLstmStride];
-            const float* wih0 = w; const float* whh0 = wih0 + 64 * nin; const float* bih0 = whh0 + 64 * 16; const float* bhh0 = bih0 + 64;
-            const float* wih1 = bhh0 + 64; const float* whh1 = wih1 + 64 * 16; const float* bih1 = whh1 + 64 * 16; const float* bhh1 = bih1 + 64;
-            const float* wl = bhh1 + 64; const float* bl = wl + 16;
-            for (int r = 0; r < 64; ++r) {
-                for (int i = 0; i < nin; ++i) o[r * 16 + i] = wih0[r * nin + i];
-                for (int i = 0; i < 16; ++i) o[64 * 16 + r * 16 + i] = whh0[r * 16 + i];
-                o[64 * 32 + r] = bih0[r] + bhh0[r];
-                for (int i = 0; i < 16; ++i) o[kLstmLayerStride + r * 16 + i] = wih1[r * 16 + i];
-                for (int i = 0; i < 16; ++i) o[kLstmLayerStride + 64 * 16 + r * 16 + i] = whh1[r * 16 + i];
-                o[kLstmLayerStride + 64 * 32 + r] = bih1[r] + bhh1[r];
+            const float* wih0 = w; const float* whh0 = wih0 + G * nin; const float* bih0 = whh0 + G * H; const float* bhh0 = bih0 + G;
+            const float* wih1 = bhh0 + G; const float* whh1 = wih1 + G * H; const float* bih1 = whh1 + G * H; const float* bhh1 = bih1 + G;
+            const float* wl = bhh1 + G; const float* bl = wl + H;
+            for (int q = 0; q < 4; ++q) {
+                for (int j = 0; j < H; ++j) {
+                    const int rs = q * H + j, r = q * kLstmH + j;      // gate-major rows (i, f, g, o)
+                    for (int i = 0; i < nin; ++i) o[r * 16 + i] = wih0[rs * nin + i];
+                    for (int i = 0; i < H; ++i) o[64 * 16 + r * 16 + i] = whh0[rs * H + i];
+                    o[64 * 32 + r] = bih0[rs] + bhh0[rs];
+                    for (int i = 0; i < H; ++i) o[kLstmLayerStride + r * 16 + i] = wih1[rs * H + i];
+                    for (int i = 0; i < H; ++i) o[kLstmLayerStride + 64 * 16 + r * 16 + i] = whh1[rs * H + i];
+                    o[kLstmLayerStride + 64 * 32 + r] = bih1[rs] + bhh1[rs];
+                }
             }
-            for (int i = 0; i < 16; ++i) o[2 * kLstmLayerStride + i] = wl[i];
+            for (int i = 0; i < H; ++i) o[2 * kLstmLayerStride + i] = wl[i];
             o[2 * kLstmLayerStride + 16] = bl[0];
         }
         float* pw = nullptr;

@@ -89,6 +89,10 @@ F_HS_HAS_MAX_IN = 1 << 7
 F_HS_HAS_MAX_OUT = 1 << 8
 F_DS_HAS_MAX_IN = 1 << 9
 F_DS_HAS_MAX_OUT = 1 << 10
+F_CS_CAPACITY_F32 = 1 << 11     # autosized tank: capacity is an np.float32 in the reference -> `action * capacity` is a float32 product
+F_HS_CAPACITY_F32 = 1 << 12
+F_CD_NOMINAL_F32 = 1 << 13      # autosized heat pump: np.float32 nominal power -> float32 `action * nominal_power`
+F_HD_NOMINAL_F32 = 1 << 14
 
 # per-unit dynamic values (obs writer / reward / trace)  (cl_dyn)
 DYN = {name: i for i, name in enumerate([
@@ -410,6 +414,30 @@ def resolve_battery(attrs: Optional[dict], seed: int) -> dict:
     }
 
 
+def _autosize(device_name: str, dev: dict, series: Mapping[str, np.ndarray], spec: 'DistrictSpec', seed: int, kwargs: dict):
+    """Load-time sizing of heat pumps, heaters and tanks to the building's peak demand over the simulation window
+    (`Building.autosize_*`, citylearn/building.py:2284-2403; device formulas citylearn/energy_model.py:309-352, 425-450, 770-795).
+
+    Devices are sized right after construction, while their own `time_step_ratio` is still 1, on float32 series - the sized
+    value is therefore a float32 number, which is kept (it feeds float64 arithmetic later).
+    """
+    window = slice(spec.simulation_start_time_step, spec.simulation_end_time_step + 1)
+    end_use = device_name.split('_')[0]
+    demand = np.asarray(series[f'{end_use}_demand'][window], dtype='float32')
+    with np.errstate(divide='ignore', invalid='ignore'):
+        if dev['type'] == 'StorageTank':
+            safety = _draw(kwargs.get('safety_factor'), (1.0, 2.0), seed)
+            dev['capacity'] = float(np.nanmax(demand * 1.0) * safety)
+        elif dev['type'] == 'HeatPump':
+            safety = _draw(kwargs.get('safety_factor'), 1.0, seed)
+            cop = cop32(dev, series['outdoor_dry_bulb_temperature'][window], heating=end_use != 'cooling')
+            dev['nominal_power'] = float(np.nanmax(np.array(demand * 1) / cop + 0) * safety)
+        else:
+            safety = _draw(kwargs.get('safety_factor'), 1.0, seed)
+            dev['nominal_power'] = float(np.nanmax(np.array(demand * 1) / dev['efficiency']) * safety)
+    dev['autosized'] = True
+
+
 _DEVICE_RESOLVERS = {
     'citylearn.energy_model.HeatPump': resolve_heat_pump,
     'citylearn.energy_model.ElectricHeater': resolve_electric_heater,
@@ -681,7 +709,9 @@ def _load_building(index, name, sch, source: DataSource, observations, actions, 
         ds = bs.get(dn)
         if ds is None or (dn == 'pv' and not solar_generation):
             continue
-        if ds.get('autosize'):
+        if ds.get('autosize') and dn in ('electrical_storage', 'pv'):
+            # Battery / PV autosizing samples external sizing tables and runs SAM's PVWatts (citylearn/energy_model.py:490-600,
+            # 1143-1260): a dataset-construction step, not part of the stepped path.
             raise UnsupportedSchemaError(f"building '{name}': autosize of '{dn}' is outside the accelerated hot path (SURVEY.md §2 row 2e)")
         dt = ds['type']
         attrs = dict(ds.get('attributes', {}) or {})
@@ -695,6 +725,8 @@ def _load_building(index, name, sch, source: DataSource, observations, actions, 
         attrs.pop('seconds_per_time_step', None)
         devices[dn] = _DEVICE_RESOLVERS[dt](attrs, seed)
         devices[dn]['class'] = dt
+        if ds.get('autosize'):
+            _autosize(dn, devices[dn], series, spec, seed, dict(ds.get('autosize_attributes') or {}))
     for dn, resolver in _ABSENT_DEFAULT.items():
         if dn not in devices:
             if dn == 'electrical_storage':
@@ -1009,6 +1041,8 @@ def finalize(spec: DistrictSpec) -> None:
         for pre, dn in (('CS', 'cooling_storage'), ('HS', 'heating_storage'), ('DS', 'dhw_storage')):
             t = dv[dn]
             p[P[f'{pre}_CAPACITY']] = t['capacity']
+            if t.get('autosized') and pre != 'DS':
+                flags |= F_CS_CAPACITY_F32 if pre == 'CS' else F_HS_CAPACITY_F32
             p[P[f'{pre}_EFFICIENCY']] = t['efficiency']
             p[P[f'{pre}_LOSS']] = t['loss_coefficient']
             p[P[f'{pre}_INITIAL_SOC']] = t['initial_soc']
@@ -1020,6 +1054,10 @@ def finalize(spec: DistrictSpec) -> None:
                 flags |= {'CS': F_CS_HAS_MAX_OUT, 'HS': F_HS_HAS_MAX_OUT, 'DS': F_DS_HAS_MAX_OUT}[pre]
         cd = dv['cooling_device']
         p[P['CD_NOMINAL_POWER']] = cd['nominal_power']
+        if cd.get('autosized'):
+            flags |= F_CD_NOMINAL_F32
+        if dv['heating_device'].get('autosized'):
+            flags |= F_HD_NOMINAL_F32
         p[P['CD_COP_NUM']] = cd['efficiency'] * (cd['target_cooling_temperature'] + 273.15)
         p[P['CD_TARGET']] = cd['target_cooling_temperature']
         for pre, dn, fl in (('HD', 'heating_device', F_HEATING_IS_HEAT_PUMP), ('DD', 'dhw_device', F_DHW_IS_HEAT_PUMP)):

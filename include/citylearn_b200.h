@@ -93,6 +93,10 @@ enum cl_building_iparam {
 #define CL_F_HS_HAS_MAX_OUT       (1 << 8)
 #define CL_F_DS_HAS_MAX_IN        (1 << 9)
 #define CL_F_DS_HAS_MAX_OUT       (1 << 10)
+#define CL_F_CS_CAPACITY_F32      (1 << 11) /* autosized tank: np.float32 capacity -> float32 `action * capacity` (energy_model.py:770-795) */
+#define CL_F_HS_CAPACITY_F32      (1 << 12)
+#define CL_F_CD_NOMINAL_F32       (1 << 13) /* autosized heat pump: np.float32 nominal power -> float32 `action * nominal_power` (building.py:3110,3146) */
+#define CL_F_HD_NOMINAL_F32       (1 << 14)
 
 /* ---- per-unit dynamic values at time step t (trace output, DYN observation slots) --------------- */
 enum cl_dyn {

@@ -398,11 +398,15 @@ class OracleEnv:
         if self.has_dyn and self.window_fill > self.L_max():
             sim = dyn_b & ((self.ip[:, IP['A_COOLING_DEVICE']][None, :] >= 0) | (slot_coh[None, :] >= 0))
             power = a_cd * self.P('CD_NOMINAL_POWER') * hstep
+            cd32 = ((self.flags & S.F_CD_NOMINAL_F32) != 0)[None, :]      # autosized: np.float32 nominal power (building.py:3110)
+            power = np.where(cd32, ((a_cd.astype(np.float32) * self.P('CD_NOMINAL_POWER').astype(np.float32)) * np.float32(hstep)).astype(f64), power)
             d = np.minimum(power, avail64('cool')) * eff['cool'].astype(f64)
             d = np.where((hvac == 1) | (hvac == 3), d, 0.0)
             dem32['cool'] = np.where(sim, w32(d), dem32['cool']).astype(np.float32)
             simh = dyn_b & ((self.ip[:, IP['A_HEATING_DEVICE']][None, :] >= 0) | (slot_coh[None, :] >= 0))
             powerh = a_hd * self.P('HD_NOMINAL_POWER')          # no hours factor (:3146)
+            hd32 = ((self.flags & S.F_HD_NOMINAL_F32) != 0)[None, :]
+            powerh = np.where(hd32, (a_hd.astype(np.float32) * self.P('HD_NOMINAL_POWER').astype(np.float32)).astype(f64), powerh)
             dh = np.minimum(powerh, avail64('heat')) * eff['heat'].astype(f64)
             dh = np.where((hvac == 2) | (hvac == 3), dh, 0.0)
             dem32['heat'] = np.where(simh, w32(dh), dem32['heat']).astype(np.float32)
@@ -419,11 +423,14 @@ class OracleEnv:
             cons = input_power(key, out64, is32 & np.broadcast_to(eff_is_cop[key] | True, (E, B)))
             add_ec(key, np.maximum(0.0, cons), np.ones((E, B), dtype=bool))
 
-        def storage(key, pre_tank, cap_for_action, hours, a_s, mask):
+        def storage(key, pre_tank, cap_for_action, hours, a_s, mask, cap_f32=None):
             if not mask.any():
                 return
             sk = sk_of[key]
-            energy = a_s * cap_for_action * hours                # python float
+            energy = a_s * cap_for_action * hours                # python float ...
+            if cap_f32 is not None:                              # ... unless the tank was autosized: np.float32 capacity
+                e32 = (a_s.astype(np.float32) * cap_for_action.astype(np.float32)) * np.float32(hours)
+                energy = np.where(cap_f32[None, :], e32.astype(f64), energy)
             mo64 = max_output64(key)
             up = energy > 0.0
             lim_up = mo64 <= energy                             # min(max_output, energy): np.float64 wins when smaller or equal
@@ -440,14 +447,15 @@ class OracleEnv:
         thermal = bool((self.flags & S.F_HAS_THERMAL).any())
         if thermal:
             # storage goes before its device when discharging (building.py:1614-1622)
-            plan = (('cool', 'CS', self.P('CS_CAPACITY'), 1.0, a_cs),
-                    ('heat', 'HS', self.P('CS_CAPACITY'), hstep, a_hs),    # COOLING tank capacity (building.py:1720)
-                    ('dhw', 'DS', self.P('HS_CAPACITY'), hstep, a_ds))     # HEATING tank capacity (building.py:1765)
-            for key, pre_tank, capa, hours, a_s in plan:
+            cs32, hs32 = (self.flags & S.F_CS_CAPACITY_F32) != 0, (self.flags & S.F_HS_CAPACITY_F32) != 0
+            plan = (('cool', 'CS', self.P('CS_CAPACITY'), 1.0, a_cs, cs32),
+                    ('heat', 'HS', self.P('CS_CAPACITY'), hstep, a_hs, cs32),    # COOLING tank capacity (building.py:1720)
+                    ('dhw', 'DS', self.P('HS_CAPACITY'), hstep, a_ds, hs32))     # HEATING tank capacity (building.py:1765)
+            for key, pre_tank, capa, hours, a_s, c32 in plan:
                 neg = np.broadcast_to(a_s < 0.0, (E, B))
-                storage(key, pre_tank, capa, hours, a_s, neg)
+                storage(key, pre_tank, capa, hours, a_s, neg, c32)
                 device(key)
-                storage(key, pre_tank, capa, hours, a_s, ~neg)
+                storage(key, pre_tank, capa, hours, a_s, ~neg, c32)
             self.soc_cs, self.soc_hs, self.soc_ds = [soc_new[k].astype(f64) for k in ('cs', 'hs', 'ds')]
         # non-shiftable load (building.py:1784-1789)
         dem_nsl = np.minimum(np.broadcast_to(nsl32, (E, B)).astype(f64), flex64())

@@ -205,6 +205,9 @@ def sparse(K):
 P1 = 'citylearn_challenge_2022_phase_1'
 PALL = 'citylearn_challenge_2022_phase_all'
 C23 = 'citylearn_challenge_2023_phase_2_local_evaluation'
+Z20 = 'citylearn_challenge_2020_climate_zone_1'
+BAEDA = 'baeda_3dem'
+C23P3 = 'citylearn_challenge_2023_phase_3_1'
 MARL = {'type': 'citylearn.reward_function.MARL', 'attributes': {}}
 
 CASES = {
@@ -230,6 +233,13 @@ CASES = {
                              reward={'type': 'citylearn.reward_function.SolarPenaltyAndComfortReward',
                                      'attributes': {'band': 1.0, 'lower_exponent': 2.0, 'higher_exponent': 3.0, 'coefficients': [1.0, 2.0]}},
                              steps=200, seed=4),
+    # thermal tanks + autosized heat pumps / heaters / tanks (2020 challenge, 9 buildings; cooling, dhw and battery actions)
+    'c6_tanks_2020': dict(dataset=Z20, steps=None, record=sparse, seed=6),
+    'c6_tanks_2020_marl_central': dict(dataset=Z20, overrides={'central_agent': True}, reward=MARL, steps=150, seed=7),
+    # cooling tank + cooling-device action on LSTM buildings (hidden 8, 11 inputs); Building_4's 1x50 LSTM is outside the kernel's shape
+    'c6_baeda3': dict(dataset=BAEDA, overrides={'buildings': ['Building_1', 'Building_2', 'Building_3']}, steps=600, seed=8),
+    # 6 LSTM buildings with stochastic outages, central agent, full 2207-step episode
+    'c7_phase3': dict(dataset=C23P3, steps=None, record=sparse, seed=9),
 }
 
 if __name__ == '__main__':

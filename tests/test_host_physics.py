@@ -70,7 +70,7 @@ CHECKED = ['electrical_storage_soc', 'electrical_storage_energy_balance', 'elect
            'non_shiftable_load_electricity_consumption']
 
 
-@pytest.mark.parametrize('case', ['c1_phase1_300', 'c1_subhour', 'c2_marl', 'c3_marl'])
+@pytest.mark.parametrize('case', ['c1_phase1_300', 'c1_subhour', 'c2_marl', 'c3_marl', 'c6_tanks_2020_marl_central', 'c6_baeda3'])
 def test_fp64_flow_is_bit_exact(hostlib, case):
     z, cfg, _ = load_golden(case)
     spec = spec_for(cfg)

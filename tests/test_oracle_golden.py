@@ -11,7 +11,7 @@ from helpers import TRACE_TO_DYN, actions_of, golden_cases, load_golden, max_abs
 # is reproduced to the last bit; the golden traces are stored as float32, hence the half-ulp allowances.
 TOL = {
     'default': 0.0,
-    'electrical_storage_degraded_capacity': 3e-7,     # float64 in the reference, float32 in the fixture
+    'electrical_storage_degraded_capacity': 6e-8,     # relative: float64 in the reference, float32 in the fixture
     'indoor_dry_bulb_temperature': 2e-5,
 }
 
@@ -40,8 +40,12 @@ def test_oracle_reproduces_reference(case):
                 worst['reward'] = max(worst.get('reward', 0.0), max_abs_diff(rew[0], z['reward'][gi]) / max(1.0, float(np.nanmax(np.abs(z['reward'][gi])))))
                 worst['district'] = max(worst.get('district', 0.0), max_abs_diff(dist[0], z['district'][gi]))
                 for gn, dn in TRACE_TO_DYN.items():
-                    worst[gn] = max(worst.get(gn, 0.0), max_abs_diff(dyn[0, :, DYN[dn]].astype('float32') if gn != 'electrical_storage_degraded_capacity' else dyn[0, :, DYN[dn]],
-                                                                    z['trace'][gi, :, tn.index(gn)]))
+                    ref = z['trace'][gi, :, tn.index(gn)]
+                    if gn == 'electrical_storage_degraded_capacity':      # float64 in the reference, float32 in the fixture: half an ulp
+                        d = float(np.max(np.abs(dyn[0, :, DYN[dn]] - ref) / np.maximum(1.0, np.abs(ref))))
+                    else:
+                        d = max_abs_diff(dyn[0, :, DYN[dn]].astype('float32'), ref)
+                    worst[gn] = max(worst.get(gn, 0.0), d)
                 gi += 1
     assert gi == len(z['steps'])
     for k, v in worst.items():

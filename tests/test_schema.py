@@ -24,10 +24,13 @@ def test_names_spaces_and_devices_match_reference(case):
         np.testing.assert_allclose(b.action_high, mb['action_high'], rtol=1e-6)
         bat, mbat = b.devices['electrical_storage'], mb['electrical_storage']
         # md5-seeded stochastic defaults (citylearn/citylearn.py:2364-2378, energy_model.py:977-1003)
-        np.testing.assert_allclose(bat['power_efficiency_curve'], mbat['power_efficiency_curve'], rtol=1e-13)
-        np.testing.assert_allclose(bat['capacity_power_curve'], mbat['capacity_power_curve'], rtol=1e-13)
-        for k in ('capacity', 'nominal_power', 'depth_of_discharge', 'capacity_loss_coefficient', 'initial_soc'):
-            assert bat[k] == pytest.approx(mbat[k], rel=1e-13)
+        if not bat.get('absent'):   # an absent battery is a zero-sized one whose defaults the reference draws from the global `random`
+            np.testing.assert_allclose(bat['power_efficiency_curve'], mbat['power_efficiency_curve'], rtol=1e-13)
+            np.testing.assert_allclose(bat['capacity_power_curve'], mbat['capacity_power_curve'], rtol=1e-13)
+            for k in ('capacity', 'nominal_power', 'depth_of_discharge', 'capacity_loss_coefficient', 'initial_soc'):
+                assert bat[k] == pytest.approx(mbat[k], rel=1e-13)
+        else:
+            assert mbat['capacity'] == 0.0 and mbat['nominal_power'] == 0.0
         for dn in ('cooling_storage', 'heating_storage', 'dhw_storage', 'cooling_device', 'heating_device', 'dhw_device'):
             if b.devices[dn].get('absent'):
                 continue          # absent devices get unreproducible random parameters in the reference
