@@ -8,6 +8,7 @@ from __future__ import annotations
 import ctypes
 import os
 from pathlib import Path
+from typing import Optional
 
 import numpy as np
 
@@ -70,8 +71,11 @@ def load():
     lib.cl_get_state.argtypes = [vp, vp, vp]
     lib.cl_set_state.argtypes = [vp, vp, i32, vp]
     lib.cl_launch_count.argtypes = [vp, i64p]
+    i32p = ctypes.POINTER(ctypes.c_int32)
+    lib.cl_launch_geometry.argtypes = [vp, i32p, i32p, i32p]
+    lib.cl_set_transforms.argtypes = [vp, vp, vp, vp]
     for name in ('cl_create', 'cl_destroy', 'cl_set_outage', 'cl_reset', 'cl_step', 'cl_rollout', 'cl_time_step',
-                 'cl_state_size', 'cl_get_state', 'cl_set_state', 'cl_launch_count'):
+                 'cl_state_size', 'cl_get_state', 'cl_set_state', 'cl_launch_count', 'cl_launch_geometry', 'cl_set_transforms'):
         getattr(lib, name).restype = ctypes.c_int
     if lib.cl_abi_version() != ABI_VERSION:
         raise NativeLibraryError(f'{path}: ABI version {lib.cl_abi_version()} != {ABI_VERSION}; rebuild the extension')
@@ -164,6 +168,23 @@ class Handle:
 
     def set_state(self, src_ptr, time_step: int, stream: int):
         check(self.lib.cl_set_state(self.ptr, src_ptr, int(time_step), stream), 'cl_set_state')
+
+    def set_transforms(self, obs_transform: Optional[np.ndarray], action_range: Optional[np.ndarray], action_low: Optional[np.ndarray]):
+        """Fused wrapper semantics (host arrays, copied by the call): cl_obs_transform records [L]; action range / low [A]."""
+        t = None if obs_transform is None else np.ascontiguousarray(obs_transform, dtype=S.OBS_TRANSFORM_DTYPE)
+        r = None if action_range is None else np.ascontiguousarray(action_range, dtype='float32')
+        l = None if action_low is None else np.ascontiguousarray(action_low, dtype='float32')
+        check(self.lib.cl_set_transforms(self.ptr, None if t is None else t.ctypes.data, None if r is None else r.ctypes.data,
+                                         None if l is None else l.ctypes.data), 'cl_set_transforms')
+
+    def geometry(self):
+        b, t, n = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
+        check(self.lib.cl_launch_geometry(self.ptr, ctypes.byref(b), ctypes.byref(t), ctypes.byref(n)))
+        return {'blocks': b.value, 'threads': t.value, 'tiles': n.value}
+
+    @property
+    def tiles(self) -> int:
+        return self.geometry()['tiles']
 
     def launch_count(self) -> int:
         n = ctypes.c_int64()

@@ -35,6 +35,14 @@ namespace cl {
 struct Dev {
     int B, E, U, n_rows, W, Wp, A, L, T;
     int central, reward_id, stale, envs_per_block, uniform_start, start0, has_outage, any_dynamics, lstm_smem;
+    // building tiles: a district wider than one block is split into `tiles` tiles of `tile_b` buildings, one CTA per tile,
+    // the CTAs of an env forming a thread-block cluster (tiles == 1: tile_b == B, Lt == L, no cluster)
+    int tiles, tile_b, Lt;
+    const int32_t* tile_k; // [tiles + 1] observation-row range of every tile (wide districts only)
+    // optional wrapper semantics fused into the observation writers / action fetch (cl_set_transforms; nullptr: identity)
+    const cl_obs_transform* obs_t;   // [L]
+    const float* act_range;          // [A] normalised action a in [0, 1] -> a * range + low (wrappers.py:208-222)
+    const float* act_low;            // [A]
     float rp[8];
     const float* table;
     const float* pf;       // [NPARAM][B]
@@ -159,16 +167,27 @@ __device__ __forceinline__ void load_inputs(const Dev& d, const UnitCtx<R>& c, c
 struct RawActions { float es, cd, hd, coh, cs, hs, ds; };
 
 template <typename R, bool THERMAL>
-__device__ __forceinline__ void fetch_actions(const UnitCtx<R>& c, const float* act_row, RawActions& a) {
-    a.es = c.a_es >= 0 ? __ldg(act_row + c.a_es) : 0.f;
+__device__ __forceinline__ void fetch_actions(const Dev& d, const UnitCtx<R>& c, const float* act_row, RawActions& a) {
+    // with an action transform the caller's values are fractions of the action range (NormalizedActionWrapper)
+    auto get = [&](int col) -> float {
+        if (col < 0) return 0.f;
+        const float v = __ldg(act_row + col);
+        return d.act_range ? v * __ldg(d.act_range + col) + __ldg(d.act_low + col) : v;
+    };
+    a.es = get(c.a_es);
     if (THERMAL) {
-        a.cd = c.a_cd >= 0 ? __ldg(act_row + c.a_cd) : 0.f;
-        a.hd = c.a_hd >= 0 ? __ldg(act_row + c.a_hd) : 0.f;
-        a.coh = c.a_coh >= 0 ? __ldg(act_row + c.a_coh) : 0.f;
-        a.cs = c.a_cs >= 0 ? __ldg(act_row + c.a_cs) : 0.f;
-        a.hs = c.a_hs >= 0 ? __ldg(act_row + c.a_hs) : 0.f;
-        a.ds = c.a_ds >= 0 ? __ldg(act_row + c.a_ds) : 0.f;
+        a.cd = get(c.a_cd); a.hd = get(c.a_hd); a.coh = get(c.a_coh);
+        a.cs = get(c.a_cs); a.hs = get(c.a_hs); a.ds = get(c.a_ds);
     }
+}
+
+// observation transform of column k (cl_obs_transform): periodic sin / cos, affine min-max, clip - NaN passes through
+__device__ __forceinline__ float transform_obs(const cl_obs_transform* t, int k, float v) {
+    const cl_obs_transform x = t[k];
+    if (x.fn == CL_OBS_FN_SIN) v = sinf(v * x.w);
+    else if (x.fn == CL_OBS_FN_COS) v = cosf(v * x.w);
+    v = v * x.scale + x.offset;
+    return v < x.lo ? x.lo : (v > x.hi ? x.hi : v);
 }
 
 // inactive storage actions are 0, inactive device actions NaN (building.py:1555-1564)
@@ -326,31 +345,44 @@ __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk
 template <int N> __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 template <int N> __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
 
+// thread-block cluster primitives (wide districts): rank, all-thread barrier, distributed-shared-memory loads
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_map(uint32_t local_smem_addr, uint32_t rank) {
+    uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(rank)); return r;
+}
+__device__ __forceinline__ float ld_cluster_f32(uint32_t addr) { float v; asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory"); return v; }
+__device__ __forceinline__ double ld_cluster_f64(uint32_t addr) { double v; asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(addr) : "memory"); return v; }
+
 // ------------------------------------------------------------------------------------------------------------------
 // observation writers: the rows of a block's envs are one contiguous span obs[e0*L .. (e0+n)*L)
 // ------------------------------------------------------------------------------------------------------------------
 // general path: any descriptor kind, per-env start rows, DYN values from shared memory (or zero)
 __device__ __forceinline__ void write_obs_general(const Dev& d, float* obs, int e0, int n_env, int t_obs,
-                                                   const float* dynbuf /* [n_env*B][CL_NDYN] or nullptr */, int tid, int nt) {
-    const int L = d.L;
-    const int total = n_env * L;
+                                                   const float* dynbuf /* [n_env*nb][CL_NDYN] or nullptr */, int tid, int nt,
+                                                   int k0, int k1, int b0, int nb) {
+    const int L = d.L, Lt = k1 - k0;               // this block writes columns [k0, k1) of its envs' rows (whole rows: k0 = 0, k1 = L)
+    const int total = n_env * Lt;
     int j = tid;
-    int e_l = j / L, k = j - e_l * L;
-    const int de = nt / L, dk = nt - de * L;
+    int e_l = j / Lt, k = j - e_l * Lt;
+    const int de = nt / Lt, dk = nt - de * Lt;
     for (; j < total; j += nt) {
-        const int4 ds = __ldg(d.desc + k);
+        const int4 ds = __ldg(d.desc + k0 + k);
         float v;
         if (ds.x == CL_OBS_TS) {
             const int row = __ldg(d.start + e0 + e_l) + t_obs;
             v = __ldg(d.table + (size_t)row * d.Wp + ds.y);
         } else if (ds.x == CL_OBS_DYN) {
-            v = dynbuf ? dynbuf[(e_l * d.B + ds.w) * CL_NDYN + ds.y] : 0.f;
+            v = dynbuf ? dynbuf[(e_l * nb + (ds.w - b0)) * CL_NDYN + ds.y] : 0.f;
         } else {
             v = d.has_outage ? __ldg(d.outage + ds.w * d.T + t_obs) : 0.f;
         }
-        obs[(size_t)e0 * L + j] = v;
+        if (d.obs_t) v = transform_obs(d.obs_t, k0 + k, v);
+        obs[(size_t)(e0 + e_l) * L + k0 + k] = v;
         e_l += de; k += dk;
-        if (k >= L) { k -= L; e_l += 1; }
+        if (k >= Lt) { k -= Lt; e_l += 1; }
     }
 }
 
@@ -362,7 +394,7 @@ __device__ __forceinline__ void write_obs_general(const Dev& d, float* obs, int 
 // offsets in floats from the start of the dynamic shared memory (kept as plain ints so that every access is derived
 // directly from the `extern __shared__` array and compiles to LDS/STS with 32-bit addressing, not generic loads)
 struct SmemLayout {
-    int curves, bsolar, rows, tcol, tmpl, red, rsum, dsum, lstm, dynbuf, Lp;
+    int curves, bsolar, rows, tcol, tmpl, red, rsum, dsum, wpart, rpart, lstm, dynbuf, Lp;
 };
 __host__ __device__ __forceinline__ SmemLayout smem_layout(int B, int Wp, int L, int epb, int nt, int rsize, int lstm_smem = 0) {
     SmemLayout o;
@@ -376,12 +408,14 @@ __host__ __device__ __forceinline__ SmemLayout smem_layout(int B, int Wp, int L,
     o.red = f; f += 6 * nt;
     o.rsum = f; f += nt;
     o.dsum = f; f += (2 * epb + 3) & ~3;
+    o.wpart = f; f += 2 * 3 * 32;                // wide districts: per-warp partial district sums [2][3][32 warps]
+    o.rpart = f; f += 2 * 32 * 2;                // wide districts, central agent: per-warp partial reward sums [2][32] doubles (8-byte aligned: f is even)
     o.lstm = f; f += lstm_smem ? B * kLstmStride : 0;      // kLstmStride is a multiple of 4 floats: 16-byte aligned rows
     o.dynbuf = f;
     return o;
 }
 static size_t smem_bytes(const Dev& d, int nt, bool with_dyn, int rsize) {
-    const SmemLayout o = smem_layout(d.B, d.Wp, d.L, d.envs_per_block, nt, rsize, d.lstm_smem);
+    const SmemLayout o = smem_layout(d.tile_b, d.Wp, d.Lt, d.envs_per_block, nt, rsize, d.lstm_smem);
     size_t n = sizeof(float) * (size_t)o.dynbuf;
     if (with_dyn) n += sizeof(float) * (size_t)nt * CL_NDYN;
     return n;
@@ -474,7 +508,7 @@ __device__ __forceinline__ float lstm_update(const Dev& d, const UnitCtx<R>& c, 
 // of step t.  `red`, `dsum` and the per-building buffers are double-buffered by step parity, so one barrier per step suffices
 // (two when a reward needs the district sum, more for central-agent sums).
 // ------------------------------------------------------------------------------------------------------------------
-template <typename R, bool THERMAL, bool DYNAMICS, int MAXT>
+template <typename R, bool THERMAL, bool DYNAMICS, int MAXT, bool WIDE = false>
 __global__ void __launch_bounds__(MAXT) advance_kernel(Dev d, int t0, int K, const float* __restrict__ actions, float* __restrict__ obs,
                                                         float* __restrict__ reward, float* __restrict__ district, float* __restrict__ trace) {
     extern __shared__ __align__(16) float smf[];
@@ -483,7 +517,16 @@ __global__ void __launch_bounds__(MAXT) advance_kernel(Dev d, int t0, int K, con
     const bool is_helper = tid >= np_;
     const int lane = tid & 31;
     const int B = d.B, epb = d.envs_per_block, Wp = d.Wp;
-    const SmemLayout lo = smem_layout(B, Wp, d.L, epb, nt, (int)sizeof(R), DYNAMICS ? d.lstm_smem : 0);
+    // wide districts: CTA `rank` of the cluster owns buildings [b0, b0 + nb) of the cluster's env(s) and columns [k0, k1) of
+    // their observation rows; otherwise the block owns whole envs (b0 = 0, nb = B, [k0, k1) = [0, L))
+    const int NT = WIDE ? d.tiles : 1;
+    const int rank = WIDE ? (int)cluster_ctarank() : 0;
+    const int TBs = WIDE ? d.tile_b : B;            // smem stride of per-building arrays
+    const int b0 = rank * TBs;
+    const int nb = WIDE ? min(TBs, B - b0) : B;
+    const int k0 = WIDE ? __ldg(d.tile_k + rank) : 0, k1 = WIDE ? __ldg(d.tile_k + rank + 1) : d.L;
+    const int Ltile = k1 - k0;
+    const SmemLayout lo = smem_layout(TBs, Wp, WIDE ? d.Lt : d.L, epb, nt, (int)sizeof(R), DYNAMICS ? d.lstm_smem : 0);
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(smf);
     R* scurves = reinterpret_cast<R*>(smf + lo.curves);
     R* s_bsolar = reinterpret_cast<R*>(smf + lo.bsolar);          // [2][B] PV generation of the step, per building
@@ -492,15 +535,18 @@ __global__ void __launch_bounds__(MAXT) advance_kernel(Dev d, int t0, int K, con
     float* s_dsum = smf + lo.dsum;
     float* s_rsum = smf + lo.rsum;
     float* s_dynbuf = smf + lo.dynbuf;
-    const int e0 = blockIdx.x * epb;
+    float* s_wpart = smf + lo.wpart;
+    double* s_rpart = reinterpret_cast<double*>(smf + lo.rpart);
+    const int e0 = (WIDE ? (int)blockIdx.x / NT : (int)blockIdx.x) * epb;
     const int n_env = min(epb, d.E - e0);
-    const int n_units = n_env * B;
+    const int n_units = n_env * nb;
     const bool active = tid < n_units;
     // thread -> unit: env-major (building fastest: coalesced state / action / reward slices) except for LSTM districts, where
     // building-major keeps the lanes of a warp on ONE building so that its LSTM weights are broadcast loads
-    const int b = DYNAMICS ? tid / n_env : tid % B;
-    const int e_l = DYNAMICS ? tid - b * n_env : tid / B;
-    const int ul = e_l * B + b;                    // unit slot inside the block's shared-memory arrays (always env-major)
+    const int bl = DYNAMICS ? tid / n_env : tid % nb;       // building inside the tile
+    const int e_l = DYNAMICS ? tid - bl * n_env : tid / nb;
+    const int b = b0 + bl;
+    const int ul = e_l * nb + bl;                  // unit slot inside the block's shared-memory arrays (always env-major)
     const int e = e0 + e_l, u = e * B + b;
     const bool uniform = d.uniform_start != 0;
     const bool want_dyn = (!d.stale && obs != nullptr);
@@ -520,10 +566,10 @@ __global__ void __launch_bounds__(MAXT) advance_kernel(Dev d, int t0, int K, con
         }
     }
     // block-wide staging: template columns and the battery curves of every building (dynamic indexing -> shared memory)
-    if (tmpl_path) for (int k = tid; k < d.L; k += nt) s_tcol[k] = __ldg(d.tcol + k);
+    if (tmpl_path) for (int k = tid; k < Ltile; k += nt) s_tcol[k] = __ldg(d.tcol + k0 + k);
     {
         const auto* P = PSel<R>::p(d) + CL_P_PE_X0 * B;
-        for (int i = tid; i < B * 32; i += nt) { const int bb = i >> 5, j = i & 31; scurves[i] = (R)__ldg(P + j * B + bb); }
+        for (int i = tid; i < nb * 32; i += nt) { const int bb = b0 + (i >> 5), j = i & 31; scurves[i] = (R)__ldg(P + j * B + bb); }
     }
     UnitCtx<R> c;
     UnitState<R> s;
@@ -533,9 +579,9 @@ __global__ void __launch_bounds__(MAXT) advance_kernel(Dev d, int t0, int K, con
         load_ctx<R, THERMAL>(d, b, c);
         load_state<R, THERMAL>(d, u, s);
         start_e = __ldg(d.start + e);
-        fetch_actions<R, THERMAL>(c, actions + (size_t)e * d.A, act_next);
+        fetch_actions<R, THERMAL>(d, c, actions + (size_t)e * d.A, act_next);
     }
-    const R* curves = scurves + (active ? b : 0) * 32;
+    const R* curves = scurves + (active ? bl : 0) * 32;
     const float* lstm_w = nullptr;
     if (DYNAMICS) {
         if (d.lstm_smem) {                            // stage every building's packed LSTM weights in shared memory (16-byte copies)
@@ -552,9 +598,9 @@ __global__ void __launch_bounds__(MAXT) advance_kernel(Dev d, int t0, int K, con
     // per-building PV generation of time row `rowp` -> dst[b]  (building.py:2554; the same value for every env of the block)
     auto building_inputs = [&](const float* rowp, R* dst) {
         const auto* P = PSel<R>::p(d);
-        for (int bb = lane; bb < B; bb += 32) {
-            const R pv = (R)__ldg(P + CL_P_PV_NOMINAL_POWER * B + bb);
-            dst[bb] = -dvd(pv * (R)rowp[__ldg(d.ip + CL_IP_C_SOLAR * B + bb)], (R)1000);
+        for (int bb = lane; bb < nb; bb += 32) {
+            const R pv = (R)__ldg(P + CL_P_PV_NOMINAL_POWER * B + b0 + bb);
+            dst[bb] = -dvd(pv * (R)rowp[__ldg(d.ip + CL_IP_C_SOLAR * B + b0 + bb)], (R)1000);
         }
     };
     if (uniform) {
@@ -591,35 +637,37 @@ __global__ void __launch_bounds__(MAXT) advance_kernel(Dev d, int t0, int K, con
 
         if (is_helper) {
             // ---------------- helper warp ----------------
-            if (uniform && k + 1 < K) building_inputs(row_next, s_bsolar + ((k + 1) & 1) * B);
-            __syncthreads();                                                   // S1
+            if (uniform && k + 1 < K) building_inputs(row_next, s_bsolar + ((k + 1) & 1) * TBs);
+            if (WIDE) cluster_sync_all(); else __syncthreads();                // S1
             if (need_dsum) __syncthreads();                                    // S2
-            if (central_sync) { if (k > 0) __syncthreads(); __syncthreads(); }
+            if (central_sync) { if (WIDE) cluster_sync_all(); else { if (k > 0) __syncthreads(); __syncthreads(); } }
             if (tmpl_path) {
                 // observation slab of step k: every env row of the block equals the row gathered from time row t+1
-                float* ok = obs + (size_t)k * d.E * d.L + (size_t)e0 * d.L;
+                float* ok = obs + (size_t)k * d.E * d.L + (size_t)e0 * d.L + k0;
                 const int L = d.L;
                 auto gather = [&](int j) -> float {
                     const int cc = s_tcol[j];
-                    if (cc >= 0) return row_next[cc];
-                    if (cc == -1) return 0.f;
-                    return d.has_outage ? __ldg(d.outage + (-2 - cc) * d.T + t + 1) : 0.f;
+                    float v;
+                    if (cc >= 0) v = row_next[cc];
+                    else if (cc == -1) v = 0.f;
+                    else v = d.has_outage ? __ldg(d.outage + (-2 - cc) * d.T + t + 1) : 0.f;
+                    return d.obs_t ? transform_obs(d.obs_t, k0 + j, v) : v;
                 };
-                if ((L & 3) == 0) {
+                if (((L | k0 | Ltile) & 3) == 0) {
                     // build the row once in shared memory, then one TMA bulk store (cp.async.bulk shared -> global) per env row:
                     // the copy engine moves the slab, the SM's load/store path stays free for the physics warps
                     float* tmpl = smf + lo.tmpl + pb * lo.Lp;
                     tma_store_wait_read<1>();                                   // the stores issued two steps ago have read this buffer
-                    for (int j = lane; j < L; j += 32) tmpl[j] = gather(j);
+                    for (int j = lane; j < Ltile; j += 32) tmpl[j] = gather(j);
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // generic-proxy writes -> visible to the async proxy
                     __syncwarp();
                     if (lane == 0) {
-                        const uint32_t bytes = (uint32_t)L * sizeof(float);
+                        const uint32_t bytes = (uint32_t)Ltile * sizeof(float);
                         for (int le = 0; le < n_env; ++le) tma_store_1d(ok + (size_t)le * L, tmpl, bytes);
                         tma_store_commit();
                     }
                 } else {
-                    for (int j = lane; j < L; j += 32) {
+                    for (int j = lane; j < Ltile; j += 32) {
                         const float v = gather(j);
                         for (int le = 0; le < n_env; ++le) __stcs(ok + (size_t)le * L + j, v);
                     }
@@ -636,9 +684,9 @@ __global__ void __launch_bounds__(MAXT) advance_kernel(Dev d, int t0, int K, con
         if (active) {
             UnitInputs<R> in;
             load_inputs<R, THERMAL>(d, c, row, b, t, in, uniform);
-            if (uniform) in.solar = s_bsolar[pb * B + b];
+            if (uniform) in.solar = s_bsolar[pb * TBs + bl];
             apply_actions<R, THERMAL>(c, act_next, in);
-            if (k + 1 < K) fetch_actions<R, THERMAL>(c, actions + ((size_t)(k + 1) * d.E + e) * d.A, act_next);   // prefetch
+            if (k + 1 < K) fetch_actions<R, THERMAL>(d, c, actions + ((size_t)(k + 1) * d.E + e) * d.A, act_next);   // prefetch
             if (DYNAMICS && (c.p.flags & CL_F_DYNAMICS) && t > c.dyn_lookback) {
                 // partial-load control is live once the input window is full (building.py:3108, 3144)
                 in.control_cooling_demand = (c.a_cd >= 0 || c.a_coh >= 0);
@@ -676,7 +724,22 @@ __global__ void __launch_bounds__(MAXT) advance_kernel(Dev d, int t0, int K, con
             }
         }
         CL_STAMP(4);
-        __syncthreads();                                                       // S1: red / dynbuf / next-step building inputs complete
+        if (WIDE) {
+            // the tile's partial district sums: fixed-order shuffle tree per warp, one slot per warp; the cluster barrier below
+            // publishes them to every CTA of the env (distributed shared memory)
+            float vn = active ? (float)o.net : 0.f, vc = active ? (float)o.cost : 0.f, ve = active ? (float)o.emission : 0.f;
+#pragma unroll
+            for (int m = 16; m > 0; m >>= 1) {
+                vn += __shfl_xor_sync(0xffffffffu, vn, m); vc += __shfl_xor_sync(0xffffffffu, vc, m); ve += __shfl_xor_sync(0xffffffffu, ve, m);
+            }
+            if (lane == 0) {
+                const int w = tid >> 5;
+                s_wpart[(pb * 3 + 0) * 32 + w] = vn; s_wpart[(pb * 3 + 1) * 32 + w] = vc; s_wpart[(pb * 3 + 2) * 32 + w] = ve;
+            }
+            cluster_sync_all();                                                // S1 for the whole cluster
+        } else {
+            __syncthreads();                                                   // S1: red / dynbuf / next-step building inputs complete
+        }
         CL_STAMP(5);
         if (uniform && tid == 0 && k + 3 <= K) {
             // nobody reads row t any more (reward inputs were captured above): its slot takes the row of step t + 3
@@ -686,6 +749,21 @@ __global__ void __launch_bounds__(MAXT) advance_kernel(Dev d, int t0, int K, con
         }
         // district sums in building order, like the reference's sum() over buildings (citylearn.py:1908-1918);
         // one thread per (quantity, env)
+        if (WIDE) {
+            // district sums = partial sums of every tile, in (tile, warp) order - the same order in every CTA of the cluster
+            // (float32 like the reference, but a different association than its left-to-right sum(): DESIGN.md 'Wide districts')
+            if (tid < 3 && (tid == 0 || district != nullptr)) {
+                const int q = tid, nw = np_ >> 5;
+                const uint32_t local = smem_u32(s_wpart + (pb * 3 + q) * 32);
+                float acc = 0.f;
+                for (int r = 0; r < NT; ++r) {
+                    const uint32_t ra = cluster_map(local, (uint32_t)r);
+                    for (int w = 0; w < nw; ++w) acc += ld_cluster_f32(ra + 4u * (uint32_t)w);
+                }
+                if (q == 0) s_dsum[pb * epb] = acc;
+                if (district != nullptr && rank == 0) district[((size_t)k * d.E + e0) * 3 + q] = acc;
+            }
+        } else
         for (int idx = tid; idx < 3 * n_env; idx += np_) {
             const int q = idx / n_env, le = idx - q * n_env;
             if (q > 0 && district == nullptr) continue;
@@ -705,7 +783,22 @@ __global__ void __launch_bounds__(MAXT) advance_kernel(Dev d, int t0, int K, con
                 r = unit_reward(d.reward_id, d.rp, ri);
             }
             float* rk = reward + (size_t)k * d.E * Rdim;
-            if (d.central) {
+            if (d.central && WIDE) {
+                double v = active ? (double)r : 0.0;
+#pragma unroll
+                for (int m = 16; m > 0; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+                if (lane == 0) s_rpart[pb * 32 + (tid >> 5)] = v;
+                cluster_sync_all();
+                if (rank == 0 && tid == 0) {
+                    const uint32_t local = smem_u32(s_rpart + pb * 32);
+                    double acc = 0.0;
+                    for (int rr = 0; rr < NT; ++rr) {
+                        const uint32_t ra = cluster_map(local, (uint32_t)rr);
+                        for (int w = 0; w < (np_ >> 5); ++w) acc += ld_cluster_f64(ra + 8u * (uint32_t)w);
+                    }
+                    rk[e0] = (float)acc;
+                }
+            } else if (d.central) {
                 if (k > 0) __syncthreads();                                    // previous step's rsum readers are done
                 s_rsum[ul] = r;
                 __syncthreads();
@@ -726,7 +819,7 @@ __global__ void __launch_bounds__(MAXT) advance_kernel(Dev d, int t0, int K, con
         }
         CL_STAMP(6);
         if (obs != nullptr && !tmpl_path) {
-            write_obs_general(d, obs + (size_t)k * d.E * d.L, e0, n_env, t + 1, want_dyn ? s_dynbuf : nullptr, tid, np_);
+            write_obs_general(d, obs + (size_t)k * d.E * d.L, e0, n_env, t + 1, want_dyn ? s_dynbuf : nullptr, tid, np_, k0, k1, b0, nb);
             if (want_dyn && k + 1 < K) __syncthreads();                         // dynbuf is single-buffered
         }
     }
@@ -735,6 +828,7 @@ __global__ void __launch_bounds__(MAXT) advance_kernel(Dev d, int t0, int K, con
 #endif
     if (is_helper) tma_store_wait_all<0>();
     if (active && !is_helper) store_state<R, THERMAL>(d, u, s);
+    if (WIDE) cluster_sync_all();     // nobody exits while a peer may still read its partial sums
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -745,12 +839,16 @@ __global__ void __launch_bounds__(MAXT) reset_kernel(Dev d, float* __restrict__ 
     extern __shared__ __align__(16) float smf[];
     const int nt = blockDim.x, tid = threadIdx.x;
     const int B = d.B, epb = d.envs_per_block;
-    const SmemLayout lo = smem_layout(B, d.Wp, d.L, epb, nt, (int)sizeof(R));
+    const SmemLayout lo = smem_layout(d.tile_b, d.Wp, d.Lt, epb, nt, (int)sizeof(R));
     float* s_dynbuf = smf + lo.dynbuf;
-    const int e0 = blockIdx.x * epb;
+    // building tiles (wide districts): block (group, rank) owns buildings [b0, b0 + nb) and observation columns [k0, k1)
+    const int rank = (int)blockIdx.x % d.tiles;
+    const int b0 = rank * d.tile_b, nb = min(d.tile_b, B - b0);
+    const int k0 = d.tiles > 1 ? __ldg(d.tile_k + rank) : 0, k1 = d.tiles > 1 ? __ldg(d.tile_k + rank + 1) : d.L;
+    const int e0 = ((int)blockIdx.x / d.tiles) * epb;
     const int n_env = min(epb, d.E - e0);
-    const int n_units = n_env * B;
-    const int e_l = tid / B, b = tid - e_l * B;
+    const int n_units = n_env * nb;
+    const int e_l = tid / nb, b = b0 + (tid - e_l * nb);
     const int e = e0 + e_l, u = e * B + b;
     if (tid < n_units) {
         const auto* P = PSel<R>::p(d);
@@ -778,7 +876,7 @@ __global__ void __launch_bounds__(MAXT) reset_kernel(Dev d, float* __restrict__ 
     }
     if (obs != nullptr) {
         __syncthreads();
-        write_obs_general(d, obs, e0, n_env, 0, s_dynbuf, tid, nt);
+        write_obs_general(d, obs, e0, n_env, 0, s_dynbuf, tid, nt, k0, k1, b0, nb);
     }
 }
 
@@ -802,6 +900,7 @@ struct cl_env {
     int t = -1;              // -1: not reset
     int T = 0;
     int threads = 0, blocks = 0;
+    bool wide = false;       // building-tiled district: cluster launch of advance_kernel<..., WIDE = true>
     int64_t launches = 0;
     std::vector<void*> allocs;
     float* outage_dev = nullptr;
@@ -829,7 +928,7 @@ extern "C" int cl_create(const cl_district_desc* desc, cl_env** out) {
     if (desc->abi_version != CL_ABI_VERSION) return fail(CL_ERR_INVALID, "cl_create: ABI version mismatch");
     if (desc->n_buildings < 1 || desc->n_envs < 1 || desc->n_rows < 2 || desc->n_cols < 1 || desc->obs_dim < 1)
         return fail(CL_ERR_INVALID, "cl_create: empty district");
-    if (desc->n_buildings > 992) return fail(CL_ERR_UNSUPPORTED, "cl_create: more than 992 buildings per district not supported yet (one env per block + helper warp)");
+    if (desc->n_buildings > 8 * 480) return fail(CL_ERR_UNSUPPORTED, "cl_create: more than 3840 buildings per district (8 tiles of 480) not supported");
     if (!desc->table || !desc->params || !desc->iparams || !desc->obs_desc) return fail(CL_ERR_INVALID, "cl_create: null table/params");
     if (desc->precision != CL_PRECISION_FP32 && desc->precision != CL_PRECISION_FP64) return fail(CL_ERR_INVALID, "cl_create: bad precision");
     cl_env* env = new (std::nothrow) cl_env();
@@ -992,8 +1091,76 @@ extern "C" int cl_create(const cl_district_desc* desc, cl_env** out) {
     if (epb < 1) epb = 1;
     if (epb > d.E) epb = d.E;
     d.envs_per_block = epb;
+    d.tiles = 1; d.tile_b = B; d.Lt = d.L; d.tile_k = nullptr;
     env->threads = ((epb * B + 31) / 32) * 32;
     env->blocks = (d.E + epb - 1) / epb;
+    // Wide districts: one env per thread-block CLUSTER, the buildings split into `tiles` tiles of `tile_b` (one CTA each); the
+    // district sums travel through distributed shared memory.  Chosen when a whole env does not fit one 512-thread block
+    // (CL_B200_TILES forces a tile count for experiments).
+    int want_tiles = 0;
+    if (const char* ev = std::getenv("CL_B200_TILES")) { const int v = std::atoi(ev); if (v >= 2 && v <= 8) want_tiles = v; }
+    if ((B > 480 || want_tiles) && !any_dyn) {
+        int regs_w = regs;
+        {
+            cudaFuncAttributes fa;
+            const void* fn = env->precision == CL_PRECISION_FP64
+                ? (any_thermal ? (const void*)advance_kernel<double, true, false, 512, true> : (const void*)advance_kernel<double, false, false, 512, true>)
+                : (any_thermal ? (const void*)advance_kernel<float, true, false, 512, true> : (const void*)advance_kernel<float, false, false, 512, true>);
+            if (cudaFuncGetAttributes(&fa, fn) == cudaSuccess && fa.numRegs > 0) regs_w = fa.numRegs;
+            cudaGetLastError();
+        }
+        // observation columns of a tile must be one contiguous range: rows are ordered by building (schema.observation_layout)
+        auto tile_ranges = [&](int nt_, int tb, std::vector<int32_t>& tk) -> bool {
+            tk.assign(nt_ + 1, d.L);
+            int prev = 0;
+            tk[0] = 0;
+            for (int k = 0; k < d.L; ++k) {
+                const int bb = desc->obs_desc[4 * (size_t)k + 3];
+                if (bb < prev) return false;
+                for (int r = prev / tb + 1; r <= bb / tb && r <= nt_; ++r) tk[r] = k;
+                prev = bb;
+            }
+            for (int r = 1; r <= nt_; ++r) if (tk[r] < tk[r - 1]) tk[r] = tk[r - 1];
+            tk[nt_] = d.L;
+            return true;
+        };
+        int best_nt = 0; double best_score = -1.0; std::vector<int32_t> best_tk;
+        for (int nt_ = 2; nt_ <= 8; ++nt_) {
+            if (want_tiles && nt_ != want_tiles) continue;
+            const int tb = (B + nt_ - 1) / nt_;
+            if (tb > 480 || (nt_ - 1) * tb >= B) continue;              // every tile must own at least one building
+            std::vector<int32_t> tk;
+            if (!tile_ranges(nt_, tb, tk)) continue;
+            int lt = 0;
+            for (int r = 0; r < nt_; ++r) lt = std::max(lt, tk[r + 1] - tk[r]);
+            const int thr = ((tb + 31) / 32) * 32 + 32;
+            Dev probe = d; probe.tiles = nt_; probe.tile_b = tb; probe.Lt = lt; probe.envs_per_block = 1;
+            const size_t sm = smem_bytes(probe, thr, true, env->precision == CL_PRECISION_FP64 ? 8 : 4);
+            if (sm > 200 * 1024) continue;
+            const int regs_alloc = ((regs_w + 7) / 8) * 8;
+            int bps = 65536 / (regs_alloc * thr);
+            bps = std::min(bps, 2048 / thr);
+            bps = std::min(bps, (int)((227 * 1024) / (sm + 1024)));
+            if (bps < 1) continue;
+            const double score = (double)bps * tb - 1e-3 * nt_;           // resident physics threads per SM; fewer tiles on ties
+            if (score > best_score) { best_score = score; best_nt = nt_; best_tk = tk; }
+        }
+        if (best_nt == 0) {
+            if (B > 992 || want_tiles) { cl_destroy(env); return fail(CL_ERR_UNSUPPORTED, "cl_create: no building tiling fits this district (observation rows must be ordered by building; <= 8 tiles of <= 480 buildings)"); }
+        } else {
+            const int tb = (B + best_nt - 1) / best_nt;
+            int lt = 0;
+            for (int r = 0; r < best_nt; ++r) lt = std::max(lt, best_tk[r + 1] - best_tk[r]);
+            int32_t* tkd = nullptr;
+            int rc = dev_copy(env, best_tk.data(), best_tk.size(), &tkd);
+            if (rc) { cl_destroy(env); return rc; }
+            d.tiles = best_nt; d.tile_b = tb; d.Lt = lt; d.tile_k = tkd; d.envs_per_block = 1;
+            env->wide = true;
+            env->threads = ((tb + 31) / 32) * 32;
+            env->blocks = d.E * best_nt;
+        }
+    }
+    if (!env->wide && B > 992) { cl_destroy(env); return fail(CL_ERR_UNSUPPORTED, "cl_create: districts wider than 992 buildings with LSTM dynamics are not supported"); }
     // opt in to large dynamic shared memory once (both kernels, all instantiations)
     const size_t smem = smem_bytes(d, env->threads + 32, true, 8);
     if (smem > 200 * 1024) { cl_destroy(env); return fail(CL_ERR_UNSUPPORTED, "cl_create: district too wide for the shared-memory staging"); }
@@ -1002,6 +1169,8 @@ extern "C" int cl_create(const cl_district_desc* desc, cl_env** out) {
 #define OPTINA(M) OPTIN((advance_kernel<float, false, false, M>)); OPTIN((advance_kernel<float, true, false, M>)); OPTIN((advance_kernel<float, true, true, M>)); \
     OPTIN((advance_kernel<double, false, false, M>)); OPTIN((advance_kernel<double, true, false, M>)); OPTIN((advance_kernel<double, true, true, M>))
     OPTINA(512); OPTINA(1024); OPTIN4(reset_kernel, 512); OPTIN4(reset_kernel, 1024);
+    OPTIN((advance_kernel<float, false, false, 512, true>)); OPTIN((advance_kernel<float, true, false, 512, true>));
+    OPTIN((advance_kernel<double, false, false, 512, true>)); OPTIN((advance_kernel<double, true, false, 512, true>));
 #undef OPTINA
 #undef OPTIN4
 #undef OPTIN
@@ -1049,6 +1218,19 @@ static void launch_advance(cl_env* env, int K, const float* actions, float* obs,
     const bool want_dyn = !env->d.stale && obs != nullptr;
     const int nthreads = env->threads + 32;          // + the helper warp
     const size_t smem = smem_bytes(env->d, nthreads, want_dyn, (int)sizeof(R));
+    if (env->wide) {
+        // one thread-block cluster per env: `tiles` CTAs, one per building tile
+        if constexpr (!DY) {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((unsigned)env->blocks); cfg.blockDim = dim3((unsigned)nthreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = (unsigned)env->d.tiles; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            cudaLaunchKernelEx(&cfg, advance_kernel<R, TH, false, 512, true>, env->d, env->t, K, actions, obs, reward, district, trace);
+        }
+        return;
+    }
     if (nthreads <= 512) advance_kernel<R, TH, DY, 512><<<env->blocks, nthreads, smem, st>>>(env->d, env->t, K, actions, obs, reward, district, trace);
     else advance_kernel<R, TH, DY, 1024><<<env->blocks, nthreads, smem, st>>>(env->d, env->t, K, actions, obs, reward, district, trace);
 }
@@ -1160,6 +1342,40 @@ extern "C" int cl_set_state(cl_env* env, const void* src_dev, int32_t time_step,
     p += env->st_floats * sizeof(float);
     if (env->lst_floats) CUDA_TRY(cudaMemcpyAsync(env->d.lst, p, env->lst_floats * sizeof(float), cudaMemcpyDeviceToDevice, st));
     env->t = time_step;
+    return CL_OK;
+}
+
+extern "C" int cl_set_transforms(cl_env* env, const cl_obs_transform* obs_transform, const float* action_range, const float* action_low) {
+    if (!env) return fail(CL_ERR_INVALID, "cl_set_transforms: null env");
+    if ((action_range == nullptr) != (action_low == nullptr)) return fail(CL_ERR_INVALID, "cl_set_transforms: action_range and action_low go together");
+    Dev& d = env->d;
+    CUDA_TRY(cudaDeviceSynchronize());            // configuration call: no launch may still read the previous arrays
+    d.obs_t = nullptr; d.act_range = nullptr; d.act_low = nullptr;
+    if (obs_transform) {
+        for (int k = 0; k < d.L; ++k) {
+            const int fn = obs_transform[k].fn;
+            if (fn != CL_OBS_FN_IDENTITY && fn != CL_OBS_FN_SIN && fn != CL_OBS_FN_COS) return fail(CL_ERR_INVALID, "cl_set_transforms: unknown observation function");
+        }
+        cl_obs_transform* p = nullptr;
+        int rc = dev_copy(env, obs_transform, (size_t)d.L, &p);
+        if (rc) return rc;
+        d.obs_t = p;
+    }
+    if (action_range) {
+        float *r = nullptr, *l = nullptr;
+        int rc = dev_copy(env, action_range, (size_t)d.A, &r);
+        if (!rc) rc = dev_copy(env, action_low, (size_t)d.A, &l);
+        if (rc) return rc;
+        d.act_range = r; d.act_low = l;
+    }
+    return CL_OK;
+}
+
+extern "C" int cl_launch_geometry(const cl_env* env, int32_t* blocks, int32_t* threads, int32_t* tiles) {
+    if (!env) return fail(CL_ERR_INVALID, "cl_launch_geometry: null env");
+    if (blocks) *blocks = env->blocks;
+    if (threads) *threads = env->threads + 32;
+    if (tiles) *tiles = env->d.tiles;
     return CL_OK;
 }
 

@@ -89,13 +89,19 @@ class PackSource(DataSource):
         self._path = str(path)
         self._npz = np.load(self._path, allow_pickle=False)
         self._index = json.loads(bytes(self._npz['__index__']).decode())
+        self._tables: Dict[str, Dict[str, np.ndarray]] = {}
 
     def schema(self) -> dict:
         return json.loads(bytes(self._npz['__schema__']).decode())
 
     def table(self, filename: str) -> Dict[str, np.ndarray]:
-        cols = self._index['tables'][filename]
-        return {c: self._npz[f'{filename}::{c}'].astype('float64') for c in cols}
+        if filename not in self._tables:        # decompress once; callers get a fresh dict of read-only arrays
+            cols = self._index['tables'][filename]
+            t = {c: self._npz[f'{filename}::{c}'].astype('float64') for c in cols}
+            for a in t.values():
+                a.setflags(write=False)
+            self._tables[filename] = t
+        return dict(self._tables[filename])
 
     def state_dict(self, filename: str) -> Dict[str, np.ndarray]:
         keys = self._index['state_dicts'][filename]

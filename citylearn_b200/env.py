@@ -98,7 +98,8 @@ class CityLearnEnv:
 
     def __init__(self, schema, num_envs: int = 1, device: Union[str, torch.device, None] = None, precision: str = 'fp64',
                  stale_observations: bool = True, track_episode_rewards: Optional[bool] = None, debug_trace: bool = False,
-                 record_history: Optional[bool] = None, history_env: int = 0, **kwargs):
+                 record_history: Optional[bool] = None, history_env: int = 0, observation_transform: Optional[str] = None,
+                 normalized_actions: bool = False, **kwargs):
         self.spec = S.load(schema, **kwargs)
         self.schema = self.spec.schema
         self.num_envs = int(num_envs)
@@ -124,9 +125,11 @@ class CityLearnEnv:
         self.random_episode_split = spec.random_episode_split
         self.episode_tracker = S.EpisodeTracker(spec.simulation_start_time_step, spec.simulation_end_time_step)
         self.buildings = [BuildingProxy(self, b) for b in spec.buildings]
-        self._entries, self._desc = S.observation_layout(spec, self.central_agent, self.stale_observations)
-        self._obs_dim = len(self._entries)
-        self._sizes_obs = [len(b.active_observations) for b in spec.buildings]
+        # `_entries` is the raw observation row (what `observation_names` / `observation_space` describe); `_out_entries` is the
+        # row the kernels write, which differs under a fused observation wrapper (citylearn_b200/wrappers.py)
+        self._entries, self._raw_desc = S.observation_layout(spec, self.central_agent, self.stale_observations)
+        self._observation_transform = observation_transform
+        self._normalized_actions = bool(normalized_actions)
         self._sizes_act = [len(b.active_actions) for b in spec.buildings]
         self._track = (self.num_envs == 1) if track_episode_rewards is None else bool(track_episode_rewards)
         # per-step history of ONE env for evaluate() (the reference keeps full series for its single env)
@@ -140,8 +143,38 @@ class CityLearnEnv:
         rid, rparams = self._fused_reward()
         self._reward_id = rid
         self._reward_dim = 1 if self.central_agent else spec.n_buildings
+        self._reward_params = rparams
+        self._debug_trace = debug_trace
+        self._h = None
+        self._build_native()
+        self._table_dev = None
+        self.time_step = 0
+        self._episode_rewards: List[Mapping[str, Any]] = []
+        self._rsum = self._rmin = self._rmax = None
+        self.reset()
+        self.episode_tracker.reset_episode_index()       # citylearn/citylearn.py:237-240
+        self.reward_function.env_metadata = self.get_metadata()
+        self._episode_rewards = []
+
+    def _build_native(self):
+        """(Re)create the device-side district and the output buffers for the current observation / action transforms."""
+        spec, rid, precision = self.spec, self._reward_id, self.precision
+        debug_trace = self._debug_trace
+        if self._observation_transform is None:
+            self._out_entries, self._desc, transforms = self._entries, self._raw_desc, None
+        else:
+            self._out_entries, self._desc, transforms = S.transformed_observation_layout(spec, self._entries, self._raw_desc, self._observation_transform)
+        self._obs_dim = len(self._out_entries)
+        counts = np.bincount(np.fromiter((bi for bi, _ in self._out_entries), dtype=np.int64, count=self._obs_dim), minlength=spec.n_buildings)
+        self._sizes_obs = [int(c) for c in counts]
+        if self._h is not None:
+            self._h.close()
         with torch.cuda.device(self.device):
-            self._h = _native.Handle(spec, self.num_envs, self._desc, self.central_agent, rid, rparams, precision, self.stale_observations)
+            self._h = _native.Handle(spec, self.num_envs, self._desc, self.central_agent, rid, self._reward_params, precision, self.stale_observations)
+            if transforms is not None or self._normalized_actions:
+                lo = np.array([v for b in spec.buildings for v in b.action_low], dtype='float32')
+                hi = np.array([v for b in spec.buildings for v in b.action_high], dtype='float32')
+                self._h.set_transforms(transforms, (hi - lo) if self._normalized_actions else None, lo if self._normalized_actions else None)
             E = self.num_envs
             # observations and rewards share one allocation so that the host path needs ONE device->host copy per step
             self._out = torch.zeros(E * (self._obs_dim + self._reward_dim), dtype=torch.float32, device=self.device)
@@ -163,13 +196,19 @@ class CityLearnEnv:
             self._obs_pinned = self._out_pinned[:E * self._obs_dim].view(E, self._obs_dim)
             self._reward_pinned = self._out_pinned[E * self._obs_dim:].view(E, self._reward_dim)
             self._obs_host, self._reward_host = self._obs_pinned.numpy(), self._reward_pinned.numpy()
-        self._table_dev = None
-        self.time_step = 0
-        self._episode_rewards: List[Mapping[str, Any]] = []
-        self._rsum = self._rmin = self._rmax = None
+
+    def configure_transforms(self, observation_transform: Optional[str] = 'unchanged', normalized_actions: Optional[bool] = None):
+        """Fuse wrapper semantics into the kernels (used by `citylearn_b200.wrappers`): `observation_transform` in
+        {None, 'normalized', 'clipped'}; `normalized_actions`: step() takes fractions of the action range.  Rebuilds the
+        device-side district, i.e. starts a fresh episode like a reset."""
+        if observation_transform != 'unchanged':
+            self._observation_transform = observation_transform
+        if normalized_actions is not None:
+            self._normalized_actions = bool(normalized_actions)
+        self._build_native()
+        self.episode_tracker.reset_episode_index()
         self.reset()
-        self.episode_tracker.reset_episode_index()       # citylearn/citylearn.py:237-240
-        self.reward_function.env_metadata = self.get_metadata()
+        self.episode_tracker.reset_episode_index()
         self._episode_rewards = []
 
     # ---------------------------------------------------------------------------------------------

@@ -547,7 +547,14 @@ def _ingest_energy_simulation(tab: Dict[str, np.ndarray], seconds_per_time_step:
 
 
 def load(schema: Union[str, os.PathLike, Mapping[str, Any]], **kwargs) -> DistrictSpec:
-    """schema (+ `CityLearnEnv.__init__` keyword overrides) -> finalized `DistrictSpec`."""
+    """schema (+ `CityLearnEnv.__init__` keyword overrides) -> finalized `DistrictSpec`.
+
+    An already loaded `DistrictSpec` is returned as is (several envs over one large district); overrides need a reload."""
+    if isinstance(schema, DistrictSpec):
+        extra = [k for k, v in kwargs.items() if v is not None]
+        if extra:
+            raise ValueError(f'a loaded DistrictSpec cannot take overrides {extra}: load the schema again with them')
+        return schema
     sch, source = resolve_source(schema, kwargs.get('root_directory'), kwargs.get('data_source'))
     sch = copy.deepcopy(sch)
     g = lambda k: kwargs.get(k)  # noqa: E731
@@ -780,6 +787,17 @@ def pv_generation(b: BuildingSpec, series: np.ndarray) -> np.ndarray:
     return b.devices['pv']['nominal_power'] * np.array(series, dtype='float64') / 1000.0
 
 
+def _bmin(a):
+    """Python's `min(array)` as the reference uses it (citylearn/building.py:1836-2106), vectorised when no NaN can change the answer."""
+    a = np.asarray(a)
+    return min(a) if a.ndim != 1 or a.size == 0 or np.isnan(a).any() else a[np.argmin(a)]
+
+
+def _bmax(a):
+    a = np.asarray(a)
+    return max(a) if a.ndim != 1 or a.size == 0 or np.isnan(a).any() else a[np.argmax(a)]
+
+
 def estimate_observation_space_limits(b: BuildingSpec, spec: DistrictSpec, include_all=False, periodic_normalization=False):
     internal = ['net_electricity_consumption_without_storage', 'net_electricity_consumption_without_storage_and_partial_load',
                 'net_electricity_consumption_without_storage_and_partial_load_and_pv']
@@ -794,7 +812,7 @@ def estimate_observation_space_limits(b: BuildingSpec, spec: DistrictSpec, inclu
     def dev_eff(d, heating):
         if d['type'] == 'HeatPump':
             cop = cop32(d, t_out, heating)
-            return min(cop), max(cop)
+            return _bmin(cop), _bmax(cop)
         return d['efficiency'], d['efficiency']
 
     def input_power(d, demand, heating):
@@ -833,7 +851,7 @@ def estimate_observation_space_limits(b: BuildingSpec, spec: DistrictSpec, inclu
         elif key in ('indoor_dry_bulb_temperature_cooling_delta', 'indoor_dry_bulb_temperature_heating_delta'):
             low[key], high[key] = -b.maximum_temperature_delta, b.maximum_temperature_delta
         elif key == 'comfort_band':
-            low[key], high[key] = 0, max(data[key])
+            low[key], high[key] = 0, _bmax(data[key])
         elif key in ('cooling_demand', 'heating_demand', 'dhw_demand'):
             low[key] = 0.0
             high[key] = data[key].max() * b.demand_observation_limit_factor
@@ -844,13 +862,13 @@ def estimate_observation_space_limits(b: BuildingSpec, spec: DistrictSpec, inclu
         elif key == 'dhw_electricity_consumption':
             low[key], high[key] = 0.0, dv['dhw_device']['nominal_power']
         elif key == 'cooling_storage_electricity_consumption':
-            low[key] = -max(input_power(dv['cooling_device'], data['cooling_demand'], False))
+            low[key] = -_bmax(input_power(dv['cooling_device'], data['cooling_demand'], False))
             high[key] = dv['cooling_device']['nominal_power']
         elif key == 'heating_storage_electricity_consumption':
-            low[key] = -max(input_power(dv['heating_device'], data['heating_demand'], True))
+            low[key] = -_bmax(input_power(dv['heating_device'], data['heating_demand'], True))
             high[key] = dv['heating_device']['nominal_power']
         elif key == 'dhw_storage_electricity_consumption':
-            low[key] = -max(input_power(dv['dhw_device'], data['dhw_demand'], True))
+            low[key] = -_bmax(input_power(dv['dhw_device'], data['dhw_demand'], True))
             high[key] = dv['dhw_device']['nominal_power']
         elif key == 'electrical_storage_electricity_consumption':
             low[key], high[key] = -dv['electrical_storage']['nominal_power'], dv['electrical_storage']['nominal_power']
@@ -859,14 +877,14 @@ def estimate_observation_space_limits(b: BuildingSpec, spec: DistrictSpec, inclu
         elif periodic_normalization and key in PERIODIC:
             x = 2 * np.pi * np.array(list(range(1, PERIODIC[key] + 1))) / PERIODIC[key]
             x_sin, x_cos = np.sin(x), np.cos(x)
-            low[f'{key}_cos'], high[f'{key}_cos'] = min(x_cos), max(x_cos)
-            low[f'{key}_sin'], high[f'{key}_sin'] = min(x_sin), max(x_sin)
+            low[f'{key}_cos'], high[f'{key}_cos'] = _bmin(x_cos), _bmax(x_cos)
+            low[f'{key}_sin'], high[f'{key}_sin'] = _bmin(x_sin), _bmax(x_sin)
         elif key == 'occupant_interaction_indoor_dry_bulb_temperature_set_point_delta':
             pass
         else:
             if key not in data:
                 raise UnsupportedSchemaError(f"observation '{key}' is outside the accelerated hot path")
-            low[key], high[key] = min(data[key]), max(data[key])
+            low[key], high[key] = _bmin(data[key]), _bmax(data[key])
     d = b.observation_space_limit_delta
     return {k: v - d for k, v in low.items()}, {k: v + d for k, v in high.items()}
 
@@ -1163,6 +1181,46 @@ def observation_layout(spec: DistrictSpec, central_agent: Optional[bool] = None,
         else:
             desc[j] = (OBS_TS, spec.columns[(bi, name)], 0, bi)
     return entries, desc
+
+
+PERIODIC_OBSERVATIONS = {'hour': 24, 'day_type': 7, 'month': 12, 'minutes': 60}   # max of the ranges in building.py:1484-1498
+OBS_FN_IDENTITY, OBS_FN_SIN, OBS_FN_COS = 0, 1, 2
+OBS_TRANSFORM_DTYPE = np.dtype([('fn', '<i4'), ('w', '<f4'), ('scale', '<f4'), ('offset', '<f4'), ('lo', '<f4'), ('hi', '<f4')])   # cl_obs_transform
+
+
+def transformed_observation_layout(spec: DistrictSpec, entries, desc: np.ndarray, mode: str):
+    """Observation row under a wrapper (`citylearn/wrappers.py:15-167`): (entries, descriptors, cl_obs_transform records).
+
+    'normalized' (NormalizedObservationWrapper): every periodic observation (hour, day_type, month) becomes a `<name>_cos`,
+    `<name>_sin` pair - in that order, `Building.observations(periodic_normalization=True)` building.py:1191-1204 - and every
+    value is min-max scaled with the limits of `estimate_observation_space_limits(include_all=True, periodic_normalization=True)`
+    (`x_min == x_max` gives 0, preprocessing.py:139-152).  'clipped' (ClippedObservationWrapper): values are clipped to the
+    observation space.
+    """
+    out_entries, rows, recs = [], [], []
+    limits = {}
+    for j, (bi, name) in enumerate(entries):
+        b = spec.buildings[bi]
+        if mode == 'normalized':
+            if bi not in limits:
+                limits[bi] = estimate_observation_space_limits(b, spec, include_all=True, periodic_normalization=True)
+            lo, hi = limits[bi]
+            parts = ([(f'{name}_cos', OBS_FN_COS), (f'{name}_sin', OBS_FN_SIN)] if name in PERIODIC_OBSERVATIONS else [(name, OBS_FN_IDENTITY)])
+            for n2, fn in parts:
+                x_min, x_max = float(lo[n2]), float(hi[n2])
+                scale, offset = (0.0, 0.0) if x_min == x_max else (1.0 / (x_max - x_min), -x_min / (x_max - x_min))
+                w = 2.0 * math.pi / PERIODIC_OBSERVATIONS[name] if fn != OBS_FN_IDENTITY else 0.0
+                out_entries.append((bi, n2))
+                rows.append(desc[j])
+                recs.append((fn, w, scale, offset, -np.inf, np.inf))
+        elif mode == 'clipped':
+            k = b.active_observations.index(name)
+            out_entries.append((bi, name))
+            rows.append(desc[j])
+            recs.append((OBS_FN_IDENTITY, 0.0, 1.0, 0.0, float(b.observation_low[k]), float(b.observation_high[k])))
+        else:
+            raise ValueError(f"unknown observation transform '{mode}' (expected 'normalized' or 'clipped')")
+    return out_entries, np.array(rows, dtype='int32').reshape(-1, 4), np.array(recs, dtype=OBS_TRANSFORM_DTYPE)
 
 
 def outage_signals(spec: DistrictSpec, episode_time_steps: int, episode_start: int) -> np.ndarray:

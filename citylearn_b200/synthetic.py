@@ -1,0 +1,91 @@
+"""Synthetic wide districts (BASELINE.json configs[3], SURVEY.md §8d "C4").
+
+Building i of an N-building district replays `Building_{(i mod 17)+1}.csv` of `citylearn_challenge_2022_phase_all` with its
+non-shiftable load scaled by `s_i = RandomState(seed).uniform(0.5, 1.5, N)[i]`, a 6.4 kWh / 5 kW battery (efficiency 0.9,
+capacity loss 1e-5, no self-discharge; curves are the reference's md5-seeded defaults, so they differ per building name) and
+a `4 + (i mod 2)` kW PV array.  Weather, pricing and carbon intensity are shared.
+
+`SyntheticWideSource` serves the district from memory; `write_directory` writes the same thing as a real schema directory
+(`schema.json` + CSV files) so that the unmodified reference can be run on it (oracle/make_golden.py uses a 32-building one).
+"""
+from __future__ import annotations
+
+import copy
+import json
+import os
+from pathlib import Path
+from typing import Dict, Optional
+
+import numpy as np
+
+from .data import DataSet, DataSource
+
+BASE = 'citylearn_challenge_2022_phase_all'
+N_BASE = 17
+
+
+class SyntheticWideSource(DataSource):
+    def __init__(self, n_buildings: int, seed: int = 0, base: Optional[DataSource] = None):
+        assert n_buildings >= 1
+        self.n = int(n_buildings)
+        self.base = DataSet.get_source(BASE) if base is None else base
+        self.scale = np.random.RandomState(seed).uniform(0.5, 1.5, self.n)
+
+    @staticmethod
+    def file_of(i: int) -> str:
+        return f'Synthetic_{i + 1}.csv'
+
+    def root_directory(self):
+        return None
+
+    def schema(self) -> dict:
+        s = copy.deepcopy(self.base.schema())
+        proto = s['buildings']['Building_1']
+        buildings = {}
+        for i in range(self.n):
+            b = copy.deepcopy(proto)
+            b['energy_simulation'] = self.file_of(i)
+            b['electrical_storage']['attributes'] = {'capacity': 6.4, 'efficiency': 0.9, 'capacity_loss_coefficient': 1e-05,
+                                                    'loss_coefficient': 0.0, 'nominal_power': 5.0}
+            b['pv']['attributes'] = {'nominal_power': 4.0 + (i % 2)}
+            buildings[f'Building_{i + 1}'] = b
+        s['buildings'] = buildings
+        s['root_directory'] = None
+        return s
+
+    def table(self, filename: str) -> Dict[str, np.ndarray]:
+        if filename.startswith('Synthetic_'):
+            i = int(filename[len('Synthetic_'):-len('.csv')]) - 1
+            t = dict(self.base.table(f'Building_{(i % N_BASE) + 1}.csv'))
+            # what a CSV round trip of the scaled float32 series gives: float64 text -> float32 in the loader
+            t['non_shiftable_load'] = np.asarray(t['non_shiftable_load'], dtype='float64') * self.scale[i]
+            return t
+        return self.base.table(filename)
+
+    def state_dict(self, filename: str):
+        return self.base.state_dict(filename)
+
+    def write_directory(self, root: os.PathLike) -> Path:
+        """Materialise the district as `root/schema.json` + CSV files (lossless decimal text)."""
+        root = Path(root)
+        root.mkdir(parents=True, exist_ok=True)
+        sch = self.schema()
+        files = {'weather.csv', 'carbon_intensity.csv', 'pricing.csv'} | {self.file_of(i) for i in range(self.n)}
+        for fn in sorted(files):
+            t = self.table(fn)
+            cols = list(t)
+            arr = np.stack([np.asarray(t[c], dtype='float64') for c in cols], axis=1)
+            with open(root / fn, 'w') as f:
+                f.write(','.join(cols) + '\n')
+                for r in arr:
+                    f.write(','.join('' if np.isnan(v) else repr(float(v)) for v in r) + '\n')
+        sch['root_directory'] = None
+        with open(root / 'schema.json', 'w') as f:
+            json.dump(sch, f, indent=1)
+        return root
+
+
+def make_wide_district(n_buildings: int = 1024, seed: int = 0):
+    """(schema dict, data source) of the synthetic N-building district; pass both to `CityLearnEnv(schema, data_source=...)`."""
+    src = SyntheticWideSource(n_buildings, seed)
+    return src.schema(), src

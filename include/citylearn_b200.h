@@ -207,6 +207,28 @@ int cl_set_state(cl_env* env, const void* src_dev, int32_t time_step, cl_stream 
 /* Number of kernels this library has launched on behalf of `env` since creation (bench.py's gpu_launches). */
 int cl_launch_count(const cl_env* env, int64_t* n);
 
+/*
+ * Wrapper semantics fused into the kernels (citylearn/wrappers.py:15-238).  Both arguments are HOST arrays
+ * copied by the call; NULL restores the identity.  Call between episodes (the call synchronises the device).
+ *   obs_transform [L]: per observation column  x -> clip(fn(x) * scale + offset, lo, hi)  with fn = identity, sin(w x) or
+ *       cos(w x): NormalizedObservationWrapper (periodic sin / cos columns are separate entries of obs_desc naming the same
+ *       source) and ClippedObservationWrapper.
+ *   action_range, action_low [action_dim]: the caller's actions are fractions in [0, 1]:  a -> a * range + low
+ *       (NormalizedActionWrapper :208-222).
+ */
+enum cl_obs_fn { CL_OBS_FN_IDENTITY = 0, CL_OBS_FN_SIN = 1, CL_OBS_FN_COS = 2 };
+typedef struct cl_obs_transform {
+    int32_t fn;        /* cl_obs_fn */
+    float w;           /* angular factor 2 pi / x_max of the periodic functions */
+    float scale, offset;
+    float lo, hi;      /* clip bounds (-inf / +inf: none) */
+} cl_obs_transform;
+int cl_set_transforms(cl_env* env, const cl_obs_transform* obs_transform, const float* action_range, const float* action_low);
+
+/* Launch geometry chosen at cl_create: CTAs per launch, threads per CTA (incl. the helper warp) and building tiles per env
+ * (1: a block owns whole envs; > 1: one thread-block cluster per env, one CTA per tile of buildings). */
+int cl_launch_geometry(const cl_env* env, int32_t* blocks, int32_t* threads, int32_t* tiles);
+
 const char* cl_last_error(void);
 int cl_abi_version(void);
 

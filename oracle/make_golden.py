@@ -65,7 +65,14 @@ def make_env(CityLearnEnv, dataset, overrides=None, reward=None):
         if isinstance(dflt, list):
             dflt.clear()
     overrides = dict(overrides or {})
-    root = DATASETS / dataset
+    if dataset.startswith('synthetic_wide_'):
+        # first N buildings of the synthetic wide district (BASELINE.json configs[3]), written out as a real schema directory
+        import tempfile
+        sys.path.insert(0, str(HERE.parent))
+        from citylearn_b200.synthetic import SyntheticWideSource
+        root = SyntheticWideSource(int(dataset.rsplit('_', 1)[1])).write_directory(tempfile.mkdtemp(prefix='citylearn_wide_'))
+    else:
+        root = DATASETS / dataset
     schema = json.load(open(root / 'schema.json'))
     schema['root_directory'] = str(root)
     if reward is not None:   # set in the schema dict so that schema attributes do not leak
@@ -198,6 +205,55 @@ def run_case(CityLearnEnv, name, dataset, overrides=None, reward=None, steps=Non
     print(name, {k: v.shape for k, v in arrays.items() if k not in ('config', 'meta')}, (OUT / f'{name}.npz').stat().st_size)
 
 
+def run_wrapper_case(CityLearnEnv, name, dataset, wrapper, overrides=None, steps=60, seed=0):
+    """Reference env under one of its own wrappers (citylearn/wrappers.py): records what the WRAPPED env returns."""
+    import citylearn.wrappers as W
+    base = make_env(CityLearnEnv, dataset, overrides, None)
+    env = getattr(W, wrapper)(base)
+    u = env.unwrapped
+    space = env.action_space
+    lo = np.concatenate([np.asarray(s.low, dtype='float64') for s in space])
+    hi = np.concatenate([np.asarray(s.high, dtype='float64') for s in space])
+    sizes = [s.shape[0] for s in space]
+    rng = np.random.RandomState(seed)
+    obs, _ = env.reset()
+    reset_obs = flat(obs)
+    K = min(steps, u.time_steps - 1)
+    actions = (lo + rng.uniform(0.0, 1.0, size=(K, len(lo))) * (hi - lo)).astype('float32')
+    out_obs, out_rew, out_soc = [], [], []
+    for k in range(K):
+        a = [float(x) for x in actions[k]]
+        act, o = [], 0
+        for n in sizes:
+            act.append(a[o:o + n])
+            o += n
+        obs, rew, term, trunc, _ = env.step(act)
+        out_obs.append(flat(obs))
+        out_rew.append(flat(rew))
+        out_soc.append([float(b.electrical_storage.soc[k]) for b in u.buildings])
+    arrays = {
+        'actions': actions, 'obs': np.array(out_obs, dtype='float64'), 'reward': np.array(out_rew, dtype='float32'),
+        'reset_obs': np.array(reset_obs, dtype='float64'), 'soc': np.array(out_soc, dtype='float32'),
+        'space_low': np.concatenate([np.asarray(s.low, dtype='float32') for s in env.observation_space]),
+        'space_high': np.concatenate([np.asarray(s.high, dtype='float32') for s in env.observation_space]),
+    }
+    names = getattr(env, 'observation_names', u.observation_names)
+    config = {'dataset': dataset, 'overrides': overrides or {}, 'wrapper': wrapper, 'seed': seed, 'observation_names': names,
+              'numpy': np.__version__}
+    arrays['config'] = np.frombuffer(json.dumps(config).encode(), dtype='uint8')
+    (OUT / 'wrappers').mkdir(parents=True, exist_ok=True)
+    np.savez_compressed(OUT / 'wrappers' / f'{name}.npz', **arrays)
+    print(name, {k: v.shape for k, v in arrays.items() if k != 'config'})
+
+
+WRAPPER_CASES = {
+    'w_normalized_space': dict(dataset='citylearn_challenge_2022_phase_1', wrapper='NormalizedSpaceWrapper', steps=60, seed=11),
+    'w_normalized_space_central': dict(dataset='citylearn_challenge_2022_phase_1', wrapper='NormalizedSpaceWrapper', overrides={'central_agent': True}, steps=40, seed=12),
+    'w_normalized_obs_2023': dict(dataset='citylearn_challenge_2023_phase_2_local_evaluation', wrapper='NormalizedObservationWrapper', steps=60, seed=13),
+    'w_clipped': dict(dataset='citylearn_challenge_2022_phase_1', wrapper='ClippedObservationWrapper', steps=40, seed=14),
+}
+
+
 def sparse(K):
     return sorted(set(list(range(0, 48)) + list(range(0, K, 41)) + list(range(K - 48, K))))
 
@@ -238,12 +294,17 @@ CASES = {
     'c6_tanks_2020_marl_central': dict(dataset=Z20, overrides={'central_agent': True}, reward=MARL, steps=150, seed=7),
     # cooling tank + cooling-device action on LSTM buildings (hidden 8, 11 inputs); Building_4's 1x50 LSTM is outside the kernel's shape
     'c6_baeda3': dict(dataset=BAEDA, overrides={'buildings': ['Building_1', 'Building_2', 'Building_3']}, steps=600, seed=8),
+    # 32-building slice of the synthetic wide district (C4): pins the per-building path of the 1024-building runs
+    'c4_slice32': dict(dataset='synthetic_wide_32', steps=200, seed=10),
     # 6 LSTM buildings with stochastic outages, central agent, full 2207-step episode
     'c7_phase3': dict(dataset=C23P3, steps=None, record=sparse, seed=9),
 }
 
 if __name__ == '__main__':
     CityLearnEnv = import_reference()
-    todo = sys.argv[1:] or list(CASES)
+    todo = sys.argv[1:] or (list(CASES) + list(WRAPPER_CASES))
     for n in todo:
-        run_case(CityLearnEnv, n, **CASES[n])
+        if n in WRAPPER_CASES:
+            run_wrapper_case(CityLearnEnv, n, **WRAPPER_CASES[n])
+        else:
+            run_case(CityLearnEnv, n, **CASES[n])

@@ -42,7 +42,11 @@ def load_golden(name):
 
 def schema_for(cfg):
     """(schema dict, data source, overrides) reproducing the fixture's environment from the bundled packs."""
-    src = DataSet.get_source(cfg['dataset'])
+    if cfg['dataset'].startswith('synthetic_wide_'):
+        from citylearn_b200.synthetic import SyntheticWideSource
+        src = SyntheticWideSource(int(cfg['dataset'].rsplit('_', 1)[1]))
+    else:
+        src = DataSet.get_source(cfg['dataset'])
     sch = src.schema()
     if cfg.get('reward') is not None:
         sch['reward_function'] = {'type': cfg['reward']['type'], 'attributes': cfg['reward'].get('attributes', {})}

@@ -18,7 +18,8 @@ pytestmark = pytest.mark.gpu
 
 NON_LSTM_CASES = ['c1_phase1_300', 'c1_phase1_central', 'c1_episodes', 'c1_subhour', 'c2_marl', 'c2_isac', 'c2_solar_penalty', 'c2_central_exp2', 'c2_year',
                   # 2020 schema: autosized heat pumps / heaters / tanks, cooling + DHW tank actions
-                  'c6_tanks_2020', 'c6_tanks_2020_marl_central']
+                  'c6_tanks_2020', 'c6_tanks_2020_marl_central',
+                  'c4_slice32']      # first 32 buildings of the synthetic wide district (BASELINE configs[3])
 # 2023 schema: heat pump + electric heater + DHW tank + battery + outages + LSTM indoor-temperature dynamics (BASELINE configs[2])
 LSTM_CASES = ['c3_marl', 'c3_default_central_comfort', 'c3_solar_comfort',
               'c6_baeda3',      # cooling tank + cooling-device action, LSTM hidden 8 / 11 inputs
@@ -61,7 +62,9 @@ def test_single_env_matches_reference_traces(case):
                 flat = np.array([v for row in obs for v in row], dtype='float32')
                 assert max_abs_diff(flat, z['obs'][gi]) == 0.0, f'obs step {k}'
                 r = np.array(rew, dtype='float32')
-                ok, w = within_scaled_tolerance(r, z['reward'][gi], 1.0, rtol=1e-5 if lstm else 2e-7)
+                # float32 rewards: 1 ulp per building; a central agent sums them (MARL terms of both signs cancel), so the sum gets the
+                # north-star tolerance of 1e-5
+                ok, w = within_scaled_tolerance(r, z['reward'][gi], 1.0, rtol=1e-5 if (lstm or env.central_agent) else 2e-7)
                 assert ok, f'reward step {k}: {w}'
                 assert max_abs_diff(env.district[0].cpu().numpy(), z['district'][gi]) == 0.0, f'district step {k}'
                 tr = env.trace[0].cpu().numpy()
@@ -350,3 +353,104 @@ def test_back_to_back_host_actions_do_not_race():
                 torch.cuda.synchronize()
         sums.append(total.cpu().numpy())
     assert np.array_equal(sums[0], sums[1])
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# wide districts (BASELINE.json configs[3]: synthetic 1024-building schema): one thread-block cluster per env, buildings tiled
+# over its CTAs, district sums through distributed shared memory
+# ----------------------------------------------------------------------------------------------------------------------
+_WIDE = {}
+
+
+def wide_spec(n, **overrides):
+    from citylearn_b200.synthetic import make_wide_district
+    key = (n, tuple(sorted(overrides.items())))
+    if key not in _WIDE:
+        sch, src = make_wide_district(n)
+        _WIDE[key] = S.load(sch, data_source=src, **overrides)
+    return _WIDE[key]
+
+
+@pytest.mark.parametrize('n_buildings', [1024, 700])
+def test_wide_district_matches_oracle(n_buildings):
+    """Per-building physics, rewards and observations are bit-exact (they do not depend on the tiling); the district sums are
+    float32 sums in a different association than the reference's left-to-right sum(): 1e-5 of the district scale."""
+    from citylearn_b200 import CityLearnEnv
+    from citylearn_oracle import OracleEnv
+    E, K = 3, 30
+    spec = wide_spec(n_buildings)
+    env = CityLearnEnv(spec, num_envs=E, debug_trace=True)
+    assert env._h.tiles > 1
+    oracle = OracleEnv(spec, E)
+    obs0 = oracle.reset()
+    o, _ = env.reset()
+    assert max_abs_diff(o.cpu().numpy(), obs0.astype('float32')) == 0.0
+    rng = np.random.RandomState(21)
+    for k in range(K):
+        a = rng.uniform(-1, 1, size=(E, spec.action_dim)).astype('float32')
+        obs, rew, term, _, _ = env.step(torch.from_numpy(a).cuda())
+        oobs, orew, odist, odyn = oracle.step(a)
+        assert max_abs_diff(obs.cpu().numpy(), oobs) == 0.0
+        assert np.array_equal(rew.cpu().numpy(), orew)
+        tr = env.trace.cpu().numpy()
+        for n in ('electrical_storage_soc', 'electrical_storage_energy_balance', 'net_electricity_consumption',
+                  'net_electricity_consumption_cost', 'net_electricity_consumption_emission'):
+            assert np.array_equal(tr[..., DYN[n]], odyn[..., DYN[n]].astype('float32')), (n, k)
+        # district sums vs a float64 sum of the exact per-building values
+        exact = np.stack([odyn[..., DYN[n]].astype('float32').astype('float64').sum(axis=1) for n in
+                          ('net_electricity_consumption', 'net_electricity_consumption_cost', 'net_electricity_consumption_emission')], axis=1)
+        scale = np.stack([np.abs(odyn[..., DYN[n]]).sum(axis=1) for n in
+                          ('net_electricity_consumption', 'net_electricity_consumption_cost', 'net_electricity_consumption_emission')], axis=1)
+        ok, w = within_scaled_tolerance(env.district.cpu().numpy(), exact, np.maximum(scale, 1.0), rtol=1e-5)
+        assert ok, ('district', k, w)
+
+
+def test_wide_district_rollout_marl_central_and_fresh_observations():
+    """The cluster paths that exchange data between tiles: MARL (district sum feeds every reward), central agent (reward sum over
+    tiles), fresh observations (per-tile dynamic slab) and K-step rollouts (== K single steps)."""
+    from citylearn_b200 import CityLearnEnv
+    from citylearn_oracle import OracleEnv
+    E, K, N = 2, 12, 1024
+    marl = {'type': 'citylearn.reward_function.MARL', 'attributes': {}}
+    rng = np.random.RandomState(22)
+    acts = rng.uniform(-1, 1, size=(K, E, N)).astype('float32')
+    # MARL, decentralised, fresh observations
+    from citylearn_b200.synthetic import make_wide_district
+    sch, src = make_wide_district(N)
+    sch['reward_function'] = marl
+    spec = S.load(sch, data_source=src)
+    env = CityLearnEnv(spec, num_envs=E, stale_observations=False)
+    ref = OracleEnv(spec, E)
+    ref.reset()
+    env.reset()
+    steps_obs, steps_rew = [], []
+    for k in range(K):
+        obs, rew, _, _, _ = env.step(torch.from_numpy(acts[k]).cuda())
+        _, orew, odist, odyn = ref.step(acts[k])
+        ok, w = within_scaled_tolerance(rew.cpu().numpy(), orew, np.abs(orew).max(), rtol=1e-5)
+        assert ok, ('marl reward', k, w)
+        steps_obs.append(obs.cpu().numpy().copy()); steps_rew.append(rew.cpu().numpy().copy())
+        # fresh observations carry this step's net consumption of every building
+        names = [n for _, n in env._entries]
+        idx = [i for i, n in enumerate(names) if n == 'net_electricity_consumption']
+        assert len(idx) == N
+        assert np.array_equal(steps_obs[-1][:, idx], odyn[..., DYN['net_electricity_consumption']].astype('float32'))
+    env.reset()
+    ro = torch.zeros((K, E, env._obs_dim), device='cuda')
+    rr = torch.zeros((K, E, N), device='cuda')
+    rd = torch.zeros((K, E, 3), device='cuda')
+    env.rollout(torch.from_numpy(acts).cuda(), ro, rr, rd)
+    assert np.array_equal(ro.cpu().numpy(), np.stack(steps_obs))
+    assert np.array_equal(rr.cpu().numpy(), np.stack(steps_rew))
+    # central agent, default reward: one reward per env = sum over all tiles
+    sch2, src2 = make_wide_district(N)
+    spec_c = S.load(sch2, data_source=src2, central_agent=True)
+    envc = CityLearnEnv(spec_c, num_envs=E)
+    refc = OracleEnv(spec_c, E)
+    refc.reset(); envc.reset()
+    for k in range(4):
+        obs, rew, _, _, _ = envc.step(torch.from_numpy(acts[k]).cuda())
+        oobs, orew, _, _ = refc.step(acts[k])
+        assert max_abs_diff(obs.cpu().numpy(), oobs) == 0.0
+        ok, w = within_scaled_tolerance(rew.cpu().numpy(), orew, 1.0, rtol=1e-5)
+        assert ok, ('central reward', k, w)
