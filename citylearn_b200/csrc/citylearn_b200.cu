@@ -38,11 +38,21 @@ struct Dev {
     // building tiles: a district wider than one block is split into `tiles` tiles of `tile_b` buildings, one CTA per tile,
     // the CTAs of an env forming a thread-block cluster (tiles == 1: tile_b == B, Lt == L, no cluster)
     int tiles, tile_b, Lt;
+    int coupled;           // wide districts, set per launch: 1 = a reward needs cross-tile sums in-step (cluster + DSMEM path);
+                           // 0 = tiles are independent, per-tile partial district sums go to a scratch buffer (district_finish_kernel)
+    int tab_layout;        // 1: observation rows come from obs_tab (no gather-column staging in shared memory)
     const int32_t* tile_k; // [tiles + 1] observation-row range of every tile (wide districts only)
     // optional wrapper semantics fused into the observation writers / action fetch (cl_set_transforms; nullptr: identity)
     const cl_obs_transform* obs_t;   // [L]
     const float* act_range;          // [A] normalised action a in [0, 1] -> a * range + low (wrappers.py:208-222)
     const float* act_low;            // [A]
+    // reference-parity observation rows do not depend on the env or the actions: row r of `obs_tab` is the complete (transformed)
+    // observation of the time step whose table row is r, built once (build_obs_table_kernel).  The helper warp then only moves
+    // it: TMA load of the block's column range -> shared memory -> TMA stores into the envs' rows.
+    const float* obs_tab;            // [n_rows][obs_pitch] or nullptr (gather path)
+    int obs_pitch;                   // floats per row (L rounded up to 4)
+    int n_out_cols;                  // observation columns that carry an outage signal (patched per step: they change per episode)
+    const int32_t* out_cols;         // [n_out_cols] column index k
     float rp[8];
     const float* table;
     const float* pf;       // [NPARAM][B]
@@ -183,11 +193,19 @@ __device__ __forceinline__ void fetch_actions(const Dev& d, const UnitCtx<R>& c,
 
 // observation transform of column k (cl_obs_transform): periodic sin / cos, affine min-max, clip - NaN passes through
 __device__ __forceinline__ float transform_obs(const cl_obs_transform* t, int k, float v) {
-    const cl_obs_transform x = t[k];
-    if (x.fn == CL_OBS_FN_SIN) v = sinf(v * x.w);
-    else if (x.fn == CL_OBS_FN_COS) v = cosf(v * x.w);
-    v = v * x.scale + x.offset;
-    return v < x.lo ? x.lo : (v > x.hi ? x.hi : v);
+    const cl_obs_transform* x = t + k;
+    const int fn = __ldg(&x->fn);
+    if (fn != CL_OBS_FN_IDENTITY) {
+        // periodic observations are 1 .. x_max, i.e. the angle is in (0, 2 pi]: fold it into (-pi, pi] and use the hardware
+        // approximations (absolute error < 5e-7 there) - the library sinf / cosf would drag their slow-path local array and a
+        // lower register budget into every instantiation of the step kernel
+        float a = v * __ldg(&x->w);
+        if (a > 3.14159265358979f) a -= 6.28318530717959f;
+        v = fn == CL_OBS_FN_SIN ? __sinf(a) : __cosf(a);
+    }
+    v = v * __ldg(&x->scale) + __ldg(&x->offset);
+    const float lo = __ldg(&x->lo), hi = __ldg(&x->hi);
+    return v < lo ? lo : (v > hi ? hi : v);
 }
 
 // inactive storage actions are 0, inactive device actions NaN (building.py:1555-1564)
@@ -396,14 +414,14 @@ __device__ __forceinline__ void write_obs_general(const Dev& d, float* obs, int 
 struct SmemLayout {
     int curves, bsolar, rows, tcol, tmpl, red, rsum, dsum, wpart, rpart, lstm, dynbuf, Lp;
 };
-__host__ __device__ __forceinline__ SmemLayout smem_layout(int B, int Wp, int L, int epb, int nt, int rsize, int lstm_smem = 0) {
+__host__ __device__ __forceinline__ SmemLayout smem_layout(int B, int Wp, int L, int epb, int nt, int rsize, int lstm_smem = 0, int tab_layout = 0) {
     SmemLayout o;
     o.Lp = (L + 3) & ~3;
-    int f = 8;                                   // 32 bytes of mbarriers
+    int f = 16;                                  // 64 bytes of mbarriers: 3 time-row slots + 2 observation-row buffers
     o.curves = f; f += B * 32 * (rsize / 4);     // first: keeps doubles 8-byte aligned
     o.bsolar = f; f += ((2 * B * (rsize / 4)) + 3) & ~3;
     o.rows = f; f += 3 * Wp;
-    o.tcol = f; f += o.Lp;
+    o.tcol = f; f += tab_layout ? 0 : o.Lp;      // gather columns: not needed when the rows come from the observation table
     o.tmpl = f; f += 2 * o.Lp;                   // observation row of the step, source of the TMA bulk stores (double-buffered)
     o.red = f; f += 6 * nt;
     o.rsum = f; f += nt;
@@ -415,7 +433,7 @@ __host__ __device__ __forceinline__ SmemLayout smem_layout(int B, int Wp, int L,
     return o;
 }
 static size_t smem_bytes(const Dev& d, int nt, bool with_dyn, int rsize) {
-    const SmemLayout o = smem_layout(d.tile_b, d.Wp, d.Lt, d.envs_per_block, nt, rsize, d.lstm_smem);
+    const SmemLayout o = smem_layout(d.tile_b, d.Wp, d.Lt, d.envs_per_block, nt, rsize, d.lstm_smem, d.tab_layout);
     size_t n = sizeof(float) * (size_t)o.dynbuf;
     if (with_dyn) n += sizeof(float) * (size_t)nt * CL_NDYN;
     return n;
@@ -520,13 +538,13 @@ __global__ void __launch_bounds__(MAXT) advance_kernel(Dev d, int t0, int K, con
     // wide districts: CTA `rank` of the cluster owns buildings [b0, b0 + nb) of the cluster's env(s) and columns [k0, k1) of
     // their observation rows; otherwise the block owns whole envs (b0 = 0, nb = B, [k0, k1) = [0, L))
     const int NT = WIDE ? d.tiles : 1;
-    const int rank = WIDE ? (int)cluster_ctarank() : 0;
+    const int rank = WIDE ? (int)blockIdx.x % NT : 0;   // == %cluster_ctarank of the 1-D cluster when launched as one
     const int TBs = WIDE ? d.tile_b : B;            // smem stride of per-building arrays
     const int b0 = rank * TBs;
     const int nb = WIDE ? min(TBs, B - b0) : B;
     const int k0 = WIDE ? __ldg(d.tile_k + rank) : 0, k1 = WIDE ? __ldg(d.tile_k + rank + 1) : d.L;
     const int Ltile = k1 - k0;
-    const SmemLayout lo = smem_layout(TBs, Wp, WIDE ? d.Lt : d.L, epb, nt, (int)sizeof(R), DYNAMICS ? d.lstm_smem : 0);
+    const SmemLayout lo = smem_layout(TBs, Wp, WIDE ? d.Lt : d.L, epb, nt, (int)sizeof(R), DYNAMICS ? d.lstm_smem : 0, d.tab_layout);
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(smf);
     R* scurves = reinterpret_cast<R*>(smf + lo.curves);
     R* s_bsolar = reinterpret_cast<R*>(smf + lo.bsolar);          // [2][B] PV generation of the step, per building
@@ -557,8 +575,10 @@ __global__ void __launch_bounds__(MAXT) advance_kernel(Dev d, int t0, int K, con
     const int Rdim = d.central ? 1 : B;
     const uint32_t row_bytes = (uint32_t)Wp * sizeof(float);
 
+    const bool tab_path = tmpl_path && d.obs_tab != nullptr;      // the host only sets obs_tab when every tile range is 16-byte aligned
+    const bool coupled = WIDE && d.coupled;                        // cross-tile sums needed inside the step
     if (uniform && tid == 0) {
-        for (int i = 0; i < 3; ++i) mbar_init(s_bar + i, 1);
+        for (int i = 0; i < 5; ++i) mbar_init(s_bar + i, 1);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         for (int i = 0; i < 3 && i <= K; ++i) {     // rows t0 .. t0+2 (row t0+K is the last one any step needs)
             mbar_expect_tx(s_bar + i, row_bytes);
@@ -566,7 +586,7 @@ __global__ void __launch_bounds__(MAXT) advance_kernel(Dev d, int t0, int K, con
         }
     }
     // block-wide staging: template columns and the battery curves of every building (dynamic indexing -> shared memory)
-    if (tmpl_path) for (int k = tid; k < Ltile; k += nt) s_tcol[k] = __ldg(d.tcol + k0 + k);
+    if (tmpl_path && !tab_path) for (int k = tid; k < Ltile; k += nt) s_tcol[k] = __ldg(d.tcol + k0 + k);
     {
         const auto* P = PSel<R>::p(d) + CL_P_PE_X0 * B;
         for (int i = tid; i < nb * 32; i += nt) { const int bb = b0 + (i >> 5), j = i & 31; scurves[i] = (R)__ldg(P + j * B + bb); }
@@ -638,10 +658,48 @@ __global__ void __launch_bounds__(MAXT) advance_kernel(Dev d, int t0, int K, con
         if (is_helper) {
             // ---------------- helper warp ----------------
             if (uniform && k + 1 < K) building_inputs(row_next, s_bsolar + ((k + 1) & 1) * TBs);
-            if (WIDE) cluster_sync_all(); else __syncthreads();                // S1
+            if (coupled) cluster_sync_all(); else __syncthreads();             // S1
             if (need_dsum) __syncthreads();                                    // S2
             if (central_sync) { if (WIDE) cluster_sync_all(); else { if (k > 0) __syncthreads(); __syncthreads(); } }
-            if (tmpl_path) {
+            if (tab_path) {
+                // observation slab of step k straight from the precomputed table: buffer pb holds columns [k0, k1) of table row
+                // start0 + t + 1 (requested one step ago); patch the outage columns, bulk-store it into every env row of the
+                // block, then request the row of step k + 1 into the other buffer once its previous stores have read it
+                float* ok = obs + (size_t)k * d.E * d.L + (size_t)e0 * d.L + k0;
+                float* tmpl = smf + lo.tmpl + pb * lo.Lp;
+                const uint32_t bytes = (uint32_t)Ltile * sizeof(float);
+                if (k == 0) {
+                    if (lane == 0) {
+                        mbar_expect_tx(s_bar + 3, bytes);
+                        tma_load_1d(tmpl, d.obs_tab + (size_t)(d.start0 + t + 1) * d.obs_pitch + k0, bytes, s_bar + 3);
+                    }
+                    __syncwarp();
+                }
+                mbar_wait(s_bar + 3 + pb, (uint32_t)((k >> 1) & 1));
+                if (d.has_outage && d.n_out_cols > 0) {
+                    for (int i = lane; i < d.n_out_cols; i += 32) {
+                        const int kk = __ldg(d.out_cols + i);
+                        if (kk >= k0 && kk < k1) {
+                            const int bb = __ldg(d.desc + kk).w;
+                            float v = __ldg(d.outage + bb * d.T + t + 1);
+                            if (d.obs_t) v = transform_obs(d.obs_t, kk, v);
+                            tmpl[kk - k0] = v;
+                        }
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                }
+                if (lane == 0) {
+                    for (int le = 0; le < n_env; ++le) tma_store_1d(ok + (size_t)le * d.L, tmpl, bytes);
+                    tma_store_commit();
+                    if (k + 1 < K) {
+                        tma_store_wait_read<1>();                               // the stores of step k - 1 have read the other buffer
+                        mbar_expect_tx(s_bar + 3 + (pb ^ 1), bytes);
+                        tma_load_1d(smf + lo.tmpl + (pb ^ 1) * lo.Lp, d.obs_tab + (size_t)(d.start0 + t + 2) * d.obs_pitch + k0, bytes, s_bar + 3 + (pb ^ 1));
+                    }
+                }
+                __syncwarp();
+            } else if (tmpl_path) {
                 // observation slab of step k: every env row of the block equals the row gathered from time row t+1
                 float* ok = obs + (size_t)k * d.E * d.L + (size_t)e0 * d.L + k0;
                 const int L = d.L;
@@ -736,7 +794,7 @@ __global__ void __launch_bounds__(MAXT) advance_kernel(Dev d, int t0, int K, con
                 const int w = tid >> 5;
                 s_wpart[(pb * 3 + 0) * 32 + w] = vn; s_wpart[(pb * 3 + 1) * 32 + w] = vc; s_wpart[(pb * 3 + 2) * 32 + w] = ve;
             }
-            cluster_sync_all();                                                // S1 for the whole cluster
+            if (coupled) cluster_sync_all(); else __syncthreads();             // S1 (for the whole cluster when tiles exchange sums)
         } else {
             __syncthreads();                                                   // S1: red / dynbuf / next-step building inputs complete
         }
@@ -750,18 +808,37 @@ __global__ void __launch_bounds__(MAXT) advance_kernel(Dev d, int t0, int K, con
         // district sums in building order, like the reference's sum() over buildings (citylearn.py:1908-1918);
         // one thread per (quantity, env)
         if (WIDE) {
-            // district sums = partial sums of every tile, in (tile, warp) order - the same order in every CTA of the cluster
-            // (float32 like the reference, but a different association than its left-to-right sum(): DESIGN.md 'Wide districts')
-            if (tid < 3 && (tid == 0 || district != nullptr)) {
-                const int q = tid, nw = np_ >> 5;
-                const uint32_t local = smem_u32(s_wpart + (pb * 3 + q) * 32);
-                float acc = 0.f;
-                for (int r = 0; r < NT; ++r) {
-                    const uint32_t ra = cluster_map(local, (uint32_t)r);
-                    for (int w = 0; w < nw; ++w) acc += ld_cluster_f32(ra + 4u * (uint32_t)w);
+            const int nw = np_ >> 5;
+            if (coupled) {
+                // district sums = partial sums of every (tile, warp) of the cluster, read through distributed shared memory by
+                // warp 0 of every CTA: one slot per lane, then a fixed-order shuffle tree (float32 like the reference, but a
+                // different association than its left-to-right sum(): DESIGN.md 'Wide districts')
+                if (tid < 32) {
+                    const int total = NT * nw;
+#pragma unroll 1
+                    for (int q = 0; q < 3; ++q) {
+                        if (q > 0 && district == nullptr) break;
+                        const uint32_t local = smem_u32(s_wpart + (pb * 3 + q) * 32);
+                        float acc = 0.f;
+                        for (int idx = lane; idx < total; idx += 32) {
+                            const int r = idx / nw, w = idx - r * nw;
+                            acc += ld_cluster_f32(cluster_map(local, (uint32_t)r) + 4u * (uint32_t)w);
+                        }
+#pragma unroll
+                        for (int m = 16; m > 0; m >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, m);
+                        if (lane == 0) {
+                            if (q == 0) s_dsum[pb * epb] = acc;
+                            if (district != nullptr && rank == 0) district[((size_t)k * d.E + e0) * 3 + q] = acc;
+                        }
+                    }
                 }
-                if (q == 0) s_dsum[pb * epb] = acc;
-                if (district != nullptr && rank == 0) district[((size_t)k * d.E + e0) * 3 + q] = acc;
+            } else if (district != nullptr && tid < 3) {
+                // independent tiles: this tile's partial sums go to the scratch buffer [K][E][tiles][3]; district_finish_kernel
+                // adds the tiles up in order after the launch
+                const float* src = s_wpart + (pb * 3 + tid) * 32;
+                float acc = 0.f;
+                for (int w = 0; w < nw; ++w) acc += src[w];
+                district[(((size_t)k * d.E + e0) * NT + rank) * 3 + tid] = acc;
             }
         } else
         for (int idx = tid; idx < 3 * n_env; idx += np_) {
@@ -828,7 +905,34 @@ __global__ void __launch_bounds__(MAXT) advance_kernel(Dev d, int t0, int K, con
 #endif
     if (is_helper) tma_store_wait_all<0>();
     if (active && !is_helper) store_state<R, THERMAL>(d, u, s);
-    if (WIDE) cluster_sync_all();     // nobody exits while a peer may still read its partial sums
+    if (coupled) cluster_sync_all();  // nobody exits while a peer may still read its partial sums
+}
+
+// district sums of independent tiles: district[n][q] = sum over tiles (in order) of part[n][tile][q], n = (step, env)
+__global__ void district_finish_kernel(const float* __restrict__ part, float* __restrict__ district, long n3, int tiles) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n3) return;
+    const long n = i / 3; const int q = (int)(i - n * 3);
+    float acc = 0.f;
+    for (int r = 0; r < tiles; ++r) acc += part[(n * tiles + r) * 3 + q];
+    district[i] = acc;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// observation table: obs_tab[r][k] = transformed observation column k at the time step whose table row is r (stale DYN columns
+// and outage columns are 0 here; outage columns are patched per step)
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void build_obs_table_kernel(Dev d, float* __restrict__ out) {
+    for (int r = blockIdx.y; r < d.n_rows; r += gridDim.y)
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < d.obs_pitch; k += gridDim.x * blockDim.x) {
+        float v = 0.f;
+        if (k < d.L) {
+            const int cc = __ldg(d.tcol + k);
+            if (cc >= 0) v = __ldg(d.table + (size_t)r * d.Wp + cc);
+            if (d.obs_t) v = transform_obs(d.obs_t, k, v);
+        }
+        out[(size_t)r * d.obs_pitch + k] = v;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -839,7 +943,7 @@ __global__ void __launch_bounds__(MAXT) reset_kernel(Dev d, float* __restrict__ 
     extern __shared__ __align__(16) float smf[];
     const int nt = blockDim.x, tid = threadIdx.x;
     const int B = d.B, epb = d.envs_per_block;
-    const SmemLayout lo = smem_layout(d.tile_b, d.Wp, d.Lt, epb, nt, (int)sizeof(R));
+    const SmemLayout lo = smem_layout(d.tile_b, d.Wp, d.Lt, epb, nt, (int)sizeof(R), 0, d.tab_layout);
     float* s_dynbuf = smf + lo.dynbuf;
     // building tiles (wide districts): block (group, rank) owns buildings [b0, b0 + nb) and observation columns [k0, k1)
     const int rank = (int)blockIdx.x % d.tiles;
@@ -900,6 +1004,9 @@ struct cl_env {
     int t = -1;              // -1: not reset
     int T = 0;
     int threads = 0, blocks = 0;
+    float* obs_tab_dev = nullptr;   // precomputed observation table (build_obs_table)
+    float* dpart = nullptr;         // wide districts: per-tile partial district sums of one launch chunk
+    size_t dpart_floats = 0;
     bool wide = false;       // building-tiled district: cluster launch of advance_kernel<..., WIDE = true>
     int64_t launches = 0;
     std::vector<void*> allocs;
@@ -917,6 +1024,40 @@ template <typename T> static int dev_copy(cl_env* env, const T* host, size_t n, 
     env->allocs.push_back(p);
     if (n) CUDA_TRY(cudaMemcpy(p, host, n * sizeof(T), cudaMemcpyHostToDevice));
     *out = static_cast<T*>(p);
+    return CL_OK;
+}
+
+// (Re)build the precomputed observation table of a reference-parity (stale-observation) district.  Skipped - the kernels then
+// gather the row every step - when it would exceed CL_B200_OBS_TABLE_MB (default 4096 MiB) or the observation row is not a
+// multiple of 16 bytes.
+static bool obs_table_fits(const Dev& d) {
+    if (!d.stale || (d.L & 3) != 0) return false;
+    long budget_mb = 4096;
+    if (const char* ev = std::getenv("CL_B200_OBS_TABLE_MB")) budget_mb = std::atol(ev);
+    return (size_t)d.n_rows * (size_t)((d.L + 3) & ~3) * sizeof(float) <= (size_t)budget_mb * 1024 * 1024;
+}
+static int build_obs_table(cl_env* env) {
+    Dev& d = env->d;
+    d.obs_tab = nullptr;
+    if (!d.tab_layout) return CL_OK;               // decided with the launch geometry (cl_create)
+    const int pitch = (d.L + 3) & ~3;
+    const size_t bytes = (size_t)d.n_rows * pitch * sizeof(float);
+    if (!env->obs_tab_dev) {
+        if (cudaMalloc(reinterpret_cast<void**>(&env->obs_tab_dev), bytes) != cudaSuccess) {
+            cudaGetLastError();
+            env->obs_tab_dev = nullptr;
+            return fail(CL_ERR_CUDA, "cl_create: not enough device memory for the observation table (lower CL_B200_OBS_TABLE_MB to use the gather path)");
+        }
+        env->allocs.push_back(env->obs_tab_dev);
+    }
+    d.obs_pitch = pitch;
+    const int threads = 256;
+    int bx = (pitch + threads - 1) / threads;
+    if (bx > 64) bx = 64;
+    build_obs_table_kernel<<<dim3((unsigned)bx, (unsigned)std::min(d.n_rows, 65535)), threads>>>(d, env->obs_tab_dev);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaDeviceSynchronize());
+    d.obs_tab = env->obs_tab_dev;
     return CL_OK;
 }
 
@@ -1022,6 +1163,12 @@ extern "C" int cl_create(const cl_district_desc* desc, cl_env** out) {
         if (!rc) rc = dev_copy(env, tcol.data(), tcol.size(), &tc);
         if (rc) { cl_destroy(env); return rc; }
         d.pf = p; d.pd = q; d.ip = ip; d.desc = ds; d.tcol = tc;
+        std::vector<int32_t> oc;
+        for (int k = 0; k < d.L; ++k) if (desc->obs_desc[4 * (size_t)k] == CL_OBS_OUTAGE) oc.push_back(k);
+        int32_t* ocd = nullptr;
+        rc = dev_copy(env, oc.data(), oc.size(), &ocd);
+        if (rc) { cl_destroy(env); return rc; }
+        d.out_cols = ocd; d.n_out_cols = (int)oc.size();
     }
     {
         void* p = nullptr;
@@ -1092,6 +1239,8 @@ extern "C" int cl_create(const cl_district_desc* desc, cl_env** out) {
     if (epb > d.E) epb = d.E;
     d.envs_per_block = epb;
     d.tiles = 1; d.tile_b = B; d.Lt = d.L; d.tile_k = nullptr;
+    const bool tab_fits = obs_table_fits(d);
+    d.tab_layout = tab_fits ? 1 : 0;
     env->threads = ((epb * B + 31) / 32) * 32;
     env->blocks = (d.E + epb - 1) / epb;
     // Wide districts: one env per thread-block CLUSTER, the buildings split into `tiles` tiles of `tile_b` (one CTA each); the
@@ -1134,7 +1283,10 @@ extern "C" int cl_create(const cl_district_desc* desc, cl_env** out) {
             int lt = 0;
             for (int r = 0; r < nt_; ++r) lt = std::max(lt, tk[r + 1] - tk[r]);
             const int thr = ((tb + 31) / 32) * 32 + 32;
+            bool aligned = true;
+            for (int r = 0; r <= nt_; ++r) aligned = aligned && (tk[r] & 3) == 0;
             Dev probe = d; probe.tiles = nt_; probe.tile_b = tb; probe.Lt = lt; probe.envs_per_block = 1;
+            probe.tab_layout = (tab_fits && aligned) ? 1 : 0;
             const size_t sm = smem_bytes(probe, thr, true, env->precision == CL_PRECISION_FP64 ? 8 : 4);
             if (sm > 200 * 1024) continue;
             const int regs_alloc = ((regs_w + 7) / 8) * 8;
@@ -1154,6 +1306,9 @@ extern "C" int cl_create(const cl_district_desc* desc, cl_env** out) {
             int32_t* tkd = nullptr;
             int rc = dev_copy(env, best_tk.data(), best_tk.size(), &tkd);
             if (rc) { cl_destroy(env); return rc; }
+            bool aligned = true;
+            for (int r = 0; r <= best_nt; ++r) aligned = aligned && (best_tk[r] & 3) == 0;
+            d.tab_layout = (tab_fits && aligned) ? 1 : 0;
             d.tiles = best_nt; d.tile_b = tb; d.Lt = lt; d.tile_k = tkd; d.envs_per_block = 1;
             env->wide = true;
             env->threads = ((tb + 31) / 32) * 32;
@@ -1162,7 +1317,7 @@ extern "C" int cl_create(const cl_district_desc* desc, cl_env** out) {
     }
     if (!env->wide && B > 992) { cl_destroy(env); return fail(CL_ERR_UNSUPPORTED, "cl_create: districts wider than 992 buildings with LSTM dynamics are not supported"); }
     // opt in to large dynamic shared memory once (both kernels, all instantiations)
-    const size_t smem = smem_bytes(d, env->threads + 32, true, 8);
+    const size_t smem = smem_bytes(d, env->threads + 32, true, env->precision == CL_PRECISION_FP64 ? 8 : 4);
     if (smem > 200 * 1024) { cl_destroy(env); return fail(CL_ERR_UNSUPPORTED, "cl_create: district too wide for the shared-memory staging"); }
 #define OPTIN(K) cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
 #define OPTIN4(K, M) OPTIN((K<float, false, M>)); OPTIN((K<float, true, M>)); OPTIN((K<double, false, M>)); OPTIN((K<double, true, M>))
@@ -1176,6 +1331,7 @@ extern "C" int cl_create(const cl_district_desc* desc, cl_env** out) {
 #undef OPTIN
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { cl_destroy(env); return fail(CL_ERR_CUDA, std::string("cl_create: ") + cudaGetErrorString(e)); }
+    { const int rc = build_obs_table(env); if (rc) { cl_destroy(env); return rc; } }
     *out = env;
     return CL_OK;
 }
@@ -1184,6 +1340,7 @@ extern "C" int cl_destroy(cl_env* env) {
     if (!env) return CL_OK;
     for (void* p : env->allocs) cudaFree(p);
     if (env->outage_dev) cudaFree(env->outage_dev);
+    if (env->dpart) cudaFree(env->dpart);
     delete env;
     return CL_OK;
 }
@@ -1214,37 +1371,73 @@ static void launch_reset(cl_env* env, float* obs, cudaStream_t st) {
     else reset_kernel<R, TH, 1024><<<env->blocks, env->threads, smem, st>>>(env->d, obs);
 }
 template <typename R, bool TH, bool DY>
-static void launch_advance(cl_env* env, int K, const float* actions, float* obs, float* reward, float* district, float* trace, cudaStream_t st) {
+static void launch_advance(cl_env* env, int t0, int K, const float* actions, float* obs, float* reward, float* district, float* trace,
+                           bool coupled, cudaStream_t st) {
     const bool want_dyn = !env->d.stale && obs != nullptr;
     const int nthreads = env->threads + 32;          // + the helper warp
     const size_t smem = smem_bytes(env->d, nthreads, want_dyn, (int)sizeof(R));
     if (env->wide) {
-        // one thread-block cluster per env: `tiles` CTAs, one per building tile
         if constexpr (!DY) {
-            cudaLaunchConfig_t cfg = {};
-            cfg.gridDim = dim3((unsigned)env->blocks); cfg.blockDim = dim3((unsigned)nthreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-            cudaLaunchAttribute at[1];
-            at[0].id = cudaLaunchAttributeClusterDimension;
-            at[0].val.clusterDim.x = (unsigned)env->d.tiles; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-            cfg.attrs = at; cfg.numAttrs = 1;
-            cudaLaunchKernelEx(&cfg, advance_kernel<R, TH, false, 512, true>, env->d, env->t, K, actions, obs, reward, district, trace);
+            Dev dd = env->d;
+            dd.coupled = coupled ? 1 : 0;
+            if (coupled) {
+                // tiles exchange sums inside the step: one thread-block cluster per env, one CTA per building tile
+                cudaLaunchConfig_t cfg = {};
+                cfg.gridDim = dim3((unsigned)env->blocks); cfg.blockDim = dim3((unsigned)nthreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+                cudaLaunchAttribute at[1];
+                at[0].id = cudaLaunchAttributeClusterDimension;
+                at[0].val.clusterDim.x = (unsigned)env->d.tiles; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+                cfg.attrs = at; cfg.numAttrs = 1;
+                cudaLaunchKernelEx(&cfg, advance_kernel<R, TH, false, 512, true>, dd, t0, K, actions, obs, reward, district, trace);
+            } else {
+                advance_kernel<R, TH, false, 512, true><<<env->blocks, nthreads, smem, st>>>(dd, t0, K, actions, obs, reward, district, trace);
+            }
         }
         return;
     }
-    if (nthreads <= 512) advance_kernel<R, TH, DY, 512><<<env->blocks, nthreads, smem, st>>>(env->d, env->t, K, actions, obs, reward, district, trace);
-    else advance_kernel<R, TH, DY, 1024><<<env->blocks, nthreads, smem, st>>>(env->d, env->t, K, actions, obs, reward, district, trace);
+    if (nthreads <= 512) advance_kernel<R, TH, DY, 512><<<env->blocks, nthreads, smem, st>>>(env->d, t0, K, actions, obs, reward, district, trace);
+    else advance_kernel<R, TH, DY, 1024><<<env->blocks, nthreads, smem, st>>>(env->d, t0, K, actions, obs, reward, district, trace);
 }
-static void dispatch_advance(cl_env* env, int K, const float* actions, float* obs, float* reward, float* district, float* trace, cudaStream_t st) {
+static void dispatch_one(cl_env* env, int t0, int K, const float* actions, float* obs, float* reward, float* district, float* trace,
+                         bool coupled, cudaStream_t st) {
     if (env->precision == CL_PRECISION_FP64) {
-        if (env->dynamics) launch_advance<double, true, true>(env, K, actions, obs, reward, district, trace, st);
-        else if (env->thermal) launch_advance<double, true, false>(env, K, actions, obs, reward, district, trace, st);
-        else launch_advance<double, false, false>(env, K, actions, obs, reward, district, trace, st);
+        if (env->dynamics) launch_advance<double, true, true>(env, t0, K, actions, obs, reward, district, trace, coupled, st);
+        else if (env->thermal) launch_advance<double, true, false>(env, t0, K, actions, obs, reward, district, trace, coupled, st);
+        else launch_advance<double, false, false>(env, t0, K, actions, obs, reward, district, trace, coupled, st);
     } else {
-        if (env->dynamics) launch_advance<float, true, true>(env, K, actions, obs, reward, district, trace, st);
-        else if (env->thermal) launch_advance<float, true, false>(env, K, actions, obs, reward, district, trace, st);
-        else launch_advance<float, false, false>(env, K, actions, obs, reward, district, trace, st);
+        if (env->dynamics) launch_advance<float, true, true>(env, t0, K, actions, obs, reward, district, trace, coupled, st);
+        else if (env->thermal) launch_advance<float, true, false>(env, t0, K, actions, obs, reward, district, trace, coupled, st);
+        else launch_advance<float, false, false>(env, t0, K, actions, obs, reward, district, trace, coupled, st);
     }
     env->launches++;
+}
+static int dispatch_advance(cl_env* env, int K, const float* actions, float* obs, float* reward, float* district, float* trace, cudaStream_t st) {
+    const Dev& d = env->d;
+    // same predicate as the kernel's need_dsum || central_sync
+    const bool coupled = env->wide && reward != nullptr && (d.reward_id == CL_REWARD_MARL || (d.central && d.reward_id >= 0));
+    if (!env->wide || coupled || district == nullptr) {
+        dispatch_one(env, env->t, K, actions, obs, reward, district, trace, coupled, st);
+        return CL_OK;
+    }
+    // wide district with independent tiles: the kernel leaves per-tile partial district sums in a scratch buffer, a second small
+    // kernel adds the tiles up.  Long rollouts run in chunks so that the scratch stays small ([chunk][E][tiles][3] floats).
+    const int chunk = 64;
+    const size_t need = (size_t)std::min(K, chunk) * d.E * d.tiles * 3;
+    if (env->dpart_floats < need) {
+        if (env->dpart) { CUDA_TRY(cudaStreamSynchronize(st)); cudaFree(env->dpart); env->dpart = nullptr; env->dpart_floats = 0; }
+        CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&env->dpart), need * sizeof(float)));
+        env->dpart_floats = need;
+    }
+    const int Rdim = d.central ? 1 : d.B;
+    for (int off = 0; off < K; off += chunk) {
+        const int kc = std::min(chunk, K - off);
+        dispatch_one(env, env->t + off, kc, actions + (size_t)off * d.E * d.A, obs ? obs + (size_t)off * d.E * d.L : nullptr,
+                     reward ? reward + (size_t)off * d.E * Rdim : nullptr, env->dpart, trace, false, st);
+        const long n3 = (long)kc * d.E * 3;
+        district_finish_kernel<<<(unsigned)((n3 + 255) / 256), 256, 0, st>>>(env->dpart, district + (size_t)off * d.E * 3, n3, d.tiles);
+        env->launches++;
+    }
+    return CL_OK;
 }
 
 __global__ void fill_start_kernel(int32_t* start, int n, int v) {
@@ -1282,7 +1475,7 @@ extern "C" int cl_step(cl_env* env, const float* actions, float* obs, float* rew
     if (!env || !actions) return fail(CL_ERR_INVALID, "cl_step: null argument");
     if (env->t < 0) return fail(CL_ERR_STATE, "cl_step: call cl_reset first");
     if (env->t >= env->T - 1) return fail(CL_ERR_STATE, "cl_step: episode has ended (terminated); call cl_reset");
-    dispatch_advance(env, 1, actions, obs, reward, district, trace, static_cast<cudaStream_t>(stream));
+    { const int rc = dispatch_advance(env, 1, actions, obs, reward, district, trace, static_cast<cudaStream_t>(stream)); if (rc) return rc; }
     CUDA_TRY(cudaGetLastError());
     env->t += 1;
     return CL_OK;
@@ -1294,9 +1487,9 @@ extern "C" int cl_rollout(cl_env* env, int32_t n_steps, const float* actions, fl
     if (env->t < 0) return fail(CL_ERR_STATE, "cl_rollout: call cl_reset first");
     if (env->t + n_steps > env->T - 1) return fail(CL_ERR_STATE, "cl_rollout: block runs past the end of the episode");
 #ifdef CL_PHASE_TIMING
-    dispatch_advance(env, n_steps, actions, obs, reward, nullptr, district, static_cast<cudaStream_t>(stream));   // `district` receives the stamps
+    { const int rc = dispatch_advance(env, n_steps, actions, obs, reward, nullptr, district, static_cast<cudaStream_t>(stream)); if (rc) return rc; }   // `district` receives the stamps
 #else
-    dispatch_advance(env, n_steps, actions, obs, reward, district, nullptr, static_cast<cudaStream_t>(stream));
+    { const int rc = dispatch_advance(env, n_steps, actions, obs, reward, district, nullptr, static_cast<cudaStream_t>(stream)); if (rc) return rc; }
 #endif
     CUDA_TRY(cudaGetLastError());
     env->t += n_steps;
@@ -1368,7 +1561,7 @@ extern "C" int cl_set_transforms(cl_env* env, const cl_obs_transform* obs_transf
         if (rc) return rc;
         d.act_range = r; d.act_low = l;
     }
-    return CL_OK;
+    return build_obs_table(env);      // the table holds transformed values
 }
 
 extern "C" int cl_launch_geometry(const cl_env* env, int32_t* blocks, int32_t* threads, int32_t* tiles) {
