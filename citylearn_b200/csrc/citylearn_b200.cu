@@ -1319,7 +1319,10 @@ extern "C" int cl_create(const cl_district_desc* desc, cl_env** out) {
     // opt in to large dynamic shared memory once (both kernels, all instantiations)
     const size_t smem = smem_bytes(d, env->threads + 32, true, env->precision == CL_PRECISION_FP64 ? 8 : 4);
     if (smem > 200 * 1024) { cl_destroy(env); return fail(CL_ERR_UNSUPPORTED, "cl_create: district too wide for the shared-memory staging"); }
-#define OPTIN(K) cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+    // the attribute is per function and process-wide: never lower it below what an earlier handle needs
+    static size_t optin_max = 0;
+    if (smem > optin_max) optin_max = smem;
+#define OPTIN(K) cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)optin_max)
 #define OPTIN4(K, M) OPTIN((K<float, false, M>)); OPTIN((K<float, true, M>)); OPTIN((K<double, false, M>)); OPTIN((K<double, true, M>))
 #define OPTINA(M) OPTIN((advance_kernel<float, false, false, M>)); OPTIN((advance_kernel<float, true, false, M>)); OPTIN((advance_kernel<float, true, true, M>)); \
     OPTIN((advance_kernel<double, false, false, M>)); OPTIN((advance_kernel<double, true, false, M>)); OPTIN((advance_kernel<double, true, true, M>))
