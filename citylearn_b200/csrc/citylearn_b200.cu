@@ -469,6 +469,8 @@ __device__ __forceinline__ float lstm_update(const Dev& d, const UnitCtx<R>& c, 
                                              float obs_cool_dem, float t_in_dataset) {
     const int U = d.U;
     const int L = c.dyn_lookback, ring = L + 1;
+    const bool smem_w = d.lstm_smem != 0;                 // W then points into shared memory
+    const uint32_t ws = smem_w ? smem_u32(W) : 0u;
     float* lst = d.lst;
     float* win_c = lst + (size_t)(4 * kLstmH) * U + u;                     // [ring][U]
     float* win_t = lst + (size_t)(4 * kLstmH + kLstmMaxLookback + 1) * U + u;
@@ -493,8 +495,13 @@ __device__ __forceinline__ float lstm_update(const Dev& d, const UnitCtx<R>& c, 
         const float xt = win_t[(size_t)((tau - 1) % ring) * U];             // indoor temperature is lagged by one step (building.py:3044-3049)
 #pragma unroll
         for (int i = 0; i < kLstmIn; ++i) { if (i == c.dyn_slot_cdem) x[i] = xc; if (i == c.dyn_slot_tin) x[i] = xt; }
-        lstm_cell(W, x, h0, c0);
-        lstm_cell(W + kLstmLayerStride, h0, h1, c1);
+        if (smem_w) {
+            lstm_cell<true>(W, ws, x, h0, c0);
+            lstm_cell<true>(W, ws + 4u * kLstmLayerStride, h0, h1, c1);
+        } else {
+            lstm_cell<false>(W, 0u, x, h0, c0);
+            lstm_cell<false>(W + kLstmLayerStride, 0u, h0, h1, c1);
+        }
     }
     const float* wl = W + 2 * kLstmLayerStride;
     float y = wl[16];
