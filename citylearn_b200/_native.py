@@ -74,8 +74,12 @@ def load():
     i32p = ctypes.POINTER(ctypes.c_int32)
     lib.cl_launch_geometry.argtypes = [vp, i32p, i32p, i32p]
     lib.cl_set_transforms.argtypes = [vp, vp, vp, vp]
+    lib.cl_kpi_enable.argtypes = [vp, i32]
+    lib.cl_kpi_accumulate.argtypes = [vp, vp, vp, vp]
+    lib.cl_kpi_read.argtypes = [vp, vp, vp, vp]
     for name in ('cl_create', 'cl_destroy', 'cl_set_outage', 'cl_reset', 'cl_step', 'cl_rollout', 'cl_time_step',
-                 'cl_state_size', 'cl_get_state', 'cl_set_state', 'cl_launch_count', 'cl_launch_geometry', 'cl_set_transforms'):
+                 'cl_state_size', 'cl_get_state', 'cl_set_state', 'cl_launch_count', 'cl_launch_geometry', 'cl_set_transforms',
+                 'cl_kpi_enable', 'cl_kpi_accumulate', 'cl_kpi_read'):
         getattr(lib, name).restype = ctypes.c_int
     if lib.cl_abi_version() != ABI_VERSION:
         raise NativeLibraryError(f'{path}: ABI version {lib.cl_abi_version()} != {ABI_VERSION}; rebuild the extension')
@@ -176,6 +180,15 @@ class Handle:
         l = None if action_low is None else np.ascontiguousarray(action_low, dtype='float32')
         check(self.lib.cl_set_transforms(self.ptr, None if t is None else t.ctypes.data, None if r is None else r.ctypes.data,
                                          None if l is None else l.ctypes.data), 'cl_set_transforms')
+
+    def kpi_enable(self, enable: bool = True):
+        check(self.lib.cl_kpi_enable(self.ptr, int(bool(enable))), 'cl_kpi_enable')
+
+    def kpi_accumulate(self, trace_ptr, district_ptr, stream: int):
+        check(self.lib.cl_kpi_accumulate(self.ptr, trace_ptr, district_ptr, stream), 'cl_kpi_accumulate')
+
+    def kpi_read(self, unit_ptr, env_ptr, stream: int):
+        check(self.lib.cl_kpi_read(self.ptr, unit_ptr, env_ptr, stream), 'cl_kpi_read')
 
     def geometry(self):
         b, t, n = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()

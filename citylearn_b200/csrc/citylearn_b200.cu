@@ -915,6 +915,61 @@ __global__ void __launch_bounds__(MAXT) advance_kernel(Dev d, int t0, int K, con
     if (coupled) cluster_sync_all();  // nobody exits while a peer may still read its partial sums
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// online KPI accumulators (cl_kpi_*): one block per env, threads stride over the buildings
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void kpi_push(double* a, double x) {
+    const double n = a[CL_KE_N];
+    if (n > 0.0) a[CL_KE_RAMP] += fmax(x - a[CL_KE_PREV], 0.0);          // CostFunction.ramping: positive ramps only
+    a[CL_KE_PREV] = x;
+    a[CL_KE_ALL_MAX] = n > 0.0 ? fmax(a[CL_KE_ALL_MAX], x) : x;
+    a[CL_KE_N] = n + 1.0;
+    a[CL_KE_D_SUM] += x; a[CL_KE_D_MAX] = a[CL_KE_D_CNT] > 0.0 ? fmax(a[CL_KE_D_MAX], x) : x; a[CL_KE_D_CNT] += 1.0;
+    if (a[CL_KE_D_CNT] == 24.0) {
+        a[CL_KE_D_FIN_LF] += 1.0 - (a[CL_KE_D_SUM] / 24.0) / a[CL_KE_D_MAX];
+        a[CL_KE_D_FIN_PEAK] += a[CL_KE_D_MAX]; a[CL_KE_D_FIN_N] += 1.0;
+        a[CL_KE_D_SUM] = 0.0; a[CL_KE_D_CNT] = 0.0;
+    }
+    a[CL_KE_M_SUM] += x; a[CL_KE_M_MAX] = a[CL_KE_M_CNT] > 0.0 ? fmax(a[CL_KE_M_MAX], x) : x; a[CL_KE_M_CNT] += 1.0;
+    if (a[CL_KE_M_CNT] == 730.0) {
+        a[CL_KE_M_FIN_LF] += 1.0 - (a[CL_KE_M_SUM] / 730.0) / a[CL_KE_M_MAX];
+        a[CL_KE_M_FIN_N] += 1.0;
+        a[CL_KE_M_SUM] = 0.0; a[CL_KE_M_CNT] = 0.0;
+    }
+}
+__global__ void kpi_accumulate_kernel(Dev d, int t, const float* __restrict__ trace, const float* __restrict__ district,
+                                      double* __restrict__ ku, double* __restrict__ ke) {
+    __shared__ double s_part[32];
+    const int e = blockIdx.x;
+    const float* row = d.table + (size_t)(__ldg(d.start + e) + t) * d.Wp;
+    double base_sum = 0.0;
+    for (int b = threadIdx.x; b < d.B; b += blockDim.x) {
+        const float* tr = trace + ((size_t)e * d.B + b) * CL_NDYN;
+        const double net = tr[CL_DYN_NET_ELECTRICITY_CONSUMPTION];
+        const double sto = (double)tr[CL_DYN_COOLING_STORAGE_ELECTRICITY_CONSUMPTION] + (double)tr[CL_DYN_HEATING_STORAGE_ELECTRICITY_CONSUMPTION]
+                         + (double)tr[CL_DYN_DHW_STORAGE_ELECTRICITY_CONSUMPTION] + (double)tr[CL_DYN_ELECTRICAL_STORAGE_ELECTRICITY_CONSUMPTION];
+        const double nws = net - sto;                                     // net_electricity_consumption_without_storage (building.py:2886-2893)
+        const double price = row[__ldg(d.ip + CL_IP_C_PRICE * d.B + b)], carbon = row[__ldg(d.ip + CL_IP_C_CARBON * d.B + b)];
+        double* a = ku + ((size_t)e * d.B + b) * CL_NKPI_UNIT;
+        a[CL_KPI_EC] += fmax(net, 0.0); a[CL_KPI_ZNE] += net;
+        a[CL_KPI_EMISSION] += fmax((double)tr[CL_DYN_NET_ELECTRICITY_CONSUMPTION_EMISSION], 0.0);
+        a[CL_KPI_COST] += fmax((double)tr[CL_DYN_NET_ELECTRICITY_CONSUMPTION_COST], 0.0);
+        a[CL_KPI_B_EC] += fmax(nws, 0.0); a[CL_KPI_B_ZNE] += nws;
+        a[CL_KPI_B_EMISSION] += fmax(carbon * nws, 0.0); a[CL_KPI_B_COST] += fmax(price * nws, 0.0);
+        base_sum += nws;
+    }
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) base_sum += __shfl_xor_sync(0xffffffffu, base_sum, m);
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = base_sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tot = 0.0;
+        for (int w = 0; w < (int)((blockDim.x + 31) >> 5); ++w) tot += s_part[w];
+        kpi_push(ke + ((size_t)e * 2 + 0) * CL_NKPI_ENV, (double)district[(size_t)e * 3]);
+        kpi_push(ke + ((size_t)e * 2 + 1) * CL_NKPI_ENV, tot);
+    }
+}
+
 // district sums of independent tiles: district[n][q] = sum over tiles (in order) of part[n][tile][q], n = (step, env)
 __global__ void district_finish_kernel(const float* __restrict__ part, float* __restrict__ district, long n3, int tiles) {
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1012,6 +1067,8 @@ struct cl_env {
     int T = 0;
     int threads = 0, blocks = 0;
     float* obs_tab_dev = nullptr;   // precomputed observation table (build_obs_table)
+    double* kpi_unit = nullptr;     // online KPI accumulators (cl_kpi_enable)
+    double* kpi_env = nullptr;
     float* dpart = nullptr;         // wide districts: per-tile partial district sums of one launch chunk
     size_t dpart_floats = 0;
     bool wide = false;       // building-tiled district: cluster launch of advance_kernel<..., WIDE = true>
@@ -1351,6 +1408,8 @@ extern "C" int cl_destroy(cl_env* env) {
     for (void* p : env->allocs) cudaFree(p);
     if (env->outage_dev) cudaFree(env->outage_dev);
     if (env->dpart) cudaFree(env->dpart);
+    if (env->kpi_unit) cudaFree(env->kpi_unit);
+    if (env->kpi_env) cudaFree(env->kpi_env);
     delete env;
     return CL_OK;
 }
@@ -1477,6 +1536,10 @@ extern "C" int cl_reset(cl_env* env, const int32_t* episode_start, int32_t unifo
     else { if (env->thermal) launch_reset<float, true>(env, obs, st); else launch_reset<float, false>(env, obs, st); }
     env->launches++;
     CUDA_TRY(cudaGetLastError());
+    if (env->kpi_unit) {
+        CUDA_TRY(cudaMemsetAsync(env->kpi_unit, 0, (size_t)d.U * CL_NKPI_UNIT * sizeof(double), st));
+        CUDA_TRY(cudaMemsetAsync(env->kpi_env, 0, (size_t)d.E * 2 * CL_NKPI_ENV * sizeof(double), st));
+    }
     env->t = 0;
     return CL_OK;
 }
@@ -1572,6 +1635,46 @@ extern "C" int cl_set_transforms(cl_env* env, const cl_obs_transform* obs_transf
         d.act_range = r; d.act_low = l;
     }
     return build_obs_table(env);      // the table holds transformed values
+}
+
+extern "C" int cl_kpi_enable(cl_env* env, int32_t enable) {
+    if (!env) return fail(CL_ERR_INVALID, "cl_kpi_enable: null env");
+    if (enable && env->dynamics) return fail(CL_ERR_UNSUPPORTED, "cl_kpi_enable: the `_without_storage` baseline does not apply to LSTM-dynamics districts (use evaluate() on a recorded history)");
+    if (!enable) {
+        CUDA_TRY(cudaDeviceSynchronize());
+        if (env->kpi_unit) cudaFree(env->kpi_unit);
+        if (env->kpi_env) cudaFree(env->kpi_env);
+        env->kpi_unit = env->kpi_env = nullptr;
+        return CL_OK;
+    }
+    if (!env->kpi_unit) {
+        const size_t nu = (size_t)env->d.U * CL_NKPI_UNIT, ne = (size_t)env->d.E * 2 * CL_NKPI_ENV;
+        CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&env->kpi_unit), nu * sizeof(double)));
+        CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&env->kpi_env), ne * sizeof(double)));
+        CUDA_TRY(cudaMemset(env->kpi_unit, 0, nu * sizeof(double)));
+        CUDA_TRY(cudaMemset(env->kpi_env, 0, ne * sizeof(double)));
+    }
+    return CL_OK;
+}
+
+extern "C" int cl_kpi_accumulate(cl_env* env, const float* trace, const float* district, cl_stream stream) {
+    if (!env || !trace || !district) return fail(CL_ERR_INVALID, "cl_kpi_accumulate: null argument");
+    if (!env->kpi_unit) return fail(CL_ERR_STATE, "cl_kpi_accumulate: call cl_kpi_enable first");
+    if (env->t < 1) return fail(CL_ERR_STATE, "cl_kpi_accumulate: no step has been taken since cl_reset");
+    int threads = ((std::min(env->d.B, 256) + 31) / 32) * 32;
+    kpi_accumulate_kernel<<<env->d.E, threads, 0, static_cast<cudaStream_t>(stream)>>>(env->d, env->t - 1, trace, district, env->kpi_unit, env->kpi_env);
+    CUDA_TRY(cudaGetLastError());
+    env->launches++;
+    return CL_OK;
+}
+
+extern "C" int cl_kpi_read(cl_env* env, double* unit_dev, double* env_dev, cl_stream stream) {
+    if (!env) return fail(CL_ERR_INVALID, "cl_kpi_read: null env");
+    if (!env->kpi_unit) return fail(CL_ERR_STATE, "cl_kpi_read: call cl_kpi_enable first");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (unit_dev) CUDA_TRY(cudaMemcpyAsync(unit_dev, env->kpi_unit, (size_t)env->d.U * CL_NKPI_UNIT * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    if (env_dev) CUDA_TRY(cudaMemcpyAsync(env_dev, env->kpi_env, (size_t)env->d.E * 2 * CL_NKPI_ENV * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    return CL_OK;
 }
 
 extern "C" int cl_launch_geometry(const cl_env* env, int32_t* blocks, int32_t* threads, int32_t* tiles) {

@@ -99,7 +99,7 @@ class CityLearnEnv:
     def __init__(self, schema, num_envs: int = 1, device: Union[str, torch.device, None] = None, precision: str = 'fp64',
                  stale_observations: bool = True, track_episode_rewards: Optional[bool] = None, debug_trace: bool = False,
                  record_history: Optional[bool] = None, history_env: int = 0, observation_transform: Optional[str] = None,
-                 normalized_actions: bool = False, **kwargs):
+                 normalized_actions: bool = False, track_kpis: bool = False, **kwargs):
         self.spec = S.load(schema, **kwargs)
         self.schema = self.spec.schema
         self.num_envs = int(num_envs)
@@ -137,7 +137,9 @@ class CityLearnEnv:
         self._history_env = int(history_env)
         if not 0 <= self._history_env < self.num_envs:
             raise ValueError('history_env out of range')
-        debug_trace = debug_trace or self._record
+        # online KPI accumulators for every env: fed from the per-step trace by a small second kernel
+        self._track_kpis = bool(track_kpis)
+        debug_trace = debug_trace or self._record or self._track_kpis
         # reward function (citylearn/citylearn.py:2100-2163)
         self.reward_function = self._make_reward_function()
         rid, rparams = self._fused_reward()
@@ -175,6 +177,9 @@ class CityLearnEnv:
                 lo = np.array([v for b in spec.buildings for v in b.action_low], dtype='float32')
                 hi = np.array([v for b in spec.buildings for v in b.action_high], dtype='float32')
                 self._h.set_transforms(transforms, (hi - lo) if self._normalized_actions else None, lo if self._normalized_actions else None)
+            if self._track_kpis:
+                self._h.kpi_enable(True)
+            self._kpi_valid = True
             E = self.num_envs
             # observations and rewards share one allocation so that the host path needs ONE device->host copy per step
             self._out = torch.zeros(E * (self._obs_dim + self._reward_dim), dtype=torch.float32, device=self.device)
@@ -380,6 +385,7 @@ class CityLearnEnv:
             self._hist_dyn = torch.zeros((T - 1, self.spec.n_buildings, S.NDYN), dtype=torch.float32, device=self.device)
             self._hist_district = torch.zeros((T - 1, 3), dtype=torch.float32, device=self.device)
             self._hist_valid = True
+        self._kpi_valid = True
         if self.num_envs == 1:
             return self._shape_obs(self._obs), self.get_info()
         return self._obs, self.get_info()
@@ -439,6 +445,8 @@ class CityLearnEnv:
                          None if self._trace is None else self._trace.data_ptr(), stream)
             if not fused:
                 self._python_reward()
+            if self._track_kpis:
+                self._h.kpi_accumulate(self._trace.data_ptr(), self._district.data_ptr(), stream)
             if self._record:
                 self._hist_dyn[self.time_step].copy_(self._trace[self._history_env])
                 self._hist_district[self.time_step].copy_(self._district[self._history_env])
@@ -473,6 +481,7 @@ class CityLearnEnv:
                             None if district is None else district.data_ptr(), self._stream())
         self.time_step += K
         self._hist_valid = False          # rollouts do not produce the per-unit trace evaluate() needs
+        self._kpi_valid = False
         return obs, reward, self.terminated
 
     # ---------------------------------------------------------------------------------------------
@@ -514,6 +523,19 @@ class CityLearnEnv:
         h = History(self._hist_dyn[:k].cpu().numpy(), self._hist_district[:k].cpu().numpy(), int(self._start_dev[self._history_env].item()),
                     self._outage)
         return evaluate(self.spec, h, control_condition, baseline_condition, comfort_band)
+
+    def evaluate_batched(self) -> Dict[str, Dict[str, np.ndarray]]:
+        """The action-dependent KPI ratios of EVERY env (`track_kpis=True`): `{'district': {name: [E]}, 'building': {name: [E, B]}}`,
+        control vs the `_without_storage` baseline, from accumulators kept on the device (`cl_kpi_*`) - no per-step history."""
+        from .evaluate import evaluate_batched
+        if not self._track_kpis or not self._kpi_valid:
+            raise RuntimeError('evaluate_batched() needs track_kpis=True and an episode advanced with step() (not rollout())')
+        E, B = self.num_envs, self.spec.n_buildings
+        with torch.cuda.device(self.device):
+            unit = torch.empty((E, B, 8), dtype=torch.float64, device=self.device)
+            envacc = torch.empty((E, 2, 15), dtype=torch.float64, device=self.device)
+            self._h.kpi_read(unit.data_ptr(), envacc.data_ptr(), self._stream())
+        return evaluate_batched(self.spec, unit.cpu().numpy(), envacc.cpu().numpy())
 
     # ---------------------------------------------------------------------------------------------
     def state_dict(self) -> Dict[str, Any]:

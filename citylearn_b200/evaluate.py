@@ -186,3 +186,85 @@ def evaluate(spec: S.DistrictSpec, history: History, control_condition=None, bas
         except Exception:   # pragma: no cover
             pass
     return records
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# batched envs: KPIs from the on-device accumulators (cl_kpi_*, include/citylearn_b200.h) instead of a per-step history
+# ------------------------------------------------------------------------------------------------------------------
+KU = {'ec': 0, 'zne': 1, 'emission': 2, 'cost': 3, 'b_ec': 4, 'b_zne': 5, 'b_emission': 6, 'b_cost': 7}
+KE = {n: i for i, n in enumerate(['n', 'prev', 'ramp', 'all_max', 'd_sum', 'd_max', 'd_cnt', 'd_fin_lf', 'd_fin_peak', 'd_fin_n',
+                                  'm_sum', 'm_max', 'm_cnt', 'm_fin_lf', 'm_fin_n'])}
+
+
+def _push(a: np.ndarray, x: float):
+    """`kpi_push` of the CUDA kernel on a copy of the accumulators `[E, NKE]` (used for the baseline's trailing entry)."""
+    a = a.copy()
+    n = a[:, KE['n']]
+    a[:, KE['ramp']] += np.where(n > 0, np.maximum(x - a[:, KE['prev']], 0.0), 0.0)
+    a[:, KE['prev']] = x
+    a[:, KE['all_max']] = np.where(n > 0, np.maximum(a[:, KE['all_max']], x), x)
+    a[:, KE['n']] = n + 1
+    for p, w in (('d', 24.0), ('m', 730.0)):
+        a[:, KE[f'{p}_sum']] += x
+        a[:, KE[f'{p}_max']] = np.where(a[:, KE[f'{p}_cnt']] > 0, np.maximum(a[:, KE[f'{p}_max']], x), x)
+        a[:, KE[f'{p}_cnt']] += 1
+        full = a[:, KE[f'{p}_cnt']] == w
+        with np.errstate(invalid='ignore', divide='ignore'):
+            a[:, KE[f'{p}_fin_lf']] += np.where(full, 1.0 - (a[:, KE[f'{p}_sum']] / w) / a[:, KE[f'{p}_max']], 0.0)
+        if p == 'd':
+            a[:, KE['d_fin_peak']] += np.where(full, a[:, KE['d_max']], 0.0)
+        a[:, KE[f'{p}_fin_n']] += full
+        a[:, KE[f'{p}_sum']] = np.where(full, 0.0, a[:, KE[f'{p}_sum']])
+        a[:, KE[f'{p}_cnt']] = np.where(full, 0.0, a[:, KE[f'{p}_cnt']])
+    return a
+
+
+def _windowed(a: np.ndarray, p: str, what: str) -> np.ndarray:
+    """mean over the windows (finished ones + the open one) of `1 - mean/max` ('lf') or of the window maximum ('peak')."""
+    cnt = a[:, KE[f'{p}_cnt']]
+    open_ = cnt > 0
+    with np.errstate(invalid='ignore', divide='ignore'):
+        if what == 'lf':
+            last = 1.0 - (a[:, KE[f'{p}_sum']] / np.maximum(cnt, 1.0)) / a[:, KE[f'{p}_max']]
+            total = a[:, KE[f'{p}_fin_lf']] + np.where(open_, last, 0.0)
+        else:
+            total = a[:, KE['d_fin_peak']] + np.where(open_, a[:, KE['d_max']], 0.0)
+        return total / (a[:, KE[f'{p}_fin_n']] + open_)
+
+
+def _safe_div_array(c: np.ndarray, b: np.ndarray) -> np.ndarray:
+    c = np.where(np.isfinite(c), c, 0.0)
+    b = np.where(np.isfinite(b), b, 0.0)
+    with np.errstate(invalid='ignore', divide='ignore'):
+        return np.where(b == 0.0, np.where(c == 0.0, 1.0, np.nan), c / np.where(b == 0.0, 1.0, b))
+
+
+def evaluate_batched(spec: S.DistrictSpec, unit: np.ndarray, env: np.ndarray) -> Dict[str, Dict[str, np.ndarray]]:
+    """KPI ratios of every env from the accumulators `unit [E, B, 8]`, `env [E, 2, 15]` (control vs `_without_storage` baseline).
+
+    Returns `{'district': {cost_function: [E]}, 'building': {cost_function: [E, B]}}` with the action-dependent rows of
+    `CityLearnEnv.evaluate()`: electricity_consumption_total, zero_net_energy, carbon_emissions_total, cost_total (building level,
+    district = mean over buildings) and ramping_average, daily / monthly_one_minus_load_factor_average, daily_peak_average,
+    all_time_peak_average (district level).  Same slicing quirk as the history path: the baseline district series carries one
+    trailing not-yet-simulated (zero) entry, the control series does not (citylearn.py:1188-1200).
+    """
+    unit = np.asarray(unit, dtype='float64')
+    env = np.asarray(env, dtype='float64')
+    c, b = env[:, 0, :], _push(env[:, 1, :], 0.0)
+    has_carbon = np.array([float(x.series['carbon_intensity'].sum()) != 0 for x in spec.buildings])
+    has_price = np.array([float(x.series['electricity_pricing'].sum()) != 0 for x in spec.buildings])
+    building = {
+        'electricity_consumption_total': _safe_div_array(unit[..., KU['ec']], unit[..., KU['b_ec']]),
+        'zero_net_energy': _safe_div_array(unit[..., KU['zne']], unit[..., KU['b_zne']]),
+        'carbon_emissions_total': _safe_div_array(unit[..., KU['emission']], np.where(has_carbon[None, :], unit[..., KU['b_emission']], 0.0)),
+        'cost_total': _safe_div_array(unit[..., KU['cost']], np.where(has_price[None, :], unit[..., KU['b_cost']], 0.0)),
+    }
+    district = {k: np.nanmean(v, axis=1) for k, v in building.items()}
+    district.update({
+        'ramping_average': _safe_div_array(c[:, KE['ramp']], b[:, KE['ramp']]),
+        'daily_one_minus_load_factor_average': _safe_div_array(_windowed(c, 'd', 'lf'), _windowed(b, 'd', 'lf')),
+        'monthly_one_minus_load_factor_average': _safe_div_array(_windowed(c, 'm', 'lf'), _windowed(b, 'm', 'lf')),
+        'daily_peak_average': _safe_div_array(_windowed(c, 'd', 'peak'), _windowed(b, 'd', 'peak')),
+        'all_time_peak_average': _safe_div_array(c[:, KE['all_max']], b[:, KE['all_max']]),
+    })
+    return {'district': district, 'building': building}

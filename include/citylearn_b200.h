@@ -225,6 +225,27 @@ typedef struct cl_obs_transform {
 } cl_obs_transform;
 int cl_set_transforms(cl_env* env, const cl_obs_transform* obs_transform, const float* action_range, const float* action_low);
 
+/*
+ * Online KPI accumulators for batched envs (citylearn/citylearn.py:1136-1323, cost_function.py:10-388): what
+ * CityLearnEnv.evaluate() needs of the action-dependent series, kept per env on the device instead of a per-step history.
+ * Control series = the simulated values; baseline = `_without_storage` (net minus the storage devices' consumption; districts with
+ * LSTM dynamics are not supported here).  cl_kpi_accumulate is called after every cl_step with that step's `trace` and `district`
+ * outputs; cl_reset zeroes the accumulators.  Layouts (doubles):
+ *   unit [E][B][CL_NKPI_UNIT]: sum max(net,0), sum net, sum max(emission,0), sum max(cost,0) for control, then for the baseline
+ *   env  [E][2][CL_NKPI_ENV] : per series (0 control district net, 1 baseline district net) the running ramping / load-factor /
+ *                              peak window state of cl_kpi_env
+ */
+enum cl_kpi_unit { CL_KPI_EC = 0, CL_KPI_ZNE, CL_KPI_EMISSION, CL_KPI_COST, CL_KPI_B_EC, CL_KPI_B_ZNE, CL_KPI_B_EMISSION, CL_KPI_B_COST, CL_NKPI_UNIT };
+enum cl_kpi_env {
+    CL_KE_N = 0, CL_KE_PREV, CL_KE_RAMP, CL_KE_ALL_MAX,
+    CL_KE_D_SUM, CL_KE_D_MAX, CL_KE_D_CNT, CL_KE_D_FIN_LF, CL_KE_D_FIN_PEAK, CL_KE_D_FIN_N,     /* 24-step windows */
+    CL_KE_M_SUM, CL_KE_M_MAX, CL_KE_M_CNT, CL_KE_M_FIN_LF, CL_KE_M_FIN_N,                       /* 730-step windows */
+    CL_NKPI_ENV
+};
+int cl_kpi_enable(cl_env* env, int32_t enable);
+int cl_kpi_accumulate(cl_env* env, const float* trace, const float* district, cl_stream stream);
+int cl_kpi_read(cl_env* env, double* unit_dev, double* env_dev, cl_stream stream);
+
 /* Launch geometry chosen at cl_create: CTAs per launch, threads per CTA (incl. the helper warp) and building tiles per env
  * (1: a block owns whole envs; > 1: one thread-block cluster per env, one CTA per tile of buildings). */
 int cl_launch_geometry(const cl_env* env, int32_t* blocks, int32_t* threads, int32_t* tiles);
