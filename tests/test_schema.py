@@ -73,3 +73,26 @@ def test_table_layout():
     assert spec.action_dim == 17
     # shared weather / pricing series are stored once
     assert spec.columns[(0, 'outdoor_dry_bulb_temperature')] == spec.columns[(16, 'outdoor_dry_bulb_temperature')]
+
+
+def test_synthetic_wide_district_directory_round_trip(tmp_path):
+    """The synthetic C4 district written as a real schema directory loads to the same tables as the in-memory source."""
+    from citylearn_b200.synthetic import SyntheticWideSource
+    src = SyntheticWideSource(6)
+    root = src.write_directory(tmp_path / 'wide6')
+    a = S.load(src.schema(), data_source=src)
+    b = S.load(str(root / 'schema.json'))
+    assert a.table.shape == b.table.shape and np.array_equal(a.table, b.table, equal_nan=True)
+    assert np.array_equal(a.params, b.params, equal_nan=True) and np.array_equal(a.iparams, b.iparams)
+    # building i replays Building_{(i mod 17)+1} with a scaled load and a 4 / 5 kW PV
+    assert [bb.devices['pv']['nominal_power'] for bb in a.buildings] == [4.0, 5.0, 4.0, 5.0, 4.0, 5.0]
+    base = S.load('citylearn_challenge_2022_phase_all')
+    ratio = a.buildings[3].series['non_shiftable_load'] / np.maximum(base.buildings[3].series['non_shiftable_load'], 1e-9)
+    assert np.nanstd(ratio[base.buildings[3].series['non_shiftable_load'] > 0.1]) < 1e-6
+
+
+def test_loaded_spec_passes_through_load():
+    spec = S.load('citylearn_challenge_2022_phase_1')
+    assert S.load(spec) is spec
+    with pytest.raises(ValueError):
+        S.load(spec, central_agent=True)
