@@ -412,7 +412,7 @@ __device__ __forceinline__ void write_obs_general(const Dev& d, float* obs, int 
 // offsets in floats from the start of the dynamic shared memory (kept as plain ints so that every access is derived
 // directly from the `extern __shared__` array and compiles to LDS/STS with 32-bit addressing, not generic loads)
 struct SmemLayout {
-    int curves, bsolar, rows, tcol, tmpl, red, rsum, dsum, wpart, rpart, lstm, dynbuf, Lp;
+    int curves, bsolar, rows, tcol, tmpl, red, rsum, dsum, wpart, rpart, lstm, lstm_pre, dynbuf, Lp;
 };
 __host__ __device__ __forceinline__ SmemLayout smem_layout(int B, int Wp, int L, int epb, int nt, int rsize, int lstm_smem = 0, int tab_layout = 0) {
     SmemLayout o;
@@ -429,6 +429,7 @@ __host__ __device__ __forceinline__ SmemLayout smem_layout(int B, int Wp, int L,
     o.wpart = f; f += 2 * 3 * 32;                // wide districts: per-warp partial district sums [2][3][32 warps]
     o.rpart = f; f += 2 * 32 * 2;                // wide districts, central agent: per-warp partial reward sums [2][32] doubles (8-byte aligned: f is even)
     o.lstm = f; f += lstm_smem ? B * kLstmStride : 0;      // kLstmStride is a multiple of 4 floats: 16-byte aligned rows
+    o.lstm_pre = f; f += lstm_smem ? B * kLstmPreRing * 64 : 0;   // per-building ring of shared layer-0 input projections
     o.dynbuf = f;
     return o;
 }
@@ -466,7 +467,7 @@ __device__ __forceinline__ void reward_inputs(const Dev& d, const UnitCtx<R>& c,
 // ------------------------------------------------------------------------------------------------------------------
 template <typename R>
 __device__ __forceinline__ float lstm_update(const Dev& d, const UnitCtx<R>& c, const float* W, int u, int t, int row0 /* table row of step 0 */,
-                                             float obs_cool_dem, float t_in_dataset) {
+                                             float obs_cool_dem, float t_in_dataset, const float* pre /* this building's projection ring or nullptr */) {
     const int U = d.U;
     const int L = c.dyn_lookback, ring = L + 1;
     const bool smem_w = d.lstm_smem != 0;                 // W then points into shared memory
@@ -484,6 +485,19 @@ __device__ __forceinline__ float lstm_update(const Dev& d, const UnitCtx<R>& c, 
         h0[j] = lst[(size_t)j * U + u]; h1[j] = lst[(size_t)(kLstmH + j) * U + u];
         c0[j] = lst[(size_t)(2 * kLstmH + j) * U + u]; c1[j] = lst[(size_t)(3 * kLstmH + j) * U + u];
     }
+    if (pre != nullptr) {
+        // every env of the block sits on the same time rows: the exogenous part of W_ih x is shared (helper warp), only the
+        // two fed-back inputs are per unit
+        const uint32_t ps0 = smem_u32(pre);
+#pragma unroll 1
+        for (int sidx = 0; sidx < L; ++sidx) {
+            const int tau = t - (L - 1) + sidx;
+            const float xc = c.dyn_slot_cdem >= 0 ? win_c[(size_t)(tau % ring) * U] : 0.f;
+            const float xt = win_t[(size_t)((tau - 1) % ring) * U];
+            lstm_cell_pre(ws, ps0 + 4u * 64u * (uint32_t)(tau % kLstmPreRing), c.dyn_slot_cdem, c.dyn_slot_tin, xc, xt, h0, c0);
+            lstm_cell<true>(W, ws + 4u * kLstmLayerStride, h0, h1, c1);
+        }
+    } else
 #pragma unroll 1
     for (int sidx = 0; sidx < L; ++sidx) {
         const int tau = t - (L - 1) + sidx;                                 // time step of the non-fed-back inputs
@@ -622,6 +636,28 @@ __global__ void __launch_bounds__(MAXT) advance_kernel(Dev d, int t0, int K, con
     }
     __syncthreads();   // mbarriers initialised (visible to every waiter), curves / tcol / LSTM weights staged
 
+    // LSTM layer-0 input projections shared by all envs of the block (uniform episode windows, weights in shared memory):
+    // pre[bb][tau % ring][r] = bias0[r] + W_ih0[r][:] . x(row of time step tau); fed-back slots hold 0 in the table
+    const bool use_pre = DYNAMICS && uniform && d.lstm_smem;
+    float* s_pre = smf + lo.lstm_pre;
+    auto project_row = [&](int bb, int tau, const float* rowp, int r) {
+        const float* Wb = smf + lo.lstm + (size_t)bb * kLstmStride;
+        const int nin = __ldg(d.ip + CL_IP_DYN_N_INPUTS * B + bb);
+        const float* xin = rowp + __ldg(d.ip + CL_IP_DYN_C_INPUTS * B + bb);
+        float acc = Wb[64 * 32 + r];
+        for (int i = 0; i < nin; ++i) acc = fmaf(Wb[r * 16 + i], xin[i], acc);
+        s_pre[((size_t)bb * kLstmPreRing + (tau % kLstmPreRing)) * 64 + r] = acc;
+    };
+    if (use_pre) {
+        // rows t0 - 11 .. t0 straight from the table (later rows are projected by the helper warp one step ahead)
+        for (int idx = tid; idx < B * kLstmMaxLookback * 64; idx += nt) {
+            const int r = idx & 63, rest = idx >> 6;
+            const int bb = rest / kLstmMaxLookback, tau = t0 - (rest - bb * kLstmMaxLookback);
+            if (tau >= 0 && (__ldg(d.ip + CL_IP_FLAGS * B + bb) & CL_F_DYNAMICS))
+                project_row(bb, tau, d.table + (size_t)(d.start0 + tau) * Wp, r);
+        }
+    }
+
     // per-building PV generation of time row `rowp` -> dst[b]  (building.py:2554; the same value for every env of the block)
     auto building_inputs = [&](const float* rowp, R* dst) {
         const auto* P = PSel<R>::p(d);
@@ -665,6 +701,12 @@ __global__ void __launch_bounds__(MAXT) advance_kernel(Dev d, int t0, int K, con
         if (is_helper) {
             // ---------------- helper warp ----------------
             if (uniform && k + 1 < K) building_inputs(row_next, s_bsolar + ((k + 1) & 1) * TBs);
+            if (use_pre && k + 1 < K) {
+                for (int bb = 0; bb < B; ++bb) {
+                    if (!(__ldg(d.ip + CL_IP_FLAGS * B + bb) & CL_F_DYNAMICS)) continue;
+                    project_row(bb, t + 1, row_next, lane); project_row(bb, t + 1, row_next, lane + 32);
+                }
+            }
             if (coupled) cluster_sync_all(); else __syncthreads();             // S1
             if (need_dsum) __syncthreads();                                    // S2
             if (central_sync) { if (WIDE) cluster_sync_all(); else { if (k > 0) __syncthreads(); __syncthreads(); } }
@@ -763,7 +805,7 @@ __global__ void __launch_bounds__(MAXT) advance_kernel(Dev d, int t0, int K, con
             float t_in = row[c.c_tin];
             if (DYNAMICS && (c.p.flags & CL_F_DYNAMICS)) {
                 const float cd = (float)(o.e_from_cool + fabs(rmin(o.eb_cs, (R)0)));
-                t_in = lstm_update<R>(d, c, lstm_w, u, t, start_e, cd, t_in);
+                t_in = lstm_update<R>(d, c, lstm_w, u, t, start_e, cd, t_in, use_pre ? s_pre + (size_t)b * kLstmPreRing * 64 : nullptr);
             }
             red[ul] = (float)o.net;
             red[nt + ul] = (float)o.cost;
