@@ -1339,6 +1339,16 @@ extern "C" int cl_create(const cl_district_desc* desc, cl_env** out) {
             if (cost < best - 1e-9) { best = cost; target = cand[ci]; }
         }
         if (target == 0) target = 128;
+        // Many more units than one wave of 512-thread blocks can hold (e.g. 17 x 32768): the 1024-thread instantiation (64
+        // registers, a few spills) keeps twice the warps resident per SM and wins by 10 % (fp64 flow) / 16 % (fp32) there
+        // (profiles/README.md "Large env counts"); thermal / LSTM instantiations spill too much at 64 registers.
+        if (!any_thermal && !any_dyn && B <= 480) {
+            const int epb_t = std::max(1, std::min(target / B, d.E));
+            const long blocks_t = (d.E + epb_t - 1) / epb_t;
+            const int epb_big = std::max(1, 960 / B);
+            const long blocks_big = (d.E + epb_big - 1) / epb_big;
+            if (blocks_t > 2L * n_sm && blocks_big >= n_sm) target = 960;
+        }
     }
     int epb = target / B;
     if (epb < 1) epb = 1;
