@@ -10,12 +10,18 @@
 //   start    int32  [E]               table row of time step 0 of every env
 //   state    float  [6][E*B]  (+ double [2][E*B] in CL_PRECISION_FP64)   unit index u = e * B + b (building fastest)
 //   lstm     float  [90][E*B]         h, c of both layers and the two fed-back input windows (LSTM dynamics districts)
+//   obs_tab  float  [n_rows][L]       complete (wrapper-transformed) reference-parity observation row of every time step, built
+//                                     once; the step kernel only moves it (TMA load -> TMA stores)
+//   kpi_*    double [E][B][8], [E][2][15]   optional online KPI accumulators (cl_kpi_*)
 //
-// Kernels: `advance_kernel` (K >= 1 consecutive time steps in one launch: cl_step is K = 1, cl_rollout any K) and
-// `reset_kernel`.
+// Kernels: `advance_kernel` (K >= 1 consecutive time steps in one launch: cl_step is K = 1, cl_rollout any K), `reset_kernel`,
+// and the small one-off / per-step helpers `build_obs_table_kernel`, `district_finish_kernel`, `kpi_accumulate_kernel`.
 // Thread mapping: one thread per unit; a block owns `envs_per_block` consecutive envs x all B buildings, so its slice of
 // actions [E][A], rewards [E][B], state [.][E*B] and observations [E][L] is one contiguous range each (coalesced), and the
 // district sums of an env never leave the block (shared memory, summed in building order like the reference's sum()).
+// Districts wider than one block (WIDE instantiation) split the buildings of an env into tiles, one CTA each: independent CTAs
+// with deferred district sums, or a thread-block cluster exchanging partial sums through distributed shared memory when a
+// reward reads the district sum inside the step.
 #include <cuda_runtime.h>
 
 #include <cstdio>
