@@ -454,3 +454,60 @@ def test_wide_district_rollout_marl_central_and_fresh_observations():
         assert max_abs_diff(obs.cpu().numpy(), oobs) == 0.0
         ok, w = within_scaled_tolerance(rew.cpu().numpy(), orew, 1.0, rtol=1e-5)
         assert ok, ('central reward', k, w)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# observation table (TMA copy of precomputed rows) vs the per-step gather: both must write identical observations
+# ----------------------------------------------------------------------------------------------------------------------
+def _table_vs_gather(make, steps, monkeypatch):
+    monkeypatch.delenv('CL_B200_OBS_TABLE_MB', raising=False)
+    a = make()
+    monkeypatch.setenv('CL_B200_OBS_TABLE_MB', '0')            # budget 0 MiB: cl_create falls back to gathering the row every step
+    b = make()
+    monkeypatch.delenv('CL_B200_OBS_TABLE_MB', raising=False)
+    assert a.unwrapped._obs_dim % 4 == 0, 'the table path needs 16-byte rows'
+    oa, _ = a.reset(); ob, _ = b.reset()
+    assert torch.equal(oa, ob)
+    g = torch.Generator(device='cuda').manual_seed(5)
+    A = a.unwrapped.spec.action_dim
+    E = a.unwrapped.num_envs
+    for k in range(steps):
+        act = torch.rand((E, A), device='cuda', generator=g)
+        oa, ra, _, _, _ = a.step(act); ob, rb, _, _, _ = b.step(act)
+        assert torch.equal(oa, ob), f'observations differ at step {k}'
+        assert torch.equal(ra, rb)
+    return a
+
+
+def test_observation_table_patches_outage_columns(monkeypatch):
+    """2023 schema (stochastic outages, `power_outage` observation) trimmed to 28 observations per building so that the row is a
+    multiple of 16 bytes: the table path patches the outage columns per step; also checked against the oracle."""
+    from citylearn_b200 import CityLearnEnv
+    from citylearn_oracle import OracleEnv
+    kw = dict(central_agent=False, inactive_observations=['day_type', 'hour'], num_envs=4)
+    # the episode's outage (seed 73055) covers time steps 389-403
+    env = _table_vs_gather(lambda: CityLearnEnv('citylearn_challenge_2023_phase_2_local_evaluation', **kw), 420, monkeypatch)
+    names = [n for _, n in env._entries]
+    assert 'power_outage' in names
+    spec = env.spec
+    fresh = CityLearnEnv(spec, num_envs=4)
+    oracle = OracleEnv(spec, 4)
+    o, _ = fresh.reset()
+    assert max_abs_diff(o.cpu().numpy(), oracle.reset().astype('float32')) == 0.0
+    rng = np.random.RandomState(2)
+    saw_outage = False
+    for k in range(420):
+        a = rng.uniform(0, 1, size=(4, spec.action_dim)).astype('float32')
+        obs, _, _, _, _ = fresh.step(torch.from_numpy(a).cuda())
+        oobs, _, _, _ = oracle.step(a)
+        assert max_abs_diff(obs.cpu().numpy(), oobs) == 0.0, k
+        saw_outage = saw_outage or bool(oobs[:, [i for i, n in enumerate(names) if n == 'power_outage']].any())
+    assert saw_outage, 'the window must contain an outage for this test to mean anything'
+
+
+def test_observation_table_with_normalized_wrapper(monkeypatch):
+    """4 buildings x 31 normalised observations = 124 columns: periodic sin / cos + min-max values baked into the table."""
+    from citylearn_b200 import CityLearnEnv, wrappers as W
+    make = lambda: W.NormalizedSpaceWrapper(CityLearnEnv('citylearn_challenge_2022_phase_1', num_envs=8,          # noqa: E731
+                                                         buildings=['Building_1', 'Building_2', 'Building_3', 'Building_4']))
+    _table_vs_gather(make, 40, monkeypatch)
