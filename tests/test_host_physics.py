@@ -93,3 +93,44 @@ def test_fp32_flow_is_close(hostlib, case):
             worst = max(worst, w)
             assert ok, (n, w)
     assert worst > 0.0
+
+
+@pytest.mark.parametrize('dataset', ['citylearn_challenge_2022_phase_1', 'citylearn_challenge_2020_climate_zone_1'])
+@pytest.mark.parametrize('seed', [0, 1, 2, 3])
+def test_fp64_flow_fuzzed_parameters(hostlib, dataset, seed):
+    """Randomly perturbed device parameters (capacities, powers, efficiencies, losses, depth of discharge, sub-hour ratios) and 4 envs with extreme / zero / saturating actions: the host-compiled device code and the oracle must
+    stay bit-identical in regimes no dataset exercises."""
+    import copy
+    spec = copy.deepcopy(S.load(dataset))
+    rng = np.random.RandomState(100 + seed)
+    B = spec.n_buildings
+    p = spec.params
+    u = lambda lo, hi: rng.uniform(lo, hi, B)          # noqa: E731
+    p[:, P['BAT_CAPACITY']] *= u(0.2, 3.0)
+    p[:, P['BAT_NOMINAL_POWER']] *= u(0.3, 2.0)
+    p[:, P['BAT_LOSS']] = u(0.0, 0.01)
+    p[:, P['BAT_CLC']] = u(0.0, 1e-3)
+    p[:, P['BAT_DOD']] = u(0.6, 1.0)
+    p[:, P['BAT_INITIAL_SOC']] = np.float32(u(0.0, 0.5))
+    if seed % 2:
+        p[:, P['BAT_CAPACITY']][0] = 0.0               # an absent battery among real ones
+    thermal = bool((spec.iparams[:, S.IP['FLAGS']] & S.F_HAS_THERMAL).any())
+    for pre in (('CS', 'HS', 'DS') if thermal else ()):
+        p[:, P[f'{pre}_CAPACITY']] = np.float32(p[:, P[f'{pre}_CAPACITY']] * u(0.3, 2.0))
+        p[:, P[f'{pre}_EFFICIENCY']] = u(0.8, 1.0)
+        p[:, P[f'{pre}_LOSS']] = u(0.0, 0.02)
+        p[:, P[f'{pre}_INITIAL_SOC']] = np.float32(u(0.0, 0.9))
+    for pre in ('CD', 'HD', 'DD'):
+        p[:, P[f'{pre}_NOMINAL_POWER']] = np.float32(p[:, P[f'{pre}_NOMINAL_POWER']] * u(0.5, 1.5))
+    if seed >= 2:                                      # sub-hour control steps on an hourly dataset
+        p[:, P['TIME_STEP_RATIO']] = 0.5
+        p[:, P['HOURS_PER_STEP']] = 0.5
+    E, K = 4, 48
+    acts = rng.uniform(-1, 1, size=(K, E, spec.action_dim)).astype('float32')
+    acts[:, 1] = np.sign(acts[:, 1])                   # saturating
+    acts[::3, 2] = 0.0                                 # idle steps
+    acts[:, 3] *= 0.05                                 # tiny
+    for got, ref in run_host(hostlib, spec, acts, precision=1, E=E):
+        for n in CHECKED + ['electrical_storage_degraded_capacity']:
+            a, b = got[..., DYN[n]], ref[..., DYN[n]].astype('float32')
+            assert np.array_equal(a, b, equal_nan=True), (n, float(np.nanmax(np.abs(a.astype('float64') - b))))
