@@ -68,7 +68,13 @@ def _interp_curve(xn, xs, ys, n):
 
 class OracleEnv:
     def __init__(self, spec: S.DistrictSpec, num_envs: int = 1, central_agent=None, stale_observations: bool = True,
-                 reward=None):
+                 reward=None, libm_pow: bool = False):
+        # The reference takes the round-trip efficiency as `efficiency ** 0.5` on Python / NumPy scalars, i.e. libm `pow`
+        # (energy_model.py:675-678), which is not correctly rounded: about once in 10^4 values it differs from sqrt by one ulp,
+        # and when the affected float64 then sits on a float32 rounding tie the stored energy balance moves by a float32 ulp.
+        # `libm_pow=True` reproduces that with math.pow per element (slow; used when pinning against the reference's traces);
+        # the default is the correctly rounded sqrt, which is what the CUDA kernel computes.
+        self.libm_pow = bool(libm_pow)
         self.spec = spec
         self.E = int(num_envs)
         self.B = spec.n_buildings
@@ -88,6 +94,13 @@ class OracleEnv:
         self.dyn_weights = []
         for bi, b in enumerate(spec.buildings):
             self.dyn_weights.append(b.dynamics_weights if b.dynamics else None)
+
+    def _root(self, x):
+        x = np.asarray(x, dtype=f64)
+        if not self.libm_pow:
+            return np.sqrt(x)
+        import math
+        return np.frompyfunc(lambda v: math.pow(v, 0.5) if v >= 0 else float('nan'), 1, 1)(x).astype(f64)
 
     # -- helpers ---------------------------------------------------------------------------------
     def P(self, name):
@@ -241,7 +254,7 @@ class OracleEnv:
         energy64 = np.where(lim_out, np.fmax(-self.P(f'{pre}_MAX_OUT'), energy64), energy64)
         energy64 = energy64 * r                        # StorageDevice.charge :732
         e_init = self._energy_init64(soc32, cap, loss)
-        rte = np.sqrt(eff)
+        rte = self._root(eff)
         fin = np.where(energy64 >= 0, np.minimum(e_init + energy64 * rte, cap), np.maximum(0.0, e_init + energy64 / rte))
         soc = w32(fin / np.maximum(cap, EPS))
         d = fin - e_init
@@ -271,9 +284,9 @@ class OracleEnv:
         # discharge branch (:1046-1052): float32 soc difference, PREVIOUS efficiency
         diff32 = soc32 - w32(1.0 - self.P('BAT_DOD'))
         if self.eff_is_weak:
-            lim = (diff32 * w32(cap) * w32(np.sqrt(self.eff_b))).astype(f64)
+            lim = (diff32 * w32(cap) * w32(self._root(self.eff_b))).astype(f64)
         else:
-            lim = (diff32 * w32(cap)).astype(f64) * np.sqrt(self.eff_b)
+            lim = (diff32 * w32(cap)).astype(f64) * self._root(self.eff_b)
         lim = -np.maximum(lim, 0.0)
         e_dis = np.maximum(np.maximum(-p_max, lim), energy64)
         arg_dis = np.minimum(np.abs(action_energy), p_max)
@@ -286,7 +299,7 @@ class OracleEnv:
             eff = y0 + (xn - x0) * (y1 - y0) / (x1 - x0)
         # StorageDevice.charge with the new efficiency (:719-768)
         e = e * r
-        rte = np.sqrt(eff)
+        rte = self._root(eff)
         fin = np.where(e >= 0, np.minimum(e_init + e * rte, cap), np.maximum(0.0, e_init + e / rte))
         soc = w32(fin / np.maximum(cap, EPS))
         d = fin - e_init

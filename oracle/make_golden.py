@@ -292,6 +292,7 @@ CASES = {
     # thermal tanks + autosized heat pumps / heaters / tanks (2020 challenge, 9 buildings; cooling, dhw and battery actions)
     'c6_tanks_2020': dict(dataset=Z20, steps=None, record=sparse, seed=6),
     'c6_tanks_2020_marl_central': dict(dataset=Z20, overrides={'central_agent': True}, reward=MARL, steps=150, seed=7),
+    'c6_tanks_2020_solar_penalty': dict(dataset=Z20, reward={'type': 'citylearn.reward_function.SolarPenaltyReward', 'attributes': {}}, steps=150, seed=16),
     # cooling tank + cooling-device action on LSTM buildings (hidden 8, 11 inputs); Building_4's 1x50 LSTM is outside the kernel's shape
     'c6_baeda3': dict(dataset=BAEDA, overrides={'buildings': ['Building_1', 'Building_2', 'Building_3']}, steps=600, seed=8),
     # 32-building slice of the synthetic wide district (C4): pins the per-building path of the 1024-building runs

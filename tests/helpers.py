@@ -1,4 +1,5 @@
 """Shared test helpers: golden fixtures, spec construction from a fixture's config, comparison utilities."""
+import functools
 import json
 from pathlib import Path
 
@@ -94,3 +95,26 @@ def observation_scales(spec, entries):
         s = float(b.observation_high[k]) - float(b.observation_low[k])
         out.append(max(s, 1.0) if np.isfinite(s) else 1.0)
     return np.array(out)
+
+
+@functools.lru_cache(maxsize=None)
+def oracle_run(case):
+    """One oracle episode over a single-episode fixture's actions (shared by test_oracle_golden and test_evaluate: the year-long
+    cases take ~40 s each).  `libm_pow=True`: the reference's `efficiency ** 0.5` (see OracleEnv)."""
+    from citylearn_oracle import OracleEnv
+    z, cfg, _ = load_golden(case)
+    assert cfg['episodes'] == 1
+    spec = spec_for(cfg)
+    env = OracleEnv(spec, 1, libm_pow=True)
+    tracker = S.EpisodeTracker(spec.simulation_start_time_step, spec.simulation_end_time_step)
+    ets = spec.episode_time_steps if spec.episode_time_steps is not None else tracker.simulation_time_steps
+    tracker.next_episode(ets, spec.rolling_episode_split, spec.random_episode_split, spec.random_seed)
+    reset_obs = env.reset(tracker.episode_start_time_step, tracker.episode_time_steps)[0].astype('float32')
+    acts = actions_of(z)[0]
+    obs, rew, dist, dyn = [], [], [], []
+    for k in range(len(acts)):
+        o, r, d, y = env.step(acts[k][None])
+        obs.append(o[0].astype('float32')); rew.append(r[0].copy()); dist.append(d[0].copy()); dyn.append(y[0].copy())
+    return {'spec': spec, 'window': [tracker.episode_start_time_step, tracker.episode_end_time_step], 'reset_obs': reset_obs,
+            'obs': np.stack(obs), 'reward': np.stack(rew), 'district': np.stack(dist), 'dyn': np.stack(dyn),
+            'start': int(env.start[0]), 'outage': env.outage.copy()}

@@ -10,7 +10,7 @@ import pytest
 from citylearn_b200 import schema as S
 from citylearn_b200.evaluate import History, evaluate
 from citylearn_oracle import OracleEnv
-from helpers import actions_of, golden_cases, load_golden, spec_for
+from helpers import actions_of, golden_cases, load_golden, oracle_run, spec_for
 
 
 def golden_table(z):
@@ -37,7 +37,8 @@ def compare(table, ref, lstm):
             assert got is None or (isinstance(got, float) and np.isnan(got)), key
         else:
             tol = 2e-4 if lstm and 'discomfort' in key[1] or lstm and 'resilience' in key[1] else 2e-6
-            assert got == pytest.approx(v, rel=tol, abs=1e-9), (key, got, v)
+            # unserved-energy ratios of districts without outages are float32 rounding residue around 0 (1e-9)
+            assert got == pytest.approx(v, rel=tol, abs=5e-9 if 'unserved' in key[1] else 1e-9), (key, got, v)
 
 
 @pytest.mark.parametrize('case', [c for c in golden_cases() if c not in ('c1_episodes',)])
@@ -45,8 +46,9 @@ def test_kpis_match_reference(case):
     z, cfg, _ = load_golden(case)
     if 'evaluate' not in z.files:
         pytest.skip('fixture without KPI table')
-    spec = spec_for(cfg)
-    h = oracle_history(spec, actions_of(z)[0])
+    run = oracle_run(case)
+    spec = run['spec']
+    h = History(run['dyn'].astype('float32'), run['district'], run['start'], run['outage'])
     recs = evaluate(spec, h, as_dataframe=False)
     table = {(r['name'], r['cost_function']): r['value'] for r in recs}
     compare(table, golden_table(z), any(b.dynamics for b in spec.buildings))

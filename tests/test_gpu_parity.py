@@ -21,6 +21,10 @@ NON_LSTM_CASES = ['c1_phase1_300', 'c1_phase1_central', 'c1_episodes', 'c1_subho
                   'c6_tanks_2020', 'c6_tanks_2020_marl_central',
                   'c4_slice32']      # first 32 buildings of the synthetic wide district (BASELINE configs[3])
 # 2023 schema: heat pump + electric heater + DHW tank + battery + outages + LSTM indoor-temperature dynamics (BASELINE configs[2])
+# Cases in which the reference's `efficiency ** 0.5` (libm pow, not correctly rounded) differs from sqrt by one float64 ulp AND the
+# affected energy balance sits on a float32 rounding tie (oracle/citylearn_oracle.py `libm_pow`): the kernel computes the correctly
+# rounded sqrt, so those values may differ from the reference trace by ONE float32 ulp (observed at 1 of 1 350 battery updates here).
+POW_TIE_CASES = ['c6_tanks_2020_solar_penalty']
 LSTM_CASES = ['c3_marl', 'c3_default_central_comfort', 'c3_solar_comfort',
               'c6_baeda3',      # cooling tank + cooling-device action, LSTM hidden 8 / 11 inputs
               'c7_phase3']      # six LSTM buildings with stochastic outages, central agent
@@ -32,7 +36,7 @@ def make_env(cfg, **kw):
     return CityLearnEnv(sch, data_source=src, **ov, **kw)
 
 
-@pytest.mark.parametrize('case', NON_LSTM_CASES + LSTM_CASES)
+@pytest.mark.parametrize('case', NON_LSTM_CASES + POW_TIE_CASES + LSTM_CASES)
 def test_single_env_matches_reference_traces(case):
     """num_envs=1, nested-list actions, fp64 flow: observations / district / physics identical to the reference run."""
     z, cfg, meta = load_golden(case)
@@ -64,15 +68,19 @@ def test_single_env_matches_reference_traces(case):
                 r = np.array(rew, dtype='float32')
                 # float32 rewards: 1 ulp per building; a central agent sums them (MARL terms of both signs cancel), so the sum gets the
                 # north-star tolerance of 1e-5
-                ok, w = within_scaled_tolerance(r, z['reward'][gi], 1.0, rtol=1e-5 if (lstm or env.central_agent) else 2e-7)
+                ok, w = within_scaled_tolerance(r, z['reward'][gi], 1.0, rtol=1e-5 if (lstm or env.central_agent or case in POW_TIE_CASES) else 2e-7)
                 assert ok, f'reward step {k}: {w}'
-                assert max_abs_diff(env.district[0].cpu().numpy(), z['district'][gi]) == 0.0, f'district step {k}'
+                ulp = case in POW_TIE_CASES
+                dd = max_abs_diff(env.district[0].cpu().numpy(), z['district'][gi])
+                assert dd == 0.0 or (ulp and dd <= 2.4e-7 * float(np.abs(z['district'][gi]).max())), f'district step {k}'
                 tr = env.trace[0].cpu().numpy()
                 for gn, dn in TRACE_TO_DYN.items():
                     ref = z['trace'][gi, :, tn.index(gn)]
                     # degraded capacity: float64 in the reference, float32 in the fixture (half an ulp, relative)
                     tol = 6e-8 * max(1.0, float(np.abs(ref).max())) if gn == 'electrical_storage_degraded_capacity' else \
                         (3e-5 if (lstm and gn == 'indoor_dry_bulb_temperature') else 0.0)
+                    if ulp and tol == 0.0:
+                        tol = 1.2e-7 * max(1.0, float(np.abs(ref).max()))          # one float32 ulp
                     assert max_abs_diff(tr[:, DYN[dn]], ref) <= tol, f'{gn} step {k}'
                 assert term == bool(z['terminated'][gi])
                 gi += 1

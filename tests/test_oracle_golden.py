@@ -5,7 +5,7 @@ import pytest
 from citylearn_b200 import schema as S
 from citylearn_b200.schema import DYN
 from citylearn_oracle import OracleEnv
-from helpers import TRACE_TO_DYN, actions_of, golden_cases, load_golden, max_abs_diff, spec_for
+from helpers import TRACE_TO_DYN, actions_of, golden_cases, load_golden, max_abs_diff, oracle_run, spec_for
 
 # Everything except the LSTM-predicted indoor temperature (torch vs NumPy float32 matmul order) and values derived from it
 # is reproduced to the last bit; the golden traces are stored as float32, hence the half-ulp allowances.
@@ -16,17 +16,49 @@ TOL = {
 }
 
 
+def _check(worst, lstm):
+    for k, v in worst.items():
+        if k == 'reward':
+            assert v <= (1e-5 if lstm else 1e-7), (k, v)      # comfort rewards amplify the LSTM's 1e-6 temperature differences
+        elif k == 'district':
+            assert v <= 0.0 if not lstm else v <= 1e-6, (k, v)
+        else:
+            assert v <= TOL.get(k, TOL['default']), (k, v)
+
+
+def _accumulate(worst, z, gi, tn, obs, rew, dist, dyn, k):
+    assert max_abs_diff(obs, z['obs'][gi]) == 0.0, f'obs at step {k}'
+    worst['reward'] = max(worst.get('reward', 0.0), max_abs_diff(rew, z['reward'][gi]) / max(1.0, float(np.nanmax(np.abs(z['reward'][gi])))))
+    worst['district'] = max(worst.get('district', 0.0), max_abs_diff(dist, z['district'][gi]))
+    for gn, dn in TRACE_TO_DYN.items():
+        ref = z['trace'][gi, :, tn.index(gn)]
+        if gn == 'electrical_storage_degraded_capacity':      # float64 in the reference, float32 in the fixture: half an ulp
+            d = float(np.max(np.abs(dyn[:, DYN[dn]] - ref) / np.maximum(1.0, np.abs(ref))))
+        else:
+            d = max_abs_diff(dyn[:, DYN[dn]].astype('float32'), ref)
+        worst[gn] = max(worst.get(gn, 0.0), d)
+
+
 @pytest.mark.parametrize('case', golden_cases())
 def test_oracle_reproduces_reference(case):
     z, cfg, meta = load_golden(case)
+    tn = cfg['trace_names']
+    worst = {}
+    if cfg['episodes'] == 1:
+        run = oracle_run(case)              # shared with test_evaluate.py
+        lstm = any(b.dynamics for b in run['spec'].buildings)
+        assert run['window'] == z['episode_window'][0].tolist()
+        assert max_abs_diff(run['reset_obs'], z['reset_obs'][0]) == 0.0
+        for gi, k in enumerate(z['steps']):
+            _accumulate(worst, z, gi, tn, run['obs'][k], run['reward'][k], run['district'][k], run['dyn'][k], int(k))
+        _check(worst, lstm)
+        return
     spec = spec_for(cfg)
     lstm = any(b.dynamics for b in spec.buildings)
-    env = OracleEnv(spec, 1)
-    tn = cfg['trace_names']
+    env = OracleEnv(spec, 1, libm_pow=True)      # the reference's `efficiency ** 0.5` is libm pow, not sqrt (see OracleEnv)
     acts = actions_of(z)
     tracker = S.EpisodeTracker(spec.simulation_start_time_step, spec.simulation_end_time_step)
     gi = 0
-    worst = {}
     for ep in range(cfg['episodes']):
         ets = spec.episode_time_steps if spec.episode_time_steps is not None else tracker.simulation_time_steps
         tracker.next_episode(ets, spec.rolling_episode_split, spec.random_episode_split, spec.random_seed)
@@ -36,27 +68,10 @@ def test_oracle_reproduces_reference(case):
         for k in range(acts.shape[1]):
             obs, rew, dist, dyn = env.step(acts[ep, k][None])
             if gi < len(z['steps']) and z['steps'][gi] == k and z['episode'][gi] == ep:
-                assert max_abs_diff(obs[0], z['obs'][gi]) == 0.0, f'obs at step {k}'
-                worst['reward'] = max(worst.get('reward', 0.0), max_abs_diff(rew[0], z['reward'][gi]) / max(1.0, float(np.nanmax(np.abs(z['reward'][gi])))))
-                worst['district'] = max(worst.get('district', 0.0), max_abs_diff(dist[0], z['district'][gi]))
-                for gn, dn in TRACE_TO_DYN.items():
-                    ref = z['trace'][gi, :, tn.index(gn)]
-                    if gn == 'electrical_storage_degraded_capacity':      # float64 in the reference, float32 in the fixture: half an ulp
-                        d = float(np.max(np.abs(dyn[0, :, DYN[dn]] - ref) / np.maximum(1.0, np.abs(ref))))
-                    else:
-                        d = max_abs_diff(dyn[0, :, DYN[dn]].astype('float32'), ref)
-                    worst[gn] = max(worst.get(gn, 0.0), d)
+                _accumulate(worst, z, gi, tn, obs[0], rew[0], dist[0], dyn[0], k)
                 gi += 1
     assert gi == len(z['steps'])
-    for k, v in worst.items():
-        if k == 'reward':
-            assert v <= (1e-5 if lstm else 1e-7), (k, v)      # comfort rewards amplify the LSTM's 1e-6 temperature differences
-        elif k == 'district':
-            assert v <= 0.0 if not lstm else v <= 1e-6, (k, v)
-        else:
-            assert v <= TOL.get(k, TOL['default']), (k, v)
-    if 'episode_reward_sum' in z.files and cfg['episodes'] == 1 and not lstm:
-        pass  # sums are covered step by step above
+    _check(worst, lstm)
 
 
 def test_oracle_vectorised_envs_are_independent():
