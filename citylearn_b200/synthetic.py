@@ -67,25 +67,83 @@ class SyntheticWideSource(DataSource):
 
     def write_directory(self, root: os.PathLike) -> Path:
         """Materialise the district as `root/schema.json` + CSV files (lossless decimal text)."""
-        root = Path(root)
-        root.mkdir(parents=True, exist_ok=True)
-        sch = self.schema()
-        files = {'weather.csv', 'carbon_intensity.csv', 'pricing.csv'} | {self.file_of(i) for i in range(self.n)}
-        for fn in sorted(files):
-            t = self.table(fn)
-            cols = list(t)
-            arr = np.stack([np.asarray(t[c], dtype='float64') for c in cols], axis=1)
-            with open(root / fn, 'w') as f:
-                f.write(','.join(cols) + '\n')
-                for r in arr:
-                    f.write(','.join('' if np.isnan(v) else repr(float(v)) for v in r) + '\n')
-        sch['root_directory'] = None
-        with open(root / 'schema.json', 'w') as f:
-            json.dump(sch, f, indent=1)
-        return root
+        return _write_directory(self, root)
+
+
+def _schema_files(sch: dict):
+    files = set()
+    for b in sch['buildings'].values():
+        for k in ('energy_simulation', 'weather', 'carbon_intensity', 'pricing'):
+            if b.get(k):
+                files.add(b[k])
+    return files
+
+
+def _write_directory(src: DataSource, root: os.PathLike) -> Path:
+    root = Path(root)
+    root.mkdir(parents=True, exist_ok=True)
+    sch = src.schema()
+    files = _schema_files(sch)
+    for fn in sorted(files):
+        t = src.table(fn)
+        cols = list(t)
+        arr = np.stack([np.asarray(t[c], dtype='float64') for c in cols], axis=1)
+        with open(root / fn, 'w') as f:
+            f.write(','.join(cols) + '\n')
+            for r in arr:
+                f.write(','.join('' if np.isnan(v) else repr(float(v)) for v in r) + '\n')
+    sch['root_directory'] = None
+    with open(root / 'schema.json', 'w') as f:
+        json.dump(sch, f, indent=1)
+    return root
 
 
 def make_wide_district(n_buildings: int = 1024, seed: int = 0):
     """(schema dict, data source) of the synthetic N-building district; pass both to `CityLearnEnv(schema, data_source=...)`."""
     src = SyntheticWideSource(n_buildings, seed)
     return src.schema(), src
+
+
+class SyntheticHeatingSource(DataSource):
+    """`citylearn_challenge_2020_climate_zone_1` with a heating season: no bundled dataset has space-heating demand, so the
+    heating heat pump, the heating tank and the reference's tank-capacity quirks (heating storage actions scale with the COOLING
+    tank, DHW storage actions with the HEATING tank, `building.py:1720, 1765`) would otherwise never run.  Every building serves
+    0.6 x its December-February cooling load as HEATING demand instead, and gets an autosized heating heat pump and an autosized heating tank;
+    the `heating_storage` action and `heating_storage_soc` observation are switched on.  Test / parity infrastructure, like
+    `SyntheticWideSource`."""
+
+    def __init__(self, base: Optional[DataSource] = None):
+        self.base = DataSet.get_source('citylearn_challenge_2020_climate_zone_1') if base is None else base
+
+    def root_directory(self):
+        return None
+
+    def schema(self) -> dict:
+        s = copy.deepcopy(self.base.schema())
+        s['observations']['heating_storage_soc']['active'] = True
+        s['actions']['heating_storage']['active'] = True
+        for b in s['buildings'].values():
+            b['heating_device'] = {'type': 'citylearn.energy_model.HeatPump', 'autosize': True,
+                                   'attributes': {'nominal_power': None, 'efficiency': 0.25, 'target_cooling_temperature': 8.0,
+                                                  'target_heating_temperature': 45.0}}
+            b['heating_storage'] = {'type': 'citylearn.energy_model.StorageTank', 'autosize': True, 'autosize_attributes': {'safety_factor': 1.5},
+                                    'attributes': {'capacity': None, 'loss_coefficient': 0.004}}
+        s['root_directory'] = None
+        return s
+
+    def table(self, filename: str) -> Dict[str, np.ndarray]:
+        t = dict(self.base.table(filename))
+        if 'cooling_demand' in t and 'heating_demand' in t:
+            # December-February become a heating season (the reference forbids cooling and heating in the same time step,
+            # citylearn/data.py:470-472): the cooling load of those months, scaled, is served as heat instead
+            cool = np.asarray(t['cooling_demand'], dtype='float32')
+            winter = np.isin(np.asarray(t['month']).astype(int), (12, 1, 2))
+            t['heating_demand'] = np.where(winter, np.float32(0.6) * cool, np.float32(0.0)).astype('float64')
+            t['cooling_demand'] = np.where(winter, np.float32(0.0), cool).astype('float64')
+        return t
+
+    def state_dict(self, filename: str):
+        return self.base.state_dict(filename)
+
+    def write_directory(self, root: os.PathLike) -> Path:
+        return _write_directory(self, root)

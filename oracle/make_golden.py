@@ -71,6 +71,11 @@ def make_env(CityLearnEnv, dataset, overrides=None, reward=None):
         sys.path.insert(0, str(HERE.parent))
         from citylearn_b200.synthetic import SyntheticWideSource
         root = SyntheticWideSource(int(dataset.rsplit('_', 1)[1])).write_directory(tempfile.mkdtemp(prefix='citylearn_wide_'))
+    elif dataset == 'synthetic_heating':
+        import tempfile
+        sys.path.insert(0, str(HERE.parent))
+        from citylearn_b200.synthetic import SyntheticHeatingSource
+        root = SyntheticHeatingSource().write_directory(tempfile.mkdtemp(prefix='citylearn_heating_'))
     else:
         root = DATASETS / dataset
     schema = json.load(open(root / 'schema.json'))
@@ -297,6 +302,9 @@ CASES = {
     'c6_baeda3': dict(dataset=BAEDA, overrides={'buildings': ['Building_1', 'Building_2', 'Building_3']}, steps=600, seed=8),
     # 32-building slice of the synthetic wide district (C4): pins the per-building path of the 1024-building runs
     'c4_slice32': dict(dataset='synthetic_wide_32', steps=200, seed=10),
+    # 2020 district with a synthetic heating season: heating heat pump + heating tank + the tank-capacity quirks (no bundled dataset has them)
+    'c8_heating': dict(dataset='synthetic_heating', steps=400, seed=18),
+    'c8_heating_central_marl': dict(dataset='synthetic_heating', overrides={'central_agent': True}, reward=MARL, steps=120, seed=19),
     # 6 LSTM buildings with stochastic outages, central agent, full 2207-step episode
     'c7_phase3': dict(dataset=C23P3, steps=None, record=sparse, seed=9),
 }

@@ -19,7 +19,9 @@ pytestmark = pytest.mark.gpu
 NON_LSTM_CASES = ['c1_phase1_300', 'c1_phase1_central', 'c1_episodes', 'c1_subhour', 'c2_marl', 'c2_isac', 'c2_solar_penalty', 'c2_central_exp2', 'c2_year',
                   # 2020 schema: autosized heat pumps / heaters / tanks, cooling + DHW tank actions
                   'c6_tanks_2020', 'c6_tanks_2020_marl_central',
-                  'c4_slice32']      # first 32 buildings of the synthetic wide district (BASELINE configs[3])
+                  'c4_slice32',      # first 32 buildings of the synthetic wide district (BASELINE configs[3])
+                  # 2020 district with a synthetic heating season: heating heat pump, heating tank, tank-capacity quirks
+                  'c8_heating', 'c8_heating_central_marl']
 # 2023 schema: heat pump + electric heater + DHW tank + battery + outages + LSTM indoor-temperature dynamics (BASELINE configs[2])
 # Cases in which the reference's `efficiency ** 0.5` (libm pow, not correctly rounded) differs from sqrt by one float64 ulp AND the
 # affected energy balance sits on a float32 rounding tie (oracle/citylearn_oracle.py `libm_pow`): the kernel computes the correctly

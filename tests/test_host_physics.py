@@ -67,10 +67,12 @@ CHECKED = ['electrical_storage_soc', 'electrical_storage_energy_balance', 'elect
            'net_electricity_consumption', 'net_electricity_consumption_cost', 'net_electricity_consumption_emission',
            'cooling_storage_soc', 'dhw_storage_soc', 'dhw_storage_energy_balance', 'cooling_electricity_consumption',
            'heating_electricity_consumption', 'dhw_electricity_consumption', 'cooling_demand', 'dhw_demand',
-           'non_shiftable_load_electricity_consumption']
+           'non_shiftable_load_electricity_consumption', 'heating_storage_soc', 'heating_storage_energy_balance', 'heating_demand',
+           'cooling_storage_energy_balance', 'dhw_storage_soc']
 
 
-@pytest.mark.parametrize('case', ['c1_phase1_300', 'c1_subhour', 'c2_marl', 'c3_marl', 'c6_tanks_2020_marl_central', 'c6_baeda3'])
+@pytest.mark.parametrize('case', ['c1_phase1_300', 'c1_subhour', 'c2_marl', 'c3_marl', 'c6_tanks_2020_marl_central', 'c6_baeda3',
+                                  'c8_heating', 'c8_heating_central_marl'])
 def test_fp64_flow_is_bit_exact(hostlib, case):
     z, cfg, _ = load_golden(case)
     spec = spec_for(cfg)
