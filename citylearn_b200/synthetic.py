@@ -92,6 +92,11 @@ def _write_directory(src: DataSource, root: os.PathLike) -> Path:
             f.write(','.join(cols) + '\n')
             for r in arr:
                 f.write(','.join('' if np.isnan(v) else repr(float(v)) for v in r) + '\n')
+    for b in sch['buildings'].values():          # LSTM dynamics weights (`.pth` state dicts, citylearn/dynamics.py:112-127)
+        fn = ((b.get('dynamics') or {}).get('attributes') or {}).get('filename')
+        if fn:
+            import torch
+            torch.save({k: torch.as_tensor(np.asarray(v)) for k, v in src.state_dict(fn).items()}, root / fn)
     sch['root_directory'] = None
     with open(root / 'schema.json', 'w') as f:
         json.dump(sch, f, indent=1)
@@ -140,6 +145,56 @@ class SyntheticHeatingSource(DataSource):
             winter = np.isin(np.asarray(t['month']).astype(int), (12, 1, 2))
             t['heating_demand'] = np.where(winter, np.float32(0.6) * cool, np.float32(0.0)).astype('float64')
             t['cooling_demand'] = np.where(winter, np.float32(0.0), cool).astype('float64')
+        return t
+
+    def state_dict(self, filename: str):
+        return self.base.state_dict(filename)
+
+    def write_directory(self, root: os.PathLike) -> Path:
+        return _write_directory(self, root)
+
+
+class SyntheticDualModeSource(DataSource):
+    """`baeda_3dem` (buildings 1-3, LSTM dynamics) driven through ONE signed `cooling_or_heating_device` action
+    (`building.py:1550-1553`: negative = cooling, positive = heating share of the nominal power) instead of `cooling_device`.
+    The night hours (0-5 h) in which the HVAC is off become heating hours (`hvac_mode = 2`, a synthetic heating demand of 0.4 x the
+    building's mean cooling load) served by an autosized heating heat pump, and every 7th cooling hour runs in auto mode
+    (`hvac_mode = 3`).  The only reference datasets using this action need PV autosizing through PySAM.  Parity infrastructure."""
+
+    BUILDINGS = ['Building_1', 'Building_2', 'Building_3']
+
+    def __init__(self, base: Optional[DataSource] = None):
+        self.base = DataSet.get_source('baeda_3dem') if base is None else base
+
+    def root_directory(self):
+        return None
+
+    def schema(self) -> dict:
+        s = copy.deepcopy(self.base.schema())
+        s['buildings'] = {k: v for k, v in s['buildings'].items() if k in self.BUILDINGS}
+        s['actions']['cooling_device']['active'] = False
+        s['actions']['cooling_or_heating_device']['active'] = True
+        for b in s['buildings'].values():
+            # oversized: the reference books the ideal load at t = 0 twice (SURVEY A.6), which eats into the heat pump's head-room
+            b['heating_device'] = {'type': 'citylearn.energy_model.HeatPump', 'autosize': True, 'autosize_attributes': {'safety_factor': 3.0},
+                                   'attributes': {'nominal_power': None, 'efficiency': 0.25, 'target_cooling_temperature': 8.0,
+                                                  'target_heating_temperature': 45.0}}
+            b['inactive_actions'] = [a for a in b.get('inactive_actions', []) if a != 'cooling_or_heating_device']
+        s['root_directory'] = None
+        return s
+
+    def table(self, filename: str) -> Dict[str, np.ndarray]:
+        t = dict(self.base.table(filename))
+        if 'hvac_mode' in t and 'cooling_demand' in t:
+            cool = np.nan_to_num(np.asarray(t['cooling_demand'], dtype='float32'))
+            mode = np.nan_to_num(np.asarray(t['hvac_mode'])).astype(int)
+            hour = np.asarray(t['hour']).astype(int)
+            heat_rows = (mode == 0) & (hour <= 5) & (cool == 0)
+            level = np.float32(0.4) * np.float32(cool[cool > 0].mean())
+            t['heating_demand'] = np.where(heat_rows, level, np.float32(0.0)).astype('float64')
+            auto_rows = np.zeros(len(mode), dtype=bool)
+            auto_rows[np.nonzero(mode == 1)[0][::7]] = True
+            t['hvac_mode'] = np.where(heat_rows, 2, np.where(auto_rows, 3, mode)).astype('float64')
         return t
 
     def state_dict(self, filename: str):

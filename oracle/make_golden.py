@@ -71,6 +71,11 @@ def make_env(CityLearnEnv, dataset, overrides=None, reward=None):
         sys.path.insert(0, str(HERE.parent))
         from citylearn_b200.synthetic import SyntheticWideSource
         root = SyntheticWideSource(int(dataset.rsplit('_', 1)[1])).write_directory(tempfile.mkdtemp(prefix='citylearn_wide_'))
+    elif dataset == 'synthetic_dual_mode':
+        import tempfile
+        sys.path.insert(0, str(HERE.parent))
+        from citylearn_b200.synthetic import SyntheticDualModeSource
+        root = SyntheticDualModeSource().write_directory(tempfile.mkdtemp(prefix='citylearn_dual_'))
     elif dataset == 'synthetic_heating':
         import tempfile
         sys.path.insert(0, str(HERE.parent))
@@ -305,6 +310,8 @@ CASES = {
     # 2020 district with a synthetic heating season: heating heat pump + heating tank + the tank-capacity quirks (no bundled dataset has them)
     'c8_heating': dict(dataset='synthetic_heating', steps=400, seed=18),
     'c8_heating_central_marl': dict(dataset='synthetic_heating', overrides={'central_agent': True}, reward=MARL, steps=120, seed=19),
+    # LSTM buildings driven through the signed cooling_or_heating_device action, heating + auto hvac modes
+    'c9_dual_mode': dict(dataset='synthetic_dual_mode', steps=500, seed=20),
     # 6 LSTM buildings with stochastic outages, central agent, full 2207-step episode
     'c7_phase3': dict(dataset=C23P3, steps=None, record=sparse, seed=9),
 }

@@ -46,6 +46,9 @@ def schema_for(cfg):
     if cfg['dataset'].startswith('synthetic_wide_'):
         from citylearn_b200.synthetic import SyntheticWideSource
         src = SyntheticWideSource(int(cfg['dataset'].rsplit('_', 1)[1]))
+    elif cfg['dataset'] == 'synthetic_dual_mode':
+        from citylearn_b200.synthetic import SyntheticDualModeSource
+        src = SyntheticDualModeSource()
     elif cfg['dataset'] == 'synthetic_heating':
         from citylearn_b200.synthetic import SyntheticHeatingSource
         src = SyntheticHeatingSource()
