@@ -11,9 +11,14 @@ sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
 from citylearn_b200.data import DirectorySource, write_pack  # noqa: E402
 
 DEFAULT = [
-    'citylearn_challenge_2022_phase_1',
-    'citylearn_challenge_2022_phase_all',
-    'citylearn_challenge_2023_phase_2_local_evaluation',
+    'baeda_3dem',
+    'citylearn_challenge_2020_climate_zone_1', 'citylearn_challenge_2020_climate_zone_2', 'citylearn_challenge_2020_climate_zone_3',
+    'citylearn_challenge_2020_climate_zone_4', 'citylearn_challenge_2021',
+    'citylearn_challenge_2022_phase_1', 'citylearn_challenge_2022_phase_2', 'citylearn_challenge_2022_phase_3', 'citylearn_challenge_2022_phase_all',
+    'citylearn_challenge_2023_phase_1', 'citylearn_challenge_2023_phase_2_local_evaluation',
+    'citylearn_challenge_2023_phase_2_online_evaluation_1', 'citylearn_challenge_2023_phase_2_online_evaluation_2',
+    'citylearn_challenge_2023_phase_2_online_evaluation_3',
+    'citylearn_challenge_2023_phase_3_1', 'citylearn_challenge_2023_phase_3_2', 'citylearn_challenge_2023_phase_3_3',
 ]
 
 if __name__ == '__main__':
