@@ -521,14 +521,3 @@ def test_observation_table_with_normalized_wrapper(monkeypatch):
     make = lambda: W.NormalizedSpaceWrapper(CityLearnEnv('citylearn_challenge_2022_phase_1', num_envs=8,          # noqa: E731
                                                          buildings=['Building_1', 'Building_2', 'Building_3', 'Building_4']))
     _table_vs_gather(make, 40, monkeypatch)
-
-
-@pytest.mark.xfail(strict=False, reason='fixture added after the round\'s GPU budget was spent: pinned for the oracle on CPU, not yet run on hardware')
-def test_dual_mode_cooling_or_heating_device_matches_reference():
-    """`cooling_or_heating_device` (one signed action for both heat pumps), hvac modes 2 / 3, heating heat pump under LSTM dynamics
-    (citylearn_b200.synthetic.SyntheticDualModeSource).  The oracle reproduces the reference's trace (tests/test_oracle_golden.py)."""
-    LSTM_CASES.append('c9_dual_mode')
-    try:
-        test_single_env_matches_reference_traces('c9_dual_mode')
-    finally:
-        LSTM_CASES.remove('c9_dual_mode')
