@@ -264,6 +264,53 @@ WRAPPER_CASES = {
 }
 
 
+def run_meta_fuzz(CityLearnEnv, n=28, seed=123):
+    """Loader fuzz: random combinations of the constructor overrides -> the reference's names, spaces and episode windows."""
+    rng = np.random.RandomState(seed)
+    datasets = [P1, PALL, C23, Z20, 'citylearn_challenge_2023_phase_3_1', 'citylearn_challenge_2022_phase_3']
+    cases = []
+    for i in range(n):
+        ds = datasets[i % len(datasets)]
+        sch = json.load(open(DATASETS / ds / 'schema.json'))
+        names = list(sch['buildings'])
+        obs_names = [k for k, v in sch['observations'].items() if v['active']]
+        ov = {}
+        if rng.rand() < 0.5:
+            ov['central_agent'] = bool(rng.rand() < 0.5)
+        if rng.rand() < 0.5:
+            k = rng.randint(1, len(names) + 1)
+            ov['buildings'] = sorted(rng.choice(len(names), size=k, replace=False).tolist()) if rng.rand() < 0.5 else \
+                [names[j] for j in sorted(rng.choice(len(names), size=k, replace=False).tolist())]
+        if rng.rand() < 0.5:
+            ov['inactive_observations'] = [obs_names[j] for j in sorted(rng.choice(len(obs_names), size=rng.randint(1, 5), replace=False).tolist())]
+        end = sch['simulation_end_time_step']
+        if rng.rand() < 0.6:
+            a = int(rng.randint(0, end // 2)); b = int(rng.randint(a + 48, end + 1))
+            ov['simulation_start_time_step'], ov['simulation_end_time_step'] = a, b
+            if rng.rand() < 0.7:
+                ov['episode_time_steps'] = int(rng.randint(24, max(25, (b - a) // 2)))
+                ov['rolling_episode_split'] = bool(rng.rand() < 0.5)
+        if rng.rand() < 0.3:
+            ov['shared_observations'] = ['month', 'hour'] if 'month' in obs_names else ['hour']
+        try:
+            env = make_env(CityLearnEnv, ds, ov, None)
+            windows = []
+            for ep in range(3):
+                env.reset()
+                windows.append([env.episode_tracker.episode_start_time_step, env.episode_tracker.episode_end_time_step])
+        except Exception as e:      # e.g. ReliabilityMetricsPowerOutage.get_signals breaks on some episode lengths (power_outage.py:154)
+            print('meta', i, ds, ov, 'reference raised', repr(e)[:80])
+            continue
+        cases.append({'dataset': ds, 'overrides': ov, 'observation_names': env.observation_names, 'action_names': env.action_names,
+                      'observation_low': [s.low.tolist() for s in env.observation_space], 'observation_high': [s.high.tolist() for s in env.observation_space],
+                      'action_low': [s.low.tolist() for s in env.action_space], 'action_high': [s.high.tolist() for s in env.action_space],
+                      'central_agent': env.central_agent, 'shared_observations': env.shared_observations, 'windows': windows,
+                      'building_names': [b.name for b in env.buildings]})
+        print('meta', i, ds, ov)
+    with open(OUT / 'meta_fuzz.json', 'w') as f:
+        json.dump({'numpy': np.__version__, 'cases': cases}, f)
+
+
 def sparse(K):
     return sorted(set(list(range(0, 48)) + list(range(0, K, 41)) + list(range(K - 48, K))))
 
@@ -318,8 +365,11 @@ CASES = {
 
 if __name__ == '__main__':
     CityLearnEnv = import_reference()
-    todo = sys.argv[1:] or (list(CASES) + list(WRAPPER_CASES))
+    todo = sys.argv[1:] or (list(CASES) + list(WRAPPER_CASES) + ['meta_fuzz'])
     for n in todo:
+        if n == 'meta_fuzz':
+            run_meta_fuzz(CityLearnEnv)
+            continue
         if n in WRAPPER_CASES:
             run_wrapper_case(CityLearnEnv, n, **WRAPPER_CASES[n])
         else:

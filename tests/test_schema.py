@@ -118,3 +118,32 @@ def test_every_bundled_dataset_loads_and_steps():
             a = (lo + rng.uniform(size=(2, spec.action_dim)) * (hi - lo)).astype('float32')
             obs, rew, dist, dyn = env.step(a)
             assert np.isfinite(rew).all() and np.isfinite(dist).all(), name
+
+
+def test_loader_fuzz_matches_reference_metadata():
+    """24 random combinations of constructor overrides (central agent, building subsets by index / name, inactive observations,
+    simulation windows, episode splits, shared observations) over six datasets: names, spaces and the first three episode windows
+    equal what the unmodified reference reports (tests/golden/meta_fuzz.json, oracle/make_golden.py meta_fuzz)."""
+    import json
+    from helpers import GOLDEN
+    cases = json.load(open(GOLDEN / 'meta_fuzz.json'))['cases']
+    assert len(cases) >= 20
+    for c in cases:
+        spec = S.load(c['dataset'], **c['overrides'])
+        tag = (c['dataset'], c['overrides'])
+        assert [b.name for b in spec.buildings] == c['building_names'], tag
+        assert spec.central_agent == c['central_agent'], tag
+        entries, _ = S.observation_layout(spec)
+        assert [n for _, n in entries] == [n for row in c['observation_names'] for n in row], tag
+        assert [n for b in spec.buildings for n in b.active_actions] == [n for row in c['action_names'] for n in row], tag
+        lo = {(bi, n): v for bi, b in enumerate(spec.buildings) for n, v in zip(b.active_observations, b.observation_low)}
+        hi = {(bi, n): v for bi, b in enumerate(spec.buildings) for n, v in zip(b.active_observations, b.observation_high)}
+        np.testing.assert_allclose([lo[e] for e in entries], [v for row in c['observation_low'] for v in row], rtol=1e-6, err_msg=str(tag))
+        np.testing.assert_allclose([hi[e] for e in entries], [v for row in c['observation_high'] for v in row], rtol=1e-6, err_msg=str(tag))
+        np.testing.assert_allclose([v for b in spec.buildings for v in b.action_low], [v for row in c['action_low'] for v in row], rtol=1e-6, err_msg=str(tag))
+        np.testing.assert_allclose([v for b in spec.buildings for v in b.action_high], [v for row in c['action_high'] for v in row], rtol=1e-6, err_msg=str(tag))
+        tr = S.EpisodeTracker(spec.simulation_start_time_step, spec.simulation_end_time_step)
+        for w in c['windows']:
+            ets = spec.episode_time_steps if spec.episode_time_steps is not None else tr.simulation_time_steps
+            tr.next_episode(ets, spec.rolling_episode_split, spec.random_episode_split, spec.random_seed)
+            assert [tr.episode_start_time_step, tr.episode_end_time_step] == w, tag
