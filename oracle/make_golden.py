@@ -311,6 +311,69 @@ def run_meta_fuzz(CityLearnEnv, n=28, seed=123):
         json.dump({'numpy': np.__version__, 'cases': cases}, f)
 
 
+def run_trace_fuzz(CityLearnEnv, seed=321):
+    """Physics fuzz: short reference runs under random override combinations (sub-windows, building subsets, central agent, rewards);
+    only observations / rewards / district sums are stored."""
+    rng = np.random.RandomState(seed)
+    rewards = [None, MARL, {'type': 'citylearn.reward_function.IndependentSACReward', 'attributes': {}},
+               {'type': 'citylearn.reward_function.SolarPenaltyReward', 'attributes': {}},
+               {'type': 'citylearn.reward_function.RewardFunction', 'attributes': {'exponent': 1.5}}]
+    plan = [(P1, 40), (PALL, 30), (C23, 80), (Z20, 40), ('citylearn_challenge_2023_phase_3_1', 80), ('citylearn_challenge_2022_phase_3', 40),
+            (C23, 60), (Z20, 40), (PALL, 30), ('citylearn_challenge_2023_phase_1', 80), ('citylearn_challenge_2020_climate_zone_3', 40), (P1, 40)]
+    cases = []
+    for i, (ds, steps) in enumerate(plan):
+        sch = json.load(open(DATASETS / ds / 'schema.json'))
+        names = list(sch['buildings'])
+        ov = {'central_agent': bool(rng.rand() < 0.5)}
+        if rng.rand() < 0.6 and len(names) > 2:
+            k = rng.randint(2, len(names) + 1)
+            ov['buildings'] = [names[j] for j in sorted(rng.choice(len(names), size=k, replace=False).tolist())]
+        end = sch['simulation_end_time_step']
+        a = int(rng.randint(0, end // 2))
+        ov['simulation_start_time_step'], ov['simulation_end_time_step'] = a, int(min(end, a + rng.randint(steps + 30, steps + 400)))
+        reward = rewards[rng.randint(len(rewards))]
+        if 'LSTM' in json.dumps(sch['buildings'][names[0]].get('type', '')) and reward is not None and 'SolarPenalty' in reward['type']:
+            reward = None
+        try:
+            env = make_env(CityLearnEnv, ds, ov, reward)
+            obs, _ = env.reset()
+        except Exception as e:
+            print('trace', i, ds, ov, 'reference raised', repr(e)[:80])
+            continue
+        lo = np.concatenate([np.asarray(b.action_space.low, dtype='float64') for b in env.buildings])
+        hi = np.concatenate([np.asarray(b.action_space.high, dtype='float64') for b in env.buildings])
+        sizes = [b.action_space.shape[0] for b in env.buildings]
+        K = min(steps, env.time_steps - 1)
+        actions = (lo + rng.uniform(size=(K, len(lo))) * (hi - lo)).astype('float32')
+        rec = {'dataset': ds, 'overrides': ov, 'reward': reward, 'reset_obs': [float(np.float32(v)) for v in flat(obs)], 'actions': actions.tolist(), 'obs': [], 'reward_values': [], 'district': []}
+        failed = None
+        for k in range(K):
+            a_ = [float(x) for x in actions[k]]
+            if env.central_agent:
+                act = [a_]
+            else:
+                act, o = [], 0
+                for n_ in sizes:
+                    act.append(a_[o:o + n_]); o += n_
+            try:
+                obs, rew, term, _, _ = env.step(act)
+            except AssertionError as e:       # the reference's own limit checks (e.g. t = 0 double counting vs an autosized device)
+                failed = repr(e)[:80]
+                break
+            rec['obs'].append([float(np.float32(v)) for v in flat(obs)])
+            rec['reward_values'].append([float(np.float32(v)) for v in flat(rew)])
+            rec['district'].append([float(np.float32(env.net_electricity_consumption[k])), float(np.float32(env.net_electricity_consumption_cost[k])),
+                                    float(np.float32(env.net_electricity_consumption_emission[k]))])
+        if failed:
+            print('trace', i, ds, ov, 'reference asserted', failed)
+            continue
+        cases.append(rec)
+        print('trace', i, ds, ov, None if reward is None else reward['type'].split('.')[-1], K)
+    import gzip
+    with gzip.open(OUT / 'trace_fuzz.json.gz', 'wt') as f:
+        json.dump({'numpy': np.__version__, 'cases': cases}, f)
+
+
 def sparse(K):
     return sorted(set(list(range(0, 48)) + list(range(0, K, 41)) + list(range(K - 48, K))))
 
@@ -365,8 +428,11 @@ CASES = {
 
 if __name__ == '__main__':
     CityLearnEnv = import_reference()
-    todo = sys.argv[1:] or (list(CASES) + list(WRAPPER_CASES) + ['meta_fuzz'])
+    todo = sys.argv[1:] or (list(CASES) + list(WRAPPER_CASES) + ['meta_fuzz', 'trace_fuzz'])
     for n in todo:
+        if n == 'trace_fuzz':
+            run_trace_fuzz(CityLearnEnv)
+            continue
         if n == 'meta_fuzz':
             run_meta_fuzz(CityLearnEnv)
             continue

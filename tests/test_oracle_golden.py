@@ -89,3 +89,31 @@ def test_oracle_vectorised_envs_are_independent():
             obs, rew, dist, dyn = single.step(acts[k, e][None])
             assert np.array_equal(rew[0], batched[k][1][e])
             assert np.array_equal(dyn[0], batched[k][3][e], equal_nan=True)
+
+
+def test_oracle_matches_fuzzed_reference_runs():
+    """Short reference runs under random override combinations (mid-year sub-windows, building subsets, central agent, different
+    rewards; tests/golden/trace_fuzz.json.gz from oracle/make_golden.py trace_fuzz): observations exact, district sums exact
+    (1e-6 with LSTM buildings), rewards to float32 resolution."""
+    import gzip
+    import json
+    from helpers import GOLDEN, schema_for
+    cases = json.load(gzip.open(GOLDEN / 'trace_fuzz.json.gz', 'rt'))['cases']
+    assert len(cases) >= 6
+    for c in cases:
+        sch, src, ov = schema_for({'dataset': c['dataset'], 'reward': c['reward'], 'overrides': c['overrides']})
+        spec = S.load(sch, data_source=src, **ov)
+        lstm = any(b.dynamics for b in spec.buildings)
+        env = OracleEnv(spec, 1, libm_pow=True)
+        tr = S.EpisodeTracker(spec.simulation_start_time_step, spec.simulation_end_time_step)
+        tr.next_episode(tr.simulation_time_steps, spec.rolling_episode_split, spec.random_episode_split, spec.random_seed)
+        tag = (c['dataset'], c['overrides'])
+        obs0 = env.reset(tr.episode_start_time_step, tr.episode_time_steps)
+        assert max_abs_diff(obs0[0].astype('float32'), np.array(c['reset_obs'], dtype='float32')) == 0.0, tag
+        acts = np.array(c['actions'], dtype='float32')
+        for k in range(len(acts)):
+            obs, rew, dist, _ = env.step(acts[k][None])
+            assert max_abs_diff(obs[0].astype('float32'), np.array(c['obs'][k], dtype='float32')) == 0.0, (tag, k)
+            ref_r = np.array(c['reward_values'][k], dtype='float32')
+            assert max_abs_diff(rew[0].astype('float32'), ref_r) <= (1e-5 if lstm else 2e-7) * max(1.0, float(np.abs(ref_r).max())), (tag, k)
+            assert max_abs_diff(dist[0].astype('float32'), np.array(c['district'][k], dtype='float32')) <= (1e-6 if lstm else 0.0), (tag, k)
