@@ -13,11 +13,10 @@ stores float32 and is lossless with respect to what the reference computes with.
 """
 from __future__ import annotations
 
-import io
 import json
 import os
 from pathlib import Path
-from typing import Dict, List, Mapping, Optional
+from typing import Dict, List, Optional
 
 import numpy as np
 

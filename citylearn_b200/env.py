@@ -21,8 +21,7 @@ terminated / truncated (all envs advance in lock-step).
 from __future__ import annotations
 
 import importlib
-import math
-from typing import Any, Dict, List, Mapping, Optional, Sequence, Tuple, Union
+from typing import Any, Dict, List, Mapping, Optional, Tuple, Union
 
 import numpy as np
 import torch

@@ -13,7 +13,7 @@ Two things differ, both forced by batching:
 """
 from __future__ import annotations
 
-from typing import Any, List, Mapping, Tuple, Union
+from typing import Any, List, Mapping, Tuple
 
 import torch
 

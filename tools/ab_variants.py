@@ -1,6 +1,5 @@
 """A/B timing of kernel build variants (citylearn_b200/variants/*.so) on the C2 workload: one subprocess per (variant, precision)
 so that each loads its own library (CL_B200_LIB).  Prints µs/step of a K-step cl_rollout, best of 3."""
-import json
 import os
 import subprocess
 import sys
