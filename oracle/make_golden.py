@@ -311,15 +311,15 @@ def run_meta_fuzz(CityLearnEnv, n=28, seed=123):
         json.dump({'numpy': np.__version__, 'cases': cases}, f)
 
 
-def run_trace_fuzz(CityLearnEnv, seed=321):
+def run_trace_fuzz(CityLearnEnv, seed=321, plan=None, out_name='trace_fuzz.json.gz', sub_windows=True):
     """Physics fuzz: short reference runs under random override combinations (sub-windows, building subsets, central agent, rewards);
     only observations / rewards / district sums are stored."""
     rng = np.random.RandomState(seed)
     rewards = [None, MARL, {'type': 'citylearn.reward_function.IndependentSACReward', 'attributes': {}},
                {'type': 'citylearn.reward_function.SolarPenaltyReward', 'attributes': {}},
                {'type': 'citylearn.reward_function.RewardFunction', 'attributes': {'exponent': 1.5}}]
-    plan = [(P1, 40), (PALL, 30), (C23, 80), (Z20, 40), ('citylearn_challenge_2023_phase_3_1', 80), ('citylearn_challenge_2022_phase_3', 40),
-            (C23, 60), (Z20, 40), (PALL, 30), ('citylearn_challenge_2023_phase_1', 80), ('citylearn_challenge_2020_climate_zone_3', 40), (P1, 40)]
+    plan = plan or [(P1, 40), (PALL, 30), (C23, 80), (Z20, 40), ('citylearn_challenge_2023_phase_3_1', 80), ('citylearn_challenge_2022_phase_3', 40),
+                    (C23, 60), (Z20, 40), (PALL, 30), ('citylearn_challenge_2023_phase_1', 80), ('citylearn_challenge_2020_climate_zone_3', 40), (P1, 40)]
     cases = []
     for i, (ds, steps) in enumerate(plan):
         sch = json.load(open(DATASETS / ds / 'schema.json'))
@@ -329,8 +329,9 @@ def run_trace_fuzz(CityLearnEnv, seed=321):
             k = rng.randint(2, len(names) + 1)
             ov['buildings'] = [names[j] for j in sorted(rng.choice(len(names), size=k, replace=False).tolist())]
         end = sch['simulation_end_time_step']
-        a = int(rng.randint(0, end // 2))
-        ov['simulation_start_time_step'], ov['simulation_end_time_step'] = a, int(min(end, a + rng.randint(steps + 30, steps + 400)))
+        if sub_windows:
+            a = int(rng.randint(0, end // 2))
+            ov['simulation_start_time_step'], ov['simulation_end_time_step'] = a, int(min(end, a + rng.randint(steps + 30, steps + 400)))
         reward = rewards[rng.randint(len(rewards))]
         if 'LSTM' in json.dumps(sch['buildings'][names[0]].get('type', '')) and reward is not None and 'SolarPenalty' in reward['type']:
             reward = None
@@ -370,7 +371,7 @@ def run_trace_fuzz(CityLearnEnv, seed=321):
         cases.append(rec)
         print('trace', i, ds, ov, None if reward is None else reward['type'].split('.')[-1], K)
     import gzip
-    with gzip.open(OUT / 'trace_fuzz.json.gz', 'wt') as f:
+    with gzip.open(OUT / out_name, 'wt') as f:
         json.dump({'numpy': np.__version__, 'cases': cases}, f)
 
 
@@ -428,10 +429,17 @@ CASES = {
 
 if __name__ == '__main__':
     CityLearnEnv = import_reference()
-    todo = sys.argv[1:] or (list(CASES) + list(WRAPPER_CASES) + ['meta_fuzz', 'trace_fuzz'])
+    todo = sys.argv[1:] or (list(CASES) + list(WRAPPER_CASES) + ['meta_fuzz', 'trace_fuzz', 'trace_datasets'])
     for n in todo:
         if n == 'trace_fuzz':
             run_trace_fuzz(CityLearnEnv)
+            continue
+        if n == 'trace_datasets':        # every other bundled dataset family from its first time step (full windows)
+            run_trace_fuzz(CityLearnEnv, seed=77, out_name='trace_datasets.json.gz', sub_windows=False, plan=[
+                ('citylearn_challenge_2021', 60), ('citylearn_challenge_2020_climate_zone_2', 60), ('citylearn_challenge_2020_climate_zone_4', 60),
+                ('citylearn_challenge_2022_phase_2', 60), ('citylearn_challenge_2023_phase_2_online_evaluation_1', 60),
+                ('citylearn_challenge_2023_phase_2_online_evaluation_2', 60), ('citylearn_challenge_2023_phase_2_online_evaluation_3', 60),
+                ('citylearn_challenge_2023_phase_3_2', 60), ('citylearn_challenge_2023_phase_3_3', 60)])
             continue
         if n == 'meta_fuzz':
             run_meta_fuzz(CityLearnEnv)

@@ -91,14 +91,15 @@ def test_oracle_vectorised_envs_are_independent():
             assert np.array_equal(dyn[0], batched[k][3][e], equal_nan=True)
 
 
-def test_oracle_matches_fuzzed_reference_runs():
+@pytest.mark.parametrize('fixture', ['trace_fuzz.json.gz', 'trace_datasets.json.gz'])
+def test_oracle_matches_fuzzed_reference_runs(fixture):
     """Short reference runs under random override combinations (mid-year sub-windows, building subsets, central agent, different
     rewards; tests/golden/trace_fuzz.json.gz from oracle/make_golden.py trace_fuzz): observations exact, district sums exact
     (1e-6 with LSTM buildings), rewards to float32 resolution."""
     import gzip
     import json
     from helpers import GOLDEN, schema_for
-    cases = json.load(gzip.open(GOLDEN / 'trace_fuzz.json.gz', 'rt'))['cases']
+    cases = json.load(gzip.open(GOLDEN / fixture, 'rt'))['cases']      # trace_datasets: every other bundled dataset from t = 0
     assert len(cases) >= 6
     for c in cases:
         sch, src, ov = schema_for({'dataset': c['dataset'], 'reward': c['reward'], 'overrides': c['overrides']})
