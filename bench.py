@@ -6,16 +6,24 @@ Workload (BASELINE.json configs[1]): citylearn_challenge_2022_phase_all, 17 buil
 A "step" is one environment time step of all 17 x 4096 units of a rank: actions in, state update, district sums, reward,
 observation at t+1 out.  Metric: building-env steps / s (whole job, all ranks).
 
-  value     device-resident: K steps enqueued by ONE cl_rollout call (actions [K,E,A] already in HBM, every step writes
-            its own observation / reward slab, so the K * 7.8 MB output stream is larger than the 126 MB L2),
-            timed with CUDA events on the launch stream, max over ranks.
-  e2e       the public API with HOST buffers: env.step_host(ndarray) -> pinned H2D of the actions, kernel, D2H of the
-            observations and rewards, every step.
-  roofline  HBM: algorithmic bytes per launch / average launch duration of the step kernel over the timed region.
-  cpu_baseline  the NumPy oracle (a port of the reference algorithm, oracle/citylearn_oracle.py) on a bounded sample.
+  value     device-resident: R back-to-back `cl_rollout` launches of EXACTLY K steps each (actions [K,E,A] already in HBM, every
+            step writes its own observation / reward slab, so a launch's K * 7.8 MB output stream is larger than the 126 MB L2),
+            each launch bracketed by CUDA events on the launch stream; the launches are queued without host synchronisation, so
+            host launch latency is outside the brackets of all but the first.  `value` / `ms_per_step` come from the MEDIAN
+            launch (max over ranks); min / max / first are reported beside it.
+  e2e       the public API with HOST buffers, K steps: env.step_host(ndarray) -> pinned H2D of the actions, kernel, D2H of the
+            rewards + the observation row (reference-parity observation rows are identical for every env, so one row crosses
+            PCIe and the host gets a broadcast view; `e2e_full_observations` is the same loop with the full [E, L] copy).
+  roofline  HBM: bytes a rollout launch MOVES (actions + observations + rewards + district sums; the unit state stays in
+            registers between the steps of a launch) / median launch duration.
+  cpu_baseline  the UNMODIFIED reference (oracle/_ref, installed by oracle/build_ref.py) on one host core, when present; else the
+            NumPy oracle port.
+  extra     (N = 1, or --extras) BASELINE configs[2] (C3: 3 LSTM buildings x 65 536 envs, MARL, against a measured FP32-FMA
+            peak), configs[3] per-GPU share (C4: synthetic 1024 buildings x 1024 envs, full-year rollout) and configs[1] with
+            stale_observations=False (fresh observations) ride on the same JSON line under "extra".
 
-`--impl reference` times the CPU implementation of the same path (the oracle port, all host cores via processes; the
-reference itself is Python and cannot travel to the GPU box) and prints the same line with "impl": "reference".
+`--impl reference` times the reference's own CPU step on all host cores (one process per core, one env each; oracle/_ref when it
+travelled with the snapshot, else the oracle port) and prints the same line with "impl": "reference".
 """
 from __future__ import annotations
 
@@ -39,11 +47,12 @@ METRIC = 'building_env_steps_per_sec'
 UNIT = 'building-env steps/s'
 
 
-def bytes_per_unit(precision: str, n_obs: int, n_act: int, n_buildings: int) -> float:
-    """Algorithmic HBM bytes per (building, env) per step: actions read, state read+write, obs + reward +
-    district written.  fp64 flow keeps degraded capacity and efficiency as doubles (20 B of state instead of 12 B)."""
-    state = 20 if precision == 'fp64' else 12
-    return 4 * n_act + 2 * state + 4 * n_obs + 4 + 12.0 / n_buildings
+def bytes_per_unit(precision: str, n_obs: float, n_act: float, n_buildings: int, rollout: bool = True, reward_dim: float = 1.0) -> float:
+    """Algorithmic HBM bytes per (building, env) per step: actions read, obs + reward + district written, and -
+    for single-step launches only - the unit state read + written (fp64 flow: 20 B, fp32: 12 B).  A rollout launch keeps the
+    state in registers between its steps, so those bytes do not move (rollout=True drops them)."""
+    state = 0 if rollout else (20 if precision == 'fp64' else 12)
+    return 4 * n_act + 2 * state + 4 * n_obs + 4 * reward_dim + 12.0 / n_buildings
 
 
 class ClockSampler:
@@ -178,51 +187,214 @@ def effective_cpus() -> int:
     return n
 
 
+REF_DIR = ROOT / 'oracle' / '_ref'
+
+
+def reference_available() -> bool:
+    return (REF_DIR / 'site' / 'citylearn' / 'citylearn.py').is_file() and (REF_DIR / 'data' / 'datasets' / DATASET / 'schema.json').is_file()
+
+
+def cpu_reference_rate(steps: int, warm: int = 2, seed: int = 0):
+    """building-env steps / s of the UNMODIFIED reference (oracle/_ref) on ONE core: its own `CityLearnEnv.step` loop, one env."""
+    import shutil
+    import logging
+    import numpy as np
+    os.environ['XDG_CACHE_HOME'] = str(REF_DIR / 'cache')          # DataSet()'s cache stays inside oracle/_ref (git-ignored)
+    for q in (ROOT / 'oracle' / 'shims', REF_DIR / 'site'):
+        if str(q) not in sys.path:
+            sys.path.insert(0, str(q))
+    from platformdirs import user_cache_dir
+    d = Path(user_cache_dir(appname='citylearn', appauthor='intelligent-environments-lab', version='v2.4.2')) / 'misc'
+    d.mkdir(parents=True, exist_ok=True)
+    for f in ('battery_choices.yaml', 'lbl-tracking_the_sun-res-pv.csv'):      # CityLearnEnv._load asks DataSet() for them (citylearn.py:2055-2057)
+        if not (d / f).is_file():
+            shutil.copy(REF_DIR / 'data' / 'misc' / f, d / f)
+    logging.getLogger().setLevel(logging.WARNING)
+    from citylearn.citylearn import CityLearnEnv as RefEnv
+    env = RefEnv(str(REF_DIR / 'data' / 'datasets' / DATASET / 'schema.json'))
+    env.reset()
+    B = len(env.buildings)
+    rng = np.random.RandomState(seed)
+    acts = [[[float(x)] for x in rng.uniform(-1, 1, B)] for _ in range(steps + warm)]
+    for k in range(warm):
+        env.step(acts[k])
+    t0 = time.perf_counter()
+    for k in range(warm, warm + steps):
+        env.step(acts[k])
+    dt = time.perf_counter() - t0
+    return B * steps / dt, dt
+
+
 def _ref_worker(args):
-    n_envs, steps, seed = args
+    kind, n_envs, steps, warm, seed = args
     os.environ.setdefault('OMP_NUM_THREADS', '1')
-    return cpu_oracle_rate(n_envs, steps, seed)
+    if kind == 'reference':
+        return cpu_reference_rate(steps, warm, seed)
+    return cpu_oracle_rate(n_envs, steps + warm, seed)
 
 
 def run_reference(args):
-    """CPU arm: the oracle port on all host cores (one process per core, envs split evenly)."""
+    """CPU arm on all host cores, one process per core: the UNMODIFIED reference (oracle/_ref, one env per process - it is
+    single-threaded and single-env) when it travelled with the snapshot, else the oracle port (envs split evenly)."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
     import multiprocessing as mp
     procs = max(1, min(effective_cpus(), 128))
-    per = max(1, ENVS_PER_GPU // procs)
     steps, warm = args.steps, args.warmup
-    ctx = mp.get_context('fork')
+    real = reference_available()
+    per = 1 if real else max(1, ENVS_PER_GPU // procs)
+    ctx = mp.get_context('spawn' if real else 'fork')
     t0 = time.perf_counter()
     with ctx.Pool(procs) as pool:
-        res = pool.map(_ref_worker, [(per, steps + warm, i) for i in range(procs)])
+        res = pool.map(_ref_worker, [('reference' if real else 'port', per, steps, warm, i) for i in range(procs)])
     wall = time.perf_counter() - t0
     # per-process rates exclude construction; sum over processes = whole-host throughput
     value = float(sum(r for r, _ in res))
-    ms = 1e3 * max(dt for _, dt in res) / (steps + warm)
+    ms = 1e3 * max(dt for _, dt in res) / (steps if real else steps + warm)
+    note = ('the UNMODIFIED reference (CityLearn v2.4.2 installed into oracle/_ref by oracle/build_ref.py): its own CityLearnEnv.step loop, '
+            'one single-env process per host core') if real else \
+           ('CPU port of the reference algorithm (oracle/citylearn_oracle.py, NumPy, float64 intermediates); oracle/_ref did not travel - '
+            'BASELINE.md has the reference\'s measured 871.7 building-steps/s/core')
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': steps, 'warmup': warm,
         'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-        'config': {'workload': f'{DATASET}: 17 buildings x {per * procs} envs (bounded sample: {procs} processes x {per} envs)',
-                   'note': 'CPU port of the reference algorithm (oracle/citylearn_oracle.py, NumPy, float64 intermediates); the Python '
-                           'reference itself cannot travel to the GPU box - BASELINE.md has its measured 871.7 building-steps/s/core'},
-        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': procs, 'kind': 'port',
-                         'sample': f'{procs} processes x {per} envs x {steps + warm} steps, wall {wall:.1f}s'},
+        'config': {'workload': f'{DATASET}: 17 buildings x {ENVS_PER_GPU} envs per GPU, observations 476/env, actions 17/env',
+                   'sample': f'bounded sample: {procs} processes x {per} env(s) x {steps} steps', 'note': note},
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': procs, 'kind': 'reference' if real else 'port',
+                         'sample': f'{procs} processes x {per} env(s) x {steps} timed steps (+{warm} warm-up), wall {wall:.1f}s incl. construction'},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
     print(json.dumps(line), flush=True)
 
 
+def timed_rollouts(env, torch, acts, obs, rew, dst, K: int, R: int, reset_every: int = 0):
+    """R back-to-back K-step `cl_rollout` launches, each bracketed by CUDA events on the launch stream; nothing synchronises the
+    host in between, so from the second launch on the GPU never waits for the host.  Returns per-launch milliseconds."""
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(R)]
+    for i in range(R):
+        if env.time_step + K > env.time_steps - 1:
+            env.reset()                      # outside the brackets
+        ev[i][0].record()
+        env.rollout(acts, obs, rew, dst)
+        ev[i][1].record()
+    torch.cuda.synchronize(env.device)
+    return [a.elapsed_time(b) for a, b in ev]
+
+
+def median(xs):
+    ys = sorted(xs)
+    return ys[len(ys) // 2]
+
+
+def timing_summary(ms, K):
+    return {'repeats': len(ms), 'median_us_per_step': 1e3 * median(ms) / K, 'min_us_per_step': 1e3 * min(ms) / K,
+            'max_us_per_step': 1e3 * max(ms) / K, 'first_launch_us_per_step': 1e3 * ms[0] / K}
+
+
+def extra_fresh_c2(torch, dev, precision, K, R, peak):
+    """BASELINE configs[1] with stale_observations=False: observations carry soc / net of the step (per-env row images)."""
+    from citylearn_b200 import CityLearnEnv
+    E = ENVS_PER_GPU
+    env = CityLearnEnv(DATASET, num_envs=E, device=dev, precision=precision, stale_observations=False)
+    B, A, L = env.spec.n_buildings, env.spec.action_dim, env._obs_dim
+    acts = torch.rand((K, E, A), device=dev) * 2 - 1
+    obs = torch.empty((K, E, L), device=dev); rew = torch.empty((K, E, B), device=dev); dst = torch.empty((K, E, 3), device=dev)
+    env.reset()
+    timed_rollouts(env, torch, acts, obs, rew, dst, K, 2)
+    ms = timed_rollouts(env, torch, acts, obs, rew, dst, K, R)
+    m = median(ms)
+    bpu = bytes_per_unit(precision, L / B, A / B, B)
+    out = {'workload': f'{DATASET}: {B} x {E} envs, stale_observations=False (fresh observations)', 'ms_per_step': m / K,
+           'value': B * E * K / (m * 1e-3), 'unit': UNIT, 'timing': timing_summary(ms, K), 'table_path': bool(env._h.geometry()),
+           'roofline': {'bound': 'hbm', 'achieved': bpu * B * E * K / (m * 1e-3) / 1e9, 'peak': peak, 'unit': 'GB/s',
+                        'frac': bpu * B * E * K / (m * 1e-3) / 1e9 / peak, 'bytes_per_unit': bpu}}
+    env.close()
+    return out
+
+
+def extra_c3(torch, dev, precision, fma_peak):
+    """BASELINE configs[2]: 2023 schema, 3 LSTM buildings x 65 536 envs, MARL per-building rewards, past the LSTM warm-up."""
+    from citylearn_b200 import CityLearnEnv
+    from citylearn_b200.data import DataSet
+    src = DataSet.get_source('citylearn_challenge_2023_phase_2_local_evaluation')
+    sch = src.schema()
+    sch['reward_function'] = {'type': 'citylearn.reward_function.MARL', 'attributes': {}}
+    E, K, W, R = 65536, 20, 16, 8
+    env = CityLearnEnv(sch, data_source=src, central_agent=False, num_envs=E, device=dev, precision=precision)
+    B, A, L = env.spec.n_buildings, env.spec.action_dim, env._obs_dim
+    lo = torch.tensor([v for b in env.spec.buildings for v in b.action_low], device=dev)
+    hi = torch.tensor([v for b in env.spec.buildings for v in b.action_high], device=dev)
+    acts = lo + torch.rand((K, E, A), device=dev) * (hi - lo)
+    obs = torch.empty((K, E, L), device=dev); rew = torch.empty((K, E, B), device=dev)
+    env.reset()
+    env.rollout(acts[:W].contiguous(), obs[:W], rew[:W], None)            # LSTM warm-up (12-step lookback)
+    ms = timed_rollouts(env, torch, acts, obs, rew, None, K, R)
+    m = median(ms)
+    flop_unit = 93696.0 + 150.0                                            # SURVEY.md §8d: 46 848 LSTM MACs + device arithmetic
+    tf = flop_unit * B * E * K / (m * 1e-3) / 1e12
+    out = {'workload': f'citylearn_challenge_2023_phase_2_local_evaluation: {B} LSTM buildings x {E} envs, MARL, decentralised', 'ms_per_step': m / K,
+           'value': B * E * K / (m * 1e-3), 'unit': UNIT, 'timing': timing_summary(ms, K),
+           'roofline': {'bound': 'fp32_fma', 'achieved': tf, 'peak': fma_peak, 'unit': 'TFLOP/s', 'frac': tf / fma_peak if fma_peak else None,
+                        'flop_per_unit': flop_unit, 'peak_source': 'cl_measure_fma_peak (independent FFMA chains, this device)'}}
+    env.close()
+    return out
+
+
+def extra_c4(torch, dev, precision, peak, world, dist):
+    """BASELINE configs[3], this GPU's share: synthetic 1024 buildings x 1024 envs, the FULL 8 759-step year as back-to-back
+    8-step `cl_rollout` launches (observations + rewards + district sums written every step).  With N ranks the job is the
+    configs[3] district at N x 1024 envs (env-sharded, no collective)."""
+    from citylearn_b200 import CityLearnEnv, schema as S
+    from citylearn_b200.synthetic import make_wide_district
+    sch, src = make_wide_district(1024)
+    spec = S.load(sch, data_source=src)
+    E, K = 1024, 8
+    env = CityLearnEnv(spec, num_envs=E, device=dev, precision=precision)
+    B, A, L = spec.n_buildings, spec.action_dim, env._obs_dim
+    acts = torch.rand((K, E, A), device=dev) * 2 - 1
+    obs = torch.empty((K, E, L), device=dev); rew = torch.empty((K, E, env._reward_dim), device=dev); dst = torch.empty((K, E, 3), device=dev)
+    env.reset()
+    timed_rollouts(env, torch, acts, obs, rew, dst, K, 2)
+    env.reset()
+    T1 = env.time_steps - 1
+    n_full, rest = divmod(T1, K)
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n_full):
+        env.rollout(acts, obs, rew, dst)
+    if rest:
+        env.rollout(acts[:rest].contiguous(), obs[:rest], rew[:rest], dst[:rest])
+    e1.record()
+    torch.cuda.synchronize(dev)
+    assert env.terminated
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    bpu = bytes_per_unit(precision, L / B, A / B, B)
+    gbs = bpu * B * E * T1 / (ms * 1e-3) / 1e9
+    out = {'workload': f'synthetic {B} buildings x {E} envs per GPU ({world * E} envs on {world} GPU(s)), full {T1}-step year', 'year_ms': ms,
+           'ms_per_step': ms / T1, 'value': world * B * E * T1 / (ms * 1e-3), 'unit': UNIT, 'launches': n_full + (1 if rest else 0), 'geometry': env._h.geometry(),
+           'roofline': {'bound': 'hbm', 'achieved': gbs, 'peak': peak, 'unit': 'GB/s', 'frac': gbs / peak, 'bytes_per_unit': bpu}}
+    env.close()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=200)
-    ap.add_argument('--warmup', type=int, default=20)
+    ap.add_argument('--steps', type=int, default=100)
+    ap.add_argument('--warmup', type=int, default=10)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--precision', default='fp64', choices=['fp64', 'fp32'])
     ap.add_argument('--envs', type=int, default=ENVS_PER_GPU, help='parallel envs per GPU')
+    ap.add_argument('--repeats', type=int, default=50, help='back-to-back K-step launches in the timed region (median reported)')
+    ap.add_argument('--extras', default='auto', choices=['auto', 'all', 'none'], help="C3 / C4 / fresh-observation numbers under 'extra' (auto: N = 1 all, N > 1 C4 only)")
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
     if args.impl == 'reference':
@@ -231,7 +403,7 @@ def main():
     import numpy as np
     import torch
     import torch.distributed as dist
-    from citylearn_b200 import CityLearnEnv
+    from citylearn_b200 import CityLearnEnv, _native
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
@@ -244,112 +416,161 @@ def main():
     K, W, E = args.steps, max(args.warmup, 3), args.envs
     env = CityLearnEnv(DATASET, num_envs=E, device=dev, precision=args.precision)
     B, A, L = env.spec.n_buildings, env.spec.action_dim, env._obs_dim
-    assert W + K <= env.time_steps - 1, 'steps + warmup must fit in one episode'
+    T1 = env.time_steps - 1
+    assert W + K <= T1, 'steps + warmup must fit in one episode'
+    R = max(3, min(args.repeats, (T1 - W) // K))
 
     # ---------------- device-resident throughput ----------------
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
-    acts = torch.rand((W + K, E, A), device=dev, generator=g) * 2 - 1
-    obs = torch.empty((K, E, L), device=dev)
-    rew = torch.empty((K, E, B), device=dev)
-    dst = torch.empty((K, E, 3), device=dev)
+    acts = torch.rand((max(K, W), E, A), device=dev, generator=g) * 2 - 1
+    obs = torch.empty((max(K, W), E, L), device=dev)
+    rew = torch.empty((max(K, W), E, B), device=dev)
+    dst = torch.empty((max(K, W), E, 3), device=dev)
     env.reset()
-    env.rollout(acts[:W].contiguous(), obs[:W], rew[:W], dst[:W])                 # warm-up steps (untimed)
+    env.rollout(acts[:W].contiguous(), obs[:W], rew[:W], dst[:W])                 # W warm-up steps (untimed)
     torch.cuda.synchronize(dev)
-    if world > 1:
-        dist.barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    launches0 = env.gpu_launches
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize(dev)
-    ev0.record()
-    env.rollout(acts[W:], obs, rew, dst)       # EXACTLY K steps
-    ev1.record()
-    torch.cuda.synchronize(dev)
-    ms_total = ev0.elapsed_time(ev1)
-    launches = env.gpu_launches - launches0
-    t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.barrier()
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
-    checksum = float(rew.sum().item())            # reads the result back: the step's rewards
-    units_per_step = B * E
-    value = world * units_per_step * K / (ms_max * 1e-3)
-
-    # ---------------- end to end through the public API with host buffers ----------------
-    env.reset()
-    host_acts = np.random.RandomState(7 + rank).uniform(-1, 1, size=(W + K, E, A)).astype('float32')
-    for k in range(W):
-        env.step_host(host_acts[k])
-    torch.cuda.synchronize(dev)
-    if world > 1:
-        dist.barrier()
-    ev0.record()
-    e2e_sum = 0.0
-    for k in range(W, W + K):
-        o, r, term = env.step_host(host_acts[k])
-        e2e_sum += float(r[0, 0])
-    ev1.record()
-    torch.cuda.synchronize(dev)
-    t2 = torch.tensor([ev0.elapsed_time(ev1)], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.barrier()
-        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
-    e2e_value = world * units_per_step * K / (float(t2.item()) * 1e-3)
-    clocks = sampler.stop() if rank == 0 else None
-
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-
     peaks = {}
     try:
         peaks = json.loads((ROOT / 'MEASURED_PEAKS.json').read_text())
     except Exception:
         pass
     peak = float(peaks.get('hbm_gbs', 6650.0))
-    bpu = bytes_per_unit(args.precision, L // B, A // B, B)
-    # the timed region is `launches` launches of the rollout kernel (normally one) covering K steps: algorithmic bytes per
-    # launch = K/launches steps x bytes per step; duration = CUDA-event time of the region / launches
-    steps_per_launch = K / max(launches, 1)
-    avg_launch_s = ms_total * 1e-3 / max(launches, 1)
-    bytes_per_launch = bpu * units_per_step * steps_per_launch
-    achieved = bytes_per_launch / avg_launch_s / 1e9
-    traffic = None
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = env.gpu_launches
+    torch.cuda.synchronize(dev)
+    a_k, o_k, r_k, d_k = acts[:K].contiguous(), obs[:K], rew[:K], dst[:K]
+    launch_ms = timed_rollouts(env, torch, a_k, o_k, r_k, d_k, K, R)                # R launches of EXACTLY K steps each
+    launches = env.gpu_launches - launches0
+    ms_med = median(launch_ms)
+    t = torch.tensor([ms_med], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.barrier()
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    checksum = float(rew[:K].sum().item())            # reads the result back: the step's rewards
+    units_per_step = B * E
+    value = world * units_per_step * K / (ms_max * 1e-3)
+
+    # ---------------- end to end through the public API with host buffers ----------------
+    def e2e_loop(full):
+        env.reset()
+        host_acts = np.random.RandomState(7 + rank).uniform(-1, 1, size=(W + K, E, A)).astype('float32')
+        for k in range(W):
+            env.step_host(host_acts[k], full_observations=full)
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        acc = 0.0
+        for k in range(W, W + K):
+            o, r, term = env.step_host(host_acts[k], full_observations=full)
+            acc += float(r[0, 0]) + float(o[E - 1, 0])
+        ev1.record()
+        torch.cuda.synchronize(dev)
+        tt = torch.tensor([ev0.elapsed_time(ev1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.barrier()
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item()), acc
+    e2e_ms, e2e_sum = e2e_loop(None)                   # shared observation row (reference-parity rows are env-independent)
+    e2e_full_ms, _ = e2e_loop(True)                    # full [E, L] copy, for comparison
+    # K steps as ONE host call: one H2D of [K, E, A], one launch, one D2H of rewards + K rows
+    env.reset()
+    blk = np.random.RandomState(9 + rank).uniform(-1, 1, size=(K, E, A)).astype('float32')
+    env.rollout_host(blk)
+    torch.cuda.synchronize(dev)
+    tb = []
+    for _ in range(3):
+        if env.time_step + K > T1:
+            env.reset()
+        t0 = time.perf_counter(); env.rollout_host(blk); tb.append(time.perf_counter() - t0)
+    blk_s = torch.tensor([median(tb)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(blk_s, op=dist.ReduceOp.MAX)
+    e2e_value = world * units_per_step * K / (e2e_ms * 1e-3)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---------------- other BASELINE configs on the same line ----------------
+    extra = {}
+    want = args.extras
+    fma_peak = None
     try:
-        # measured DRAM bytes (ncu --set full: dram__bytes_read.sum + dram__bytes_write.sum) per step of the same workload, scaled to
-        # the steps of one launch like `achieved`; only valid for the default workload the capture was taken on
-        rec = json.loads((ROOT / 'profiles' / 'step_kernel_traffic.json').read_text()).get(args.precision)
-        if rec and args.envs == ENVS_PER_GPU:
-            traffic = (rec['dram_read_bytes_per_step'] + rec['dram_write_bytes_per_step']) * steps_per_launch
+        if want == 'all' or (want == 'auto' and world == 1):
+            if rank == 0:
+                with torch.cuda.device(dev):
+                    fma_peak = _native.measure_fma_peak()
+                extra['fresh_observations_c2'] = extra_fresh_c2(torch, dev, args.precision, K, min(R, 20), peak)
+                extra['c3_lstm_marl'] = extra_c3(torch, dev, args.precision, fma_peak)
+        if want != 'none':
+            extra['c4_wide_year'] = extra_c4(torch, dev, args.precision, peak, world, dist)
+    except Exception as e:          # an extra must never take the headline down
+        extra['error'] = repr(e)[:300]
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    bpu = bytes_per_unit(args.precision, L / B, A / B, B, rollout=True)
+    bpu_step = bytes_per_unit(args.precision, L / B, A / B, B, rollout=False)
+    # the timed region is R launches of the rollout kernel, K steps each: algorithmic bytes per launch = K steps x bytes a step moves;
+    # duration = the median launch (CUDA events on the launch stream)
+    bytes_per_launch = bpu * units_per_step * K
+    achieved = bytes_per_launch / (ms_med * 1e-3) / 1e9
+    traffic = None
+    traffic_note = None
+    try:
+        # measured DRAM bytes (ncu --set full: dram__bytes_read.sum + dram__bytes_write.sum) of ONE launch of this exact configuration
+        # (precision, envs, steps per launch); absent for other configurations
+        rec = json.loads((ROOT / 'profiles' / 'step_kernel_traffic.json').read_text())
+        hit = rec.get(f'{args.precision}:{E}:{K}')
+        if hit:
+            traffic = hit['dram_read_bytes'] + hit['dram_write_bytes']
+            traffic_note = hit.get('source')
     except Exception:
         pass
     cpu = None
     if not args.no_cpu_baseline:
-        rate, dt = cpu_oracle_rate(512, 1200)      # ~10-20 s of single-core NumPy work
-        cpu = {'value': rate, 'unit': UNIT, 'cores': 1, 'kind': 'port',
-               'sample': f'NumPy oracle, 17 buildings x 512 envs x 1200 steps in {dt:.1f}s on 1 core '
-                         f'(reference itself: 871.7 building-steps/s/core, BASELINE.md)'}
+        if reference_available():
+            rate, dt = cpu_reference_rate(600, 3)       # ~12-20 s of the reference's own single-core step loop
+            cpu = {'value': rate, 'unit': UNIT, 'cores': 1, 'kind': 'reference',
+                   'sample': f'UNMODIFIED reference (oracle/_ref), 17 buildings x 1 env x 600 steps in {dt:.1f}s on 1 core'}
+        else:
+            rate, dt = cpu_oracle_rate(512, 1200)       # ~10-20 s of single-core NumPy work
+            cpu = {'value': rate, 'unit': UNIT, 'cores': 1, 'kind': 'port',
+                   'sample': f'NumPy oracle, 17 buildings x 512 envs x 1200 steps in {dt:.1f}s on 1 core '
+                             f'(reference itself: 871.7 building-steps/s/core, BASELINE.md)'}
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': K, 'warmup': W, 'ms_per_step': ms_max / K,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f64' if args.precision == 'fp64' else 'f32', 'data': 'synthetic',
         'config': {'workload': f'{DATASET}: {B} buildings x {E} envs per GPU, observations {L}/env, actions {A}/env',
-                   'precision': args.precision + (' (float64 intermediates, float32 storage: the reference\'s own flow)' if args.precision == 'fp64' else ''),
-                   'mode': 'cl_rollout: ONE persistent kernel launch advances all K steps (state in registers, TMA row ring), actions pre-resident in HBM',
-                   'l2': f'every step writes its own obs/reward slab: {K} x {bpu * units_per_step / 1e6:.1f} MB > 126 MB L2',
+                   'precision': args.precision + (' (float64 intermediates, float32 storage: the reference\'s own flow, bit-exact)' if args.precision == 'fp64'
+                                                  else ' (plain float arithmetic: within 1e-4 scaled-relative of the reference, not the 1e-5 target)'),
+                   'mode': f'cl_rollout: ONE persistent kernel launch advances all K = {K} steps (state in registers, TMA row ring), actions pre-resident in HBM',
+                   'timed_region': f'{R} back-to-back launches of exactly K steps, one CUDA-event pair each on the launch stream; value = median launch, max over ranks',
+                   'l2': f'every step writes its own obs/reward slab: {K} x {bpu * units_per_step / 1e6:.1f} MB per launch vs 126 MB L2',
                    'envs_sharded_across_gpus': True, 'collectives_on_step_path': 0},
-        'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic,
-                     'kernel': 'advance_kernel', 'bytes_per_unit': bpu, 'bytes_per_step': bpu * units_per_step, 'bytes_per_launch': bytes_per_launch, 'steps_per_launch': steps_per_launch,
-                     'avg_launch_us': avg_launch_s * 1e6, 'peak_source': 'MEASURED_PEAKS.json hbm_gbs' if peaks else 'fallback 6650'},
+        'timing': timing_summary(launch_ms, K),
+        'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic, 'traffic_source': traffic_note,
+                     'kernel': 'advance_kernel', 'bytes_per_unit': bpu, 'bytes_per_unit_single_step_launch': bpu_step,
+                     'bytes_per_step': bpu * units_per_step, 'bytes_per_launch': bytes_per_launch, 'steps_per_launch': K,
+                     'avg_launch_us': ms_med * 1e3, 'peak_source': 'MEASURED_PEAKS.json hbm_gbs' if peaks else 'fallback 6650'},
         'cpu_baseline': cpu,
-        'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': E * A * 4, 'd2h_bytes_per_step': E * L * 4 + E * B * 4,
-                'ms_per_step': float(t2.item()) / K},
+        'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': E * A * 4, 'd2h_bytes_per_step': L * 4 + E * B * 4,
+                'ms_per_step': e2e_ms / K, 'api': 'CityLearnEnv.step_host(ndarray): shared observation row + rewards cross PCIe'},
+        'e2e_full_observations': {'value': world * units_per_step * K / (e2e_full_ms * 1e-3), 'unit': UNIT, 'ms_per_step': e2e_full_ms / K,
+                                  'd2h_bytes_per_step': E * L * 4 + E * B * 4},
+        'e2e_rollout_host': {'value': world * units_per_step * K / float(blk_s.item()), 'unit': UNIT, 'ms_per_step': 1e3 * float(blk_s.item()) / K,
+                             'api': 'CityLearnEnv.rollout_host(ndarray [K, E, A]): one H2D, one launch, one D2H (wall clock incl. host memcpy)'},
         'gpu_launches': int(launches),
         'clocks': clocks,
+        'extra': extra,
         'checksum': checksum + e2e_sum * 0.0,
     }
     print(json.dumps(line), flush=True)

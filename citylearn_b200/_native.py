@@ -66,6 +66,7 @@ def load():
     lib.cl_reset.argtypes = [vp, vp, i32, i32, vp, vp]
     lib.cl_step.argtypes = [vp, vp, vp, vp, vp, vp, vp]
     lib.cl_rollout.argtypes = [vp, i32, vp, vp, vp, vp, vp]
+    lib.cl_obs_rows.argtypes = [vp, i32, i32, vp, vp]
     lib.cl_time_step.argtypes = [vp, ctypes.POINTER(ctypes.c_int32)]
     lib.cl_state_size.argtypes = [vp, ctypes.POINTER(ctypes.c_size_t)]
     lib.cl_get_state.argtypes = [vp, vp, vp]
@@ -77,9 +78,10 @@ def load():
     lib.cl_kpi_enable.argtypes = [vp, i32]
     lib.cl_kpi_accumulate.argtypes = [vp, vp, vp, vp]
     lib.cl_kpi_read.argtypes = [vp, vp, vp, vp]
-    for name in ('cl_create', 'cl_destroy', 'cl_set_outage', 'cl_reset', 'cl_step', 'cl_rollout', 'cl_time_step',
+    lib.cl_measure_fma_peak.argtypes = [ctypes.POINTER(ctypes.c_double)]
+    for name in ('cl_create', 'cl_destroy', 'cl_set_outage', 'cl_reset', 'cl_step', 'cl_rollout', 'cl_obs_rows', 'cl_time_step',
                  'cl_state_size', 'cl_get_state', 'cl_set_state', 'cl_launch_count', 'cl_launch_geometry', 'cl_set_transforms',
-                 'cl_kpi_enable', 'cl_kpi_accumulate', 'cl_kpi_read'):
+                 'cl_kpi_enable', 'cl_kpi_accumulate', 'cl_kpi_read', 'cl_measure_fma_peak'):
         getattr(lib, name).restype = ctypes.c_int
     if lib.cl_abi_version() != ABI_VERSION:
         raise NativeLibraryError(f'{path}: ABI version {lib.cl_abi_version()} != {ABI_VERSION}; rebuild the extension')
@@ -92,6 +94,13 @@ def check(rc: int, what: str = ''):
         msg = load().cl_last_error().decode(errors='replace')
         exc = {1: ValueError, 3: NotImplementedError}.get(rc, RuntimeError)
         raise exc(f'{what}: {msg}' if what else msg)
+
+
+def measure_fma_peak() -> float:
+    """Measured FP32 FMA throughput of the current CUDA device, TFLOP/s."""
+    v = ctypes.c_double()
+    check(load().cl_measure_fma_peak(ctypes.byref(v)), 'cl_measure_fma_peak')
+    return v.value
 
 
 class Handle:
@@ -156,6 +165,9 @@ class Handle:
 
     def rollout(self, n_steps: int, actions_ptr, obs_ptr, reward_ptr, district_ptr, stream: int):
         check(self.lib.cl_rollout(self.ptr, int(n_steps), actions_ptr, obs_ptr, reward_ptr, district_ptr, stream), 'cl_rollout')
+
+    def obs_rows(self, first_time_step: int, n_rows: int, rows_ptr, stream: int):
+        check(self.lib.cl_obs_rows(self.ptr, int(first_time_step), int(n_rows), rows_ptr, stream), 'cl_obs_rows')
 
     def time_step(self) -> int:
         t = ctypes.c_int32()

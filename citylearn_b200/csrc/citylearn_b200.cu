@@ -41,6 +41,7 @@ namespace cl {
 struct Dev {
     int B, E, U, n_rows, W, Wp, A, L, T;
     int central, reward_id, stale, envs_per_block, uniform_start, start0, has_outage, any_dynamics, lstm_smem;
+    int curve_nmax;        // max number of points of any battery curve of the district (uniform bound of the segment search)
     // building tiles: a district wider than one block is split into `tiles` tiles of `tile_b` buildings, one CTA per tile,
     // the CTAs of an env forming a thread-block cluster (tiles == 1: tile_b == B, Lt == L, no cluster)
     int tiles, tile_b, Lt;
@@ -59,6 +60,11 @@ struct Dev {
     int obs_pitch;                   // floats per row (L rounded up to 4)
     int n_out_cols;                  // observation columns that carry an outage signal (patched per step: they change per episode)
     const int32_t* out_cols;         // [n_out_cols] column index k
+    // stale_observations = 0 with an observation table: every env of a block owns a shared-memory image of its row (TMA-loaded
+    // from obs_tab), the physics threads patch their action-dependent (DYN) columns into it, one TMA bulk store per env row
+    int fresh_slots;                 // 1: the shared-memory layout holds 2 x envs_per_block row images (else 2 x 1)
+    const int2* dyn_cols;            // [dyn_off[B]] (observation column k, cl_dyn slot), grouped by building
+    const int32_t* dyn_off;          // [B + 1]
     float rp[8];
     const float* table;
     const float* pf;       // [NPARAM][B]
@@ -137,6 +143,7 @@ __device__ __forceinline__ void load_ctx(const Dev& d, int b, UnitCtx<R>& c) {
     }
 #undef LD
 #undef LDI
+    derive_params(p);
 }
 
 template <typename R, bool THERMAL>
@@ -232,37 +239,46 @@ __device__ __forceinline__ void apply_actions(const UnitCtx<R>& c, const RawActi
     }
 }
 
-// dyn values of a unit (cl_dyn order) from a step / time-0 result
+// value of cl_dyn slot `slot` of a unit from a step / time-0 result
+template <typename R>
+__device__ __forceinline__ float dyn_value(int slot, const BuildingParams<R>& p, const UnitState<R>& s, const UnitResult<R>& o, R t_in) {
+    using N = Num<R>;
+    switch (slot) {
+        case CL_DYN_ELECTRICAL_STORAGE_SOC: return (float)s.soc_b;
+        case CL_DYN_COOLING_STORAGE_SOC: return (float)s.soc_cs;
+        case CL_DYN_HEATING_STORAGE_SOC: return (float)s.soc_hs;
+        case CL_DYN_DHW_STORAGE_SOC: return (float)s.soc_ds;
+        case CL_DYN_NET_ELECTRICITY_CONSUMPTION: return (float)o.net;
+        case CL_DYN_COOLING_DEMAND: return (float)(o.e_from_cool + fabs(rmin(o.eb_cs, (R)0)));
+        case CL_DYN_HEATING_DEMAND: return (float)(o.e_from_heat + fabs(rmin(o.eb_hs, (R)0)));
+        case CL_DYN_DHW_DEMAND: return (float)(o.e_from_dhw + fabs(rmin(o.eb_ds, (R)0)));
+        case CL_DYN_COOLING_ELECTRICITY_CONSUMPTION: return (float)(o.ec_cool * p.ratio);
+        case CL_DYN_HEATING_ELECTRICITY_CONSUMPTION: return (float)(o.ec_heat * p.ratio);
+        case CL_DYN_DHW_ELECTRICITY_CONSUMPTION: return (float)(o.ec_dhw * p.ratio);
+        case CL_DYN_COOLING_STORAGE_ELECTRICITY_CONSUMPTION: return (float)N::div32(o.eb_cs, o.eff_cool);
+        case CL_DYN_HEATING_STORAGE_ELECTRICITY_CONSUMPTION: return (float)N::div32(o.eb_hs, o.eff_heat);
+        case CL_DYN_DHW_STORAGE_ELECTRICITY_CONSUMPTION: return (float)N::div32(o.eb_ds, o.eff_dhw);
+        case CL_DYN_ELECTRICAL_STORAGE_ELECTRICITY_CONSUMPTION: return (float)(o.ec_bat * p.ratio);
+        case CL_DYN_INDOOR_DRY_BULB_TEMPERATURE: return (float)t_in;
+        case CL_DYN_NON_SHIFTABLE_LOAD_ELECTRICITY_CONSUMPTION: return (float)(o.ec_nsl * p.ratio);
+        case CL_DYN_ELECTRICAL_STORAGE_ENERGY_BALANCE: return (float)o.eb_bat;
+        case CL_DYN_COOLING_STORAGE_ENERGY_BALANCE: return (float)o.eb_cs;
+        case CL_DYN_HEATING_STORAGE_ENERGY_BALANCE: return (float)o.eb_hs;
+        case CL_DYN_DHW_STORAGE_ENERGY_BALANCE: return (float)o.eb_ds;
+        case CL_DYN_NET_ELECTRICITY_CONSUMPTION_COST: return (float)o.cost;
+        case CL_DYN_NET_ELECTRICITY_CONSUMPTION_EMISSION: return (float)o.emission;
+        case CL_DYN_ELECTRICAL_STORAGE_DEGRADED_CAPACITY: return (float)s.cap_deg;
+        case CL_DYN_ENERGY_TO_NON_SHIFTABLE_LOAD: return (float)o.e_to_nsl;
+        case CL_DYN_COOLING_DEMAND_SERIES: return (float)o.cool_dem;
+        case CL_DYN_HEATING_DEMAND_SERIES: return (float)o.heat_dem;
+        default: return 0.f;
+    }
+}
+// all dyn values of a unit (cl_dyn order)
 template <typename R>
 __device__ __forceinline__ void fill_dyn(const BuildingParams<R>& p, const UnitState<R>& s, const UnitResult<R>& o, R t_in, float* dyn) {
-    using N = Num<R>;
-    dyn[CL_DYN_ELECTRICAL_STORAGE_SOC] = (float)s.soc_b;
-    dyn[CL_DYN_COOLING_STORAGE_SOC] = (float)s.soc_cs;
-    dyn[CL_DYN_HEATING_STORAGE_SOC] = (float)s.soc_hs;
-    dyn[CL_DYN_DHW_STORAGE_SOC] = (float)s.soc_ds;
-    dyn[CL_DYN_NET_ELECTRICITY_CONSUMPTION] = (float)o.net;
-    dyn[CL_DYN_COOLING_DEMAND] = (float)(o.e_from_cool + fabs(rmin(o.eb_cs, (R)0)));
-    dyn[CL_DYN_HEATING_DEMAND] = (float)(o.e_from_heat + fabs(rmin(o.eb_hs, (R)0)));
-    dyn[CL_DYN_DHW_DEMAND] = (float)(o.e_from_dhw + fabs(rmin(o.eb_ds, (R)0)));
-    dyn[CL_DYN_COOLING_ELECTRICITY_CONSUMPTION] = (float)(o.ec_cool * p.ratio);
-    dyn[CL_DYN_HEATING_ELECTRICITY_CONSUMPTION] = (float)(o.ec_heat * p.ratio);
-    dyn[CL_DYN_DHW_ELECTRICITY_CONSUMPTION] = (float)(o.ec_dhw * p.ratio);
-    dyn[CL_DYN_COOLING_STORAGE_ELECTRICITY_CONSUMPTION] = (float)N::div32(o.eb_cs, o.eff_cool);
-    dyn[CL_DYN_HEATING_STORAGE_ELECTRICITY_CONSUMPTION] = (float)N::div32(o.eb_hs, o.eff_heat);
-    dyn[CL_DYN_DHW_STORAGE_ELECTRICITY_CONSUMPTION] = (float)N::div32(o.eb_ds, o.eff_dhw);
-    dyn[CL_DYN_ELECTRICAL_STORAGE_ELECTRICITY_CONSUMPTION] = (float)(o.ec_bat * p.ratio);
-    dyn[CL_DYN_INDOOR_DRY_BULB_TEMPERATURE] = (float)t_in;
-    dyn[CL_DYN_NON_SHIFTABLE_LOAD_ELECTRICITY_CONSUMPTION] = (float)(o.ec_nsl * p.ratio);
-    dyn[CL_DYN_ELECTRICAL_STORAGE_ENERGY_BALANCE] = (float)o.eb_bat;
-    dyn[CL_DYN_COOLING_STORAGE_ENERGY_BALANCE] = (float)o.eb_cs;
-    dyn[CL_DYN_HEATING_STORAGE_ENERGY_BALANCE] = (float)o.eb_hs;
-    dyn[CL_DYN_DHW_STORAGE_ENERGY_BALANCE] = (float)o.eb_ds;
-    dyn[CL_DYN_NET_ELECTRICITY_CONSUMPTION_COST] = (float)o.cost;
-    dyn[CL_DYN_NET_ELECTRICITY_CONSUMPTION_EMISSION] = (float)o.emission;
-    dyn[CL_DYN_ELECTRICAL_STORAGE_DEGRADED_CAPACITY] = (float)s.cap_deg;
-    dyn[CL_DYN_ENERGY_TO_NON_SHIFTABLE_LOAD] = (float)o.e_to_nsl;
-    dyn[CL_DYN_COOLING_DEMAND_SERIES] = (float)o.cool_dem;
-    dyn[CL_DYN_HEATING_DEMAND_SERIES] = (float)o.heat_dem;
+#pragma unroll
+    for (int j = 0; j < CL_NDYN; ++j) dyn[j] = dyn_value<R>(j, p, s, o, t_in);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -412,23 +428,23 @@ __device__ __forceinline__ void write_obs_general(const Dev& d, float* obs, int 
 
 // ------------------------------------------------------------------------------------------------------------------
 // shared memory carve-up (dynamic)
-//   [mbarriers 32 B][curves B*32 (R)][bsolar 2*B (R)][rows 3*Wp][tcol Lp (int)][tmpl 2*Lp][red 2*3*nt][rsum nt][dsum 2*epb][dynbuf nt*NDYN (opt)]
+//   [mbarriers 64 B][curves B*kCurveTab (R)][bsolar 2*B (R)][rows 3*Wp][tcol Lp (int)][tmpl 2*Lp][red 2*3*nt][rsum nt][dsum 2*epb][dynbuf nt*NDYN (opt)]
 // red / dsum / bsolar are double-buffered by step parity so that a step needs ONE block barrier (see advance_kernel).
 // ------------------------------------------------------------------------------------------------------------------
 // offsets in floats from the start of the dynamic shared memory (kept as plain ints so that every access is derived
 // directly from the `extern __shared__` array and compiles to LDS/STS with 32-bit addressing, not generic loads)
 struct SmemLayout {
-    int curves, bsolar, rows, tcol, tmpl, red, rsum, dsum, wpart, rpart, lstm, lstm_pre, dynbuf, Lp;
+    int curves, bsolar, rows, tcol, tmpl, red, rsum, dsum, wpart, rpart, lstm, lstm_pre, dynbuf, end, Lp;
 };
-__host__ __device__ __forceinline__ SmemLayout smem_layout(int B, int Wp, int L, int epb, int nt, int rsize, int lstm_smem = 0, int tab_layout = 0) {
+__host__ __device__ __forceinline__ SmemLayout smem_layout(int B, int Wp, int L, int epb, int nt, int rsize, int lstm_smem = 0, int tab_layout = 0, int fresh_slots = 0) {
     SmemLayout o;
     o.Lp = (L + 3) & ~3;
     int f = 16;                                  // 64 bytes of mbarriers: 3 time-row slots + 2 observation-row buffers
-    o.curves = f; f += B * 32 * (rsize / 4);     // first: keeps doubles 8-byte aligned
+    o.curves = f; f += B * kCurveTab * (rsize / 4);   // first: keeps doubles 8-byte aligned
     o.bsolar = f; f += ((2 * B * (rsize / 4)) + 3) & ~3;
     o.rows = f; f += 3 * Wp;
     o.tcol = f; f += tab_layout ? 0 : o.Lp;      // gather columns: not needed when the rows come from the observation table
-    o.tmpl = f; f += 2 * o.Lp;                   // observation row of the step, source of the TMA bulk stores (double-buffered)
+    o.tmpl = f; f += 2 * o.Lp * (fresh_slots ? epb : 1);   // observation row image(s) of the step, source of the TMA bulk stores (double-buffered)
     o.red = f; f += 6 * nt;
     o.rsum = f; f += nt;
     o.dsum = f; f += (2 * epb + 3) & ~3;
@@ -436,13 +452,15 @@ __host__ __device__ __forceinline__ SmemLayout smem_layout(int B, int Wp, int L,
     o.rpart = f; f += 2 * 32 * 2;                // wide districts, central agent: per-warp partial reward sums [2][32] doubles (8-byte aligned: f is even)
     o.lstm = f; f += lstm_smem ? B * kLstmStride : 0;      // kLstmStride is a multiple of 4 floats: 16-byte aligned rows
     o.lstm_pre = f; f += lstm_smem ? B * kLstmPreRing * 64 : 0;   // per-building ring of shared layer-0 input projections
-    o.dynbuf = f;
+    // with per-env row images the general writer's dynbuf is never live at the same time: it aliases them (cl_create checks the size)
+    o.dynbuf = fresh_slots ? o.tmpl : f;
+    o.end = f;
     return o;
 }
 static size_t smem_bytes(const Dev& d, int nt, bool with_dyn, int rsize) {
-    const SmemLayout o = smem_layout(d.tile_b, d.Wp, d.Lt, d.envs_per_block, nt, rsize, d.lstm_smem, d.tab_layout);
-    size_t n = sizeof(float) * (size_t)o.dynbuf;
-    if (with_dyn) n += sizeof(float) * (size_t)nt * CL_NDYN;
+    const SmemLayout o = smem_layout(d.tile_b, d.Wp, d.Lt, d.envs_per_block, nt, rsize, d.lstm_smem, d.tab_layout, d.fresh_slots);
+    size_t n = sizeof(float) * (size_t)o.end;
+    if (with_dyn && !d.fresh_slots) n += sizeof(float) * (size_t)nt * CL_NDYN;
     return n;
 }
 
@@ -571,7 +589,7 @@ __global__ void __launch_bounds__(MAXT) advance_kernel(Dev d, int t0, int K, con
     const int nb = WIDE ? min(TBs, B - b0) : B;
     const int k0 = WIDE ? __ldg(d.tile_k + rank) : 0, k1 = WIDE ? __ldg(d.tile_k + rank + 1) : d.L;
     const int Ltile = k1 - k0;
-    const SmemLayout lo = smem_layout(TBs, Wp, WIDE ? d.Lt : d.L, epb, nt, (int)sizeof(R), DYNAMICS ? d.lstm_smem : 0, d.tab_layout);
+    const SmemLayout lo = smem_layout(TBs, Wp, WIDE ? d.Lt : d.L, epb, nt, (int)sizeof(R), DYNAMICS ? d.lstm_smem : 0, d.tab_layout, d.fresh_slots);
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(smf);
     R* scurves = reinterpret_cast<R*>(smf + lo.curves);
     R* s_bsolar = reinterpret_cast<R*>(smf + lo.bsolar);          // [2][B] PV generation of the step, per building
@@ -594,7 +612,9 @@ __global__ void __launch_bounds__(MAXT) advance_kernel(Dev d, int t0, int K, con
     const int ul = e_l * nb + bl;                  // unit slot inside the block's shared-memory arrays (always env-major)
     const int e = e0 + e_l, u = e * B + b;
     const bool uniform = d.uniform_start != 0;
-    const bool want_dyn = (!d.stale && obs != nullptr);
+    // observations with action-dependent (DYN) columns and an observation table: per-env row images in shared memory
+    const bool fresh_tab = obs != nullptr && uniform && !d.stale && d.obs_tab != nullptr && d.fresh_slots;
+    const bool want_dyn = (!d.stale && obs != nullptr) && !fresh_tab;      // general writer (per-env windows, no table)
     const bool tmpl_path = obs != nullptr && uniform && d.stale;
     const bool need_dsum = d.reward_id == CL_REWARD_MARL && reward != nullptr;
     const bool fused_reward = reward != nullptr && d.reward_id >= 0;
@@ -602,7 +622,9 @@ __global__ void __launch_bounds__(MAXT) advance_kernel(Dev d, int t0, int K, con
     const int Rdim = d.central ? 1 : B;
     const uint32_t row_bytes = (uint32_t)Wp * sizeof(float);
 
-    const bool tab_path = tmpl_path && d.obs_tab != nullptr;      // the host only sets obs_tab when every tile range is 16-byte aligned
+    const bool tab_path = (tmpl_path && d.obs_tab != nullptr) || fresh_tab;   // the host only sets obs_tab when every tile range is 16-byte aligned
+    const int n_slots = fresh_tab ? n_env : 1;                     // row images per buffer
+    const uint32_t slab_bytes = (uint32_t)Ltile * sizeof(float);
     const bool coupled = WIDE && d.coupled;                        // cross-tile sums needed inside the step
     if (uniform && tid == 0) {
         for (int i = 0; i < 5; ++i) mbar_init(s_bar + i, 1);
@@ -611,24 +633,47 @@ __global__ void __launch_bounds__(MAXT) advance_kernel(Dev d, int t0, int K, con
             mbar_expect_tx(s_bar + i, row_bytes);
             tma_load_1d(s_rows + i * Wp, d.table + (size_t)(d.start0 + t0 + i) * Wp, row_bytes, s_bar + i);
         }
+        if (tab_path) {                             // observation row of step 0 (table row start0 + t0 + 1) into buffer 0
+            mbar_expect_tx(s_bar + 3, (uint32_t)n_slots * slab_bytes);
+            for (int le = 0; le < n_slots; ++le)
+                tma_load_1d(smf + lo.tmpl + (size_t)le * lo.Lp, d.obs_tab + (size_t)(d.start0 + t0 + 1) * d.obs_pitch + k0, slab_bytes, s_bar + 3);
+        }
     }
     // block-wide staging: template columns and the battery curves of every building (dynamic indexing -> shared memory)
     if (tmpl_path && !tab_path) for (int k = tid; k < Ltile; k += nt) s_tcol[k] = __ldg(d.tcol + k0 + k);
     {
+        // per building: [PE_X 8][PE_Y 8][CP_X 8][CP_Y 8][PE_RW 8][CP_RW 8] (SmemCurves): x entries beyond the curve's points are
+        // +inf, RW[k] = refined reciprocal of the segment width x[k+1] - x[k]
         const auto* P = PSel<R>::p(d) + CL_P_PE_X0 * B;
-        for (int i = tid; i < nb * 32; i += nt) { const int bb = b0 + (i >> 5), j = i & 31; scurves[i] = (R)__ldg(P + j * B + bb); }
+        for (int i = tid; i < nb * kCurveTab; i += nt) {
+            const int bb = b0 + i / kCurveTab, j = i % kCurveTab;
+            R v;
+            if (j < 4 * CL_MAX_CURVE) {
+                v = (R)__ldg(P + j * B + bb);
+                const int which = j >> 4, k = j & 7;
+                if (!(j & 8) && k >= __ldg(d.ip + (which ? CL_IP_CP_N : CL_IP_PE_N) * B + bb)) v = Num<R>::inf();
+            } else {
+                const int which = (j - 4 * CL_MAX_CURVE) >> 3, k = j & 7;
+                const int n = __ldg(d.ip + (which ? CL_IP_CP_N : CL_IP_PE_N) * B + bb);
+                v = (R)0;
+                if (k + 1 < n) v = make_divisor((R)__ldg(P + (which * 16 + k + 1) * B + bb) - (R)__ldg(P + (which * 16 + k) * B + bb)).r;
+            }
+            scurves[i] = v;
+        }
     }
     UnitCtx<R> c;
     UnitState<R> s;
     int start_e = 0;
+    int dyn_lo = 0, dyn_hi = 0;                    // this building's (column, cl_dyn slot) pairs in d.dyn_cols
     RawActions act_next = {};
     if (active) {
+        if (fresh_tab) { dyn_lo = __ldg(d.dyn_off + b); dyn_hi = __ldg(d.dyn_off + b + 1); }
         load_ctx<R, THERMAL>(d, b, c);
         load_state<R, THERMAL>(d, u, s);
         start_e = __ldg(d.start + e);
         fetch_actions<R, THERMAL>(d, c, actions + (size_t)e * d.A, act_next);
     }
-    const R* curves = scurves + (active ? bl : 0) * 32;
+    const SmemCurves<R> curves = {scurves + (active ? bl : 0) * kCurveTab, d.curve_nmax};
     const float* lstm_w = nullptr;
     if (DYNAMICS) {
         if (d.lstm_smem) {                            // stage every building's packed LSTM weights in shared memory (16-byte copies)
@@ -665,11 +710,12 @@ __global__ void __launch_bounds__(MAXT) advance_kernel(Dev d, int t0, int K, con
     }
 
     // per-building PV generation of time row `rowp` -> dst[b]  (building.py:2554; the same value for every env of the block)
+    const Divisor<R> div1000 = make_divisor((R)1000);
     auto building_inputs = [&](const float* rowp, R* dst) {
         const auto* P = PSel<R>::p(d);
         for (int bb = lane; bb < nb; bb += 32) {
             const R pv = (R)__ldg(P + CL_P_PV_NOMINAL_POWER * B + b0 + bb);
-            dst[bb] = -dvd(pv * (R)rowp[__ldg(d.ip + CL_IP_C_SOLAR * B + b0 + bb)], (R)1000);
+            dst[bb] = -dvr(pv * (R)rowp[__ldg(d.ip + CL_IP_C_SOLAR * B + b0 + bb)], div1000);
         }
     };
     if (uniform) {
@@ -718,18 +764,12 @@ __global__ void __launch_bounds__(MAXT) advance_kernel(Dev d, int t0, int K, con
             if (central_sync) { if (WIDE) cluster_sync_all(); else { if (k > 0) __syncthreads(); __syncthreads(); } }
             if (tab_path) {
                 // observation slab of step k straight from the precomputed table: buffer pb holds columns [k0, k1) of table row
-                // start0 + t + 1 (requested one step ago); patch the outage columns, bulk-store it into every env row of the
-                // block, then request the row of step k + 1 into the other buffer once its previous stores have read it
+                // start0 + t + 1 (requested one step ago) - ONE image shared by every env (reference-parity rows are env-independent) or,
+                // with action-dependent columns, one image per env that the physics threads have patched before S1.  Patch the outage
+                // columns, bulk-store the image(s) into the env rows, then request the row of step k + 1 into the other buffer once
+                // its previous stores have read it
                 float* ok = obs + (size_t)k * d.E * d.L + (size_t)e0 * d.L + k0;
-                float* tmpl = smf + lo.tmpl + pb * lo.Lp;
-                const uint32_t bytes = (uint32_t)Ltile * sizeof(float);
-                if (k == 0) {
-                    if (lane == 0) {
-                        mbar_expect_tx(s_bar + 3, bytes);
-                        tma_load_1d(tmpl, d.obs_tab + (size_t)(d.start0 + t + 1) * d.obs_pitch + k0, bytes, s_bar + 3);
-                    }
-                    __syncwarp();
-                }
+                float* tmpl = smf + lo.tmpl + (size_t)pb * n_slots * lo.Lp;
                 mbar_wait(s_bar + 3 + pb, (uint32_t)((k >> 1) & 1));
                 if (d.has_outage && d.n_out_cols > 0) {
                     for (int i = lane; i < d.n_out_cols; i += 32) {
@@ -738,19 +778,21 @@ __global__ void __launch_bounds__(MAXT) advance_kernel(Dev d, int t0, int K, con
                             const int bb = __ldg(d.desc + kk).w;
                             float v = __ldg(d.outage + bb * d.T + t + 1);
                             if (d.obs_t) v = transform_obs(d.obs_t, kk, v);
-                            tmpl[kk - k0] = v;
+                            for (int le = 0; le < n_slots; ++le) tmpl[(size_t)le * lo.Lp + kk - k0] = v;
                         }
                     }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     __syncwarp();
                 }
                 if (lane == 0) {
-                    for (int le = 0; le < n_env; ++le) tma_store_1d(ok + (size_t)le * d.L, tmpl, bytes);
+                    for (int le = 0; le < n_env; ++le) tma_store_1d(ok + (size_t)le * d.L, tmpl + (fresh_tab ? (size_t)le * lo.Lp : 0), slab_bytes);
                     tma_store_commit();
                     if (k + 1 < K) {
                         tma_store_wait_read<1>();                               // the stores of step k - 1 have read the other buffer
-                        mbar_expect_tx(s_bar + 3 + (pb ^ 1), bytes);
-                        tma_load_1d(smf + lo.tmpl + (pb ^ 1) * lo.Lp, d.obs_tab + (size_t)(d.start0 + t + 2) * d.obs_pitch + k0, bytes, s_bar + 3 + (pb ^ 1));
+                        float* other = smf + lo.tmpl + (size_t)(pb ^ 1) * n_slots * lo.Lp;
+                        mbar_expect_tx(s_bar + 3 + (pb ^ 1), (uint32_t)n_slots * slab_bytes);
+                        for (int le = 0; le < n_slots; ++le)
+                            tma_load_1d(other + (size_t)le * lo.Lp, d.obs_tab + (size_t)(d.start0 + t + 2) * d.obs_pitch + k0, slab_bytes, s_bar + 3 + (pb ^ 1));
                     }
                 }
                 __syncwarp();
@@ -806,7 +848,7 @@ __global__ void __launch_bounds__(MAXT) advance_kernel(Dev d, int t0, int K, con
                 in.control_heating_demand = (c.a_hd >= 0 || c.a_coh >= 0);
             }
             CL_STAMP(2);
-            unit_step<R, THERMAL>(c.p, curves, 1, t, in, s, o);
+            unit_step<R, THERMAL>(c.p, curves, t, in, s, o);
             CL_STAMP(3);
             float t_in = row[c.c_tin];
             if (DYNAMICS && (c.p.flags & CL_F_DYNAMICS)) {
@@ -817,6 +859,18 @@ __global__ void __launch_bounds__(MAXT) advance_kernel(Dev d, int t0, int K, con
             red[nt + ul] = (float)o.cost;
             red[2 * nt + ul] = (float)o.emission;
             if (fused_reward) reward_inputs<R, THERMAL>(d, c, s, o, row, t_in, ri);     // everything the reward needs from row t
+            if (fresh_tab) {
+                // this unit's action-dependent observation columns go into its env's row image (loaded one step ago)
+                mbar_wait(s_bar + 3 + pb, (uint32_t)((k >> 1) & 1));
+                float* img = smf + lo.tmpl + ((size_t)pb * n_slots + e_l) * lo.Lp - k0;
+                for (int i = dyn_lo; i < dyn_hi; ++i) {
+                    const int2 cs = __ldg(d.dyn_cols + i);
+                    float v = dyn_value<R>(cs.y, c.p, s, o, (R)t_in);
+                    if (d.obs_t) v = transform_obs(d.obs_t, cs.x, v);
+                    img[cs.x] = v;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // generic-proxy writes -> visible to the TMA stores
+            }
 #ifdef CL_PHASE_TIMING
             if (want_dyn) {
 #else
@@ -950,7 +1004,7 @@ __global__ void __launch_bounds__(MAXT) advance_kernel(Dev d, int t0, int K, con
             }
         }
         CL_STAMP(6);
-        if (obs != nullptr && !tmpl_path) {
+        if (obs != nullptr && !tmpl_path && !fresh_tab) {
             write_obs_general(d, obs + (size_t)k * d.E * d.L, e0, n_env, t + 1, want_dyn ? s_dynbuf : nullptr, tid, np_, k0, k1, b0, nb);
             if (want_dyn && k + 1 < K) __syncthreads();                         // dynbuf is single-buffered
         }
@@ -1045,6 +1099,22 @@ __global__ void build_obs_table_kernel(Dev d, float* __restrict__ out) {
     }
 }
 
+// the env-independent observation rows of time steps t_first .. t_first + n - 1 (reference-parity observations after a step, SURVEY
+// A.6-1): what every env's row holds - for callers that want ONE row per step instead of E identical ones (cl_obs_rows)
+__global__ void obs_rows_kernel(Dev d, int t_first, int n, float* __restrict__ out) {
+    const long total = (long)n * d.L;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int r = (int)(i / d.L), k = (int)(i - (long)r * d.L);
+        const int t_obs = t_first + r;
+        const int cc = __ldg(d.tcol + k);
+        float v = 0.f;
+        if (cc >= 0) v = __ldg(d.table + (size_t)(d.start0 + t_obs) * d.Wp + cc);
+        else if (cc <= -2 && d.has_outage) v = __ldg(d.outage + (-2 - cc) * d.T + t_obs);
+        if (d.obs_t) v = transform_obs(d.obs_t, k, v);
+        out[i] = v;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // reset kernel: state <- initial values; obs <- observation at t = 0 (citylearn.py:1829-1886, building.py:2526-2564)
 // ------------------------------------------------------------------------------------------------------------------
@@ -1053,7 +1123,7 @@ __global__ void __launch_bounds__(MAXT) reset_kernel(Dev d, float* __restrict__ 
     extern __shared__ __align__(16) float smf[];
     const int nt = blockDim.x, tid = threadIdx.x;
     const int B = d.B, epb = d.envs_per_block;
-    const SmemLayout lo = smem_layout(d.tile_b, d.Wp, d.Lt, epb, nt, (int)sizeof(R), 0, d.tab_layout);
+    const SmemLayout lo = smem_layout(d.tile_b, d.Wp, d.Lt, epb, nt, (int)sizeof(R), d.lstm_smem, d.tab_layout, d.fresh_slots);
     float* s_dynbuf = smf + lo.dynbuf;
     // building tiles (wide districts): block (group, rank) owns buildings [b0, b0 + nb) and observation columns [k0, k1)
     const int rank = (int)blockIdx.x % d.tiles;
@@ -1143,7 +1213,7 @@ template <typename T> static int dev_copy(cl_env* env, const T* host, size_t n, 
 // gather the row every step - when it would exceed CL_B200_OBS_TABLE_MB (default 4096 MiB) or the observation row is not a
 // multiple of 16 bytes.
 static bool obs_table_fits(const Dev& d) {
-    if (!d.stale || (d.L & 3) != 0) return false;
+    if ((d.L & 3) != 0) return false;
     long budget_mb = 4096;
     if (const char* ev = std::getenv("CL_B200_OBS_TABLE_MB")) budget_mb = std::atol(ev);
     return (size_t)d.n_rows * (size_t)((d.L + 3) & ~3) * sizeof(float) <= (size_t)budget_mb * 1024 * 1024;
@@ -1194,12 +1264,23 @@ extern "C" int cl_create(const cl_district_desc* desc, cl_env** out) {
     d.stale = desc->stale_observations;
     for (int i = 0; i < 8; ++i) d.rp[i] = (float)desc->reward_params[i];
     env->precision = desc->precision;
-    int any_thermal = 0, any_dyn = 0;
+    int any_thermal = 0, any_dyn = 0, nmax = 2;
     for (int b = 0; b < B; ++b) {
         const int f = desc->iparams[CL_IP_FLAGS * B + b];
         any_thermal |= (f & CL_F_HAS_THERMAL);
         any_dyn |= (f & CL_F_DYNAMICS);
+        const int pe = desc->iparams[CL_IP_PE_N * B + b], cp = desc->iparams[CL_IP_CP_N * B + b];
+        if (pe < 2 || pe > CL_MAX_CURVE || cp < 2 || cp > CL_MAX_CURVE) { delete env; return fail(CL_ERR_INVALID, "cl_create: battery curves need 2 .. 8 points"); }
+        nmax = std::max(nmax, std::max(pe, cp));
+        // the segment search counts the points below x: the curve abscissae must ascend (energy_model.py:1083-1109 assumes it too)
+        for (int w = 0; w < 2; ++w)
+            for (int k = 0; k + 1 < (w ? cp : pe); ++k) {
+                const double* xs = desc->params + (size_t)(w ? CL_P_CP_X0 : CL_P_PE_X0) * B;
+                if (!(xs[(size_t)k * B + b] <= xs[(size_t)(k + 1) * B + b]) || !(xs[(size_t)k * B + b] >= 0.0))
+                    { delete env; return fail(CL_ERR_INVALID, "cl_create: battery curve abscissae must be non-negative and ascending"); }
+            }
     }
+    d.curve_nmax = nmax;
     env->thermal = any_thermal != 0;
     d.any_dynamics = any_dyn != 0;
     env->dynamics = any_dyn != 0;
@@ -1281,6 +1362,23 @@ extern "C" int cl_create(const cl_district_desc* desc, cl_env** out) {
         rc = dev_copy(env, oc.data(), oc.size(), &ocd);
         if (rc) { cl_destroy(env); return rc; }
         d.out_cols = ocd; d.n_out_cols = (int)oc.size();
+        // action-dependent observation columns grouped by building (fresh-observation table path)
+        std::vector<int32_t> doff((size_t)B + 1, 0);
+        for (int k = 0; k < d.L; ++k) if (desc->obs_desc[4 * (size_t)k] == CL_OBS_DYN) doff[(size_t)desc->obs_desc[4 * (size_t)k + 3] + 1]++;
+        for (int b = 0; b < B; ++b) doff[(size_t)b + 1] += doff[(size_t)b];
+        std::vector<int2> dcols((size_t)doff[(size_t)B]);
+        {
+            std::vector<int32_t> fill(doff.begin(), doff.end() - 1);
+            for (int k = 0; k < d.L; ++k) {
+                const int32_t* e4 = desc->obs_desc + 4 * (size_t)k;
+                if (e4[0] == CL_OBS_DYN) dcols[(size_t)fill[(size_t)e4[3]]++] = make_int2(k, e4[1]);
+            }
+        }
+        int2* dcd = nullptr; int32_t* dod = nullptr;
+        rc = dev_copy(env, dcols.data(), dcols.size(), &dcd);
+        if (!rc) rc = dev_copy(env, doff.data(), doff.size(), &dod);
+        if (rc) { cl_destroy(env); return rc; }
+        d.dyn_cols = dcd; d.dyn_off = dod;
     }
     {
         void* p = nullptr;
@@ -1348,7 +1446,7 @@ extern "C" int cl_create(const cl_district_desc* desc, cl_env** out) {
         // Many more units than one wave of 512-thread blocks can hold (e.g. 17 x 32768): the 1024-thread instantiation (64
         // registers, a few spills) keeps twice the warps resident per SM and wins by 10 % (fp64 flow) / 16 % (fp32) there
         // (profiles/README.md "Large env counts"); thermal / LSTM instantiations spill too much at 64 registers.
-        if (!any_thermal && !any_dyn && B <= 480) {
+        if (!any_thermal && !any_dyn && B <= 480 && d.stale) {      // (per-env row images of fresh observations need the 512-thread geometry)
             const int epb_t = std::max(1, std::min(target / B, d.E));
             const long blocks_t = (d.E + epb_t - 1) / epb_t;
             const int epb_big = std::max(1, 960 / B);
@@ -1365,6 +1463,16 @@ extern "C" int cl_create(const cl_district_desc* desc, cl_env** out) {
     d.tab_layout = tab_fits ? 1 : 0;
     env->threads = ((epb * B + 31) / 32) * 32;
     env->blocks = (d.E + epb - 1) / epb;
+    // observations with action-dependent columns: per-env row images (2 x envs_per_block x L floats of shared memory) when they fit
+    // and are large enough to host the general writer's dynbuf, which aliases them (smem_layout)
+    auto fresh_fits = [&](const Dev& q, int nthreads) -> bool {
+        if (q.stale || !q.tab_layout) return false;
+        Dev t = q; t.fresh_slots = 1;
+        const int lp = (t.Lt + 3) & ~3;
+        if ((size_t)2 * t.envs_per_block * lp < (size_t)nthreads * CL_NDYN) return false;
+        return smem_bytes(t, nthreads, false, env->precision == CL_PRECISION_FP64 ? 8 : 4) <= 200 * 1024;
+    };
+    if (!d.stale) { d.fresh_slots = fresh_fits(d, env->threads + 32) ? 1 : 0; d.tab_layout = d.fresh_slots; }
     // Wide districts: one env per thread-block CLUSTER, the buildings split into `tiles` tiles of `tile_b` (one CTA each); the
     // district sums travel through distributed shared memory.  Chosen when a whole env does not fit one 512-thread block
     // (CL_B200_TILES forces a tile count for experiments).
@@ -1407,7 +1515,7 @@ extern "C" int cl_create(const cl_district_desc* desc, cl_env** out) {
             const int thr = ((tb + 31) / 32) * 32 + 32;
             bool aligned = true;
             for (int r = 0; r <= nt_; ++r) aligned = aligned && (tk[r] & 3) == 0;
-            Dev probe = d; probe.tiles = nt_; probe.tile_b = tb; probe.Lt = lt; probe.envs_per_block = 1;
+            Dev probe = d; probe.tiles = nt_; probe.tile_b = tb; probe.Lt = lt; probe.envs_per_block = 1; probe.fresh_slots = 0;
             probe.tab_layout = (tab_fits && aligned) ? 1 : 0;
             const size_t sm = smem_bytes(probe, thr, true, env->precision == CL_PRECISION_FP64 ? 8 : 4);
             if (sm > 200 * 1024) continue;
@@ -1435,6 +1543,8 @@ extern "C" int cl_create(const cl_district_desc* desc, cl_env** out) {
             env->wide = true;
             env->threads = ((tb + 31) / 32) * 32;
             env->blocks = d.E * best_nt;
+            d.fresh_slots = 0;
+            if (!d.stale) { d.fresh_slots = fresh_fits(d, env->threads + 32) ? 1 : 0; d.tab_layout = d.fresh_slots; }
         }
     }
     if (!env->wide && B > 992) { cl_destroy(env); return fail(CL_ERR_UNSUPPORTED, "cl_create: districts wider than 992 buildings with LSTM dynamics are not supported"); }
@@ -1578,7 +1688,8 @@ extern "C" int cl_reset(cl_env* env, const int32_t* episode_start, int32_t unifo
     Dev& d = env->d;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (episode_time_steps < 2) return fail(CL_ERR_INVALID, "cl_reset: episode_time_steps must be >= 2");
-    if (d.has_outage && env->outage_T < episode_time_steps) return fail(CL_ERR_STATE, "cl_reset: outage signal shorter than the episode");
+    // the kernels index the signal with the episode length as the row stride
+    if (d.has_outage && env->outage_T != episode_time_steps) return fail(CL_ERR_STATE, "cl_reset: the outage signal must have exactly episode_time_steps entries per building (cl_set_outage)");
     if (episode_start == nullptr) {
         if (uniform_start < 0 || uniform_start + episode_time_steps > d.n_rows) return fail(CL_ERR_INVALID, "cl_reset: episode window outside the table");
         fill_start_kernel<<<(d.E + 255) / 256, 256, 0, st>>>(const_cast<int32_t*>(d.start), d.E, uniform_start);
@@ -1624,6 +1735,18 @@ extern "C" int cl_rollout(cl_env* env, int32_t n_steps, const float* actions, fl
 #endif
     CUDA_TRY(cudaGetLastError());
     env->t += n_steps;
+    return CL_OK;
+}
+
+extern "C" int cl_obs_rows(cl_env* env, int32_t first_time_step, int32_t n_rows, float* rows, cl_stream stream) {
+    if (!env || !rows) return fail(CL_ERR_INVALID, "cl_obs_rows: null argument");
+    if (env->t < 0) return fail(CL_ERR_STATE, "cl_obs_rows: call cl_reset first");
+    if (!env->d.stale || !env->d.uniform_start) return fail(CL_ERR_STATE, "cl_obs_rows: observation rows are only env-independent with stale_observations and one episode window for all envs");
+    if (n_rows < 1 || first_time_step < 1 || first_time_step + n_rows > env->T) return fail(CL_ERR_INVALID, "cl_obs_rows: time steps must lie in [1, T - 1] (the observation at t = 0 differs per env)");
+    const long total = (long)n_rows * env->d.L;
+    obs_rows_kernel<<<(unsigned)std::min<long>((total + 255) / 256, 4096), 256, 0, static_cast<cudaStream_t>(stream)>>>(env->d, first_time_step, n_rows, rows);
+    CUDA_TRY(cudaGetLastError());
+    env->launches++;
     return CL_OK;
 }
 
@@ -1732,6 +1855,54 @@ extern "C" int cl_kpi_read(cl_env* env, double* unit_dev, double* env_dev, cl_st
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (unit_dev) CUDA_TRY(cudaMemcpyAsync(unit_dev, env->kpi_unit, (size_t)env->d.U * CL_NKPI_UNIT * sizeof(double), cudaMemcpyDeviceToDevice, st));
     if (env_dev) CUDA_TRY(cudaMemcpyAsync(env_dev, env->kpi_env, (size_t)env->d.E * 2 * CL_NKPI_ENV * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    return CL_OK;
+}
+
+// FP32 FMA throughput of the device (the roofline of the LSTM-dynamics path): 16 independent FFMA chains per thread
+__global__ void fma_peak_kernel(float* __restrict__ out, int iters) {
+    float a[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) a[j] = 1.0f + 1e-3f * (float)(threadIdx.x + j);
+    const float b = 0.99999f, c = 1e-6f;
+#pragma unroll 1
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) a[j] = fmaf(a[j], b, c);
+        }
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) sum += a[j];
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = sum;
+}
+
+extern "C" int cl_measure_fma_peak(double* tflops) {
+    if (!tflops) return fail(CL_ERR_INVALID, "cl_measure_fma_peak: null argument");
+    int dev = 0, n_sm = 148;
+    CUDA_TRY(cudaGetDevice(&dev));
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    const int blocks = n_sm * 8, threads = 256, iters = 2048;
+    float* out = nullptr;
+    CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&out), (size_t)blocks * threads * sizeof(float)));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    double best = 0.0;
+    for (int rep = 0; rep < 4; ++rep) {
+        cudaEventRecord(e0);
+        fma_peak_kernel<<<blocks, threads>>>(out, iters);
+        cudaEventRecord(e1);
+        if (cudaEventSynchronize(e1) != cudaSuccess) break;
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double flops = 2.0 * 16 * 8 * (double)iters * blocks * threads;
+        if (rep > 0 && ms > 0.f) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(out);
+    CUDA_TRY(cudaGetLastError());
+    *tflops = best;
     return CL_OK;
 }
 

@@ -37,6 +37,13 @@ def make_sharded_env(schema, total_envs: int, device=None, **kwargs):
     offset, count = shard_range(total_envs, rank, world)
     if count == 0:
         raise ValueError(f'rank {rank} of {world} would own no env out of {total_envs}')
+    if device is None and torch.cuda.is_available():
+        # one process per GPU: this rank's device is LOCAL_RANK (torchrun), not whatever happens to be current (cuda:0 on every rank
+        # unless the caller ran torch.cuda.set_device)
+        import os
+        local = os.environ.get('LOCAL_RANK')
+        index = int(local) if local is not None else (rank % torch.cuda.device_count() if world > 1 else torch.cuda.current_device())
+        device = torch.device('cuda', index)
     env = CityLearnEnv(schema, num_envs=count, device=device, **kwargs)
     env.env_offset, env.total_envs = offset, total_envs
     return env

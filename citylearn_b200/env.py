@@ -180,10 +180,14 @@ class CityLearnEnv:
                 self._h.kpi_enable(True)
             self._kpi_valid = True
             E = self.num_envs
-            # observations and rewards share one allocation so that the host path needs ONE device->host copy per step
-            self._out = torch.zeros(E * (self._obs_dim + self._reward_dim), dtype=torch.float32, device=self.device)
-            self._obs = self._out[:E * self._obs_dim].view(E, self._obs_dim)
-            self._reward = self._out[E * self._obs_dim:].view(E, self._reward_dim)
+            # observations, rewards and the shared observation row live in one allocation [obs E*L | reward E*R | row L] so that the
+            # host path needs ONE device->host copy per step: head (obs + reward) or tail (reward + the row every env shares)
+            nL, nR = E * self._obs_dim, E * self._reward_dim
+            self._out = torch.zeros(nL + nR + self._obs_dim, dtype=torch.float32, device=self.device)
+            self._obs = self._out[:nL].view(E, self._obs_dim)
+            self._reward = self._out[nL:nL + nR].view(E, self._reward_dim)
+            self._row = self._out[nL + nR:]
+            self._obs_current = True            # False after a shared-row host step: self._obs was not written
             self._district = torch.zeros((E, 3), dtype=torch.float32, device=self.device)
             self._trace = (torch.zeros((E, spec.n_buildings, S.NDYN), dtype=torch.float32, device=self.device)
                            if (rid < 0 or debug_trace) else None)
@@ -196,10 +200,12 @@ class CityLearnEnv:
             self._stage_event = [torch.cuda.Event() for _ in range(self._stage_n)]
             self._stage_used = [False] * self._stage_n
             self._stage_i = 0
-            self._out_pinned = torch.zeros(E * (self._obs_dim + self._reward_dim), dtype=torch.float32).pin_memory()
-            self._obs_pinned = self._out_pinned[:E * self._obs_dim].view(E, self._obs_dim)
-            self._reward_pinned = self._out_pinned[E * self._obs_dim:].view(E, self._reward_dim)
+            self._out_pinned = torch.zeros(nL + nR + self._obs_dim, dtype=torch.float32).pin_memory()
+            self._obs_pinned = self._out_pinned[:nL].view(E, self._obs_dim)
+            self._reward_pinned = self._out_pinned[nL:nL + nR].view(E, self._reward_dim)
             self._obs_host, self._reward_host = self._obs_pinned.numpy(), self._reward_pinned.numpy()
+            self._row_host = self._out_pinned[nL + nR:].numpy()
+            self._roll = None                   # buffers of rollout_host, keyed by K
 
     def configure_transforms(self, observation_transform: Optional[str] = 'unchanged', normalized_actions: Optional[bool] = None):
         """Fuse wrapper semantics into the kernels (used by `citylearn_b200.wrappers`): `observation_transform` in
@@ -326,6 +332,13 @@ class CityLearnEnv:
     @property
     def observations(self):
         """Current observation: reference-shaped lists for num_envs == 1, else the `[E, L]` CUDA tensor."""
+        if not self._obs_current and self.shared_observation_row:
+            # the last step(s) did not materialise the [E, L] slab (shared-row host path, rollout without `obs`): every env's row is
+            # the shared row of the current time step
+            with torch.cuda.device(self.device):
+                self._h.obs_rows(self.time_step, 1, self._row.data_ptr(), self._stream())
+                self._obs.copy_(self._row.expand(self.num_envs, self._obs_dim))
+            self._obs_current = True
         return self._shape_obs(self._obs) if self.num_envs == 1 else self._obs
 
     def get_metadata(self) -> Mapping[str, Any]:
@@ -340,7 +353,8 @@ class CityLearnEnv:
         return {}
 
     def close(self):
-        self._h.close()
+        with torch.cuda.device(self.device):
+            self._h.close()
 
     # ---------------------------------------------------------------------------------------------
     def _stream(self) -> int:
@@ -372,8 +386,17 @@ class CityLearnEnv:
             self._h.set_outage(self._outage if any(b.simulate_power_outage for b in self.spec.buildings) else None, stream)
             per_env = None if not options else options.get('episode_start')
             if per_env is not None:
-                self._start_dev = torch.as_tensor(per_env, dtype=torch.int32, device=self.device).contiguous()
-                assert self._start_dev.shape == (self.num_envs,)
+                starts = torch.as_tensor(per_env).to(torch.int64).reshape(-1).cpu()
+                if starts.shape != (self.num_envs,):
+                    raise ValueError(f"options['episode_start'] must hold one table row per env ({self.num_envs}), got {tuple(starts.shape)}")
+                lo, hi = int(starts.min()), int(starts.max())
+                first, last = self.episode_tracker.simulation_start_time_step, self.episode_tracker.simulation_end_time_step
+                if lo < first or hi + T - 1 > last or hi + T > self.spec.table.shape[0]:
+                    raise ValueError(f"options['episode_start']: every window [start, start + {T}) must lie inside the simulation period "
+                                     f'[{first}, {last}] (got starts in [{lo}, {hi}])')
+                if self._outage.any():
+                    raise ValueError('per-env episode starts cannot be combined with power-outage signals (one signal per episode window)')
+                self._start_dev = starts.to(device=self.device, dtype=torch.int32).contiguous()
                 self._h.reset(self._start_dev.data_ptr(), 0, T, self._obs.data_ptr(), stream)
             else:
                 self._start_dev = torch.full((self.num_envs,), start, dtype=torch.int32, device=self.device)
@@ -385,6 +408,8 @@ class CityLearnEnv:
             self._hist_district = torch.zeros((T - 1, 3), dtype=torch.float32, device=self.device)
             self._hist_valid = True
         self._kpi_valid = True
+        self._obs_current = True
+        self._uniform_start = per_env is None
         if self.num_envs == 1:
             return self._shape_obs(self._obs), self.get_info()
         return self._obs, self.get_info()
@@ -434,14 +459,19 @@ class CityLearnEnv:
         self._stage_used[i] = True
 
     def step(self, actions):
+        return self._advance(actions, True)
+
+    def _advance(self, actions, write_obs: bool):
+        """One time step; `write_obs=False` skips the [E, L] observation slab (shared-row host path)."""
         if self.terminated:
             raise RuntimeError('step() called after the episode terminated; call reset().')
         with torch.cuda.device(self.device):
             a, ref_shaped = self._parse_actions(actions)
             stream = self._stream()
             fused = self._reward_id >= 0
-            self._h.step(a.data_ptr(), self._obs.data_ptr(), self._reward.data_ptr() if fused else None, self._district.data_ptr(),
-                         None if self._trace is None else self._trace.data_ptr(), stream)
+            self._h.step(a.data_ptr(), self._obs.data_ptr() if write_obs else None, self._reward.data_ptr() if fused else None,
+                         self._district.data_ptr(), None if self._trace is None else self._trace.data_ptr(), stream)
+            self._obs_current = write_obs
             if not fused:
                 self._python_reward()
             if self._track_kpis:
@@ -460,13 +490,78 @@ class CityLearnEnv:
             return self._shape_obs(self._obs), rew, terminated, False, self.get_info()
         return self._obs, self._reward, terminated, False, self.get_info()
 
-    def step_host(self, actions: np.ndarray) -> Tuple[np.ndarray, np.ndarray, bool]:
+    @property
+    def shared_observation_row(self) -> bool:
+        """True when every env's observation row after a step is the same row: reference-parity (stale) observations and one
+        episode window for all envs - the host paths then move ONE row instead of E identical ones."""
+        return self.stale_observations and getattr(self, '_uniform_start', True)
+
+    def step_host(self, actions: np.ndarray, full_observations: Optional[bool] = None) -> Tuple[np.ndarray, np.ndarray, bool]:
         """End-to-end host path: host ndarray actions in, host ndarrays out (pinned staging, one H2D + one D2H copy, one sync).
-        The returned arrays are views of a pinned buffer that the next call overwrites."""
-        _, _, terminated, _, _ = self.step(np.asarray(actions, dtype=np.float32))
-        self._out_pinned.copy_(self._out, non_blocking=True)
-        torch.cuda.current_stream(self.device).synchronize()
+
+        With `shared_observation_row` (and `full_observations` not forced) the kernel skips the [E, L] observation slab, the
+        D2H copy is rewards + ONE observation row, and the returned observations are a read-only broadcast view `[E, L]` of it.
+        The returned arrays are views of pinned buffers that the next call overwrites."""
+        shared = self.shared_observation_row if full_observations is None else not full_observations
+        if shared and not self.shared_observation_row:
+            raise ValueError('full_observations=False needs stale_observations=True and one episode window for all envs')
+        E, L, R = self.num_envs, self._obs_dim, self._reward_dim
+        _, _, terminated, _, _ = self._advance(np.asarray(actions, dtype=np.float32), not shared)
+        with torch.cuda.device(self.device):
+            if shared:
+                self._h.obs_rows(self.time_step, 1, self._row.data_ptr(), self._stream())
+                self._out_pinned[E * L:].copy_(self._out[E * L:], non_blocking=True)
+            else:
+                self._out_pinned[:E * (L + R)].copy_(self._out[:E * (L + R)], non_blocking=True)
+            torch.cuda.current_stream(self.device).synchronize()
+        if shared:
+            return np.broadcast_to(self._row_host, (E, L)), self._reward_host, terminated
         return self._obs_host, self._reward_host, terminated
+
+    def rollout_host(self, actions: np.ndarray, full_observations: Optional[bool] = None):
+        """K steps from a host block of actions `[K, E, A]`: one H2D copy, one `cl_rollout` launch, one D2H copy, one sync.
+        Returns `(observations, rewards [K, E, R], terminated)` as views of pinned host buffers (overwritten by the next call of the
+        same K); observations are `[K, L]` - one row per step - with `shared_observation_row`, else `[K, E, L]`."""
+        if self._reward_id < 0:
+            raise NotImplementedError('rollout_host needs a built-in (fused) reward function')
+        shared = self.shared_observation_row if full_observations is None else not full_observations
+        if shared and not self.shared_observation_row:
+            raise ValueError('full_observations=False needs stale_observations=True and one episode window for all envs')
+        actions = np.asarray(actions, dtype=np.float32)
+        K = actions.shape[0]
+        E, A, L, R = self.num_envs, self.spec.action_dim, self._obs_dim, self._reward_dim
+        actions = actions.reshape(K, E, A)
+        if self.time_step + K > self.time_steps - 1:
+            raise RuntimeError('rollout_host: the block runs past the end of the episode')
+        with torch.cuda.device(self.device):
+            key = (K, shared)
+            if self._roll is None or self._roll['key'] != key:
+                n_obs = K * L if shared else K * E * L
+                out = torch.empty(K * E * R + n_obs, dtype=torch.float32, device=self.device)
+                out_pinned = torch.empty(K * E * R + n_obs, dtype=torch.float32).pin_memory()
+                self._roll = {'key': key, 'act': torch.empty((K, E, A), dtype=torch.float32, device=self.device),
+                              'act_pinned': torch.empty((K, E, A), dtype=torch.float32).pin_memory(), 'out': out, 'out_pinned': out_pinned}
+            r = self._roll
+            np.copyto(r['act_pinned'].numpy(), actions)
+            r['act'].copy_(r['act_pinned'], non_blocking=True)
+            rew = r['out'][:K * E * R]
+            obs = r['out'][K * E * R:]
+            stream = self._stream()
+            t_first = self.time_step + 1
+            self._h.rollout(K, r['act'].data_ptr(), None if shared else obs.data_ptr(), rew.data_ptr(), self._district.data_ptr() if K == 1 else None, stream)
+            if shared:
+                self._h.obs_rows(t_first, K, obs.data_ptr(), stream)
+            r['out_pinned'].copy_(r['out'], non_blocking=True)
+            torch.cuda.current_stream(self.device).synchronize()
+        self.time_step += K
+        self._hist_valid = False
+        self._kpi_valid = False
+        self._obs_current = False
+        if not shared:
+            self._obs.copy_(obs.view(K, E, L)[-1])
+            self._obs_current = True
+        host = r['out_pinned'].numpy()
+        return host[K * E * R:].reshape((K, L) if shared else (K, E, L)), host[:K * E * R].reshape(K, E, R), self.terminated
 
     def rollout(self, actions: torch.Tensor, obs: Optional[torch.Tensor] = None, reward: Optional[torch.Tensor] = None,
                 district: Optional[torch.Tensor] = None):
@@ -481,6 +576,9 @@ class CityLearnEnv:
         self.time_step += K
         self._hist_valid = False          # rollouts do not produce the per-unit trace evaluate() needs
         self._kpi_valid = False
+        if obs is not None:
+            self._obs.copy_(obs[K - 1])
+        self._obs_current = obs is not None
         return obs, reward, self.terminated
 
     # ---------------------------------------------------------------------------------------------
@@ -538,17 +636,50 @@ class CityLearnEnv:
 
     # ---------------------------------------------------------------------------------------------
     def state_dict(self) -> Dict[str, Any]:
-        """Checkpoint of the mutable simulation state."""
-        n = self._h.state_size()
-        buf = torch.empty(n, dtype=torch.uint8, device=self.device)
-        self._h.get_state(buf.data_ptr(), self._stream())
-        return {'state': buf, 'time_step': self.time_step, 'episode': self.episode_tracker.episode,
-                'episode_start': self._start_dev.clone(), 'obs': self._obs.clone()}
+        """Checkpoint of the mutable simulation state and of the episode it belongs to."""
+        with torch.cuda.device(self.device):
+            n = self._h.state_size()
+            buf = torch.empty(n, dtype=torch.uint8, device=self.device)
+            self._h.get_state(buf.data_ptr(), self._stream())
+        _ = self.observations                  # refreshes self._obs after shared-row host steps
+        obs = self._obs.clone()
+        tr = self.episode_tracker
+        return {'state': buf, 'time_step': self.time_step, 'episode': tr.episode,
+                'episode_window': (tr.episode_start_time_step, tr.episode_end_time_step), 'uniform_start': self._uniform_start,
+                'episode_start': self._start_dev.clone(), 'outage': np.array(self._outage, copy=True), 'obs': obs}
 
     def load_state_dict(self, sd: Mapping[str, Any]):
-        self._h.set_state(sd['state'].data_ptr(), int(sd['time_step']), self._stream())
-        self.time_step = int(sd['time_step'])
-        self._obs.copy_(sd['obs'])
+        """Resume a checkpoint: the episode window(s), the outage signal and the device state are all restored, so loading into a fresh
+        env or after a reset() that picked another window continues on the checkpoint's time-series rows.  Per-step history and KPI
+        accumulators are not part of a checkpoint: `evaluate()` / `evaluate_batched()` are unavailable until the next reset()."""
+        start, end = (int(v) for v in sd['episode_window'])
+        T = end - start + 1
+        starts = torch.as_tensor(sd['episode_start']).to(device=self.device, dtype=torch.int32).contiguous()
+        if starts.shape != (self.num_envs,):
+            raise ValueError(f'checkpoint holds {tuple(starts.shape)} episode starts, this env has {self.num_envs} envs')
+        if int(starts.max()) + T > self.spec.table.shape[0] or int(starts.min()) < 0:
+            raise ValueError('checkpoint episode window lies outside this dataset')
+        if not 0 <= int(sd['time_step']) <= T - 1:
+            raise ValueError('checkpoint time step outside its episode window')
+        tr = self.episode_tracker
+        tr.episode, tr.episode_start_time_step, tr.episode_end_time_step = int(sd['episode']), start, end
+        self._outage = np.array(sd['outage'], copy=True)
+        with torch.cuda.device(self.device):
+            stream = self._stream()
+            self._h.set_outage(self._outage if any(b.simulate_power_outage for b in self.spec.buildings) else None, stream)
+            self._start_dev = starts
+            self._uniform_start = bool(sd.get('uniform_start', True))
+            if self._uniform_start:
+                self._h.reset(None, start, T, None, stream)
+            else:
+                self._h.reset(self._start_dev.data_ptr(), 0, T, None, stream)
+            self._h.set_state(sd['state'].data_ptr(), int(sd['time_step']), stream)
+            self.time_step = int(sd['time_step'])
+            self._obs.copy_(sd['obs'])
+        self._obs_current = True
+        self._hist_valid = False
+        self._kpi_valid = False
+        self._rsum = self._rmin = self._rmax = None
 
     @property
     def trace(self) -> Optional[torch.Tensor]:

@@ -196,6 +196,15 @@ int cl_step(cl_env* env, const float* actions, float* obs, float* reward, float*
 int cl_rollout(cl_env* env, int32_t n_steps, const float* actions, float* obs, float* reward, float* district,
                cl_stream stream);
 
+/*
+ * The observation rows shared by every env after a step: with stale_observations (reference parity) and one
+ * episode window for all envs the E rows of `obs` are identical, so a caller that moves observations across PCIe can pass
+ * obs = NULL to cl_step / cl_rollout and fetch ONE row per time step instead (CityLearnEnv.observations,
+ * citylearn/citylearn.py:451-485).
+ *   rows  dev [n_rows][L]   observations at time steps first_time_step .. first_time_step + n_rows - 1, all within [1, T - 1]
+ */
+int cl_obs_rows(cl_env* env, int32_t first_time_step, int32_t n_rows, float* rows, cl_stream stream);
+
 /* Current time step t of the handle (host value; steps done since the last reset). */
 int cl_time_step(const cl_env* env, int32_t* t);
 
@@ -249,6 +258,10 @@ int cl_kpi_read(cl_env* env, double* unit_dev, double* env_dev, cl_stream stream
 /* Launch geometry chosen at cl_create: CTAs per launch, threads per CTA (incl. the helper warp) and building tiles per env
  * (1: a block owns whole envs; > 1: one thread-block cluster per env, one CTA per tile of buildings). */
 int cl_launch_geometry(const cl_env* env, int32_t* blocks, int32_t* threads, int32_t* tiles);
+
+/* Measured FP32 FMA throughput of the current device in TFLOP/s (a microbenchmark of independent FFMA chains): the roofline
+ * denominator of the LSTM-dynamics path, which is FP32-FMA bound.  Synchronises the device. */
+int cl_measure_fma_peak(double* tflops);
 
 const char* cl_last_error(void);
 int cl_abi_version(void);

@@ -712,7 +712,52 @@ class OracleReward:
         return r
 
 
-def resolve_reward(spec: S.DistrictSpec) -> OracleReward:
+class OracleMultiReward:
+    """MultiBuildingRewardFunction (reward_function.py:90-117, built at citylearn.py:2106-2141): building i is rewarded by its own
+    function, each evaluated on that building's observations alone (so a district sum is that building's own value)."""
+
+    def __init__(self, per_building):
+        self.per_building = per_building          # [OracleReward] in building order
+
+    def calculate(self, env, t, dyn, district):
+        cols = []
+        for bi, rf in enumerate(self.per_building):
+            own = dyn[:, bi:bi + 1, :]
+            own_district = np.stack([own[:, 0, DYN['net_electricity_consumption']]] * 3, axis=1)
+            sub = _OneBuilding(env, bi)
+            cols.append(np.asarray(rf.calculate(sub, t, own, own_district), dtype=np.float64)[:, 0])
+        return np.stack(cols, axis=1).astype(np.float32)
+
+
+class _OneBuilding:
+    """View of an OracleEnv restricted to building `bi` (what a per-building reward function sees)."""
+
+    def __init__(self, env, bi):
+        self._env, self._bi = env, bi
+        self.central = False
+
+    def col(self, name, t):
+        return self._env.col(name, t)[..., self._bi:self._bi + 1]
+
+    def col32(self, name, t):
+        return self._env.col32(name, t)[..., self._bi:self._bi + 1]
+
+    def P(self, name):
+        return self._env.P(name)[..., self._bi:self._bi + 1]
+
+
+def resolve_reward(spec: S.DistrictSpec):
     rt = spec.reward_type
+    if isinstance(rt, dict):                      # per-building reward functions, 'default' fallback (citylearn.py:2106-2141)
+        attrs = spec.reward_attributes or {}
+        default_type = rt.get('default') or (next(iter(rt.values())) if rt else None)
+        default_attrs = attrs.get('default')
+        if default_attrs is None and attrs:
+            default_attrs = next(iter(attrs.values()))
+        per = []
+        for b in spec.buildings:
+            r_type = rt.get(b.name, default_type)
+            per.append(OracleReward(r_type.split('.')[-1], **(attrs.get(b.name, default_attrs) or {})))
+        return OracleMultiReward(per)
     name = rt.split('.')[-1] if isinstance(rt, str) else getattr(rt, '__name__', str(rt))
     return OracleReward(name, **(spec.reward_attributes or {}))

@@ -398,6 +398,11 @@ CASES = {
     'c2_solar_penalty': dict(dataset=PALL, reward={'type': 'citylearn.reward_function.SolarPenaltyReward', 'attributes': {}}, steps=120),
     'c2_central_exp2': dict(dataset=PALL, overrides={'central_agent': True},
                             reward={'type': 'citylearn.reward_function.RewardFunction', 'attributes': {'exponent': 2.0}}, steps=60),
+    # per-building reward functions (MultiBuildingRewardFunction, citylearn.py:2106-2141): named entries + the 'default' fallback
+    'c1_multi_reward': dict(dataset=P1, reward={'type': {'Building_1': 'citylearn.reward_function.RewardFunction',
+                                                         'Building_2': 'citylearn.reward_function.IndependentSACReward',
+                                                         'default': 'citylearn.reward_function.SolarPenaltyReward'},
+                                                'attributes': {'Building_1': {'exponent': 2.0}, 'default': {}}}, steps=80, seed=23),
     # episode windows: consecutive splits inside a sub-range, two episodes
     'c1_episodes': dict(dataset=P1, overrides={'simulation_start_time_step': 100, 'simulation_end_time_step': 1299,
                                                'episode_time_steps': 240}, episodes=3, seed=3),

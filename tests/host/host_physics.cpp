@@ -29,6 +29,7 @@ static void load_params_host(const double* P, const int32_t* ip, int B, int b, B
         tanks[i]->has_max_in = p.flags & fin[i]; tanks[i]->has_max_out = p.flags & fout[i];
     }
 #undef LD
+    derive_params(p);
 }
 
 // state: double [6][U] (soc_b, cap_deg, rte_b = sqrt(efficiency), soc_cs, soc_hs, soc_ds); dyn out: float [U][CL_NDYN]
@@ -70,7 +71,7 @@ static void step_impl(int B, int E, int W, const double* P, const int32_t* ip, c
             s.soc_b = (R)state[0 * U + u]; s.cap_deg = (R)state[1 * U + u]; s.rte_b = (R)state[2 * U + u];
             s.soc_cs = (R)state[3 * U + u]; s.soc_hs = (R)state[4 * U + u]; s.soc_ds = (R)state[5 * U + u];
             UnitResult<R> o;
-            unit_step<R, true, R>(p, curves.data() + b, B, t, in, s, o);
+            unit_step<R, true>(p, StridedCurves<R, R>{curves.data() + b, B}, t, in, s, o);
             state[0 * U + u] = (double)s.soc_b; state[1 * U + u] = (double)s.cap_deg; state[2 * U + u] = (double)s.rte_b;
             state[3 * U + u] = (double)s.soc_cs; state[4 * U + u] = (double)s.soc_hs; state[5 * U + u] = (double)s.soc_ds;
             float* d = dyn_out + (size_t)u * CL_NDYN;

@@ -16,7 +16,8 @@ from helpers import (TRACE_TO_DYN, actions_of, load_golden, max_abs_diff, observ
 
 pytestmark = pytest.mark.gpu
 
-NON_LSTM_CASES = ['c1_phase1_300', 'c1_phase1_central', 'c1_episodes', 'c1_subhour', 'c2_marl', 'c2_isac', 'c2_solar_penalty', 'c2_central_exp2', 'c2_year',
+NON_LSTM_CASES = ['c1_phase1_300', 'c1_phase1_central', 'c1_episodes', 'c1_subhour', 'c1_multi_reward',   # (per-building reward functions: Python plug-in path)
+                  'c2_marl', 'c2_isac', 'c2_solar_penalty', 'c2_central_exp2', 'c2_year',
                   # 2020 schema: autosized heat pumps / heaters / tanks, cooling + DHW tank actions
                   'c6_tanks_2020', 'c6_tanks_2020_marl_central',
                   'c4_slice32',      # first 32 buildings of the synthetic wide district (BASELINE configs[3])
@@ -29,7 +30,8 @@ NON_LSTM_CASES = ['c1_phase1_300', 'c1_phase1_central', 'c1_episodes', 'c1_subho
 POW_TIE_CASES = ['c6_tanks_2020_solar_penalty']
 LSTM_CASES = ['c3_marl', 'c3_default_central_comfort', 'c3_solar_comfort',
               'c6_baeda3',      # cooling tank + cooling-device action, LSTM hidden 8 / 11 inputs
-              'c7_phase3']      # six LSTM buildings with stochastic outages, central agent
+              'c7_phase3',      # six LSTM buildings with stochastic outages, central agent
+              'c9_dual_mode']   # `cooling_or_heating_device` (one signed action for both heat pumps), hvac modes 2 / 3 (synthetic.SyntheticDualModeSource)
 
 
 def make_env(cfg, **kw):
@@ -521,3 +523,28 @@ def test_observation_table_with_normalized_wrapper(monkeypatch):
     make = lambda: W.NormalizedSpaceWrapper(CityLearnEnv('citylearn_challenge_2022_phase_1', num_envs=8,          # noqa: E731
                                                          buildings=['Building_1', 'Building_2', 'Building_3', 'Building_4']))
     _table_vs_gather(make, 40, monkeypatch)
+
+
+@pytest.mark.parametrize('fixture', ['trace_fuzz.json.gz', 'trace_datasets.json.gz'])
+def test_fuzzed_reference_runs_on_gpu(fixture):
+    """The short reference runs of tests/test_oracle_golden.py::test_oracle_matches_fuzzed_reference_runs through the C ABI."""
+    import gzip
+    import json
+    import numpy as np
+    from citylearn_b200 import CityLearnEnv
+    from helpers import GOLDEN
+    for c in json.load(gzip.open(GOLDEN / fixture, 'rt'))['cases']:
+        sch, src, ov = schema_for({'dataset': c['dataset'], 'reward': c['reward'], 'overrides': c['overrides']})
+        env = CityLearnEnv(sch, data_source=src, num_envs=1, **ov)
+        lstm = any(b.dynamics for b in env.spec.buildings)
+        tag = (c['dataset'], c['overrides'])
+        obs, _ = env.reset()
+        assert max_abs_diff(np.array([v for row in obs for v in row], dtype='float32'), np.array(c['reset_obs'], dtype='float32')) == 0.0, tag
+        acts = np.array(c['actions'], dtype='float32')
+        for k in range(len(acts)):
+            obs, rew, _, _, _ = env.step(acts[k][None])
+            assert max_abs_diff(obs.cpu().numpy()[0], np.array(c['obs'][k], dtype='float32')) == 0.0, (tag, k)
+            ref_r = np.array(c['reward_values'][k], dtype='float32')
+            assert max_abs_diff(rew.cpu().numpy()[0], ref_r) <= 1e-5 * max(1.0, float(np.abs(ref_r).max())), (tag, k)
+            assert max_abs_diff(env.district.cpu().numpy()[0], np.array(c['district'][k], dtype='float32')) <= (1e-6 if lstm else 0.0) * 1.0 \
+                or max_abs_diff(env.district.cpu().numpy()[0], np.array(c['district'][k], dtype='float32')) <= 2.4e-7 * float(np.abs(c['district'][k]).max()), (tag, k)

@@ -1,0 +1,200 @@
+"""GPU tests of the round-2 paths (through the C ABI): distinct-action oracle parity at full BASELINE sizes, the 1024-thread
+instantiation, the fresh-observation table path, the shared-row host paths, checkpoints across episode windows, argument checks."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip('torch')
+
+from citylearn_b200.schema import DYN                       # noqa: E402
+from helpers import max_abs_diff                            # noqa: E402
+
+pytestmark = pytest.mark.gpu
+PALL = 'citylearn_challenge_2022_phase_all'
+
+
+def _c3_schema():
+    from citylearn_b200.data import DataSet
+    src = DataSet.get_source('citylearn_challenge_2023_phase_2_local_evaluation')
+    sch = src.schema()
+    sch['reward_function'] = {'type': 'citylearn.reward_function.MARL', 'attributes': {}}
+    return sch, src
+
+
+@pytest.mark.parametrize('E,threads', [(4096, 512), (16384, 992)])
+def test_c2_distinct_actions_match_oracle_at_full_size(E, threads):
+    """BASELINE configs[1] (17 x 4096) and the 1024-thread / 64-register instantiation `cl_create` selects beyond two waves
+    (17 x 16384): every env has its own action sequence; rewards, district sums and the physics trace equal the oracle's bit for bit."""
+    from citylearn_b200 import CityLearnEnv
+    from citylearn_oracle import OracleEnv
+    env = CityLearnEnv(PALL, num_envs=E, debug_trace=True)
+    assert env._h.geometry()['threads'] == threads, env._h.geometry()
+    oracle = OracleEnv(env.spec, E)
+    assert max_abs_diff(env.reset()[0].cpu().numpy(), oracle.reset().astype('float32')) == 0.0
+    rng = np.random.RandomState(31)
+    for k in range(12):
+        a = rng.uniform(-1, 1, size=(E, env.spec.action_dim)).astype('float32')
+        if k == 5:
+            a[::3] = 0.0                            # idle batteries: zero numerators everywhere
+        obs, rew, _, _, _ = env.step(torch.from_numpy(a).cuda())
+        oobs, orew, odist, odyn = oracle.step(a)
+        assert max_abs_diff(obs.cpu().numpy(), oobs) == 0.0
+        assert np.array_equal(rew.cpu().numpy(), orew), k
+        assert np.array_equal(env.district.cpu().numpy(), odist), k
+        tr = env.trace.cpu().numpy()
+        for n in ('electrical_storage_soc', 'electrical_storage_energy_balance', 'net_electricity_consumption',
+                  'electrical_storage_degraded_capacity'):
+            assert np.array_equal(tr[..., DYN[n]], odyn[..., DYN[n]].astype('float32')), (n, k)
+
+
+def test_c3_distinct_actions_match_oracle_at_2048_envs():
+    """BASELINE configs[2] shape (3 LSTM buildings, MARL) at 2048 envs, past the LSTM warm-up."""
+    from citylearn_b200 import CityLearnEnv
+    from citylearn_oracle import OracleEnv
+    sch, src = _c3_schema()
+    E, K = 2048, 20
+    env = CityLearnEnv(sch, data_source=src, central_agent=False, num_envs=E, debug_trace=True)
+    oracle = OracleEnv(env.spec, E)
+    assert max_abs_diff(env.reset()[0].cpu().numpy(), oracle.reset().astype('float32')) == 0.0
+    rng = np.random.RandomState(41)
+    lo = np.concatenate([b.action_low for b in env.spec.buildings])
+    hi = np.concatenate([b.action_high for b in env.spec.buildings])
+    for k in range(K):
+        a = (lo + rng.uniform(0, 1, size=(E, env.spec.action_dim)) * (hi - lo)).astype('float32')
+        obs, rew, _, _, _ = env.step(a)
+        oobs, orew, odist, odyn = oracle.step(a)
+        assert max_abs_diff(obs.cpu().numpy(), oobs) == 0.0
+        tr = env.trace.cpu().numpy()
+        for n in ('electrical_storage_soc', 'dhw_storage_soc', 'net_electricity_consumption', 'cooling_electricity_consumption', 'cooling_demand'):
+            assert np.array_equal(tr[..., DYN[n]], odyn[..., DYN[n]].astype('float32')), (n, k)
+        assert max_abs_diff(tr[..., DYN['indoor_dry_bulb_temperature']], odyn[..., DYN['indoor_dry_bulb_temperature']]) < 3e-5
+        assert np.array_equal(rew.cpu().numpy(), orew)
+
+
+@pytest.mark.parametrize('dataset,E,kw', [(PALL, 4096, {}), (PALL, 640, {'central_agent': True}),
+                                          ('citylearn_challenge_2020_climate_zone_1', 256, {})])
+def test_fresh_observations_table_path_matches_oracle(dataset, E, kw):
+    """stale_observations=False through the per-env row images (TMA load of the table row, DYN columns patched in shared memory, one
+    TMA store per env row): observations incl. soc / net of the step, rewards and district sums equal the oracle's, bit for bit."""
+    from citylearn_b200 import CityLearnEnv
+    from citylearn_oracle import OracleEnv
+    env = CityLearnEnv(dataset, num_envs=E, stale_observations=False, **kw)
+    oracle = OracleEnv(env.spec, E, stale_observations=False)
+    assert max_abs_diff(env.reset()[0].cpu().numpy(), oracle.reset().astype('float32')) == 0.0
+    rng = np.random.RandomState(5)
+    lo = np.concatenate([b.action_low for b in env.spec.buildings])
+    hi = np.concatenate([b.action_high for b in env.spec.buildings])
+    K = 14
+    acts = (lo + rng.uniform(0, 1, size=(K, E, env.spec.action_dim)) * (hi - lo)).astype('float32')
+    ref = []
+    for k in range(K):
+        obs, rew, _, _, _ = env.step(torch.from_numpy(acts[k]).cuda())
+        oobs, orew, odist, _ = oracle.step(acts[k])
+        ref.append((oobs, orew))
+        assert max_abs_diff(obs.cpu().numpy(), oobs) == 0.0, k
+        assert np.array_equal(rew.cpu().numpy(), orew), k
+        assert np.array_equal(env.district.cpu().numpy(), odist), k
+    names = [n for _, n in env._entries]
+    assert float(obs[:, names.index('electrical_storage_soc')].abs().sum()) > 0.0
+    # the same through ONE rollout launch (double-buffered images across steps)
+    env.reset()
+    L, R = env._obs_dim, env._reward_dim
+    o = torch.empty((K, E, L), device='cuda'); r = torch.empty((K, E, R), device='cuda')
+    env.rollout(torch.from_numpy(acts).cuda(), o, r, None)
+    for k in range(K):
+        assert max_abs_diff(o[k].cpu().numpy(), ref[k][0]) == 0.0, k
+        assert np.array_equal(r[k].cpu().numpy(), ref[k][1]), k
+
+
+def test_fresh_observations_with_normalized_wrapper_table_vs_gather(monkeypatch):
+    """Fused observation transforms on the patched DYN columns: table path == general gather path."""
+    from citylearn_b200 import CityLearnEnv, wrappers as W
+    E, K = 64, 12
+    acts = np.random.RandomState(3).uniform(0, 1, size=(K, E, 5)).astype('float32')
+
+    def run():
+        env = W.NormalizedSpaceWrapper(CityLearnEnv('citylearn_challenge_2022_phase_1', num_envs=E, stale_observations=False))
+        env.reset()
+        return [env.step(torch.from_numpy(acts[k]).cuda())[0].clone() for k in range(K)]
+    a = run()
+    monkeypatch.setenv('CL_B200_OBS_TABLE_MB', '0')
+    b = run()
+    for k in range(K):
+        assert torch.equal(a[k], b[k]), k
+
+
+def test_step_host_shared_row_and_rollout_host():
+    from citylearn_b200 import CityLearnEnv
+    E, K = 96, 10
+    acts = np.random.RandomState(8).uniform(-1, 1, size=(K, E, 17)).astype('float32')
+    full = CityLearnEnv(PALL, num_envs=E)
+    shared = CityLearnEnv(PALL, num_envs=E)
+    block = CityLearnEnv(PALL, num_envs=E)
+    assert shared.shared_observation_row
+    full.reset(); shared.reset(); block.reset()
+    obs_rows, rew_all, term = block.rollout_host(acts)
+    assert obs_rows.shape == (K, full._obs_dim) and rew_all.shape == (K, E, 17) and not term
+    for k in range(K):
+        o1, r1, _ = full.step_host(acts[k], full_observations=True)
+        o2, r2, _ = shared.step_host(acts[k])
+        assert o2.shape == o1.shape and np.array_equal(o1, o2)
+        assert np.array_equal(r1, r2)
+        assert np.array_equal(obs_rows[k], o1[0]) and np.array_equal(rew_all[k], r1)
+    assert torch.equal(shared.observations, full.observations) and torch.equal(block.observations, full.observations)
+    assert block.time_step == K
+    # per-env windows: no shared row
+    env = CityLearnEnv('citylearn_challenge_2022_phase_1', num_envs=4, simulation_end_time_step=999, episode_time_steps=200)
+    env.reset(options={'episode_start': torch.tensor([0, 100, 200, 300])})
+    assert not env.shared_observation_row
+    with pytest.raises(ValueError):
+        env.step_host(np.zeros((4, 5), dtype='float32'), full_observations=False)
+    o, _, _ = env.step_host(np.zeros((4, 5), dtype='float32'))
+    assert o.shape == (4, env._obs_dim) and not np.array_equal(o[0], o[1])
+
+
+def test_checkpoint_restores_episode_window_and_outage():
+    """A checkpoint loaded into a FRESH env (other episode window after its own reset) continues on the checkpoint's rows."""
+    from citylearn_b200 import CityLearnEnv
+    kw = dict(num_envs=8, simulation_start_time_step=0, simulation_end_time_step=1999, episode_time_steps=400)
+    a = CityLearnEnv('citylearn_challenge_2022_phase_1', **kw)
+    a.reset(); a.reset()                            # second window: rows 400 .. 799
+    assert a.episode_tracker.episode_start_time_step == 400
+    acts = np.random.RandomState(1).uniform(-1, 1, size=(30, 8, 5)).astype('float32')
+    for k in range(10):
+        a.step(acts[k])
+    sd = a.state_dict()
+    ref = [tuple(x.clone() for x in a.step(acts[k])[:2]) for k in range(10, 30)]
+    b = CityLearnEnv('citylearn_challenge_2022_phase_1', **kw)
+    b.reset()                                       # window 0 .. 399
+    b.load_state_dict(sd)
+    assert b.time_step == 10 and b.episode_tracker.episode_start_time_step == 400
+    for k in range(10, 30):
+        o, r, _, _, _ = b.step(acts[k])
+        assert torch.equal(o, ref[k - 10][0]) and torch.equal(r, ref[k - 10][1]), k
+    with pytest.raises(RuntimeError):
+        b.evaluate_batched()
+    # per-env windows survive a checkpoint too
+    c = CityLearnEnv('citylearn_challenge_2022_phase_1', **kw)
+    starts = torch.tensor([0, 50, 100, 150, 200, 250, 300, 350])
+    c.reset(options={'episode_start': starts})
+    for k in range(5):
+        c.step(acts[k])
+    sd = c.state_dict()
+    ref = [c.step(acts[k])[0].clone() for k in range(5, 12)]
+    d = CityLearnEnv('citylearn_challenge_2022_phase_1', **kw)
+    d.load_state_dict(sd)
+    for k in range(5, 12):
+        assert torch.equal(d.step(acts[k])[0], ref[k - 5])
+
+
+def test_episode_start_validation():
+    from citylearn_b200 import CityLearnEnv
+    env = CityLearnEnv('citylearn_challenge_2022_phase_1', num_envs=4, simulation_end_time_step=999, episode_time_steps=200)
+    for bad in ([0, 100, 200, 900], [-1, 0, 0, 0], [0, 1, 2]):
+        with pytest.raises(ValueError):
+            env.reset(options={'episode_start': torch.tensor(bad)})
+    env.reset(options={'episode_start': torch.tensor([0, 100, 200, 800])})
+    from citylearn_b200.data import DataSet
+    src = DataSet.get_source('citylearn_challenge_2023_phase_2_local_evaluation')
+    out = CityLearnEnv(src.schema(), data_source=src, num_envs=2)
+    with pytest.raises(ValueError):
+        out.reset(options={'episode_start': torch.tensor([0, 0])})
