@@ -18,7 +18,8 @@ observation at t+1 out.  Metric: building-env steps / s (whole job, all ranks).
             registers between the steps of a launch) / median launch duration.
   cpu_baseline  the UNMODIFIED reference (oracle/_ref, installed by oracle/build_ref.py) on one host core, when present; else the
             NumPy oracle port.
-  extra     (N = 1, or --extras) BASELINE configs[2] (C3: 3 LSTM buildings x 65 536 envs, MARL, against a measured FP32-FMA
+  extra     (N = 1, or --extras; C4 and C5 at every N) BASELINE configs[4] (C5: closed loop with an on-device policy, 32 768 envs in total),
+            BASELINE configs[2] (C3: 3 LSTM buildings x 65 536 envs, MARL, against a measured FP32-FMA
             peak), configs[3] per-GPU share (C4: synthetic 1024 buildings x 1024 envs, full-year rollout) and configs[1] with
             stale_observations=False (fresh observations) ride on the same JSON line under "extra".
 
@@ -385,6 +386,56 @@ def extra_c4(torch, dev, precision, peak, world, dist):
     return out
 
 
+def extra_c5(torch, dev, precision, world, dist, K_total=96, n_graph=8):
+    """BASELINE configs[4]: SAC-style closed loop on 2022_phase_all, 32 768 envs in total (strong scaling: 32 768 / N per GPU),
+    fresh observations.  Per step: a random-init per-building actor (17 x [28 -> 256 -> 256 -> 1], bf16 cuBLAS batched matmuls - the
+    policy is the caller's, not part of the accelerated path) reads the observation slab on the device, writes the actions, and
+    `cl_advance_device` steps the env - `n_graph` such steps captured as ONE CUDA graph and replayed (no host round trip); after every
+    replay a parameter-sized float32 buffer is all-reduced over NCCL (stand-in for a DDP gradient exchange; skipped at N = 1)."""
+    from citylearn_b200 import CityLearnEnv
+    from citylearn_b200.closed_loop import ClosedLoop, PerBuildingMLP
+    E = 32768 // world
+    env = CityLearnEnv(DATASET, num_envs=E, device=dev, precision=precision, stale_observations=False)
+    B, A, L = env.spec.n_buildings, env.spec.action_dim, env._obs_dim
+    pol = PerBuildingMLP(B, L // B, A // B, hidden=256, dtype=torch.bfloat16, device=dev)
+    grads = torch.zeros(pol.parameter_count(), dtype=torch.float32, device=dev)
+    loop = ClosedLoop(env, pol, steps_per_replay=n_graph)
+
+    def iterate(n_steps):
+        for _ in range(n_steps // n_graph):
+            loop.run(n_graph)
+            if world > 1:
+                dist.all_reduce(grads)
+    iterate(2 * n_graph)                                   # warm-up
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); iterate(K_total); e1.record()
+    torch.cuda.synchronize(dev)
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    # env-only share of the same loop: the identical graph with a policy that writes constant actions
+    env2 = CityLearnEnv(DATASET, num_envs=E, device=dev, precision=precision, stale_observations=False)
+    const = torch.zeros((E, A), device=dev)
+    loop2 = ClosedLoop(env2, lambda o: const, steps_per_replay=n_graph)
+    loop2.run(2 * n_graph)
+    torch.cuda.synchronize(dev)
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record(); loop2.run(K_total); f1.record()
+    torch.cuda.synchronize(dev)
+    t2 = torch.tensor([f0.elapsed_time(f1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX); dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+    ms, ms_env = float(t.item()), float(t2.item())
+    out = {'workload': f'{DATASET}: {B} x {E} envs per GPU ({world * E} envs on {world} GPU(s)), stale_observations=False, closed loop with a per-building 2 x 256 MLP actor (bf16)',
+           'ms_per_step': ms / K_total, 'value': world * B * E * K_total / (ms * 1e-3), 'unit': UNIT, 'steps': K_total, 'steps_per_graph_replay': n_graph,
+           'policy_parameters': pol.parameter_count(), 'allreduce': None if world == 1 else f'{grads.numel() * 4} B float32 (NCCL) after every {n_graph} steps',
+           'env_only_ms_per_step': ms_env / K_total, 'env_only_value': world * B * E * K_total / (ms_env * 1e-3),
+           'policy_flop_per_step': 2.0 * E * B * ((L // B) * 256 + 256 * 256 + 256 * (A // B)), 'scaling': 'strong (32768 envs in total)'}
+    env.close(); env2.close()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -499,17 +550,20 @@ def main():
     extra = {}
     want = args.extras
     fma_peak = None
-    try:
-        if want == 'all' or (want == 'auto' and world == 1):
-            if rank == 0:
-                with torch.cuda.device(dev):
-                    fma_peak = _native.measure_fma_peak()
-                extra['fresh_observations_c2'] = extra_fresh_c2(torch, dev, args.precision, K, min(R, 20), peak)
-                extra['c3_lstm_marl'] = extra_c3(torch, dev, args.precision, fma_peak)
-        if want != 'none':
-            extra['c4_wide_year'] = extra_c4(torch, dev, args.precision, peak, world, dist)
-    except Exception as e:          # an extra must never take the headline down
-        extra['error'] = repr(e)[:300]
+    def guarded(name, fn):          # an extra must never take the headline (or another extra) down
+        try:
+            extra[name] = fn()
+        except Exception as e:
+            extra[name] = {'error': repr(e)[:300]}
+    if want == 'all' or (want == 'auto' and world == 1):
+        if rank == 0:
+            with torch.cuda.device(dev):
+                fma_peak = _native.measure_fma_peak()
+            guarded('fresh_observations_c2', lambda: extra_fresh_c2(torch, dev, args.precision, K, min(R, 20), peak))
+            guarded('c3_lstm_marl', lambda: extra_c3(torch, dev, args.precision, fma_peak))
+    if want != 'none':
+        guarded('c4_wide_year', lambda: extra_c4(torch, dev, args.precision, peak, world, dist))
+        guarded('c5_closed_loop', lambda: extra_c5(torch, dev, args.precision, world, dist))
 
     if rank != 0:
         if world > 1:

@@ -66,6 +66,12 @@ def load():
     lib.cl_reset.argtypes = [vp, vp, i32, i32, vp, vp]
     lib.cl_step.argtypes = [vp, vp, vp, vp, vp, vp, vp]
     lib.cl_rollout.argtypes = [vp, i32, vp, vp, vp, vp, vp]
+    lib.cl_device_time_enable.argtypes = [vp, vp]
+    lib.cl_exchange_create.argtypes = [vp, i32, i32, vp, ctypes.POINTER(vp)]
+    lib.cl_exchange_connect.argtypes = [vp, vp]
+    lib.cl_exchange_connect_ptrs.argtypes = [vp, ctypes.POINTER(vp), vp]
+    lib.cl_exchange_status.argtypes = [vp, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_uint32)]
+    lib.cl_advance_device.argtypes = [vp, i32, vp, vp, vp, vp, vp]
     lib.cl_obs_rows.argtypes = [vp, i32, i32, vp, vp]
     lib.cl_time_step.argtypes = [vp, ctypes.POINTER(ctypes.c_int32)]
     lib.cl_state_size.argtypes = [vp, ctypes.POINTER(ctypes.c_size_t)]
@@ -81,7 +87,8 @@ def load():
     lib.cl_measure_fma_peak.argtypes = [ctypes.POINTER(ctypes.c_double)]
     for name in ('cl_create', 'cl_destroy', 'cl_set_outage', 'cl_reset', 'cl_step', 'cl_rollout', 'cl_obs_rows', 'cl_time_step',
                  'cl_state_size', 'cl_get_state', 'cl_set_state', 'cl_launch_count', 'cl_launch_geometry', 'cl_set_transforms',
-                 'cl_kpi_enable', 'cl_kpi_accumulate', 'cl_kpi_read', 'cl_measure_fma_peak'):
+                 'cl_kpi_enable', 'cl_kpi_accumulate', 'cl_kpi_read', 'cl_measure_fma_peak', 'cl_device_time_enable', 'cl_advance_device',
+                 'cl_exchange_create', 'cl_exchange_connect', 'cl_exchange_connect_ptrs', 'cl_exchange_status'):
         getattr(lib, name).restype = ctypes.c_int
     if lib.cl_abi_version() != ABI_VERSION:
         raise NativeLibraryError(f'{path}: ABI version {lib.cl_abi_version()} != {ABI_VERSION}; rebuild the extension')
@@ -165,6 +172,34 @@ class Handle:
 
     def rollout(self, n_steps: int, actions_ptr, obs_ptr, reward_ptr, district_ptr, stream: int):
         check(self.lib.cl_rollout(self.ptr, int(n_steps), actions_ptr, obs_ptr, reward_ptr, district_ptr, stream), 'cl_rollout')
+
+    def device_time_enable(self, stream: int):
+        check(self.lib.cl_device_time_enable(self.ptr, stream), 'cl_device_time_enable')
+
+    def advance_device(self, n_steps: int, actions_ptr, obs_ptr, reward_ptr, district_ptr, stream: int):
+        """Capturable (CUDA graph) variant of step / rollout: the time step lives on the device."""
+        check(self.lib.cl_advance_device(self.ptr, int(n_steps), actions_ptr, obs_ptr, reward_ptr, district_ptr, stream), 'cl_advance_device')
+
+    def exchange_create(self, n_ranks: int, rank: int):
+        """-> (ipc handle bytes [64], own buffer device pointer)."""
+        h = (ctypes.c_ubyte * 64)()
+        buf = ctypes.c_void_p()
+        check(self.lib.cl_exchange_create(self.ptr, int(n_ranks), int(rank), h, ctypes.byref(buf)), 'cl_exchange_create')
+        return bytes(h), buf.value
+
+    def exchange_connect(self, handles: bytes):
+        check(self.lib.cl_exchange_connect(self.ptr, ctypes.c_char_p(handles)), 'cl_exchange_connect')
+
+    def exchange_connect_ptrs(self, buffers, devices):
+        n = len(buffers)
+        arr = (ctypes.c_void_p * n)(*buffers)
+        dv = np.ascontiguousarray(devices, dtype='int32')
+        check(self.lib.cl_exchange_connect_ptrs(self.ptr, arr, dv.ctypes.data), 'cl_exchange_connect_ptrs')
+
+    def exchange_status(self):
+        t, e = ctypes.c_int32(), ctypes.c_uint32()
+        check(self.lib.cl_exchange_status(self.ptr, ctypes.byref(t), ctypes.byref(e)), 'cl_exchange_status')
+        return {'timeouts': t.value, 'steps_exchanged': e.value}
 
     def obs_rows(self, first_time_step: int, n_rows: int, rows_ptr, stream: int):
         check(self.lib.cl_obs_rows(self.ptr, int(first_time_step), int(n_rows), rows_ptr, stream), 'cl_obs_rows')

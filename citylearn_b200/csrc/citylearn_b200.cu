@@ -42,6 +42,7 @@ struct Dev {
     int B, E, U, n_rows, W, Wp, A, L, T;
     int central, reward_id, stale, envs_per_block, uniform_start, start0, has_outage, any_dynamics, lstm_smem;
     int curve_nmax;        // max number of points of any battery curve of the district (uniform bound of the segment search)
+    const uint8_t* curve_lut;   // [B][2][kCurveLutStride] uniform-grid index of the curve abscissae or nullptr (unit_physics.cuh)
     // building tiles: a district wider than one block is split into `tiles` tiles of `tile_b` buildings, one CTA per tile,
     // the CTAs of an env forming a thread-block cluster (tiles == 1: tile_b == B, Lt == L, no cluster)
     int tiles, tile_b, Lt;
@@ -74,6 +75,15 @@ struct Dev {
     const int32_t* tcol;   // [L] >= 0: table column, -1: zero (stale DYN slot), <= -2: outage signal of building (-2 - tcol)
     const float* outage;   // [B][T] or nullptr
     const int32_t* start;  // [E]
+    const int32_t* t_dev;  // [1] device-resident time step (cl_step_device: launches with t0 < 0 read it)
+    // building-sharded districts (cl_exchange_*): this handle owns SOME buildings of every env; the per-env district sums are completed
+    // inside the step by an all-gather of the ranks' partial sums through peer memory (NVLink): every (quantity, env) value travels as
+    // ONE 8-byte {value, epoch} store into every peer's slot array - data and flag in one NVLink transaction, no fence, no second
+    // round trip - and the reader spins on the epoch.  Slot (parity p, source rank r, env e, quantity q) = ((p * n + r) * E + e) * 3 + q.
+    int x_n, x_rank;                 // ranks sharing the district (0: not sharded), this handle's rank
+    unsigned x_epoch;                // epoch of the launch's first step minus 1 (epochs count steps since cl_exchange_create, never repeat)
+    uint2* const* x_peers;           // [x_n] device array: base of every rank's slot array as mapped on THIS device (x_peers[x_rank]: own)
+    int32_t* x_err;                  // [1] spin time-outs (a peer that never arrives must not hang the GPU)
     const float* lstm_w;   // packed LSTM weights [B][kLstmStride] (buildings without dynamics: zeros)
     float* lst;            // LSTM state [kLstmStateFloats][U] (dynamics districts only)
     float* st;             // [6][U]
@@ -191,12 +201,9 @@ struct RawActions { float es, cd, hd, coh, cs, hs, ds; };
 
 template <typename R, bool THERMAL>
 __device__ __forceinline__ void fetch_actions(const Dev& d, const UnitCtx<R>& c, const float* act_row, RawActions& a) {
-    // with an action transform the caller's values are fractions of the action range (NormalizedActionWrapper)
-    auto get = [&](int col) -> float {
-        if (col < 0) return 0.f;
-        const float v = __ldg(act_row + col);
-        return d.act_range ? v * __ldg(d.act_range + col) + __ldg(d.act_low + col) : v;
-    };
+    // loads only: nothing here may consume the loaded value (even a predicated-off instruction waits for its operands, which would
+    // turn the one-step-ahead prefetch into a ~600-cycle stall); the action transform is applied where the value is used
+    auto get = [&](int col) -> float { return col < 0 ? 0.f : __ldg(act_row + col); };
     a.es = get(c.a_es);
     if (THERMAL) {
         a.cd = get(c.a_cd); a.hd = get(c.a_hd); a.coh = get(c.a_coh);
@@ -223,7 +230,13 @@ __device__ __forceinline__ float transform_obs(const cl_obs_transform* t, int k,
 
 // inactive storage actions are 0, inactive device actions NaN (building.py:1555-1564)
 template <typename R, bool THERMAL>
-__device__ __forceinline__ void apply_actions(const UnitCtx<R>& c, const RawActions& a, UnitInputs<R>& in) {
+__device__ __forceinline__ void apply_actions(const Dev& d, const UnitCtx<R>& c, RawActions a, UnitInputs<R>& in) {
+    if (d.act_range != nullptr) {
+        // with an action transform the caller's values are fractions of the action range (NormalizedActionWrapper)
+        auto tr = [&](int col, float& v) { if (col >= 0) v = v * __ldg(d.act_range + col) + __ldg(d.act_low + col); };
+        tr(c.a_es, a.es);
+        if (THERMAL) { tr(c.a_cd, a.cd); tr(c.a_hd, a.hd); tr(c.a_coh, a.coh); tr(c.a_cs, a.cs); tr(c.a_hs, a.hs); tr(c.a_ds, a.ds); }
+    }
     in.a_es = (R)a.es;
     in.a_cooling_device = in.a_heating_device = (R)NAN;
     in.a_cs = in.a_hs = in.a_ds = (R)0;
@@ -396,6 +409,39 @@ __device__ __forceinline__ uint32_t cluster_map(uint32_t local_smem_addr, uint32
 __device__ __forceinline__ float ld_cluster_f32(uint32_t addr) { float v; asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory"); return v; }
 __device__ __forceinline__ double ld_cluster_f64(uint32_t addr) { double v; asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(addr) : "memory"); return v; }
 
+// peer-memory exchange primitives (building-sharded districts): 8-byte {value, epoch} slots, written and polled with .volatile
+// accesses (system-coherent L2 path; a 64-bit aligned store is one NVLink transaction - the flag can never be seen without its value)
+__device__ __forceinline__ void st_slot(uint2* p, float v, unsigned epoch) {
+    asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(__float_as_uint(v)), "r"(epoch) : "memory");
+}
+__device__ __forceinline__ uint2 ld_slot(const uint2* p) {
+    uint2 v;
+    asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+    return v;
+}
+// this rank's partial `acc` of (env e, quantity q) at step epoch `ep` -> the sum over all ranks, added in rank order (the same value
+// on every rank).  A peer that does not deliver within ~2 s is counted in x_err and treated as 0.
+__device__ __forceinline__ float exchange_sum(const Dev& d, float acc, int e, int q, unsigned ep) {
+    const int n = d.x_n;
+    const unsigned p = ep & 1u;
+    const size_t mine = ((size_t)(p * n + d.x_rank) * d.E + e) * 3 + q;
+    for (int r = 0; r < n; ++r) st_slot(d.x_peers[r] + mine, acc, ep);              // push to every rank (own copy included)
+    const uint2* own = d.x_peers[d.x_rank];
+    float tot = 0.f;
+    for (int r = 0; r < n; ++r) {
+        const uint2* src = own + ((size_t)(p * n + r) * d.E + e) * 3 + q;
+        uint2 v = ld_slot(src);
+        if (v.y != ep) {
+            const long long t_start = clock64();
+            while ((v = ld_slot(src)).y != ep) {
+                if (clock64() - t_start > 4000000000LL) { atomicAdd(d.x_err, 1); v.x = 0u; break; }
+            }
+        }
+        tot += __uint_as_float(v.x);
+    }
+    return tot;
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // observation writers: the rows of a block's envs are one contiguous span obs[e0*L .. (e0+n)*L)
 // ------------------------------------------------------------------------------------------------------------------
@@ -434,13 +480,14 @@ __device__ __forceinline__ void write_obs_general(const Dev& d, float* obs, int 
 // offsets in floats from the start of the dynamic shared memory (kept as plain ints so that every access is derived
 // directly from the `extern __shared__` array and compiles to LDS/STS with 32-bit addressing, not generic loads)
 struct SmemLayout {
-    int curves, bsolar, rows, tcol, tmpl, red, rsum, dsum, wpart, rpart, lstm, lstm_pre, dynbuf, end, Lp;
+    int curves, clut, bsolar, rows, tcol, tmpl, red, rsum, dsum, wpart, rpart, lstm, lstm_pre, dynbuf, end, Lp;
 };
 __host__ __device__ __forceinline__ SmemLayout smem_layout(int B, int Wp, int L, int epb, int nt, int rsize, int lstm_smem = 0, int tab_layout = 0, int fresh_slots = 0) {
     SmemLayout o;
     o.Lp = (L + 3) & ~3;
     int f = 16;                                  // 64 bytes of mbarriers: 3 time-row slots + 2 observation-row buffers
     o.curves = f; f += B * kCurveTab * (rsize / 4);   // first: keeps doubles 8-byte aligned
+    o.clut = f; f += B * kCurveLutFloats;             // uniform-grid index of the curve abscissae (bytes)
     o.bsolar = f; f += ((2 * B * (rsize / 4)) + 3) & ~3;
     o.rows = f; f += 3 * Wp;
     o.tcol = f; f += tab_layout ? 0 : o.Lp;      // gather columns: not needed when the rows come from the observation table
@@ -575,6 +622,11 @@ template <typename R, bool THERMAL, bool DYNAMICS, int MAXT, bool WIDE = false>
 __global__ void __launch_bounds__(MAXT) advance_kernel(Dev d, int t0, int K, const float* __restrict__ actions, float* __restrict__ obs,
                                                         float* __restrict__ reward, float* __restrict__ district, float* __restrict__ trace) {
     extern __shared__ __align__(16) float smf[];
+    if (t0 < 0) {
+        // device-resident time step (cl_step_device, CUDA-graph replays): a launch past the end of the episode does nothing
+        t0 = *reinterpret_cast<const volatile int32_t*>(d.t_dev);
+        if (t0 + K > d.T - 1) return;
+    }
     const int nt = blockDim.x, tid = threadIdx.x;
     const int np_ = nt - 32;                       // physics threads; the last warp is the helper
     const bool is_helper = tid >= np_;
@@ -592,6 +644,7 @@ __global__ void __launch_bounds__(MAXT) advance_kernel(Dev d, int t0, int K, con
     const SmemLayout lo = smem_layout(TBs, Wp, WIDE ? d.Lt : d.L, epb, nt, (int)sizeof(R), DYNAMICS ? d.lstm_smem : 0, d.tab_layout, d.fresh_slots);
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(smf);
     R* scurves = reinterpret_cast<R*>(smf + lo.curves);
+    uint8_t* s_clut = reinterpret_cast<uint8_t*>(smf + lo.clut);
     R* s_bsolar = reinterpret_cast<R*>(smf + lo.bsolar);          // [2][B] PV generation of the step, per building
     float* s_rows = smf + lo.rows;
     int32_t* s_tcol = reinterpret_cast<int32_t*>(smf + lo.tcol);
@@ -660,6 +713,10 @@ __global__ void __launch_bounds__(MAXT) advance_kernel(Dev d, int t0, int K, con
             }
             scurves[i] = v;
         }
+        if (d.curve_lut != nullptr) {
+            const uint32_t* src = reinterpret_cast<const uint32_t*>(d.curve_lut) + (size_t)b0 * kCurveLutFloats;
+            for (int i = tid; i < nb * kCurveLutFloats; i += nt) reinterpret_cast<uint32_t*>(s_clut)[i] = __ldg(src + i);
+        }
     }
     UnitCtx<R> c;
     UnitState<R> s;
@@ -673,7 +730,8 @@ __global__ void __launch_bounds__(MAXT) advance_kernel(Dev d, int t0, int K, con
         start_e = __ldg(d.start + e);
         fetch_actions<R, THERMAL>(d, c, actions + (size_t)e * d.A, act_next);
     }
-    const SmemCurves<R> curves = {scurves + (active ? bl : 0) * kCurveTab, d.curve_nmax};
+    const SmemCurves<R> curves = {scurves + (active ? bl : 0) * kCurveTab, d.curve_nmax,
+                                  d.curve_lut != nullptr ? s_clut + (active ? bl : 0) * (2 * kCurveLutStride) : nullptr};
     const float* lstm_w = nullptr;
     if (DYNAMICS) {
         if (d.lstm_smem) {                            // stage every building's packed LSTM weights in shared memory (16-byte copies)
@@ -840,7 +898,7 @@ __global__ void __launch_bounds__(MAXT) advance_kernel(Dev d, int t0, int K, con
             UnitInputs<R> in;
             load_inputs<R, THERMAL>(d, c, row, b, t, in, uniform);
             if (uniform) in.solar = s_bsolar[pb * TBs + bl];
-            apply_actions<R, THERMAL>(c, act_next, in);
+            apply_actions<R, THERMAL>(d, c, act_next, in);
             if (k + 1 < K) fetch_actions<R, THERMAL>(d, c, actions + ((size_t)(k + 1) * d.E + e) * d.A, act_next);   // prefetch
             if (DYNAMICS && (c.p.flags & CL_F_DYNAMICS) && t > c.dyn_lookback) {
                 // partial-load control is live once the input window is full (building.py:3108, 3144)
@@ -958,6 +1016,8 @@ __global__ void __launch_bounds__(MAXT) advance_kernel(Dev d, int t0, int K, con
             int j = 0;
             for (; j + 4 <= B; j += 4) { acc += src[j]; acc += src[j + 1]; acc += src[j + 2]; acc += src[j + 3]; }   // same left-to-right order
             for (; j < B; ++j) acc += src[j];
+            // building-sharded district: `acc` covers this rank's buildings; complete it over the ranks through peer memory
+            if (d.x_n > 1) acc = exchange_sum(d, acc, e0 + le, q, d.x_epoch + (unsigned)k + 1u);
             if (q == 0) s_dsum[pb * epb + le] = acc;
             if (district != nullptr) district[((size_t)k * d.E + e0 + le) * 3 + q] = acc;
         }
@@ -1182,6 +1242,15 @@ struct cl_env {
     int precision = 0;
     bool thermal = false;
     int t = -1;              // -1: not reset
+    int32_t* t_dev = nullptr;       // device-resident copy of t (cl_device_time_enable / cl_advance_device)
+    bool device_time = false;       // sticky: the device counter is authoritative (graph replays advance it without the host)
+    // building-sharded district (cl_exchange_*)
+    uint2* x_buf = nullptr;          // own slot array [2][n][E][3]
+    uint2** x_peers_dev = nullptr;   // device array of the ranks' slot arrays as mapped here
+    int32_t* x_err_dev = nullptr;
+    std::vector<void*> x_opened;     // cudaIpcOpenMemHandle mappings to close
+    unsigned x_epoch = 0;            // steps exchanged so far
+    int n_sm = 148;
     int T = 0;
     int threads = 0, blocks = 0;
     float* obs_tab_dev = nullptr;   // precomputed observation table (build_obs_table)
@@ -1281,6 +1350,23 @@ extern "C" int cl_create(const cl_district_desc* desc, cl_env** out) {
             }
     }
     d.curve_nmax = nmax;
+    {
+        // uniform-grid index of the curve abscissae (unit_physics.cuh, SmemCurves): usable when no cell holds two points of a curve.
+        // The cells are those of the values the kernel compares, i.e. of the float-rounded abscissae in CL_PRECISION_FP32.
+        std::vector<uint8_t> lut((size_t)B * 2 * kCurveLutStride, 0);
+        bool ok = std::getenv("CL_B200_NO_CURVE_LUT") == nullptr;
+        for (int b = 0; b < B && ok; ++b)
+            for (int w = 0; w < 2 && ok; ++w)
+                ok = build_curve_lut(desc->params + (size_t)(w ? CL_P_CP_X0 : CL_P_PE_X0) * B + b, (size_t)B,
+                                     desc->iparams[(w ? CL_IP_CP_N : CL_IP_PE_N) * B + b], desc->precision == CL_PRECISION_FP32,
+                                     &lut[((size_t)b * 2 + w) * kCurveLutStride]);
+        if (ok) {
+            uint8_t* p = nullptr;
+            int rc = dev_copy(env, lut.data(), lut.size(), &p);
+            if (rc) { cl_destroy(env); return rc; }
+            d.curve_lut = p;
+        }
+    }
     env->thermal = any_thermal != 0;
     d.any_dynamics = any_dyn != 0;
     env->dynamics = any_dyn != 0;
@@ -1400,6 +1486,9 @@ extern "C" int cl_create(const cl_district_desc* desc, cl_env** out) {
         }
         if (cudaMalloc(&p, (size_t)d.E * sizeof(int32_t)) != cudaSuccess) { cl_destroy(env); return fail(CL_ERR_CUDA, "cl_create: start allocation failed"); }
         env->allocs.push_back(p); d.start = static_cast<int32_t*>(p);
+        if (cudaMalloc(&p, sizeof(int32_t)) != cudaSuccess) { cl_destroy(env); return fail(CL_ERR_CUDA, "cl_create: time-step allocation failed"); }
+        env->allocs.push_back(p); env->t_dev = static_cast<int32_t*>(p); d.t_dev = env->t_dev;
+        cudaMemset(p, 0, sizeof(int32_t));
     }
     // launch geometry.  A block = whole envs x all B buildings (physics threads, rounded up to warps) + one helper warp.
     // Every block must be RESIDENT for the whole launch to run in one wave (the kernel is register-heavy: ~100-128 registers
@@ -1412,6 +1501,7 @@ extern "C" int cl_create(const cl_district_desc* desc, cl_env** out) {
         if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
         if (n_sm < 1) n_sm = 148;
     }
+    env->n_sm = n_sm;
     int regs = 128;
     {
         cudaFuncAttributes fa;
@@ -1578,6 +1668,10 @@ extern "C" int cl_destroy(cl_env* env) {
     if (env->dpart) cudaFree(env->dpart);
     if (env->kpi_unit) cudaFree(env->kpi_unit);
     if (env->kpi_env) cudaFree(env->kpi_env);
+    for (void* q : env->x_opened) cudaIpcCloseMemHandle(q);
+    if (env->x_buf) cudaFree(env->x_buf);
+    if (env->x_peers_dev) cudaFree(env->x_peers_dev);
+    if (env->x_err_dev) cudaFree(env->x_err_dev);
     delete env;
     return CL_OK;
 }
@@ -1637,6 +1731,7 @@ static void launch_advance(cl_env* env, int t0, int K, const float* actions, flo
 }
 static void dispatch_one(cl_env* env, int t0, int K, const float* actions, float* obs, float* reward, float* district, float* trace,
                          bool coupled, cudaStream_t st) {
+    if (env->d.x_n > 1) { env->d.x_epoch = env->x_epoch; env->x_epoch += (unsigned)K; }   // every rank runs the same launch sequence
     if (env->precision == CL_PRECISION_FP64) {
         if (env->dynamics) launch_advance<double, true, true>(env, t0, K, actions, obs, reward, district, trace, coupled, st);
         else if (env->thermal) launch_advance<double, true, false>(env, t0, K, actions, obs, reward, district, trace, coupled, st);
@@ -1677,9 +1772,30 @@ static int dispatch_advance(cl_env* env, int K, const float* actions, float* obs
     return CL_OK;
 }
 
+// device-resident time step: t <- v, or t += k while the episode lasts (the launch that follows a finished episode is a no-op too)
+__global__ void set_time_kernel(int32_t* t, int v) { *t = v; }
+__global__ void bump_time_kernel(int32_t* t, int k, int T) { if (*t + k <= T - 1) *t += k; }
+
 __global__ void fill_start_kernel(int32_t* start, int n, int v) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) start[i] = v;
+}
+
+// device-time mode: the counter on the device is authoritative (a captured graph may have advanced it any number of times)
+static int refresh_time(cl_env* env, cudaStream_t st) {
+    if (!env->device_time) return CL_OK;
+    int32_t t = 0;
+    CUDA_TRY(cudaMemcpyAsync(&t, env->t_dev, sizeof(t), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    env->t = t;
+    return CL_OK;
+}
+static int publish_time(cl_env* env, cudaStream_t st) {
+    if (!env->device_time) return CL_OK;
+    set_time_kernel<<<1, 1, 0, st>>>(env->t_dev, env->t);
+    CUDA_TRY(cudaGetLastError());
+    env->launches++;
+    return CL_OK;
 }
 
 extern "C" int cl_reset(cl_env* env, const int32_t* episode_start, int32_t uniform_start, int32_t episode_time_steps, float* obs,
@@ -1710,23 +1826,25 @@ extern "C" int cl_reset(cl_env* env, const int32_t* episode_start, int32_t unifo
         CUDA_TRY(cudaMemsetAsync(env->kpi_env, 0, (size_t)d.E * 2 * CL_NKPI_ENV * sizeof(double), st));
     }
     env->t = 0;
-    return CL_OK;
+    return publish_time(env, st);
 }
 
 extern "C" int cl_step(cl_env* env, const float* actions, float* obs, float* reward, float* district, float* trace, cl_stream stream) {
     if (!env || !actions) return fail(CL_ERR_INVALID, "cl_step: null argument");
     if (env->t < 0) return fail(CL_ERR_STATE, "cl_step: call cl_reset first");
+    { const int rc = refresh_time(env, static_cast<cudaStream_t>(stream)); if (rc) return rc; }
     if (env->t >= env->T - 1) return fail(CL_ERR_STATE, "cl_step: episode has ended (terminated); call cl_reset");
     { const int rc = dispatch_advance(env, 1, actions, obs, reward, district, trace, static_cast<cudaStream_t>(stream)); if (rc) return rc; }
     CUDA_TRY(cudaGetLastError());
     env->t += 1;
-    return CL_OK;
+    return publish_time(env, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int cl_rollout(cl_env* env, int32_t n_steps, const float* actions, float* obs, float* reward, float* district, cl_stream stream) {
     if (!env || !actions) return fail(CL_ERR_INVALID, "cl_rollout: null argument");
     if (n_steps < 1) return fail(CL_ERR_INVALID, "cl_rollout: n_steps must be >= 1");
     if (env->t < 0) return fail(CL_ERR_STATE, "cl_rollout: call cl_reset first");
+    { const int rc = refresh_time(env, static_cast<cudaStream_t>(stream)); if (rc) return rc; }
     if (env->t + n_steps > env->T - 1) return fail(CL_ERR_STATE, "cl_rollout: block runs past the end of the episode");
 #ifdef CL_PHASE_TIMING
     { const int rc = dispatch_advance(env, n_steps, actions, obs, reward, nullptr, district, static_cast<cudaStream_t>(stream)); if (rc) return rc; }   // `district` receives the stamps
@@ -1735,12 +1853,135 @@ extern "C" int cl_rollout(cl_env* env, int32_t n_steps, const float* actions, fl
 #endif
     CUDA_TRY(cudaGetLastError());
     env->t += n_steps;
+    return publish_time(env, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int cl_device_time_enable(cl_env* env, cl_stream stream) {
+    if (!env) return fail(CL_ERR_INVALID, "cl_device_time_enable: null env");
+    if (env->t < 0) return fail(CL_ERR_STATE, "cl_device_time_enable: call cl_reset first");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (env->wide) {
+        // independent tiles leave per-tile district partials in a scratch buffer: allocate it now, never inside a capture
+        const size_t need = (size_t)64 * env->d.E * env->d.tiles * 3;
+        if (env->dpart_floats < need) {
+            if (env->dpart) { CUDA_TRY(cudaStreamSynchronize(st)); cudaFree(env->dpart); env->dpart = nullptr; env->dpart_floats = 0; }
+            CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&env->dpart), need * sizeof(float)));
+            env->dpart_floats = need;
+        }
+    }
+    env->device_time = true;
+    return publish_time(env, st);
+}
+
+extern "C" int cl_advance_device(cl_env* env, int32_t n_steps, const float* actions, float* obs, float* reward, float* district, cl_stream stream) {
+    if (!env || !actions) return fail(CL_ERR_INVALID, "cl_advance_device: null argument");
+    if (n_steps < 1) return fail(CL_ERR_INVALID, "cl_advance_device: n_steps must be >= 1");
+    if (!env->device_time) return fail(CL_ERR_STATE, "cl_advance_device: call cl_device_time_enable first (outside any stream capture)");
+    if (env->d.x_n > 1) return fail(CL_ERR_UNSUPPORTED, "cl_advance_device: building-sharded districts advance through cl_step / cl_rollout (the exchange epoch is a launch argument)");
+    if (env->wide && n_steps > 64 && district != nullptr) return fail(CL_ERR_UNSUPPORTED, "cl_advance_device: at most 64 steps per launch for building-tiled districts with district sums");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int t_host = env->t;
+    env->t = -1;                                     // launches read the device counter
+    const int rc = dispatch_advance(env, n_steps, actions, obs, reward, district, nullptr, st);
+    env->t = t_host;
+    if (rc) return rc;
+    bump_time_kernel<<<1, 1, 0, st>>>(env->t_dev, n_steps, env->T);
+    env->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return CL_OK;
+}
+
+// ---- building-sharded districts: all-gather of partial district sums through peer memory ----------------------------------------
+static size_t exchange_bytes(const cl_env* env, int n) { return (size_t)2 * n * env->d.E * 3 * sizeof(uint2); }
+
+extern "C" int cl_exchange_create(cl_env* env, int32_t n_ranks, int32_t rank, void* ipc_handle_out, void** buffer_out) {
+    if (!env) return fail(CL_ERR_INVALID, "cl_exchange_create: null env");
+    if (n_ranks < 2 || n_ranks > 64 || rank < 0 || rank >= n_ranks) return fail(CL_ERR_INVALID, "cl_exchange_create: need 2 <= n_ranks <= 64 and 0 <= rank < n_ranks");
+    if (env->wide) return fail(CL_ERR_UNSUPPORTED, "cl_exchange_create: building-tiled (wide) districts are not building-sharded across GPUs");
+    if (env->d.central) return fail(CL_ERR_UNSUPPORTED, "cl_exchange_create: central-agent reward sums are not exchanged; use decentralised rewards");
+    if (env->x_buf) return fail(CL_ERR_STATE, "cl_exchange_create: already created");
+    // a block spins on its peers inside the step: every block of the launch must be resident (one wave), or blocks waiting for an SM
+    // could be the ones a resident block waits for
+    if (env->blocks > env->n_sm) return fail(CL_ERR_UNSUPPORTED, "cl_exchange_create: the launch must fit one wave (at most one block per SM); use fewer envs per GPU");
+    const size_t bytes = exchange_bytes(env, n_ranks);
+    CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&env->x_buf), bytes));
+    CUDA_TRY(cudaMemset(env->x_buf, 0, bytes));              // epoch 0 never matches a step (epochs start at 1)
+    CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&env->x_peers_dev), sizeof(uint2*) * n_ranks));
+    CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&env->x_err_dev), sizeof(int32_t)));
+    CUDA_TRY(cudaMemset(env->x_err_dev, 0, sizeof(int32_t)));
+    CUDA_TRY(cudaDeviceSynchronize());
+    if (ipc_handle_out) {
+        cudaIpcMemHandle_t h;
+        CUDA_TRY(cudaIpcGetMemHandle(&h, env->x_buf));
+        static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+        std::memcpy(ipc_handle_out, &h, sizeof(h));
+    }
+    if (buffer_out) *buffer_out = env->x_buf;
+    env->d.x_rank = rank;
+    env->d.x_n = -n_ranks;                                   // negative: created, not connected yet
+    return CL_OK;
+}
+
+static int exchange_finish(cl_env* env, const std::vector<uint2*>& peers) {
+    CUDA_TRY(cudaMemcpy(env->x_peers_dev, peers.data(), sizeof(uint2*) * peers.size(), cudaMemcpyHostToDevice));
+    env->d.x_peers = env->x_peers_dev;
+    env->d.x_err = env->x_err_dev;
+    env->d.x_n = (int)peers.size();
+    env->x_epoch = 0;
+    return CL_OK;
+}
+
+extern "C" int cl_exchange_connect(cl_env* env, const void* ipc_handles) {
+    if (!env || !ipc_handles) return fail(CL_ERR_INVALID, "cl_exchange_connect: null argument");
+    if (env->d.x_n >= 0 || !env->x_buf) return fail(CL_ERR_STATE, "cl_exchange_connect: call cl_exchange_create first (once)");
+    const int n = -env->d.x_n;
+    std::vector<uint2*> peers((size_t)n, nullptr);
+    for (int r = 0; r < n; ++r) {
+        if (r == env->d.x_rank) { peers[(size_t)r] = env->x_buf; continue; }
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, static_cast<const char*>(ipc_handles) + (size_t)r * sizeof(h), sizeof(h));
+        void* q = nullptr;
+        CUDA_TRY(cudaIpcOpenMemHandle(&q, h, cudaIpcMemLazyEnablePeerAccess));
+        env->x_opened.push_back(q);
+        peers[(size_t)r] = static_cast<uint2*>(q);
+    }
+    return exchange_finish(env, peers);
+}
+
+extern "C" int cl_exchange_connect_ptrs(cl_env* env, void* const* buffers, const int32_t* devices) {
+    if (!env || !buffers) return fail(CL_ERR_INVALID, "cl_exchange_connect_ptrs: null argument");
+    if (env->d.x_n >= 0 || !env->x_buf) return fail(CL_ERR_STATE, "cl_exchange_connect_ptrs: call cl_exchange_create first (once)");
+    const int n = -env->d.x_n;
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    std::vector<uint2*> peers((size_t)n, nullptr);
+    for (int r = 0; r < n; ++r) {
+        peers[(size_t)r] = static_cast<uint2*>(buffers[r]);
+        if (r == env->d.x_rank) { if (buffers[r] != env->x_buf) return fail(CL_ERR_INVALID, "cl_exchange_connect_ptrs: buffers[rank] must be this handle's own buffer"); continue; }
+        if (devices && devices[r] != dev) {
+            int can = 0;
+            CUDA_TRY(cudaDeviceCanAccessPeer(&can, dev, devices[r]));
+            if (!can) return fail(CL_ERR_UNSUPPORTED, "cl_exchange_connect_ptrs: no peer access between the devices");
+            const cudaError_t e = cudaDeviceEnablePeerAccess(devices[r], 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(CL_ERR_CUDA, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
+            cudaGetLastError();
+        }
+    }
+    return exchange_finish(env, peers);
+}
+
+extern "C" int cl_exchange_status(cl_env* env, int32_t* timeouts, uint32_t* epoch) {
+    if (!env) return fail(CL_ERR_INVALID, "cl_exchange_status: null env");
+    if (env->d.x_n < 2) return fail(CL_ERR_STATE, "cl_exchange_status: no exchange connected");
+    if (timeouts) { CUDA_TRY(cudaDeviceSynchronize()); CUDA_TRY(cudaMemcpy(timeouts, env->x_err_dev, sizeof(int32_t), cudaMemcpyDeviceToHost)); }
+    if (epoch) *epoch = env->x_epoch;
     return CL_OK;
 }
 
 extern "C" int cl_obs_rows(cl_env* env, int32_t first_time_step, int32_t n_rows, float* rows, cl_stream stream) {
     if (!env || !rows) return fail(CL_ERR_INVALID, "cl_obs_rows: null argument");
     if (env->t < 0) return fail(CL_ERR_STATE, "cl_obs_rows: call cl_reset first");
+    { const int rc = refresh_time(env, static_cast<cudaStream_t>(stream)); if (rc) return rc; }
     if (!env->d.stale || !env->d.uniform_start) return fail(CL_ERR_STATE, "cl_obs_rows: observation rows are only env-independent with stale_observations and one episode window for all envs");
     if (n_rows < 1 || first_time_step < 1 || first_time_step + n_rows > env->T) return fail(CL_ERR_INVALID, "cl_obs_rows: time steps must lie in [1, T - 1] (the observation at t = 0 differs per env)");
     const long total = (long)n_rows * env->d.L;
@@ -1752,6 +1993,13 @@ extern "C" int cl_obs_rows(cl_env* env, int32_t first_time_step, int32_t n_rows,
 
 extern "C" int cl_time_step(const cl_env* env, int32_t* t) {
     if (!env || !t) return fail(CL_ERR_INVALID, "cl_time_step: null argument");
+    if (env->device_time && env->t >= 0) {
+        // the counter may have been advanced by graph replays the host never saw
+        int32_t v = 0;
+        CUDA_TRY(cudaDeviceSynchronize());
+        CUDA_TRY(cudaMemcpy(&v, env->t_dev, sizeof(v), cudaMemcpyDeviceToHost));
+        const_cast<cl_env*>(env)->t = v;
+    }
     *t = env->t;
     return CL_OK;
 }
@@ -1789,7 +2037,7 @@ extern "C" int cl_set_state(cl_env* env, const void* src_dev, int32_t time_step,
     p += env->st_floats * sizeof(float);
     if (env->lst_floats) CUDA_TRY(cudaMemcpyAsync(env->d.lst, p, env->lst_floats * sizeof(float), cudaMemcpyDeviceToDevice, st));
     env->t = time_step;
-    return CL_OK;
+    return publish_time(env, st);
 }
 
 extern "C" int cl_set_transforms(cl_env* env, const cl_obs_transform* obs_transform, const float* action_range, const float* action_low) {
@@ -1841,6 +2089,7 @@ extern "C" int cl_kpi_enable(cl_env* env, int32_t enable) {
 extern "C" int cl_kpi_accumulate(cl_env* env, const float* trace, const float* district, cl_stream stream) {
     if (!env || !trace || !district) return fail(CL_ERR_INVALID, "cl_kpi_accumulate: null argument");
     if (!env->kpi_unit) return fail(CL_ERR_STATE, "cl_kpi_accumulate: call cl_kpi_enable first");
+    { const int rc = refresh_time(env, static_cast<cudaStream_t>(stream)); if (rc) return rc; }
     if (env->t < 1) return fail(CL_ERR_STATE, "cl_kpi_accumulate: no step has been taken since cl_reset");
     int threads = ((std::min(env->d.B, 256) + 31) / 32) * 32;
     kpi_accumulate_kernel<<<env->d.E, threads, 0, static_cast<cudaStream_t>(stream)>>>(env->d, env->t - 1, trace, district, env->kpi_unit, env->kpi_env);

@@ -197,6 +197,42 @@ int cl_rollout(cl_env* env, int32_t n_steps, const float* actions, float* obs, f
                cl_stream stream);
 
 /*
+ * Device-resident time step: closed loops without the host (policy -> step -> policy ..., citylearn/agents/base.py:155-176)
+ * captured ONCE as a CUDA graph and replayed.  cl_step / cl_rollout take the time step from the host handle, so a captured launch
+ * would repeat the same step; cl_advance_device instead reads it from a counter on the device and advances the counter in-stream
+ * (a second, one-thread kernel), so the captured sequence is replayable.  A launch that would run past the end of the episode is a
+ * no-op (the counter stays at T - 1).
+ *   cl_device_time_enable  once per handle, OUTSIDE any capture: publishes the host's time step to the counter; from then on the
+ *                          counter is authoritative - the host entry points read it back (one stream synchronisation) when they
+ *                          need the time step, and cl_reset / cl_set_state / cl_step / cl_rollout keep it up to date
+ *   cl_advance_device      n_steps like cl_rollout (n_steps = 1: cl_step); capturable: no allocation, no synchronisation
+ */
+int cl_device_time_enable(cl_env* env, cl_stream stream);
+int cl_advance_device(cl_env* env, int32_t n_steps, const float* actions, float* obs, float* reward, float* district, cl_stream stream);
+
+/*
+ * Building-sharded districts (SURVEY.md §8e "district all-reduce variant"; citylearn/citylearn.py:1908-1918 sums net / cost /
+ * emission over ALL buildings, citylearn/reward_function.py:132-143 reads that sum).  Rank r of n holds a handle over ITS buildings of
+ * every env (same n_envs, same episode windows, decentralised rewards); inside cl_step / cl_rollout the per-env district sums are
+ * completed across the ranks by an all-gather of the partial sums through peer memory over NVLink: each (quantity, env) partial is
+ * pushed as one 8-byte {value, epoch} store into every rank's slot array and summed in rank order, so `district` and the district
+ * term of MARL are the same on every rank (float32, associated per rank: within 1e-5 of the single-GPU sums).
+ * Every rank must issue the same sequence of cl_step / cl_rollout calls (same n_steps, `district` NULL or not on all ranks).
+ *   cl_exchange_create        allocates this rank's slot array; ipc_handle_out (64 bytes, may be NULL) is its cudaIpcMemHandle for
+ *                             ranks in OTHER processes, buffer_out (may be NULL) its device pointer for ranks in THIS process
+ *   cl_exchange_connect       multi-process: ipc_handles[n_ranks][64], gathered from all ranks (entry `rank` is ignored)
+ *   cl_exchange_connect_ptrs  one process, several devices: buffers[n_ranks] device pointers, devices[n_ranks] their CUDA devices
+ *                             (peer access is enabled by the call)
+ *   cl_exchange_status        time-outs so far (a peer that does not deliver within ~2 s is counted and read as 0 instead of hanging
+ *                             the GPU; synchronises the device) and the number of steps exchanged
+ * Not available for building-tiled (wide) districts, central-agent rewards, cl_advance_device, or launches of more than one wave.
+ */
+int cl_exchange_create(cl_env* env, int32_t n_ranks, int32_t rank, void* ipc_handle_out, void** buffer_out);
+int cl_exchange_connect(cl_env* env, const void* ipc_handles);
+int cl_exchange_connect_ptrs(cl_env* env, void* const* buffers, const int32_t* devices);
+int cl_exchange_status(cl_env* env, int32_t* timeouts, uint32_t* epoch);
+
+/*
  * The observation rows shared by every env after a step: with stale_observations (reference parity) and one
  * episode window for all envs the E rows of `obs` are identical, so a caller that moves observations across PCIe can pass
  * obs = NULL to cl_step / cl_rollout and fetch ONE row per time step instead (CityLearnEnv.observations,

@@ -102,3 +102,32 @@ extern "C" void host_step(int precision, int B, int E, int W, const double* P, c
     if (precision == CL_PRECISION_FP64) step_impl<double>(B, E, W, P, ip, table, start, t, outage, T, actions, A, state, dyn_out, control_cool);
     else step_impl<float>(B, E, W, P, ip, table, start, t, outage, T, actions, A, state, dyn_out, control_cool);
 }
+
+// segment index chosen by the device-side uniform-grid search (SmemCurves with its index) and by the reference-order scan
+// (StridedCurves) for the points x[0..nx): returns -1 when the curve has no index (two points in one cell), else the mismatches.
+template <typename R>
+static int curve_check_impl(const double* xs, const double* ys, int n, const double* x, int nx, int* first_bad) {
+    R tab[kCurveTab];
+    for (int k = 0; k < CL_MAX_CURVE; ++k) {
+        tab[k] = k < n ? (R)xs[k] : Num<R>::inf(); tab[CL_MAX_CURVE + k] = k < n ? (R)ys[k] : (R)0;
+        tab[2 * CL_MAX_CURVE + k] = tab[k]; tab[3 * CL_MAX_CURVE + k] = tab[CL_MAX_CURVE + k];
+        tab[4 * CL_MAX_CURVE + k] = (R)0; tab[5 * CL_MAX_CURVE + k] = (R)0;
+    }
+    uint8_t lut[2 * kCurveLutStride];
+    if (!build_curve_lut(xs, 1, n, sizeof(R) == 4, lut)) return -1;
+    std::memcpy(lut + kCurveLutStride, lut, kCurveLutStride);
+    R strided[4 * CL_MAX_CURVE];
+    for (int k = 0; k < CL_MAX_CURVE; ++k) { strided[k] = (R)xs[k < n ? k : n - 1]; strided[CL_MAX_CURVE + k] = (R)ys[k < n ? k : n - 1]; }
+    const SmemCurves<R> a{tab, n, lut};
+    const SmemCurves<R> loop{tab, n, nullptr};
+    const StridedCurves<R, R> b{strided, 1};
+    int bad = 0;
+    for (int i = 0; i < nx; ++i) {
+        const CurveSegment<R> ga = a.segment(CL_CURVE_PE, n, (R)x[i]), gl = loop.segment(CL_CURVE_PE, n, (R)x[i]), gb = b.segment(CL_CURVE_PE, n, (R)x[i]);
+        if (!(ga.x0 == gb.x0 && ga.y0 == gb.y0 && ga.dy == gb.dy && gl.x0 == gb.x0 && gl.y0 == gb.y0)) { if (!bad) *first_bad = i; ++bad; }
+    }
+    return bad;
+}
+extern "C" int host_curve_check(int precision, const double* xs, const double* ys, int n, const double* x, int nx, int* first_bad) {
+    return precision == CL_PRECISION_FP64 ? curve_check_impl<double>(xs, ys, n, x, nx, first_bad) : curve_check_impl<float>(xs, ys, n, x, nx, first_bad);
+}

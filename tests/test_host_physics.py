@@ -136,3 +136,32 @@ def test_fp64_flow_fuzzed_parameters(hostlib, dataset, seed):
         for n in CHECKED + ['electrical_storage_degraded_capacity']:
             a, b = got[..., DYN[n]], ref[..., DYN[n]].astype('float32')
             assert np.array_equal(a, b, equal_nan=True), (n, float(np.nanmax(np.abs(a.astype('float64') - b))))
+
+
+@pytest.mark.parametrize('precision', [0, 1])
+def test_curve_grid_search_matches_reference_scan(hostlib, precision):
+    """The device-side uniform-grid segment search (SmemCurves + its index) picks the segment the reference's
+    `argmax(x <= xs) - 1` picks (energy_model.py:1083-1109): dataset curves and random ascending curves, probed at random points,
+    at / next to every abscissa and cell boundary, below 0, above 1, NaN and inf."""
+    rng = np.random.RandomState(5)
+    curves = [np.array([0.0, 0.3, 0.7, 0.8, 1.0]), np.array([0.0, 0.8, 1.0]), np.array([0.0, 1.0])]
+    for _ in range(40):
+        n = rng.randint(2, 9)
+        cells = np.sort(rng.choice(33, size=n, replace=False))
+        curves.append(np.minimum((cells + rng.uniform(0, 0.999, n)) / 32.0, 1.0 + 0 * cells))
+    hostlib.host_curve_check.restype = ctypes.c_int
+    n_indexed = 0
+    for xs in curves:
+        xs = np.ascontiguousarray(xs, dtype='float64')
+        ys = np.ascontiguousarray(rng.uniform(0.1, 1.0, len(xs)))
+        probes = [rng.uniform(-0.1, 1.2, 4000), xs, np.nextafter(xs, -1), np.nextafter(xs, 2), np.float32(xs).astype('float64'),
+                  np.nextafter(np.float32(xs), np.float32(-1)).astype('float64'), np.nextafter(np.float32(xs), np.float32(2)).astype('float64'),
+                  np.arange(34) / 32.0, np.nextafter(np.arange(34) / 32.0, -1), [np.nan, np.inf, -np.inf, 0.0, -0.0, 1e300, 5e-324]]
+        x = np.ascontiguousarray(np.concatenate([np.asarray(p, dtype='float64') for p in probes]))
+        first = ctypes.c_int(-1)
+        bad = hostlib.host_curve_check(precision, ptr(xs), ptr(ys), len(xs), ptr(x), len(x), ctypes.byref(first))
+        if bad == -1:
+            continue
+        n_indexed += 1
+        assert bad == 0, f'curve {xs}: {bad} mismatches, first at x = {x[first.value]!r}'
+    assert n_indexed >= 20
