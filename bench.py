@@ -345,13 +345,13 @@ def extra_c3(torch, dev, precision, fma_peak):
 
 def extra_c4(torch, dev, precision, peak, world, dist):
     """BASELINE configs[3], this GPU's share: synthetic 1024 buildings x 1024 envs, the FULL 8 759-step year as back-to-back
-    8-step `cl_rollout` launches (observations + rewards + district sums written every step).  With N ranks the job is the
+    32-step `cl_rollout` launches (observations + rewards + district sums written every step).  With N ranks the job is the
     configs[3] district at N x 1024 envs (env-sharded, no collective)."""
     from citylearn_b200 import CityLearnEnv, schema as S
     from citylearn_b200.synthetic import make_wide_district
     sch, src = make_wide_district(1024)
     spec = S.load(sch, data_source=src)
-    E, K = 1024, 8
+    E, K = 1024, 32                     # 32 steps per launch: observation slab 3.8 GB + rewards 134 MB per launch
     env = CityLearnEnv(spec, num_envs=E, device=dev, precision=precision)
     B, A, L = spec.n_buildings, spec.action_dim, env._obs_dim
     acts = torch.rand((K, E, A), device=dev) * 2 - 1
@@ -433,6 +433,71 @@ def extra_c5(torch, dev, precision, world, dist, K_total=96, n_graph=8):
            'env_only_ms_per_step': ms_env / K_total, 'env_only_value': world * B * E * K_total / (ms_env * 1e-3),
            'policy_flop_per_step': 2.0 * E * B * ((L // B) * 256 + 256 * 256 + 256 * (A // B)), 'scaling': 'strong (32768 envs in total)'}
     env.close(); env2.close()
+    return out
+
+
+def extra_building_sharded(torch, dev, precision, world, dist, rank, K=40, R=8, E=4096):
+    """SURVEY.md §8e "district all-reduce variant" (north_star: district-level reward terms across GPUs): 2022_phase_all with the 17
+    buildings of EVERY env split over the N GPUs, MARL rewards (they read the district sum inside the step).  Three ways to complete
+    the per-env district sums: (p2p_rollout) the fused path - K steps in ONE persistent launch per GPU, partial sums pushed into the
+    peers' memory over NVLink and summed in the kernel; (p2p_step) the same exchange with one launch per step; (nccl_step) the
+    two-phase baseline - kernel, `all_reduce` (NCCL), reward evaluation with tensor ops.  value = buildings x envs x steps / s of the
+    whole district (17 x E), max over ranks."""
+    import citylearn_b200.reward_function as rf
+    from citylearn_b200.distributed import BuildingShardedEnv
+    out = {'workload': f'{DATASET}: 17 buildings split over {world} GPUs x {E} envs, MARL (district sum inside the step)', 'unit': UNIT}
+
+    def timed(fn, n_steps, reps):
+        ms = []
+        for _ in range(reps):
+            torch.cuda.synchronize(dev); dist.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record(); torch.cuda.synchronize(dev)
+            ms.append(e0.elapsed_time(e1))
+        t = torch.tensor([median(ms)], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) / n_steps
+
+    sh = BuildingShardedEnv(DATASET, E, device=dev, exchange='p2p', reward_function=rf.MARL, precision=precision)
+    env = sh.env
+    Bl, A, L = env.spec.n_buildings, env.spec.action_dim, env._obs_dim
+    acts = torch.rand((K, E, A), device=dev) * 2 - 1
+    obs = torch.empty((K, E, L), device=dev); rew = torch.empty((K, E, Bl), device=dev); dst = torch.empty((K, E, 3), device=dev)
+    sh.reset(); sh.rollout(acts, obs, rew, dst)
+    ms = timed(lambda: sh.rollout(acts, obs, rew, dst), K, R)
+    out['p2p_rollout'] = {'ms_per_step': ms, 'value': 17 * E / (ms * 1e-3), 'steps_per_launch': K, 'buildings_on_rank0': Bl}
+
+    def steps_p2p():
+        for k in range(K):
+            sh.step(acts[k])
+    sh.reset(); steps_p2p()
+    ms = timed(steps_p2p, K, 3)
+    out['p2p_step'] = {'ms_per_step': ms, 'value': 17 * E / (ms * 1e-3)}
+    st = sh.exchange_status()
+    out['exchange'] = st
+    checksum = float(dst[-1].double().sum().item())
+    sh.close()
+
+    sn = BuildingShardedEnv(DATASET, E, device=dev, exchange='nccl', reward_function=rf.MARL, precision=precision)
+
+    def steps_nccl():
+        for k in range(K):
+            sn.step(acts[k])
+    sn.reset(); steps_nccl()
+    ms = timed(steps_nccl, K, 3)
+    out['nccl_step'] = {'ms_per_step': ms, 'value': 17 * E / (ms * 1e-3)}
+    sn.close()
+    # the same district env-sharded (no exchange at all): this rank's E / N envs of all 17 buildings
+    from citylearn_b200 import CityLearnEnv
+    Es = E // world
+    es = CityLearnEnv(DATASET, num_envs=Es, device=dev, precision=precision, central_agent=False, reward_function=rf.MARL)
+    a2 = torch.rand((K, Es, 17), device=dev) * 2 - 1
+    o2 = torch.empty((K, Es, es._obs_dim), device=dev); r2 = torch.empty((K, Es, 17), device=dev); d2 = torch.empty((K, Es, 3), device=dev)
+    es.reset(); es.rollout(a2, o2, r2, d2)
+    ms = timed(lambda: es.rollout(a2, o2, r2, d2), K, R)
+    out['env_sharded_rollout'] = {'ms_per_step': ms, 'value': 17 * E / (ms * 1e-3)}
+    es.close()
+    out['district_checksum'] = checksum
     return out
 
 
@@ -564,6 +629,8 @@ def main():
     if want != 'none':
         guarded('c4_wide_year', lambda: extra_c4(torch, dev, args.precision, peak, world, dist))
         guarded('c5_closed_loop', lambda: extra_c5(torch, dev, args.precision, world, dist))
+        if world > 1:
+            guarded('building_sharded_district', lambda: extra_building_sharded(torch, dev, args.precision, world, dist, rank))
 
     if rank != 0:
         if world > 1:

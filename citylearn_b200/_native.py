@@ -80,6 +80,7 @@ def load():
     lib.cl_launch_count.argtypes = [vp, i64p]
     i32p = ctypes.POINTER(ctypes.c_int32)
     lib.cl_launch_geometry.argtypes = [vp, i32p, i32p, i32p]
+    lib.cl_launch_occupancy.argtypes = [vp, i32p, i32p]
     lib.cl_set_transforms.argtypes = [vp, vp, vp, vp]
     lib.cl_kpi_enable.argtypes = [vp, i32]
     lib.cl_kpi_accumulate.argtypes = [vp, vp, vp, vp]
@@ -88,7 +89,7 @@ def load():
     for name in ('cl_create', 'cl_destroy', 'cl_set_outage', 'cl_reset', 'cl_step', 'cl_rollout', 'cl_obs_rows', 'cl_time_step',
                  'cl_state_size', 'cl_get_state', 'cl_set_state', 'cl_launch_count', 'cl_launch_geometry', 'cl_set_transforms',
                  'cl_kpi_enable', 'cl_kpi_accumulate', 'cl_kpi_read', 'cl_measure_fma_peak', 'cl_device_time_enable', 'cl_advance_device',
-                 'cl_exchange_create', 'cl_exchange_connect', 'cl_exchange_connect_ptrs', 'cl_exchange_status'):
+                 'cl_launch_occupancy', 'cl_exchange_create', 'cl_exchange_connect', 'cl_exchange_connect_ptrs', 'cl_exchange_status'):
         getattr(lib, name).restype = ctypes.c_int
     if lib.cl_abi_version() != ABI_VERSION:
         raise NativeLibraryError(f'{path}: ABI version {lib.cl_abi_version()} != {ABI_VERSION}; rebuild the extension')
@@ -240,7 +241,11 @@ class Handle:
     def geometry(self):
         b, t, n = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
         check(self.lib.cl_launch_geometry(self.ptr, ctypes.byref(b), ctypes.byref(t), ctypes.byref(n)))
-        return {'blocks': b.value, 'threads': t.value, 'tiles': n.value}
+        out = {'blocks': b.value, 'threads': t.value, 'tiles': n.value}
+        o, sm = ctypes.c_int32(), ctypes.c_int32()
+        if self.lib.cl_launch_occupancy(self.ptr, ctypes.byref(o), ctypes.byref(sm)) == 0:
+            out.update(blocks_per_sm=o.value, smem_bytes=sm.value)
+        return out
 
     @property
     def tiles(self) -> int:

@@ -30,14 +30,17 @@ class PerBuildingMLP(torch.nn.Module):
 
         def init(*shape, fan_in):
             return torch.nn.Parameter(((torch.rand(shape, generator=g) * 2 - 1) / fan_in ** 0.5).to(device=device, dtype=dtype))
-        self.w1, self.b1 = init(B, O, H, fan_in=O), init(B, 1, H, fan_in=O)
+        self.Op = (O + 7) // 8 * 8                 # layer-1 K padded to 16-byte rows (tensor-core eligible); the padding weights are zero
+        w1 = torch.zeros((B, self.Op, H), dtype=dtype, device=device)
+        w1[:, :O] = init(B, O, H, fan_in=O).data
+        self.w1, self.b1 = torch.nn.Parameter(w1), init(B, 1, H, fan_in=O)
         self.w2, self.b2 = init(B, H, H, fan_in=H), init(B, 1, H, fan_in=H)
         self.w3, self.b3 = init(B, H, A, fan_in=H), init(B, 1, A, fan_in=H)
         self.dtype = dtype
 
     def forward(self, obs: torch.Tensor) -> torch.Tensor:
         E = obs.shape[0]
-        x = obs.view(E, self.B, self.O).transpose(0, 1).to(self.dtype)                 # [B, E, O]
+        x = torch.nn.functional.pad(obs.view(E, self.B, self.O), (0, self.Op - self.O)).transpose(0, 1).to(self.dtype).contiguous()   # [B, E, Op]
         x = torch.relu(torch.baddbmm(self.b1, x, self.w1))
         x = torch.relu(torch.baddbmm(self.b2, x, self.w2))
         a = torch.tanh(torch.baddbmm(self.b3, x, self.w3))                              # [B, E, A]

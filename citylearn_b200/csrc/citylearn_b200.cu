@@ -43,6 +43,11 @@ struct Dev {
     int central, reward_id, stale, envs_per_block, uniform_start, start0, has_outage, any_dynamics, lstm_smem;
     int curve_nmax;        // max number of points of any battery curve of the district (uniform bound of the segment search)
     const uint8_t* curve_lut;   // [B][2][kCurveLutStride] uniform-grid index of the curve abscissae or nullptr (unit_physics.cuh)
+    // buildings usually share a handful of distinct battery curve sets (one, in the bundled datasets and the synthetic districts): with
+    // n_curves > 0 shared memory holds the n_curves distinct tables only, curve_id[b] names building b's, curve_rep[c] a building that has it
+    int n_curves;                    // 0: one table per building of the block / tile (no sharing)
+    const int32_t* curve_id;         // [B]
+    const int32_t* curve_rep;        // [n_curves]
     // building tiles: a district wider than one block is split into `tiles` tiles of `tile_b` buildings, one CTA per tile,
     // the CTAs of an env forming a thread-block cluster (tiles == 1: tile_b == B, Lt == L, no cluster)
     int tiles, tile_b, Lt;
@@ -203,7 +208,13 @@ template <typename R, bool THERMAL>
 __device__ __forceinline__ void fetch_actions(const Dev& d, const UnitCtx<R>& c, const float* act_row, RawActions& a) {
     // loads only: nothing here may consume the loaded value (even a predicated-off instruction waits for its operands, which would
     // turn the one-step-ahead prefetch into a ~600-cycle stall); the action transform is applied where the value is used
-    auto get = [&](int col) -> float { return col < 0 ? 0.f : __ldg(act_row + col); };
+    // `asm volatile`: the compiler may otherwise sink the load to its use one step later (it did: the action load sat at the top of the
+    // next iteration with a full global-memory latency exposed - ncu: 10 % of the stall samples on the F2F that consumes it)
+    auto get = [&](int col) -> float {
+        float v = 0.f;
+        if (col >= 0) asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(act_row + col));
+        return v;
+    };
     a.es = get(c.a_es);
     if (THERMAL) {
         a.cd = get(c.a_cd); a.hd = get(c.a_hd); a.coh = get(c.a_coh);
@@ -432,9 +443,11 @@ __device__ __forceinline__ float exchange_sum(const Dev& d, float acc, int e, in
         const uint2* src = own + ((size_t)(p * n + r) * d.E + e) * 3 + q;
         uint2 v = ld_slot(src);
         if (v.y != ep) {
+            // a peer that has gone away must not hang the GPU: the first wait that runs out (~2 s) raises x_err, after which no wait
+            // spins any more (the results are garbage from then on; cl_exchange_status reports it)
             const long long t_start = clock64();
             while ((v = ld_slot(src)).y != ep) {
-                if (clock64() - t_start > 4000000000LL) { atomicAdd(d.x_err, 1); v.x = 0u; break; }
+                if (clock64() - t_start > 4000000000LL || *reinterpret_cast<volatile int32_t*>(d.x_err) != 0) { atomicAdd(d.x_err, 1); v.x = 0u; break; }
             }
         }
         tot += __uint_as_float(v.x);
@@ -482,12 +495,13 @@ __device__ __forceinline__ void write_obs_general(const Dev& d, float* obs, int 
 struct SmemLayout {
     int curves, clut, bsolar, rows, tcol, tmpl, red, rsum, dsum, wpart, rpart, lstm, lstm_pre, dynbuf, end, Lp;
 };
-__host__ __device__ __forceinline__ SmemLayout smem_layout(int B, int Wp, int L, int epb, int nt, int rsize, int lstm_smem = 0, int tab_layout = 0, int fresh_slots = 0) {
+__host__ __device__ __forceinline__ SmemLayout smem_layout(int B, int Wp, int L, int epb, int nt, int rsize, int lstm_smem = 0, int tab_layout = 0, int fresh_slots = 0, int n_curves = 0) {
     SmemLayout o;
     o.Lp = (L + 3) & ~3;
     int f = 16;                                  // 64 bytes of mbarriers: 3 time-row slots + 2 observation-row buffers
-    o.curves = f; f += B * kCurveTab * (rsize / 4);   // first: keeps doubles 8-byte aligned
-    o.clut = f; f += B * kCurveLutFloats;             // uniform-grid index of the curve abscissae (bytes)
+    const int nc = n_curves > 0 ? n_curves : B;
+    o.curves = f; f += nc * kCurveTab * (rsize / 4);  // first: keeps doubles 8-byte aligned
+    o.clut = f; f += nc * kCurveLutFloats;            // uniform-grid index of the curve abscissae (bytes)
     o.bsolar = f; f += ((2 * B * (rsize / 4)) + 3) & ~3;
     o.rows = f; f += 3 * Wp;
     o.tcol = f; f += tab_layout ? 0 : o.Lp;      // gather columns: not needed when the rows come from the observation table
@@ -505,7 +519,7 @@ __host__ __device__ __forceinline__ SmemLayout smem_layout(int B, int Wp, int L,
     return o;
 }
 static size_t smem_bytes(const Dev& d, int nt, bool with_dyn, int rsize) {
-    const SmemLayout o = smem_layout(d.tile_b, d.Wp, d.Lt, d.envs_per_block, nt, rsize, d.lstm_smem, d.tab_layout, d.fresh_slots);
+    const SmemLayout o = smem_layout(d.tile_b, d.Wp, d.Lt, d.envs_per_block, nt, rsize, d.lstm_smem, d.tab_layout, d.fresh_slots, d.n_curves);
     size_t n = sizeof(float) * (size_t)o.end;
     if (with_dyn && !d.fresh_slots) n += sizeof(float) * (size_t)nt * CL_NDYN;
     return n;
@@ -641,7 +655,7 @@ __global__ void __launch_bounds__(MAXT) advance_kernel(Dev d, int t0, int K, con
     const int nb = WIDE ? min(TBs, B - b0) : B;
     const int k0 = WIDE ? __ldg(d.tile_k + rank) : 0, k1 = WIDE ? __ldg(d.tile_k + rank + 1) : d.L;
     const int Ltile = k1 - k0;
-    const SmemLayout lo = smem_layout(TBs, Wp, WIDE ? d.Lt : d.L, epb, nt, (int)sizeof(R), DYNAMICS ? d.lstm_smem : 0, d.tab_layout, d.fresh_slots);
+    const SmemLayout lo = smem_layout(TBs, Wp, WIDE ? d.Lt : d.L, epb, nt, (int)sizeof(R), DYNAMICS ? d.lstm_smem : 0, d.tab_layout, d.fresh_slots, d.n_curves);
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(smf);
     R* scurves = reinterpret_cast<R*>(smf + lo.curves);
     uint8_t* s_clut = reinterpret_cast<uint8_t*>(smf + lo.clut);
@@ -698,8 +712,10 @@ __global__ void __launch_bounds__(MAXT) advance_kernel(Dev d, int t0, int K, con
         // per building: [PE_X 8][PE_Y 8][CP_X 8][CP_Y 8][PE_RW 8][CP_RW 8] (SmemCurves): x entries beyond the curve's points are
         // +inf, RW[k] = refined reciprocal of the segment width x[k+1] - x[k]
         const auto* P = PSel<R>::p(d) + CL_P_PE_X0 * B;
-        for (int i = tid; i < nb * kCurveTab; i += nt) {
-            const int bb = b0 + i / kCurveTab, j = i % kCurveTab;
+        const int ncv = d.n_curves > 0 ? d.n_curves : nb;      // distinct tables of the district, or one per building of the tile
+        for (int i = tid; i < ncv * kCurveTab; i += nt) {
+            const int ci = i / kCurveTab, j = i % kCurveTab;
+            const int bb = d.n_curves > 0 ? __ldg(d.curve_rep + ci) : b0 + ci;
             R v;
             if (j < 4 * CL_MAX_CURVE) {
                 v = (R)__ldg(P + j * B + bb);
@@ -714,8 +730,12 @@ __global__ void __launch_bounds__(MAXT) advance_kernel(Dev d, int t0, int K, con
             scurves[i] = v;
         }
         if (d.curve_lut != nullptr) {
-            const uint32_t* src = reinterpret_cast<const uint32_t*>(d.curve_lut) + (size_t)b0 * kCurveLutFloats;
-            for (int i = tid; i < nb * kCurveLutFloats; i += nt) reinterpret_cast<uint32_t*>(s_clut)[i] = __ldg(src + i);
+            const uint32_t* src = reinterpret_cast<const uint32_t*>(d.curve_lut);
+            for (int i = tid; i < ncv * kCurveLutFloats; i += nt) {
+                const int ci = i / kCurveLutFloats, j = i - ci * kCurveLutFloats;
+                const int bb = d.n_curves > 0 ? __ldg(d.curve_rep + ci) : b0 + ci;
+                reinterpret_cast<uint32_t*>(s_clut)[i] = __ldg(src + (size_t)bb * kCurveLutFloats + j);
+            }
         }
     }
     UnitCtx<R> c;
@@ -730,8 +750,9 @@ __global__ void __launch_bounds__(MAXT) advance_kernel(Dev d, int t0, int K, con
         start_e = __ldg(d.start + e);
         fetch_actions<R, THERMAL>(d, c, actions + (size_t)e * d.A, act_next);
     }
-    const SmemCurves<R> curves = {scurves + (active ? bl : 0) * kCurveTab, d.curve_nmax,
-                                  d.curve_lut != nullptr ? s_clut + (active ? bl : 0) * (2 * kCurveLutStride) : nullptr};
+    const int my_curve = !active ? 0 : (d.n_curves > 0 ? __ldg(d.curve_id + b) : bl);
+    const SmemCurves<R> curves = {scurves + my_curve * kCurveTab, d.curve_nmax,
+                                  d.curve_lut != nullptr ? s_clut + my_curve * (2 * kCurveLutStride) : nullptr};
     const float* lstm_w = nullptr;
     if (DYNAMICS) {
         if (d.lstm_smem) {                            // stage every building's packed LSTM weights in shared memory (16-byte copies)
@@ -1183,7 +1204,7 @@ __global__ void __launch_bounds__(MAXT) reset_kernel(Dev d, float* __restrict__ 
     extern __shared__ __align__(16) float smf[];
     const int nt = blockDim.x, tid = threadIdx.x;
     const int B = d.B, epb = d.envs_per_block;
-    const SmemLayout lo = smem_layout(d.tile_b, d.Wp, d.Lt, epb, nt, (int)sizeof(R), d.lstm_smem, d.tab_layout, d.fresh_slots);
+    const SmemLayout lo = smem_layout(d.tile_b, d.Wp, d.Lt, epb, nt, (int)sizeof(R), d.lstm_smem, d.tab_layout, d.fresh_slots, d.n_curves);
     float* s_dynbuf = smf + lo.dynbuf;
     // building tiles (wide districts): block (group, rank) owns buildings [b0, b0 + nb) and observation columns [k0, k1)
     const int rank = (int)blockIdx.x % d.tiles;
@@ -1365,6 +1386,29 @@ extern "C" int cl_create(const cl_district_desc* desc, cl_env** out) {
             int rc = dev_copy(env, lut.data(), lut.size(), &p);
             if (rc) { cl_destroy(env); return rc; }
             d.curve_lut = p;
+        }
+    }
+    {
+        // distinct curve sets (point counts + the 32 abscissae / ordinates): shared-memory tables are per distinct set when there are few
+        std::vector<int32_t> cid((size_t)B, 0), rep;
+        for (int b = 0; b < B; ++b) {
+            int found = -1;
+            for (size_t c = 0; c < rep.size() && found < 0; ++c) {
+                const int r = rep[c];
+                bool same = desc->iparams[CL_IP_PE_N * B + b] == desc->iparams[CL_IP_PE_N * B + r] && desc->iparams[CL_IP_CP_N * B + b] == desc->iparams[CL_IP_CP_N * B + r];
+                for (int k = 0; k < 4 * CL_MAX_CURVE && same; ++k)
+                    same = std::memcmp(&desc->params[(size_t)(CL_P_PE_X0 + k) * B + b], &desc->params[(size_t)(CL_P_PE_X0 + k) * B + r], sizeof(double)) == 0;
+                if (same) found = (int)c;
+            }
+            if (found < 0) { if (rep.size() >= 64) { rep.clear(); break; } found = (int)rep.size(); rep.push_back(b); }
+            cid[(size_t)b] = found;
+        }
+        if (!rep.empty() && std::getenv("CL_B200_NO_CURVE_SHARING") == nullptr) {
+            int32_t *pc = nullptr, *pr = nullptr;
+            int rc = dev_copy(env, cid.data(), cid.size(), &pc);
+            if (!rc) rc = dev_copy(env, rep.data(), rep.size(), &pr);
+            if (rc) { cl_destroy(env); return rc; }
+            d.curve_id = pc; d.curve_rep = pr; d.n_curves = (int)rep.size();
         }
     }
     env->thermal = any_thermal != 0;
@@ -1644,7 +1688,9 @@ extern "C" int cl_create(const cl_district_desc* desc, cl_env** out) {
     // the attribute is per function and process-wide: never lower it below what an earlier handle needs
     static size_t optin_max = 0;
     if (smem > optin_max) optin_max = smem;
-#define OPTIN(K) cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)optin_max)
+// (the carve-out hint: prefer shared memory over L1 so that as many blocks as the registers allow are resident - the driver's default
+    // carve-out fits ONE block of a kernel with large dynamic shared memory)
+#define OPTIN(K) (cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)optin_max), cudaFuncSetAttribute(K, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared))
 #define OPTIN4(K, M) OPTIN((K<float, false, M>)); OPTIN((K<float, true, M>)); OPTIN((K<double, false, M>)); OPTIN((K<double, true, M>))
 #define OPTINA(M) OPTIN((advance_kernel<float, false, false, M>)); OPTIN((advance_kernel<float, true, false, M>)); OPTIN((advance_kernel<float, true, true, M>)); \
     OPTIN((advance_kernel<double, false, false, M>)); OPTIN((advance_kernel<double, true, false, M>)); OPTIN((advance_kernel<double, true, true, M>))
@@ -2152,6 +2198,31 @@ extern "C" int cl_measure_fma_peak(double* tflops) {
     cudaFree(out);
     CUDA_TRY(cudaGetLastError());
     *tflops = best;
+    return CL_OK;
+}
+
+// resident blocks per SM of the step kernel this handle launches (occupancy calculator with the launch's block size and dynamic
+// shared memory): diagnostics for bench.py / profiles
+extern "C" int cl_launch_occupancy(const cl_env* env, int32_t* blocks_per_sm, int32_t* smem_bytes_per_block) {
+    if (!env) return fail(CL_ERR_INVALID, "cl_launch_occupancy: null env");
+    const int nthreads = env->threads + 32;
+    const bool f64 = env->precision == CL_PRECISION_FP64;
+    const size_t smem = smem_bytes(env->d, nthreads, false, f64 ? 8 : 4);
+    const void* fn = nullptr;
+    if (env->wide) {
+        fn = f64 ? (env->thermal ? (const void*)advance_kernel<double, true, false, 512, true> : (const void*)advance_kernel<double, false, false, 512, true>)
+                 : (env->thermal ? (const void*)advance_kernel<float, true, false, 512, true> : (const void*)advance_kernel<float, false, false, 512, true>);
+    } else if (nthreads <= 512) {
+        fn = f64 ? (env->dynamics ? (const void*)advance_kernel<double, true, true, 512> : (env->thermal ? (const void*)advance_kernel<double, true, false, 512> : (const void*)advance_kernel<double, false, false, 512>))
+                 : (env->dynamics ? (const void*)advance_kernel<float, true, true, 512> : (env->thermal ? (const void*)advance_kernel<float, true, false, 512> : (const void*)advance_kernel<float, false, false, 512>));
+    } else {
+        fn = f64 ? (env->dynamics ? (const void*)advance_kernel<double, true, true, 1024> : (env->thermal ? (const void*)advance_kernel<double, true, false, 1024> : (const void*)advance_kernel<double, false, false, 1024>))
+                 : (env->dynamics ? (const void*)advance_kernel<float, true, true, 1024> : (env->thermal ? (const void*)advance_kernel<float, true, false, 1024> : (const void*)advance_kernel<float, false, false, 1024>));
+    }
+    int n = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, nthreads, smem));
+    if (blocks_per_sm) *blocks_per_sm = n;
+    if (smem_bytes_per_block) *smem_bytes_per_block = (int32_t)smem;
     return CL_OK;
 }
 

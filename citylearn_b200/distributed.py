@@ -69,3 +69,116 @@ def fleet_reward_stats(reward_sum: torch.Tensor, reward_min: torch.Tensor, rewar
     n_envs = local_n.item()
     return {'sum_per_env_mean': local_sum / n_envs, 'mean_per_step': local_sum / (n_envs * max(steps, 1)), 'min': local_min, 'max': local_max,
             'n_envs': int(n_envs)}
+
+
+# ------------------------------------------------------------------------------------------------------------------------------
+# Building-sharded districts (SURVEY.md §8e "district all-reduce variant"): rank r holds SOME buildings of every env; the per-env
+# district sums (citylearn/citylearn.py:1908-1918) - and with them the district term of MARL (citylearn/reward_function.py:132-143) -
+# are completed across the ranks inside the step.
+# ------------------------------------------------------------------------------------------------------------------------------
+class BuildingShardedEnv:
+    """This rank's buildings `[first, first + count)` of every env of a district that is split over `world` GPUs.
+
+    `exchange='p2p'` (default): the fused path - the step kernel pushes its partial district sums into every peer's memory over
+    NVLink and completes the sums itself (`cl_exchange_*`, include/citylearn_b200.h): ONE launch per step, no collective call.
+    `exchange='nccl'`: the two-phase baseline - the step kernel leaves partial sums, `torch.distributed.all_reduce` (NCCL) adds them,
+    district-dependent rewards are evaluated afterwards with tensor ops (RewardFunction / MARL only).
+
+    Observations, rewards and actions cover this rank's buildings only (`[E, L_local]`, `[E, B_local]`, `[E, A_local]`); `district`
+    is the full-district `[E, 3]` on every rank.  All ranks must step in lock-step."""
+
+    def __init__(self, schema, num_envs: int, device=None, exchange: str = 'p2p', rank: Optional[int] = None, world: Optional[int] = None,
+                 connect: bool = True, **kwargs):
+        from . import schema as S
+        from .env import CityLearnEnv
+        if rank is None or world is None:
+            rank, world = rank_and_world()
+        if exchange not in ('p2p', 'nccl'):
+            raise ValueError("exchange must be 'p2p' or 'nccl'")
+        self.rank, self.world, self.exchange = rank, world, exchange
+        kwargs.pop('central_agent', None)
+        kwargs.pop('buildings', None)
+        full = S.load(schema, central_agent=False, **kwargs)
+        names = [b.name for b in full.buildings]
+        self.first, self.count = shard_range(len(names), rank, world)
+        if self.count == 0:
+            raise ValueError(f'rank {rank} of {world} would own no building out of {len(names)}')
+        self.n_buildings_total = len(names)
+        self.env = CityLearnEnv(schema, num_envs=num_envs, device=device, central_agent=False,
+                                buildings=names[self.first:self.first + self.count], debug_trace=(exchange == 'nccl'), **kwargs)
+        self.env.building_offset, self.env.total_buildings = self.first, len(names)
+        self._handle_bytes, self._buffer = (None, None)
+        if world > 1 and exchange == 'p2p':
+            with torch.cuda.device(self.env.device):
+                self._handle_bytes, self._buffer = self.env._h.exchange_create(world, rank)
+            if connect:
+                self.connect_processes()
+        if exchange == 'nccl':
+            from . import reward_function as rf
+            self._marl = isinstance(self.env.reward_function, rf.MARL)
+            if not self._marl and type(self.env.reward_function) is not rf.RewardFunction:
+                raise NotImplementedError("exchange='nccl' evaluates RewardFunction / MARL only")
+
+    # ---- wiring ----
+    def connect_processes(self, group=None):
+        """One process per GPU: all-gather the 64-byte IPC handles of the slot arrays and map the peers' arrays."""
+        dev = self.env.device
+        mine = torch.tensor(list(self._handle_bytes), dtype=torch.uint8, device=dev)
+        outs = [torch.empty_like(mine) for _ in range(self.world)]
+        dist.all_gather(outs, mine, group=group)
+        handles = b''.join(bytes(o.cpu().tolist()) for o in outs)
+        with torch.cuda.device(dev):
+            self.env._h.exchange_connect(handles)
+        dist.barrier(group=group)
+
+    @staticmethod
+    def connect_in_process(shards):
+        """All ranks live in THIS process on different devices (tests, single-process multi-GPU drivers)."""
+        bufs = [s._buffer for s in shards]
+        devs = [s.env.device.index for s in shards]
+        for s in shards:
+            with torch.cuda.device(s.env.device):
+                s.env._h.exchange_connect_ptrs(bufs, devs)
+
+    # ---- stepping ----
+    def reset(self, **kw):
+        return self.env.reset(**kw)
+
+    def step(self, actions: torch.Tensor):
+        env = self.env
+        if self.exchange == 'p2p' or self.world == 1:
+            return env.step(actions)
+        # two-phase baseline: partial sums -> NCCL all-reduce -> district-dependent rewards
+        from . import schema as S
+        with torch.cuda.device(env.device):
+            a, _ = env._parse_actions(actions)
+            env._h.step(a.data_ptr(), env._obs.data_ptr(), None, env._district.data_ptr(), env._trace.data_ptr(), env._stream())
+            dist.all_reduce(env._district)
+            net = env._trace[:, :, S.DYN['net_electricity_consumption']]
+            if self._marl:
+                be = -net.double()
+                r = torch.sign(be) * 0.01 * be * be * env._district[:, 0:1].double().clamp_min(0.0)
+                env._reward.copy_(r.float())
+            else:
+                m = net.clamp_min(0.0)
+                ex = float(env.reward_function.exponent)
+                env._reward.copy_(-m if ex == 1.0 else -m.pow(ex))
+            env.time_step += 1
+            env._obs_current = True
+        return env._obs, env._reward, env.terminated, False, {}
+
+    def rollout(self, actions, obs=None, reward=None, district=None):
+        if self.exchange != 'p2p' and self.world > 1:
+            raise NotImplementedError("rollout() needs exchange='p2p'")
+        return self.env.rollout(actions, obs, reward, district)
+
+    @property
+    def district(self) -> torch.Tensor:
+        return self.env.district
+
+    def exchange_status(self):
+        with torch.cuda.device(self.env.device):
+            return self.env._h.exchange_status()
+
+    def close(self):
+        self.env.close()

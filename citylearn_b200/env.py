@@ -59,6 +59,7 @@ class BuildingProxy:
         self.action_space = Box(low=spec.action_low, high=spec.action_high, dtype=np.float32)
         self.time_step_ratio = spec.time_step_ratio
         self.seconds_per_time_step = spec.seconds_per_time_step
+        self._norm_limits = None
 
     @property
     def active_observations(self) -> List[str]:
@@ -67,6 +68,78 @@ class BuildingProxy:
     @property
     def active_actions(self) -> List[str]:
         return self._spec.active_actions
+
+    # ---- what the reference's own wrappers / agents call on `env.unwrapped.buildings[i]` (citylearn/wrappers.py:90-165, 193-204) ----
+    @property
+    def index(self) -> int:
+        return self._env.spec.buildings.index(self._spec)
+
+    def _current_values(self) -> Dict[str, float]:
+        """name -> value of this building's ACTIVE observations at the env's current time step (what `Building.observations()` walks,
+        citylearn/building.py:1115-1160): series values from the table, action-dependent values from the env's observation row."""
+        env = self._env
+        if env.num_envs != 1:
+            raise RuntimeError('BuildingProxy.observations() mirrors the single-env reference API; batched envs read `env.observations`')
+        if env._observation_transform is not None:
+            raise RuntimeError('BuildingProxy.observations() needs the raw observation row (the env has a fused observation transform)')
+        bi = self.index
+        if env._proxy_layout is None:
+            entries, desc = S.observation_layout(env.spec, False, env.stale_observations)
+            env._proxy_layout = (entries, desc, {key: j for j, key in enumerate(env._entries)})
+        entries, desc, pos = env._proxy_layout
+        row = env.observations
+        flat = row[0] if env.central_agent else [v for r in row for v in r]
+        t = env.time_step
+        trow = env.spec.table[int(env.episode_tracker.episode_start_time_step) + t]
+        out: Dict[str, float] = {}
+        for (b2, name), d in zip(entries, desc):
+            if b2 != bi:
+                continue
+            if d[0] == S.OBS_TS:
+                out[name] = float(trow[d[1]])
+            elif d[0] == S.OBS_OUTAGE:
+                out[name] = float(env._outage[bi, t])
+            else:
+                out[name] = float(flat[pos[(bi, name)]])
+        return out
+
+    def estimate_observation_space_limits(self, include_all: bool = None, periodic_normalization: bool = None):
+        return S.estimate_observation_space_limits(self._spec, self._env.spec, include_all=bool(include_all), periodic_normalization=bool(periodic_normalization))
+
+    def estimate_observation_space(self, include_all: bool = None, normalize: bool = None) -> Box:
+        """citylearn/building.py:1836-1865."""
+        if normalize:
+            lo, _ = self.estimate_observation_space_limits(include_all, True)
+            return Box(low=np.zeros(len(lo), dtype='float32'), high=np.ones(len(lo), dtype='float32'), dtype=np.float32)
+        lo, hi = self.estimate_observation_space_limits(include_all, False)
+        return Box(low=np.array(list(lo.values()), dtype='float32'), high=np.array(list(hi.values()), dtype='float32'), dtype=np.float32)
+
+    def observations(self, include_all: bool = None, normalize: bool = None, periodic_normalization: bool = None,
+                     check_limits: bool = None) -> Mapping[str, float]:
+        """Observations at the current time step as the reference's `Building.observations` returns them (citylearn/building.py:1115-1219):
+        active observations in schema order, optionally `<name>_cos`, `<name>_sin` for the periodic ones (in that order) and min-max
+        normalisation with the `include_all=True` limits (`x_min == x_max` gives 0, citylearn/preprocessing.py:139-152)."""
+        if include_all:
+            raise NotImplementedError('include_all=True (the 67-key reward dictionary) is served to reward functions directly; wrappers use active observations')
+        obs = self._current_values()
+        if periodic_normalization:
+            out: Dict[str, float] = {}
+            for k, v in obs.items():
+                if k in S.PERIODIC_OBSERVATIONS:
+                    x = 2 * np.pi * v / S.PERIODIC_OBSERVATIONS[k]
+                    out[f'{k}_cos'] = float(np.cos(x))
+                    out[f'{k}_sin'] = float(np.sin(x))
+                else:
+                    out[k] = v
+            obs = out
+        if normalize:
+            if self._norm_limits is None:
+                self._norm_limits = S.estimate_observation_space_limits(self._spec, self._env.spec, include_all=True, periodic_normalization=True)
+            lo, hi = self._norm_limits
+            for k, v in obs.items():
+                x_min, x_max = lo[k], hi[k]
+                obs[k] = 0 if x_min == x_max else (v - x_min) / (x_max - x_min)
+        return obs
 
     def get_metadata(self) -> Mapping[str, Any]:
         dv = self._spec.devices
@@ -147,6 +220,7 @@ class CityLearnEnv:
         self._reward_params = rparams
         self._debug_trace = debug_trace
         self._h = None
+        self._proxy_layout = None
         self._build_native()
         self._table_dev = None
         self.time_step = 0

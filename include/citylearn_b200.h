@@ -294,6 +294,8 @@ int cl_kpi_read(cl_env* env, double* unit_dev, double* env_dev, cl_stream stream
 /* Launch geometry chosen at cl_create: CTAs per launch, threads per CTA (incl. the helper warp) and building tiles per env
  * (1: a block owns whole envs; > 1: one thread-block cluster per env, one CTA per tile of buildings). */
 int cl_launch_geometry(const cl_env* env, int32_t* blocks, int32_t* threads, int32_t* tiles);
+/* Resident CTAs per SM of that launch (CUDA occupancy calculator) and its dynamic shared memory per CTA - diagnostics. */
+int cl_launch_occupancy(const cl_env* env, int32_t* blocks_per_sm, int32_t* smem_bytes_per_block);
 
 /* Measured FP32 FMA throughput of the current device in TFLOP/s (a microbenchmark of independent FFMA chains): the roofline
  * denominator of the LSTM-dynamics path, which is FP32-FMA bound.  Synchronises the device. */

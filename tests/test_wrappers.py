@@ -127,3 +127,46 @@ def test_fused_wrappers_batched_rollout_and_sb3():
             if t['fn'][col] == S.OBS_FN_IDENTITY:
                 exp = orr[:, j].astype('float64') * float(t['scale'][col]) + float(t['offset'][col])
                 np.testing.assert_allclose(ow[:, col], exp, rtol=0, atol=2e-6)
+
+
+def _reference_wrappers():
+    """The reference's own `citylearn.wrappers` from oracle/_ref (installed by oracle/build_ref.py; travels to the GPU box)."""
+    import sys
+    ROOT = GOLDEN.parents[1]
+    site = ROOT / 'oracle' / '_ref' / 'site'
+    if not (site / 'citylearn' / 'wrappers.py').is_file():
+        pytest.skip('oracle/_ref not built (run __graft_entry__.build() where /root/reference exists)')
+    for q in (ROOT / 'oracle' / 'shims', site):
+        if str(q) not in sys.path:
+            sys.path.insert(0, str(q))
+    import citylearn.wrappers as RW
+    return RW
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('case', CASES)
+def test_reference_wrappers_run_unmodified_on_this_env(case):
+    """SURVEY §8b "metadata facade": the UNMODIFIED reference wrappers (citylearn/wrappers.py:15-238) wrap this env at num_envs = 1 -
+    they walk `env.unwrapped.buildings[i].observations(normalize=..., periodic_normalization=...)`, `estimate_observation_space(normalize=True)`
+    and `action_space` - and return what they return around the reference env (tests/golden/wrappers)."""
+    RW = _reference_wrappers()
+    from citylearn_b200 import CityLearnEnv
+    z, cfg = load(case)
+    sch, src, ov = schema_for(cfg)
+    base = CityLearnEnv(sch, data_source=src, num_envs=1, **ov)
+    env = getattr(RW, cfg['wrapper'])(base)
+    assert [n for row in env.observation_names for n in row] == [n for row in cfg['observation_names'] for n in row]
+    assert np.array_equal(np.concatenate([s.low for s in env.observation_space]), z['space_low'])
+    assert np.array_equal(np.concatenate([s.high for s in env.observation_space]), z['space_high'])
+    obs, _ = env.reset()
+    np.testing.assert_allclose(np.array([v for row in obs for v in row], dtype='float64'), z['reset_obs'], rtol=0, atol=2e-6)
+    sizes = [len(r) for r in base.action_names]
+    for k in range(len(z['actions'])):
+        a = [float(x) for x in z['actions'][k]]
+        nested, o = [], 0
+        for n in sizes:
+            nested.append(a[o:o + n])
+            o += n
+        obs, rew, term, _, _ = env.step(nested)
+        np.testing.assert_allclose(np.array([v for row in obs for v in row], dtype='float64'), z['obs'][k], rtol=0, atol=2e-6)
+        np.testing.assert_allclose(np.array(rew, dtype='float32'), z['reward'][k], rtol=1e-5, atol=1e-5)
