@@ -85,11 +85,12 @@ def load():
     lib.cl_kpi_enable.argtypes = [vp, i32]
     lib.cl_kpi_accumulate.argtypes = [vp, vp, vp, vp]
     lib.cl_kpi_read.argtypes = [vp, vp, vp, vp]
+    lib.cl_kpi_fused.argtypes = [vp, i32p]
     lib.cl_measure_fma_peak.argtypes = [ctypes.POINTER(ctypes.c_double)]
     for name in ('cl_create', 'cl_destroy', 'cl_set_outage', 'cl_reset', 'cl_step', 'cl_rollout', 'cl_obs_rows', 'cl_time_step',
                  'cl_state_size', 'cl_get_state', 'cl_set_state', 'cl_launch_count', 'cl_launch_geometry', 'cl_set_transforms',
                  'cl_kpi_enable', 'cl_kpi_accumulate', 'cl_kpi_read', 'cl_measure_fma_peak', 'cl_device_time_enable', 'cl_advance_device',
-                 'cl_launch_occupancy', 'cl_exchange_create', 'cl_exchange_connect', 'cl_exchange_connect_ptrs', 'cl_exchange_status'):
+                 'cl_launch_occupancy', 'cl_kpi_fused', 'cl_exchange_create', 'cl_exchange_connect', 'cl_exchange_connect_ptrs', 'cl_exchange_status'):
         getattr(lib, name).restype = ctypes.c_int
     if lib.cl_abi_version() != ABI_VERSION:
         raise NativeLibraryError(f'{path}: ABI version {lib.cl_abi_version()} != {ABI_VERSION}; rebuild the extension')
@@ -231,6 +232,11 @@ class Handle:
 
     def kpi_enable(self, enable: bool = True):
         check(self.lib.cl_kpi_enable(self.ptr, int(bool(enable))), 'cl_kpi_enable')
+
+    def kpi_fused(self) -> bool:
+        f = ctypes.c_int32()
+        check(self.lib.cl_kpi_fused(self.ptr, ctypes.byref(f)), 'cl_kpi_fused')
+        return bool(f.value)
 
     def kpi_accumulate(self, trace_ptr, district_ptr, stream: int):
         check(self.lib.cl_kpi_accumulate(self.ptr, trace_ptr, district_ptr, stream), 'cl_kpi_accumulate')

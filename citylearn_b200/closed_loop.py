@@ -111,5 +111,5 @@ class ClosedLoop:
         env.time_step += int(n_steps)
         env._obs_current = True
         env._hist_valid = False
-        env._kpi_valid = False
+        env._kpi_valid = env._kpi_valid and env._kpi_fused
         return self.ret

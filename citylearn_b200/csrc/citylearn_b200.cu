@@ -81,6 +81,11 @@ struct Dev {
     const float* outage;   // [B][T] or nullptr
     const int32_t* start;  // [E]
     const int32_t* t_dev;  // [1] device-resident time step (cl_step_device: launches with t0 < 0 read it)
+    // online KPI accumulators fused into the step (cl_kpi_enable on a district that is neither building-tiled nor LSTM-driven): the
+    // running sums live in shared memory for the steps of a launch and are folded into these arrays when it ends
+    double* kpi_unit;                // [E][B][CL_NKPI_UNIT] or nullptr
+    double* kpi_env;                 // [E][2][CL_NKPI_ENV]
+    int kpi_smem;                    // 1: the shared-memory layout carries the accumulators
     // building-sharded districts (cl_exchange_*): this handle owns SOME buildings of every env; the per-env district sums are completed
     // inside the step by an all-gather of the ranks' partial sums through peer memory (NVLink): every (quantity, env) value travels as
     // ONE 8-byte {value, epoch} store into every peer's slot array - data and flag in one NVLink transaction, no fence, no second
@@ -493,9 +498,9 @@ __device__ __forceinline__ void write_obs_general(const Dev& d, float* obs, int 
 // offsets in floats from the start of the dynamic shared memory (kept as plain ints so that every access is derived
 // directly from the `extern __shared__` array and compiles to LDS/STS with 32-bit addressing, not generic loads)
 struct SmemLayout {
-    int curves, clut, bsolar, rows, tcol, tmpl, red, rsum, dsum, wpart, rpart, lstm, lstm_pre, dynbuf, end, Lp;
+    int curves, clut, bsolar, rows, tcol, tmpl, red, rsum, dsum, wpart, rpart, lstm, lstm_pre, dynbuf, kpi_acc, kpi_nws, kpi_env, end, Lp;
 };
-__host__ __device__ __forceinline__ SmemLayout smem_layout(int B, int Wp, int L, int epb, int nt, int rsize, int lstm_smem = 0, int tab_layout = 0, int fresh_slots = 0, int n_curves = 0) {
+__host__ __device__ __forceinline__ SmemLayout smem_layout(int B, int Wp, int L, int epb, int nt, int rsize, int lstm_smem = 0, int tab_layout = 0, int fresh_slots = 0, int n_curves = 0, int kpi = 0) {
     SmemLayout o;
     o.Lp = (L + 3) & ~3;
     int f = 16;                                  // 64 bytes of mbarriers: 3 time-row slots + 2 observation-row buffers
@@ -515,11 +520,17 @@ __host__ __device__ __forceinline__ SmemLayout smem_layout(int B, int Wp, int L,
     o.lstm_pre = f; f += lstm_smem ? B * kLstmPreRing * 64 : 0;   // per-building ring of shared layer-0 input projections
     // with per-env row images the general writer's dynbuf is never live at the same time: it aliases them (cl_create checks the size)
     o.dynbuf = fresh_slots ? o.tmpl : f;
+    // fused KPI accumulators (doubles; f is kept even): [CL_NKPI_UNIT][nt] running sums, [2][nt] baseline net of the step (by step
+    // parity), [epb][2][CL_NKPI_ENV] district series state.  The general writer's dynbuf (appended after `end`) never coexists with them.
+    f = (f + 1) & ~1;
+    o.kpi_acc = f; f += kpi ? 2 * CL_NKPI_UNIT * nt : 0;
+    o.kpi_nws = f; f += kpi ? 2 * 2 * nt : 0;
+    o.kpi_env = f; f += kpi ? 2 * 2 * CL_NKPI_ENV * epb : 0;
     o.end = f;
     return o;
 }
 static size_t smem_bytes(const Dev& d, int nt, bool with_dyn, int rsize) {
-    const SmemLayout o = smem_layout(d.tile_b, d.Wp, d.Lt, d.envs_per_block, nt, rsize, d.lstm_smem, d.tab_layout, d.fresh_slots, d.n_curves);
+    const SmemLayout o = smem_layout(d.tile_b, d.Wp, d.Lt, d.envs_per_block, nt, rsize, d.lstm_smem, d.tab_layout, d.fresh_slots, d.n_curves, d.kpi_smem);
     size_t n = sizeof(float) * (size_t)o.end;
     if (with_dyn && !d.fresh_slots) n += sizeof(float) * (size_t)nt * CL_NDYN;
     return n;
@@ -615,6 +626,8 @@ __device__ __forceinline__ float lstm_update(const Dev& d, const UnitCtx<R>& c, 
     return y * c.tin_range + c.tin_min;                                      // de-normalised (building.py:3031-3037)
 }
 
+__device__ __forceinline__ void kpi_push(double* a, double x);
+
 // ------------------------------------------------------------------------------------------------------------------
 // advance kernel: K consecutive time steps in one launch (cl_step: K = 1, cl_rollout: any K).
 //
@@ -655,7 +668,7 @@ __global__ void __launch_bounds__(MAXT) advance_kernel(Dev d, int t0, int K, con
     const int nb = WIDE ? min(TBs, B - b0) : B;
     const int k0 = WIDE ? __ldg(d.tile_k + rank) : 0, k1 = WIDE ? __ldg(d.tile_k + rank + 1) : d.L;
     const int Ltile = k1 - k0;
-    const SmemLayout lo = smem_layout(TBs, Wp, WIDE ? d.Lt : d.L, epb, nt, (int)sizeof(R), DYNAMICS ? d.lstm_smem : 0, d.tab_layout, d.fresh_slots, d.n_curves);
+    const SmemLayout lo = smem_layout(TBs, Wp, WIDE ? d.Lt : d.L, epb, nt, (int)sizeof(R), DYNAMICS ? d.lstm_smem : 0, d.tab_layout, d.fresh_slots, d.n_curves, d.kpi_smem);
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(smf);
     R* scurves = reinterpret_cast<R*>(smf + lo.curves);
     uint8_t* s_clut = reinterpret_cast<uint8_t*>(smf + lo.clut);
@@ -667,6 +680,10 @@ __global__ void __launch_bounds__(MAXT) advance_kernel(Dev d, int t0, int K, con
     float* s_dynbuf = smf + lo.dynbuf;
     float* s_wpart = smf + lo.wpart;
     double* s_rpart = reinterpret_cast<double*>(smf + lo.rpart);
+    const bool kpi = !WIDE && !DYNAMICS && d.kpi_smem && d.kpi_unit != nullptr;
+    double* s_kacc = reinterpret_cast<double*>(smf + lo.kpi_acc);      // [CL_NKPI_UNIT][nt]
+    double* s_knws = reinterpret_cast<double*>(smf + lo.kpi_nws);      // [2][nt]
+    double* s_kenv = reinterpret_cast<double*>(smf + lo.kpi_env);      // [epb][2][CL_NKPI_ENV]
     const int e0 = (WIDE ? (int)blockIdx.x / NT : (int)blockIdx.x) * epb;
     const int n_env = min(epb, d.E - e0);
     const int n_units = n_env * nb;
@@ -763,6 +780,11 @@ __global__ void __launch_bounds__(MAXT) advance_kernel(Dev d, int t0, int K, con
         } else {
             lstm_w = d.lstm_w + (size_t)(active ? b : 0) * kLstmStride;
         }
+    }
+    if (kpi) {
+#pragma unroll
+        for (int j = 0; j < CL_NKPI_UNIT; ++j) s_kacc[j * nt + tid] = 0.0;
+        for (int i = tid; i < n_env * 2 * CL_NKPI_ENV; i += nt) s_kenv[i] = d.kpi_env[(size_t)e0 * 2 * CL_NKPI_ENV + i];
     }
     __syncthreads();   // mbarriers initialised (visible to every waiter), curves / tcol / LSTM weights staged
 
@@ -938,6 +960,23 @@ __global__ void __launch_bounds__(MAXT) advance_kernel(Dev d, int t0, int K, con
             red[nt + ul] = (float)o.cost;
             red[2 * nt + ul] = (float)o.emission;
             if (fused_reward) reward_inputs<R, THERMAL>(d, c, s, o, row, t_in, ri);     // everything the reward needs from row t
+            if (kpi) {
+                // CityLearnEnv.evaluate()'s action-dependent series (citylearn.py:1136-1323): control = the simulated values, baseline
+                // = net without the storage devices' consumption (building.py:2886-2893); float32 values like the traced ones
+                const double net = (double)(float)o.net;
+                const double sto = (double)dyn_value<R>(CL_DYN_COOLING_STORAGE_ELECTRICITY_CONSUMPTION, c.p, s, o, (R)t_in)
+                                 + (double)dyn_value<R>(CL_DYN_HEATING_STORAGE_ELECTRICITY_CONSUMPTION, c.p, s, o, (R)t_in)
+                                 + (double)dyn_value<R>(CL_DYN_DHW_STORAGE_ELECTRICITY_CONSUMPTION, c.p, s, o, (R)t_in)
+                                 + (double)dyn_value<R>(CL_DYN_ELECTRICAL_STORAGE_ELECTRICITY_CONSUMPTION, c.p, s, o, (R)t_in);
+                const double nws = net - sto;
+                const double price = (double)row[c.c_price], carbon = (double)row[c.c_carbon];
+                double* a = s_kacc + tid;
+                a[CL_KPI_EC * nt] += fmax(net, 0.0); a[CL_KPI_ZNE * nt] += net;
+                a[CL_KPI_EMISSION * nt] += fmax((double)(float)o.emission, 0.0); a[CL_KPI_COST * nt] += fmax((double)(float)o.cost, 0.0);
+                a[CL_KPI_B_EC * nt] += fmax(nws, 0.0); a[CL_KPI_B_ZNE * nt] += nws;
+                a[CL_KPI_B_EMISSION * nt] += fmax(carbon * nws, 0.0); a[CL_KPI_B_COST * nt] += fmax(price * nws, 0.0);
+                s_knws[pb * nt + ul] = nws;
+            }
             if (fresh_tab) {
                 // this unit's action-dependent observation columns go into its env's row image (loaded one step ago)
                 mbar_wait(s_bar + 3 + pb, (uint32_t)((k >> 1) & 1));
@@ -1041,6 +1080,14 @@ __global__ void __launch_bounds__(MAXT) advance_kernel(Dev d, int t0, int K, con
             if (d.x_n > 1) acc = exchange_sum(d, acc, e0 + le, q, d.x_epoch + (unsigned)k + 1u);
             if (q == 0) s_dsum[pb * epb + le] = acc;
             if (district != nullptr) district[((size_t)k * d.E + e0 + le) * 3 + q] = acc;
+            if (kpi && q == 0) {
+                // district series of this env: control = the district net, baseline = sum over buildings of the net without storage
+                const double* nw = s_knws + pb * nt + le * B;
+                double tot = 0.0;
+                for (int jj = 0; jj < B; ++jj) tot += nw[jj];
+                kpi_push(s_kenv + (size_t)(le * 2 + 0) * CL_NKPI_ENV, (double)acc);
+                kpi_push(s_kenv + (size_t)(le * 2 + 1) * CL_NKPI_ENV, tot);
+            }
         }
         if (need_dsum) __syncthreads();                                        // S2 only when a reward reads the district sum
         if (fused_reward) {
@@ -1093,6 +1140,14 @@ __global__ void __launch_bounds__(MAXT) advance_kernel(Dev d, int t0, int K, con
 #ifdef CL_PHASE_TIMING
     { const int k = K - 1; CL_STAMP(7); }
 #endif
+    if (kpi) {
+        __syncthreads();                                 // the last step's env-level pushes are complete
+        if (active && !is_helper) {
+#pragma unroll
+            for (int j = 0; j < CL_NKPI_UNIT; ++j) d.kpi_unit[(size_t)u * CL_NKPI_UNIT + j] += s_kacc[j * nt + tid];
+        }
+        for (int i = tid; i < n_env * 2 * CL_NKPI_ENV; i += nt) d.kpi_env[(size_t)e0 * 2 * CL_NKPI_ENV + i] = s_kenv[i];
+    }
     if (is_helper) tma_store_wait_all<0>();
     if (active && !is_helper) store_state<R, THERMAL>(d, u, s);
     if (coupled) cluster_sync_all();  // nobody exits while a peer may still read its partial sums
@@ -1204,7 +1259,7 @@ __global__ void __launch_bounds__(MAXT) reset_kernel(Dev d, float* __restrict__ 
     extern __shared__ __align__(16) float smf[];
     const int nt = blockDim.x, tid = threadIdx.x;
     const int B = d.B, epb = d.envs_per_block;
-    const SmemLayout lo = smem_layout(d.tile_b, d.Wp, d.Lt, epb, nt, (int)sizeof(R), d.lstm_smem, d.tab_layout, d.fresh_slots, d.n_curves);
+    const SmemLayout lo = smem_layout(d.tile_b, d.Wp, d.Lt, epb, nt, (int)sizeof(R), d.lstm_smem, d.tab_layout, d.fresh_slots, d.n_curves, d.kpi_smem);
     float* s_dynbuf = smf + lo.dynbuf;
     // building tiles (wide districts): block (group, rank) owns buildings [b0, b0 + nb) and observation columns [k0, k1)
     const int rank = (int)blockIdx.x % d.tiles;
@@ -1277,6 +1332,7 @@ struct cl_env {
     float* obs_tab_dev = nullptr;   // precomputed observation table (build_obs_table)
     double* kpi_unit = nullptr;     // online KPI accumulators (cl_kpi_enable)
     double* kpi_env = nullptr;
+    bool kpi_fused = false;         // accumulated inside advance_kernel (else: cl_kpi_accumulate on the step's trace)
     float* dpart = nullptr;         // wide districts: per-tile partial district sums of one launch chunk
     size_t dpart_floats = 0;
     bool wide = false;       // building-tiled district: cluster launch of advance_kernel<..., WIDE = true>
@@ -1331,6 +1387,25 @@ static int build_obs_table(cl_env* env) {
     CUDA_TRY(cudaDeviceSynchronize());
     d.obs_tab = env->obs_tab_dev;
     return CL_OK;
+}
+
+// opt in to large dynamic shared memory (both kernels, all instantiations).  The attribute is per function and process-wide: never
+// lower it below what an earlier handle needs
+static void ensure_smem_optin(size_t smem) {
+    static size_t optin_max = 0;
+    if (smem > optin_max) optin_max = smem;
+// (the carve-out hint: prefer shared memory over L1 so that as many blocks as the registers allow are resident - the driver's default
+    // carve-out fits ONE block of a kernel with large dynamic shared memory)
+#define OPTIN(K) (cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)optin_max), cudaFuncSetAttribute(K, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared))
+#define OPTIN4(K, M) OPTIN((K<float, false, M>)); OPTIN((K<float, true, M>)); OPTIN((K<double, false, M>)); OPTIN((K<double, true, M>))
+#define OPTINA(M) OPTIN((advance_kernel<float, false, false, M>)); OPTIN((advance_kernel<float, true, false, M>)); OPTIN((advance_kernel<float, true, true, M>)); \
+    OPTIN((advance_kernel<double, false, false, M>)); OPTIN((advance_kernel<double, true, false, M>)); OPTIN((advance_kernel<double, true, true, M>))
+    OPTINA(512); OPTINA(1024); OPTIN4(reset_kernel, 512); OPTIN4(reset_kernel, 1024);
+    OPTIN((advance_kernel<float, false, false, 512, true>)); OPTIN((advance_kernel<float, true, false, 512, true>));
+    OPTIN((advance_kernel<double, false, false, 512, true>)); OPTIN((advance_kernel<double, true, false, 512, true>));
+#undef OPTINA
+#undef OPTIN4
+#undef OPTIN
 }
 
 extern "C" int cl_abi_version(void) { return CL_ABI_VERSION; }
@@ -1651,7 +1726,8 @@ extern "C" int cl_create(const cl_district_desc* desc, cl_env** out) {
             for (int r = 0; r <= nt_; ++r) aligned = aligned && (tk[r] & 3) == 0;
             Dev probe = d; probe.tiles = nt_; probe.tile_b = tb; probe.Lt = lt; probe.envs_per_block = 1; probe.fresh_slots = 0;
             probe.tab_layout = (tab_fits && aligned) ? 1 : 0;
-            const size_t sm = smem_bytes(probe, thr, true, env->precision == CL_PRECISION_FP64 ? 8 : 4);
+            // (the general writer's dynbuf only exists with action-dependent observation columns)
+            const size_t sm = smem_bytes(probe, thr, !d.stale, env->precision == CL_PRECISION_FP64 ? 8 : 4);
             if (sm > 200 * 1024) continue;
             const int regs_alloc = ((regs_w + 7) / 8) * 8;
             int bps = 65536 / (regs_alloc * thr);
@@ -1685,21 +1761,7 @@ extern "C" int cl_create(const cl_district_desc* desc, cl_env** out) {
     // opt in to large dynamic shared memory once (both kernels, all instantiations)
     const size_t smem = smem_bytes(d, env->threads + 32, true, env->precision == CL_PRECISION_FP64 ? 8 : 4);
     if (smem > 200 * 1024) { cl_destroy(env); return fail(CL_ERR_UNSUPPORTED, "cl_create: district too wide for the shared-memory staging"); }
-    // the attribute is per function and process-wide: never lower it below what an earlier handle needs
-    static size_t optin_max = 0;
-    if (smem > optin_max) optin_max = smem;
-// (the carve-out hint: prefer shared memory over L1 so that as many blocks as the registers allow are resident - the driver's default
-    // carve-out fits ONE block of a kernel with large dynamic shared memory)
-#define OPTIN(K) (cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)optin_max), cudaFuncSetAttribute(K, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared))
-#define OPTIN4(K, M) OPTIN((K<float, false, M>)); OPTIN((K<float, true, M>)); OPTIN((K<double, false, M>)); OPTIN((K<double, true, M>))
-#define OPTINA(M) OPTIN((advance_kernel<float, false, false, M>)); OPTIN((advance_kernel<float, true, false, M>)); OPTIN((advance_kernel<float, true, true, M>)); \
-    OPTIN((advance_kernel<double, false, false, M>)); OPTIN((advance_kernel<double, true, false, M>)); OPTIN((advance_kernel<double, true, true, M>))
-    OPTINA(512); OPTINA(1024); OPTIN4(reset_kernel, 512); OPTIN4(reset_kernel, 1024);
-    OPTIN((advance_kernel<float, false, false, 512, true>)); OPTIN((advance_kernel<float, true, false, 512, true>));
-    OPTIN((advance_kernel<double, false, false, 512, true>)); OPTIN((advance_kernel<double, true, false, 512, true>));
-#undef OPTINA
-#undef OPTIN4
-#undef OPTIN
+    ensure_smem_optin(std::max<size_t>(smem, 116 * 1024));
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { cl_destroy(env); return fail(CL_ERR_CUDA, std::string("cl_create: ") + cudaGetErrorString(e)); }
     { const int rc = build_obs_table(env); if (rc) { cl_destroy(env); return rc; } }
@@ -1752,7 +1814,11 @@ static void launch_advance(cl_env* env, int t0, int K, const float* actions, flo
                            bool coupled, cudaStream_t st) {
     const bool want_dyn = !env->d.stale && obs != nullptr;
     const int nthreads = env->threads + 32;          // + the helper warp
-    const size_t smem = smem_bytes(env->d, nthreads, want_dyn, (int)sizeof(R));
+    size_t smem = smem_bytes(env->d, nthreads, want_dyn, (int)sizeof(R));
+    // a launch of at most one block per SM must SPREAD over the SMs: when two of its blocks would fit one SM (small blocks, the float
+    // instantiations) the block scheduler may pair them up and leave SMs idle (measured: 17 x 4096 fp32 3.6 -> 5.4 us / step) - ask
+    // for more than half an SM's shared memory so that a block owns its SM
+    if (env->blocks <= env->n_sm && smem < 116 * 1024) smem = 116 * 1024;
     if (env->wide) {
         if constexpr (!DY) {
             Dev dd = env->d;
@@ -1946,6 +2012,7 @@ extern "C" int cl_exchange_create(cl_env* env, int32_t n_ranks, int32_t rank, vo
     if (env->wide) return fail(CL_ERR_UNSUPPORTED, "cl_exchange_create: building-tiled (wide) districts are not building-sharded across GPUs");
     if (env->d.central) return fail(CL_ERR_UNSUPPORTED, "cl_exchange_create: central-agent reward sums are not exchanged; use decentralised rewards");
     if (env->x_buf) return fail(CL_ERR_STATE, "cl_exchange_create: already created");
+    if (env->kpi_unit) return fail(CL_ERR_UNSUPPORTED, "cl_exchange_create: online KPI accumulators need the whole district on one handle");
     // a block spins on its peers inside the step: every block of the launch must be resident (one wave), or blocks waiting for an SM
     // could be the ones a resident block waits for
     if (env->blocks > env->n_sm) return fail(CL_ERR_UNSUPPORTED, "cl_exchange_create: the launch must fit one wave (at most one block per SM); use fewer envs per GPU");
@@ -2115,11 +2182,14 @@ extern "C" int cl_set_transforms(cl_env* env, const cl_obs_transform* obs_transf
 extern "C" int cl_kpi_enable(cl_env* env, int32_t enable) {
     if (!env) return fail(CL_ERR_INVALID, "cl_kpi_enable: null env");
     if (enable && env->dynamics) return fail(CL_ERR_UNSUPPORTED, "cl_kpi_enable: the `_without_storage` baseline does not apply to LSTM-dynamics districts (use evaluate() on a recorded history)");
+    if (enable && env->d.x_n != 0) return fail(CL_ERR_UNSUPPORTED, "cl_kpi_enable: a building-sharded handle sees only its own buildings' baseline");
     if (!enable) {
         CUDA_TRY(cudaDeviceSynchronize());
         if (env->kpi_unit) cudaFree(env->kpi_unit);
         if (env->kpi_env) cudaFree(env->kpi_env);
         env->kpi_unit = env->kpi_env = nullptr;
+        env->kpi_fused = false;
+        env->d.kpi_unit = env->d.kpi_env = nullptr; env->d.kpi_smem = 0;
         return CL_OK;
     }
     if (!env->kpi_unit) {
@@ -2129,12 +2199,32 @@ extern "C" int cl_kpi_enable(cl_env* env, int32_t enable) {
         CUDA_TRY(cudaMemset(env->kpi_unit, 0, nu * sizeof(double)));
         CUDA_TRY(cudaMemset(env->kpi_env, 0, ne * sizeof(double)));
     }
+    // fused into the step kernel when the district is a plain one (whole envs per block) and the accumulators fit its shared memory
+    env->kpi_fused = false;
+    env->d.kpi_smem = 0; env->d.kpi_unit = nullptr; env->d.kpi_env = nullptr;
+    if (!env->wide && std::getenv("CL_B200_KPI_UNFUSED") == nullptr) {
+        Dev t = env->d; t.kpi_smem = 1;
+        const size_t smem = smem_bytes(t, env->threads + 32, true, env->precision == CL_PRECISION_FP64 ? 8 : 4);
+        if (smem <= 200 * 1024) {
+            ensure_smem_optin(smem);
+            CUDA_TRY(cudaGetLastError());
+            env->d.kpi_smem = 1; env->d.kpi_unit = env->kpi_unit; env->d.kpi_env = env->kpi_env;
+            env->kpi_fused = true;
+        }
+    }
+    return CL_OK;
+}
+
+extern "C" int cl_kpi_fused(const cl_env* env, int32_t* fused) {
+    if (!env || !fused) return fail(CL_ERR_INVALID, "cl_kpi_fused: null argument");
+    *fused = env->kpi_fused ? 1 : 0;
     return CL_OK;
 }
 
 extern "C" int cl_kpi_accumulate(cl_env* env, const float* trace, const float* district, cl_stream stream) {
     if (!env || !trace || !district) return fail(CL_ERR_INVALID, "cl_kpi_accumulate: null argument");
     if (!env->kpi_unit) return fail(CL_ERR_STATE, "cl_kpi_accumulate: call cl_kpi_enable first");
+    if (env->kpi_fused) return CL_OK;                // already accumulated inside the step kernel
     { const int rc = refresh_time(env, static_cast<cudaStream_t>(stream)); if (rc) return rc; }
     if (env->t < 1) return fail(CL_ERR_STATE, "cl_kpi_accumulate: no step has been taken since cl_reset");
     int threads = ((std::min(env->d.B, 256) + 31) / 32) * 32;
@@ -2207,7 +2297,8 @@ extern "C" int cl_launch_occupancy(const cl_env* env, int32_t* blocks_per_sm, in
     if (!env) return fail(CL_ERR_INVALID, "cl_launch_occupancy: null env");
     const int nthreads = env->threads + 32;
     const bool f64 = env->precision == CL_PRECISION_FP64;
-    const size_t smem = smem_bytes(env->d, nthreads, false, f64 ? 8 : 4);
+    size_t smem = smem_bytes(env->d, nthreads, false, f64 ? 8 : 4);
+    if (env->blocks <= env->n_sm && smem < 116 * 1024) smem = 116 * 1024;     // launch_advance: a single-wave launch owns its SMs
     const void* fn = nullptr;
     if (env->wide) {
         fn = f64 ? (env->thermal ? (const void*)advance_kernel<double, true, false, 512, true> : (const void*)advance_kernel<double, false, false, 512, true>)

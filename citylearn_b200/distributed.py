@@ -182,3 +182,68 @@ class BuildingShardedEnv:
 
     def close(self):
         self.env.close()
+
+
+# ------------------------------------------------------------------------------------------------------------------------------
+# One process, several devices: `CityLearnEnv(..., devices=[...])`
+# ------------------------------------------------------------------------------------------------------------------------------
+class DeviceShardedEnv:
+    """`num_envs` parallel envs sharded by env index over the CUDA devices of this process: one `CityLearnEnv` per device, no
+    collective (envs are independent).  `step` takes the fleet's actions `[E, A]` (any device / host) or a list of per-device
+    tensors, launches every shard's kernel without synchronising in between, and returns per-device lists (`obs[i]` lives on
+    `devices[i]`) - concatenate with `gather()` when one tensor is wanted."""
+
+    def __init__(self, schema, num_envs: int = 1, devices=None, **kwargs):
+        from .env import CityLearnEnv
+        devices = [torch.device(d) for d in devices]
+        if num_envs < len(devices):
+            raise ValueError('fewer envs than devices')
+        kwargs.pop('device', None)
+        self.devices = devices
+        self.num_envs = int(num_envs)
+        self.spans = [shard_range(self.num_envs, i, len(devices)) for i in range(len(devices))]
+        self.envs = [CityLearnEnv(schema, num_envs=c, device=d, **kwargs) for d, (_, c) in zip(devices, self.spans)]
+        for e, (o, _) in zip(self.envs, self.spans):
+            e.env_offset, e.total_envs = o, self.num_envs
+
+    def __getattr__(self, name):                       # metadata, spaces, names ...: identical on every shard
+        if name.startswith('_') or name in ('envs', 'devices', 'spans'):
+            raise AttributeError(name)
+        return getattr(self.envs[0], name)
+
+    def _split(self, actions):
+        if isinstance(actions, (list, tuple)) and len(actions) == len(self.envs) and all(isinstance(a, torch.Tensor) for a in actions):
+            return list(actions)
+        a = torch.as_tensor(actions)
+        return [a[o:o + c].to(e.device, non_blocking=True) for e, (o, c) in zip(self.envs, self.spans)]
+
+    def reset(self, **kw):
+        outs = [e.reset(**kw) for e in self.envs]
+        return [o for o, _ in outs], {}
+
+    def step(self, actions):
+        outs = [e.step(a) for e, a in zip(self.envs, self._split(actions))]
+        return [o[0] for o in outs], [o[1] for o in outs], outs[0][2], False, {}
+
+    def rollout(self, actions, obs=None, reward=None, district=None):
+        none = [None] * len(self.envs)
+        for e, a, o, r, d in zip(self.envs, actions, obs or none, reward or none, district or none):
+            e.rollout(a, o, r, d)
+        return obs, reward, self.envs[0].terminated
+
+    @staticmethod
+    def gather(parts, device=None) -> torch.Tensor:
+        device = parts[0].device if device is None else torch.device(device)
+        return torch.cat([p.to(device, non_blocking=True) for p in parts], dim=0)
+
+    @property
+    def time_step(self) -> int:
+        return self.envs[0].time_step
+
+    @property
+    def terminated(self) -> bool:
+        return self.envs[0].terminated
+
+    def close(self):
+        for e in self.envs:
+            e.close()

@@ -168,10 +168,20 @@ class CityLearnEnv:
     metadata: Dict[str, Any] = {}
     render_mode = None
 
+    def __new__(cls, *args, devices=None, **kwargs):
+        # `devices=[...]` with more than one entry: the envs are sharded over the devices of THIS process; the object
+        # returned is a `distributed.DeviceShardedEnv` holding one CityLearnEnv per device
+        if cls is CityLearnEnv and devices is not None and len(list(devices)) > 1:
+            from .distributed import DeviceShardedEnv
+            return DeviceShardedEnv(*args, devices=list(devices), **kwargs)
+        return super().__new__(cls)
+
     def __init__(self, schema, num_envs: int = 1, device: Union[str, torch.device, None] = None, precision: str = 'fp64',
                  stale_observations: bool = True, track_episode_rewards: Optional[bool] = None, debug_trace: bool = False,
                  record_history: Optional[bool] = None, history_env: int = 0, observation_transform: Optional[str] = None,
-                 normalized_actions: bool = False, track_kpis: bool = False, **kwargs):
+                 normalized_actions: bool = False, track_kpis: bool = False, auto_reset: bool = False, devices=None, **kwargs):
+        if devices is not None and device is None and len(list(devices)) == 1:
+            device = list(devices)[0]
         self.spec = S.load(schema, **kwargs)
         self.schema = self.spec.schema
         self.num_envs = int(num_envs)
@@ -186,6 +196,12 @@ class CityLearnEnv:
             self.device = torch.device('cuda', torch.cuda.current_device())
         self.precision = precision
         self.stale_observations = bool(stale_observations)
+        # batched episode end: opt-in Gymnasium-VectorEnv "same-step" auto-reset - the step that ends the episode resets
+        # every env (they advance in lock-step) and returns the first observation of the next episode, the last one of the finished
+        # episode in info['final_observation'].  Never at num_envs == 1: the reference leaves reset() to the caller (citylearn.py:995-997)
+        self.auto_reset = bool(auto_reset)
+        if self.auto_reset and self.num_envs == 1:
+            raise ValueError('auto_reset is a batched-env option; with num_envs == 1 the caller resets, like the reference')
         spec = self.spec
         self.central_agent = spec.central_agent
         self.shared_observations = spec.shared_observations
@@ -211,7 +227,7 @@ class CityLearnEnv:
             raise ValueError('history_env out of range')
         # online KPI accumulators for every env: fed from the per-step trace by a small second kernel
         self._track_kpis = bool(track_kpis)
-        debug_trace = debug_trace or self._record or self._track_kpis
+        debug_trace = debug_trace or self._record        # (track_kpis adds the trace only where the accumulators are not fused, _build_native)
         # reward function (citylearn/citylearn.py:2100-2163)
         self.reward_function = self._make_reward_function()
         rid, rparams = self._fused_reward()
@@ -250,8 +266,11 @@ class CityLearnEnv:
                 lo = np.array([v for b in spec.buildings for v in b.action_low], dtype='float32')
                 hi = np.array([v for b in spec.buildings for v in b.action_high], dtype='float32')
                 self._h.set_transforms(transforms, (hi - lo) if self._normalized_actions else None, lo if self._normalized_actions else None)
+            self._kpi_fused = False
             if self._track_kpis:
                 self._h.kpi_enable(True)
+                self._kpi_fused = self._h.kpi_fused()        # accumulated inside the step kernel: no trace, survives rollout()
+                debug_trace = debug_trace or not self._kpi_fused
             self._kpi_valid = True
             E = self.num_envs
             # observations, rewards and the shared observation row live in one allocation [obs E*L | reward E*R | row L] so that the
@@ -444,9 +463,18 @@ class CityLearnEnv:
             o += n
         return out
 
-    def reset(self, seed: int = None, options: Mapping[str, Any] = None):
+    def reset(self, seed: int = None, options: Mapping[str, Any] = None, mask=None):
         """Start the next episode (citylearn/citylearn.py:1829-1886). `options={'episode_start': Tensor[E] int32}` gives every
-        env its own window start (same length) instead of the tracker's."""
+        env its own window start (same length) instead of the tracker's.  `mask` (bool [E]): which envs to reset - the envs of a
+        handle share ONE time step (every env ends its episode on the same step, also with per-env windows), so only the full mask
+        is meaningful; a partial mask raises."""
+        if mask is not None:
+            m = torch.as_tensor(mask).reshape(-1).bool()
+            if m.numel() != self.num_envs:
+                raise ValueError(f'mask must have one entry per env ({self.num_envs})')
+            if not bool(m.all()):
+                raise NotImplementedError('partial reset: the envs of a CityLearnEnv advance in lock-step and terminate together; reset all of them '
+                                          '(mask=None), or hold groups that must restart independently in separate CityLearnEnv objects')
         if seed is not None:
             self.random_seed = seed
         ets = self.episode_time_steps if self.episode_time_steps is not None else self.episode_tracker.simulation_time_steps
@@ -548,7 +576,7 @@ class CityLearnEnv:
             self._obs_current = write_obs
             if not fused:
                 self._python_reward()
-            if self._track_kpis:
+            if self._track_kpis and not self._kpi_fused:
                 self._h.kpi_accumulate(self._trace.data_ptr(), self._district.data_ptr(), stream)
             if self._record:
                 self._hist_dyn[self.time_step].copy_(self._trace[self._history_env])
@@ -559,6 +587,11 @@ class CityLearnEnv:
         terminated = self.terminated
         if terminated and self._track:
             self._finish_episode_rewards()
+        if terminated and self.auto_reset:
+            final = self._obs.clone() if write_obs else None
+            rew = self._reward.clone()
+            self.reset()
+            return self._obs, rew, True, False, {'final_observation': final}
         if ref_shaped:
             rew = self._reward[0].tolist()
             return self._shape_obs(self._obs), rew, terminated, False, self.get_info()
@@ -629,7 +662,7 @@ class CityLearnEnv:
             torch.cuda.current_stream(self.device).synchronize()
         self.time_step += K
         self._hist_valid = False
-        self._kpi_valid = False
+        self._kpi_valid = self._kpi_valid and self._kpi_fused
         self._obs_current = False
         if not shared:
             self._obs.copy_(obs.view(K, E, L)[-1])
@@ -649,7 +682,7 @@ class CityLearnEnv:
                             None if district is None else district.data_ptr(), self._stream())
         self.time_step += K
         self._hist_valid = False          # rollouts do not produce the per-unit trace evaluate() needs
-        self._kpi_valid = False
+        self._kpi_valid = self._kpi_valid and self._kpi_fused       # fused accumulators run inside every launch
         if obs is not None:
             self._obs.copy_(obs[K - 1])
         self._obs_current = obs is not None
@@ -700,7 +733,7 @@ class CityLearnEnv:
         control vs the `_without_storage` baseline, from accumulators kept on the device (`cl_kpi_*`) - no per-step history."""
         from .evaluate import evaluate_batched
         if not self._track_kpis or not self._kpi_valid:
-            raise RuntimeError('evaluate_batched() needs track_kpis=True and an episode advanced with step() (not rollout())')
+            raise RuntimeError('evaluate_batched() needs track_kpis=True (and, for building-tiled districts, an episode advanced with step())')
         E, B = self.num_envs, self.spec.n_buildings
         with torch.cuda.device(self.device):
             unit = torch.empty((E, B, 8), dtype=torch.float64, device=self.device)

@@ -276,6 +276,9 @@ int cl_set_transforms(cl_env* env, const cl_obs_transform* obs_transform, const 
  * Control series = the simulated values; baseline = `_without_storage` (net minus the storage devices' consumption; districts with
  * LSTM dynamics are not supported here).  cl_kpi_accumulate is called after every cl_step with that step's `trace` and `district`
  * outputs; cl_reset zeroes the accumulators.  Layouts (doubles):
+ * Plain districts (whole envs per thread block, no LSTM dynamics) keep the accumulators INSIDE the step kernel: every cl_step /
+ * cl_rollout / cl_advance_device launch updates them (shared memory during the launch, folded into the arrays at its end), no
+ * trace is needed and cl_kpi_accumulate is a no-op (cl_kpi_fused reports 1).  Building-tiled districts use cl_kpi_accumulate.
  *   unit [E][B][CL_NKPI_UNIT]: sum max(net,0), sum net, sum max(emission,0), sum max(cost,0) for control, then for the baseline
  *   env  [E][2][CL_NKPI_ENV] : per series (0 control district net, 1 baseline district net) the running ramping / load-factor /
  *                              peak window state of cl_kpi_env
@@ -289,6 +292,7 @@ enum cl_kpi_env {
 };
 int cl_kpi_enable(cl_env* env, int32_t enable);
 int cl_kpi_accumulate(cl_env* env, const float* trace, const float* district, cl_stream stream);
+int cl_kpi_fused(const cl_env* env, int32_t* fused);
 int cl_kpi_read(cl_env* env, double* unit_dev, double* env_dev, cl_stream stream);
 
 /* Launch geometry chosen at cl_create: CTAs per launch, threads per CTA (incl. the helper warp) and building tiles per env

@@ -80,3 +80,47 @@ def test_advance_device_needs_enable():
     act = torch.zeros((4, env.spec.action_dim), device='cuda')
     with pytest.raises(RuntimeError, match='cl_device_time_enable'):
         env._h.advance_device(1, act.data_ptr(), None, None, None, torch.cuda.current_stream().cuda_stream)
+
+
+def test_auto_reset_and_mask_semantics():
+    """Batched episode end: opt-in same-step auto-reset; a partial reset mask is refused (lock-step envs)."""
+    from citylearn_b200 import CityLearnEnv
+    E, T = 16, 5
+    env = CityLearnEnv(PALL, num_envs=E, episode_time_steps=T, auto_reset=True)
+    ref = CityLearnEnv(PALL, num_envs=E, episode_time_steps=T)
+    act = torch.zeros((E, env.spec.action_dim), device='cuda')
+    for k in range(T - 1):
+        obs, rew, term, _, info = env.step(act)
+        o2, r2, t2, _, _ = ref.step(act)
+        assert term == t2 and torch.equal(rew, r2)
+    assert term and env.time_step == 0 and torch.equal(info['final_observation'], o2)
+    ref.reset()                                                      # the reference-style caller resets itself: same next episode
+    assert torch.equal(obs, ref.observations) and env.episode_tracker.episode == ref.episode_tracker.episode
+    obs, rew, term, _, _ = env.step(act)                             # and the next episode runs
+    assert not term and env.time_step == 1
+    with pytest.raises(NotImplementedError, match='lock-step'):
+        env.reset(mask=torch.arange(E) < 3)
+    env.reset(mask=torch.ones(E, dtype=torch.bool))
+    with pytest.raises(ValueError):
+        CityLearnEnv(PALL, num_envs=1, auto_reset=True)
+
+
+def test_devices_keyword_shards_envs_over_the_devices_of_one_process():
+    from citylearn_b200 import CityLearnEnv
+    from citylearn_b200.distributed import DeviceShardedEnv
+    one = CityLearnEnv(PALL, num_envs=8, devices=['cuda:0'])
+    assert isinstance(one, CityLearnEnv) and one.device == torch.device('cuda', 0)
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 CUDA devices')
+    E = 64
+    fleet = CityLearnEnv(PALL, num_envs=E, devices=['cuda:0', 'cuda:1'])
+    assert isinstance(fleet, DeviceShardedEnv) and [e.num_envs for e in fleet.envs] == [32, 32]
+    ref = CityLearnEnv(PALL, num_envs=E, device='cuda:0')
+    g = torch.Generator().manual_seed(0)
+    for k in range(6):
+        a = torch.rand((E, ref.spec.action_dim), generator=g) * 2 - 1
+        obs, rew, term, _, _ = fleet.step(a)
+        o2, r2, t2, _, _ = ref.step(a.cuda())
+        assert obs[1].device == torch.device('cuda', 1)
+        assert torch.equal(DeviceShardedEnv.gather(rew, 'cuda:0'), r2) and torch.equal(DeviceShardedEnv.gather(obs, 'cuda:0'), o2)
+    assert fleet.time_step == 6 and fleet.observation_names == ref.observation_names

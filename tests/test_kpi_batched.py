@@ -95,3 +95,42 @@ def test_device_accumulators_match_history_evaluate_for_every_env():
         assert got['district'][name][2] == pytest.approx(table[name], rel=2e-6, abs=1e-9), name
     with pytest.raises(RuntimeError):
         CityLearnEnv(spec, num_envs=2).evaluate_batched()
+
+
+@pytest.mark.gpu
+def test_fused_accumulators_survive_rollouts_and_equal_the_trace_fed_kernel(monkeypatch):
+    """The accumulators live inside advance_kernel: a mix of step(), rollout() and CUDA-graph replays gives the KPIs of the
+    trace-fed second kernel (CL_B200_KPI_UNFUSED, the round-1 path) stepping one by one - and no trace buffer is allocated."""
+    import torch
+    from citylearn_b200 import CityLearnEnv
+    from citylearn_b200.closed_loop import ClosedLoop
+    E, K = 40, 96
+    spec = S.load('citylearn_challenge_2022_phase_1')
+    g = torch.Generator(device='cuda').manual_seed(5)
+    acts = torch.rand((K, E, spec.action_dim), device='cuda', generator=g) * 2 - 1
+    fused = CityLearnEnv(spec, num_envs=E, track_kpis=True)
+    assert fused._kpi_fused and fused.trace is None
+    fused.reset()
+    for k in range(10):
+        fused.step(acts[k])
+    fused.rollout(acts[10:50].contiguous(), None, torch.empty((40, E, spec.n_buildings), device='cuda'), None)     # one 40-step launch
+    idx = torch.zeros(1, dtype=torch.long, device='cuda')          # step counter on the device: the captured policy reads acts[idx]
+
+    def pol(obs):
+        a = acts.index_select(0, idx.clamp(max=K - 1))[0]
+        idx.add_(1)
+        return a
+    loop = ClosedLoop(fused, pol, steps_per_replay=8)
+    idx.fill_(50)
+    loop.run(K - 50)                                               # 5 graph replays of 8 steps + 6 single-step replays
+    got = fused.evaluate_batched()
+    monkeypatch.setenv('CL_B200_KPI_UNFUSED', '1')
+    ref = CityLearnEnv(spec, num_envs=E, track_kpis=True)
+    assert not ref._kpi_fused and ref.trace is not None
+    ref.reset()
+    for k in range(K):
+        ref.step(acts[k])
+    exp = ref.evaluate_batched()
+    for level in ('district', 'building'):
+        for name, v in exp[level].items():
+            np.testing.assert_allclose(got[level][name], v, rtol=1e-12, atol=0, equal_nan=True, err_msg=f'{level} {name}')
