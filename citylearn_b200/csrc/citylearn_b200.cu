@@ -185,9 +185,21 @@ __device__ __forceinline__ void store_state(const Dev& d, int u, const UnitState
     if (THERMAL) { d.st[ST_SOC_CS * U + u] = (float)s.soc_cs; d.st[ST_SOC_HS * U + u] = (float)s.soc_hs; d.st[ST_SOC_DS * U + u] = (float)s.soc_ds; }
 }
 
+// a time row: TMA-staged in shared memory (lock-step episode windows; `s` is its shared-window address - explicit ld.shared instead
+// of a generic load, which is tracked like a global one) or straight from the table in global memory (`s` == 0)
+struct RowRef {
+    const float* g; uint32_t s;
+    __device__ __forceinline__ float operator[](int col) const {
+        float v;
+        if (s != 0u) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(s + 4u * (uint32_t)col));   // volatile: stays behind the row's mbarrier wait
+        else v = __ldg(g + col);
+        return v;
+    }
+};
+
 // exogenous inputs of a unit at time step t; `row` points at the time row (shared or global memory)
 template <typename R, bool THERMAL>
-__device__ __forceinline__ void load_inputs(const Dev& d, const UnitCtx<R>& c, const float* row, int b, int t, UnitInputs<R>& in,
+__device__ __forceinline__ void load_inputs(const Dev& d, const UnitCtx<R>& c, const RowRef row, int b, int t, UnitInputs<R>& in,
                                             bool solar_from_block = false) {
     in.nsl = (R)row[c.c_nsl];
     // building.py:2554, energy_model.py:488; with lock-step rows the helper warp computes it once per building
@@ -538,7 +550,7 @@ static size_t smem_bytes(const Dev& d, int nt, bool with_dyn, int rsize) {
 
 template <typename R, bool THERMAL>
 __device__ __forceinline__ void reward_inputs(const Dev& d, const UnitCtx<R>& c, const UnitState<R>& s, const UnitResult<R>& o,
-                                              const float* row, float t_in, RewardIn& ri) {
+                                              const RowRef row, float t_in, RewardIn& ri) {
     const BuildingParams<R>& p = c.p;
     ri.net = (float)o.net; ri.district_net = 0.f;
     ri.soc_b = (float)s.soc_b; ri.soc_cs = (float)s.soc_cs; ri.soc_hs = (float)s.soc_hs; ri.soc_ds = (float)s.soc_ds;
@@ -563,7 +575,8 @@ __device__ __forceinline__ void reward_inputs(const Dev& d, const UnitCtx<R>& c,
 // ------------------------------------------------------------------------------------------------------------------
 template <typename R>
 __device__ __forceinline__ float lstm_update(const Dev& d, const UnitCtx<R>& c, const float* W, int u, int t, int row0 /* table row of step 0 */,
-                                             float obs_cool_dem, float t_in_dataset, const float* pre /* this building's projection ring or nullptr */) {
+                                             float obs_cool_dem, float t_in_dataset, const float* pre /* this building's projection ring or nullptr */,
+                                             int g /* lane of the unit's quad */, unsigned quad_mask, int quad_base) {
     const int U = d.U;
     const int L = c.dyn_lookback, ring = L + 1;
     const bool smem_w = d.lstm_smem != 0;                 // W then points into shared memory
@@ -571,15 +584,19 @@ __device__ __forceinline__ float lstm_update(const Dev& d, const UnitCtx<R>& c, 
     float* lst = d.lst;
     float* win_c = lst + (size_t)(4 * kLstmH) * U + u;                     // [ring][U]
     float* win_t = lst + (size_t)(4 * kLstmH + kLstmMaxLookback + 1) * U + u;
-    // _update_dynamics_input: append the normalised observation of step t (float32 arithmetic)
+    // _update_dynamics_input: append the normalised observation of step t (float32 arithmetic); the four lanes of the unit write the
+    // same values
     if (c.dyn_slot_cdem >= 0) win_c[(size_t)(t % ring) * U] = (obs_cool_dem - c.cdem_min) / c.cdem_range;
     win_t[(size_t)(t % ring) * U] = (t_in_dataset - c.tin_min) / c.tin_range;
     if (t < L) return t_in_dataset;                                         // window not full yet (building.py:2996-2998)
-    float h0[kLstmH], h1[kLstmH], c0[kLstmH], c1[kLstmH];
+    __syncwarp(quad_mask);                                                  // the quad's window writes are visible to its four lanes
+    // every lane keeps the full outputs h of both layers and the cell states of ITS hidden units j = 4 i + g
+    float h0[kLstmH], h1[kLstmH], c0[kLstmOwn], c1[kLstmOwn];
 #pragma unroll
-    for (int j = 0; j < kLstmH; ++j) {
-        h0[j] = lst[(size_t)j * U + u]; h1[j] = lst[(size_t)(kLstmH + j) * U + u];
-        c0[j] = lst[(size_t)(2 * kLstmH + j) * U + u]; c1[j] = lst[(size_t)(3 * kLstmH + j) * U + u];
+    for (int j = 0; j < kLstmH; ++j) { h0[j] = lst[(size_t)j * U + u]; h1[j] = lst[(size_t)(kLstmH + j) * U + u]; }
+#pragma unroll
+    for (int i = 0; i < kLstmOwn; ++i) {
+        c0[i] = lst[(size_t)(2 * kLstmH + 4 * i + g) * U + u]; c1[i] = lst[(size_t)(3 * kLstmH + 4 * i + g) * U + u];
     }
     if (pre != nullptr) {
         // every env of the block sits on the same time rows: the exogenous part of W_ih x is shared (helper warp), only the
@@ -590,8 +607,9 @@ __device__ __forceinline__ float lstm_update(const Dev& d, const UnitCtx<R>& c, 
             const int tau = t - (L - 1) + sidx;
             const float xc = c.dyn_slot_cdem >= 0 ? win_c[(size_t)(tau % ring) * U] : 0.f;
             const float xt = win_t[(size_t)((tau - 1) % ring) * U];
-            lstm_cell_pre(ws, ps0 + 4u * 64u * (uint32_t)(tau % kLstmPreRing), c.dyn_slot_cdem, c.dyn_slot_tin, xc, xt, h0, c0);
-            lstm_cell<true>(W, ws + 4u * kLstmLayerStride, h0, h1, c1);
+            lstm_cell_q<true, true>(W, ws, g, quad_mask, quad_base, nullptr, ps0 + 4u * 64u * (uint32_t)(tau % kLstmPreRing), c.dyn_slot_cdem, c.dyn_slot_tin,
+                                    xc, xt, h0, c0);
+            lstm_cell_q<true, false>(W, ws + 4u * kLstmLayerStride, g, quad_mask, quad_base, h0, 0u, -1, 0, 0.f, 0.f, h1, c1);
         }
     } else
 #pragma unroll 1
@@ -606,22 +624,29 @@ __device__ __forceinline__ float lstm_update(const Dev& d, const UnitCtx<R>& c, 
 #pragma unroll
         for (int i = 0; i < kLstmIn; ++i) { if (i == c.dyn_slot_cdem) x[i] = xc; if (i == c.dyn_slot_tin) x[i] = xt; }
         if (smem_w) {
-            lstm_cell<true>(W, ws, x, h0, c0);
-            lstm_cell<true>(W, ws + 4u * kLstmLayerStride, h0, h1, c1);
+            lstm_cell_q<true, false>(W, ws, g, quad_mask, quad_base, x, 0u, -1, 0, 0.f, 0.f, h0, c0);
+            lstm_cell_q<true, false>(W, ws + 4u * kLstmLayerStride, g, quad_mask, quad_base, h0, 0u, -1, 0, 0.f, 0.f, h1, c1);
         } else {
-            lstm_cell<false>(W, 0u, x, h0, c0);
-            lstm_cell<false>(W + kLstmLayerStride, 0u, h0, h1, c1);
+            lstm_cell_q<false, false>(W, 0u, g, quad_mask, quad_base, x, 0u, -1, 0, 0.f, 0.f, h0, c0);
+            lstm_cell_q<false, false>(W + kLstmLayerStride, 0u, g, quad_mask, quad_base, h0, 0u, -1, 0, 0.f, 0.f, h1, c1);
         }
     }
     const float* wl = W + 2 * kLstmLayerStride;
     float y = wl[16];
 #pragma unroll
     for (int j = 0; j < kLstmH; ++j) y = fmaf(wl[j], h1[j], y);
+    // lane g stores the outputs and cell states of its hidden units
 #pragma unroll
-    for (int j = 0; j < kLstmH; ++j) {
-        lst[(size_t)j * U + u] = h0[j]; lst[(size_t)(kLstmH + j) * U + u] = h1[j];
-        lst[(size_t)(2 * kLstmH + j) * U + u] = c0[j]; lst[(size_t)(3 * kLstmH + j) * U + u] = c1[j];
+    for (int i = 0; i < kLstmOwn; ++i) {
+        const int j = 4 * i + g;
+        // (h0 / h1 are indexed dynamically only through this unrolled select: keeps them in registers)
+        float v0 = 0.f, v1 = 0.f;
+#pragma unroll
+        for (int gg = 0; gg < kLstmLanes; ++gg) { if (gg == g) { v0 = h0[4 * i + gg]; v1 = h1[4 * i + gg]; } }
+        lst[(size_t)j * U + u] = v0; lst[(size_t)(kLstmH + j) * U + u] = v1;
+        lst[(size_t)(2 * kLstmH + j) * U + u] = c0[i]; lst[(size_t)(3 * kLstmH + j) * U + u] = c1[i];
     }
+    __syncwarp(quad_mask);
     win_t[(size_t)(t % ring) * U] = y;                                       // the prediction replaces the slot (building.py:3027-3028)
     return y * c.tin_range + c.tin_min;                                      // de-normalised (building.py:3031-3037)
 }
@@ -645,8 +670,17 @@ __device__ __forceinline__ void kpi_push(double* a, double x);
 // of step t.  `red`, `dsum` and the per-building buffers are double-buffered by step parity, so one barrier per step suffices
 // (two when a reward needs the district sum, more for central-agent sums).
 // ------------------------------------------------------------------------------------------------------------------
-template <typename R, bool THERMAL, bool DYNAMICS, int MAXT, bool WIDE = false>
-__global__ void __launch_bounds__(MAXT) advance_kernel(Dev d, int t0, int K, const float* __restrict__ actions, float* __restrict__ obs,
+// LSTM districts: block size cap / resident blocks per SM the dynamics instantiation is compiled for (A/B-tested on B200; the LSTM
+// loops need ~80 registers, the fp64 thermal physics around them spills either way)
+#ifndef CL_DYN_MAXT
+#define CL_DYN_MAXT 512
+#endif
+#ifndef CL_DYN_MINBLOCKS
+#define CL_DYN_MINBLOCKS 1
+#endif
+constexpr int kDynMaxT = CL_DYN_MAXT;
+template <typename R, bool THERMAL, bool DYNAMICS, int MAXT, bool WIDE = false, bool KPI = false>
+__global__ void __launch_bounds__(MAXT, (DYNAMICS && MAXT == CL_DYN_MAXT) ? CL_DYN_MINBLOCKS : 1) advance_kernel(Dev d, int t0, int K, const float* __restrict__ actions, float* __restrict__ obs,
                                                         float* __restrict__ reward, float* __restrict__ district, float* __restrict__ trace) {
     extern __shared__ __align__(16) float smf[];
     if (t0 < 0) {
@@ -680,18 +714,23 @@ __global__ void __launch_bounds__(MAXT) advance_kernel(Dev d, int t0, int K, con
     float* s_dynbuf = smf + lo.dynbuf;
     float* s_wpart = smf + lo.wpart;
     double* s_rpart = reinterpret_cast<double*>(smf + lo.rpart);
-    const bool kpi = !WIDE && !DYNAMICS && d.kpi_smem && d.kpi_unit != nullptr;
+    constexpr bool kpi = KPI && !WIDE && !DYNAMICS;     // a separate instantiation: the plain step kernel carries none of this code
     double* s_kacc = reinterpret_cast<double*>(smf + lo.kpi_acc);      // [CL_NKPI_UNIT][nt]
     double* s_knws = reinterpret_cast<double*>(smf + lo.kpi_nws);      // [2][nt]
     double* s_kenv = reinterpret_cast<double*>(smf + lo.kpi_env);      // [epb][2][CL_NKPI_ENV]
     const int e0 = (WIDE ? (int)blockIdx.x / NT : (int)blockIdx.x) * epb;
     const int n_env = min(epb, d.E - e0);
     const int n_units = n_env * nb;
-    const bool active = tid < n_units;
+    // LSTM districts: a unit is served by a QUAD of adjacent lanes (kLstmLanes = 4) - the four run the unit's physics redundantly
+    // (same loads, same values, same stores) and share its LSTM: lane lg owns 4 of the 16 hidden units (unit_physics.cuh)
+    const int vt = DYNAMICS ? (tid >> 2) : tid;             // unit slot of this thread
+    const int lg = DYNAMICS ? (tid & 3) : 0;
+    const unsigned quad_mask = DYNAMICS ? (0xFu << (lane & 28)) : 0xffffffffu;
+    const bool active = vt < n_units && !is_helper;
     // thread -> unit: env-major (building fastest: coalesced state / action / reward slices) except for LSTM districts, where
     // building-major keeps the lanes of a warp on ONE building so that its LSTM weights are broadcast loads
-    const int bl = DYNAMICS ? tid / n_env : tid % nb;       // building inside the tile
-    const int e_l = DYNAMICS ? tid - bl * n_env : tid / nb;
+    const int bl = DYNAMICS ? vt / n_env : vt % nb;         // building inside the tile
+    const int e_l = DYNAMICS ? vt - bl * n_env : vt / nb;
     const int b = b0 + bl;
     const int ul = e_l * nb + bl;                  // unit slot inside the block's shared-memory arrays (always env-major)
     const int e = e0 + e_l, u = e * B + b;
@@ -797,7 +836,7 @@ __global__ void __launch_bounds__(MAXT) advance_kernel(Dev d, int t0, int K, con
         const int nin = __ldg(d.ip + CL_IP_DYN_N_INPUTS * B + bb);
         const float* xin = rowp + __ldg(d.ip + CL_IP_DYN_C_INPUTS * B + bb);
         float acc = Wb[64 * 32 + r];
-        for (int i = 0; i < nin; ++i) acc = fmaf(Wb[r * 16 + i], xin[i], acc);
+        for (int i = 0; i < nin; ++i) acc = fmaf(Wb[lstm_widx(r, i)], xin[i], acc);
         s_pre[((size_t)bb * kLstmPreRing + (tau % kLstmPreRing)) * 64 + r] = acc;
     };
     if (use_pre) {
@@ -838,15 +877,15 @@ __global__ void __launch_bounds__(MAXT) advance_kernel(Dev d, int t0, int K, con
         const int pb = k & 1;
         CL_STAMP(0);
         const int slot_t = k % 3, slot_n = (k + 1) % 3;
-        const float* row;
+        RowRef row;
         const float* row_next = nullptr;
         if (uniform) {
             mbar_wait(s_bar + slot_t, (uint32_t)((k / 3) & 1));
             mbar_wait(s_bar + slot_n, (uint32_t)(((k + 1) / 3) & 1));
-            row = s_rows + slot_t * Wp;
+            row.g = s_rows + slot_t * Wp; row.s = smem_u32(row.g);
             row_next = s_rows + slot_n * Wp;
         } else {
-            row = d.table + (size_t)(start_e + t) * Wp;
+            row.g = d.table + (size_t)(start_e + t) * Wp; row.s = 0u;
         }
         CL_STAMP(1);
         float* red = smf + lo.red + pb * 3 * nt;
@@ -954,7 +993,8 @@ __global__ void __launch_bounds__(MAXT) advance_kernel(Dev d, int t0, int K, con
             float t_in = row[c.c_tin];
             if (DYNAMICS && (c.p.flags & CL_F_DYNAMICS)) {
                 const float cd = (float)(o.e_from_cool + fabs(rmin(o.eb_cs, (R)0)));
-                t_in = lstm_update<R>(d, c, lstm_w, u, t, start_e, cd, t_in, use_pre ? s_pre + (size_t)b * kLstmPreRing * 64 : nullptr);
+                t_in = lstm_update<R>(d, c, lstm_w, u, t, start_e, cd, t_in, use_pre ? s_pre + (size_t)b * kLstmPreRing * 64 : nullptr,
+                                      lg, quad_mask, lane & 28);
             }
             red[ul] = (float)o.net;
             red[nt + ul] = (float)o.cost;
@@ -1286,7 +1326,7 @@ __global__ void __launch_bounds__(MAXT) reset_kernel(Dev d, float* __restrict__ 
             for (int j = 0; j < kLstmStateFloats; ++j) d.lst[(size_t)j * d.U + u] = 0.f;   // dynamics.py:112-127
         }
         if (obs != nullptr) {
-            const float* row = d.table + (size_t)__ldg(d.start + e) * d.Wp;
+            const RowRef row = {d.table + (size_t)__ldg(d.start + e) * d.Wp, 0u};
             UnitInputs<R> in;
             load_inputs<R, THERMAL>(d, c, row, b, 0, in);
             UnitResult<R> o;
@@ -1400,7 +1440,11 @@ static void ensure_smem_optin(size_t smem) {
 #define OPTIN4(K, M) OPTIN((K<float, false, M>)); OPTIN((K<float, true, M>)); OPTIN((K<double, false, M>)); OPTIN((K<double, true, M>))
 #define OPTINA(M) OPTIN((advance_kernel<float, false, false, M>)); OPTIN((advance_kernel<float, true, false, M>)); OPTIN((advance_kernel<float, true, true, M>)); \
     OPTIN((advance_kernel<double, false, false, M>)); OPTIN((advance_kernel<double, true, false, M>)); OPTIN((advance_kernel<double, true, true, M>))
-    OPTINA(512); OPTINA(1024); OPTIN4(reset_kernel, 512); OPTIN4(reset_kernel, 1024);
+#define OPTINK(M) OPTIN((advance_kernel<float, false, false, M, false, true>)); OPTIN((advance_kernel<float, true, false, M, false, true>)); \
+    OPTIN((advance_kernel<double, false, false, M, false, true>)); OPTIN((advance_kernel<double, true, false, M, false, true>))
+    OPTINK(512); OPTINK(1024);
+#undef OPTINK
+    OPTINA(512); OPTINA(1024); OPTIN((advance_kernel<float, true, true, kDynMaxT>)); OPTIN((advance_kernel<double, true, true, kDynMaxT>)); OPTIN4(reset_kernel, 512); OPTIN4(reset_kernel, 1024);
     OPTIN((advance_kernel<float, false, false, 512, true>)); OPTIN((advance_kernel<float, true, false, 512, true>));
     OPTIN((advance_kernel<double, false, false, 512, true>)); OPTIN((advance_kernel<double, true, false, 512, true>));
 #undef OPTINA
@@ -1515,11 +1559,12 @@ extern "C" int cl_create(const cl_district_desc* desc, cl_env** out) {
             for (int q = 0; q < 4; ++q) {
                 for (int j = 0; j < H; ++j) {
                     const int rs = q * H + j, r = q * kLstmH + j;      // gate-major rows (i, f, g, o)
-                    for (int i = 0; i < nin; ++i) o[r * 16 + i] = wih0[rs * nin + i];
-                    for (int i = 0; i < H; ++i) o[64 * 16 + r * 16 + i] = whh0[rs * H + i];
+                    // (matrices in the quad-interleaved layout of unit_physics.cuh: lstm_widx)
+                    for (int i = 0; i < nin; ++i) o[lstm_widx(r, i)] = wih0[rs * nin + i];
+                    for (int i = 0; i < H; ++i) o[64 * 16 + lstm_widx(r, i)] = whh0[rs * H + i];
                     o[64 * 32 + r] = bih0[rs] + bhh0[rs];
-                    for (int i = 0; i < H; ++i) o[kLstmLayerStride + r * 16 + i] = wih1[rs * H + i];
-                    for (int i = 0; i < H; ++i) o[kLstmLayerStride + 64 * 16 + r * 16 + i] = whh1[rs * H + i];
+                    for (int i = 0; i < H; ++i) o[kLstmLayerStride + lstm_widx(r, i)] = wih1[rs * H + i];
+                    for (int i = 0; i < H; ++i) o[kLstmLayerStride + 64 * 16 + lstm_widx(r, i)] = whh1[rs * H + i];
                     o[kLstmLayerStride + 64 * 32 + r] = bih1[rs] + bhh1[rs];
                 }
             }
@@ -1625,22 +1670,24 @@ extern "C" int cl_create(const cl_district_desc* desc, cl_env** out) {
     {
         cudaFuncAttributes fa;
         const void* fn = env->precision == CL_PRECISION_FP64
-            ? (any_dyn ? (const void*)advance_kernel<double, true, true, 512> : (any_thermal ? (const void*)advance_kernel<double, true, false, 512> : (const void*)advance_kernel<double, false, false, 512>))
-            : (any_dyn ? (const void*)advance_kernel<float, true, true, 512> : (any_thermal ? (const void*)advance_kernel<float, true, false, 512> : (const void*)advance_kernel<float, false, false, 512>));
+            ? (any_dyn ? (const void*)advance_kernel<double, true, true, kDynMaxT> : (any_thermal ? (const void*)advance_kernel<double, true, false, 512> : (const void*)advance_kernel<double, false, false, 512>))
+            : (any_dyn ? (const void*)advance_kernel<float, true, true, kDynMaxT> : (any_thermal ? (const void*)advance_kernel<float, true, false, 512> : (const void*)advance_kernel<float, false, false, 512>));
         if (cudaFuncGetAttributes(&fa, fn) == cudaSuccess && fa.numRegs > 0) regs = fa.numRegs;
         cudaGetLastError();
     }
+    // threads per env: one per building, times the lanes that share a unit's LSTM in dynamics districts (unit_physics.cuh)
+    const int BT = B * (any_dyn ? kLstmLanes : 1);
     int target = 0;
     if (const char* ev = std::getenv("CL_B200_BLOCK_THREADS")) { const int v = std::atoi(ev); if (v >= 32 && v <= 992) target = v; }
     if (target == 0) {
         const int cand[] = {96, 128, 224, 352, 480};
         double best = 1e30;
         for (int ci = 0; ci < 5; ++ci) {
-            int epb_c = cand[ci] / B;
+            int epb_c = cand[ci] / BT;
             if (epb_c < 1) epb_c = 1;
             if (epb_c > d.E) epb_c = d.E;
-            const int thr = ((epb_c * B + 31) / 32) * 32 + 32;
-            if (thr > 512 && ci > 0) continue;
+            const int thr = ((epb_c * BT + 31) / 32) * 32 + 32;
+            if (thr > (any_dyn ? kDynMaxT : 512) && ci > 0) continue;
             const int regs_alloc = ((regs + 7) / 8) * 8;
             int bps = 65536 / (regs_alloc * thr);
             if (bps > 2048 / thr) bps = 2048 / thr;
@@ -1663,14 +1710,14 @@ extern "C" int cl_create(const cl_district_desc* desc, cl_env** out) {
             if (blocks_t > 2L * n_sm && blocks_big >= n_sm) target = 960;
         }
     }
-    int epb = target / B;
+    int epb = target / BT;
     if (epb < 1) epb = 1;
     if (epb > d.E) epb = d.E;
     d.envs_per_block = epb;
     d.tiles = 1; d.tile_b = B; d.Lt = d.L; d.tile_k = nullptr;
     const bool tab_fits = obs_table_fits(d);
     d.tab_layout = tab_fits ? 1 : 0;
-    env->threads = ((epb * B + 31) / 32) * 32;
+    env->threads = ((epb * BT + 31) / 32) * 32;
     env->blocks = (d.E + epb - 1) / epb;
     // observations with action-dependent columns: per-env row images (2 x envs_per_block x L floats of shared memory) when they fit
     // and are large enough to host the general writer's dynbuf, which aliases them (smem_layout)
@@ -1759,9 +1806,12 @@ extern "C" int cl_create(const cl_district_desc* desc, cl_env** out) {
     }
     if (!env->wide && B > 992) { cl_destroy(env); return fail(CL_ERR_UNSUPPORTED, "cl_create: districts wider than 992 buildings with LSTM dynamics are not supported"); }
     // opt in to large dynamic shared memory once (both kernels, all instantiations)
-    const size_t smem = smem_bytes(d, env->threads + 32, true, env->precision == CL_PRECISION_FP64 ? 8 : 4);
+    const size_t smem = smem_bytes(d, env->threads + 32, !d.stale, env->precision == CL_PRECISION_FP64 ? 8 : 4);   // (dynbuf: only with action-dependent observation columns)
     if (smem > 200 * 1024) { cl_destroy(env); return fail(CL_ERR_UNSUPPORTED, "cl_create: district too wide for the shared-memory staging"); }
-    ensure_smem_optin(std::max<size_t>(smem, 116 * 1024));
+    // (the reset kernel stages every unit's t = 0 values through the general writer's dynbuf)
+    const size_t smem_reset = smem_bytes(d, env->threads, true, env->precision == CL_PRECISION_FP64 ? 8 : 4);
+    if (smem_reset > 227 * 1024) { cl_destroy(env); return fail(CL_ERR_UNSUPPORTED, "cl_create: district too wide for the shared-memory staging"); }
+    ensure_smem_optin(std::max<size_t>(std::max(smem, smem_reset), 116 * 1024));
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { cl_destroy(env); return fail(CL_ERR_CUDA, std::string("cl_create: ") + cudaGetErrorString(e)); }
     { const int rc = build_obs_table(env); if (rc) { cl_destroy(env); return rc; } }
@@ -1838,7 +1888,14 @@ static void launch_advance(cl_env* env, int t0, int K, const float* actions, flo
         }
         return;
     }
-    if (nthreads <= 512) advance_kernel<R, TH, DY, 512><<<env->blocks, nthreads, smem, st>>>(env->d, t0, K, actions, obs, reward, district, trace);
+    if constexpr (!DY) {
+        if (env->kpi_fused) {                         // online KPI accumulators inside the step (cl_kpi_enable)
+            if (nthreads <= 512) advance_kernel<R, TH, false, 512, false, true><<<env->blocks, nthreads, smem, st>>>(env->d, t0, K, actions, obs, reward, district, trace);
+            else advance_kernel<R, TH, false, 1024, false, true><<<env->blocks, nthreads, smem, st>>>(env->d, t0, K, actions, obs, reward, district, trace);
+            return;
+        }
+    }
+    if (nthreads <= (DY ? kDynMaxT : 512)) advance_kernel<R, TH, DY, (DY ? kDynMaxT : 512)><<<env->blocks, nthreads, smem, st>>>(env->d, t0, K, actions, obs, reward, district, trace);
     else advance_kernel<R, TH, DY, 1024><<<env->blocks, nthreads, smem, st>>>(env->d, t0, K, actions, obs, reward, district, trace);
 }
 static void dispatch_one(cl_env* env, int t0, int K, const float* actions, float* obs, float* reward, float* district, float* trace,
@@ -2303,9 +2360,9 @@ extern "C" int cl_launch_occupancy(const cl_env* env, int32_t* blocks_per_sm, in
     if (env->wide) {
         fn = f64 ? (env->thermal ? (const void*)advance_kernel<double, true, false, 512, true> : (const void*)advance_kernel<double, false, false, 512, true>)
                  : (env->thermal ? (const void*)advance_kernel<float, true, false, 512, true> : (const void*)advance_kernel<float, false, false, 512, true>);
-    } else if (nthreads <= 512) {
-        fn = f64 ? (env->dynamics ? (const void*)advance_kernel<double, true, true, 512> : (env->thermal ? (const void*)advance_kernel<double, true, false, 512> : (const void*)advance_kernel<double, false, false, 512>))
-                 : (env->dynamics ? (const void*)advance_kernel<float, true, true, 512> : (env->thermal ? (const void*)advance_kernel<float, true, false, 512> : (const void*)advance_kernel<float, false, false, 512>));
+    } else if (nthreads <= (env->dynamics ? kDynMaxT : 512)) {
+        fn = f64 ? (env->dynamics ? (const void*)advance_kernel<double, true, true, kDynMaxT> : (env->thermal ? (const void*)advance_kernel<double, true, false, 512> : (const void*)advance_kernel<double, false, false, 512>))
+                 : (env->dynamics ? (const void*)advance_kernel<float, true, true, kDynMaxT> : (env->thermal ? (const void*)advance_kernel<float, true, false, 512> : (const void*)advance_kernel<float, false, false, 512>));
     } else {
         fn = f64 ? (env->dynamics ? (const void*)advance_kernel<double, true, true, 1024> : (env->thermal ? (const void*)advance_kernel<double, true, false, 1024> : (const void*)advance_kernel<double, false, false, 1024>))
                  : (env->dynamics ? (const void*)advance_kernel<float, true, true, 1024> : (env->thermal ? (const void*)advance_kernel<float, true, false, 1024> : (const void*)advance_kernel<float, false, false, 1024>));
