@@ -575,8 +575,7 @@ __device__ __forceinline__ void reward_inputs(const Dev& d, const UnitCtx<R>& c,
 // ------------------------------------------------------------------------------------------------------------------
 template <typename R>
 __device__ __forceinline__ float lstm_update(const Dev& d, const UnitCtx<R>& c, const float* W, int u, int t, int row0 /* table row of step 0 */,
-                                             float obs_cool_dem, float t_in_dataset, const float* pre /* this building's projection ring or nullptr */,
-                                             int g /* lane of the unit's quad */, unsigned quad_mask, int quad_base) {
+                                             float obs_cool_dem, float t_in_dataset, const float* pre /* this building's projection ring or nullptr */) {
     const int U = d.U;
     const int L = c.dyn_lookback, ring = L + 1;
     const bool smem_w = d.lstm_smem != 0;                 // W then points into shared memory
@@ -584,19 +583,15 @@ __device__ __forceinline__ float lstm_update(const Dev& d, const UnitCtx<R>& c, 
     float* lst = d.lst;
     float* win_c = lst + (size_t)(4 * kLstmH) * U + u;                     // [ring][U]
     float* win_t = lst + (size_t)(4 * kLstmH + kLstmMaxLookback + 1) * U + u;
-    // _update_dynamics_input: append the normalised observation of step t (float32 arithmetic); the four lanes of the unit write the
-    // same values
+    // _update_dynamics_input: append the normalised observation of step t (float32 arithmetic)
     if (c.dyn_slot_cdem >= 0) win_c[(size_t)(t % ring) * U] = (obs_cool_dem - c.cdem_min) / c.cdem_range;
     win_t[(size_t)(t % ring) * U] = (t_in_dataset - c.tin_min) / c.tin_range;
     if (t < L) return t_in_dataset;                                         // window not full yet (building.py:2996-2998)
-    __syncwarp(quad_mask);                                                  // the quad's window writes are visible to its four lanes
-    // every lane keeps the full outputs h of both layers and the cell states of ITS hidden units j = 4 i + g
-    float h0[kLstmH], h1[kLstmH], c0[kLstmOwn], c1[kLstmOwn];
+    float h0[kLstmH], h1[kLstmH], c0[kLstmH], c1[kLstmH];
 #pragma unroll
-    for (int j = 0; j < kLstmH; ++j) { h0[j] = lst[(size_t)j * U + u]; h1[j] = lst[(size_t)(kLstmH + j) * U + u]; }
-#pragma unroll
-    for (int i = 0; i < kLstmOwn; ++i) {
-        c0[i] = lst[(size_t)(2 * kLstmH + 4 * i + g) * U + u]; c1[i] = lst[(size_t)(3 * kLstmH + 4 * i + g) * U + u];
+    for (int j = 0; j < kLstmH; ++j) {
+        h0[j] = lst[(size_t)j * U + u]; h1[j] = lst[(size_t)(kLstmH + j) * U + u];
+        c0[j] = lst[(size_t)(2 * kLstmH + j) * U + u]; c1[j] = lst[(size_t)(3 * kLstmH + j) * U + u];
     }
     if (pre != nullptr) {
         // every env of the block sits on the same time rows: the exogenous part of W_ih x is shared (helper warp), only the
@@ -607,9 +602,8 @@ __device__ __forceinline__ float lstm_update(const Dev& d, const UnitCtx<R>& c, 
             const int tau = t - (L - 1) + sidx;
             const float xc = c.dyn_slot_cdem >= 0 ? win_c[(size_t)(tau % ring) * U] : 0.f;
             const float xt = win_t[(size_t)((tau - 1) % ring) * U];
-            lstm_cell_q<true, true>(W, ws, g, quad_mask, quad_base, nullptr, ps0 + 4u * 64u * (uint32_t)(tau % kLstmPreRing), c.dyn_slot_cdem, c.dyn_slot_tin,
-                                    xc, xt, h0, c0);
-            lstm_cell_q<true, false>(W, ws + 4u * kLstmLayerStride, g, quad_mask, quad_base, h0, 0u, -1, 0, 0.f, 0.f, h1, c1);
+            lstm_cell_pre(ws, ps0 + 4u * 64u * (uint32_t)(tau % kLstmPreRing), c.dyn_slot_cdem, c.dyn_slot_tin, xc, xt, h0, c0);
+            lstm_cell<true>(W, ws + 4u * kLstmLayerStride, h0, h1, c1);
         }
     } else
 #pragma unroll 1
@@ -624,29 +618,22 @@ __device__ __forceinline__ float lstm_update(const Dev& d, const UnitCtx<R>& c, 
 #pragma unroll
         for (int i = 0; i < kLstmIn; ++i) { if (i == c.dyn_slot_cdem) x[i] = xc; if (i == c.dyn_slot_tin) x[i] = xt; }
         if (smem_w) {
-            lstm_cell_q<true, false>(W, ws, g, quad_mask, quad_base, x, 0u, -1, 0, 0.f, 0.f, h0, c0);
-            lstm_cell_q<true, false>(W, ws + 4u * kLstmLayerStride, g, quad_mask, quad_base, h0, 0u, -1, 0, 0.f, 0.f, h1, c1);
+            lstm_cell<true>(W, ws, x, h0, c0);
+            lstm_cell<true>(W, ws + 4u * kLstmLayerStride, h0, h1, c1);
         } else {
-            lstm_cell_q<false, false>(W, 0u, g, quad_mask, quad_base, x, 0u, -1, 0, 0.f, 0.f, h0, c0);
-            lstm_cell_q<false, false>(W + kLstmLayerStride, 0u, g, quad_mask, quad_base, h0, 0u, -1, 0, 0.f, 0.f, h1, c1);
+            lstm_cell<false>(W, 0u, x, h0, c0);
+            lstm_cell<false>(W + kLstmLayerStride, 0u, h0, h1, c1);
         }
     }
     const float* wl = W + 2 * kLstmLayerStride;
     float y = wl[16];
 #pragma unroll
     for (int j = 0; j < kLstmH; ++j) y = fmaf(wl[j], h1[j], y);
-    // lane g stores the outputs and cell states of its hidden units
 #pragma unroll
-    for (int i = 0; i < kLstmOwn; ++i) {
-        const int j = 4 * i + g;
-        // (h0 / h1 are indexed dynamically only through this unrolled select: keeps them in registers)
-        float v0 = 0.f, v1 = 0.f;
-#pragma unroll
-        for (int gg = 0; gg < kLstmLanes; ++gg) { if (gg == g) { v0 = h0[4 * i + gg]; v1 = h1[4 * i + gg]; } }
-        lst[(size_t)j * U + u] = v0; lst[(size_t)(kLstmH + j) * U + u] = v1;
-        lst[(size_t)(2 * kLstmH + j) * U + u] = c0[i]; lst[(size_t)(3 * kLstmH + j) * U + u] = c1[i];
+    for (int j = 0; j < kLstmH; ++j) {
+        lst[(size_t)j * U + u] = h0[j]; lst[(size_t)(kLstmH + j) * U + u] = h1[j];
+        lst[(size_t)(2 * kLstmH + j) * U + u] = c0[j]; lst[(size_t)(3 * kLstmH + j) * U + u] = c1[j];
     }
-    __syncwarp(quad_mask);
     win_t[(size_t)(t % ring) * U] = y;                                       // the prediction replaces the slot (building.py:3027-3028)
     return y * c.tin_range + c.tin_min;                                      // de-normalised (building.py:3031-3037)
 }
@@ -721,16 +708,11 @@ __global__ void __launch_bounds__(MAXT, (DYNAMICS && MAXT == CL_DYN_MAXT) ? CL_D
     const int e0 = (WIDE ? (int)blockIdx.x / NT : (int)blockIdx.x) * epb;
     const int n_env = min(epb, d.E - e0);
     const int n_units = n_env * nb;
-    // LSTM districts: a unit is served by a QUAD of adjacent lanes (kLstmLanes = 4) - the four run the unit's physics redundantly
-    // (same loads, same values, same stores) and share its LSTM: lane lg owns 4 of the 16 hidden units (unit_physics.cuh)
-    const int vt = DYNAMICS ? (tid >> 2) : tid;             // unit slot of this thread
-    const int lg = DYNAMICS ? (tid & 3) : 0;
-    const unsigned quad_mask = DYNAMICS ? (0xFu << (lane & 28)) : 0xffffffffu;
-    const bool active = vt < n_units && !is_helper;
+    const bool active = tid < n_units;
     // thread -> unit: env-major (building fastest: coalesced state / action / reward slices) except for LSTM districts, where
     // building-major keeps the lanes of a warp on ONE building so that its LSTM weights are broadcast loads
-    const int bl = DYNAMICS ? vt / n_env : vt % nb;         // building inside the tile
-    const int e_l = DYNAMICS ? vt - bl * n_env : vt / nb;
+    const int bl = DYNAMICS ? tid / n_env : tid % nb;       // building inside the tile
+    const int e_l = DYNAMICS ? tid - bl * n_env : tid / nb;
     const int b = b0 + bl;
     const int ul = e_l * nb + bl;                  // unit slot inside the block's shared-memory arrays (always env-major)
     const int e = e0 + e_l, u = e * B + b;
@@ -836,7 +818,7 @@ __global__ void __launch_bounds__(MAXT, (DYNAMICS && MAXT == CL_DYN_MAXT) ? CL_D
         const int nin = __ldg(d.ip + CL_IP_DYN_N_INPUTS * B + bb);
         const float* xin = rowp + __ldg(d.ip + CL_IP_DYN_C_INPUTS * B + bb);
         float acc = Wb[64 * 32 + r];
-        for (int i = 0; i < nin; ++i) acc = fmaf(Wb[lstm_widx(r, i)], xin[i], acc);
+        for (int i = 0; i < nin; ++i) acc = fmaf(Wb[r * 16 + i], xin[i], acc);
         s_pre[((size_t)bb * kLstmPreRing + (tau % kLstmPreRing)) * 64 + r] = acc;
     };
     if (use_pre) {
@@ -993,8 +975,7 @@ __global__ void __launch_bounds__(MAXT, (DYNAMICS && MAXT == CL_DYN_MAXT) ? CL_D
             float t_in = row[c.c_tin];
             if (DYNAMICS && (c.p.flags & CL_F_DYNAMICS)) {
                 const float cd = (float)(o.e_from_cool + fabs(rmin(o.eb_cs, (R)0)));
-                t_in = lstm_update<R>(d, c, lstm_w, u, t, start_e, cd, t_in, use_pre ? s_pre + (size_t)b * kLstmPreRing * 64 : nullptr,
-                                      lg, quad_mask, lane & 28);
+                t_in = lstm_update<R>(d, c, lstm_w, u, t, start_e, cd, t_in, use_pre ? s_pre + (size_t)b * kLstmPreRing * 64 : nullptr);
             }
             red[ul] = (float)o.net;
             red[nt + ul] = (float)o.cost;
@@ -1559,12 +1540,11 @@ extern "C" int cl_create(const cl_district_desc* desc, cl_env** out) {
             for (int q = 0; q < 4; ++q) {
                 for (int j = 0; j < H; ++j) {
                     const int rs = q * H + j, r = q * kLstmH + j;      // gate-major rows (i, f, g, o)
-                    // (matrices in the quad-interleaved layout of unit_physics.cuh: lstm_widx)
-                    for (int i = 0; i < nin; ++i) o[lstm_widx(r, i)] = wih0[rs * nin + i];
-                    for (int i = 0; i < H; ++i) o[64 * 16 + lstm_widx(r, i)] = whh0[rs * H + i];
+                    for (int i = 0; i < nin; ++i) o[r * 16 + i] = wih0[rs * nin + i];
+                    for (int i = 0; i < H; ++i) o[64 * 16 + r * 16 + i] = whh0[rs * H + i];
                     o[64 * 32 + r] = bih0[rs] + bhh0[rs];
-                    for (int i = 0; i < H; ++i) o[kLstmLayerStride + lstm_widx(r, i)] = wih1[rs * H + i];
-                    for (int i = 0; i < H; ++i) o[kLstmLayerStride + 64 * 16 + lstm_widx(r, i)] = whh1[rs * H + i];
+                    for (int i = 0; i < H; ++i) o[kLstmLayerStride + r * 16 + i] = wih1[rs * H + i];
+                    for (int i = 0; i < H; ++i) o[kLstmLayerStride + 64 * 16 + r * 16 + i] = whh1[rs * H + i];
                     o[kLstmLayerStride + 64 * 32 + r] = bih1[rs] + bhh1[rs];
                 }
             }
@@ -1675,8 +1655,8 @@ extern "C" int cl_create(const cl_district_desc* desc, cl_env** out) {
         if (cudaFuncGetAttributes(&fa, fn) == cudaSuccess && fa.numRegs > 0) regs = fa.numRegs;
         cudaGetLastError();
     }
-    // threads per env: one per building, times the lanes that share a unit's LSTM in dynamics districts (unit_physics.cuh)
-    const int BT = B * (any_dyn ? kLstmLanes : 1);
+    // threads per env: one per building
+    const int BT = B;
     int target = 0;
     if (const char* ev = std::getenv("CL_B200_BLOCK_THREADS")) { const int v = std::atoi(ev); if (v >= 32 && v <= 992) target = v; }
     if (target == 0) {
@@ -1776,6 +1756,7 @@ extern "C" int cl_create(const cl_district_desc* desc, cl_env** out) {
             // (the general writer's dynbuf only exists with action-dependent observation columns)
             const size_t sm = smem_bytes(probe, thr, !d.stale, env->precision == CL_PRECISION_FP64 ? 8 : 4);
             if (sm > 200 * 1024) continue;
+            if (smem_bytes(probe, thr - 32, true, env->precision == CL_PRECISION_FP64 ? 8 : 4) > 227 * 1024) continue;   // the reset kernel's staging
             const int regs_alloc = ((regs_w + 7) / 8) * 8;
             int bps = 65536 / (regs_alloc * thr);
             bps = std::min(bps, 2048 / thr);
