@@ -510,7 +510,7 @@ __device__ __forceinline__ void write_obs_general(const Dev& d, float* obs, int 
 // offsets in floats from the start of the dynamic shared memory (kept as plain ints so that every access is derived
 // directly from the `extern __shared__` array and compiles to LDS/STS with 32-bit addressing, not generic loads)
 struct SmemLayout {
-    int curves, clut, bsolar, rows, tcol, tmpl, red, rsum, dsum, wpart, rpart, lstm, lstm_pre, lstm_io, dynbuf, kpi_acc, kpi_nws, kpi_env, end, Lp;
+    int curves, clut, bsolar, rows, tcol, tmpl, red, rsum, dsum, wpart, rpart, lstm, lstm_pre, dynbuf, kpi_acc, kpi_nws, kpi_env, end, Lp;
 };
 __host__ __device__ __forceinline__ SmemLayout smem_layout(int B, int Wp, int L, int epb, int nt, int rsize, int lstm_smem = 0, int tab_layout = 0, int fresh_slots = 0, int n_curves = 0, int kpi = 0) {
     SmemLayout o;
@@ -530,7 +530,6 @@ __host__ __device__ __forceinline__ SmemLayout smem_layout(int B, int Wp, int L,
     o.rpart = f; f += 2 * 32 * 2;                // wide districts, central agent: per-warp partial reward sums [2][32] doubles (8-byte aligned: f is even)
     o.lstm = f; f += lstm_smem ? B * kLstmStride : 0;      // kLstmStride is a multiple of 4 floats: 16-byte aligned rows
     o.lstm_pre = f; f += lstm_smem ? B * kLstmPreRing * 64 : 0;   // per-building ring of shared layer-0 input projections
-    o.lstm_io = f; f += lstm_smem ? nt + 32 * 32 : 0;              // warp-per-unit LSTM: predictions per unit slot + 32 floats of h broadcast per warp
     // with per-env row images the general writer's dynbuf is never live at the same time: it aliases them (cl_create checks the size)
     o.dynbuf = fresh_slots ? o.tmpl : f;
     // fused KPI accumulators (doubles; f is kept even): [CL_NKPI_UNIT][nt] running sums, [2][nt] baseline net of the step (by step
@@ -577,22 +576,22 @@ __device__ __forceinline__ void reward_inputs(const Dev& d, const UnitCtx<R>& c,
 template <typename R>
 __device__ __forceinline__ float lstm_update(const Dev& d, const UnitCtx<R>& c, const float* W, int u, int t, int row0 /* table row of step 0 */,
                                              float obs_cool_dem, float t_in_dataset, const float* pre /* this building's projection ring or nullptr */) {
+    const int U = d.U;
     const int L = c.dyn_lookback, ring = L + 1;
     const bool smem_w = d.lstm_smem != 0;                 // W then points into shared memory
     const uint32_t ws = smem_w ? smem_u32(W) : 0u;
     float* lst = d.lst;
-    float* su = lst + (size_t)u * kLstmStateFloats;                        // this unit's block: h0 h1 c0 c1 [16 each], win_c [13], win_t [13]
-    float* win_c = su + 4 * kLstmH;
-    float* win_t = su + 4 * kLstmH + kLstmMaxLookback + 1;
+    float* win_c = lst + (size_t)(4 * kLstmH) * U + u;                     // [ring][U]
+    float* win_t = lst + (size_t)(4 * kLstmH + kLstmMaxLookback + 1) * U + u;
     // _update_dynamics_input: append the normalised observation of step t (float32 arithmetic)
-    if (c.dyn_slot_cdem >= 0) win_c[t % ring] = (obs_cool_dem - c.cdem_min) / c.cdem_range;
-    win_t[t % ring] = (t_in_dataset - c.tin_min) / c.tin_range;
+    if (c.dyn_slot_cdem >= 0) win_c[(size_t)(t % ring) * U] = (obs_cool_dem - c.cdem_min) / c.cdem_range;
+    win_t[(size_t)(t % ring) * U] = (t_in_dataset - c.tin_min) / c.tin_range;
     if (t < L) return t_in_dataset;                                         // window not full yet (building.py:2996-2998)
     float h0[kLstmH], h1[kLstmH], c0[kLstmH], c1[kLstmH];
 #pragma unroll
     for (int j = 0; j < kLstmH; ++j) {
-        h0[j] = su[j]; h1[j] = su[kLstmH + j];
-        c0[j] = su[2 * kLstmH + j]; c1[j] = su[3 * kLstmH + j];
+        h0[j] = lst[(size_t)j * U + u]; h1[j] = lst[(size_t)(kLstmH + j) * U + u];
+        c0[j] = lst[(size_t)(2 * kLstmH + j) * U + u]; c1[j] = lst[(size_t)(3 * kLstmH + j) * U + u];
     }
     if (pre != nullptr) {
         // every env of the block sits on the same time rows: the exogenous part of W_ih x is shared (helper warp), only the
@@ -601,8 +600,8 @@ __device__ __forceinline__ float lstm_update(const Dev& d, const UnitCtx<R>& c, 
 #pragma unroll 1
         for (int sidx = 0; sidx < L; ++sidx) {
             const int tau = t - (L - 1) + sidx;
-            const float xc = c.dyn_slot_cdem >= 0 ? win_c[tau % ring] : 0.f;
-            const float xt = win_t[(tau - 1) % ring];
+            const float xc = c.dyn_slot_cdem >= 0 ? win_c[(size_t)(tau % ring) * U] : 0.f;
+            const float xt = win_t[(size_t)((tau - 1) % ring) * U];
             lstm_cell_pre(ws, ps0 + 4u * 64u * (uint32_t)(tau % kLstmPreRing), c.dyn_slot_cdem, c.dyn_slot_tin, xc, xt, h0, c0);
             lstm_cell<true>(W, ws + 4u * kLstmLayerStride, h0, h1, c1);
         }
@@ -614,8 +613,8 @@ __device__ __forceinline__ float lstm_update(const Dev& d, const UnitCtx<R>& c, 
         float x[kLstmIn];
 #pragma unroll
         for (int i = 0; i < kLstmIn; ++i) x[i] = i < c.dyn_n_inputs ? __ldg(row + i) : 0.f;
-        const float xc = c.dyn_slot_cdem >= 0 ? win_c[tau % ring] : 0.f;
-        const float xt = win_t[(tau - 1) % ring];             // indoor temperature is lagged by one step (building.py:3044-3049)
+        const float xc = c.dyn_slot_cdem >= 0 ? win_c[(size_t)(tau % ring) * U] : 0.f;
+        const float xt = win_t[(size_t)((tau - 1) % ring) * U];             // indoor temperature is lagged by one step (building.py:3044-3049)
 #pragma unroll
         for (int i = 0; i < kLstmIn; ++i) { if (i == c.dyn_slot_cdem) x[i] = xc; if (i == c.dyn_slot_tin) x[i] = xt; }
         if (smem_w) {
@@ -632,104 +631,11 @@ __device__ __forceinline__ float lstm_update(const Dev& d, const UnitCtx<R>& c, 
     for (int j = 0; j < kLstmH; ++j) y = fmaf(wl[j], h1[j], y);
 #pragma unroll
     for (int j = 0; j < kLstmH; ++j) {
-        su[j] = h0[j]; su[kLstmH + j] = h1[j];
-        su[2 * kLstmH + j] = c0[j]; su[3 * kLstmH + j] = c1[j];
+        lst[(size_t)j * U + u] = h0[j]; lst[(size_t)(kLstmH + j) * U + u] = h1[j];
+        lst[(size_t)(2 * kLstmH + j) * U + u] = c0[j]; lst[(size_t)(3 * kLstmH + j) * U + u] = c1[j];
     }
-    win_t[t % ring] = y;                                       // the prediction replaces the slot (building.py:3027-3028)
+    win_t[(size_t)(t % ring) * U] = y;                                       // the prediction replaces the slot (building.py:3027-3028)
     return y * c.tin_range + c.tin_min;                                      // de-normalised (building.py:3031-3037)
-}
-
-
-// ------------------------------------------------------------------------------------------------------------------
-// LSTM dynamics, one WARP per unit with the weights in REGISTERS (lock-step episode windows, weights staged in shared memory).
-// The thread-per-unit cell above fetches every weight from shared memory once per unit (one 16-byte broadcast load per 4 FMAs): the
-// cell is shared-memory-bound at ~1/3 of the FMA rate.  Here lane l of the warp owns gate rows l and l + 32 of both layers (lanes
-// 0-15: input gate i and candidate g of hidden unit l; lanes 16-31: forget gate f and output gate o of hidden unit l - 16) and keeps
-// their weights in registers for as long as the warp stays on one building; the unit's h vectors are broadcast to the lanes through
-// 32 floats of per-warp shared memory (8 uniform 16-byte loads per layer pair instead of 512), the cell states live in lanes 0-15.
-// Same operation order per gate row as `lstm_cell_pre` / `lstm_cell` (input half then recurrent half, column order): the same bits.
-// ------------------------------------------------------------------------------------------------------------------
-struct LstmRowWeights {
-    float whh0a[kLstmH], whh0b[kLstmH], wih1a[kLstmH], wih1b[kLstmH], whh1a[kLstmH], whh1b[kLstmH];
-    float wca, wcb, wta, wtb, b1a, b1b;
-};
-__device__ __forceinline__ void lstm_load_rows(const float* Wb /* shared */, int lane, int slot_c, int slot_t, LstmRowWeights& w) {
-    const int ra = lane, rb = lane + 32;
-    const float* l1 = Wb + kLstmLayerStride;
-#pragma unroll
-    for (int k = 0; k < kLstmH; ++k) {
-        w.whh0a[k] = Wb[64 * 16 + ra * 16 + k]; w.whh0b[k] = Wb[64 * 16 + rb * 16 + k];
-        w.wih1a[k] = l1[ra * 16 + k]; w.wih1b[k] = l1[rb * 16 + k];
-        w.whh1a[k] = l1[64 * 16 + ra * 16 + k]; w.whh1b[k] = l1[64 * 16 + rb * 16 + k];
-    }
-    w.wca = slot_c >= 0 ? Wb[ra * 16 + slot_c] : 0.f; w.wcb = slot_c >= 0 ? Wb[rb * 16 + slot_c] : 0.f;
-    w.wta = Wb[ra * 16 + slot_t]; w.wtb = Wb[rb * 16 + slot_t];
-    w.b1a = l1[64 * 32 + ra]; w.b1b = l1[64 * 32 + rb];
-}
-__device__ __forceinline__ void lds_vec16(const float* p /* shared, 16-byte aligned */, float* v) {
-    const uint32_t a = smem_u32(p);
-#pragma unroll
-    for (int q = 0; q < 4; ++q)
-        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[4 * q]), "=f"(v[4 * q + 1]), "=f"(v[4 * q + 2]), "=f"(v[4 * q + 3]) : "r"(a + 16u * q));
-}
-// gate values of this lane's two rows -> new cell state / output of hidden unit `lane` (lanes 0-15; the upper lanes only contribute)
-__device__ __forceinline__ float lstm_gates(float ga, float gb, int lane, float& cstate) {
-    const float a = sigmoid_dev(ga);                                    // i (lanes 0-15) or f (lanes 16-31)
-    const float bq = lane < 16 ? tanh_dev(gb) : sigmoid_dev(gb);         // g or o
-    const float f = __shfl_down_sync(0xffffffffu, a, 16), o = __shfl_down_sync(0xffffffffu, bq, 16);
-    const float cn = fmaf(f, cstate, a * bq);
-    cstate = cn;
-    return o * tanh_dev(cn);
-}
-// the LSTM of ONE unit for time step t (window full): returns the normalised prediction y in every lane
-__device__ __forceinline__ float lstm_warp_unit(const LstmRowWeights& w, const float* Wb, float* su /* this unit's state block (global) */,
-                                                const float* pre /* building's projection ring (shared) */, float* sh /* 32 floats, this warp */,
-                                                int lane, int t, int L, int slot_c) {
-    const int ring = L + 1;
-    // ring windows: cooling demand in lanes 0..12, lagged indoor temperature in lanes 16..28
-    float wv = 0.f;
-    if (lane < ring) wv = slot_c >= 0 ? su[4 * kLstmH + lane] : 0.f;
-    else if (lane >= 16 && lane - 16 < ring) wv = su[4 * kLstmH + kLstmMaxLookback + 1 + lane - 16];
-    float c0 = 0.f, c1 = 0.f;
-    if (lane < 16) { sh[lane] = su[lane]; sh[16 + lane] = su[kLstmH + lane]; c0 = su[2 * kLstmH + lane]; c1 = su[3 * kLstmH + lane]; }
-    __syncwarp();
-    const int ra = lane, rb = lane + 32;
-#pragma unroll 1
-    for (int sidx = 0; sidx < L; ++sidx) {
-        const int tau = t - (L - 1) + sidx;
-        const float xc = __shfl_sync(0xffffffffu, wv, tau % ring), xt = __shfl_sync(0xffffffffu, wv, 16 + (tau - 1) % ring);
-        const float* pr = pre + (size_t)(tau % kLstmPreRing) * 64;
-        float hv[kLstmH], xv[kLstmH];
-        // ---- layer 0: shared projection + the two fed-back inputs + W_hh0 h0 ----
-        lds_vec16(sh, hv);
-        float aa = pr[ra], ab = pr[rb], a2 = 0.f, b2 = 0.f;
-        if (slot_c >= 0) { aa = fmaf(w.wca, xc, aa); ab = fmaf(w.wcb, xc, ab); }
-        aa = fmaf(w.wta, xt, aa); ab = fmaf(w.wtb, xt, ab);
-#pragma unroll
-        for (int k = 0; k < kLstmH; ++k) { a2 = fmaf(w.whh0a[k], hv[k], a2); b2 = fmaf(w.whh0b[k], hv[k], b2); }
-        const float h0n = lstm_gates(aa + a2, ab + b2, lane, c0);
-        if (lane < 16) sh[lane] = h0n;
-        __syncwarp();
-        // ---- layer 1: W_ih1 h0(new) + W_hh1 h1 ----
-        lds_vec16(sh, xv); lds_vec16(sh + 16, hv);
-        aa = w.b1a; ab = w.b1b; a2 = 0.f; b2 = 0.f;
-#pragma unroll
-        for (int k = 0; k < kLstmH; ++k) { aa = fmaf(w.wih1a[k], xv[k], aa); ab = fmaf(w.wih1b[k], xv[k], ab); }
-#pragma unroll
-        for (int k = 0; k < kLstmH; ++k) { a2 = fmaf(w.whh1a[k], hv[k], a2); b2 = fmaf(w.whh1b[k], hv[k], b2); }
-        const float h1n = lstm_gates(aa + a2, ab + b2, lane, c1);      // (the shuffles inside order every lane's reads of sh before the write below)
-        if (lane < 16) sh[16 + lane] = h1n;
-        __syncwarp();
-    }
-    // linear head (sequential like the reference-order sum of the thread-per-unit path), state write-back
-    const float* wl = Wb + 2 * kLstmLayerStride;
-    float y = wl[16];
-#pragma unroll
-    for (int j = 0; j < kLstmH; ++j) y = fmaf(wl[j], sh[16 + j], y);
-    if (lane < 16) { su[lane] = sh[lane]; su[kLstmH + lane] = sh[16 + lane]; su[2 * kLstmH + lane] = c0; su[3 * kLstmH + lane] = c1; }
-    if (lane == 0) su[4 * kLstmH + kLstmMaxLookback + 1 + t % ring] = y;   // the prediction replaces the slot (building.py:3027-3028)
-    __syncwarp();
-    return y;
 }
 
 __device__ __forceinline__ void kpi_push(double* a, double x);
@@ -754,7 +660,7 @@ __device__ __forceinline__ void kpi_push(double* a, double x);
 // LSTM districts: block size cap / resident blocks per SM the dynamics instantiation is compiled for (A/B-tested on B200; the LSTM
 // loops need ~80 registers, the fp64 thermal physics around them spills either way)
 #ifndef CL_DYN_MAXT
-#define CL_DYN_MAXT 384                       // 170 registers per thread: the register-resident LSTM rows (102) + working set
+#define CL_DYN_MAXT 512
 #endif
 #ifndef CL_DYN_MINBLOCKS
 #define CL_DYN_MINBLOCKS 1
@@ -975,7 +881,6 @@ __global__ void __launch_bounds__(MAXT, (DYNAMICS && MAXT == CL_DYN_MAXT) ? CL_D
                     project_row(bb, t + 1, row_next, lane); project_row(bb, t + 1, row_next, lane + 32);
                 }
             }
-            if (use_pre) { __syncthreads(); __syncthreads(); }                 // SL1 / SL2 around the physics warps' LSTM phase
             if (coupled) cluster_sync_all(); else __syncthreads();             // S1
             if (need_dsum) __syncthreads();                                    // S2
             if (central_sync) { if (WIDE) cluster_sync_all(); else { if (k > 0) __syncthreads(); __syncthreads(); } }
@@ -1053,8 +958,6 @@ __global__ void __launch_bounds__(MAXT, (DYNAMICS && MAXT == CL_DYN_MAXT) ? CL_D
         // ---------------- physics warps ----------------
         UnitResult<R> o;
         RewardIn ri;
-        float t_in = 0.f;
-        bool lstm_pending = false;
         if (active) {
             UnitInputs<R> in;
             load_inputs<R, THERMAL>(d, c, row, b, t, in, uniform);
@@ -1069,57 +972,14 @@ __global__ void __launch_bounds__(MAXT, (DYNAMICS && MAXT == CL_DYN_MAXT) ? CL_D
             CL_STAMP(2);
             unit_step<R, THERMAL>(c.p, curves, t, in, s, o);
             CL_STAMP(3);
-            t_in = row[c.c_tin];
+            float t_in = row[c.c_tin];
+            if (DYNAMICS && (c.p.flags & CL_F_DYNAMICS)) {
+                const float cd = (float)(o.e_from_cool + fabs(rmin(o.eb_cs, (R)0)));
+                t_in = lstm_update<R>(d, c, lstm_w, u, t, start_e, cd, t_in, use_pre ? s_pre + (size_t)b * kLstmPreRing * 64 : nullptr);
+            }
             red[ul] = (float)o.net;
             red[nt + ul] = (float)o.cost;
             red[2 * nt + ul] = (float)o.emission;
-            if (DYNAMICS && (c.p.flags & CL_F_DYNAMICS)) {
-                const float cd = (float)(o.e_from_cool + fabs(rmin(o.eb_cs, (R)0)));
-                if (use_pre) {
-                    // warp-per-unit LSTM below: this thread only appends its unit's normalised observation of step t to the input
-                    // windows (_update_dynamics_input; float32 arithmetic)
-                    float* su = d.lst + (size_t)u * kLstmStateFloats;
-                    const int ring = c.dyn_lookback + 1;
-                    if (c.dyn_slot_cdem >= 0) su[4 * kLstmH + t % ring] = (cd - c.cdem_min) / c.cdem_range;
-                    su[4 * kLstmH + kLstmMaxLookback + 1 + t % ring] = (t_in - c.tin_min) / c.tin_range;
-                    lstm_pending = t >= c.dyn_lookback;                         // window full (building.py:2996-2998)
-                } else {
-                    t_in = lstm_update<R>(d, c, lstm_w, u, t, start_e, cd, t_in, nullptr);
-                }
-            }
-        }
-        if (DYNAMICS && use_pre) {
-            __syncthreads();                                                   // SL1: the window appends of every unit of the block are visible
-            {
-                // every physics warp takes its share of the block's (building, env) units; the gate rows of the warp's current building
-                // stay in registers while it works through that building's envs
-                const int wid = tid >> 5, P = np_ >> 5, J = n_env * B;
-                float* s_lout = smf + lo.lstm_io;
-                float* sh = s_lout + nt + wid * 32;
-                LstmRowWeights w;
-                int cur_b = -1, slot_c = -1, slot_t = 0, L = 0;
-                bool dynb = false;
-                for (int job = wid; job < J; job += P) {
-                    const int bi = job / n_env, le = job - bi * n_env;
-                    if (bi != cur_b) {
-                        cur_b = bi;
-                        dynb = (__ldg(d.ip + CL_IP_FLAGS * B + bi) & CL_F_DYNAMICS) != 0;
-                        if (dynb) {
-                            slot_c = __ldg(d.ip + CL_IP_DYN_SLOT_CDEM * B + bi); slot_t = __ldg(d.ip + CL_IP_DYN_SLOT_TIN * B + bi);
-                            L = __ldg(d.ip + CL_IP_DYN_LOOKBACK * B + bi);
-                            lstm_load_rows(smf + lo.lstm + (size_t)bi * kLstmStride, lane, slot_c, slot_t, w);
-                        }
-                    }
-                    if (!dynb || t < L) continue;
-                    const float y = lstm_warp_unit(w, smf + lo.lstm + (size_t)bi * kLstmStride, d.lst + ((size_t)(e0 + le) * B + bi) * kLstmStateFloats,
-                                                   s_pre + (size_t)bi * kLstmPreRing * 64, sh, lane, t, L, slot_c);
-                    if (lane == 0) s_lout[le * B + bi] = y;
-                }
-            }
-            __syncthreads();                                                   // SL2: predictions published
-            if (active && lstm_pending) t_in = smf[lo.lstm_io + ul] * c.tin_range + c.tin_min;   // de-normalised (building.py:3031-3037)
-        }
-        if (active) {
             if (fused_reward) reward_inputs<R, THERMAL>(d, c, s, o, row, t_in, ri);     // everything the reward needs from row t
             if (kpi) {
                 // CityLearnEnv.evaluate()'s action-dependent series (citylearn.py:1136-1323): control = the simulated values, baseline
@@ -1444,7 +1304,7 @@ __global__ void __launch_bounds__(MAXT) reset_kernel(Dev d, float* __restrict__ 
         s.soc_ds = Num<R>::r32((R)__ldg(P + CL_P_DS_INITIAL_SOC * B + b));
         store_state<R, true>(d, u, s);
         if (d.lst != nullptr) {
-            for (int j = 0; j < kLstmStateFloats; ++j) d.lst[(size_t)u * kLstmStateFloats + j] = 0.f;   // dynamics.py:112-127 (unit-major blocks)
+            for (int j = 0; j < kLstmStateFloats; ++j) d.lst[(size_t)j * d.U + u] = 0.f;   // dynamics.py:112-127
         }
         if (obs != nullptr) {
             const RowRef row = {d.table + (size_t)__ldg(d.start + e) * d.Wp, 0u};
