@@ -15,6 +15,7 @@ NVCC_FLAGS = [
     '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
     '--fmad=false',          # the fp64 mode reproduces the reference's (non-fused) NumPy arithmetic bit for bit
     '-shared', '-Xcompiler', '-fPIC',
+    '--split-compile', '0',  # ptxas works on the kernels of the one translation unit in parallel (the unrolled LSTM cells dominate the build)
 ]
 
 

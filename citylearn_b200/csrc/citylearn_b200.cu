@@ -29,6 +29,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "unit_physics.cuh"
@@ -41,6 +42,7 @@ namespace cl {
 struct Dev {
     int B, E, U, n_rows, W, Wp, A, L, T;
     int central, reward_id, stale, envs_per_block, uniform_start, start0, has_outage, any_dynamics, lstm_smem;
+    int lstm_const;        // 1: this district's packed LSTM weights are in the constant bank (c_lstm_w) for this launch
     int curve_nmax;        // max number of points of any battery curve of the district (uniform bound of the segment search)
     const uint8_t* curve_lut;   // [B][2][kCurveLutStride] uniform-grid index of the curve abscissae or nullptr (unit_physics.cuh)
     // buildings usually share a handful of distinct battery curve sets (one, in the bundled datasets and the synthetic districts): with
@@ -573,9 +575,10 @@ __device__ __forceinline__ void reward_inputs(const Dev& d, const UnitCtx<R>& c,
 // the exogenous inputs come pre-normalised from the table.  Returns the indoor temperature of step t (prediction once the
 // window is full, else the dataset value).
 // ------------------------------------------------------------------------------------------------------------------
-template <typename R>
+template <typename R, bool CONSTW>
 __device__ __forceinline__ float lstm_update(const Dev& d, const UnitCtx<R>& c, const float* W, int u, int t, int row0 /* table row of step 0 */,
-                                             float obs_cool_dem, float t_in_dataset, const float* pre /* this building's projection ring or nullptr */) {
+                                             float obs_cool_dem, float t_in_dataset, const float* pre /* this building's projection ring or nullptr */,
+                                             int bslot /* building index: slot in c_lstm_w */) {
     const int U = d.U;
     const int L = c.dyn_lookback, ring = L + 1;
     const bool smem_w = d.lstm_smem != 0;                 // W then points into shared memory
@@ -593,7 +596,27 @@ __device__ __forceinline__ float lstm_update(const Dev& d, const UnitCtx<R>& c, 
         h0[j] = lst[(size_t)j * U + u]; h1[j] = lst[(size_t)(kLstmH + j) * U + u];
         c0[j] = lst[(size_t)(2 * kLstmH + j) * U + u]; c1[j] = lst[(size_t)(3 * kLstmH + j) * U + u];
     }
-    if (pre != nullptr) {
+    if (CONSTW && pre != nullptr && d.lstm_const) {
+        // weights as immediate constant-bank operands: one fully unrolled instantiation per building slot (unit_physics.cuh)
+        const uint32_t ps0 = smem_u32(pre);
+        auto run = [&](auto BI) {
+          if constexpr (CONSTW) {
+#pragma unroll 1
+            for (int sidx = 0; sidx < L; ++sidx) {
+                const int tau = t - (L - 1) + sidx;
+                const float xc = c.dyn_slot_cdem >= 0 ? win_c[(size_t)(tau % ring) * U] : 0.f;
+                const float xt = win_t[(size_t)((tau - 1) % ring) * U];
+                lstm_cell_const<decltype(BI)::value, 0, true>(ps0 + 4u * 64u * (uint32_t)(tau % kLstmPreRing), c.dyn_slot_cdem, c.dyn_slot_tin, xc, xt, nullptr, h0, c0);
+                lstm_cell_const<decltype(BI)::value, 1, false>(0u, -1, 0, 0.f, 0.f, h0, h1, c1);
+            }
+          }
+        };
+        switch (bslot) {
+            case 0: run(std::integral_constant<int, 0>{}); break;
+            case 1: run(std::integral_constant<int, 1>{}); break;
+            default: run(std::integral_constant<int, 2>{}); break;
+        }
+    } else if (pre != nullptr) {
         // every env of the block sits on the same time rows: the exogenous part of W_ih x is shared (helper warp), only the
         // two fed-back inputs are per unit
         const uint32_t ps0 = smem_u32(pre);
@@ -975,7 +998,13 @@ __global__ void __launch_bounds__(MAXT, (DYNAMICS && MAXT == CL_DYN_MAXT) ? CL_D
             float t_in = row[c.c_tin];
             if (DYNAMICS && (c.p.flags & CL_F_DYNAMICS)) {
                 const float cd = (float)(o.e_from_cool + fabs(rmin(o.eb_cs, (R)0)));
-                t_in = lstm_update<R>(d, c, lstm_w, u, t, start_e, cd, t_in, use_pre ? s_pre + (size_t)b * kLstmPreRing * 64 : nullptr);
+                // (the constant-operand cells are compiled into the regular dynamics instantiation only: build time)
+#ifdef CL_LSTM_CONST            // experiment (profiles/README.md): constant-bank weight operands were 4.5x SLOWER than shared memory
+                constexpr bool kConstW = DYNAMICS && MAXT == kDynMaxT;
+#else
+                constexpr bool kConstW = false;
+#endif
+                t_in = lstm_update<R, kConstW>(d, c, lstm_w, u, t, start_e, cd, t_in, use_pre ? s_pre + (size_t)b * kLstmPreRing * 64 : nullptr, b);
             }
             red[ul] = (float)o.net;
             red[nt + ul] = (float)o.cost;
@@ -1347,6 +1376,7 @@ struct cl_env {
     int32_t* x_err_dev = nullptr;
     std::vector<void*> x_opened;     // cudaIpcOpenMemHandle mappings to close
     unsigned x_epoch = 0;            // steps exchanged so far
+    std::vector<float> lstm_packed;  // host copy of the packed LSTM weights when they fit the constant bank (<= kLstmConstBuildings buildings)
     int n_sm = 148;
     int T = 0;
     int threads = 0, blocks = 0;
@@ -1366,6 +1396,8 @@ struct cl_env {
 };
 
 using namespace cl;
+
+static cl_env* g_lstm_const_owner[64] = {};     // per device: the handle whose LSTM weights are in the constant bank (claim_lstm_constants)
 
 template <typename T> static int dev_copy(cl_env* env, const T* host, size_t n, T** out) {
     void* p = nullptr;
@@ -1555,6 +1587,9 @@ extern "C" int cl_create(const cl_district_desc* desc, cl_env** out) {
         int rc = dev_copy(env, packed.data(), packed.size(), &pw);
         if (rc) { cl_destroy(env); return rc; }
         d.lstm_w = pw;
+#ifdef CL_LSTM_CONST
+        if (B <= kLstmConstBuildings && std::getenv("CL_B200_NO_LSTM_CONST") == nullptr) env->lstm_packed = packed;
+#endif
         d.lstm_smem = ((size_t)B * kLstmStride * sizeof(float) <= 120 * 1024) ? 1 : 0;
     }
     // padded table
@@ -1676,7 +1711,9 @@ extern "C" int cl_create(const cl_district_desc* desc, cl_env** out) {
             const long waves = (blocks + (long)n_sm * bps - 1) / ((long)n_sm * bps);
             const long resident = blocks < (long)n_sm * bps ? (blocks + n_sm - 1) / n_sm : bps;   // blocks per SM actually resident
             const double cost = (double)waves * (double)resident * thr;
-            if (cost < best - 1e-9) { best = cost; target = cand[ci]; }
+            // (ties go to the larger block: per-block staging - curves, LSTM weights - is amortised over more units; measured on the
+            // LSTM district: 1.18 ms/step with 512-thread blocks against 1.35 with two 256-thread blocks per SM)
+            if (cost < best - 1e-9 || (cost < best + 1e-9 && cand[ci] > target)) { best = cost; target = cand[ci]; }
         }
         if (target == 0) target = 128;
         // Many more units than one wave of 512-thread blocks can hold (e.g. 17 x 32768): the 1024-thread instantiation (64
@@ -1807,6 +1844,7 @@ extern "C" int cl_destroy(cl_env* env) {
     if (env->dpart) cudaFree(env->dpart);
     if (env->kpi_unit) cudaFree(env->kpi_unit);
     if (env->kpi_env) cudaFree(env->kpi_env);
+    for (int i = 0; i < 64; ++i) if (g_lstm_const_owner[i] == env) g_lstm_const_owner[i] = nullptr;
     for (void* q : env->x_opened) cudaIpcCloseMemHandle(q);
     if (env->x_buf) cudaFree(env->x_buf);
     if (env->x_peers_dev) cudaFree(env->x_peers_dev);
@@ -1879,9 +1917,27 @@ static void launch_advance(cl_env* env, int t0, int K, const float* actions, flo
     if (nthreads <= (DY ? kDynMaxT : 512)) advance_kernel<R, TH, DY, (DY ? kDynMaxT : 512)><<<env->blocks, nthreads, smem, st>>>(env->d, t0, K, actions, obs, reward, district, trace);
     else advance_kernel<R, TH, DY, 1024><<<env->blocks, nthreads, smem, st>>>(env->d, t0, K, actions, obs, reward, district, trace);
 }
+// The constant bank holds ONE district's LSTM weights per device: the handle that launches next claims it (device-wide synchronisation
+// + 51 KB copy when the owner changes; never inside a stream capture - the launch then uses the shared-memory path).
+static void claim_lstm_constants(cl_env* env, cudaStream_t st) {
+    env->d.lstm_const = 0;
+    if (env->lstm_packed.empty()) return;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return;
+    if (g_lstm_const_owner[dev] != env) {
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) { cudaGetLastError(); return; }
+        if (cudaDeviceSynchronize() != cudaSuccess) return;
+        if (cudaMemcpyToSymbol(c_lstm_w, env->lstm_packed.data(), env->lstm_packed.size() * sizeof(float)) != cudaSuccess) { cudaGetLastError(); return; }
+        g_lstm_const_owner[dev] = env;
+    }
+    env->d.lstm_const = 1;
+}
+
 static void dispatch_one(cl_env* env, int t0, int K, const float* actions, float* obs, float* reward, float* district, float* trace,
                          bool coupled, cudaStream_t st) {
     if (env->d.x_n > 1) { env->d.x_epoch = env->x_epoch; env->x_epoch += (unsigned)K; }   // every rank runs the same launch sequence
+    if (env->dynamics) claim_lstm_constants(env, st);
     if (env->precision == CL_PRECISION_FP64) {
         if (env->dynamics) launch_advance<double, true, true>(env, t0, K, actions, obs, reward, district, trace, coupled, st);
         else if (env->thermal) launch_advance<double, true, false>(env, t0, K, actions, obs, reward, district, trace, coupled, st);

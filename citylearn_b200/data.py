@@ -43,6 +43,11 @@ class DataSource:
         """`model_state_dict` of an LSTM dynamics file as float32 arrays."""
         raise NotImplementedError
 
+    def text_table(self, filename: str) -> Dict[str, object]:
+        """Columns of a CSV file that may hold text (charger schedules name vehicles, washing machines list load profiles): numeric
+        columns as float64 arrays (NaN for empty cells), the others as lists of `str` / None."""
+        raise NotImplementedError
+
     @property
     def root_directory(self) -> Optional[str]:
         return None
@@ -73,6 +78,18 @@ class DirectorySource(DataSource):
             self._cache[filename] = {c: df[c].to_numpy(dtype='float64', na_value=np.nan) for c in df.columns}
         return self._cache[filename]
 
+    def text_table(self, filename: str) -> Dict[str, object]:
+        import pandas as pd
+        df = pd.read_csv(os.path.join(self._root, filename))
+        out: Dict[str, object] = {}
+        for c in df.columns:
+            col = df[c]
+            if pd.api.types.is_numeric_dtype(col):
+                out[c] = col.to_numpy(dtype='float64', na_value=np.nan)
+            else:
+                out[c] = [None if (v is None or (isinstance(v, float) and np.isnan(v)) or v is pd.NA) else str(v) for v in col.tolist()]
+        return out
+
     def state_dict(self, filename: str) -> Dict[str, np.ndarray]:
         import torch
         path = os.path.join(self._root, filename)
@@ -102,6 +119,16 @@ class PackSource(DataSource):
             self._tables[filename] = t
         return dict(self._tables[filename])
 
+    def text_table(self, filename: str) -> Dict[str, object]:
+        cols = self._index['text_tables'][filename]
+        out: Dict[str, object] = {}
+        for c, kind in cols.items():
+            if kind == 'num':
+                out[c] = self._npz[f'{filename}::{c}'].astype('float64')
+            else:
+                out[c] = json.loads(bytes(self._npz[f'{filename}::{c}']).decode())
+        return out
+
     def state_dict(self, filename: str) -> Dict[str, np.ndarray]:
         keys = self._index['state_dicts'][filename]
         return {k: self._npz[f'{filename}::{k}'] for k in keys}
@@ -111,7 +138,7 @@ def write_pack(src: DirectorySource, out_path: os.PathLike) -> None:
     """Pack every file the schema of `src` refers to into one compressed `.npz`."""
     schema = src.schema()
     arrays: Dict[str, np.ndarray] = {}
-    index = {'tables': {}, 'state_dicts': {}}
+    index = {'tables': {}, 'state_dicts': {}, 'text_tables': {}}
 
     def add_table(fn):
         if fn is None or fn in index['tables']:
@@ -121,9 +148,26 @@ def write_pack(src: DirectorySource, out_path: os.PathLike) -> None:
         for c, v in t.items():
             arrays[f'{fn}::{c}'] = v.astype('float32')
 
+    def add_text_table(fn):
+        if fn is None or fn in index['text_tables']:
+            return
+        t = src.text_table(fn)
+        index['text_tables'][fn] = {}
+        for c, v in t.items():
+            if isinstance(v, np.ndarray):
+                index['text_tables'][fn][c] = 'num'
+                arrays[f'{fn}::{c}'] = v.astype('float64')      # schedules are small; keep the parsed values exactly
+            else:
+                index['text_tables'][fn][c] = 'text'
+                arrays[f'{fn}::{c}'] = np.frombuffer(json.dumps(v).encode(), dtype='uint8')
+
     for b in schema['buildings'].values():
         for k in ('energy_simulation', 'weather', 'carbon_intensity', 'pricing'):
             add_table(b.get(k))
+        for cfg in (b.get('chargers') or {}).values():
+            add_text_table(cfg.get('charger_simulation'))
+        for cfg in (b.get('washing_machines') or {}).values():
+            add_text_table(cfg.get('washing_machine_energy_simulation'))
         dyn = b.get('dynamics')
         if dyn is not None:
             fn = dyn['attributes']['filename']

@@ -279,6 +279,8 @@ class BuildingSpec:
     maximum_temperature_delta: float = 20.0
     observation_space_limit_delta: float = 0.0
     demand_observation_limit_factor: float = 2.0
+    chargers: List[Any] = field(default_factory=list)            # ev.ChargerSpec
+    washing_machines: List[Any] = field(default_factory=list)    # ev.WashingMachineSpec
 
     @property
     def active_observations(self) -> List[str]:
@@ -313,6 +315,9 @@ class DistrictSpec:
     iparams: Optional[np.ndarray] = None          # [B, NIPARAM] int32
     lstm_weights: Optional[np.ndarray] = None     # flat float32, per-building blocks
     action_dim: int = 0
+    evs: List[Any] = field(default_factory=list)   # ev.ElectricVehicleSpec: vehicles shared by the district's chargers
+    ev: Optional[Dict[str, Any]] = None           # device-ready electric-vehicle / charger / washing-machine arrays (finalize)
+    ev_random_seed: Optional[int] = None
 
     @property
     def n_buildings(self) -> int:
@@ -592,9 +597,6 @@ def load(schema: Union[str, os.PathLike, Mapping[str, Any]], **kwargs) -> Distri
             raise Exception('Unknown buildings type. Allowed types are int and str.')
     else:
         names = [b for b in names if sch['buildings'][b]['include']]
-    if sch.get('electric_vehicles_def'):
-        if any(v.get('include') for v in sch['electric_vehicles_def'].values()):
-            raise UnsupportedSchemaError('electric vehicles are outside the accelerated hot path (SURVEY.md §8f-3)')
 
     spec = DistrictSpec(
         buildings=[], schema=sch, root_directory=source.root_directory, central_agent=bool(central_agent),
@@ -604,6 +606,13 @@ def load(schema: Union[str, os.PathLike, Mapping[str, Any]], **kwargs) -> Distri
         simulation_start_time_step=int(sim_start), simulation_end_time_step=int(sim_end),
         reward_type=None, reward_attributes=None)
 
+    # electric vehicles, chargers, washing machines (citylearn/citylearn.py:2010-2016, 2088-2098): per-charger / per-machine
+    # observations and actions are expanded from these schema-level switches in `_load_building`
+    from . import ev as EV
+    spec.evs = EV.load_electric_vehicles(sch, kwargs, resolve_battery)
+    spec.ev_random_seed = g('ev_random_seed') if g('ev_random_seed') is not None else random_seed
+    spec._helpers = {'ev_obs': {k: sch['observations'][k] for k in ev_obs}, 'wm_obs': {k: sch['observations'][k] for k in wm_obs},
+                     'ev_act': {k: sch['actions'][k] for k in ev_act}, 'wm_act': {k: sch['actions'][k] for k in wm_act}}
     ratios: List[float] = []
     for index, name in enumerate(names):
         spec.buildings.append(_load_building(index, name, sch, source, observations, actions, random_seed,
@@ -626,6 +635,20 @@ def load(schema: Union[str, os.PathLike, Mapping[str, Any]], **kwargs) -> Distri
         spec.reward_type = reward_type
         spec.reward_attributes = g('reward_function_kwargs') or reward_attrs or {}
 
+    # vehicle schedule: who is plugged in where, arrival SOCs, away-drift factors - all action-independent (ev.compile_schedule);
+    # charger observations become plain series of their building
+    all_chargers = [c for b in spec.buildings for c in b.chargers]
+    if all_chargers:
+        n_rows = len(spec.buildings[0].series['hour'])
+        sched = EV.compile_schedule(all_chargers, len(spec.evs), n_rows, spec.simulation_start_time_step, spec.simulation_end_time_step,
+                                    spec.ev_random_seed)
+        spec.ev = {'schedule': sched}
+        init = np.array([e.battery['initial_soc'] for e in spec.evs], dtype='float64')
+        for b in spec.buildings:
+            for c in b.chargers:
+                cols = EV.charger_observation_columns(c, sched, init)
+                for key, pattern in EV.CHARGER_OBSERVATIONS:
+                    b.series[pattern.format(id=c.charger_id)] = cols[key]
     finalize(spec)
     return spec
 
@@ -633,7 +656,7 @@ def load(schema: Union[str, os.PathLike, Mapping[str, Any]], **kwargs) -> Distri
 def _load_building(index, name, sch, source: DataSource, observations, actions, schema_seed, seconds_per_time_step,
                    ratios, spec: DistrictSpec, kwargs) -> BuildingSpec:
     bs = sch['buildings'][name]
-    for unsupported in ('chargers', 'washing_machines', 'occupant', 'charging_constraints'):
+    for unsupported in ('occupant', 'charging_constraints'):
         if bs.get(unsupported):
             raise UnsupportedSchemaError(f"building '{name}': '{unsupported}' is outside the accelerated hot path (SURVEY.md §8f)")
     if bs.get('noise_std', 0.0):
@@ -690,6 +713,40 @@ def _load_building(index, name, sch, source: DataSource, observations, actions, 
     else:
         ia = []
     am = {k: False if k in ia else v for k, v in am.items()}
+    # per-charger / per-machine observations and actions (process_metadata, citylearn/citylearn.py:2411-2555)
+    from . import ev as EV
+    hp = getattr(spec, '_helpers', {'ev_obs': {}, 'wm_obs': {}, 'ev_act': {}, 'wm_act': {}})
+    lo_row, hi_row = spec.simulation_start_time_step, spec.simulation_end_time_step
+    chargers = EV.load_chargers(index, bs, source, lo_row, hi_row, [e.name for e in spec.evs])
+    wms = EV.load_washing_machines(index, bs, source, kwargs)
+    for obj, names_ in [(c, ('state', 'ev', 'capacity', 'current_soc', 'departure_time', 'required_soc', 'arrival_time', 'soc_arrival')) for c in chargers] + \
+                       [(w, ('start', 'end', 'profile_sum', 'profile_len')) for w in wms]:
+        for an in names_:          # schedules index by dataset row like every other series
+            a = getattr(obj, an)
+            if len(a) < n:
+                raise UnsupportedSchemaError(f"building '{name}': a charger / washing-machine schedule is shorter than the building's series")
+            setattr(obj, an, a[:n])
+
+    def helper_flags(h, active_list, inactive_list):
+        f = {k: v['active'] for k, v in h.items()}
+        if active_list is not None:
+            f = {k: k in active_list for k in f}
+        return {k: False if k in inactive_list else v for k, v in f.items()}
+    ev_obs_f, wm_obs_f = helper_flags(hp['ev_obs'], ao, io_), helper_flags(hp['wm_obs'], ao, io_)
+    ev_act_f, wm_act_f = helper_flags(hp['ev_act'], aa, ia), helper_flags(hp['wm_act'], aa, ia)
+    for c in chargers:
+        for key, pattern in EV.CHARGER_OBSERVATIONS:
+            if ev_obs_f.get(key, False):
+                om[pattern.format(id=c.charger_id)] = True
+        if ev_act_f.get('electric_vehicle_storage', False):
+            am[f'electric_vehicle_storage_{c.charger_id}'] = True
+    for w in wms:
+        if wm_obs_f.get('washing_machine_start_time_step', False):
+            om[f'{w.name}_start_time_step'] = True
+        if wm_obs_f.get('washing_machine_end_time_step', False):
+            om[f'{w.name}_end_time_step'] = True
+        if wm_act_f.get('washing_machine', False):
+            am[f'{w.name}'] = True
 
     # ---- power outage (citylearn/citylearn.py:2273-2290) ----
     po = bs.get('power_outage', {}) or {}
@@ -761,7 +818,10 @@ def _load_building(index, name, sch, source: DataSource, observations, actions, 
         name=name, index=index, building_type=building_type, dynamics=is_dyn, observation_metadata=om, action_metadata=am,
         series=series, devices=devices, time_step_ratio=1.0 if time_step_ratio is None else float(time_step_ratio),
         seconds_per_time_step=seconds_per_time_step, simulate_power_outage=bool(simulate), stochastic_power_outage=bool(stochastic),
-        outage_model=model, dynamics_attrs=dyn_attrs, dynamics_weights=dyn_weights)
+        outage_model=model, dynamics_attrs=dyn_attrs, dynamics_weights=dyn_weights, chargers=chargers, washing_machines=wms)
+    for w in wms:      # observation columns (citylearn/building.py:1298-1335): the machine's schedule at the observed time step
+        series[f'{w.name}_start_time_step'] = np.asarray(w.start, dtype='float32')
+        series[f'{w.name}_end_time_step'] = np.asarray(w.end, dtype='float32')
     if 'cooling_or_heating_device' in b.active_actions:
         assert 'cooling_device' not in b.active_actions and 'heating_device' not in b.active_actions, \
             'cooling_device and heating_device actions must be set to False when cooling_or_heating_device is True.'
@@ -879,6 +939,16 @@ def estimate_observation_space_limits(b: BuildingSpec, spec: DistrictSpec, inclu
             x_sin, x_cos = np.sin(x), np.cos(x)
             low[f'{key}_cos'], high[f'{key}_cos'] = _bmin(x_cos), _bmax(x_cos)
             low[f'{key}_sin'], high[f'{key}_sin'] = _bmin(x_sin), _bmax(x_sin)
+        elif 'connected_state' in key or '_incoming_state' in key:
+            low[key], high[key] = 0, 1
+        elif '_departure_time' in key or '_estimated_arrival_time' in key:
+            low[key], high[key] = -1, 24
+        elif '_soc' in key and '_electric_vehicle' in key:
+            low[key], high[key] = -0.1, 1.0
+        elif 'charger' in key and key.endswith('_battery_capacity'):
+            low[key], high[key] = -1, 100
+        elif any(key in (f'{w.name}_start_time_step', f'{w.name}_end_time_step') for w in b.washing_machines):
+            low[key], high[key] = -1, 24
         elif key == 'occupant_interaction_indoor_dry_bulb_temperature_set_point_delta':
             pass
         else:
@@ -908,6 +978,13 @@ def estimate_action_space(b: BuildingSpec, spec: DistrictSpec) -> Tuple[np.ndarr
             limit = min(limit, 1.0)
             lo.append(-limit)
             hi.append(limit)
+        elif key.startswith('electric_vehicle_storage_'):       # citylearn/building.py:2199-2205
+            c = next(c for c in b.chargers if key == f'electric_vehicle_storage_{c.charger_id}')
+            lo.append(0.0 if c.max_discharging_power == 0 else -1.0)
+            hi.append(1.0)
+        elif any(key == w.name for w in b.washing_machines):   # :2207-2212
+            lo.append(0.0)
+            hi.append(1.0)
         else:
             raise UnsupportedSchemaError(f"action '{key}' is outside the accelerated hot path")
     return np.array(lo, dtype='float32'), np.array(hi, dtype='float32')
@@ -1010,6 +1087,8 @@ def finalize(spec: DistrictSpec) -> None:
     weights: List[np.ndarray] = []
     w_off = 0
     a_off = 0
+    ev_action_slot: Dict[Any, int] = {}
+    wm_action_slot: Dict[Any, int] = {}
     for bi, b in enumerate(spec.buildings):
         s, dv = b.series, b.devices
         ip = iparams[bi]
@@ -1138,9 +1217,76 @@ def finalize(spec: DistrictSpec) -> None:
         ip[IP['FLAGS']] = flags
         # action slots inside the district action vector (building order, active actions in schema order)
         for an in b.active_actions:
-            ip[IP['A_' + an.upper()]] = a_off
+            if an.startswith('electric_vehicle_storage_'):
+                ev_action_slot[(bi, an[len('electric_vehicle_storage_'):])] = a_off
+            elif any(an == w.name for w in b.washing_machines):
+                wm_action_slot[(bi, an)] = a_off
+            else:
+                ip[IP['A_' + an.upper()]] = a_off
             a_off += 1
     spec.action_dim = a_off
+    # ---- electric vehicles / chargers / washing machines: flat arrays for the device and the oracle ----
+    chargers = [c for b in spec.buildings for c in b.chargers]
+    wms = [w for b in spec.buildings for w in b.washing_machines]
+    if chargers or wms or spec.evs:
+        from . import ev as EV
+        sched = (spec.ev or {}).get('schedule')
+        if sched is None:
+            sched = EV.compile_schedule(chargers, len(spec.evs), n, spec.simulation_start_time_step, spec.simulation_end_time_step, spec.ev_random_seed)
+        n_ev = len(spec.evs)
+        ev_params = np.zeros((n_ev, NPARAM), dtype='float64')
+        ev_ip = np.zeros((n_ev, 2), dtype='int32')
+        ev_cols = np.zeros((n_ev, 4), dtype='int32')
+        for v, e in enumerate(spec.evs):
+            bat, q = e.battery, ev_params[v]
+            q[P['BAT_CAPACITY']], q[P['BAT_NOMINAL_POWER']], q[P['BAT_EFFICIENCY0']] = bat['capacity'], bat['nominal_power'], bat['efficiency']
+            q[P['BAT_LOSS']], q[P['BAT_CLC']], q[P['BAT_DOD']], q[P['BAT_INITIAL_SOC']] = bat['loss_coefficient'], bat['capacity_loss_coefficient'], bat['depth_of_discharge'], bat['initial_soc']
+            pe, cp = bat['power_efficiency_curve'], bat['capacity_power_curve']
+            ev_ip[v] = (pe.shape[1], cp.shape[1])
+            for j in range(MAX_CURVE):
+                q[P['PE_X0'] + j] = pe[0][min(j, pe.shape[1] - 1)]; q[P['PE_Y0'] + j] = pe[1][min(j, pe.shape[1] - 1)]
+                q[P['CP_X0'] + j] = cp[0][min(j, cp.shape[1] - 1)]; q[P['CP_Y0'] + j] = cp[1][min(j, cp.shape[1] - 1)]
+            q[P['TIME_STEP_RATIO']] = spec.buildings[0].time_step_ratio
+            q[P['HOURS_PER_STEP']] = spec.seconds_per_time_step / 3600
+            for j, key in enumerate(('assoc', 'sim', 'drift', 't0')):     # NaN = not applicable on that row
+                cols.append(np.ascontiguousarray(sched[key][:, v], dtype='float32'))
+                index[('ev', v, key)] = len(cols) - 1
+                ev_cols[v, j] = len(cols) - 1
+        ch_building = np.array([c.building for c in chargers], dtype='int32')
+        ch_action = np.array([ev_action_slot.get((c.building, c.charger_id), -1) for c in chargers], dtype='int32')
+        ch_cols = np.zeros((len(chargers), 4), dtype='int32')
+        CHP = EV.CHARGER_PARAMS
+        ch_params = np.zeros((len(chargers), len(CHP)), dtype='float64')
+        for k, c in enumerate(chargers):
+            con = EV.connected_mask(c)
+            series = {'conn': con.astype('float32'), 'ev': np.where(con, c.ev, -1).astype('float32'),
+                      'req': np.asarray(c.required_soc, dtype='float32'), 'dep': np.asarray(c.departure_time, dtype='float32')}
+            for j, key in enumerate(('conn', 'ev', 'req', 'dep')):
+                cols.append(np.ascontiguousarray(series[key]))
+                index[('charger', c.building, c.charger_id, key)] = len(cols) - 1
+                ch_cols[k, j] = len(cols) - 1
+            q = ch_params[k]
+            q[CHP['MAX_C']], q[CHP['MIN_C']], q[CHP['MAX_D']], q[CHP['MIN_D']], q[CHP['EFF']] = (c.max_charging_power, c.min_charging_power,
+                                                                                                 c.max_discharging_power, c.min_discharging_power, c.efficiency)
+            for pre, cv in (('C', c.charge_curve), ('D', c.discharge_curve)):
+                if cv is None:
+                    continue
+                if cv.shape[1] > MAX_CURVE:
+                    raise UnsupportedSchemaError('charger efficiency curves with more than 8 points are not supported')
+                q[CHP[f'{pre}_N']] = cv.shape[1]
+                for j in range(cv.shape[1]):
+                    q[CHP[f'{pre}_X0'] + j], q[CHP[f'{pre}_Y0'] + j] = cv[0][j], cv[1][j]
+        wm_building = np.array([w.building for w in wms], dtype='int32')
+        wm_action = np.array([wm_action_slot.get((w.building, w.name), -1) for w in wms], dtype='int32')
+        wm_cols = np.zeros((len(wms), 3), dtype='int32')
+        for k, w in enumerate(wms):
+            for j, (key, arr) in enumerate((('start', w.start), ('end', w.end), ('load', w.profile_sum))):
+                cols.append(np.ascontiguousarray(arr, dtype='float32'))
+                index[('wm', w.building, w.name, key)] = len(cols) - 1
+                wm_cols[k, j] = len(cols) - 1
+        spec.ev = {'schedule': sched, 'n_ev': n_ev, 'ev_params': ev_params, 'ev_ip': ev_ip, 'ev_cols': ev_cols, 'chargers': chargers,
+                   'ch_building': ch_building, 'ch_action': ch_action, 'ch_cols': ch_cols, 'ch_params': ch_params, 'wms': wms,
+                   'wm_building': wm_building, 'wm_action': wm_action, 'wm_cols': wm_cols}
     spec.table = np.ascontiguousarray(np.stack(cols, axis=1), dtype='float32')
     spec.columns = index
     spec.params = params

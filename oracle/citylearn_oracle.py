@@ -94,6 +94,7 @@ class OracleEnv:
         self.dyn_weights = []
         for bi, b in enumerate(spec.buildings):
             self.dyn_weights.append(b.dynamics_weights if b.dynamics else None)
+        self.evd = spec.ev if getattr(spec, 'ev', None) and (len(spec.ev.get('chargers', [])) or len(spec.ev.get('wms', []))) else None
 
     def _root(self, x):
         x = np.asarray(x, dtype=f64)
@@ -175,6 +176,8 @@ class OracleEnv:
             self.window = np.zeros((E, B, nin, L + 1), dtype=np.float64)
             self.window_fill = 0
             self.cool_dem_override = {}   # cooling demand written by update_cooling_demand at past steps is not needed again
+        if self.evd is not None:
+            self._ev_reset()
         # t = 0 accumulation from reset -> update_variables (citylearn/building.py:2618-2652)
         dyn = self._time0_values()
         return self._observations(0, dyn, zero_dyn=False)
@@ -192,14 +195,19 @@ class OracleEnv:
         ec_nsl = self.col32('C_NSL', 0)
         return [np.broadcast_to(x, (self.E, self.B)).astype(np.float32) for x in (ec_cool, ec_heat, ec_dhw, ec_nsl)]
 
-    def _net(self, ec, solar64, outage):
-        """building.py:2685-2703: float64 adds (series getter * np.float64 ratio), + float64 solar; stores are float32."""
+    def _net(self, ec, solar64, outage, chargers32=None, machines32=None):
+        """building.py:2685-2703: float64 adds (series getter * np.float64 ratio), + float64 solar (+ the float32 totals of the
+        building's chargers and washing machines); stores are float32."""
         r = self.P('TIME_STEP_RATIO')           # np.float64 in the reference -> the getter yields float64 series
         s = ec['cool'].astype(f64) * r + ec['heat'].astype(f64) * r
         s = s + ec['dhw'].astype(f64) * r
         s = s + ec['nsl'].astype(f64) * r
         s = s + ec['bat'].astype(f64) * r
-        net64 = np.where(outage, 0.0, s + solar64)
+        s = s + solar64
+        if chargers32 is not None:
+            s = s + chargers32.astype(f64)
+            s = s + machines32.astype(f64)
+        net64 = np.where(outage, 0.0, s)
         return net64
 
     def _time0_values(self):
@@ -475,6 +483,9 @@ class OracleEnv:
         e_to_nsl32 = w32(dem_nsl)
         add_ec('nsl', dem_nsl, np.ones((E, B), dtype=bool))
         battery(~np.broadcast_to(battery_first, (E, B)))
+        ch_ec32 = wm_ec32 = None
+        if self.evd is not None:
+            ch_ec32, wm_ec32 = self._ev_step(t, a)      # appended to the priority list (building.py:1582-1604): chargers, then washing machines
         self.cap_deg = self._pending_cap
         self.cap_deg_is_f32 = True
         self.eff_is_weak = False
@@ -494,7 +505,7 @@ class OracleEnv:
             add_ec('dhw', ((e_from['dhw'] + eb['ds']) / w32(eff['dhw'])).astype(f64), allm)
             add_ec('nsl', e_to_nsl32, allm)
             add_ec('bat', eb['bat'], allm)
-        net64 = self._net(ec, solar64, outage)
+        net64 = self._net(ec, solar64, outage, ch_ec32, wm_ec32)
         net = r32(net64)
         cost = r32(net64 * self.col('C_PRICE', t))
         emission = r32(np.maximum(0.0, net64 * self.col('C_CARBON', t)))
@@ -541,11 +552,196 @@ class OracleEnv:
 
         reward = self.reward.calculate(self, t, dyn, district)
         self.t = t + 1
+        if self.evd is not None:
+            self._ev_advance(self.t)
         if self.stale:
             obs = self._observations(self.t, None, zero_dyn=True)
         else:
             obs = self._observations(self.t, dyn, zero_dyn=False)
         return obs.astype(np.float32), reward.astype(np.float32), district.astype(np.float32), dyn
+
+    # -- electric vehicles, chargers, washing machines ---------------------------
+    def _ev_reset(self):
+        """`ElectricVehicle.reset` / `Battery.reset` + `associate_chargers_to_electric_vehicles` at t = 0 (citylearn.py:1871-1874)."""
+        ev, E = self.evd, self.E
+        q = ev['ev_params']
+        n = ev['n_ev']
+        self.ev_soc_prev = np.zeros((E, n))                                                  # soc[t - 1] entries (float32 values)
+        self.ev_soc = np.broadcast_to(r32(q[:, P['BAT_INITIAL_SOC']]), (E, n)).copy()        # soc[t] entries
+        self.ev_cap_deg = np.broadcast_to(q[:, P['BAT_CAPACITY']], (E, n)).copy()
+        self.ev_eff = np.broadcast_to(q[:, P['BAT_EFFICIENCY0']], (E, n)).copy()
+        self.ev_charged = np.zeros((E, n), dtype=bool)          # efficiency / degraded capacity are python floats until the first charge()
+        t0 = self.table[self.start[:, None], ev['ev_cols'][:, 3][None, :]].astype(f64)      # every connection is new at t = 0
+        self.ev_soc = np.where(np.isnan(t0), self.ev_soc, t0)
+        self.wm_initiated = np.zeros((E, len(ev['wms'])), dtype=bool)
+        self.last_ev = None
+
+    def _ev_interp(self, x, xs, ys, n):
+        """np.interp(x, xs[:n], ys[:n]) element-wise (Charger.get_efficiency, electric_vehicle_charger.py:252-281)."""
+        return np.array([np.interp(v, xs[:n], ys[:n]) for v in np.atleast_1d(x)])
+
+    def _ev_battery_charge(self, v, energy64):
+        """`Battery.charge(energy)` of vehicle v[e] for every env (energy_model.py:1027-1057): returns (soc32, eb32, eff, cap_deg)."""
+        ev = self.evd
+        q = ev['ev_params'][v]                                   # [E, NPARAM]
+        E = len(v)
+        ar = np.arange(E)
+        r = q[:, P['TIME_STEP_RATIO']]
+        cap, pnom = q[:, P['BAT_CAPACITY']], q[:, P['BAT_NOMINAL_POWER']]
+        t = self.t
+        soc_init32 = w32(self.ev_soc_prev[ar, v] if t > 0 else self.ev_soc[ar, v])           # soc[t-1], or soc[0] at t == 0 (:664-666, :1046)
+        charged = self.ev_charged[ar, v]
+        cap_deg, eff_prev = self.ev_cap_deg[ar, v], self.ev_eff[ar, v]
+        energy64 = energy64 * r
+        action_energy = energy64
+        e_init = np.maximum(0.0, (soc_init32 * w32(cap)).astype(f64) * (1 - q[:, P['BAT_LOSS']] * r))
+        soc_n = e_init / np.maximum(cap, EPS)
+
+        def seg(xn, x_off, y_off, n):
+            xs = q[:, x_off:x_off + S.MAX_CURVE]; ys = q[:, y_off:y_off + S.MAX_CURVE]
+            k = np.arange(S.MAX_CURVE)[None, :]
+            mask = (xn[:, None] <= xs) & (k < n[:, None])
+            first = np.where(mask.any(axis=1), mask.argmax(axis=1), 0)
+            idx = np.maximum(0, first - 1)
+            return xs[ar, idx], xs[ar, idx + 1], ys[ar, idx], ys[ar, idx + 1]
+        n_pe, n_cp = ev['ev_ip'][v, 0], ev['ev_ip'][v, 1]
+        x0, x1, y0, y1 = seg(soc_n, P['CP_X0'], P['CP_Y0'], n_cp)
+        with np.errstate(divide='ignore', invalid='ignore'):
+            p_max = pnom * (y0 + (y1 - y0) * (soc_n - x0) / (x1 - x0))
+        avail = pnom - 0.0 * r                                   # the vehicle battery's own consumption at t is 0 before its one charge
+        e_chg = np.minimum(np.minimum(np.minimum(p_max, avail), cap_deg - e_init), energy64)
+        arg_chg = np.minimum(action_energy, p_max)
+        diff32 = soc_init32 - w32(1.0 - q[:, P['BAT_DOD']])
+        root_prev = self._root(eff_prev)
+        lim = np.where(charged, (diff32 * w32(cap)).astype(f64) * root_prev, (diff32 * w32(cap) * w32(root_prev)).astype(f64))
+        lim = -np.maximum(lim, 0.0)
+        e_dis = np.maximum(np.maximum(-p_max, lim), energy64)
+        arg_dis = np.minimum(np.abs(action_energy), p_max)
+        pos = energy64 >= 0
+        e = np.where(pos, e_chg, e_dis)
+        arg = np.where(pos, arg_chg, arg_dis)
+        xn = np.abs(arg) / np.maximum(pnom, EPS)
+        x0, x1, y0, y1 = seg(xn, P['PE_X0'], P['PE_Y0'], n_pe)
+        with np.errstate(divide='ignore', invalid='ignore'):
+            eff = y0 + (xn - x0) * (y1 - y0) / (x1 - x0)
+        e = e * r
+        rte = self._root(eff)
+        fin = np.where(e >= 0, np.minimum(e_init + e * rte, cap), np.maximum(0.0, e_init + e / rte))
+        soc = w32(fin / np.maximum(cap, EPS))
+        d = fin - e_init
+        eb32 = w32(np.where(d >= 0, d / rte, d * rte))
+        ceb32 = w32(q[:, P['BAT_CLC']] * cap) * np.abs(eb32)
+        deg = np.where(charged, ceb32.astype(f64) / (2 * np.maximum(cap_deg, EPS)) * r, (ceb32 / w32(2 * np.maximum(cap, EPS))).astype(f64) * r)
+        return soc, eb32, eff, np.maximum(cap_deg - deg, 0.0)
+
+    def _ev_step(self, t, a):
+        """`Charger.update_connected_electric_vehicle_soc` for every charger, `WashingMachine.start_cycle` for every machine
+        (electric_vehicle_charger.py:283-329, energy_model.py:1311-1327); returns the per-building float32 consumption totals."""
+        ev, E, B = self.evd, self.E, self.B
+        rows = self.start + t
+        ar = np.arange(E)
+        CH = ev['chargers']
+        from citylearn_b200.ev import CHARGER_PARAMS as CP
+        nc = len(CH)
+        ch_ec = np.zeros((E, nc), dtype=np.float32)
+        past = np.zeros((E, nc), dtype=np.float32)
+        info = {k: np.zeros((E, nc)) for k in ('connected', 'soc_prev', 'soc_now', 'capacity', 'min_capacity', 'required', 'hours')}
+        hours = self.spec.seconds_per_time_step / 3600
+        for k, c in enumerate(CH):
+            slot = ev['ch_action'][k]
+            q = ev['ch_params'][k]
+            conn = self.table[rows, ev['ch_cols'][k, 0]] > 0
+            v = np.maximum(self.table[rows, ev['ch_cols'][k, 1]].astype(np.int64), 0)
+            act = a[:, slot] if slot >= 0 else np.zeros(E)
+            nz = (act != 0) & (slot >= 0)
+            charging = act > 0
+            n_c, n_d = int(q[CP['C_N']]), int(q[CP['D_N']])
+            eff_c = self._ev_interp(np.abs(act), q[CP['C_X0']:CP['C_X0'] + 8], q[CP['C_Y0']:CP['C_Y0'] + 8], n_c) if n_c else np.full(E, q[CP['EFF']])
+            eff_d = self._ev_interp(np.abs(act), q[CP['D_X0']:CP['D_X0'] + 8], q[CP['D_Y0']:CP['D_Y0'] + 8], n_d) if n_d else np.full(E, q[CP['EFF']])
+            eff = np.where(charging, eff_c, eff_d)
+            eff_is_f64 = np.where(charging, bool(n_c), bool(n_d))        # np.interp yields np.float64, the flat efficiency is a python float
+            en_c = np.maximum(np.minimum(act * q[CP['MAX_C']] * hours, q[CP['MAX_C']]), q[CP['MIN_C']])
+            en_d = np.maximum(np.minimum(act * q[CP['MAX_D']] * hours, -q[CP['MIN_D']]), -q[CP['MAX_D']])
+            energy = np.where(charging, en_c, en_d)
+            with np.errstate(divide='ignore', invalid='ignore'):
+                energy_kwh = np.where(charging, energy * eff, energy / eff)
+            past[:, k] = np.where(nz, energy, 0.0).astype(np.float32)
+            do = nz & conn
+            if do.any():
+                soc, eb32, eff_new, cap_new = self._ev_battery_charge(v, energy_kwh)
+                self.ev_soc[ar[do], v[do]] = soc[do].astype(f64)
+                self.ev_eff[ar[do], v[do]] = eff_new[do]
+                self.ev_cap_deg[ar[do], v[do]] = cap_new[do]
+                self.ev_charged[ar[do], v[do]] = True
+                # battery_energy_balance / efficiency (>= 0) or * efficiency: float32 arithmetic with the python-float efficiency,
+                # float64 with an interpolated one; stored into a float32 array either way
+                e32 = w32(eff)
+                with np.errstate(divide='ignore', invalid='ignore'):
+                    c32 = np.where(eb32 >= 0, eb32 / e32, eb32 * e32)
+                    c64 = w32(np.where(eb32 >= 0, eb32.astype(f64) / eff, eb32.astype(f64) * eff))
+                ch_ec[:, k] = np.where(do, np.where(eff_is_f64, c64, c32), 0.0).astype(np.float32)
+            info['connected'][:, k] = conn
+            info['soc_prev'][:, k] = np.where(t == 0, ev['ev_params'][v, P['BAT_INITIAL_SOC']], self.ev_soc_prev[ar, v])
+            info['soc_now'][:, k] = self.ev_soc[ar, v]
+            info['capacity'][:, k] = ev['ev_params'][v, P['BAT_CAPACITY']]
+            info['min_capacity'][:, k] = (1 - ev['ev_params'][v, P['BAT_DOD']]) * ev['ev_params'][v, P['BAT_CAPACITY']]
+            info['required'][:, k] = self.table[rows, ev['ch_cols'][k, 2]].astype(f64)
+            info['hours'][:, k] = self.table[rows, ev['ch_cols'][k, 3]].astype(f64)
+        info['past'] = past
+        info['ch_ec'] = ch_ec
+        # washing machines
+        WM = ev['wms']
+        wm_ec = np.zeros((E, len(WM)), dtype=np.float32)
+        for k, w in enumerate(WM):
+            slot = ev['wm_action'][k]
+            st = self.table[rows, ev['wm_cols'][k, 0]].astype(np.int64)
+            en = self.table[rows, ev['wm_cols'][k, 1]].astype(np.int64)
+            if t > 0:      # WashingMachine.next_time_step (energy_model.py:1302-1309): a new window re-arms the machine
+                pst = self.table[rows - 1, ev['wm_cols'][k, 0]].astype(np.int64)
+                pen = self.table[rows - 1, ev['wm_cols'][k, 1]].astype(np.int64)
+                self.wm_initiated[:, k] &= ~((pst != st) | (pen != en))
+            if slot < 0:
+                continue
+            act = a[:, slot]
+            go = (~self.wm_initiated[:, k]) & (act > 0) & (st != -1) & (en != -1) & (st <= t) & (t <= en)
+            load = w.profile_sum[rows]
+            # every entry of the profile whose step t + offset lies inside the episode is ADDED to ec[t] (float32 accumulate)
+            for e_i in np.nonzero(go)[0]:
+                acc = np.float32(0.0)
+                for off in range(int(w.profile_len[rows[e_i]])):
+                    if t + off < self.T:
+                        acc = np.float32(np.float64(acc) + np.float64(w.profile_values(rows[e_i])[off]))    # float32 slot += np.float64 entry
+                wm_ec[e_i, k] = acc
+            self.wm_initiated[:, k] |= go & (w.profile_len[rows] > 0)
+        info['wm_ec'] = wm_ec
+        self.last_ev = info
+        # building totals: python `0 + float32 + ...` in charger / machine order (building.py:2654-2672) -> float32
+        ch_tot = np.zeros((E, B), dtype=np.float32)
+        for k, c in enumerate(CH):
+            ch_tot[:, c.building] = (ch_tot[:, c.building] + ch_ec[:, k]).astype(np.float32)
+        wm_tot = np.zeros((E, B), dtype=np.float32)
+        for k, w in enumerate(WM):
+            wm_tot[:, w.building] = (wm_tot[:, w.building] + wm_ec[:, k]).astype(np.float32)
+        return ch_tot, wm_tot
+
+    def _ev_advance(self, t_new):
+        """`next_time_step` for the vehicles: new soc[t] entry = 0, then `simulate_unconnected_ev_soc` and
+        `associate_chargers_to_electric_vehicles` (citylearn.py:1336-1351) - compiled per row by ev.compile_schedule."""
+        ev = self.evd
+        self.ev_soc_prev = self.ev_soc.copy()
+        self.ev_soc = np.zeros_like(self.ev_soc)
+        if t_new > self.T - 1:
+            return
+        rows = self.start + t_new
+        cols = ev['ev_cols']
+        assoc = self.table[rows[:, None], cols[:, 0][None, :]].astype(f64)
+        if t_new + 1 < self.T:                                   # simulate_unconnected_ev_soc returns early on the last step (:1415-1417)
+            sim = self.table[rows[:, None], cols[:, 1][None, :]].astype(f64)
+            drift = ev['schedule']['drift'][rows]                # float64 factors (the table is float32)
+            drifted = r32(np.clip(self.ev_soc_prev * drift, 0.0, 1.0))
+            self.ev_soc = np.where(np.isnan(drift), self.ev_soc, drifted)
+            self.ev_soc = np.where(np.isnan(sim), self.ev_soc, sim)
+        self.ev_soc = np.where(np.isnan(assoc), self.ev_soc, assoc)
 
     # -- LSTM dynamics ---------------------------------------------------------------------------
     def L_max(self):

@@ -56,7 +56,7 @@ def import_reference():
     return CityLearnEnv
 
 
-def make_env(CityLearnEnv, dataset, overrides=None, reward=None):
+def make_env(CityLearnEnv, dataset, overrides=None, reward=None, schema_hook=None):
     # `EnergySimulation.__init__(..., time_step_ratios=[])` is a mutable default shared by every env of the process and indexed by
     # building position (citylearn/data.py:403,454): a second env in the same process silently reuses the FIRST env's ratios.
     # Clear it so that every fixture is what a fresh process would produce.
@@ -87,6 +87,8 @@ def make_env(CityLearnEnv, dataset, overrides=None, reward=None):
     schema['root_directory'] = str(root)
     if reward is not None:   # set in the schema dict so that schema attributes do not leak
         schema['reward_function'] = {'type': reward['type'], 'attributes': reward.get('attributes', {})}
+    if schema_hook is not None:
+        schema_hook(schema)
     return CityLearnEnv(schema, **overrides)
 
 
@@ -213,6 +215,70 @@ def run_case(CityLearnEnv, name, dataset, overrides=None, reward=None, steps=Non
     OUT.mkdir(parents=True, exist_ok=True)
     np.savez_compressed(OUT / f'{name}.npz', **arrays)
     print(name, {k: v.shape for k, v in arrays.items() if k not in ('config', 'meta')}, (OUT / f'{name}.npz').stat().st_size)
+
+
+def run_ev_case(CityLearnEnv, name, dataset, overrides=None, reward=None, steps=200, seed=0, np_seed=5):
+    """Electric vehicles / chargers / washing machines.  The reference draws the SOC drift of away vehicles from NumPy's
+    GLOBAL generator (citylearn/citylearn.py:1473) and a missing vehicle `initial_soc` from Python's global `random`
+    (citylearn.py:2564): the fixture seeds the former (`np_seed`, = `ev_random_seed` of the replacement) and writes the latter into the
+    schema (the replacement's own stable default, `citylearn_b200.ev._stable_unit`)."""
+    sys.path.insert(0, str(HERE.parent))
+    from citylearn_b200.ev import _stable_unit
+
+    def hook(schema):
+        for n, e in (schema.get('electric_vehicles_def') or {}).items():
+            a = e['battery']['attributes']
+            if a.get('initial_soc') is None:
+                a['initial_soc'] = _stable_unit(n)
+    np.random.seed(np_seed)
+    env = make_env(CityLearnEnv, dataset, overrides, reward, schema_hook=hook)
+    meta = env_meta(env)
+    lo = np.concatenate([np.asarray(b.action_space.low, dtype='float64') for b in env.buildings])
+    hi = np.concatenate([np.asarray(b.action_space.high, dtype='float64') for b in env.buildings])
+    sizes = [b.action_space.shape[0] for b in env.buildings]
+    rng = np.random.RandomState(seed)
+    obs, _ = env.reset()
+    reset_obs = flat(obs)
+    K = min(steps, env.time_steps - 1)
+    actions = (lo + rng.uniform(0.0, 1.0, size=(K, len(lo))) * (hi - lo)).astype('float32')
+    actions[rng.rand(*actions.shape) < 0.08] = 0.0          # exact zeros: an idle charger leaves soc[t] untouched (electric_vehicle_charger.py:325-327)
+    chargers = [(b, c) for b in env.buildings for c in (b.electric_vehicle_chargers or [])]
+    machines = [(b, w) for b in env.buildings for w in (b.washing_machines or [])]
+    out = {k: [] for k in ('obs', 'reward', 'district', 'trace', 'ev_soc', 'charger_ec', 'charger_kwh', 'wm_ec')}
+    for k in range(K):
+        a = [float(x) for x in actions[k]]
+        act, o = [], 0
+        for n in sizes:
+            act.append(a[o:o + n])
+            o += n
+        obs, rew, term, trunc, _ = env.step([a] if env.central_agent else act)
+        out['obs'].append(flat(obs)); out['reward'].append(flat(rew))
+        out['district'].append([float(env.net_electricity_consumption[k]), float(env.net_electricity_consumption_cost[k]),
+                                float(env.net_electricity_consumption_emission[k])])
+        out['trace'].append([unit_trace(b, k) for b in env.buildings])
+        out['ev_soc'].append([float(e.battery.soc[k]) for e in env.electric_vehicles])
+        out['charger_ec'].append([float(c.electricity_consumption[k]) for _, c in chargers])
+        out['charger_kwh'].append([float(c.past_charging_action_values_kwh[k]) for _, c in chargers])
+        out['wm_ec'].append([float(w.electricity_consumption[k]) for _, w in machines])
+    arrays = {'actions': actions, 'reset_obs': np.array(reset_obs, dtype='float32'), 'obs': np.array(out['obs'], dtype='float32'),
+              'reward': np.array(out['reward'], dtype='float32'), 'district': np.array(out['district'], dtype='float32'),
+              'trace': np.array(out['trace'], dtype='float32'), 'ev_soc': np.array(out['ev_soc'], dtype='float32'),
+              'charger_ec': np.array(out['charger_ec'], dtype='float32'), 'charger_kwh': np.array(out['charger_kwh'], dtype='float32'),
+              'wm_ec': np.array(out['wm_ec'], dtype='float32')}
+    config = {'dataset': dataset, 'overrides': overrides or {}, 'reward': reward, 'seed': seed, 'np_seed': np_seed, 'trace_names': TRACE_NAMES,
+              'numpy': np.__version__, 'chargers': [c.charger_id for _, c in chargers], 'vehicles': [e.name for e in env.electric_vehicles]}
+    arrays['config'] = np.frombuffer(json.dumps(config).encode(), dtype='uint8')
+    arrays['meta'] = np.frombuffer(json.dumps(meta).encode(), dtype='uint8')
+    OUT.mkdir(parents=True, exist_ok=True)
+    np.savez_compressed(OUT / f'{name}.npz', **arrays)
+    print(name, {k: v.shape for k, v in arrays.items() if k not in ('config', 'meta')}, (OUT / f'{name}.npz').stat().st_size)
+
+
+EV_CASES = {
+    'c10_evs': dict(dataset='citylearn_challenge_2022_phase_all_plus_evs', steps=300, seed=21, np_seed=5,
+                    reward={'type': 'citylearn.reward_function.RewardFunction', 'attributes': {}}),
+    'c10_evs_reward': dict(dataset='citylearn_challenge_2022_phase_all_plus_evs', steps=120, seed=22, np_seed=6),
+}
 
 
 def run_wrapper_case(CityLearnEnv, name, dataset, wrapper, overrides=None, steps=60, seed=0):
@@ -434,7 +500,7 @@ CASES = {
 
 if __name__ == '__main__':
     CityLearnEnv = import_reference()
-    todo = sys.argv[1:] or (list(CASES) + list(WRAPPER_CASES) + ['meta_fuzz', 'trace_fuzz', 'trace_datasets'])
+    todo = sys.argv[1:] or (list(CASES) + list(EV_CASES) + list(WRAPPER_CASES) + ['meta_fuzz', 'trace_fuzz', 'trace_datasets'])
     for n in todo:
         if n == 'trace_fuzz':
             run_trace_fuzz(CityLearnEnv)
@@ -449,7 +515,9 @@ if __name__ == '__main__':
         if n == 'meta_fuzz':
             run_meta_fuzz(CityLearnEnv)
             continue
-        if n in WRAPPER_CASES:
+        if n in EV_CASES:
+            run_ev_case(CityLearnEnv, n, **EV_CASES[n])
+        elif n in WRAPPER_CASES:
             run_wrapper_case(CityLearnEnv, n, **WRAPPER_CASES[n])
         else:
             run_case(CityLearnEnv, n, **CASES[n])
