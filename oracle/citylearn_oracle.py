@@ -879,6 +879,59 @@ class OracleReward:
             reward = reward + np.where(cap > EPS, term, np.float32(0.0)).astype(np.float32)
         return reward
 
+    def _ev_reward(self, env, t, dyn, district):
+        """Electric_Vehicles_Reward_Function (reward_function.py:389-523): the MARL reward only scales the penalty / bonus terms of the
+        building's chargers; a building without chargers is rewarded 0."""
+        E, B = dyn.shape[0], dyn.shape[1]
+        w = self.attrs.get('weights') or {"no_car_charging": -5.0, "battery_limits": -2.0, "soc_impossible": -10.0, "soc_under": -5.0,
+                                          "close_soc": 10.0, "self_ev_consumption": 5.0, "extra_self_production": 5.0}
+        e = dyn[..., DYN['net_electricity_consumption']]
+        be = e * -1
+        marl = np.sign(be) * 0.01 * be ** 2 * np.fmax(0.0, district[:, 0:1])
+        if env.central:
+            tot = np.zeros(E)
+            for bi in range(B):
+                tot = tot + marl[:, bi]
+            marl = np.broadcast_to(tot[:, None], (E, B))
+        out = np.zeros((E, B))
+        info = env.last_ev
+        from citylearn_b200.ev import CHARGER_PARAMS as CP
+        for k, c in enumerate(env.evd['chargers']):
+            bi = c.building
+            mult = 1.0 / (1.0 + np.abs(marl[:, bi]))
+            q = env.evd['ch_params'][k]
+            con = info['connected'][:, k] > 0
+            kwh = info['past'][:, k].astype(f64)
+            net = w32(e[:, bi])
+            contrib = np.zeros(E)
+            # (a charger without a vehicle reports last_charged_kwh = 0.0 (building.py:1378-1389), so the `no_car_charging` term never fires)
+            soc_prev, soc_now, cap, mincap = info['soc_prev'][:, k], info['soc_now'][:, k], info['capacity'][:, k], info['min_capacity'][:, k]
+            # np.float32 soc * python capacity + python kWh is float32 arithmetic (python-float initial_soc at t == 0: float64)
+            cur = (w32(soc_prev) * w32(cap) + w32(kwh)).astype(f64) if t > 0 else soc_prev * cap + kwh
+            c_con = np.where((cur > cap) | (cur < mincap), w['battery_limits'] * mult, 0.0)
+            req, hrs = info['required'][:, k], info['hours'][:, k]
+            diff = w32(soc_now).astype(f64) - req
+            diff_kwh = diff * cap
+            max_c, max_d = q[CP['MAX_C']] * hrs, q[CP['MAX_D']] * hrs
+            c_con = c_con + np.where(diff_kwh > max_c, w['soc_impossible'] * mult, 0.0)
+            at_dep = hrs == 0
+            c_con = c_con + np.where(at_dep & (-0.25 < diff) & (diff <= -0.10), 2 * w['soc_under'] * mult, 0.0)
+            c_con = c_con + np.where(at_dep & (diff <= -0.25), (w['soc_under'] ** 2) * mult, 0.0)
+            c_con = c_con + np.where(at_dep & (-0.10 < diff) & (diff <= 0.10), w['close_soc'] * mult, 0.0)
+            with np.errstate(divide='ignore'):
+                c_con = c_con + np.where(np.abs(diff_kwh) <= np.maximum(max_c, max_d), w['close_soc'] * mult * (1.0 / (hrs + 0.1)), 0.0)
+            c_con = c_con + np.where((kwh > 0) & (net < 0), w['extra_self_production'] * mult, 0.0)
+            c_con = c_con + np.where((kwh < 0) & (net < 0), -0.5 * w['extra_self_production'] * mult, 0.0)
+            c_con = c_con + np.where((kwh < 0) & (net > 0), w['self_ev_consumption'] * mult, 0.0)
+            c_con = c_con + np.where((kwh > 0) & (net > 0), -0.5 * w['self_ev_consumption'] * mult, 0.0)
+            out[:, bi] = out[:, bi] + contrib + np.where(con, c_con, 0.0)
+        if env.central:
+            tot = np.zeros((E, 1))
+            for bi in range(B):
+                tot[:, 0] = tot[:, 0] + out[:, bi]
+            return tot
+        return out
+
     def calculate(self, env, t, dyn, district):
         e = dyn[..., DYN['net_electricity_consumption']]
         k = self.kind
@@ -898,6 +951,8 @@ class OracleReward:
         elif k == 'SolarPenaltyAndComfortReward':
             co = self.attrs.get('coefficients') or [1.0, 1.0]
             r = self._solar_penalty(env, dyn).astype(f64) * co[0] + self._comfort(env, t, dyn).astype(f64) * co[1]
+        elif k == 'Electric_Vehicles_Reward_Function':
+            return self._ev_reward(env, t, dyn, district)
         else:
             raise NotImplementedError(k)
         if env.central:

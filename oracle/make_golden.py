@@ -269,9 +269,9 @@ def run_ev_case(CityLearnEnv, name, dataset, overrides=None, reward=None, steps=
               'numpy': np.__version__, 'chargers': [c.charger_id for _, c in chargers], 'vehicles': [e.name for e in env.electric_vehicles]}
     arrays['config'] = np.frombuffer(json.dumps(config).encode(), dtype='uint8')
     arrays['meta'] = np.frombuffer(json.dumps(meta).encode(), dtype='uint8')
-    OUT.mkdir(parents=True, exist_ok=True)
-    np.savez_compressed(OUT / f'{name}.npz', **arrays)
-    print(name, {k: v.shape for k, v in arrays.items() if k not in ('config', 'meta')}, (OUT / f'{name}.npz').stat().st_size)
+    (OUT / 'ev').mkdir(parents=True, exist_ok=True)
+    np.savez_compressed(OUT / 'ev' / f'{name}.npz', **arrays)
+    print(name, {k: v.shape for k, v in arrays.items() if k not in ('config', 'meta')}, (OUT / 'ev' / f'{name}.npz').stat().st_size)
 
 
 EV_CASES = {
