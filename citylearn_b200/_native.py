@@ -30,11 +30,17 @@ class DistrictDesc(ctypes.Structure):
         ('precision', ctypes.c_int32), ('stale_observations', ctypes.c_int32), ('lstm_weight_count', ctypes.c_int32),
         ('reward_params', ctypes.c_double * 8),
         ('table', ctypes.c_void_p), ('params', ctypes.c_void_p), ('iparams', ctypes.c_void_p),
-        ('obs_desc', ctypes.c_void_p), ('lstm_weights', ctypes.c_void_p),
+        ('obs_desc', ctypes.c_void_p), ('lstm_weights', ctypes.c_void_p), ('ev', ctypes.c_void_p),
     ]
 
 
-ABI_VERSION = 1
+class EvDesc(ctypes.Structure):          # cl_ev_desc
+    _fields_ = [('n_ev', ctypes.c_int32), ('n_chargers', ctypes.c_int32), ('n_machines', ctypes.c_int32)] + [
+        (n, ctypes.c_void_p) for n in ('ev_params', 'ev_iparams', 'ev_cols', 'ev_drift', 'ch_building', 'ch_action', 'ch_cols', 'ch_params',
+                                       'wm_building', 'wm_action', 'wm_cols')]
+
+
+ABI_VERSION = 2
 PRECISION = {'fp32': 0, 'fp64': 1}
 
 
@@ -67,6 +73,7 @@ def load():
     lib.cl_step.argtypes = [vp, vp, vp, vp, vp, vp, vp]
     lib.cl_rollout.argtypes = [vp, i32, vp, vp, vp, vp, vp]
     lib.cl_device_time_enable.argtypes = [vp, vp]
+    lib.cl_ev_read.argtypes = [vp, vp, vp, vp]
     lib.cl_exchange_create.argtypes = [vp, i32, i32, vp, ctypes.POINTER(vp)]
     lib.cl_exchange_connect.argtypes = [vp, vp]
     lib.cl_exchange_connect_ptrs.argtypes = [vp, ctypes.POINTER(vp), vp]
@@ -90,7 +97,7 @@ def load():
     for name in ('cl_create', 'cl_destroy', 'cl_set_outage', 'cl_reset', 'cl_step', 'cl_rollout', 'cl_obs_rows', 'cl_time_step',
                  'cl_state_size', 'cl_get_state', 'cl_set_state', 'cl_launch_count', 'cl_launch_geometry', 'cl_set_transforms',
                  'cl_kpi_enable', 'cl_kpi_accumulate', 'cl_kpi_read', 'cl_measure_fma_peak', 'cl_device_time_enable', 'cl_advance_device',
-                 'cl_launch_occupancy', 'cl_kpi_fused', 'cl_exchange_create', 'cl_exchange_connect', 'cl_exchange_connect_ptrs', 'cl_exchange_status'):
+                 'cl_launch_occupancy', 'cl_kpi_fused', 'cl_ev_read', 'cl_exchange_create', 'cl_exchange_connect', 'cl_exchange_connect_ptrs', 'cl_exchange_status'):
         getattr(lib, name).restype = ctypes.c_int
     if lib.cl_abi_version() != ABI_VERSION:
         raise NativeLibraryError(f'{path}: ABI version {lib.cl_abi_version()} != {ABI_VERSION}; rebuild the extension')
@@ -144,6 +151,24 @@ class Handle:
         d.iparams = iparams.ctypes.data
         d.obs_desc = desc_arr.ctypes.data
         d.lstm_weights = weights.ctypes.data if weights.size else None
+        evd = getattr(spec, 'ev', None)
+        keep = []
+        if evd and (len(evd['chargers']) or len(evd['wms'])):
+            e = EvDesc()
+            e.n_ev, e.n_chargers, e.n_machines = int(evd['n_ev']), len(evd['chargers']), len(evd['wms'])
+            drift = np.ascontiguousarray(evd['schedule']['drift'], dtype='float64') if evd['n_ev'] else np.zeros((table.shape[0], 1))
+            arrays = {'ev_params': (evd['ev_params'], 'float64'), 'ev_iparams': (evd['ev_ip'], 'int32'), 'ev_cols': (evd['ev_cols'], 'int32'),
+                      'ev_drift': (drift, 'float64'), 'ch_building': (evd['ch_building'], 'int32'), 'ch_action': (evd['ch_action'], 'int32'),
+                      'ch_cols': (evd['ch_cols'], 'int32'), 'ch_params': (evd['ch_params'], 'float64'), 'wm_building': (evd['wm_building'], 'int32'),
+                      'wm_action': (evd['wm_action'], 'int32'), 'wm_cols': (evd['wm_cols'], 'int32')}
+            for name, (arr, dt) in arrays.items():
+                a = np.ascontiguousarray(arr, dtype=dt)
+                keep.append(a)
+                setattr(e, name, a.ctypes.data if a.size else None)
+            keep.append(e)
+            d.ev = ctypes.addressof(e)
+        else:
+            d.ev = None
         out = ctypes.c_void_p()
         check(self.lib.cl_create(ctypes.byref(d), ctypes.byref(out)), 'cl_create')
         self.ptr = out
@@ -174,6 +199,9 @@ class Handle:
 
     def rollout(self, n_steps: int, actions_ptr, obs_ptr, reward_ptr, district_ptr, stream: int):
         check(self.lib.cl_rollout(self.ptr, int(n_steps), actions_ptr, obs_ptr, reward_ptr, district_ptr, stream), 'cl_rollout')
+
+    def ev_read(self, soc_prev_ptr, soc_ptr, stream: int):
+        check(self.lib.cl_ev_read(self.ptr, soc_prev_ptr, soc_ptr, stream), 'cl_ev_read')
 
     def device_time_enable(self, stream: int):
         check(self.lib.cl_device_time_enable(self.ptr, stream), 'cl_device_time_enable')

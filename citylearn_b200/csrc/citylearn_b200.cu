@@ -88,6 +88,23 @@ struct Dev {
     double* kpi_unit;                // [E][B][CL_NKPI_UNIT] or nullptr
     double* kpi_env;                 // [E][2][CL_NKPI_ENV]
     int kpi_smem;                    // 1: the shared-memory layout carries the accumulators
+    // electric vehicles / chargers / washing machines (cl_ev_desc; unit_physics.cuh: charger_step)
+    int ev_n, ch_n, wm_n;
+    const double* ev_pd;             // [ev_n][CL_NPARAM] vehicle battery parameters
+    const int32_t* ev_ip;            // [ev_n][2] curve point counts
+    const int32_t* ev_cols;          // [ev_n][4] table columns (association SOC, pre-connection SOC, -, episode-start SOC)
+    const double* ev_drift;          // [n_rows][ev_n]
+    const int32_t* ch_off;           // [B + 1] chargers of building b: [ch_off[b], ch_off[b + 1])
+    const int32_t* ch_action;        // [ch_n]
+    const int32_t* ch_cols;          // [ch_n][4]
+    const double* ch_pd;             // [ch_n][CL_NCHP]
+    const int32_t* wm_off;           // [B + 1]
+    const int32_t* wm_action;        // [wm_n]
+    const int32_t* wm_cols;          // [wm_n][4]
+    float* ev_sf;                    // [2][E * ev_n] soc[t-1], soc[t] entries of every vehicle
+    double* ev_sd;                   // [2][E * ev_n] degraded capacity, round-trip efficiency of the last charge
+    uint8_t* ev_flag;                // [E * ev_n] 1: the vehicle's battery has charged before (its efficiency / capacity are np.float64 from then on)
+    uint8_t* wm_flag;                // [E * wm_n] 1: a cycle was started in the current window
     // building-sharded districts (cl_exchange_*): this handle owns SOME buildings of every env; the per-env district sums are completed
     // inside the step by an all-gather of the ranks' partial sums through peer memory (NVLink): every (quantity, env) value travels as
     // ONE 8-byte {value, epoch} store into every peer's slot array - data and flag in one NVLink transaction, no fence, no second
@@ -370,6 +387,40 @@ __device__ __forceinline__ float solar_penalty_reward(const RewardIn& r) {
     return reward;
 }
 
+// Electric_Vehicles_Reward_Function (citylearn/reward_function.py:389-523): what `electric_vehicles_chargers_dict` holds per charger at t
+struct ChargerInfo { bool conn; float kwh, soc_now; double soc_prev, cap, min_cap, req, hrs, max_c, max_d; };
+__device__ __forceinline__ float ev_reward(const ChargerInfo* ch, int n, float net, float district_net, int t) {
+    if (n == 0) return 0.f;                                             // a building without chargers is rewarded 0 (:421-422)
+    const double be = -(double)net;
+    const double sg = be > 0 ? 1.0 : (be < 0 ? -1.0 : 0.0);
+    const double marl = sg * 0.01 * (be * be) * fmax(0.0, (double)district_net);
+    const double mult = 1.0 / (1.0 + fabs(marl));
+    const double w_limits = -2.0, w_impossible = -10.0, w_under = -5.0, w_close = 10.0, w_self = 5.0, w_extra = 5.0;
+    double total = 0.0;
+    for (int i = 0; i < n; ++i) {
+        const ChargerInfo& c = ch[i];
+        if (!c.conn) continue;                                          // (its last_charged_kwh reads 0.0: `no_car_charging` never fires)
+        double s = 0.0;
+        const double kwh = (double)c.kwh;
+        // soc[t-1] * capacity + kWh: float32 arithmetic on the np.float32 entry, float64 on the python-float initial SOC at t == 0
+        const double cur = t > 0 ? (double)((float)c.soc_prev * (float)c.cap + c.kwh) : c.soc_prev * c.cap + kwh;
+        if (cur > c.cap || cur < c.min_cap) s += w_limits * mult;
+        const double diff = (double)c.soc_now - c.req, diff_kwh = diff * c.cap;
+        const double max_c = c.max_c * c.hrs, max_d = c.max_d * c.hrs;
+        if (diff_kwh > max_c) s += w_impossible * mult;
+        if (c.hrs == 0.0) {
+            if (-0.25 < diff && diff <= -0.10) s += 2 * w_under * mult;
+            else if (diff <= -0.25) s += (w_under * w_under) * mult;
+            else if (-0.10 < diff && diff <= 0.10) s += w_close * mult;
+        }
+        if (fabs(diff_kwh) <= fmax(max_c, max_d)) s += w_close * mult * (1.0 / (c.hrs + 0.1));
+        if (kwh > 0 && net < 0.f) s += w_extra * mult; else if (kwh < 0 && net < 0.f) s += -0.5 * w_extra * mult;
+        if (kwh < 0 && net > 0.f) s += w_self * mult; else if (kwh > 0 && net > 0.f) s += -0.5 * w_self * mult;
+        total += s;
+    }
+    return (float)total;
+}
+
 __device__ __forceinline__ float unit_reward(int reward_id, const float* rp, const RewardIn& r) {
     switch (reward_id) {
         case CL_REWARD_DEFAULT: {
@@ -491,7 +542,7 @@ __device__ __forceinline__ void write_obs_general(const Dev& d, float* obs, int 
         float v;
         if (ds.x == CL_OBS_TS) {
             const int row = __ldg(d.start + e0 + e_l) + t_obs;
-            v = __ldg(d.table + (size_t)row * d.Wp + ds.y);
+            v = __ldg(d.table + (size_t)row * d.Wp + ((t_obs == 0 && ds.z > 0) ? ds.z - 1 : ds.y));   // (b: the column to read on an episode's first row)
         } else if (ds.x == CL_OBS_DYN) {
             v = dynbuf ? dynbuf[(e_l * nb + (ds.w - b0)) * CL_NDYN + ds.y] : 0.f;
         } else {
@@ -518,7 +569,7 @@ __host__ __device__ __forceinline__ SmemLayout smem_layout(int B, int Wp, int L,
     SmemLayout o;
     o.Lp = (L + 3) & ~3;
     int f = 16;                                  // 64 bytes of mbarriers: 3 time-row slots + 2 observation-row buffers
-    const int nc = n_curves > 0 ? n_curves : B;
+    const int nc = n_curves > 0 ? n_curves : B;       // (districts with vehicles pass B + ev_n: the vehicles' battery curves follow the buildings')
     o.curves = f; f += nc * kCurveTab * (rsize / 4);  // first: keeps doubles 8-byte aligned
     o.clut = f; f += nc * kCurveLutFloats;            // uniform-grid index of the curve abscissae (bytes)
     o.bsolar = f; f += ((2 * B * (rsize / 4)) + 3) & ~3;
@@ -544,7 +595,7 @@ __host__ __device__ __forceinline__ SmemLayout smem_layout(int B, int Wp, int L,
     return o;
 }
 static size_t smem_bytes(const Dev& d, int nt, bool with_dyn, int rsize) {
-    const SmemLayout o = smem_layout(d.tile_b, d.Wp, d.Lt, d.envs_per_block, nt, rsize, d.lstm_smem, d.tab_layout, d.fresh_slots, d.n_curves, d.kpi_smem);
+    const SmemLayout o = smem_layout(d.tile_b, d.Wp, d.Lt, d.envs_per_block, nt, rsize, d.lstm_smem, d.tab_layout, d.fresh_slots, d.ev_n > 0 ? d.tile_b + d.ev_n : d.n_curves, d.kpi_smem);
     size_t n = sizeof(float) * (size_t)o.end;
     if (with_dyn && !d.fresh_slots) n += sizeof(float) * (size_t)nt * CL_NDYN;
     return n;
@@ -689,7 +740,7 @@ __device__ __forceinline__ void kpi_push(double* a, double x);
 #define CL_DYN_MINBLOCKS 1
 #endif
 constexpr int kDynMaxT = CL_DYN_MAXT;
-template <typename R, bool THERMAL, bool DYNAMICS, int MAXT, bool WIDE = false, bool KPI = false>
+template <typename R, bool THERMAL, bool DYNAMICS, int MAXT, bool WIDE = false, bool KPI = false, bool EVD = false>
 __global__ void __launch_bounds__(MAXT, (DYNAMICS && MAXT == CL_DYN_MAXT) ? CL_DYN_MINBLOCKS : 1) advance_kernel(Dev d, int t0, int K, const float* __restrict__ actions, float* __restrict__ obs,
                                                         float* __restrict__ reward, float* __restrict__ district, float* __restrict__ trace) {
     extern __shared__ __align__(16) float smf[];
@@ -712,7 +763,7 @@ __global__ void __launch_bounds__(MAXT, (DYNAMICS && MAXT == CL_DYN_MAXT) ? CL_D
     const int nb = WIDE ? min(TBs, B - b0) : B;
     const int k0 = WIDE ? __ldg(d.tile_k + rank) : 0, k1 = WIDE ? __ldg(d.tile_k + rank + 1) : d.L;
     const int Ltile = k1 - k0;
-    const SmemLayout lo = smem_layout(TBs, Wp, WIDE ? d.Lt : d.L, epb, nt, (int)sizeof(R), DYNAMICS ? d.lstm_smem : 0, d.tab_layout, d.fresh_slots, d.n_curves, d.kpi_smem);
+    const SmemLayout lo = smem_layout(TBs, Wp, WIDE ? d.Lt : d.L, epb, nt, (int)sizeof(R), DYNAMICS ? d.lstm_smem : 0, d.tab_layout, d.fresh_slots, d.ev_n > 0 ? TBs + d.ev_n : d.n_curves, d.kpi_smem);
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(smf);
     R* scurves = reinterpret_cast<R*>(smf + lo.curves);
     uint8_t* s_clut = reinterpret_cast<uint8_t*>(smf + lo.clut);
@@ -744,7 +795,8 @@ __global__ void __launch_bounds__(MAXT, (DYNAMICS && MAXT == CL_DYN_MAXT) ? CL_D
     const bool fresh_tab = obs != nullptr && uniform && !d.stale && d.obs_tab != nullptr && d.fresh_slots;
     const bool want_dyn = (!d.stale && obs != nullptr) && !fresh_tab;      // general writer (per-env windows, no table)
     const bool tmpl_path = obs != nullptr && uniform && d.stale;
-    const bool need_dsum = d.reward_id == CL_REWARD_MARL && reward != nullptr;
+    const bool need_dsum = (d.reward_id == CL_REWARD_MARL || d.reward_id == CL_REWARD_ELECTRIC_VEHICLES) && reward != nullptr;
+    constexpr bool has_ev = EVD && !WIDE && !DYNAMICS;                  // chargers / washing machines: a separate instantiation (like KPI)
     const bool fused_reward = reward != nullptr && d.reward_id >= 0;
     const bool central_sync = fused_reward && d.central;
     const int Rdim = d.central ? 1 : B;
@@ -773,28 +825,37 @@ __global__ void __launch_bounds__(MAXT, (DYNAMICS && MAXT == CL_DYN_MAXT) ? CL_D
         // per building: [PE_X 8][PE_Y 8][CP_X 8][CP_Y 8][PE_RW 8][CP_RW 8] (SmemCurves): x entries beyond the curve's points are
         // +inf, RW[k] = refined reciprocal of the segment width x[k+1] - x[k]
         const auto* P = PSel<R>::p(d) + CL_P_PE_X0 * B;
-        const int ncv = d.n_curves > 0 ? d.n_curves : nb;      // distinct tables of the district, or one per building of the tile
+        // distinct tables of the district, or one per building of the tile - followed by the vehicles' battery curves (tables nb ..)
+        const int ncv = (d.n_curves > 0 ? d.n_curves : nb) + d.ev_n;
+        const int nbt = ncv - d.ev_n;
+        auto cpar = [&](int ci, int jj) -> R {          // entry jj of [PE_X 8][PE_Y 8][CP_X 8][CP_Y 8] of table ci
+            if (ci >= nbt) return (R)__ldg(d.ev_pd + (size_t)(ci - nbt) * CL_NPARAM + CL_P_PE_X0 + jj);
+            return (R)__ldg(P + jj * B + (d.n_curves > 0 ? __ldg(d.curve_rep + ci) : b0 + ci));
+        };
+        auto cnum = [&](int ci, int which) -> int {
+            if (ci >= nbt) return __ldg(d.ev_ip + (ci - nbt) * 2 + which);
+            return __ldg(d.ip + (which ? CL_IP_CP_N : CL_IP_PE_N) * B + (d.n_curves > 0 ? __ldg(d.curve_rep + ci) : b0 + ci));
+        };
         for (int i = tid; i < ncv * kCurveTab; i += nt) {
             const int ci = i / kCurveTab, j = i % kCurveTab;
-            const int bb = d.n_curves > 0 ? __ldg(d.curve_rep + ci) : b0 + ci;
             R v;
             if (j < 4 * CL_MAX_CURVE) {
-                v = (R)__ldg(P + j * B + bb);
+                v = cpar(ci, j);
                 const int which = j >> 4, k = j & 7;
-                if (!(j & 8) && k >= __ldg(d.ip + (which ? CL_IP_CP_N : CL_IP_PE_N) * B + bb)) v = Num<R>::inf();
+                if (!(j & 8) && k >= cnum(ci, which)) v = Num<R>::inf();
             } else {
                 const int which = (j - 4 * CL_MAX_CURVE) >> 3, k = j & 7;
-                const int n = __ldg(d.ip + (which ? CL_IP_CP_N : CL_IP_PE_N) * B + bb);
+                const int n = cnum(ci, which);
                 v = (R)0;
-                if (k + 1 < n) v = make_divisor((R)__ldg(P + (which * 16 + k + 1) * B + bb) - (R)__ldg(P + (which * 16 + k) * B + bb)).r;
+                if (k + 1 < n) v = make_divisor(cpar(ci, which * 16 + k + 1) - cpar(ci, which * 16 + k)).r;
             }
             scurves[i] = v;
         }
         if (d.curve_lut != nullptr) {
-            const uint32_t* src = reinterpret_cast<const uint32_t*>(d.curve_lut);
+            const uint32_t* src = reinterpret_cast<const uint32_t*>(d.curve_lut);       // [B + ev_n] indices: buildings, then vehicles
             for (int i = tid; i < ncv * kCurveLutFloats; i += nt) {
                 const int ci = i / kCurveLutFloats, j = i - ci * kCurveLutFloats;
-                const int bb = d.n_curves > 0 ? __ldg(d.curve_rep + ci) : b0 + ci;
+                const int bb = ci >= nbt ? B + (ci - nbt) : (d.n_curves > 0 ? __ldg(d.curve_rep + ci) : b0 + ci);
                 reinterpret_cast<uint32_t*>(s_clut)[i] = __ldg(src + (size_t)bb * kCurveLutFloats + j);
             }
         }
@@ -975,12 +1036,15 @@ __global__ void __launch_bounds__(MAXT, (DYNAMICS && MAXT == CL_DYN_MAXT) ? CL_D
             } else if (obs != nullptr && want_dyn && k + 1 < K) {
                 __syncthreads();
             }
+            if (has_ev && k + 1 < K) __syncthreads();
             continue;
         }
 
         // ---------------- physics warps ----------------
         UnitResult<R> o;
         RewardIn ri;
+        ChargerInfo chi[CL_MAX_CHARGERS_PER_BUILDING];
+        int n_chi = 0;
         if (active) {
             UnitInputs<R> in;
             load_inputs<R, THERMAL>(d, c, row, b, t, in, uniform);
@@ -991,6 +1055,80 @@ __global__ void __launch_bounds__(MAXT, (DYNAMICS && MAXT == CL_DYN_MAXT) ? CL_D
                 // partial-load control is live once the input window is full (building.py:3108, 3144)
                 in.control_cooling_demand = (c.a_cd >= 0 || c.a_coh >= 0);
                 in.control_heating_demand = (c.a_hd >= 0 || c.a_coh >= 0);
+            }
+            if (has_ev) {
+                // chargers, then washing machines (appended to the priority list, building.py:1582-1604; they neither use nor change
+                // the building's flexibility, so running them before the building's own devices gives the same values)
+                float ch_tot = 0.f, wm_tot = 0.f;
+                const float* arow = actions + ((size_t)k * d.E + e) * d.A;
+                const size_t EV = (size_t)d.E * d.ev_n;
+                const int tab0 = d.n_curves > 0 ? d.n_curves : nb;     // vehicles' curve tables follow the buildings'
+                for (int kk = __ldg(d.ch_off + b); kk < __ldg(d.ch_off + b + 1); ++kk) {
+                    const int4 cc = __ldg(reinterpret_cast<const int4*>(d.ch_cols) + kk);
+                    const bool conn = row[cc.x] > 0.f;
+                    const int v = conn ? (int)row[cc.y] : 0;
+                    const int slot = __ldg(d.ch_action + kk);
+                    double a = 0.0;
+                    if (slot >= 0) {
+                        float av = __ldg(arow + slot);
+                        if (d.act_range != nullptr) av = av * __ldg(d.act_range + slot) + __ldg(d.act_low + slot);
+                        a = (double)av;
+                    }
+                    const double* qp = d.ch_pd + (size_t)kk * CL_NCHP;
+                    ChargerParams<R> q;
+                    q.max_c = (R)__ldg(qp + CL_CH_MAX_C); q.min_c = (R)__ldg(qp + CL_CH_MIN_C); q.max_d = (R)__ldg(qp + CL_CH_MAX_D);
+                    q.min_d = (R)__ldg(qp + CL_CH_MIN_D); q.eff = (R)__ldg(qp + CL_CH_EFF);
+                    q.c_n = (int)__ldg(qp + CL_CH_C_N); q.d_n = (int)__ldg(qp + CL_CH_D_N); q.curves = qp + CL_CH_C_X0;
+                    const double* ep = d.ev_pd + (size_t)v * CL_NPARAM;
+                    const size_t i = (size_t)e * d.ev_n + v;
+                    BuildingParams<R> evp;
+                    UnitState<R> evs;
+                    evp.bat_capacity = (R)__ldg(ep + CL_P_BAT_CAPACITY); evp.bat_pnom = (R)__ldg(ep + CL_P_BAT_NOMINAL_POWER);
+                    evp.bat_loss = (R)__ldg(ep + CL_P_BAT_LOSS); evp.bat_clc = (R)__ldg(ep + CL_P_BAT_CLC); evp.bat_dod = (R)__ldg(ep + CL_P_BAT_DOD);
+                    evp.ratio = (R)__ldg(ep + CL_P_TIME_STEP_RATIO); evp.hours = (R)__ldg(ep + CL_P_HOURS_PER_STEP); evp.flags = 0;
+                    evp.pe_n = __ldg(d.ev_ip + v * 2); evp.cp_n = __ldg(d.ev_ip + v * 2 + 1);
+                    derive_params(evp);
+                    // Battery.charge starts from the soc[t-1] entry - the soc[0] entry at t == 0 (energy_model.py:662-666, 1046)
+                    evs.soc_b = (R)(t == 0 ? d.ev_sf[EV + i] : d.ev_sf[i]); evs.cap_deg = (R)d.ev_sd[i]; evs.rte_b = (R)d.ev_sd[EV + i];
+                    evs.soc_cs = evs.soc_hs = evs.soc_ds = (R)0;
+                    const SmemCurves<R> evc = {scurves + (size_t)(tab0 + v) * kCurveTab, d.curve_nmax,
+                                               d.curve_lut != nullptr ? s_clut + (size_t)(tab0 + v) * (2 * kCurveLutStride) : nullptr};
+                    float kwh; bool charged;
+                    const float ecc = charger_step<R>(q, a, conn, evp, evc, d.ev_flag[i] == 0, evs, (double)evp.hours, kwh, charged);
+                    if (charged) {
+                        d.ev_sf[EV + i] = (float)evs.soc_b; d.ev_sd[i] = (double)evs.cap_deg; d.ev_sd[EV + i] = (double)evs.rte_b; d.ev_flag[i] = 1;
+                    }
+                    ch_tot = ch_tot + ecc;                                          // `0 + float32 + ...` in charger order (building.py:2654-2661)
+                    if (n_chi < CL_MAX_CHARGERS_PER_BUILDING) {
+                        ChargerInfo& ci = chi[n_chi++];
+                        ci.conn = conn; ci.kwh = conn ? kwh : 0.f; ci.soc_now = d.ev_sf[EV + i];
+                        ci.soc_prev = t == 0 ? __ldg(ep + CL_P_BAT_INITIAL_SOC) : (double)d.ev_sf[i];
+                        ci.cap = __ldg(ep + CL_P_BAT_CAPACITY); ci.min_cap = (1.0 - __ldg(ep + CL_P_BAT_DOD)) * ci.cap;
+                        ci.req = (double)row[cc.z]; ci.hrs = (double)row[cc.w]; ci.max_c = (double)q.max_c; ci.max_d = (double)q.max_d;
+                    }
+                }
+                for (int kk = __ldg(d.wm_off + b); kk < __ldg(d.wm_off + b + 1); ++kk) {
+                    // WashingMachine.next_time_step / start_cycle (energy_model.py:1289-1327)
+                    const int4 wc = __ldg(reinterpret_cast<const int4*>(d.wm_cols) + kk);
+                    const int st = (int)row[wc.x], en = (int)row[wc.y];
+                    const size_t wi = (size_t)e * d.wm_n + kk;
+                    bool init = d.wm_flag[wi] != 0;
+                    if (t > 0) {
+                        const float* prow = d.table + (size_t)(start_e + t - 1) * Wp;   // a new window re-arms the machine
+                        if ((int)__ldg(prow + wc.x) != st || (int)__ldg(prow + wc.y) != en) init = false;
+                    }
+                    const int slot = __ldg(d.wm_action + kk);
+                    if (slot >= 0) {
+                        float av = __ldg(arow + slot);
+                        if (d.act_range != nullptr) av = av * __ldg(d.act_range + slot) + __ldg(d.act_low + slot);
+                        if (!init && av > 0.f && st != -1 && en != -1 && st <= t && t <= en && (int)row[wc.w] > 0) {
+                            wm_tot = wm_tot + row[wc.z];                            // every entry of the load profile lands in ec[t]
+                            init = true;
+                        }
+                    }
+                    d.wm_flag[wi] = init ? 1 : 0;
+                }
+                in.has_ev = true; in.chargers_ec = (R)ch_tot; in.machines_ec = (R)wm_tot;
             }
             CL_STAMP(2);
             unit_step<R, THERMAL>(c.p, curves, t, in, s, o);
@@ -1139,12 +1277,39 @@ __global__ void __launch_bounds__(MAXT, (DYNAMICS && MAXT == CL_DYN_MAXT) ? CL_D
                 kpi_push(s_kenv + (size_t)(le * 2 + 1) * CL_NKPI_ENV, tot);
             }
         }
+        if (has_ev && d.ev_n > 0) {
+            // next_time_step for the vehicles (citylearn.py:1336-1351): the soc[t+1] entry starts at 0, then the row's compiled operation
+            // (ev.compile_schedule): drift of an away vehicle, pre-connection SOC, arrival SOC of a new connection.  Every charger of the
+            // block has finished step t (S1); the barrier at the end of the iteration publishes the entries to step t + 1.
+            const size_t EV = (size_t)d.E * d.ev_n;
+            const int tn = t + 1;
+            for (int idx = tid; idx < n_env * d.ev_n; idx += np_) {
+                const int le = idx / d.ev_n, v = idx - le * d.ev_n;
+                const size_t i = (size_t)(e0 + le) * d.ev_n + v;
+                const float prev = d.ev_sf[EV + i];
+                float cur = 0.f;
+                if (tn <= d.T - 1) {
+                    const int4 ec = __ldg(reinterpret_cast<const int4*>(d.ev_cols) + v);
+                    const float* rn = uniform ? row_next : d.table + (size_t)(start_e + tn) * Wp;
+                    if (tn + 1 < d.T) {                                   // simulate_unconnected_ev_soc returns early on the last step
+                        const double dr = __ldg(d.ev_drift + (size_t)(d.start0 + tn) * d.ev_n + v);
+                        if (dr == dr) cur = (float)fmin(fmax((double)prev * dr, 0.0), 1.0);
+                        const float sm = rn[ec.y];
+                        if (sm == sm) cur = sm;
+                    }
+                    const float as = rn[ec.x];
+                    if (as == as) cur = as;
+                }
+                d.ev_sf[i] = prev; d.ev_sf[EV + i] = cur;
+            }
+        }
         if (need_dsum) __syncthreads();                                        // S2 only when a reward reads the district sum
         if (fused_reward) {
             float r = 0.f;
             if (active) {
                 if (need_dsum) ri.district_net = s_dsum[pb * epb + e_l];
-                r = unit_reward(d.reward_id, d.rp, ri);
+                if constexpr (has_ev) r = d.reward_id == CL_REWARD_ELECTRIC_VEHICLES ? ev_reward(chi, n_chi, ri.net, ri.district_net, t) : unit_reward(d.reward_id, d.rp, ri);
+                else r = unit_reward(d.reward_id, d.rp, ri);
             }
             float* rk = reward + (size_t)k * d.E * Rdim;
             if (d.central && WIDE) {
@@ -1186,6 +1351,7 @@ __global__ void __launch_bounds__(MAXT, (DYNAMICS && MAXT == CL_DYN_MAXT) ? CL_D
             write_obs_general(d, obs + (size_t)k * d.E * d.L, e0, n_env, t + 1, want_dyn ? s_dynbuf : nullptr, tid, np_, k0, k1, b0, nb);
             if (want_dyn && k + 1 < K) __syncthreads();                         // dynbuf is single-buffered
         }
+        if (has_ev && k + 1 < K) __syncthreads();                               // the vehicles' soc[t+1] entries are in place for step t + 1
     }
 #ifdef CL_PHASE_TIMING
     { const int k = K - 1; CL_STAMP(7); }
@@ -1309,7 +1475,7 @@ __global__ void __launch_bounds__(MAXT) reset_kernel(Dev d, float* __restrict__ 
     extern __shared__ __align__(16) float smf[];
     const int nt = blockDim.x, tid = threadIdx.x;
     const int B = d.B, epb = d.envs_per_block;
-    const SmemLayout lo = smem_layout(d.tile_b, d.Wp, d.Lt, epb, nt, (int)sizeof(R), d.lstm_smem, d.tab_layout, d.fresh_slots, d.n_curves, d.kpi_smem);
+    const SmemLayout lo = smem_layout(d.tile_b, d.Wp, d.Lt, epb, nt, (int)sizeof(R), d.lstm_smem, d.tab_layout, d.fresh_slots, d.ev_n > 0 ? d.tile_b + d.ev_n : d.n_curves, d.kpi_smem);
     float* s_dynbuf = smf + lo.dynbuf;
     // building tiles (wide districts): block (group, rank) owns buildings [b0, b0 + nb) and observation columns [k0, k1)
     const int rank = (int)blockIdx.x % d.tiles;
@@ -1344,6 +1510,23 @@ __global__ void __launch_bounds__(MAXT) reset_kernel(Dev d, float* __restrict__ 
             fill_dyn<R>(c.p, s, o, (R)row[c.c_tin], s_dynbuf + tid * CL_NDYN);
         }
     }
+    if ((d.ev_n + d.wm_n) > 0 && rank == 0) {
+        // ElectricVehicle.reset + associate_chargers_to_electric_vehicles at t = 0 (citylearn.py:1871-1874): soc[0] = initial SOC, replaced
+        // by the arrival SOC of a vehicle that is plugged in on the episode's first row
+        const size_t EV = (size_t)d.E * d.ev_n;
+        for (int idx = tid; idx < n_env * d.ev_n; idx += nt) {
+            const int le = idx / d.ev_n, v = idx - le * d.ev_n;
+            const size_t i = (size_t)(e0 + le) * d.ev_n + v;
+            const double* ep = d.ev_pd + (size_t)v * CL_NPARAM;
+            const float t0v = __ldg(d.table + (size_t)__ldg(d.start + e0 + le) * d.Wp + __ldg(d.ev_cols + v * 4 + 3));
+            d.ev_sf[i] = 0.f;
+            d.ev_sf[EV + i] = t0v == t0v ? t0v : (float)__ldg(ep + CL_P_BAT_INITIAL_SOC);
+            d.ev_sd[i] = __ldg(ep + CL_P_BAT_CAPACITY);
+            d.ev_sd[EV + i] = sqrt(__ldg(ep + CL_P_BAT_EFFICIENCY0));
+            d.ev_flag[i] = 0;
+        }
+        for (int idx = tid; idx < n_env * d.wm_n; idx += nt) d.wm_flag[(size_t)e0 * d.wm_n + idx] = 0;
+    }
     if (obs != nullptr) {
         __syncthreads();
         write_obs_general(d, obs, e0, n_env, 0, s_dynbuf, tid, nt, k0, k1, b0, nb);
@@ -1376,6 +1559,7 @@ struct cl_env {
     int32_t* x_err_dev = nullptr;
     std::vector<void*> x_opened;     // cudaIpcOpenMemHandle mappings to close
     unsigned x_epoch = 0;            // steps exchanged so far
+    size_t ev_sf_floats = 0, ev_sd_doubles = 0, ev_flag_bytes = 0, wm_flag_bytes = 0;   // vehicle / washing-machine state (districts with cl_ev_desc)
     std::vector<float> lstm_packed;  // host copy of the packed LSTM weights when they fit the constant bank (<= kLstmConstBuildings buildings)
     int n_sm = 148;
     int T = 0;
@@ -1457,6 +1641,10 @@ static void ensure_smem_optin(size_t smem) {
     OPTIN((advance_kernel<double, false, false, M, false, true>)); OPTIN((advance_kernel<double, true, false, M, false, true>))
     OPTINK(512); OPTINK(1024);
 #undef OPTINK
+#define OPTINE(M) OPTIN((advance_kernel<float, false, false, M, false, false, true>)); OPTIN((advance_kernel<float, true, false, M, false, false, true>)); \
+    OPTIN((advance_kernel<double, false, false, M, false, false, true>)); OPTIN((advance_kernel<double, true, false, M, false, false, true>))
+    OPTINE(512); OPTINE(1024);
+#undef OPTINE
     OPTINA(512); OPTINA(1024); OPTIN((advance_kernel<float, true, true, kDynMaxT>)); OPTIN((advance_kernel<double, true, true, kDynMaxT>)); OPTIN4(reset_kernel, 512); OPTIN4(reset_kernel, 1024);
     OPTIN((advance_kernel<float, false, false, 512, true>)); OPTIN((advance_kernel<float, true, false, 512, true>));
     OPTIN((advance_kernel<double, false, false, 512, true>)); OPTIN((advance_kernel<double, true, false, 512, true>));
@@ -1476,6 +1664,9 @@ extern "C" int cl_create(const cl_district_desc* desc, cl_env** out) {
     if (desc->n_buildings > 8 * 480) return fail(CL_ERR_UNSUPPORTED, "cl_create: more than 3840 buildings per district (8 tiles of 480) not supported");
     if (!desc->table || !desc->params || !desc->iparams || !desc->obs_desc) return fail(CL_ERR_INVALID, "cl_create: null table/params");
     if (desc->precision != CL_PRECISION_FP32 && desc->precision != CL_PRECISION_FP64) return fail(CL_ERR_INVALID, "cl_create: bad precision");
+    if (desc->reward_id < CL_REWARD_NONE || desc->reward_id > CL_REWARD_ELECTRIC_VEHICLES) return fail(CL_ERR_INVALID, "cl_create: unknown reward_id");
+    if (desc->reward_id == CL_REWARD_ELECTRIC_VEHICLES && !(desc->ev && desc->ev->n_chargers + desc->ev->n_machines > 0))
+        return fail(CL_ERR_INVALID, "cl_create: CL_REWARD_ELECTRIC_VEHICLES needs a district with chargers (cl_district_desc.ev)");
     cl_env* env = new (std::nothrow) cl_env();
     if (!env) return fail(CL_ERR_INVALID, "cl_create: out of host memory");
     Dev& d = env->d;
@@ -1506,13 +1697,22 @@ extern "C" int cl_create(const cl_district_desc* desc, cl_env** out) {
     {
         // uniform-grid index of the curve abscissae (unit_physics.cuh, SmemCurves): usable when no cell holds two points of a curve.
         // The cells are those of the values the kernel compares, i.e. of the float-rounded abscissae in CL_PRECISION_FP32.
-        std::vector<uint8_t> lut((size_t)B * 2 * kCurveLutStride, 0);
+        const int n_ev_l = desc->ev ? desc->ev->n_ev : 0;          // the vehicles' battery curves follow the buildings'
+        std::vector<uint8_t> lut((size_t)(B + n_ev_l) * 2 * kCurveLutStride, 0);
         bool ok = std::getenv("CL_B200_NO_CURVE_LUT") == nullptr;
         for (int b = 0; b < B && ok; ++b)
             for (int w = 0; w < 2 && ok; ++w)
                 ok = build_curve_lut(desc->params + (size_t)(w ? CL_P_CP_X0 : CL_P_PE_X0) * B + b, (size_t)B,
                                      desc->iparams[(w ? CL_IP_CP_N : CL_IP_PE_N) * B + b], desc->precision == CL_PRECISION_FP32,
                                      &lut[((size_t)b * 2 + w) * kCurveLutStride]);
+        for (int v = 0; v < n_ev_l && ok; ++v)
+            for (int w = 0; w < 2 && ok; ++w) {
+                const int n = desc->ev->ev_iparams[v * 2 + w];
+                if (n < 2 || n > CL_MAX_CURVE) { delete env; return fail(CL_ERR_INVALID, "cl_create: vehicle battery curves need 2 .. 8 points"); }
+                d.curve_nmax = std::max(d.curve_nmax, n);
+                ok = build_curve_lut(desc->ev->ev_params + (size_t)v * CL_NPARAM + (w ? CL_P_CP_X0 : CL_P_PE_X0), 1, n,
+                                     desc->precision == CL_PRECISION_FP32, &lut[((size_t)(B + v) * 2 + w) * kCurveLutStride]);
+            }
         if (ok) {
             uint8_t* p = nullptr;
             int rc = dev_copy(env, lut.data(), lut.size(), &p);
@@ -1535,7 +1735,7 @@ extern "C" int cl_create(const cl_district_desc* desc, cl_env** out) {
             if (found < 0) { if (rep.size() >= 64) { rep.clear(); break; } found = (int)rep.size(); rep.push_back(b); }
             cid[(size_t)b] = found;
         }
-        if (!rep.empty() && std::getenv("CL_B200_NO_CURVE_SHARING") == nullptr) {
+        if (!rep.empty() && std::getenv("CL_B200_NO_CURVE_SHARING") == nullptr && !(desc->ev && desc->ev->n_ev > 0)) {
             int32_t *pc = nullptr, *pr = nullptr;
             int rc = dev_copy(env, cid.data(), cid.size(), &pc);
             if (!rc) rc = dev_copy(env, rep.data(), rep.size(), &pr);
@@ -1668,6 +1868,70 @@ extern "C" int cl_create(const cl_district_desc* desc, cl_env** out) {
         if (cudaMalloc(&p, sizeof(int32_t)) != cudaSuccess) { cl_destroy(env); return fail(CL_ERR_CUDA, "cl_create: time-step allocation failed"); }
         env->allocs.push_back(p); env->t_dev = static_cast<int32_t*>(p); d.t_dev = env->t_dev;
         cudaMemset(p, 0, sizeof(int32_t));
+    }
+    if (desc->ev != nullptr && (desc->ev->n_chargers > 0 || desc->ev->n_machines > 0)) {
+        // electric vehicles / chargers / washing machines (cl_ev_desc)
+        const cl_ev_desc& ev = *desc->ev;
+        if (ev.n_ev < 0 || ev.n_chargers < 0 || ev.n_machines < 0) { cl_destroy(env); return fail(CL_ERR_INVALID, "cl_create: negative vehicle / charger / machine count"); }
+        if (any_dyn || !d.stale) { cl_destroy(env); return fail(CL_ERR_UNSUPPORTED, "cl_create: districts with vehicles run with reference-parity (stale) observations and without LSTM dynamics"); }
+        if (B > 480) { cl_destroy(env); return fail(CL_ERR_UNSUPPORTED, "cl_create: districts with vehicles are not building-tiled (at most 480 buildings)"); }
+        if (ev.n_chargers > 0 && (ev.n_ev < 1 || !ev.ev_params || !ev.ev_iparams || !ev.ev_cols || !ev.ev_drift || !ev.ch_building || !ev.ch_action || !ev.ch_cols || !ev.ch_params))
+            { cl_destroy(env); return fail(CL_ERR_INVALID, "cl_create: incomplete cl_ev_desc"); }
+        if (ev.n_machines > 0 && (!ev.wm_building || !ev.wm_action || !ev.wm_cols)) { cl_destroy(env); return fail(CL_ERR_INVALID, "cl_create: incomplete cl_ev_desc (washing machines)"); }
+        std::vector<int32_t> ch_off((size_t)B + 1, 0), wm_off((size_t)B + 1, 0);
+        for (int k = 0; k < ev.n_chargers; ++k) {
+            const int b = ev.ch_building[k];
+            if (b < 0 || b >= B || (k > 0 && b < ev.ch_building[k - 1])) { cl_destroy(env); return fail(CL_ERR_INVALID, "cl_create: chargers must be listed in building order"); }
+            ch_off[(size_t)b + 1]++;
+            for (int j = 0; j < 4; ++j) if (ev.ch_cols[k * 4 + j] < 0 || ev.ch_cols[k * 4 + j] >= d.W) { cl_destroy(env); return fail(CL_ERR_INVALID, "cl_create: charger column outside the table"); }
+            if (ev.ch_action[k] >= d.A) { cl_destroy(env); return fail(CL_ERR_INVALID, "cl_create: charger action slot outside the action vector"); }
+        }
+        for (int k = 0; k < ev.n_machines; ++k) {
+            const int b = ev.wm_building[k];
+            if (b < 0 || b >= B || (k > 0 && b < ev.wm_building[k - 1])) { cl_destroy(env); return fail(CL_ERR_INVALID, "cl_create: washing machines must be listed in building order"); }
+            wm_off[(size_t)b + 1]++;
+            for (int j = 0; j < 4; ++j) if (ev.wm_cols[k * 4 + j] < 0 || ev.wm_cols[k * 4 + j] >= d.W) { cl_destroy(env); return fail(CL_ERR_INVALID, "cl_create: washing-machine column outside the table"); }
+            if (ev.wm_action[k] >= d.A) { cl_destroy(env); return fail(CL_ERR_INVALID, "cl_create: washing-machine action slot outside the action vector"); }
+        }
+        for (int b = 0; b < B; ++b) {
+            if (ch_off[(size_t)b + 1] > CL_MAX_CHARGERS_PER_BUILDING) { cl_destroy(env); return fail(CL_ERR_UNSUPPORTED, "cl_create: more than CL_MAX_CHARGERS_PER_BUILDING chargers on one building"); }
+            ch_off[(size_t)b + 1] += ch_off[(size_t)b]; wm_off[(size_t)b + 1] += wm_off[(size_t)b];
+        }
+        for (int v = 0; v < ev.n_ev; ++v) {
+            if (ev.ev_params[(size_t)v * CL_NPARAM + CL_P_TIME_STEP_RATIO] != 1.0) { cl_destroy(env); return fail(CL_ERR_UNSUPPORTED, "cl_create: vehicles need time_step_ratio == 1"); }
+            for (int j = 0; j < 4; ++j) if (j != 2 && (ev.ev_cols[v * 4 + j] < 0 || ev.ev_cols[v * 4 + j] >= d.W)) { cl_destroy(env); return fail(CL_ERR_INVALID, "cl_create: vehicle column outside the table"); }
+        }
+        double *evp = nullptr, *drift = nullptr, *chp = nullptr;
+        int32_t *evip = nullptr, *evc = nullptr, *cho = nullptr, *cha = nullptr, *chc = nullptr, *wmo = nullptr, *wma = nullptr, *wmc = nullptr;
+        const int32_t zero4[4] = {0, 0, 0, 0};
+        int rc = dev_copy(env, ev.ev_params, (size_t)ev.n_ev * CL_NPARAM, &evp);
+        if (!rc) rc = dev_copy(env, ev.ev_iparams, (size_t)ev.n_ev * 2, &evip);
+        if (!rc) rc = dev_copy(env, ev.ev_cols, (size_t)ev.n_ev * 4, &evc);
+        if (!rc) rc = dev_copy(env, ev.ev_drift, (size_t)d.n_rows * ev.n_ev, &drift);
+        if (!rc) rc = dev_copy(env, ch_off.data(), ch_off.size(), &cho);
+        if (!rc) rc = dev_copy(env, ev.n_chargers ? ev.ch_action : zero4, (size_t)ev.n_chargers, &cha);
+        if (!rc) rc = dev_copy(env, ev.n_chargers ? ev.ch_cols : zero4, (size_t)ev.n_chargers * 4, &chc);
+        if (!rc) rc = dev_copy(env, ev.ch_params, (size_t)ev.n_chargers * CL_NCHP, &chp);
+        if (!rc) rc = dev_copy(env, wm_off.data(), wm_off.size(), &wmo);
+        if (!rc) rc = dev_copy(env, ev.n_machines ? ev.wm_action : zero4, (size_t)ev.n_machines, &wma);
+        if (!rc) rc = dev_copy(env, ev.n_machines ? ev.wm_cols : zero4, (size_t)ev.n_machines * 4, &wmc);
+        if (rc) { cl_destroy(env); return rc; }
+        d.ev_n = ev.n_ev; d.ch_n = ev.n_chargers; d.wm_n = ev.n_machines;
+        d.ev_pd = evp; d.ev_ip = evip; d.ev_cols = evc; d.ev_drift = drift; d.ch_off = cho; d.ch_action = cha; d.ch_cols = chc; d.ch_pd = chp;
+        d.wm_off = wmo; d.wm_action = wma; d.wm_cols = wmc;
+        void* q = nullptr;
+        env->ev_sf_floats = (size_t)2 * d.E * std::max(ev.n_ev, 1); env->ev_sd_doubles = env->ev_sf_floats;
+        env->ev_flag_bytes = (size_t)d.E * std::max(ev.n_ev, 1); env->wm_flag_bytes = (size_t)d.E * std::max(ev.n_machines, 1);
+        if (cudaMalloc(&q, env->ev_sf_floats * sizeof(float)) != cudaSuccess) { cl_destroy(env); return fail(CL_ERR_CUDA, "cl_create: vehicle state allocation failed"); }
+        env->allocs.push_back(q); d.ev_sf = static_cast<float*>(q); cudaMemset(q, 0, env->ev_sf_floats * sizeof(float));
+        if (cudaMalloc(&q, env->ev_sd_doubles * sizeof(double)) != cudaSuccess) { cl_destroy(env); return fail(CL_ERR_CUDA, "cl_create: vehicle state allocation failed"); }
+        env->allocs.push_back(q); d.ev_sd = static_cast<double*>(q); cudaMemset(q, 0, env->ev_sd_doubles * sizeof(double));
+        if (cudaMalloc(&q, env->ev_flag_bytes) != cudaSuccess) { cl_destroy(env); return fail(CL_ERR_CUDA, "cl_create: vehicle state allocation failed"); }
+        env->allocs.push_back(q); d.ev_flag = static_cast<uint8_t*>(q); cudaMemset(q, 0, env->ev_flag_bytes);
+        if (cudaMalloc(&q, env->wm_flag_bytes) != cudaSuccess) { cl_destroy(env); return fail(CL_ERR_CUDA, "cl_create: washing-machine state allocation failed"); }
+        env->allocs.push_back(q); d.wm_flag = static_cast<uint8_t*>(q); cudaMemset(q, 0, env->wm_flag_bytes);
+    }
+    {
     }
     // launch geometry.  A block = whole envs x all B buildings (physics threads, rounded up to warps) + one helper warp.
     // Every block must be RESIDENT for the whole launch to run in one wave (the kernel is register-heavy: ~100-128 registers
@@ -1908,6 +2172,11 @@ static void launch_advance(cl_env* env, int t0, int K, const float* actions, flo
         return;
     }
     if constexpr (!DY) {
+        if (env->d.ch_n + env->d.wm_n > 0) {          // districts with electric vehicles / washing machines (cl_ev_desc)
+            if (nthreads <= 512) advance_kernel<R, TH, false, 512, false, false, true><<<env->blocks, nthreads, smem, st>>>(env->d, t0, K, actions, obs, reward, district, trace);
+            else advance_kernel<R, TH, false, 1024, false, false, true><<<env->blocks, nthreads, smem, st>>>(env->d, t0, K, actions, obs, reward, district, trace);
+            return;
+        }
         if (env->kpi_fused) {                         // online KPI accumulators inside the step (cl_kpi_enable)
             if (nthreads <= 512) advance_kernel<R, TH, false, 512, false, true><<<env->blocks, nthreads, smem, st>>>(env->d, t0, K, actions, obs, reward, district, trace);
             else advance_kernel<R, TH, false, 1024, false, true><<<env->blocks, nthreads, smem, st>>>(env->d, t0, K, actions, obs, reward, district, trace);
@@ -2018,6 +2287,7 @@ extern "C" int cl_reset(cl_env* env, const int32_t* episode_start, int32_t unifo
         env->launches++;
         d.uniform_start = 1; d.start0 = uniform_start;
     } else {
+        if (d.ch_n + d.wm_n > 0) return fail(CL_ERR_UNSUPPORTED, "cl_reset: districts with electric vehicles / washing machines use one episode window for all envs");
         CUDA_TRY(cudaMemcpyAsync(const_cast<int32_t*>(d.start), episode_start, sizeof(int32_t) * d.E, cudaMemcpyDeviceToDevice, st));
         d.uniform_start = 0; d.start0 = 0;
     }
@@ -2105,6 +2375,7 @@ extern "C" int cl_exchange_create(cl_env* env, int32_t n_ranks, int32_t rank, vo
     if (n_ranks < 2 || n_ranks > 64 || rank < 0 || rank >= n_ranks) return fail(CL_ERR_INVALID, "cl_exchange_create: need 2 <= n_ranks <= 64 and 0 <= rank < n_ranks");
     if (env->wide) return fail(CL_ERR_UNSUPPORTED, "cl_exchange_create: building-tiled (wide) districts are not building-sharded across GPUs");
     if (env->d.central) return fail(CL_ERR_UNSUPPORTED, "cl_exchange_create: central-agent reward sums are not exchanged; use decentralised rewards");
+    if (env->d.ch_n + env->d.wm_n > 0) return fail(CL_ERR_UNSUPPORTED, "cl_exchange_create: districts with electric vehicles / washing machines are not building-sharded");
     if (env->x_buf) return fail(CL_ERR_STATE, "cl_exchange_create: already created");
     if (env->kpi_unit) return fail(CL_ERR_UNSUPPORTED, "cl_exchange_create: online KPI accumulators need the whole district on one handle");
     // a block spins on its peers inside the step: every block of the launch must be resident (one wave), or blocks waiting for an SM
@@ -2198,6 +2469,16 @@ extern "C" int cl_obs_rows(cl_env* env, int32_t first_time_step, int32_t n_rows,
     return CL_OK;
 }
 
+extern "C" int cl_ev_read(cl_env* env, float* soc_prev_dev, float* soc_dev, cl_stream stream) {
+    if (!env) return fail(CL_ERR_INVALID, "cl_ev_read: null env");
+    if (env->d.ev_n < 1) return fail(CL_ERR_STATE, "cl_ev_read: the district has no electric vehicles");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t n = (size_t)env->d.E * env->d.ev_n;
+    if (soc_prev_dev) CUDA_TRY(cudaMemcpyAsync(soc_prev_dev, env->d.ev_sf, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (soc_dev) CUDA_TRY(cudaMemcpyAsync(soc_dev, env->d.ev_sf + n, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return CL_OK;
+}
+
 extern "C" int cl_time_step(const cl_env* env, int32_t* t) {
     if (!env || !t) return fail(CL_ERR_INVALID, "cl_time_step: null argument");
     if (env->device_time && env->t >= 0) {
@@ -2213,7 +2494,8 @@ extern "C" int cl_time_step(const cl_env* env, int32_t* t) {
 
 extern "C" int cl_state_size(const cl_env* env, size_t* bytes) {
     if (!env || !bytes) return fail(CL_ERR_INVALID, "cl_state_size: null argument");
-    *bytes = env->st_floats * sizeof(float) + env->dst_doubles * sizeof(double) + env->lst_floats * sizeof(float);
+    *bytes = env->st_floats * sizeof(float) + env->dst_doubles * sizeof(double) + env->lst_floats * sizeof(float)
+             + env->ev_sd_doubles * sizeof(double) + env->ev_sf_floats * sizeof(float) + env->ev_flag_bytes + env->wm_flag_bytes;
     return CL_OK;
 }
 
@@ -2228,6 +2510,13 @@ extern "C" int cl_get_state(cl_env* env, void* dst_dev, cl_stream stream) {
     CUDA_TRY(cudaMemcpyAsync(p, env->d.st, env->st_floats * sizeof(float), cudaMemcpyDeviceToDevice, st));
     p += env->st_floats * sizeof(float);
     if (env->lst_floats) CUDA_TRY(cudaMemcpyAsync(p, env->d.lst, env->lst_floats * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    p += env->lst_floats * sizeof(float);
+    if (env->ev_sf_floats) {      // vehicles / washing machines (the blob layout keeps 8-byte alignment: lst_floats and st_floats are even)
+        CUDA_TRY(cudaMemcpyAsync(p, env->d.ev_sd, env->ev_sd_doubles * sizeof(double), cudaMemcpyDeviceToDevice, st)); p += env->ev_sd_doubles * sizeof(double);
+        CUDA_TRY(cudaMemcpyAsync(p, env->d.ev_sf, env->ev_sf_floats * sizeof(float), cudaMemcpyDeviceToDevice, st)); p += env->ev_sf_floats * sizeof(float);
+        CUDA_TRY(cudaMemcpyAsync(p, env->d.ev_flag, env->ev_flag_bytes, cudaMemcpyDeviceToDevice, st)); p += env->ev_flag_bytes;
+        CUDA_TRY(cudaMemcpyAsync(p, env->d.wm_flag, env->wm_flag_bytes, cudaMemcpyDeviceToDevice, st));
+    }
     return CL_OK;
 }
 
@@ -2243,6 +2532,13 @@ extern "C" int cl_set_state(cl_env* env, const void* src_dev, int32_t time_step,
     CUDA_TRY(cudaMemcpyAsync(env->d.st, p, env->st_floats * sizeof(float), cudaMemcpyDeviceToDevice, st));
     p += env->st_floats * sizeof(float);
     if (env->lst_floats) CUDA_TRY(cudaMemcpyAsync(env->d.lst, p, env->lst_floats * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    p += env->lst_floats * sizeof(float);
+    if (env->ev_sf_floats) {
+        CUDA_TRY(cudaMemcpyAsync(env->d.ev_sd, p, env->ev_sd_doubles * sizeof(double), cudaMemcpyDeviceToDevice, st)); p += env->ev_sd_doubles * sizeof(double);
+        CUDA_TRY(cudaMemcpyAsync(env->d.ev_sf, p, env->ev_sf_floats * sizeof(float), cudaMemcpyDeviceToDevice, st)); p += env->ev_sf_floats * sizeof(float);
+        CUDA_TRY(cudaMemcpyAsync(env->d.ev_flag, p, env->ev_flag_bytes, cudaMemcpyDeviceToDevice, st)); p += env->ev_flag_bytes;
+        CUDA_TRY(cudaMemcpyAsync(env->d.wm_flag, p, env->wm_flag_bytes, cudaMemcpyDeviceToDevice, st));
+    }
     env->t = time_step;
     return publish_time(env, st);
 }
@@ -2277,6 +2573,7 @@ extern "C" int cl_kpi_enable(cl_env* env, int32_t enable) {
     if (!env) return fail(CL_ERR_INVALID, "cl_kpi_enable: null env");
     if (enable && env->dynamics) return fail(CL_ERR_UNSUPPORTED, "cl_kpi_enable: the `_without_storage` baseline does not apply to LSTM-dynamics districts (use evaluate() on a recorded history)");
     if (enable && env->d.x_n != 0) return fail(CL_ERR_UNSUPPORTED, "cl_kpi_enable: a building-sharded handle sees only its own buildings' baseline");
+    if (enable && (env->d.ch_n + env->d.wm_n) > 0) return fail(CL_ERR_UNSUPPORTED, "cl_kpi_enable: KPI accumulators do not cover districts with electric vehicles / washing machines");
     if (!enable) {
         CUDA_TRY(cudaDeviceSynchronize());
         if (env->kpi_unit) cudaFree(env->kpi_unit);

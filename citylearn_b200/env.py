@@ -221,6 +221,16 @@ class CityLearnEnv:
         self._sizes_act = [len(b.active_actions) for b in spec.buildings]
         self._track = (self.num_envs == 1) if track_episode_rewards is None else bool(track_episode_rewards)
         # per-step history of ONE env for evaluate() (the reference keeps full series for its single env)
+        # districts with electric vehicles / chargers / washing machines: the fused step only - reference-parity
+        # observations, built-in rewards, no KPI history (the reference's evaluate() adds charger cost functions this build does not have)
+        evd = spec.ev or {}
+        self._has_ev = bool(len(evd.get('chargers', ())) or len(evd.get('wms', ())))
+        if self._has_ev:
+            if not self.stale_observations:
+                raise NotImplementedError('districts with electric vehicles / washing machines need stale_observations=True')
+            if record_history or track_kpis or debug_trace:
+                raise NotImplementedError('record_history / track_kpis / debug_trace are not available for districts with electric vehicles / washing machines')
+            record_history = False
         self._record = (self.num_envs == 1) if record_history is None else bool(record_history)
         self._history_env = int(history_env)
         if not 0 <= self._history_env < self.num_envs:
@@ -232,6 +242,8 @@ class CityLearnEnv:
         self.reward_function = self._make_reward_function()
         rid, rparams = self._fused_reward()
         self._reward_id = rid
+        if self._has_ev and rid < 0:
+            raise NotImplementedError('districts with electric vehicles / washing machines need a built-in reward function (evaluated in the step kernel)')
         self._reward_dim = 1 if self.central_agent else spec.n_buildings
         self._reward_params = rparams
         self._debug_trace = debug_trace

@@ -123,6 +123,8 @@ def load_chargers(building_index: int, bs: Mapping[str, Any], source, lo: int, h
         if cfg.get('noise_std', 0.0):
             from .schema import UnsupportedSchemaError
             raise UnsupportedSchemaError(f"charger '{cid}': noise_std > 0 draws from NumPy's global generator at load time; not supported")
+        if not cfg.get('charger_simulation'):
+            raise ValueError(f"charger '{cid}': the schema names no 'charger_simulation' file")
         t = source.text_table(cfg['charger_simulation'])
         n = len(next(iter(t.values())))
         a = dict(cfg.get('attributes', {}) or {})

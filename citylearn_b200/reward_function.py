@@ -20,7 +20,7 @@ import torch
 from .data import ZERO_DIVISION_PLACEHOLDER
 
 __all__ = ['RewardFunction', 'MultiBuildingRewardFunction', 'MARL', 'IndependentSACReward', 'SolarPenaltyReward',
-           'ComfortReward', 'SolarPenaltyAndComfortReward', 'BUILTIN_REWARD_IDS']
+           'ComfortReward', 'SolarPenaltyAndComfortReward', 'Electric_Vehicles_Reward_Function', 'BUILTIN_REWARD_IDS']
 
 
 def _t(x) -> torch.Tensor:
@@ -202,7 +202,25 @@ class SolarPenaltyAndComfortReward(RewardFunction):
         return [_total([p[i].double() * c for p, c in zip(parts, self.coefficients)]) for i in range(len(parts[0]))]
 
 
+class Electric_Vehicles_Reward_Function(MARL):
+    """`citylearn.reward_function.Electric_Vehicles_Reward_Function` (reward_function.py:389-523): the MARL reward only scales the
+    penalty / bonus terms of a building's chargers (battery limits, reachability and closeness of the required departure SOC,
+    self-consumption / self-production); a building without chargers is rewarded 0.  Evaluated inside the step kernel (default weights;
+    custom weights would need the Python path, which this class does not provide: the per-charger dictionaries live on the device)."""
+
+    def __init__(self, env_metadata: Mapping[str, Any] = None, weights: Mapping[str, float] = None):
+        super().__init__(env_metadata)
+        if weights:
+            raise NotImplementedError('Electric_Vehicles_Reward_Function: custom weights are not supported (the fused kernel uses the defaults)')
+        self.weights = {"no_car_charging": -5.0, "battery_limits": -2.0, "soc_impossible": -10.0, "soc_under": -5.0, "close_soc": 10.0,
+                        "self_ev_consumption": 5.0, "extra_self_production": 5.0}
+
+    def calculate(self, observations):
+        raise NotImplementedError('Electric_Vehicles_Reward_Function is evaluated by the step kernel (cl_reward_id 6)')
+
+
 # class -> cl_reward_id (include/citylearn_b200.h); identity match only, subclasses go through the Python path
 BUILTIN_REWARD_IDS = {
     RewardFunction: 0, MARL: 1, IndependentSACReward: 2, SolarPenaltyReward: 3, ComfortReward: 4, SolarPenaltyAndComfortReward: 5,
+    Electric_Vehicles_Reward_Function: 6,
 }

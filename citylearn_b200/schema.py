@@ -649,6 +649,12 @@ def load(schema: Union[str, os.PathLike, Mapping[str, Any]], **kwargs) -> Distri
                 cols = EV.charger_observation_columns(c, sched, init)
                 for key, pattern in EV.CHARGER_OBSERVATIONS:
                     b.series[pattern.format(id=c.charger_id)] = cols[key]
+                # the same observation on the FIRST row of an episode: every connection is new at t = 0 (arrival SOC, else the vehicle's
+                # initial SOC stays in soc[0])
+                con = EV.connected_mask(c)
+                t0v = sched['t0'][np.arange(len(con)), np.maximum(c.ev, 0)]
+                soc0 = np.where(con, np.where(np.isnan(t0v), init[np.maximum(c.ev, 0)], t0v), EV.DEFAULT_SOC)
+                b.series[f'connected_electric_vehicle_at_charger_{c.charger_id}_soc__t0'] = np.asarray(soc0, dtype='float32')
     finalize(spec)
     return spec
 
@@ -1115,6 +1121,8 @@ def finalize(spec: DistrictSpec) -> None:
                 add((bi, name), s[name])
             elif kind == 'derived':
                 add((bi, name), derived_series(b, payload))
+        for name in [k for k in s if k.endswith('__t0')]:          # episode-start variants of observation columns (chargers)
+            add((bi, name), s[name])
         # dyn-mapped observation names that are table-backed in reference-parity ("stale") mode
         for name in ('cooling_demand', 'heating_demand', 'dhw_demand', 'indoor_dry_bulb_temperature'):
             add((bi, name), s[name])
@@ -1278,9 +1286,9 @@ def finalize(spec: DistrictSpec) -> None:
                     q[CHP[f'{pre}_X0'] + j], q[CHP[f'{pre}_Y0'] + j] = cv[0][j], cv[1][j]
         wm_building = np.array([w.building for w in wms], dtype='int32')
         wm_action = np.array([wm_action_slot.get((w.building, w.name), -1) for w in wms], dtype='int32')
-        wm_cols = np.zeros((len(wms), 3), dtype='int32')
+        wm_cols = np.zeros((len(wms), 4), dtype='int32')
         for k, w in enumerate(wms):
-            for j, (key, arr) in enumerate((('start', w.start), ('end', w.end), ('load', w.profile_sum))):
+            for j, (key, arr) in enumerate((('start', w.start), ('end', w.end), ('load', w.profile_sum), ('len', w.profile_len))):
                 cols.append(np.ascontiguousarray(arr, dtype='float32'))
                 index[('wm', w.building, w.name, key)] = len(cols) - 1
                 wm_cols[k, j] = len(cols) - 1
@@ -1325,7 +1333,8 @@ def observation_layout(spec: DistrictSpec, central_agent: Optional[bool] = None,
         elif name == 'power_outage':
             desc[j] = (OBS_OUTAGE, 0, 0, bi)
         else:
-            desc[j] = (OBS_TS, spec.columns[(bi, name)], 0, bi)
+            alt = spec.columns.get((bi, name + '__t0'))       # value on the first row of an episode, when it differs (b = column + 1)
+            desc[j] = (OBS_TS, spec.columns[(bi, name)], 0 if alt is None else alt + 1, bi)
     return entries, desc
 
 

@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define CL_ABI_VERSION 1
+#define CL_ABI_VERSION 2
 
 typedef enum cl_status {
     CL_OK = 0,
@@ -130,6 +130,7 @@ enum cl_reward_id {
     CL_REWARD_SOLAR_PENALTY = 3,      /* SolarPenaltyReward :189-214                                       */
     CL_REWARD_COMFORT = 4,            /* ComfortReward :269-334  p[0]=band (NaN: series) p[1]=lower p[2]=higher exponent */
     CL_REWARD_SOLAR_PENALTY_AND_COMFORT = 5, /* :381-386         p[3], p[4] = coefficients                 */
+    CL_REWARD_ELECTRIC_VEHICLES = 6,  /* Electric_Vehicles_Reward_Function :389-523 (default weights; needs cl_ev_desc)      */
     CL_REWARD_NONE = -1               /* rewards are computed by the caller from the trace (custom RewardFunction) */
 };
 
@@ -137,6 +138,34 @@ enum cl_precision {
     CL_PRECISION_FP32 = 0,  /* float arithmetic (north-star contract: <= 1e-5 scaled-relative of the reference)      */
     CL_PRECISION_FP64 = 1   /* the reference's own float64-intermediate / float32-storage flow (bit-exact physics)    */
 };
+
+/*
+ * Electric vehicles, chargers and washing machines (citylearn/electric_vehicle_charger.py, electric_vehicle.py,
+ * energy_model.py:1244-1398, citylearn.py:1325-1475).  Which vehicle is plugged in where, arrival SOCs and the SOC drift of away
+ * vehicles do not depend on the actions: the host compiles them into table columns (citylearn_b200/ev.py) and the device keeps, per
+ * (vehicle, env), the soc[t-1] / soc[t] entries, the degraded capacity, the last round-trip efficiency and a "has charged" flag.
+ * All arrays are HOST arrays copied by cl_create.  Districts with vehicles use whole-env blocks (no building tiles), one episode
+ * window for all envs and reference-parity (stale) observations.
+ */
+enum cl_charger_param {
+    CL_CH_MAX_C = 0, CL_CH_MIN_C, CL_CH_MAX_D, CL_CH_MIN_D, CL_CH_EFF, CL_CH_C_N, CL_CH_D_N,
+    CL_CH_C_X0, CL_CH_C_Y0 = CL_CH_C_X0 + 8, CL_CH_D_X0 = CL_CH_C_Y0 + 8, CL_CH_D_Y0 = CL_CH_D_X0 + 8, CL_NCHP = CL_CH_D_Y0 + 8
+};
+#define CL_MAX_CHARGERS_PER_BUILDING 4
+typedef struct cl_ev_desc {
+    int32_t n_ev, n_chargers, n_machines;
+    const double* ev_params;      /* [n_ev][CL_NPARAM]: the CL_P_BAT_* / curve / time-step entries of every vehicle battery      */
+    const int32_t* ev_iparams;    /* [n_ev][2]: points of the power-efficiency and capacity-power curves                          */
+    const int32_t* ev_cols;       /* [n_ev][4] table columns: association SOC, pre-connection SOC, (unused), SOC at an episode start; NaN = none */
+    const double* ev_drift;       /* [n_rows][n_ev] factor on soc[t-1] for a vehicle that is away on that row, NaN = none (float64) */
+    const int32_t* ch_building;   /* [n_chargers] ascending                                                                        */
+    const int32_t* ch_action;     /* [n_chargers] slot in the district action vector or -1                                         */
+    const int32_t* ch_cols;       /* [n_chargers][4] table columns: connected (0/1), vehicle index, required SOC, hours to departure */
+    const double* ch_params;      /* [n_chargers][CL_NCHP]                                                                         */
+    const int32_t* wm_building;   /* [n_machines] ascending                                                                        */
+    const int32_t* wm_action;     /* [n_machines]                                                                                  */
+    const int32_t* wm_cols;       /* [n_machines][4] table columns: window start, window end, load (sum of the profile), profile length */
+} cl_ev_desc;
 
 typedef struct cl_district_desc {
     int32_t abi_version;         /* CL_ABI_VERSION */
@@ -157,6 +186,7 @@ typedef struct cl_district_desc {
     const int32_t* iparams;      /* host [CL_NIPARAM][B] */
     const int32_t* obs_desc;     /* host [L][4] */
     const float* lstm_weights;   /* host, per-building blocks at iparams[CL_IP_DYN_W_OFFSET] */
+    const cl_ev_desc* ev;        /* electric vehicles / chargers / washing machines, or NULL */
 } cl_district_desc;
 
 typedef struct cl_env cl_env;    /* opaque */
@@ -248,6 +278,9 @@ int cl_time_step(const cl_env* env, int32_t* t);
 int cl_state_size(const cl_env* env, size_t* bytes);
 int cl_get_state(cl_env* env, void* dst_dev, cl_stream stream);
 int cl_set_state(cl_env* env, const void* src_dev, int32_t time_step, cl_stream stream);
+
+/* Per-vehicle SOC entries of every env: soc_prev, soc dev [E][n_ev] float (soc[t-1], soc[t]) - diagnostics / parity tests. */
+int cl_ev_read(cl_env* env, float* soc_prev_dev, float* soc_dev, cl_stream stream);
 
 /* Number of kernels this library has launched on behalf of `env` since creation (bench.py's gpu_launches). */
 int cl_launch_count(const cl_env* env, int64_t* n);

@@ -815,7 +815,7 @@ class OracleEnv:
         rows = self.start + t_eff
         for j, (kind, a, b_, bi) in enumerate(self.desc):
             if kind == S.OBS_TS:
-                obs[:, j] = self.table[rows, a]
+                obs[:, j] = self.table[rows, b_ - 1 if (t == 0 and b_ > 0) else a]      # b: the column to read at t = 0 (+ 1), if any
             elif kind == S.OBS_DYN:
                 obs[:, j] = 0.0 if zero_dyn else dyn[:, bi, a]
             elif kind == S.OBS_OUTAGE:

@@ -21,7 +21,7 @@ def enum_members(name):
             continue
         if '=' in item:
             k, v = [x.strip() for x in item.split('=')]
-            value = int(v, 0)
+            value = int(v, 0) if re.fullmatch(r'-?\w+', v) and not v.startswith('CL_') else int(eval(v, {}, dict(out)))
         else:
             k = item
         out[k] = value
@@ -68,9 +68,24 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_descriptor_struct_layout():
-    from citylearn_b200._native import DistrictDesc
-    # 12 int32 + 8 double + 5 pointers, no padding surprises
-    assert ctypes.sizeof(DistrictDesc) == 12 * 4 + 8 * 8 + 5 * 8
+    from citylearn_b200._native import DistrictDesc, EvDesc
+    # 12 int32 + 8 double + 6 pointers, no padding surprises (ABI 2: + the cl_ev_desc pointer)
+    assert ctypes.sizeof(DistrictDesc) == 12 * 4 + 8 * 8 + 6 * 8
+    assert DistrictDesc.ev.offset == 12 * 4 + 8 * 8 + 5 * 8
+    # cl_ev_desc: 3 int32 (+ 4 bytes of padding before the first pointer) + 11 pointers
+    assert ctypes.sizeof(EvDesc) == 16 + 11 * 8 and EvDesc.ev_params.offset == 16
+    assert int(re.search(r'#define CL_ABI_VERSION (\d+)', HEADER).group(1)) == 2
+
+
+def test_charger_param_enum_matches_python():
+    from citylearn_b200 import ev
+    p = enum_members('cl_charger_param')
+    assert p['CL_NCHP'] == len(ev.CHARGER_PARAMS)
+    for k, v in ev.CHARGER_PARAMS.items():
+        if 'CL_CH_' + k in p:
+            assert p['CL_CH_' + k] == v, k
+    assert {'CL_CH_MAX_C', 'CL_CH_EFF', 'CL_CH_C_N', 'CL_CH_D_N', 'CL_CH_C_X0', 'CL_CH_C_Y0', 'CL_CH_D_X0', 'CL_CH_D_Y0'} <= set(p)
+    assert enum_members('cl_reward_id')['CL_REWARD_ELECTRIC_VEHICLES'] == 6
 
 
 def test_product_fails_loudly_without_cuda():

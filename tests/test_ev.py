@@ -65,3 +65,134 @@ def test_schedule_is_action_independent_and_seeded():
     assert np.array_equal(a['assoc'], c['assoc'], equal_nan=True) and not np.array_equal(a['drift'], c['drift'], equal_nan=True)
     d = a['drift'][np.isfinite(a['drift'])]
     assert d.size > 0 and d.min() >= 0.6 and d.max() <= 1.4
+
+
+# ---------------------------------------------------------------------------------------------------------------- GPU (C ABI) parity
+def make_gpu_env(cfg, **kw):
+    from citylearn_b200 import CityLearnEnv
+    src = DataSet.get_source(cfg['dataset'])
+    sch = src.schema()
+    if cfg.get('reward') is not None:
+        sch['reward_function'] = {'type': cfg['reward']['type'], 'attributes': cfg['reward'].get('attributes', {})}
+    return CityLearnEnv(sch, data_source=src, ev_random_seed=cfg['np_seed'], **(cfg.get('overrides') or {}), **kw)
+
+
+def ev_soc_entries(env):
+    import torch
+    n = env.spec.ev['n_ev']
+    prev = torch.zeros((env.num_envs, n), dtype=torch.float32, device=env.device)
+    now = torch.zeros_like(prev)
+    env._h.ev_read(prev.data_ptr(), now.data_ptr(), torch.cuda.current_stream(env.device).cuda_stream)
+    torch.cuda.synchronize()
+    return prev.cpu().numpy(), now.cpu().numpy()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('case', CASES)
+def test_gpu_single_env_matches_reference_bit_for_bit(case):
+    """The step kernel (fp64 flow) against the recorded reference run: observations, rewards, district sums and every vehicle's SOC
+    entry at every step, through `CityLearnEnv.step` with nested-list actions (the reference's call)."""
+    z, cfg, meta, spec = load(case)
+    env = make_gpu_env(cfg, num_envs=1)
+    obs, _ = env.reset()
+    assert np.array_equal(np.array([v for row in obs for v in row], dtype='float32'), z['reset_obs'])
+    sizes = [len(b.active_actions) for b in env.spec.buildings]
+    central = env.central_agent
+    for k in range(len(z['actions'])):
+        a = [float(x) for x in z['actions'][k]]
+        nested, o = [], 0
+        for s in sizes:
+            nested.append(a[o:o + s])
+            o += s
+        obs, rew, term, trunc, _ = env.step([a] if central else nested)
+        assert np.array_equal(np.array([v for row in obs for v in row], dtype='float32'), z['obs'][k]), f'obs step {k}'
+        r = np.array(rew, dtype='float32')
+        # a central agent's reward is the float32 sum of the buildings' rewards in building order, like the reference's
+        assert np.array_equal(r, z['reward'][k]), f'reward step {k}: {np.abs(r - z["reward"][k]).max()}'
+        assert np.array_equal(env.district[0].cpu().numpy(), z['district'][k]), f'district step {k}'
+        prev, now = ev_soc_entries(env)
+        assert np.array_equal(prev[0], z['ev_soc'][k]), f'vehicle soc step {k}'
+    assert env.gpu_launches > 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('precision', ['fp64', 'fp32'])
+def test_gpu_batched_envs_match_oracle(precision):
+    """96 envs with different action sequences (exact zeros included), 160 steps of the reward case, against the vectorised oracle:
+    bit-exact in the fp64 flow, north-star tolerance in fp32; one `rollout` launch equals the step-by-step run."""
+    import torch
+    z, cfg, meta, spec = load('c10_evs_reward')
+    E, K = 96, 160
+    env = make_gpu_env(cfg, num_envs=E, precision=precision)
+    ora = OracleEnv(spec, E, libm_pow=False)
+    rng = np.random.RandomState(3)
+    lo = np.concatenate([b.action_low for b in spec.buildings]).astype('float64')
+    hi = np.concatenate([b.action_high for b in spec.buildings]).astype('float64')
+    acts = (lo + rng.uniform(size=(K, E, lo.size)) * (hi - lo)).astype('float32')
+    acts[rng.rand(*acts.shape) < 0.1] = 0.0
+    o0 = ora.reset()
+    assert np.array_equal(env.observations.cpu().numpy(), o0.astype('float32'))
+    roll = make_gpu_env(cfg, num_envs=E, precision=precision)
+    ro, rr, rd = roll.rollout(torch.as_tensor(acts, device='cuda'))
+    worst = 0.0
+    for k in range(K):
+        obs, rew, term, _, _ = env.step(torch.as_tensor(acts[k], device='cuda'))
+        oo, orw, od, _ = ora.step(acts[k])
+        got = {'obs': obs.cpu().numpy(), 'reward': rew.cpu().numpy(), 'district': env.district.cpu().numpy(), 'soc': ev_soc_entries(env)[0]}
+        ref = {'obs': oo.astype('float32'), 'reward': orw.astype('float32').reshape(got['reward'].shape), 'district': od.astype('float32'),
+               'soc': ora.ev_soc_prev.astype('float32')}
+        for name in got:
+            if precision == 'fp64':
+                assert np.array_equal(got[name], ref[name]), f'{name} step {k}: {np.abs(got[name] - ref[name]).max()}'
+            else:
+                scale = np.maximum(np.abs(ref[name]), 1.0)
+                worst = max(worst, float((np.abs(got[name] - ref[name]) / scale).max()))
+        assert torch.equal(ro[k], obs) and torch.equal(rr[k], rew) and torch.equal(rd[k], env.district), f'rollout step {k}'
+    assert worst <= 1e-4, worst
+
+
+@pytest.mark.gpu
+def test_gpu_checkpoint_resume_and_second_episode():
+    """state_dict / load_state_dict carry the vehicles' state; a second episode starts from the same initial SOCs."""
+    import torch
+    z, cfg, meta, spec = load('c10_evs')
+    E = 8
+    a = make_gpu_env(cfg, num_envs=E, episode_time_steps=48)
+    b = make_gpu_env(cfg, num_envs=E, episode_time_steps=48)
+    g = torch.Generator().manual_seed(1)
+    acts = (torch.rand((47, E, a.spec.action_dim), generator=g) * 2 - 1).cuda()
+    first = []
+    for k in range(20):
+        first.append(a.step(acts[k])[1].clone())
+    sd = a.state_dict()
+    tail = [a.step(acts[k])[1].clone() for k in range(20, 47)]
+    assert a.terminated
+    b.load_state_dict(sd)
+    for k in range(20, 47):
+        assert torch.equal(b.step(acts[k])[1], tail[k - 20]), k
+    assert torch.equal(b.observations, a.observations)
+    assert np.array_equal(ev_soc_entries(a)[1], ev_soc_entries(b)[1])
+    a.reset()
+    b2 = make_gpu_env(cfg, num_envs=E, episode_time_steps=48)
+    b2.reset()                                    # rolling episodes: same second window
+    for k in range(10):
+        assert torch.equal(a.step(acts[k])[1], b2.step(acts[k])[1]), k
+
+
+@pytest.mark.gpu
+def test_gpu_unsupported_combinations_fail_loudly():
+    import torch
+    z, cfg, meta, spec = load('c10_evs')
+    with pytest.raises(NotImplementedError):
+        make_gpu_env(cfg, num_envs=4, stale_observations=False)
+    with pytest.raises(NotImplementedError):
+        make_gpu_env(cfg, num_envs=4, track_kpis=True)
+    env = make_gpu_env(cfg, num_envs=4)
+    with pytest.raises(NotImplementedError):
+        env.reset(options={'episode_start': torch.tensor([0, 24, 48, 72])})
+    with pytest.raises(RuntimeError):
+        env.evaluate()
+    from citylearn_b200 import CityLearnEnv
+    from citylearn_b200.reward_function import Electric_Vehicles_Reward_Function
+    with pytest.raises(ValueError, match='chargers'):
+        CityLearnEnv('citylearn_challenge_2022_phase_all', num_envs=2, reward_function=Electric_Vehicles_Reward_Function)

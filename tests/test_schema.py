@@ -60,8 +60,15 @@ def test_unsupported_features_fail_loudly():
     src = DataSet.get_source('citylearn_challenge_2022_phase_1')
     sch = src.schema()
     sch['buildings']['Building_1']['chargers'] = {'c1': {}}
-    with pytest.raises(S.UnsupportedSchemaError):
+    with pytest.raises(ValueError, match='charger_simulation'):
         S.load(sch, data_source=src)
+    # chargers are supported (citylearn_b200/ev.py); load-time noise from NumPy's global generator is not
+    ev_src = DataSet.get_source('citylearn_challenge_2022_phase_all_plus_evs')
+    sch = ev_src.schema()
+    b = next(n for n, v in sch['buildings'].items() if v.get('chargers'))
+    next(iter(sch['buildings'][b]['chargers'].values()))['noise_std'] = 0.1
+    with pytest.raises(S.UnsupportedSchemaError):
+        S.load(sch, data_source=ev_src)
     with pytest.raises(S.UnknownSchemaError):
         S.load('no_such_dataset')
 
