@@ -1122,16 +1122,18 @@ __global__ void __launch_bounds__(MAXT, (DYNAMICS && MAXT == CL_DYN_MAXT) ? CL_D
                         float av = __ldg(arow + slot);
                         if (d.act_range != nullptr) av = av * __ldg(d.act_range + slot) + __ldg(d.act_low + slot);
                         if (!init && av > 0.f && st != -1 && en != -1 && st <= t && t <= en && (int)row[wc.w] > 0) {
-                            wm_tot = wm_tot + row[wc.z];                            // every entry of the load profile lands in ec[t]
+                            // every entry of the load profile lands in ec[t]; entries whose step t + offset is past the episode are skipped
+                            const int len = (int)row[wc.w], left = d.T - t;
+                            wm_tot = wm_tot + row[len > left ? wc.z + left : wc.z];
                             init = true;
                         }
                     }
                     d.wm_flag[wi] = init ? 1 : 0;
                 }
-                in.has_ev = true; in.chargers_ec = (R)ch_tot; in.machines_ec = (R)wm_tot;
+                in.chargers_ec = (R)ch_tot; in.machines_ec = (R)wm_tot;
             }
             CL_STAMP(2);
-            unit_step<R, THERMAL>(c.p, curves, t, in, s, o);
+            unit_step<R, THERMAL, has_ev>(c.p, curves, t, in, s, o);
             CL_STAMP(3);
             float t_in = row[c.c_tin];
             if (DYNAMICS && (c.p.flags & CL_F_DYNAMICS)) {
@@ -1891,6 +1893,9 @@ extern "C" int cl_create(const cl_district_desc* desc, cl_env** out) {
             if (b < 0 || b >= B || (k > 0 && b < ev.wm_building[k - 1])) { cl_destroy(env); return fail(CL_ERR_INVALID, "cl_create: washing machines must be listed in building order"); }
             wm_off[(size_t)b + 1]++;
             for (int j = 0; j < 4; ++j) if (ev.wm_cols[k * 4 + j] < 0 || ev.wm_cols[k * 4 + j] >= d.W) { cl_destroy(env); return fail(CL_ERR_INVALID, "cl_create: washing-machine column outside the table"); }
+            int max_len = 1;                       // the partial-sum columns follow the load column
+            for (int r = 0; r < d.n_rows; ++r) max_len = std::max(max_len, (int)desc->table[(size_t)r * d.W + ev.wm_cols[k * 4 + 3]]);
+            if (ev.wm_cols[k * 4 + 2] + max_len - 1 >= d.W) { cl_destroy(env); return fail(CL_ERR_INVALID, "cl_create: washing-machine partial-sum columns outside the table"); }
             if (ev.wm_action[k] >= d.A) { cl_destroy(env); return fail(CL_ERR_INVALID, "cl_create: washing-machine action slot outside the action vector"); }
         }
         for (int b = 0; b < B; ++b) {

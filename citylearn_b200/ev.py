@@ -85,6 +85,9 @@ class WashingMachineSpec:
     profile_sum: np.ndarray                    # float64: sum of the row's load profile (the reference adds every entry to ec[t], energy_model.py:1324-1327)
     profile_len: np.ndarray
     profiles: List[np.ndarray] = field(default_factory=list)      # the row's load profile entries
+    # [n_rows][max_len - 1]: the same float32 accumulation over the first 1, 2, ... entries only - a cycle started so close to the end of
+    # the episode that `t + offset` leaves it adds just those (energy_model.py:1325-1327)
+    profile_prefix: np.ndarray = None
 
     def profile_values(self, row: int) -> np.ndarray:
         return self.profiles[row]
@@ -177,7 +180,7 @@ def load_washing_machines(building_index: int, bs: Mapping[str, Any], source, kw
         en = _num(t['wm_end_time_step'])
         st = np.where(np.isnan(st), DEFAULT_TIME, st).astype('int64')
         en = np.where(np.isnan(en), DEFAULT_TIME, en).astype('int64')
-        sums, lens, profs = [], [], []
+        sums, lens, profs, partial = [], [], [], []
         for s in t['load_profile']:
             try:
                 p = np.array(eval(str(s), {'__builtins__': {}}, {}), dtype='float64')      # '[3.157]' -> array; '-1' -> 0-d array
@@ -185,12 +188,20 @@ def load_washing_machines(building_index: int, bs: Mapping[str, Any], source, kw
             except Exception:
                 p = np.zeros(0)
             acc = np.float32(0.0)
+            part = []
             for x in p:                      # `ec[t] += entry`: float32 slot, np.float64 entries (energy_model.py:1324-1327)
                 acc = np.float32(np.float64(acc) + np.float64(x))
+                part.append(float(acc))
             sums.append(float(acc))
+            partial.append(part)
             lens.append(len(p))
             profs.append(p)
-        out.append(WashingMachineSpec(name, building_index, st, en, np.array(sums), np.array(lens, dtype='int64'), profs))
+        width = max(max(lens, default=1) - 1, 0)
+        prefix = np.zeros((len(sums), width))
+        for r, part in enumerate(partial):
+            for j in range(width):           # first j + 1 entries (the full sum once the profile is exhausted)
+                prefix[r, j] = part[min(j, len(part) - 1)] if part else 0.0
+        out.append(WashingMachineSpec(name, building_index, st, en, np.array(sums), np.array(lens, dtype='int64'), profs, prefix))
     return out
 
 

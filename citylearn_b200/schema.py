@@ -726,7 +726,7 @@ def _load_building(index, name, sch, source: DataSource, observations, actions, 
     chargers = EV.load_chargers(index, bs, source, lo_row, hi_row, [e.name for e in spec.evs])
     wms = EV.load_washing_machines(index, bs, source, kwargs)
     for obj, names_ in [(c, ('state', 'ev', 'capacity', 'current_soc', 'departure_time', 'required_soc', 'arrival_time', 'soc_arrival')) for c in chargers] + \
-                       [(w, ('start', 'end', 'profile_sum', 'profile_len')) for w in wms]:
+                       [(w, ('start', 'end', 'profile_sum', 'profile_len', 'profile_prefix')) for w in wms]:
         for an in names_:          # schedules index by dataset row like every other series
             a = getattr(obj, an)
             if len(a) < n:
@@ -1288,10 +1288,15 @@ def finalize(spec: DistrictSpec) -> None:
         wm_action = np.array([wm_action_slot.get((w.building, w.name), -1) for w in wms], dtype='int32')
         wm_cols = np.zeros((len(wms), 4), dtype='int32')
         for k, w in enumerate(wms):
-            for j, (key, arr) in enumerate((('start', w.start), ('end', w.end), ('load', w.profile_sum), ('len', w.profile_len))):
+            # the load column is FOLLOWED by the partial-sum columns (first 1, 2, ... entries of the profile): the device reads
+            # `load + (T - t)` for a cycle whose profile would run past the episode end (include/citylearn_b200.h, cl_ev_desc.wm_cols)
+            for j, (key, arr) in ((0, ('start', w.start)), (1, ('end', w.end)), (3, ('len', w.profile_len)), (2, ('load', w.profile_sum))):
                 cols.append(np.ascontiguousarray(arr, dtype='float32'))
                 index[('wm', w.building, w.name, key)] = len(cols) - 1
                 wm_cols[k, j] = len(cols) - 1
+            for j in range(w.profile_prefix.shape[1]):
+                cols.append(np.ascontiguousarray(w.profile_prefix[:, j], dtype='float32'))
+                index[('wm', w.building, w.name, f'load_first_{j + 1}')] = len(cols) - 1
         spec.ev = {'schedule': sched, 'n_ev': n_ev, 'ev_params': ev_params, 'ev_ip': ev_ip, 'ev_cols': ev_cols, 'chargers': chargers,
                    'ch_building': ch_building, 'ch_action': ch_action, 'ch_cols': ch_cols, 'ch_params': ch_params, 'wms': wms,
                    'wm_building': wm_building, 'wm_action': wm_action, 'wm_cols': wm_cols}

@@ -164,7 +164,9 @@ typedef struct cl_ev_desc {
     const double* ch_params;      /* [n_chargers][CL_NCHP]                                                                         */
     const int32_t* wm_building;   /* [n_machines] ascending                                                                        */
     const int32_t* wm_action;     /* [n_machines]                                                                                  */
-    const int32_t* wm_cols;       /* [n_machines][4] table columns: window start, window end, load (sum of the profile), profile length */
+    const int32_t* wm_cols;       /* [n_machines][4] table columns: window start, window end, load (sum of the profile), profile length.
+                                     The load column is followed by max(profile length) - 1 columns holding the sum of the first 1, 2, ...
+                                     entries: a cycle whose profile would run past the episode end adds only those (energy_model.py:1325-1327) */
 } cl_ev_desc;
 
 typedef struct cl_district_desc {

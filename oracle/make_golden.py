@@ -217,7 +217,7 @@ def run_case(CityLearnEnv, name, dataset, overrides=None, reward=None, steps=Non
     print(name, {k: v.shape for k, v in arrays.items() if k not in ('config', 'meta')}, (OUT / f'{name}.npz').stat().st_size)
 
 
-def run_ev_case(CityLearnEnv, name, dataset, overrides=None, reward=None, steps=200, seed=0, np_seed=5):
+def run_ev_case(CityLearnEnv, name, dataset, overrides=None, reward=None, steps=200, seed=0, np_seed=5, hold=None):
     """Electric vehicles / chargers / washing machines.  The reference draws the SOC drift of away vehicles from NumPy's
     GLOBAL generator (citylearn/citylearn.py:1473) and a missing vehicle `initial_soc` from Python's global `random`
     (citylearn.py:2564): the fixture seeds the former (`np_seed`, = `ev_random_seed` of the replacement) and writes the latter into the
@@ -242,6 +242,13 @@ def run_ev_case(CityLearnEnv, name, dataset, overrides=None, reward=None, steps=
     K = min(steps, env.time_steps - 1)
     actions = (lo + rng.uniform(0.0, 1.0, size=(K, len(lo))) * (hi - lo)).astype('float32')
     actions[rng.rand(*actions.shape) < 0.08] = 0.0          # exact zeros: an idle charger leaves soc[t] untouched (electric_vehicle_charger.py:325-327)
+    if hold:                                                # {action name: first step with a non-zero action} - e.g. start a washing cycle late
+        names = [n for b in env.buildings for n in b.active_actions]
+        for an, first in hold.items():
+            for j, n in enumerate(names):
+                if n == an:
+                    actions[:first, j] = 0.0
+                    actions[first, j] = np.float32(0.5 * (lo[j] + hi[j])) if lo[j] + hi[j] != 0 else np.float32(hi[j])
     chargers = [(b, c) for b in env.buildings for c in (b.electric_vehicle_chargers or [])]
     machines = [(b, w) for b in env.buildings for w in (b.washing_machines or [])]
     out = {k: [] for k in ('obs', 'reward', 'district', 'trace', 'ev_soc', 'charger_ec', 'charger_kwh', 'wm_ec')}
@@ -277,6 +284,10 @@ def run_ev_case(CityLearnEnv, name, dataset, overrides=None, reward=None, steps=
 EV_CASES = {
     'c10_evs': dict(dataset='citylearn_challenge_2022_phase_all_plus_evs', steps=300, seed=21, np_seed=5,
                     reward={'type': 'citylearn.reward_function.RewardFunction', 'attributes': {}}),
+    # a washing cycle started on the LAST step of the episode (window 49..52, three profile entries, T = 52): only the entries whose
+    # step lies inside the episode are added (energy_model.py:1325-1327)
+    'c10_evs_short': dict(dataset='citylearn_challenge_2022_phase_all_plus_evs', steps=51, seed=23, np_seed=7,
+                          overrides={'episode_time_steps': 52}, hold={'washing_machine_1': 50}),
     'c10_evs_reward': dict(dataset='citylearn_challenge_2022_phase_all_plus_evs', steps=120, seed=22, np_seed=6),
 }
 

@@ -95,3 +95,39 @@ def test_product_fails_loudly_without_cuda():
     from citylearn_b200 import CityLearnEnv
     with pytest.raises(RuntimeError, match='no CPU fallback'):
         CityLearnEnv('citylearn_challenge_2022_phase_1')
+
+
+def test_step_kernel_resource_budget():
+    """Regression guard (no GPU: reads the cubin's resource table): the headline instantiations of the step kernel must stay spill-free
+    and under the register count that lets one 512-thread block per SM be resident.  (A run-time `has_ev` flag in `unit_step` once cost
+    every instantiation 8+ registers and 170-900 B of spills - 8 % of the C2 step time - without failing a single parity test.)"""
+    import shutil
+    import subprocess
+    from citylearn_b200 import _native, build
+    tool = shutil.which('cuobjdump') or '/usr/local/cuda/bin/cuobjdump'
+    if not Path(tool).exists():
+        pytest.skip('cuobjdump not available')
+    build.build()
+    out = subprocess.run([tool, '-res-usage', str(_native.library_path())], capture_output=True, text=True, check=True).stdout
+    usage = {}
+    for name, reg, stack in re.findall(r'Function (\S*advance_kernel\S*):\s*\n\s*REG:(\d+) STACK:(\d+)', out):
+        usage[name] = (int(reg), int(stack))
+    assert len(usage) >= 20
+
+    def find(real, thermal, dynamics, maxt, wide, kpi, ev):
+        b = lambda v: f'Lb{int(v)}E'  # noqa: E731
+        key = f'advance_kernelI{real}{b(thermal)}{b(dynamics)}Li{maxt}E{b(wide)}{b(kpi)}{b(ev)}E'
+        hits = [v for k, v in usage.items() if key in k]
+        assert len(hits) == 1, key
+        return hits[0]
+    # BASELINE configs[1] (2022 districts): fp64 flow and fp32, plain and with fused KPI accumulators
+    for real, max_reg in (('d', 120), ('f', 112)):
+        reg, stack = find(real, 0, 0, 512, 0, 0, 0)
+        assert reg <= max_reg and stack == 0, (real, reg, stack)
+    assert find('d', 0, 0, 512, 0, 1, 0)[1] == 0 and find('f', 0, 0, 512, 0, 1, 0)[1] == 0
+    # wide (building-tiled) districts, BASELINE configs[3]
+    assert find('d', 0, 0, 512, 1, 0, 0)[1] <= 16 and find('f', 0, 0, 512, 1, 0, 0)[1] == 0
+    # every 512-thread instantiation must fit one block per SM: 65536 registers / 512 threads
+    for k, (reg, _) in usage.items():
+        if 'Li512E' in k:
+            assert reg <= 128, k

@@ -26,6 +26,13 @@ def load(case):
     return z, cfg, meta, spec
 
 
+def oracle_reset(env, spec):
+    tracker = S.EpisodeTracker(spec.simulation_start_time_step, spec.simulation_end_time_step)
+    ets = spec.episode_time_steps if spec.episode_time_steps is not None else tracker.simulation_time_steps
+    tracker.next_episode(ets, spec.rolling_episode_split, spec.random_episode_split, spec.random_seed)
+    return env.reset(tracker.episode_start_time_step, tracker.episode_time_steps)
+
+
 @pytest.mark.parametrize('case', CASES)
 def test_loader_reproduces_reference_names_and_spaces(case):
     z, cfg, meta, spec = load(case)
@@ -43,7 +50,7 @@ def test_oracle_matches_reference_bit_for_bit(case):
     washing machine's consumption and the charged energy - exact at every recorded step (exact-zero actions included)."""
     z, cfg, meta, spec = load(case)
     env = OracleEnv(spec, 1, libm_pow=True)
-    assert np.array_equal(env.reset()[0].astype('float32'), z['reset_obs'])
+    assert np.array_equal(oracle_reset(env, spec)[0].astype('float32'), z['reset_obs'])
     for k in range(len(z['actions'])):
         obs, rew, dist, dyn = env.step(z['actions'][k][None])
         info = env.last_ev
@@ -130,10 +137,13 @@ def test_gpu_batched_envs_match_oracle(precision):
     hi = np.concatenate([b.action_high for b in spec.buildings]).astype('float64')
     acts = (lo + rng.uniform(size=(K, E, lo.size)) * (hi - lo)).astype('float32')
     acts[rng.rand(*acts.shape) < 0.1] = 0.0
-    o0 = ora.reset()
+    o0 = oracle_reset(ora, spec)
     assert np.array_equal(env.observations.cpu().numpy(), o0.astype('float32'))
     roll = make_gpu_env(cfg, num_envs=E, precision=precision)
-    ro, rr, rd = roll.rollout(torch.as_tensor(acts, device='cuda'))
+    ro = torch.zeros((K, E, roll._obs_dim), device='cuda')
+    rr = torch.zeros((K, E, roll._reward_dim), device='cuda')
+    rd = torch.zeros((K, E, 3), device='cuda')
+    roll.rollout(torch.as_tensor(acts, device='cuda'), ro, rr, rd)
     worst = 0.0
     for k in range(K):
         obs, rew, term, _, _ = env.step(torch.as_tensor(acts[k], device='cuda'))
