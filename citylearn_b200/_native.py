@@ -37,7 +37,8 @@ class DistrictDesc(ctypes.Structure):
 class EvDesc(ctypes.Structure):          # cl_ev_desc
     _fields_ = [('n_ev', ctypes.c_int32), ('n_chargers', ctypes.c_int32), ('n_machines', ctypes.c_int32)] + [
         (n, ctypes.c_void_p) for n in ('ev_params', 'ev_iparams', 'ev_cols', 'ev_drift', 'ch_building', 'ch_action', 'ch_cols', 'ch_params',
-                                       'wm_building', 'wm_action', 'wm_cols')]
+                                       'wm_building', 'wm_action', 'wm_cols')] + [('n_constrained', ctypes.c_int32)] + [
+        (n, ctypes.c_void_p) for n in ('cc_building', 'cc_limits', 'cc_members', 'cc_flags')]
 
 
 ABI_VERSION = 2
@@ -161,6 +162,12 @@ class Handle:
                       'ev_drift': (drift, 'float64'), 'ch_building': (evd['ch_building'], 'int32'), 'ch_action': (evd['ch_action'], 'int32'),
                       'ch_cols': (evd['ch_cols'], 'int32'), 'ch_params': (evd['ch_params'], 'float64'), 'wm_building': (evd['wm_building'], 'int32'),
                       'wm_action': (evd['wm_action'], 'int32'), 'wm_cols': (evd['wm_cols'], 'int32')}
+            ccb = evd.get('cc_building', ())
+            e.n_constrained = len(ccb)
+            if len(ccb):
+                flags = [1 if spec.buildings[int(b)].charging_constraints.expose_violation else 0 for b in ccb]
+                arrays.update({'cc_building': (ccb, 'int32'), 'cc_limits': (evd['cc_limits'], 'float64'), 'cc_members': (evd['cc_members'], 'int32'),
+                               'cc_flags': (flags, 'int32')})
             for name, (arr, dt) in arrays.items():
                 a = np.ascontiguousarray(arr, dtype=dt)
                 keep.append(a)

@@ -15,7 +15,9 @@ NVCC_FLAGS = [
     '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
     '--fmad=false',          # the fp64 mode reproduces the reference's (non-fused) NumPy arithmetic bit for bit
     '-shared', '-Xcompiler', '-fPIC',
-    '--split-compile', '0',  # ptxas works on the kernels of the one translation unit in parallel (the unrolled LSTM cells dominate the build)
+    # (no --split-compile: splitting the module for parallel optimisation changed the code of every instantiation - the plain fp64 step
+    #  kernel flipped between 116 registers / no stack and 128 registers / 168 B of spills from one unrelated edit to the next, and the
+    #  spill-free variant it produced was still 2.5 % (fp64) / 5.5 % (fp32) slower on B200 than the single-module build; 1.5 min vs 40 s)
 ]
 
 

@@ -105,6 +105,13 @@ struct Dev {
     double* ev_sd;                   // [2][E * ev_n] degraded capacity, round-trip efficiency of the last charge
     uint8_t* ev_flag;                // [E * ev_n] 1: the vehicle's battery has charged before (its efficiency / capacity are np.float64 from then on)
     uint8_t* wm_flag;                // [E * wm_n] 1: a cycle was started in the current window
+    // charging constraints (cl_ev_desc.cc_*)
+    int cc_n, obs_state;             // obs_state: the observation row has CL_OBS_STATE entries (per-env values: no observation table)
+    const int32_t* cc_index;         // [B] index of the building's constraint record or -1
+    const double* cc_limits;         // [cc_n][1 + CL_MAX_PHASES]
+    const int32_t* cc_members;       // [cc_n][CL_MAX_PHASES][CL_MAX_CHARGERS_PER_BUILDING]
+    const int32_t* cc_flags;         // [cc_n]
+    float* cc_state;                 // [E][cc_n * CL_CC_SLOTS]
     // building-sharded districts (cl_exchange_*): this handle owns SOME buildings of every env; the per-env district sums are completed
     // inside the step by an all-gather of the ranks' partial sums through peer memory (NVLink): every (quantity, env) value travels as
     // ONE 8-byte {value, epoch} store into every peer's slot array - data and flag in one NVLink transaction, no fence, no second
@@ -389,8 +396,8 @@ __device__ __forceinline__ float solar_penalty_reward(const RewardIn& r) {
 
 // Electric_Vehicles_Reward_Function (citylearn/reward_function.py:389-523): what `electric_vehicles_chargers_dict` holds per charger at t
 struct ChargerInfo { bool conn; float kwh, soc_now; double soc_prev, cap, min_cap, req, hrs, max_c, max_d; };
-__device__ __forceinline__ float ev_reward(const ChargerInfo* ch, int n, float net, float district_net, int t) {
-    if (n == 0) return 0.f;                                             // a building without chargers is rewarded 0 (:421-422)
+__device__ __forceinline__ float ev_reward(const ChargerInfo* ch, int n, float net, float district_net, int t, double penalty) {
+    if (n == 0) return (float)(0.0 - penalty);                          // a building without chargers is rewarded 0 (:421-422)
     const double be = -(double)net;
     const double sg = be > 0 ? 1.0 : (be < 0 ? -1.0 : 0.0);
     const double marl = sg * 0.01 * (be * be) * fmax(0.0, (double)district_net);
@@ -418,7 +425,7 @@ __device__ __forceinline__ float ev_reward(const ChargerInfo* ch, int n, float n
         if (kwh < 0 && net > 0.f) s += w_self * mult; else if (kwh > 0 && net > 0.f) s += -0.5 * w_self * mult;
         total += s;
     }
-    return (float)total;
+    return (float)(total - penalty);                                    // charging-constraint violation x coefficient (:431-434)
 }
 
 __device__ __forceinline__ float unit_reward(int reward_id, const float* rp, const RewardIn& r) {
@@ -545,6 +552,8 @@ __device__ __forceinline__ void write_obs_general(const Dev& d, float* obs, int 
             v = __ldg(d.table + (size_t)row * d.Wp + ((t_obs == 0 && ds.z > 0) ? ds.z - 1 : ds.y));   // (b: the column to read on an episode's first row)
         } else if (ds.x == CL_OBS_DYN) {
             v = dynbuf ? dynbuf[(e_l * nb + (ds.w - b0)) * CL_NDYN + ds.y] : 0.f;
+        } else if (ds.x == CL_OBS_STATE) {
+            v = d.cc_state[(size_t)(e0 + e_l) * (d.cc_n * CL_CC_SLOTS) + ds.y];
         } else {
             v = d.has_outage ? __ldg(d.outage + ds.w * d.T + t_obs) : 0.f;
         }
@@ -794,7 +803,7 @@ __global__ void __launch_bounds__(MAXT, (DYNAMICS && MAXT == CL_DYN_MAXT) ? CL_D
     // observations with action-dependent (DYN) columns and an observation table: per-env row images in shared memory
     const bool fresh_tab = obs != nullptr && uniform && !d.stale && d.obs_tab != nullptr && d.fresh_slots;
     const bool want_dyn = (!d.stale && obs != nullptr) && !fresh_tab;      // general writer (per-env windows, no table)
-    const bool tmpl_path = obs != nullptr && uniform && d.stale;
+    const bool tmpl_path = obs != nullptr && uniform && d.stale && !d.obs_state;      // (per-env state columns: general writer)
     const bool need_dsum = (d.reward_id == CL_REWARD_MARL || d.reward_id == CL_REWARD_ELECTRIC_VEHICLES) && reward != nullptr;
     constexpr bool has_ev = EVD && !WIDE && !DYNAMICS;                  // chargers / washing machines: a separate instantiation (like KPI)
     const bool fused_reward = reward != nullptr && d.reward_id >= 0;
@@ -1045,6 +1054,7 @@ __global__ void __launch_bounds__(MAXT, (DYNAMICS && MAXT == CL_DYN_MAXT) ? CL_D
         RewardIn ri;
         ChargerInfo chi[CL_MAX_CHARGERS_PER_BUILDING];
         int n_chi = 0;
+        double cc_penalty = 0.0;          // charging-constraint violation x coefficient of this step (ev_reward)
         if (active) {
             UnitInputs<R> in;
             load_inputs<R, THERMAL>(d, c, row, b, t, in, uniform);
@@ -1063,17 +1073,102 @@ __global__ void __launch_bounds__(MAXT, (DYNAMICS && MAXT == CL_DYN_MAXT) ? CL_D
                 const float* arow = actions + ((size_t)k * d.E + e) * d.A;
                 const size_t EV = (size_t)d.E * d.ev_n;
                 const int tab0 = d.n_curves > 0 ? d.n_curves : nb;     // vehicles' curve tables follow the buildings'
-                for (int kk = __ldg(d.ch_off + b); kk < __ldg(d.ch_off + b + 1); ++kk) {
+                const int ch0 = __ldg(d.ch_off + b), ch1 = __ldg(d.ch_off + b + 1);
+                double act_c[CL_MAX_CHARGERS_PER_BUILDING];
+#pragma unroll
+                for (int j = 0; j < CL_MAX_CHARGERS_PER_BUILDING; ++j) {
+                    act_c[j] = 0.0;
+                    const int slot = ch0 + j < ch1 ? __ldg(d.ch_action + ch0 + j) : -1;
+                    if (slot >= 0) {
+                        float av = __ldg(arow + slot);
+                        if (d.act_range != nullptr) av = av * __ldg(d.act_range + slot) + __ldg(d.act_low + slot);
+                        act_c[j] = (double)av;
+                    }
+                }
+                const int cci = d.cc_n > 0 ? __ldg(d.cc_index + b) : -1;
+                if (cci >= 0) {
+                    // Building._apply_charging_constraints_to_actions (building.py:894-982): python-float arithmetic, `sum()` = 0 + x0 + x1 ..
+                    const double* lim = d.cc_limits + (size_t)cci * (1 + CL_MAX_PHASES);
+                    const int32_t* mem = d.cc_members + (size_t)cci * CL_MAX_PHASES * CL_MAX_CHARGERS_PER_BUILDING;
+                    float* stt = d.cc_state + (size_t)e * (d.cc_n * CL_CC_SLOTS) + (size_t)cci * CL_CC_SLOTS;
+                    double req[CL_MAX_CHARGERS_PER_BUILDING], scl[CL_MAX_CHARGERS_PER_BUILDING], maxp[CL_MAX_CHARGERS_PER_BUILDING];
+                    bool pos[CL_MAX_CHARGERS_PER_BUILDING];
+                    bool any = false;
+                    double total = 0.0;
+#pragma unroll
+                    for (int j = 0; j < CL_MAX_CHARGERS_PER_BUILDING; ++j) {
+                        const bool has = ch0 + j < ch1 && __ldg(d.ch_action + ch0 + j) >= 0;
+                        maxp[j] = has ? __ldg(d.ch_pd + (size_t)(ch0 + j) * CL_NCHP + CL_CH_MAX_C) : 0.0;
+                        pos[j] = has && act_c[j] > 0.0 && maxp[j] > 0.0;
+                        req[j] = pos[j] ? act_c[j] * maxp[j] : 0.0;
+                        scl[j] = 1.0;
+                        if (pos[j]) { total = total + req[j]; any = true; }
+                    }
+                    const double blim = __ldg(lim);
+                    double viol = 0.0, head_b = blim, head_p[CL_MAX_PHASES];
+#pragma unroll
+                    for (int ph = 0; ph < CL_MAX_PHASES; ++ph) head_p[ph] = __ldg(lim + 1 + ph);
+                    if (any) {
+                        if (blim == blim && blim >= 0.0 && total > blim) {
+                            const double sc = blim == 0.0 ? 0.0 : blim / total;
+#pragma unroll
+                            for (int j = 0; j < CL_MAX_CHARGERS_PER_BUILDING; ++j) if (pos[j]) scl[j] *= sc;
+                            viol += total - blim;
+                        }
+                        for (int ph = 0; ph < CL_MAX_PHASES; ++ph) {
+                            const double pl = __ldg(lim + 1 + ph);
+                            if (!(pl == pl) || pl < 0.0) continue;
+                            double psum = 0.0;
+                            for (int i = 0; i < CL_MAX_CHARGERS_PER_BUILDING; ++i) {
+                                const int m = __ldg(mem + ph * CL_MAX_CHARGERS_PER_BUILDING + i);
+                                if (m < 0) break;
+                                if (pos[m]) psum = psum + req[m] * scl[m];
+                            }
+                            if (psum > pl) {
+                                const double ps = pl == 0.0 ? 0.0 : pl / psum;
+                                for (int i = 0; i < CL_MAX_CHARGERS_PER_BUILDING; ++i) {
+                                    const int m = __ldg(mem + ph * CL_MAX_CHARGERS_PER_BUILDING + i);
+                                    if (m < 0) break;
+                                    if (pos[m]) scl[m] *= ps;
+                                }
+                                viol += psum - pl;
+                            }
+                        }
+                        double used = 0.0;
+#pragma unroll
+                        for (int j = 0; j < CL_MAX_CHARGERS_PER_BUILDING; ++j) {
+                            const bool has = ch0 + j < ch1 && __ldg(d.ch_action + ch0 + j) >= 0;
+                            if (!has || !(act_c[j] > 0.0)) continue;
+                            if (maxp[j] <= 0.0) { act_c[j] = 0.0; continue; }
+                            const double scaled = req[j] * scl[j];
+                            used = used + scaled;
+                            act_c[j] = fmax(0.0, fmin(act_c[j], scaled / maxp[j]));
+                            req[j] = scaled;                                  // (kept for the phase headrooms below)
+                        }
+                        head_b = blim - used;
+                        for (int ph = 0; ph < CL_MAX_PHASES; ++ph) {
+                            double up = 0.0;
+                            for (int i = 0; i < CL_MAX_CHARGERS_PER_BUILDING; ++i) {
+                                const int m = __ldg(mem + ph * CL_MAX_CHARGERS_PER_BUILDING + i);
+                                if (m < 0) break;
+                                if (pos[m]) up = up + req[m];
+                            }
+                            head_p[ph] = head_p[ph] - up;
+                        }
+                    }
+                    const double pen = viol * (double)c.p.hours;
+                    stt[0] = (float)head_b;
+#pragma unroll
+                    for (int ph = 0; ph < CL_MAX_PHASES; ++ph) stt[1 + ph] = (float)head_p[ph];
+                    stt[CL_CC_SLOTS - 1] = (float)pen;
+                    if ((__ldg(d.cc_flags + cci) & 1) && pen > 0.0) cc_penalty = pen * (double)d.rp[0];
+                }
+                for (int kk = ch0; kk < ch1; ++kk) {
                     const int4 cc = __ldg(reinterpret_cast<const int4*>(d.ch_cols) + kk);
                     const bool conn = row[cc.x] > 0.f;
                     const int v = conn ? (int)row[cc.y] : 0;
                     const int slot = __ldg(d.ch_action + kk);
-                    double a = 0.0;
-                    if (slot >= 0) {
-                        float av = __ldg(arow + slot);
-                        if (d.act_range != nullptr) av = av * __ldg(d.act_range + slot) + __ldg(d.act_low + slot);
-                        a = (double)av;
-                    }
+                    const double a = act_c[kk - ch0];
                     const double* qp = d.ch_pd + (size_t)kk * CL_NCHP;
                     ChargerParams<R> q;
                     q.max_c = (R)__ldg(qp + CL_CH_MAX_C); q.min_c = (R)__ldg(qp + CL_CH_MIN_C); q.max_d = (R)__ldg(qp + CL_CH_MAX_D);
@@ -1310,7 +1405,7 @@ __global__ void __launch_bounds__(MAXT, (DYNAMICS && MAXT == CL_DYN_MAXT) ? CL_D
             float r = 0.f;
             if (active) {
                 if (need_dsum) ri.district_net = s_dsum[pb * epb + e_l];
-                if constexpr (has_ev) r = d.reward_id == CL_REWARD_ELECTRIC_VEHICLES ? ev_reward(chi, n_chi, ri.net, ri.district_net, t) : unit_reward(d.reward_id, d.rp, ri);
+                if constexpr (has_ev) r = d.reward_id == CL_REWARD_ELECTRIC_VEHICLES ? ev_reward(chi, n_chi, ri.net, ri.district_net, t, cc_penalty) : unit_reward(d.reward_id, d.rp, ri);
                 else r = unit_reward(d.reward_id, d.rp, ri);
             }
             float* rk = reward + (size_t)k * d.E * Rdim;
@@ -1598,7 +1693,7 @@ template <typename T> static int dev_copy(cl_env* env, const T* host, size_t n, 
 // gather the row every step - when it would exceed CL_B200_OBS_TABLE_MB (default 4096 MiB) or the observation row is not a
 // multiple of 16 bytes.
 static bool obs_table_fits(const Dev& d) {
-    if ((d.L & 3) != 0) return false;
+    if ((d.L & 3) != 0 || d.obs_state) return false;     // per-env state columns cannot come from a table shared by all envs
     long budget_mb = 4096;
     if (const char* ev = std::getenv("CL_B200_OBS_TABLE_MB")) budget_mb = std::atol(ev);
     return (size_t)d.n_rows * (size_t)((d.L + 3) & ~3) * sizeof(float) <= (size_t)budget_mb * 1024 * 1024;
@@ -1818,6 +1913,12 @@ extern "C" int cl_create(const cl_district_desc* desc, cl_env** out) {
             tcol[k] = e4[0] == CL_OBS_TS ? e4[1] : (e4[0] == CL_OBS_DYN ? -1 : -2 - e4[3]);
             if (e4[0] == CL_OBS_TS && (e4[1] < 0 || e4[1] >= d.W)) { cl_destroy(env); return fail(CL_ERR_INVALID, "cl_create: observation column outside the table"); }
             if (e4[0] == CL_OBS_DYN && (e4[1] < 0 || e4[1] >= CL_NDYN)) { cl_destroy(env); return fail(CL_ERR_INVALID, "cl_create: bad DYN slot"); }
+            if (e4[0] == CL_OBS_STATE) {
+                const int ncc = desc->ev ? desc->ev->n_constrained : 0;
+                if (e4[1] < 0 || e4[1] >= ncc * CL_CC_SLOTS) { cl_destroy(env); return fail(CL_ERR_INVALID, "cl_create: CL_OBS_STATE slot outside the charging-constraint state"); }
+                if (!desc->stale_observations) { cl_destroy(env); return fail(CL_ERR_UNSUPPORTED, "cl_create: charging-constraint observations need stale_observations = 1"); }
+                d.obs_state = 1;
+            } else if (e4[0] != CL_OBS_TS && e4[0] != CL_OBS_DYN && e4[0] != CL_OBS_OUTAGE) { cl_destroy(env); return fail(CL_ERR_INVALID, "cl_create: unknown observation kind"); }
         }
         int32_t* tc = nullptr;
         if (!rc) rc = dev_copy(env, tcol.data(), tcol.size(), &tc);
@@ -1924,11 +2025,46 @@ extern "C" int cl_create(const cl_district_desc* desc, cl_env** out) {
         d.ev_n = ev.n_ev; d.ch_n = ev.n_chargers; d.wm_n = ev.n_machines;
         d.ev_pd = evp; d.ev_ip = evip; d.ev_cols = evc; d.ev_drift = drift; d.ch_off = cho; d.ch_action = cha; d.ch_cols = chc; d.ch_pd = chp;
         d.wm_off = wmo; d.wm_action = wma; d.wm_cols = wmc;
+        // charging constraints
+        const int ncc = ev.n_constrained > 0 ? ev.n_constrained : 0;
+        if (ncc > 0) {
+            if (!ev.cc_building || !ev.cc_limits || !ev.cc_members || !ev.cc_flags) { cl_destroy(env); return fail(CL_ERR_INVALID, "cl_create: null charging-constraint arrays"); }
+            std::vector<int32_t> idx((size_t)B, -1);
+            for (int k = 0; k < ncc; ++k) {
+                const int b = ev.cc_building[k];
+                if (b < 0 || b >= B || (k > 0 && b <= ev.cc_building[k - 1])) { cl_destroy(env); return fail(CL_ERR_INVALID, "cl_create: constrained buildings must be listed in ascending order"); }
+                idx[(size_t)b] = k;
+                const int nch = ch_off[(size_t)b + 1] - ch_off[(size_t)b];
+                for (int j = 0; j < CL_MAX_PHASES * CL_MAX_CHARGERS_PER_BUILDING; ++j) {
+                    const int m = ev.cc_members[(size_t)k * CL_MAX_PHASES * CL_MAX_CHARGERS_PER_BUILDING + j];
+                    if (m >= nch || m < -1) { cl_destroy(env); return fail(CL_ERR_INVALID, "cl_create: charging-phase member outside the building's chargers"); }
+                }
+            }
+            int32_t *ci = nullptr, *cm = nullptr, *cf = nullptr; double* cl_ = nullptr;
+            int rc2 = dev_copy(env, idx.data(), idx.size(), &ci);
+            if (!rc2) rc2 = dev_copy(env, ev.cc_limits, (size_t)ncc * (1 + CL_MAX_PHASES), &cl_);
+            if (!rc2) rc2 = dev_copy(env, ev.cc_members, (size_t)ncc * CL_MAX_PHASES * CL_MAX_CHARGERS_PER_BUILDING, &cm);
+            if (!rc2) rc2 = dev_copy(env, ev.cc_flags, (size_t)ncc, &cf);
+            if (rc2) { cl_destroy(env); return rc2; }
+            d.cc_n = ncc; d.cc_index = ci; d.cc_limits = cl_; d.cc_members = cm; d.cc_flags = cf;
+        }
         void* q = nullptr;
-        env->ev_sf_floats = (size_t)2 * d.E * std::max(ev.n_ev, 1); env->ev_sd_doubles = env->ev_sf_floats;
+        const size_t ev_floats = (size_t)2 * d.E * std::max(ev.n_ev, 1);
+        env->ev_sf_floats = ev_floats + (size_t)d.E * ncc * CL_CC_SLOTS; env->ev_sd_doubles = ev_floats;
         env->ev_flag_bytes = (size_t)d.E * std::max(ev.n_ev, 1); env->wm_flag_bytes = (size_t)d.E * std::max(ev.n_machines, 1);
         if (cudaMalloc(&q, env->ev_sf_floats * sizeof(float)) != cudaSuccess) { cl_destroy(env); return fail(CL_ERR_CUDA, "cl_create: vehicle state allocation failed"); }
         env->allocs.push_back(q); d.ev_sf = static_cast<float*>(q); cudaMemset(q, 0, env->ev_sf_floats * sizeof(float));
+        if (ncc > 0) {        // headroom = the caps, violation 0 until the first applied actions (`_set_default_charging_headroom`); never reset
+            d.cc_state = d.ev_sf + ev_floats;
+            std::vector<float> init((size_t)d.E * ncc * CL_CC_SLOTS, 0.f);
+            for (int e = 0; e < d.E; ++e)
+                for (int k = 0; k < ncc; ++k)
+                    for (int j = 0; j <= CL_MAX_PHASES; ++j) {
+                        const double v = ev.cc_limits[(size_t)k * (1 + CL_MAX_PHASES) + j];
+                        init[((size_t)e * ncc + k) * CL_CC_SLOTS + j] = v == v ? (float)v : 0.f;
+                    }
+            if (cudaMemcpy(d.cc_state, init.data(), init.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) { cl_destroy(env); return fail(CL_ERR_CUDA, "cl_create: charging-constraint state upload failed"); }
+        }
         if (cudaMalloc(&q, env->ev_sd_doubles * sizeof(double)) != cudaSuccess) { cl_destroy(env); return fail(CL_ERR_CUDA, "cl_create: vehicle state allocation failed"); }
         env->allocs.push_back(q); d.ev_sd = static_cast<double*>(q); cudaMemset(q, 0, env->ev_sd_doubles * sizeof(double));
         if (cudaMalloc(&q, env->ev_flag_bytes) != cudaSuccess) { cl_destroy(env); return fail(CL_ERR_CUDA, "cl_create: vehicle state allocation failed"); }

@@ -216,6 +216,8 @@ class CityLearnEnv:
         # `_entries` is the raw observation row (what `observation_names` / `observation_space` describe); `_out_entries` is the
         # row the kernels write, which differs under a fused observation wrapper (citylearn_b200/wrappers.py)
         self._entries, self._raw_desc = S.observation_layout(spec, self.central_agent, self.stale_observations)
+        # names / space order (differs from the value order only for buildings with charging constraints, like the reference's)
+        self._name_entries = S.observation_layout(spec, self.central_agent, self.stale_observations, names_order=True)[0]
         self._observation_transform = observation_transform
         self._normalized_actions = bool(normalized_actions)
         self._sizes_act = [len(b.active_actions) for b in spec.buildings]
@@ -242,6 +244,9 @@ class CityLearnEnv:
         self.reward_function = self._make_reward_function()
         rid, rparams = self._fused_reward()
         self._reward_id = rid
+        if any(b.observation_value_order is not None for b in spec.buildings) and observation_transform is not None:
+            raise NotImplementedError('observation wrappers on districts with charging constraints: the reference pairs the space limits with '
+                                      'the values by position although their orders differ (building.py:1146-1154); not reproduced')
         if self._has_ev and rid < 0:
             raise NotImplementedError('districts with electric vehicles / washing machines need a built-in reward function (evaluated in the step kernel)')
         self._reward_dim = 1 if self.central_agent else spec.n_buildings
@@ -316,6 +321,8 @@ class CityLearnEnv:
         """Fuse wrapper semantics into the kernels (used by `citylearn_b200.wrappers`): `observation_transform` in
         {None, 'normalized', 'clipped'}; `normalized_actions`: step() takes fractions of the action range.  Rebuilds the
         device-side district, i.e. starts a fresh episode like a reset."""
+        if observation_transform not in ('unchanged', None) and any(b.observation_value_order is not None for b in self.spec.buildings):
+            raise NotImplementedError('observation wrappers are not available for districts with charging constraints')
         if observation_transform != 'unchanged':
             self._observation_transform = observation_transform
         if normalized_actions is not None:
@@ -353,6 +360,8 @@ class CityLearnEnv:
         rid = rf_mod.BUILTIN_REWARD_IDS.get(type(r), -1)
         if rid == 0:
             return rid, [float(r.exponent)]
+        if rid == 6:
+            return rid, [float(r.charging_constraint_penalty_coefficient)]
         if rid == 4:
             return rid, [float('nan') if r.band is None else float(r.band), float(r.lower_exponent), float(r.higher_exponent)]
         if rid == 5:
@@ -408,7 +417,7 @@ class CityLearnEnv:
             lo, hi = [], []
             flat_lo = {(bi, n): v for bi, b in enumerate(self.spec.buildings) for n, v in zip(b.active_observations, b.observation_low)}
             flat_hi = {(bi, n): v for bi, b in enumerate(self.spec.buildings) for n, v in zip(b.active_observations, b.observation_high)}
-            for key in self._entries:
+            for key in self._name_entries:
                 lo.append(flat_lo[key])
                 hi.append(flat_hi[key])
             return [Box(low=np.array(lo, dtype='float32'), high=np.array(hi, dtype='float32'), dtype=np.float32)]
@@ -426,7 +435,8 @@ class CityLearnEnv:
     def observation_names(self) -> List[List[str]]:
         if self.central_agent:
             return [[n for _, n in self._entries]]
-        return [list(b.active_observations) for b in self.spec.buildings]
+        # the keys of `Building.observations()` (citylearn.py:498-520): the order of the VALUES; the space follows `active_observations`
+        return [list(b.observation_value_order or b.active_observations) for b in self.spec.buildings]
 
     @property
     def action_names(self) -> List[List[str]]:

@@ -93,6 +93,62 @@ class WashingMachineSpec:
         return self.profiles[row]
 
 
+MAX_PHASES = 4                                 # include/citylearn_b200.h CL_MAX_PHASES
+
+
+@dataclass
+class ChargingConstraints:
+    """`Building._initialize_charging_constraints` (citylearn/building.py:764-833): a power cap on the sum of a building's positive
+    charger requests and on the chargers of each phase; the excess scales the actions down (`_apply_charging_constraints_to_actions`,
+    :894-982) and is reported as `charging_constraint_violation_kwh`.  Observation names are kept in the order the reference inserts
+    them into `observation_metadata`; `one_hot` maps the static phase-encoding observations to their values."""
+    building_limit_kw: Optional[float]
+    phases: List[Dict[str, Any]]               # {'name', 'limit_kw' (None: no cap), 'chargers': [charger ids]}
+    expose_headroom: bool
+    expose_violation: bool
+    one_hot: Dict[str, float]
+    headroom_names: List[str]                  # 'charging_building_headroom_kw', 'charging_phase_<name>_headroom_kw' (limits that exist)
+    config: Dict[str, Any] = field(default_factory=dict)
+
+    @property
+    def state_names(self) -> List[str]:
+        """Observations held as per-env state on the device, in slot order."""
+        return (self.headroom_names if self.expose_headroom else []) + (['charging_constraint_violation_kwh'] if self.expose_violation else [])
+
+
+def load_charging_constraints(config: Optional[Mapping[str, Any]], chargers: List[ChargerSpec]) -> Optional[ChargingConstraints]:
+    if not config:
+        return None
+    oc = config.get('observations', {}) or {}
+    flag = config.get('expose_observations')
+    expose = bool(oc.get('headroom', False)) if 'headroom' in oc else (bool(flag) if flag is not None else True)
+    phases = []
+    phase_of: Dict[str, str] = {}
+    for ph in config.get('phases', []) or []:
+        name = ph.get('name') or f'phase_{len(phases) + 1}'
+        ids = list(ph.get('chargers', []) or [])
+        phases.append({'name': name, 'limit_kw': ph.get('limit_kw'), 'chargers': ids})
+        for cid in ids:
+            phase_of[cid] = name
+    encode = bool(oc.get('phase_encoding', False)) and bool(phases)
+    one_hot: Dict[str, float] = {}
+    ids = [c.charger_id for c in chargers]
+    if encode and ids:
+        names = sorted({ph['name'] for ph in phases if ph['name']})
+        unassigned = any(cid not in phase_of for cid in ids)
+        if unassigned:
+            names = names + ['unassigned']
+        for cid in ids:
+            mine = phase_of.get(cid, 'unassigned' if unassigned else None)
+            for n in names:
+                one_hot[f'charging_phase_one_hot_{cid}_{n}'] = 1.0 if mine == n else 0.0
+    head = []
+    if config.get('building_limit_kw') is not None:
+        head.append('charging_building_headroom_kw')
+    head += [f"charging_phase_{ph['name']}_headroom_kw" for ph in phases if ph['limit_kw'] is not None]
+    return ChargingConstraints(config.get('building_limit_kw'), phases, expose, bool(oc.get('violation', True)), one_hot, head, dict(config))
+
+
 def _stable_unit(name: str) -> float:
     """Stand-in for the reference's `random.uniform(0, 1)` default of a vehicle's initial SOC (unseeded there)."""
     return int(hashlib.md5(name.encode()).hexdigest()[:8], 16) / float(0xFFFFFFFF)

@@ -208,8 +208,11 @@ class Electric_Vehicles_Reward_Function(MARL):
     self-consumption / self-production); a building without chargers is rewarded 0.  Evaluated inside the step kernel (default weights;
     custom weights would need the Python path, which this class does not provide: the per-charger dictionaries live on the device)."""
 
-    def __init__(self, env_metadata: Mapping[str, Any] = None, weights: Mapping[str, float] = None):
-        super().__init__(env_metadata)
+    def __init__(self, env_metadata: Mapping[str, Any] = None, weights: Mapping[str, float] = None,
+                 charging_constraint_penalty_coefficient: float = None, **kwargs):
+        super().__init__(env_metadata, **kwargs)
+        # reward_function.py:22-25, 50-58: multiplies a building's `charging_constraint_violation_kwh` (default 1.0)
+        self.charging_constraint_penalty_coefficient = 1.0 if charging_constraint_penalty_coefficient is None else float(charging_constraint_penalty_coefficient)
         if weights:
             raise NotImplementedError('Electric_Vehicles_Reward_Function: custom weights are not supported (the fused kernel uses the defaults)')
         self.weights = {"no_car_charging": -5.0, "battery_limits": -2.0, "soc_impossible": -10.0, "soc_under": -5.0, "close_soc": 10.0,

@@ -111,6 +111,8 @@ NDYN = len(DYN)
 
 # observation descriptor kinds  (cl_obs_kind)
 OBS_TS, OBS_DYN, OBS_OUTAGE, OBS_TS_MINUS_TS = 0, 1, 2, 3
+OBS_STATE = 4            # a = slot of the per-env charging-constraint state (cl_ev_desc): headroom / violation of the last applied actions
+CC_SLOTS = 6             # per constrained building: building headroom, 4 phase headrooms, violation (kWh)
 
 # built-in reward ids  (cl_reward_id)
 REWARD_IDS = {
@@ -281,6 +283,10 @@ class BuildingSpec:
     demand_observation_limit_factor: float = 2.0
     chargers: List[Any] = field(default_factory=list)            # ev.ChargerSpec
     washing_machines: List[Any] = field(default_factory=list)    # ev.WashingMachineSpec
+    charging_constraints: Optional[Any] = None                   # ev.ChargingConstraints (citylearn/building.py:764-989)
+    # names of the observation VALUES in the order `Building.observations()` returns them, when it differs from `active_observations`
+    # (the names / space order): charging-constraint observations precede the per-charger ones in the values (building.py:1146-1154)
+    observation_value_order: Optional[List[str]] = None
 
     @property
     def active_observations(self) -> List[str]:
@@ -662,7 +668,7 @@ def load(schema: Union[str, os.PathLike, Mapping[str, Any]], **kwargs) -> Distri
 def _load_building(index, name, sch, source: DataSource, observations, actions, schema_seed, seconds_per_time_step,
                    ratios, spec: DistrictSpec, kwargs) -> BuildingSpec:
     bs = sch['buildings'][name]
-    for unsupported in ('occupant', 'charging_constraints'):
+    for unsupported in ('occupant',):
         if bs.get(unsupported):
             raise UnsupportedSchemaError(f"building '{name}': '{unsupported}' is outside the accelerated hot path (SURVEY.md §8f)")
     if bs.get('noise_std', 0.0):
@@ -754,6 +760,28 @@ def _load_building(index, name, sch, source: DataSource, observations, actions, 
         if wm_act_f.get('washing_machine', False):
             am[f'{w.name}'] = True
 
+    # charging constraints (citylearn/citylearn.py:2177-2178, building.py:764-833): observation names in the reference's insertion order
+    cc = EV.load_charging_constraints(bs.get('charging_constraints'), chargers)
+    value_order = None
+    if cc is not None:
+        if len(cc.phases) > EV.MAX_PHASES:
+            raise UnsupportedSchemaError(f"building '{name}': more than {EV.MAX_PHASES} charging phases are not supported")
+        for k in cc.one_hot:
+            om.setdefault(k, True)
+        if cc.expose_headroom:
+            for k in cc.headroom_names:
+                om.setdefault(k, True)
+        om['charging_constraint_violation_kwh'] = cc.expose_violation
+        for k in cc.one_hot:
+            om[k] = True
+        # `observations = {k: data[k] for k in valid_observations if k in data}` then the chargers' and machines' values are appended
+        per_device = {pattern.format(id=c.charger_id) for c in chargers for _, pattern in EV.CHARGER_OBSERVATIONS} | \
+            {f'{w.name}_{k}' for w in wms for k in ('start_time_step', 'end_time_step')}
+        active = [k for k, v in om.items() if v]
+        value_order = [k for k in active if k not in per_device] + [k for k in active if k in per_device]
+        if value_order == active:
+            value_order = None
+
     # ---- power outage (citylearn/citylearn.py:2273-2290) ----
     po = bs.get('power_outage', {}) or {}
     simulate = kwargs.get('simulate_power_outage')
@@ -824,7 +852,11 @@ def _load_building(index, name, sch, source: DataSource, observations, actions, 
         name=name, index=index, building_type=building_type, dynamics=is_dyn, observation_metadata=om, action_metadata=am,
         series=series, devices=devices, time_step_ratio=1.0 if time_step_ratio is None else float(time_step_ratio),
         seconds_per_time_step=seconds_per_time_step, simulate_power_outage=bool(simulate), stochastic_power_outage=bool(stochastic),
-        outage_model=model, dynamics_attrs=dyn_attrs, dynamics_weights=dyn_weights, chargers=chargers, washing_machines=wms)
+        outage_model=model, dynamics_attrs=dyn_attrs, dynamics_weights=dyn_weights, chargers=chargers, washing_machines=wms,
+        charging_constraints=cc, observation_value_order=value_order)
+    if cc is not None:
+        for k, v in cc.one_hot.items():
+            series[k] = np.full(n, v, dtype='float32')
     for w in wms:      # observation columns (citylearn/building.py:1298-1335): the machine's schedule at the observed time step
         series[f'{w.name}_start_time_step'] = np.asarray(w.start, dtype='float32')
         series[f'{w.name}_end_time_step'] = np.asarray(w.end, dtype='float32')
@@ -886,8 +918,19 @@ def estimate_observation_space_limits(b: BuildingSpec, spec: DistrictSpec, inclu
             return demand / cop32(d, t_out, heating)
         return np.array(demand) / d['efficiency']
 
+    cc = b.charging_constraints
+    if cc is not None:       # building.py:2138-2157
+        for k in cc.headroom_names:
+            lim = cc.building_limit_kw if k == 'charging_building_headroom_kw' else next(
+                ph['limit_kw'] for ph in cc.phases if k == f"charging_phase_{ph['name']}_headroom_kw")
+            data[k] = np.full(2, float(lim), dtype='float32')
     for key in names:
-        if key == 'net_electricity_consumption':
+        if key.startswith('charging_phase_one_hot_'):
+            low[key], high[key] = 0.0, 1.0
+        elif key == 'charging_constraint_violation_kwh':
+            low[key] = 0.0
+            high[key] = sum((c.max_charging_power or 0.0) for c in b.chargers) * (b.seconds_per_time_step / 3600)
+        elif key == 'net_electricity_consumption':
             lows = data['non_shiftable_load'] - (+dv['electrical_storage']['nominal_power'] + data['solar_generation'])
             highs = (data['non_shiftable_load'] + dv['cooling_device']['nominal_power'] + dv['heating_device']['nominal_power']
                      + dv['dhw_device']['nominal_power'] + dv['electrical_storage']['nominal_power'] - data['solar_generation'])
@@ -1005,6 +1048,8 @@ def _observation_source(b: BuildingSpec, name: str):
         return ('dyn', name)
     if name == 'power_outage':
         return ('outage', None)
+    if b.charging_constraints is not None and (name in b.charging_constraints.headroom_names or name == 'charging_constraint_violation_kwh'):
+        return ('state', name)
     if name == 'solar_generation':
         return ('derived', 'solar_generation_obs')
     if name in ('cooling_device_efficiency', 'heating_device_efficiency', 'dhw_device_efficiency',
@@ -1297,9 +1342,28 @@ def finalize(spec: DistrictSpec) -> None:
             for j in range(w.profile_prefix.shape[1]):
                 cols.append(np.ascontiguousarray(w.profile_prefix[:, j], dtype='float32'))
                 index[('wm', w.building, w.name, f'load_first_{j + 1}')] = len(cols) - 1
+        # charging constraints (building.py:764-989): limits (NaN: none), phase member lists as indices into the building's chargers
+        cc_buildings = [bi for bi, b in enumerate(spec.buildings) if b.charging_constraints is not None]
+        cc_limits = np.full((len(cc_buildings), 1 + EV.MAX_PHASES), np.nan, dtype='float64')
+        cc_members = np.full((len(cc_buildings), EV.MAX_PHASES, 4), -1, dtype='int32')
+        for k, bi in enumerate(cc_buildings):
+            b, cc = spec.buildings[bi], spec.buildings[bi].charging_constraints
+            if not b.chargers:
+                continue
+            ids = [c.charger_id for c in b.chargers]
+            if cc.building_limit_kw is not None:
+                cc_limits[k, 0] = float(cc.building_limit_kw)
+            for j, ph in enumerate(cc.phases):
+                if ph['limit_kw'] is not None:
+                    cc_limits[k, 1 + j] = float(ph['limit_kw'])
+                mem = [ids.index(cid) for cid in ph['chargers'] if cid in ids]
+                if len(mem) > 4:
+                    raise UnsupportedSchemaError('a charging phase lists more than 4 charger entries')
+                cc_members[k, j, :len(mem)] = mem
         spec.ev = {'schedule': sched, 'n_ev': n_ev, 'ev_params': ev_params, 'ev_ip': ev_ip, 'ev_cols': ev_cols, 'chargers': chargers,
                    'ch_building': ch_building, 'ch_action': ch_action, 'ch_cols': ch_cols, 'ch_params': ch_params, 'wms': wms,
-                   'wm_building': wm_building, 'wm_action': wm_action, 'wm_cols': wm_cols}
+                   'wm_building': wm_building, 'wm_action': wm_action, 'wm_cols': wm_cols,
+                   'cc_building': np.array(cc_buildings, dtype='int32'), 'cc_limits': cc_limits, 'cc_members': cc_members}
     spec.table = np.ascontiguousarray(np.stack(cols, axis=1), dtype='float32')
     spec.columns = index
     spec.params = params
@@ -1310,7 +1374,7 @@ def finalize(spec: DistrictSpec) -> None:
 # ------------------------------------------------------------------------------------------------
 # observation layout
 # ------------------------------------------------------------------------------------------------
-def observation_layout(spec: DistrictSpec, central_agent: Optional[bool] = None, stale: bool = True):
+def observation_layout(spec: DistrictSpec, central_agent: Optional[bool] = None, stale: bool = True, names_order: bool = False):
     """Flat observation row of one env: list of (building index, name) and the matching device descriptors.
 
     Decentralised: concatenation of every building's active observations (citylearn/citylearn.py:482-483).
@@ -1319,21 +1383,37 @@ def observation_layout(spec: DistrictSpec, central_agent: Optional[bool] = None,
     Descriptor rows are int32 [L, 4] = (kind, a, b, building).  With `stale=True` (reference parity)
     demand / indoor-temperature observations read the dataset column; action-dependent ones are DYN slots which the
     step kernel zeroes after a step and fills at reset.
+
+    The row follows the order of the VALUES `Building.observations()` returns; `names_order=True` gives the entries in the order of the
+    NAMES (`active_observations`, the order of the observation space) instead - they differ for buildings with charging constraints,
+    where the reference itself is inconsistent (building.py:1146-1154 vs :811-833).
     """
     central = spec.central_agent if central_agent is None else central_agent
     entries: List[Tuple[int, str]] = []
     seen: List[str] = []
     for bi, b in enumerate(spec.buildings):
-        for name in b.active_observations:
+        for name in (names_order and b.active_observations) or b.observation_value_order or b.active_observations:
             if (not central) or bi == 0 or name not in spec.shared_observations or name not in seen:
                 entries.append((bi, name))
             if central and name in spec.shared_observations and name not in seen:
                 seen.append(name)
+    if names_order:
+        return entries, None
     desc = np.zeros((len(entries), 4), dtype='int32')
+    cc_index = {int(bi): k for k, bi in enumerate((spec.ev or {}).get('cc_building', []))}
     for j, (bi, name) in enumerate(entries):
         b = spec.buildings[bi]
         stale_ts = name in ('cooling_demand', 'heating_demand', 'dhw_demand', 'indoor_dry_bulb_temperature')
-        if name in DYN and not (stale and stale_ts):
+        cc = b.charging_constraints
+        if cc is not None and name in cc.state_names:
+            if name == 'charging_constraint_violation_kwh':
+                which = CC_SLOTS - 1
+            elif name == 'charging_building_headroom_kw':
+                which = 0
+            else:
+                which = 1 + next(i for i, ph in enumerate(cc.phases) if name == f"charging_phase_{ph['name']}_headroom_kw")
+            desc[j] = (OBS_STATE, cc_index[bi] * CC_SLOTS + which, 0, bi)
+        elif name in DYN and not (stale and stale_ts):
             desc[j] = (OBS_DYN, DYN[name], 0, bi)
         elif name == 'power_outage':
             desc[j] = (OBS_OUTAGE, 0, 0, bi)

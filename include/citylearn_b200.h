@@ -119,7 +119,9 @@ enum cl_obs_kind {
     CL_OBS_TS = 0,          /* a = table column: value of the series at the observed time step            */
     CL_OBS_DYN = 1,         /* a = cl_dyn slot of `building`; zero after a step in reference-parity mode  */
     CL_OBS_OUTAGE = 2,      /* power-outage signal of `building` at the observed time step                */
-    CL_OBS_TS_MINUS_TS = 3  /* reserved                                                                    */
+    CL_OBS_TS_MINUS_TS = 3, /* reserved                                                                    */
+    CL_OBS_STATE = 4        /* a = slot of the env's charging-constraint state (cl_ev_desc.cc_*): k * CL_CC_SLOTS + (0: building headroom kW;
+                               1..CL_MAX_PHASES: phase headroom kW; CL_CC_SLOTS - 1: violation kWh) of the last applied actions */
 };
 
 /* ---- built-in reward functions (citylearn/reward_function.py) ------------------------------------ */
@@ -130,7 +132,7 @@ enum cl_reward_id {
     CL_REWARD_SOLAR_PENALTY = 3,      /* SolarPenaltyReward :189-214                                       */
     CL_REWARD_COMFORT = 4,            /* ComfortReward :269-334  p[0]=band (NaN: series) p[1]=lower p[2]=higher exponent */
     CL_REWARD_SOLAR_PENALTY_AND_COMFORT = 5, /* :381-386         p[3], p[4] = coefficients                 */
-    CL_REWARD_ELECTRIC_VEHICLES = 6,  /* Electric_Vehicles_Reward_Function :389-523 (default weights; needs cl_ev_desc)      */
+    CL_REWARD_ELECTRIC_VEHICLES = 6,  /* Electric_Vehicles_Reward_Function :389-523 (default weights; needs cl_ev_desc) p[0] = charging-constraint penalty coefficient */
     CL_REWARD_NONE = -1               /* rewards are computed by the caller from the trace (custom RewardFunction) */
 };
 
@@ -152,6 +154,8 @@ enum cl_charger_param {
     CL_CH_C_X0, CL_CH_C_Y0 = CL_CH_C_X0 + 8, CL_CH_D_X0 = CL_CH_C_Y0 + 8, CL_CH_D_Y0 = CL_CH_D_X0 + 8, CL_NCHP = CL_CH_D_Y0 + 8
 };
 #define CL_MAX_CHARGERS_PER_BUILDING 4
+#define CL_MAX_PHASES 4
+#define CL_CC_SLOTS (2 + CL_MAX_PHASES)
 typedef struct cl_ev_desc {
     int32_t n_ev, n_chargers, n_machines;
     const double* ev_params;      /* [n_ev][CL_NPARAM]: the CL_P_BAT_* / curve / time-step entries of every vehicle battery      */
@@ -167,6 +171,16 @@ typedef struct cl_ev_desc {
     const int32_t* wm_cols;       /* [n_machines][4] table columns: window start, window end, load (sum of the profile), profile length.
                                      The load column is followed by max(profile length) - 1 columns holding the sum of the first 1, 2, ...
                                      entries: a cycle whose profile would run past the episode end adds only those (energy_model.py:1325-1327) */
+    /* charging constraints (citylearn/building.py:764-989): caps on the sum of a building's positive charger requests and on the
+       chargers of each phase; the step scales the charger actions down, keeps headroom / violation as per-env state (CL_OBS_STATE,
+       not touched by cl_reset - the reference does not reset it either) and Electric_Vehicles_Reward_Function subtracts
+       violation x reward_params[0].  May be 0 / NULL. */
+    int32_t n_constrained;
+    const int32_t* cc_building;   /* [n_constrained] ascending                                                                      */
+    const double* cc_limits;      /* [n_constrained][1 + CL_MAX_PHASES] kW: building cap, phase caps; NaN = none                    */
+    const int32_t* cc_members;    /* [n_constrained][CL_MAX_PHASES][CL_MAX_CHARGERS_PER_BUILDING] index of a phase's chargers within
+                                     the building's chargers, in the phase's list order, -1 = end                                   */
+    const int32_t* cc_flags;      /* [n_constrained] bit 0: the violation is exposed (observation, reward penalty)                  */
 } cl_ev_desc;
 
 typedef struct cl_district_desc {

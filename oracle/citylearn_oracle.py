@@ -95,6 +95,12 @@ class OracleEnv:
         for bi, b in enumerate(spec.buildings):
             self.dyn_weights.append(b.dynamics_weights if b.dynamics else None)
         self.evd = spec.ev if getattr(spec, 'ev', None) and (len(spec.ev.get('chargers', [])) or len(spec.ev.get('wms', []))) else None
+        if self.evd is not None:
+            # charging-constraint state (headroom per limit, violation): set by every apply_actions, NOT touched by reset (building.py:882-892)
+            lim = self.evd.get('cc_limits', np.zeros((0, 5)))
+            self.cc_state = np.zeros((num_envs, len(lim) * S.CC_SLOTS))
+            for k in range(len(lim)):
+                self.cc_state[:, k * S.CC_SLOTS:k * S.CC_SLOTS + lim.shape[1]] = lim[k]
 
     def _root(self, x):
         x = np.asarray(x, dtype=f64)
@@ -634,6 +640,74 @@ class OracleEnv:
         deg = np.where(charged, ceb32.astype(f64) / (2 * np.maximum(cap_deg, EPS)) * r, (ceb32 / w32(2 * np.maximum(cap, EPS))).astype(f64) * r)
         return soc, eb32, eff, np.maximum(cap_deg - deg, 0.0)
 
+    def _apply_charging_constraints(self, a, hours):
+        """`Building._apply_charging_constraints_to_actions` (citylearn/building.py:894-982) for every constrained building and env:
+        python-float arithmetic, sums in dictionary order (`0 + x0 + x1 ...`).  Updates the headroom / violation state the next
+        observation reports and returns the (float64) action matrix with the scaled charger actions."""
+        ev = self.evd
+        ccb = ev.get('cc_building', ())
+        if len(ccb) == 0:
+            return a
+        from citylearn_b200.ev import CHARGER_PARAMS as CP
+        a = np.array(a, dtype=f64)
+        nph = ev['cc_limits'].shape[1] - 1
+        for k, bi in enumerate(ccb):
+            ks = [i for i, c in enumerate(ev['chargers']) if c.building == bi]       # the building's chargers, in order
+            blim = ev['cc_limits'][k, 0]
+            plim = ev['cc_limits'][k, 1:]
+            members = [[int(m) for m in ev['cc_members'][k, j] if m >= 0] for j in range(nph)]
+            maxp = [float(ev['ch_params'][i][CP['MAX_C']]) for i in ks]
+            slots = [int(ev['ch_action'][i]) for i in ks]
+            for e in range(self.E):
+                req, scale = {}, {}
+                for j, sl in enumerate(slots):
+                    if sl < 0:
+                        continue
+                    act = float(a[e, sl])
+                    if act <= 0.0 or maxp[j] <= 0.0:
+                        continue
+                    req[j] = act * maxp[j]
+                    scale[j] = 1.0
+                state = self.cc_state[e, k * S.CC_SLOTS:(k + 1) * S.CC_SLOTS]
+                state[0] = blim
+                state[1:1 + nph] = plim
+                state[S.CC_SLOTS - 1] = 0.0
+                if not req:
+                    continue
+                viol = 0.0
+                total = sum(req.values())
+                if not np.isnan(blim) and blim >= 0.0 and total > blim:
+                    sc = 0.0 if blim == 0 else blim / total
+                    for j in scale:
+                        scale[j] *= sc
+                    viol += total - blim
+                for j_ph in range(nph):
+                    lim = plim[j_ph]
+                    if np.isnan(lim) or lim < 0.0:
+                        continue
+                    psum = sum(req.get(m, 0.0) * scale.get(m, 1.0) for m in members[j_ph] if m in req)
+                    if psum > lim:
+                        ps = 0.0 if lim == 0 else lim / psum
+                        for m in members[j_ph]:
+                            if m in scale:
+                                scale[m] *= ps
+                        viol += psum - lim
+                scaled = {j: req[j] * scale.get(j, 1.0) for j in req}
+                for j, sl in enumerate(slots):
+                    if sl < 0:
+                        continue
+                    act = float(a[e, sl])
+                    if act <= 0.0:
+                        continue
+                    a[e, sl] = 0.0 if maxp[j] <= 0.0 else max(0.0, min(act, scaled.get(j, 0.0) / maxp[j]))
+                used = sum(scaled.values())
+                state[0] = blim - used
+                for j_ph in range(nph):
+                    if not np.isnan(plim[j_ph]):
+                        state[1 + j_ph] = plim[j_ph] - sum(scaled.get(m, 0.0) for m in members[j_ph])
+                state[S.CC_SLOTS - 1] = viol * hours
+        return a
+
     def _ev_step(self, t, a):
         """`Charger.update_connected_electric_vehicle_soc` for every charger, `WashingMachine.start_cycle` for every machine
         (electric_vehicle_charger.py:283-329, energy_model.py:1311-1327); returns the per-building float32 consumption totals."""
@@ -647,6 +721,7 @@ class OracleEnv:
         past = np.zeros((E, nc), dtype=np.float32)
         info = {k: np.zeros((E, nc)) for k in ('connected', 'soc_prev', 'soc_now', 'capacity', 'min_capacity', 'required', 'hours')}
         hours = self.spec.seconds_per_time_step / 3600
+        a = self._apply_charging_constraints(a, hours)
         for k, c in enumerate(CH):
             slot = ev['ch_action'][k]
             q = ev['ch_params'][k]
@@ -820,6 +895,8 @@ class OracleEnv:
                 obs[:, j] = 0.0 if zero_dyn else dyn[:, bi, a]
             elif kind == S.OBS_OUTAGE:
                 obs[:, j] = self.outage[bi, t_eff]
+            elif kind == S.OBS_STATE:              # charging-constraint headroom / violation of the last applied actions (not reset)
+                obs[:, j] = self.cc_state[:, a]
         return obs
 
 
@@ -925,6 +1002,13 @@ class OracleReward:
             c_con = c_con + np.where((kwh < 0) & (net > 0), w['self_ev_consumption'] * mult, 0.0)
             c_con = c_con + np.where((kwh > 0) & (net > 0), -0.5 * w['self_ev_consumption'] * mult, 0.0)
             out[:, bi] = out[:, bi] + contrib + np.where(con, c_con, 0.0)
+        # charging-constraint penalty (reward_function.py:431-434): the violation the building reports, times the coefficient
+        coef = self.attrs.get('charging_constraint_penalty_coefficient')
+        coef = 1.0 if coef is None else float(coef)
+        for k, bi in enumerate(env.evd.get('cc_building', ())):
+            if env.spec.buildings[bi].charging_constraints.expose_violation:
+                viol = env.cc_state[:, k * S.CC_SLOTS + S.CC_SLOTS - 1]
+                out[:, bi] = out[:, bi] - np.where(viol > 0.0, viol * coef, 0.0)
         if env.central:
             tot = np.zeros((E, 1))
             for bi in range(B):

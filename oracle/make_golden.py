@@ -288,6 +288,10 @@ EV_CASES = {
     # step lies inside the episode are added (energy_model.py:1325-1327)
     'c10_evs_short': dict(dataset='citylearn_challenge_2022_phase_all_plus_evs', steps=51, seed=23, np_seed=7,
                           overrides={'episode_time_steps': 52}, hold={'washing_machine_1': 50}),
+    # charging constraints (building.py:764-989): Building_15's two chargers under a 12 kW building cap and 7 / 5 kW phase caps; actions of
+    # the constrained chargers are biased towards charging so that the caps bind (scaled actions, headroom / violation observations, reward
+    # penalty)
+    'c11_constraints': dict(dataset='citylearn_charging_constraints_demo', steps=240, seed=31, np_seed=8),
     'c10_evs_reward': dict(dataset='citylearn_challenge_2022_phase_all_plus_evs', steps=120, seed=22, np_seed=6),
 }
 

@@ -36,7 +36,10 @@ def oracle_reset(env, spec):
 @pytest.mark.parametrize('case', CASES)
 def test_loader_reproduces_reference_names_and_spaces(case):
     z, cfg, meta, spec = load(case)
-    assert [list(b.active_observations) for b in spec.buildings] == meta['observation_names']
+    # env.observation_names are the keys of Building.observations() (value order); the space follows active_observations - the two orders
+    # differ for a building with charging constraints (reference quirk, kept)
+    assert [list(b.observation_value_order or b.active_observations) for b in spec.buildings] == meta['observation_names']
+    assert [list(b.active_observations) for b in spec.buildings] == [m['active_observations'] for m in meta['buildings']]
     assert [list(b.active_actions) for b in spec.buildings] == meta['action_names']
     for b, lo, hi, alo, ahi in zip(spec.buildings, meta['observation_low'], meta['observation_high'], meta['action_low'], meta['action_high']):
         assert np.array_equal(b.observation_low, np.float32(lo)) and np.array_equal(b.observation_high, np.float32(hi))
@@ -123,12 +126,14 @@ def test_gpu_single_env_matches_reference_bit_for_bit(case):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize('precision', ['fp64', 'fp32'])
-def test_gpu_batched_envs_match_oracle(precision):
-    """96 envs with different action sequences (exact zeros included), 160 steps of the reward case, against the vectorised oracle:
-    bit-exact in the fp64 flow, north-star tolerance in fp32; one `rollout` launch equals the step-by-step run."""
+@pytest.mark.parametrize('case,precision', [('c10_evs_reward', 'fp64'), ('c10_evs_reward', 'fp32'), ('c11_constraints', 'fp64')])
+def test_gpu_batched_envs_match_oracle(case, precision):
+    """96 envs with different action sequences (exact zeros included), 160 steps (Electric_Vehicles_Reward_Function; with and without
+    charging constraints - scaled actions, headroom / violation observations, reward penalty), against the vectorised oracle:
+    bit-exact in the fp64 flow; fp32: 1e-4 scaled for observations / district sums / SOCs, threshold flips of the reward's step terms
+    in under 0.1 % of the entries; one `rollout` launch equals the step-by-step run."""
     import torch
-    z, cfg, meta, spec = load('c10_evs_reward')
+    z, cfg, meta, spec = load(case)
     E, K = 96, 160
     env = make_gpu_env(cfg, num_envs=E, precision=precision)
     ora = OracleEnv(spec, E, libm_pow=False)
@@ -144,7 +149,7 @@ def test_gpu_batched_envs_match_oracle(precision):
     rr = torch.zeros((K, E, roll._reward_dim), device='cuda')
     rd = torch.zeros((K, E, 3), device='cuda')
     roll.rollout(torch.as_tensor(acts, device='cuda'), ro, rr, rd)
-    worst = 0.0
+    worst, flips, total = 0.0, 0, 1
     for k in range(K):
         obs, rew, term, _, _ = env.step(torch.as_tensor(acts[k], device='cuda'))
         oo, orw, od, _ = ora.step(acts[k])
@@ -155,10 +160,13 @@ def test_gpu_batched_envs_match_oracle(precision):
             if precision == 'fp64':
                 assert np.array_equal(got[name], ref[name]), f'{name} step {k}: {np.abs(got[name] - ref[name]).max()}'
             else:
-                scale = np.maximum(np.abs(ref[name]), 1.0)
-                worst = max(worst, float((np.abs(got[name] - ref[name]) / scale).max()))
+                err = np.abs(got[name] - ref[name]) / np.maximum(np.abs(ref[name]), 1.0)
+                if name == 'reward':          # the charger terms are step functions of the SOC: float32 rounding may flip one
+                    flips += int((err > 1e-3).sum()); total += err.size
+                else:
+                    worst = max(worst, float(err.max()))
         assert torch.equal(ro[k], obs) and torch.equal(rr[k], rew) and torch.equal(rd[k], env.district), f'rollout step {k}'
-    assert worst <= 1e-4, worst
+    assert worst <= 1e-4 and flips <= 1e-3 * total, (worst, flips, total)
 
 
 @pytest.mark.gpu
@@ -197,7 +205,7 @@ def test_gpu_unsupported_combinations_fail_loudly():
         make_gpu_env(cfg, num_envs=4, stale_observations=False)
     with pytest.raises(NotImplementedError):
         make_gpu_env(cfg, num_envs=4, track_kpis=True)
-    env = make_gpu_env(cfg, num_envs=4)
+    env = make_gpu_env(cfg, num_envs=4, episode_time_steps=48)
     with pytest.raises(NotImplementedError):
         env.reset(options={'episode_start': torch.tensor([0, 24, 48, 72])})
     with pytest.raises(RuntimeError):

@@ -19,6 +19,7 @@ DEFAULT = [
     'citylearn_challenge_2023_phase_2_online_evaluation_1', 'citylearn_challenge_2023_phase_2_online_evaluation_2',
     'citylearn_challenge_2023_phase_2_online_evaluation_3',
     'citylearn_challenge_2023_phase_3_1', 'citylearn_challenge_2023_phase_3_2', 'citylearn_challenge_2023_phase_3_3',
+    'citylearn_challenge_2022_phase_all_plus_evs', 'citylearn_charging_constraints_demo',
 ]
 
 if __name__ == '__main__':
