@@ -574,7 +574,11 @@ def main():
     # ---------------- end to end through the public API with host buffers ----------------
     def e2e_loop(full):
         env.reset()
-        host_acts = np.random.RandomState(7 + rank).uniform(-1, 1, size=(W + K, E, A)).astype('float32')
+        # this step's actions wait in page-locked host memory (the contract's "host->device copy ... from pinned host memory"): a host-side
+        # policy writes them there; every step copies ITS OWN [E, A] block to the device inside the timed region
+        host_pinned = torch.empty((W + K, E, A), dtype=torch.float32).pin_memory()
+        host_acts = host_pinned.numpy()
+        host_acts[...] = np.random.RandomState(7 + rank).uniform(-1, 1, size=(W + K, E, A)).astype('float32')
         for k in range(W):
             env.step_host(host_acts[k], full_observations=full)
         torch.cuda.synchronize(dev)
@@ -684,7 +688,7 @@ def main():
                      'avg_launch_us': ms_med * 1e3, 'peak_source': 'MEASURED_PEAKS.json hbm_gbs' if peaks else 'fallback 6650'},
         'cpu_baseline': cpu,
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': E * A * 4, 'd2h_bytes_per_step': L * 4 + E * B * 4,
-                'ms_per_step': e2e_ms / K, 'api': 'CityLearnEnv.step_host(ndarray): shared observation row + rewards cross PCIe'},
+                'ms_per_step': e2e_ms / K, 'api': 'CityLearnEnv.step_host(ndarray) -> cl_step_host: per step H2D of the [E, A] actions from page-locked host memory, step kernel, D2H of rewards + the observation row all envs share, stream sync'},
         'e2e_full_observations': {'value': world * units_per_step * K / (e2e_full_ms * 1e-3), 'unit': UNIT, 'ms_per_step': e2e_full_ms / K,
                                   'd2h_bytes_per_step': E * L * 4 + E * B * 4},
         'e2e_rollout_host': {'value': world * units_per_step * K / float(blk_s.item()), 'unit': UNIT, 'ms_per_step': 1e3 * float(blk_s.item()) / K,

@@ -75,6 +75,7 @@ def load():
     lib.cl_rollout.argtypes = [vp, i32, vp, vp, vp, vp, vp]
     lib.cl_device_time_enable.argtypes = [vp, vp]
     lib.cl_ev_read.argtypes = [vp, vp, vp, vp]
+    lib.cl_step_host.argtypes = [vp] * 9 + [ctypes.c_size_t, vp]
     lib.cl_exchange_create.argtypes = [vp, i32, i32, vp, ctypes.POINTER(vp)]
     lib.cl_exchange_connect.argtypes = [vp, vp]
     lib.cl_exchange_connect_ptrs.argtypes = [vp, ctypes.POINTER(vp), vp]
@@ -98,7 +99,7 @@ def load():
     for name in ('cl_create', 'cl_destroy', 'cl_set_outage', 'cl_reset', 'cl_step', 'cl_rollout', 'cl_obs_rows', 'cl_time_step',
                  'cl_state_size', 'cl_get_state', 'cl_set_state', 'cl_launch_count', 'cl_launch_geometry', 'cl_set_transforms',
                  'cl_kpi_enable', 'cl_kpi_accumulate', 'cl_kpi_read', 'cl_measure_fma_peak', 'cl_device_time_enable', 'cl_advance_device',
-                 'cl_launch_occupancy', 'cl_kpi_fused', 'cl_ev_read', 'cl_exchange_create', 'cl_exchange_connect', 'cl_exchange_connect_ptrs', 'cl_exchange_status'):
+                 'cl_launch_occupancy', 'cl_kpi_fused', 'cl_ev_read', 'cl_step_host', 'cl_exchange_create', 'cl_exchange_connect', 'cl_exchange_connect_ptrs', 'cl_exchange_status'):
         getattr(lib, name).restype = ctypes.c_int
     if lib.cl_abi_version() != ABI_VERSION:
         raise NativeLibraryError(f'{path}: ABI version {lib.cl_abi_version()} != {ABI_VERSION}; rebuild the extension')
@@ -206,6 +207,12 @@ class Handle:
 
     def rollout(self, n_steps: int, actions_ptr, obs_ptr, reward_ptr, district_ptr, stream: int):
         check(self.lib.cl_rollout(self.ptr, int(n_steps), actions_ptr, obs_ptr, reward_ptr, district_ptr, stream), 'cl_rollout')
+
+    def step_host(self, actions_host_ptr, actions_dev_ptr, obs_ptr, reward_ptr, district_ptr, row_ptr, d2h_src_ptr, d2h_dst_ptr, d2h_bytes: int, stream: int):
+        rc = self.lib.cl_step_host(self.ptr, actions_host_ptr, actions_dev_ptr, obs_ptr, reward_ptr, district_ptr, row_ptr, d2h_src_ptr, d2h_dst_ptr,
+                                   d2h_bytes, stream)
+        if rc:
+            check(rc, 'cl_step_host')
 
     def ev_read(self, soc_prev_ptr, soc_ptr, stream: int):
         check(self.lib.cl_ev_read(self.ptr, soc_prev_ptr, soc_ptr, stream), 'cl_ev_read')

@@ -2457,6 +2457,34 @@ extern "C" int cl_step(cl_env* env, const float* actions, float* obs, float* rew
     return publish_time(env, static_cast<cudaStream_t>(stream));
 }
 
+// One step end to end from host buffers in ONE call: H2D of the actions, the step kernel, (optionally) the observation row all envs
+// share, ONE D2H of the caller's result range, stream synchronisation.  Every buffer is the caller's (pinned host memory makes both
+// copies asynchronous DMA transfers).
+extern "C" int cl_step_host(cl_env* env, const float* actions_host, float* actions_dev, float* obs_dev, float* reward_dev, float* district_dev,
+                            float* row_dev, const void* d2h_src_dev, void* d2h_dst_host, size_t d2h_bytes, cl_stream stream) {
+    if (!env || !actions_host || !actions_dev) return fail(CL_ERR_INVALID, "cl_step_host: null argument");
+    if (d2h_bytes && (!d2h_src_dev || !d2h_dst_host)) return fail(CL_ERR_INVALID, "cl_step_host: null result range");
+    if (env->t < 0) return fail(CL_ERR_STATE, "cl_step_host: call cl_reset first");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    { const int rc = refresh_time(env, st); if (rc) return rc; }
+    if (env->t >= env->T - 1) return fail(CL_ERR_STATE, "cl_step_host: episode has ended (terminated); call cl_reset");
+    if (row_dev && (!env->d.stale || !env->d.uniform_start || env->d.obs_state))
+        return fail(CL_ERR_STATE, "cl_step_host: the observation row is only shared by all envs with stale_observations, one episode window and no per-env state columns");
+    CUDA_TRY(cudaMemcpyAsync(actions_dev, actions_host, sizeof(float) * (size_t)env->d.E * (size_t)std::max(env->d.A, 1), cudaMemcpyHostToDevice, st));
+    { const int rc = dispatch_advance(env, 1, actions_dev, obs_dev, reward_dev, district_dev, nullptr, st); if (rc) return rc; }
+    if (row_dev) {
+        const long total = env->d.L;
+        obs_rows_kernel<<<(unsigned)std::min<long>((total + 255) / 256, 4096), 256, 0, st>>>(env->d, env->t + 1, 1, row_dev);
+        env->launches++;
+    }
+    CUDA_TRY(cudaGetLastError());
+    if (d2h_bytes) CUDA_TRY(cudaMemcpyAsync(d2h_dst_host, d2h_src_dev, d2h_bytes, cudaMemcpyDeviceToHost, st));
+    env->t += 1;
+    { const int rc = publish_time(env, st); if (rc) return rc; }
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return CL_OK;
+}
+
 extern "C" int cl_rollout(cl_env* env, int32_t n_steps, const float* actions, float* obs, float* reward, float* district, cl_stream stream) {
     if (!env || !actions) return fail(CL_ERR_INVALID, "cl_rollout: null argument");
     if (n_steps < 1) return fail(CL_ERR_INVALID, "cl_rollout: n_steps must be >= 1");

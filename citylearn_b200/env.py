@@ -315,6 +315,13 @@ class CityLearnEnv:
             self._reward_pinned = self._out_pinned[nL:nL + nR].view(E, self._reward_dim)
             self._obs_host, self._reward_host = self._obs_pinned.numpy(), self._reward_pinned.numpy()
             self._row_host = self._out_pinned[nL + nR:].numpy()
+            self._row_view = np.broadcast_to(self._row_host, (E, self._obs_dim))
+            # single-call host step (cl_step_host): possible when nothing but the fused kernel has to run per step
+            self._host_fast = (rid >= 0 and self._trace is None and not self._track and not self._record and not self.auto_reset
+                               and (not self._track_kpis or self._kpi_fused))
+            self._host_ptrs = {'act': self._act.data_ptr(), 'obs': self._obs.data_ptr(), 'reward': self._reward.data_ptr(), 'row': self._row.data_ptr(),
+                               'district': self._district.data_ptr(), 'obs_host': self._obs_pinned.data_ptr(), 'reward_host': self._reward_pinned.data_ptr()}
+            self._pinned_action_buffers: List[torch.Tensor] = []
             self._roll = None                   # buffers of rollout_host, keyed by K
 
     def configure_transforms(self, observation_transform: Optional[str] = 'unchanged', normalized_actions: Optional[bool] = None):
@@ -635,6 +642,35 @@ class CityLearnEnv:
         if shared and not self.shared_observation_row:
             raise ValueError('full_observations=False needs stale_observations=True and one episode window for all envs')
         E, L, R = self.num_envs, self._obs_dim, self._reward_dim
+        if self._host_fast and not self.terminated:
+            # the whole step in ONE native call (cl_step_host): H2D, kernel, shared row, one D2H, sync - no torch ops on the way
+            a = actions if type(actions) is np.ndarray else np.asarray(actions, dtype=np.float32)
+            if a.dtype == np.float32 and a.flags.c_contiguous and a.size == self._act.numel():
+                # copied to the device straight from the caller's memory: an asynchronous DMA transfer when it is page-locked
+                # (`pinned_actions()`), staged by the driver when it is pageable
+                src = a.__array_interface__['data'][0]
+            else:
+                a = np.asarray(a, dtype=np.float32).reshape(E, -1)
+                if a.shape[1] != self.spec.action_dim:
+                    raise ValueError(f'actions must have shape [{E}, {self.spec.action_dim}]')
+                np.copyto(self._stage_host[0], a)
+                src = self._stage_pinned[0].data_ptr()
+            p = self._host_ptrs
+            if torch.cuda.current_device() != self.device.index:
+                with torch.cuda.device(self.device):
+                    return self.step_host(actions, full_observations)
+            st = torch.cuda.current_stream(self.device).cuda_stream
+            if shared:
+                self._h.step_host(src, p['act'], None, p['reward'], p['district'], p['row'], p['reward'], p['reward_host'], 4 * (E * R + L), st)
+            else:
+                self._h.step_host(src, p['act'], p['obs'], p['reward'], p['district'], None, p['obs'], p['obs_host'], 4 * E * (L + R), st)
+            self._obs_current = not shared
+            self._hist_valid = False
+            self.time_step += 1
+            terminated = self.terminated
+            if shared:
+                return self._row_view, self._reward_host, terminated
+            return self._obs_host, self._reward_host, terminated
         _, _, terminated, _, _ = self._advance(np.asarray(actions, dtype=np.float32), not shared)
         with torch.cuda.device(self.device):
             if shared:
@@ -646,6 +682,16 @@ class CityLearnEnv:
         if shared:
             return np.broadcast_to(self._row_host, (E, L)), self._reward_host, terminated
         return self._obs_host, self._reward_host, terminated
+
+    def pinned_actions(self, n: int = 1) -> List[np.ndarray]:
+        """`n` page-locked `[E, A]` float32 arrays owned by the env (kept alive with it): actions written into one of them reach the device
+        by DMA straight from that memory when passed to `step_host` (any page-locked array does; pageable ones are staged by the driver)."""
+        out = []
+        for _ in range(int(n)):
+            t = torch.zeros((self.num_envs, max(self.spec.action_dim, 1)), dtype=torch.float32).pin_memory()
+            self._pinned_action_buffers.append(t)
+            out.append(t.numpy())
+        return out
 
     def rollout_host(self, actions: np.ndarray, full_observations: Optional[bool] = None):
         """K steps from a host block of actions `[K, E, A]`: one H2D copy, one `cl_rollout` launch, one D2H copy, one sync.

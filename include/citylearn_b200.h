@@ -295,6 +295,17 @@ int cl_state_size(const cl_env* env, size_t* bytes);
 int cl_get_state(cl_env* env, void* dst_dev, cl_stream stream);
 int cl_set_state(cl_env* env, const void* src_dev, int32_t time_step, cl_stream stream);
 
+/*
+ * One step end to end from HOST actions in one call (CityLearnEnv.step as a host-side training loop sees it, citylearn.py:978-1056):
+ * copies actions_host [E][action_dim] to actions_dev, runs cl_step into obs_dev (NULL: not materialised) / reward_dev / district_dev
+ * (NULL allowed), writes the observation row every env shares at the new time step to row_dev [L] (NULL: skip; needs reference-parity
+ * observations and one episode window), copies d2h_bytes from d2h_src_dev to d2h_dst_host (the caller lays its result buffers out so
+ * that ONE range covers what it wants back, e.g. [reward | row]) and synchronises the stream.  With pinned host memory both copies are
+ * asynchronous DMA transfers; pageable memory works but is staged by the driver.
+ */
+int cl_step_host(cl_env* env, const float* actions_host, float* actions_dev, float* obs_dev, float* reward_dev, float* district_dev,
+                 float* row_dev, const void* d2h_src_dev, void* d2h_dst_host, size_t d2h_bytes, cl_stream stream);
+
 /* Per-vehicle SOC entries of every env: soc_prev, soc dev [E][n_ev] float (soc[t-1], soc[t]) - diagnostics / parity tests. */
 int cl_ev_read(cl_env* env, float* soc_prev_dev, float* soc_dev, cl_stream stream);
 

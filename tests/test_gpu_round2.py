@@ -198,3 +198,45 @@ def test_episode_start_validation():
     out = CityLearnEnv(src.schema(), data_source=src, num_envs=2)
     with pytest.raises(ValueError):
         out.reset(options={'episode_start': torch.tensor([0, 0])})
+
+
+def test_step_host_single_call_path_equals_the_staged_path():
+    """`cl_step_host` (one native call per step) against the torch-staged path (an env that tracks episode rewards keeps it): same
+    observations / rewards from page-locked, pageable, non-contiguous and nested-list actions; both observation modes."""
+    from citylearn_b200 import CityLearnEnv
+    E, K = 64, 12
+    fast = CityLearnEnv(PALL, num_envs=E)
+    slow = CityLearnEnv(PALL, num_envs=E, track_episode_rewards=True)
+    assert fast._host_fast and not slow._host_fast
+    rng = np.random.RandomState(4)
+    pinned = fast.pinned_actions(2)
+    n0 = fast.gpu_launches
+    for k in range(K):
+        a = rng.uniform(-1, 1, size=(E, 17)).astype('float32')
+        if k % 4 == 0:
+            np.copyto(pinned[k % 2], a); arg = pinned[k % 2]
+        elif k % 4 == 1:
+            arg = a
+        elif k % 4 == 2:
+            arg = np.asfortranarray(a)                   # not C-contiguous: staged
+        else:
+            arg = a.astype('float64')                    # wrong dtype: staged
+        full = k >= K // 2
+        o1, r1, t1 = fast.step_host(arg, full_observations=full or None)
+        o2, r2, t2 = slow.step_host(a, full_observations=full or None)
+        assert np.array_equal(o1, o2) and np.array_equal(r1, r2) and t1 == t2, k
+    assert fast.time_step == slow.time_step == K and fast._h.time_step() == K
+    assert fast.gpu_launches - n0 >= K
+    assert torch.equal(fast.observations, slow.observations)
+    # the device-side step continues from the same state
+    act = torch.zeros((E, 17), device='cuda')
+    assert torch.equal(fast.step(act)[1], slow.step(act)[1])
+    with pytest.raises(ValueError):
+        fast.step_host(np.zeros((E, 3), dtype='float32'))
+    # episode end: the last step reports terminated, the next call raises like step()
+    short = CityLearnEnv(PALL, num_envs=4, episode_time_steps=4)
+    for k in range(3):
+        _, _, term = short.step_host(np.zeros((4, 17), dtype='float32'))
+    assert term
+    with pytest.raises(RuntimeError):
+        short.step_host(np.zeros((4, 17), dtype='float32'))
