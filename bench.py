@@ -572,8 +572,9 @@ def main():
     value = world * units_per_step * K / (ms_max * 1e-3)
 
     # ---------------- end to end through the public API with host buffers ----------------
-    def e2e_loop(full):
+    def e2e_loop(full, in_place=True):
         env.reset()
+        env._host_in_place = 1 if in_place else 0
         # this step's actions wait in page-locked host memory (the contract's "host->device copy ... from pinned host memory"): a host-side
         # policy writes them there; every step copies ITS OWN [E, A] block to the device inside the timed region
         host_pinned = torch.empty((W + K, E, A), dtype=torch.float32).pin_memory()
@@ -599,6 +600,8 @@ def main():
         return float(tt.item()), acc
     e2e_ms, e2e_sum = e2e_loop(None)                   # shared observation row (reference-parity rows are env-independent)
     e2e_full_ms, _ = e2e_loop(True)                    # full [E, L] copy, for comparison
+    e2e_dma_ms, _ = e2e_loop(None, in_place=False)     # same as e2e, but DMA copies before / after the kernel instead of in-place access
+    env._host_in_place = 1
     # K steps as ONE host call: one H2D of [K, E, A], one launch, one D2H of rewards + K rows
     env.reset()
     blk = np.random.RandomState(9 + rank).uniform(-1, 1, size=(K, E, A)).astype('float32')
@@ -688,9 +691,11 @@ def main():
                      'avg_launch_us': ms_med * 1e3, 'peak_source': 'MEASURED_PEAKS.json hbm_gbs' if peaks else 'fallback 6650'},
         'cpu_baseline': cpu,
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': E * A * 4, 'd2h_bytes_per_step': L * 4 + E * B * 4,
-                'ms_per_step': e2e_ms / K, 'api': 'CityLearnEnv.step_host(ndarray) -> cl_step_host: per step H2D of the [E, A] actions from page-locked host memory, step kernel, D2H of rewards + the observation row all envs share, stream sync'},
+                'ms_per_step': e2e_ms / K, 'api': 'CityLearnEnv.step_host(ndarray) -> cl_step_host, one native call per step: the step kernel reads the [E, A] actions from page-locked host memory and writes the rewards + the observation row all envs share back to it over PCIe (in place), stream sync'},
         'e2e_full_observations': {'value': world * units_per_step * K / (e2e_full_ms * 1e-3), 'unit': UNIT, 'ms_per_step': e2e_full_ms / K,
                                   'd2h_bytes_per_step': E * L * 4 + E * B * 4},
+        'e2e_dma_copies': {'value': world * units_per_step * K / (e2e_dma_ms * 1e-3), 'unit': UNIT, 'ms_per_step': e2e_dma_ms / K,
+                           'api': 'the same call with cudaMemcpyAsync H2D / D2H around the kernel instead of in-place PCIe access'},
         'e2e_rollout_host': {'value': world * units_per_step * K / float(blk_s.item()), 'unit': UNIT, 'ms_per_step': 1e3 * float(blk_s.item()) / K,
                              'api': 'CityLearnEnv.rollout_host(ndarray [K, E, A]): one H2D, one launch, one D2H (wall clock incl. host memcpy)'},
         'gpu_launches': int(launches),

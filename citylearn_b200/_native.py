@@ -75,7 +75,7 @@ def load():
     lib.cl_rollout.argtypes = [vp, i32, vp, vp, vp, vp, vp]
     lib.cl_device_time_enable.argtypes = [vp, vp]
     lib.cl_ev_read.argtypes = [vp, vp, vp, vp]
-    lib.cl_step_host.argtypes = [vp] * 9 + [ctypes.c_size_t, vp]
+    lib.cl_step_host.argtypes = [vp] * 9 + [ctypes.c_size_t, i32, vp]
     lib.cl_exchange_create.argtypes = [vp, i32, i32, vp, ctypes.POINTER(vp)]
     lib.cl_exchange_connect.argtypes = [vp, vp]
     lib.cl_exchange_connect_ptrs.argtypes = [vp, ctypes.POINTER(vp), vp]
@@ -208,9 +208,10 @@ class Handle:
     def rollout(self, n_steps: int, actions_ptr, obs_ptr, reward_ptr, district_ptr, stream: int):
         check(self.lib.cl_rollout(self.ptr, int(n_steps), actions_ptr, obs_ptr, reward_ptr, district_ptr, stream), 'cl_rollout')
 
-    def step_host(self, actions_host_ptr, actions_dev_ptr, obs_ptr, reward_ptr, district_ptr, row_ptr, d2h_src_ptr, d2h_dst_ptr, d2h_bytes: int, stream: int):
+    def step_host(self, actions_host_ptr, actions_dev_ptr, obs_ptr, reward_ptr, district_ptr, row_ptr, d2h_src_ptr, d2h_dst_ptr, d2h_bytes: int,
+                  in_place: int, stream: int):
         rc = self.lib.cl_step_host(self.ptr, actions_host_ptr, actions_dev_ptr, obs_ptr, reward_ptr, district_ptr, row_ptr, d2h_src_ptr, d2h_dst_ptr,
-                                   d2h_bytes, stream)
+                                   d2h_bytes, in_place, stream)
         if rc:
             check(rc, 'cl_step_host')
 

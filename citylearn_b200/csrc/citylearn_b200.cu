@@ -577,7 +577,7 @@ struct SmemLayout {
 __host__ __device__ __forceinline__ SmemLayout smem_layout(int B, int Wp, int L, int epb, int nt, int rsize, int lstm_smem = 0, int tab_layout = 0, int fresh_slots = 0, int n_curves = 0, int kpi = 0) {
     SmemLayout o;
     o.Lp = (L + 3) & ~3;
-    int f = 16;                                  // 64 bytes of mbarriers: 3 time-row slots + 2 observation-row buffers
+    int f = 32;                                  // 128 bytes of mbarriers: 3 time-row slots + 2 observation-row buffers + 6 hand-offs of the DEC instantiation
     const int nc = n_curves > 0 ? n_curves : B;       // (districts with vehicles pass B + ev_n: the vehicles' battery curves follow the buildings')
     o.curves = f; f += nc * kCurveTab * (rsize / 4);  // first: keeps doubles 8-byte aligned
     o.clut = f; f += nc * kCurveLutFloats;            // uniform-grid index of the curve abscissae (bytes)
@@ -749,7 +749,14 @@ __device__ __forceinline__ void kpi_push(double* a, double x);
 #define CL_DYN_MINBLOCKS 1
 #endif
 constexpr int kDynMaxT = CL_DYN_MAXT;
-template <typename R, bool THERMAL, bool DYNAMICS, int MAXT, bool WIDE = false, bool KPI = false, bool EVD = false>
+// producer / consumer hand-offs of the DEC instantiation below: mbarriers in shared memory - producers arrive (release), consumers
+// poll the phase parity (acquire) WITHOUT arriving, so a consumer never waits for its fellow consumers (a named `bar.sync id, n` is a
+// barrier among all n threads: tried first, it was slower than the plain block barrier)
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <typename R, bool THERMAL, bool DYNAMICS, int MAXT, bool WIDE = false, bool KPI = false, bool EVD = false, bool DEC = false>
 __global__ void __launch_bounds__(MAXT, (DYNAMICS && MAXT == CL_DYN_MAXT) ? CL_DYN_MINBLOCKS : 1) advance_kernel(Dev d, int t0, int K, const float* __restrict__ actions, float* __restrict__ obs,
                                                         float* __restrict__ reward, float* __restrict__ district, float* __restrict__ trace) {
     extern __shared__ __align__(16) float smf[];
@@ -806,6 +813,16 @@ __global__ void __launch_bounds__(MAXT, (DYNAMICS && MAXT == CL_DYN_MAXT) ? CL_D
     const bool tmpl_path = obs != nullptr && uniform && d.stale && !d.obs_state;      // (per-env state columns: general writer)
     const bool need_dsum = (d.reward_id == CL_REWARD_MARL || d.reward_id == CL_REWARD_ELECTRIC_VEHICLES) && reward != nullptr;
     constexpr bool has_ev = EVD && !WIDE && !DYNAMICS;                  // chargers / washing machines: a separate instantiation (like KPI)
+    // DEC: no block-wide barrier inside the step.  When nothing in the step reads the district sum (default-type rewards, decentralised
+    // agents, reference-parity observations, one episode window) the physics warps do not depend on each other: a step barrier only
+    // makes every warp wait for the slowest one of THAT step (divergent charge / discharge paths: 15 % of the stall samples).  Here the
+    // barrier is split in time: a warp ARRIVES when its step-k results are in shared memory, goes on with the physics of step k + 1 and
+    // only then WAITS for the arrivals of step k - by then a whole step old - to add up its share of the district sums of step k.
+    // mbarriers in shared memory (s_bar + 5 ..), two of each by step parity p = k & 1:
+    //   A[p] (5, 6)   helper -> physics   per-building inputs of step k are in shared memory                    1 arrival per phase
+    //   R[p] (7, 8)   physics -> all      step k: red[p] written, row t and the inputs of parity p read         1 arrival per physics warp
+    //   S[p] (9, 10)  physics -> physics  the sums of step k have been read out of red[p] (written again at step k + 2)   "
+    constexpr bool dec = DEC && !WIDE && !DYNAMICS && !KPI && !EVD;
     const bool fused_reward = reward != nullptr && d.reward_id >= 0;
     const bool central_sync = fused_reward && d.central;
     const int Rdim = d.central ? 1 : B;
@@ -817,6 +834,7 @@ __global__ void __launch_bounds__(MAXT, (DYNAMICS && MAXT == CL_DYN_MAXT) ? CL_D
     const bool coupled = WIDE && d.coupled;                        // cross-tile sums needed inside the step
     if (uniform && tid == 0) {
         for (int i = 0; i < 5; ++i) mbar_init(s_bar + i, 1);
+        if (dec) { for (int i = 5; i < 11; ++i) mbar_init(s_bar + i, i >= 7 ? (np_ >> 5) : 1); }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         for (int i = 0; i < 3 && i <= K; ++i) {     // rows t0 .. t0+2 (row t0+K is the last one any step needs)
             mbar_expect_tx(s_bar + i, row_bytes);
@@ -974,9 +992,17 @@ __global__ void __launch_bounds__(MAXT, (DYNAMICS && MAXT == CL_DYN_MAXT) ? CL_D
                     project_row(bb, t + 1, row_next, lane); project_row(bb, t + 1, row_next, lane + 32);
                 }
             }
+            if (dec) {
+                __syncwarp();
+                if (lane == 0) {
+                    if (k == 0) mbar_arrive(s_bar + 5);                         // A[0]: the prologue's inputs of step 0
+                    if (k + 1 < K) mbar_arrive(s_bar + 5 + ((k + 1) & 1));      // A: the inputs of step k + 1 are in place
+                }
+            } else {
             if (coupled) cluster_sync_all(); else __syncthreads();             // S1
             if (need_dsum) __syncthreads();                                    // S2
             if (central_sync) { if (WIDE) cluster_sync_all(); else { if (k > 0) __syncthreads(); __syncthreads(); } }
+            }
             if (tab_path) {
                 // observation slab of step k straight from the precomputed table: buffer pb holds columns [k0, k1) of table row
                 // start0 + t + 1 (requested one step ago) - ONE image shared by every env (reference-parity rows are env-independent) or,
@@ -1046,6 +1072,15 @@ __global__ void __launch_bounds__(MAXT, (DYNAMICS && MAXT == CL_DYN_MAXT) ? CL_D
                 __syncthreads();
             }
             if (has_ev && k + 1 < K) __syncthreads();
+            if (dec) {
+                mbar_wait(s_bar + 7 + pb, (uint32_t)((k >> 1) & 1));            // R: every physics warp has finished step k
+                if (lane == 0 && k + 3 <= K) {
+                    // nobody reads row t any more: its slot takes the row of step t + 3
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    mbar_expect_tx(s_bar + slot_t, row_bytes);
+                    tma_load_1d(s_rows + slot_t * Wp, d.table + (size_t)(d.start0 + t + 3) * Wp, row_bytes, s_bar + slot_t);
+                }
+            }
             continue;
         }
 
@@ -1055,6 +1090,9 @@ __global__ void __launch_bounds__(MAXT, (DYNAMICS && MAXT == CL_DYN_MAXT) ? CL_D
         ChargerInfo chi[CL_MAX_CHARGERS_PER_BUILDING];
         int n_chi = 0;
         double cc_penalty = 0.0;          // charging-constraint violation x coefficient of this step (ev_reward)
+        if (dec) {
+            mbar_wait(s_bar + 5 + pb, (uint32_t)((k >> 1) & 1));                       // A: this step's per-building inputs (helper warp, one step ahead)
+        }
         if (active) {
             UnitInputs<R> in;
             load_inputs<R, THERMAL>(d, c, row, b, t, in, uniform);
@@ -1241,6 +1279,7 @@ __global__ void __launch_bounds__(MAXT, (DYNAMICS && MAXT == CL_DYN_MAXT) ? CL_D
 #endif
                 t_in = lstm_update<R, kConstW>(d, c, lstm_w, u, t, start_e, cd, t_in, use_pre ? s_pre + (size_t)b * kLstmPreRing * 64 : nullptr, b);
             }
+            if (dec && k >= 2) mbar_wait(s_bar + 9 + pb, (uint32_t)(((k >> 1) - 1) & 1));   // S: the sums of step k - 2 have left red[pb]
             red[ul] = (float)o.net;
             red[nt + ul] = (float)o.cost;
             red[2 * nt + ul] = (float)o.emission;
@@ -1307,11 +1346,14 @@ __global__ void __launch_bounds__(MAXT, (DYNAMICS && MAXT == CL_DYN_MAXT) ? CL_D
                 s_wpart[(pb * 3 + 0) * 32 + w] = vn; s_wpart[(pb * 3 + 1) * 32 + w] = vc; s_wpart[(pb * 3 + 2) * 32 + w] = ve;
             }
             if (coupled) cluster_sync_all(); else __syncthreads();             // S1 (for the whole cluster when tiles exchange sums)
+        } else if (dec) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(s_bar + 7 + pb);                        // R: done with red[pb], row t, the inputs of parity pb
         } else {
             __syncthreads();                                                   // S1: red / dynbuf / next-step building inputs complete
         }
         CL_STAMP(5);
-        if (uniform && tid == 0 && k + 3 <= K) {
+        if (!dec && uniform && tid == 0 && k + 3 <= K) {
             // nobody reads row t any more (reward inputs were captured above): its slot takes the row of step t + 3
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_expect_tx(s_bar + slot_t, row_bytes);
@@ -1351,6 +1393,27 @@ __global__ void __launch_bounds__(MAXT, (DYNAMICS && MAXT == CL_DYN_MAXT) ? CL_D
                 float acc = 0.f;
                 for (int w = 0; w < nw; ++w) acc += src[w];
                 district[(((size_t)k * d.E + e0) * NT + rank) * 3 + tid] = acc;
+            }
+        } else if (dec) {
+            // the sums of step k - 1 (and, on the last step of the launch, of step k as well): its arrivals are a whole step old
+            for (int kk = (k > 0 ? k - 1 : k); kk <= k; ++kk) {
+                if (kk == k && k + 1 < K) break;
+                const int pp = kk & 1;
+                mbar_wait(s_bar + 7 + pp, (uint32_t)((kk >> 1) & 1));          // R: every warp's results of step kk are in red[pp]
+                if (district != nullptr) {
+                    const float* redk = smf + lo.red + pp * 3 * nt;
+                    for (int idx = tid; idx < 3 * n_env; idx += np_) {
+                        const int q = idx / n_env, le = idx - q * n_env;
+                        const float* src = redk + q * nt + le * B;
+                        float acc = 0.f;
+                        int j = 0;
+                        for (; j + 4 <= B; j += 4) { acc += src[j]; acc += src[j + 1]; acc += src[j + 2]; acc += src[j + 3]; }   // same left-to-right order
+                        for (; j < B; ++j) acc += src[j];
+                        district[((size_t)kk * d.E + e0 + le) * 3 + q] = acc;
+                    }
+                }
+                __syncwarp();
+                if (lane == 0 && kk + 2 < K) mbar_arrive(s_bar + 9 + pp);      // S: red[pp] may be written again (step kk + 2)
             }
         } else
         for (int idx = tid; idx < 3 * n_env; idx += np_) {
@@ -1664,6 +1727,7 @@ struct cl_env {
     float* obs_tab_dev = nullptr;   // precomputed observation table (build_obs_table)
     double* kpi_unit = nullptr;     // online KPI accumulators (cl_kpi_enable)
     double* kpi_env = nullptr;
+    bool decouple = false;          // CL_B200_DECOUPLE at cl_create: split-phase step barrier (advance_kernel<..., DEC>)
     bool kpi_fused = false;         // accumulated inside advance_kernel (else: cl_kpi_accumulate on the step's trace)
     float* dpart = nullptr;         // wide districts: per-tile partial district sums of one launch chunk
     size_t dpart_floats = 0;
@@ -1742,6 +1806,10 @@ static void ensure_smem_optin(size_t smem) {
     OPTIN((advance_kernel<double, false, false, M, false, false, true>)); OPTIN((advance_kernel<double, true, false, M, false, false, true>))
     OPTINE(512); OPTINE(1024);
 #undef OPTINE
+#define OPTIND(M) OPTIN((advance_kernel<float, false, false, M, false, false, false, true>)); OPTIN((advance_kernel<float, true, false, M, false, false, false, true>)); \
+    OPTIN((advance_kernel<double, false, false, M, false, false, false, true>)); OPTIN((advance_kernel<double, true, false, M, false, false, false, true>))
+    OPTIND(512); OPTIND(1024);
+#undef OPTIND
     OPTINA(512); OPTINA(1024); OPTIN((advance_kernel<float, true, true, kDynMaxT>)); OPTIN((advance_kernel<double, true, true, kDynMaxT>)); OPTIN4(reset_kernel, 512); OPTIN4(reset_kernel, 1024);
     OPTIN((advance_kernel<float, false, false, 512, true>)); OPTIN((advance_kernel<float, true, false, 512, true>));
     OPTIN((advance_kernel<double, false, false, 512, true>)); OPTIN((advance_kernel<double, true, false, 512, true>));
@@ -1766,6 +1834,7 @@ extern "C" int cl_create(const cl_district_desc* desc, cl_env** out) {
         return fail(CL_ERR_INVALID, "cl_create: CL_REWARD_ELECTRIC_VEHICLES needs a district with chargers (cl_district_desc.ev)");
     cl_env* env = new (std::nothrow) cl_env();
     if (!env) return fail(CL_ERR_INVALID, "cl_create: out of host memory");
+    { const char* v = std::getenv("CL_B200_DECOUPLE"); env->decouple = v != nullptr && v[0] != '\0' && v[0] != '0'; }
     Dev& d = env->d;
     std::memset(&d, 0, sizeof(d));
     const int B = desc->n_buildings;
@@ -2318,6 +2387,17 @@ static void launch_advance(cl_env* env, int t0, int K, const float* actions, flo
             else advance_kernel<R, TH, false, 1024, false, false, true><<<env->blocks, nthreads, smem, st>>>(env->d, t0, K, actions, obs, reward, district, trace);
             return;
         }
+        {
+            // nothing in the step reads the district sum and every env is on the same row: no block barrier per step (DEC).  OPT-IN
+            // (CL_B200_DECOUPLE=1 at cl_create): measured on B200 it is 1.5 - 3.5 % SLOWER than the plain block barrier
+            const Dev& q = env->d;
+            const bool dsum_in_step = q.reward_id == CL_REWARD_MARL || q.reward_id == CL_REWARD_ELECTRIC_VEHICLES || q.central;
+            if (env->decouple && !env->kpi_fused && !dsum_in_step && q.stale && q.uniform_start && q.x_n <= 1 && !q.obs_state) {
+                if (nthreads <= 512) advance_kernel<R, TH, false, 512, false, false, false, true><<<env->blocks, nthreads, smem, st>>>(env->d, t0, K, actions, obs, reward, district, trace);
+                else advance_kernel<R, TH, false, 1024, false, false, false, true><<<env->blocks, nthreads, smem, st>>>(env->d, t0, K, actions, obs, reward, district, trace);
+                return;
+            }
+        }
         if (env->kpi_fused) {                         // online KPI accumulators inside the step (cl_kpi_enable)
             if (nthreads <= 512) advance_kernel<R, TH, false, 512, false, true><<<env->blocks, nthreads, smem, st>>>(env->d, t0, K, actions, obs, reward, district, trace);
             else advance_kernel<R, TH, false, 1024, false, true><<<env->blocks, nthreads, smem, st>>>(env->d, t0, K, actions, obs, reward, district, trace);
@@ -2460,8 +2540,17 @@ extern "C" int cl_step(cl_env* env, const float* actions, float* obs, float* rew
 // One step end to end from host buffers in ONE call: H2D of the actions, the step kernel, (optionally) the observation row all envs
 // share, ONE D2H of the caller's result range, stream synchronisation.  Every buffer is the caller's (pinned host memory makes both
 // copies asynchronous DMA transfers).
+// page-locked host memory the device can address in place (cudaHostAlloc / cudaHostRegister under unified addressing)
+static bool device_addressable_host(const void* p, const void** dev_ptr) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    if (a.type != cudaMemoryTypeHost || a.devicePointer == nullptr) return false;
+    *dev_ptr = a.devicePointer;
+    return true;
+}
+
 extern "C" int cl_step_host(cl_env* env, const float* actions_host, float* actions_dev, float* obs_dev, float* reward_dev, float* district_dev,
-                            float* row_dev, const void* d2h_src_dev, void* d2h_dst_host, size_t d2h_bytes, cl_stream stream) {
+                            float* row_dev, const void* d2h_src_dev, void* d2h_dst_host, size_t d2h_bytes, int32_t in_place, cl_stream stream) {
     if (!env || !actions_host || !actions_dev) return fail(CL_ERR_INVALID, "cl_step_host: null argument");
     if (d2h_bytes && (!d2h_src_dev || !d2h_dst_host)) return fail(CL_ERR_INVALID, "cl_step_host: null result range");
     if (env->t < 0) return fail(CL_ERR_STATE, "cl_step_host: call cl_reset first");
@@ -2470,8 +2559,28 @@ extern "C" int cl_step_host(cl_env* env, const float* actions_host, float* actio
     if (env->t >= env->T - 1) return fail(CL_ERR_STATE, "cl_step_host: episode has ended (terminated); call cl_reset");
     if (row_dev && (!env->d.stale || !env->d.uniform_start || env->d.obs_state))
         return fail(CL_ERR_STATE, "cl_step_host: the observation row is only shared by all envs with stale_observations, one episode window and no per-env state columns");
-    CUDA_TRY(cudaMemcpyAsync(actions_dev, actions_host, sizeof(float) * (size_t)env->d.E * (size_t)std::max(env->d.A, 1), cudaMemcpyHostToDevice, st));
-    { const int rc = dispatch_advance(env, 1, actions_dev, obs_dev, reward_dev, district_dev, nullptr, st); if (rc) return rc; }
+    // in place: the kernel reads the actions from, and writes the results that lie inside the result range to, page-locked host memory
+    // directly (loads / posted stores over PCIe inside the step instead of a DMA copy before and after it).  Only when both host
+    // ranges are device-addressable and the [E, L] observation slab is not requested (8 MB of stores belong on the copy engine).
+    const float* act = actions_dev;
+    const void *in_dev = nullptr, *out_dev = nullptr;
+    bool direct = in_place && obs_dev == nullptr && device_addressable_host(actions_host, &in_dev) &&
+                  (d2h_bytes == 0 || device_addressable_host(d2h_dst_host, &out_dev));
+    if (direct) {
+        act = static_cast<const float*>(in_dev);
+        auto translate = [&](float* p) -> float* {
+            const char* lo = static_cast<const char*>(d2h_src_dev);
+            const char* q = reinterpret_cast<const char*>(p);
+            if (p && d2h_bytes && q >= lo && q < lo + d2h_bytes) return reinterpret_cast<float*>(const_cast<char*>(static_cast<const char*>(out_dev)) + (q - lo));
+            return p;
+        };
+        float* r2 = translate(reward_dev); float* w2 = translate(row_dev);
+        // everything inside the range must be produced by this call, or the host range would miss it
+        const size_t produced = (r2 != reward_dev ? sizeof(float) * (size_t)env->d.E * (env->d.central ? 1 : env->d.B) : 0) + (w2 != row_dev ? sizeof(float) * (size_t)env->d.L : 0);
+        if (produced == d2h_bytes) { reward_dev = r2; row_dev = w2; d2h_bytes = 0; } else { direct = false; act = actions_dev; }
+    }
+    if (!direct) CUDA_TRY(cudaMemcpyAsync(actions_dev, actions_host, sizeof(float) * (size_t)env->d.E * (size_t)std::max(env->d.A, 1), cudaMemcpyHostToDevice, st));
+    { const int rc = dispatch_advance(env, 1, act, obs_dev, reward_dev, district_dev, nullptr, st); if (rc) return rc; }
     if (row_dev) {
         const long total = env->d.L;
         obs_rows_kernel<<<(unsigned)std::min<long>((total + 255) / 256, 4096), 256, 0, st>>>(env->d, env->t + 1, 1, row_dev);

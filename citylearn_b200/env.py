@@ -21,6 +21,7 @@ terminated / truncated (all envs advance in lock-step).
 from __future__ import annotations
 
 import importlib
+import os
 from typing import Any, Dict, List, Mapping, Optional, Tuple, Union
 
 import numpy as np
@@ -322,6 +323,9 @@ class CityLearnEnv:
             self._host_ptrs = {'act': self._act.data_ptr(), 'obs': self._obs.data_ptr(), 'reward': self._reward.data_ptr(), 'row': self._row.data_ptr(),
                                'district': self._district.data_ptr(), 'obs_host': self._obs_pinned.data_ptr(), 'reward_host': self._reward_pinned.data_ptr()}
             self._pinned_action_buffers: List[torch.Tensor] = []
+            # in-place host step: actions read from / rewards + row written to page-locked host memory by the kernels themselves
+            self._host_in_place = 0 if os.environ.get('CL_B200_HOST_COPIES') else 1
+            self._reward_current = True
             self._roll = None                   # buffers of rollout_host, keyed by K
 
     def configure_transforms(self, observation_transform: Optional[str] = 'unchanged', normalized_actions: Optional[bool] = None):
@@ -661,9 +665,12 @@ class CityLearnEnv:
                     return self.step_host(actions, full_observations)
             st = torch.cuda.current_stream(self.device).cuda_stream
             if shared:
-                self._h.step_host(src, p['act'], None, p['reward'], p['district'], p['row'], p['reward'], p['reward_host'], 4 * (E * R + L), st)
+                self._h.step_host(src, p['act'], None, p['reward'], p['district'], p['row'], p['reward'], p['reward_host'], 4 * (E * R + L),
+                                  self._host_in_place, st)
+                if self._host_in_place:
+                    self._reward_current = False            # the device reward buffer was bypassed (results went to the host range)
             else:
-                self._h.step_host(src, p['act'], p['obs'], p['reward'], p['district'], None, p['obs'], p['obs_host'], 4 * E * (L + R), st)
+                self._h.step_host(src, p['act'], p['obs'], p['reward'], p['district'], None, p['obs'], p['obs_host'], 4 * E * (L + R), 0, st)
             self._obs_current = not shared
             self._hist_valid = False
             self.time_step += 1

@@ -201,13 +201,17 @@ def test_episode_start_validation():
 
 
 def test_step_host_single_call_path_equals_the_staged_path():
-    """`cl_step_host` (one native call per step) against the torch-staged path (an env that tracks episode rewards keeps it): same
-    observations / rewards from page-locked, pageable, non-contiguous and nested-list actions; both observation modes."""
+    """`cl_step_host` (one native call per step; in place on page-locked memory, or with DMA copies) against the torch-staged path (an
+    env that tracks episode rewards keeps it): same observations / rewards from page-locked, pageable, non-contiguous and wrong-dtype
+    actions; both observation modes."""
     from citylearn_b200 import CityLearnEnv
     E, K = 64, 12
     fast = CityLearnEnv(PALL, num_envs=E)
+    copies = CityLearnEnv(PALL, num_envs=E)
+    copies._host_in_place = 0                        # DMA copies before / after the kernel instead of in-place PCIe access
     slow = CityLearnEnv(PALL, num_envs=E, track_episode_rewards=True)
-    assert fast._host_fast and not slow._host_fast
+    assert fast._host_fast and fast._host_in_place and copies._host_fast and not slow._host_fast
+    cp = copies.pinned_actions(1)[0]
     rng = np.random.RandomState(4)
     pinned = fast.pinned_actions(2)
     n0 = fast.gpu_launches
@@ -224,7 +228,10 @@ def test_step_host_single_call_path_equals_the_staged_path():
         full = k >= K // 2
         o1, r1, t1 = fast.step_host(arg, full_observations=full or None)
         o2, r2, t2 = slow.step_host(a, full_observations=full or None)
+        np.copyto(cp, a)
+        o3, r3, t3 = copies.step_host(cp, full_observations=full or None)
         assert np.array_equal(o1, o2) and np.array_equal(r1, r2) and t1 == t2, k
+        assert np.array_equal(o3, o2) and np.array_equal(r3, r2) and t3 == t2, k
     assert fast.time_step == slow.time_step == K and fast._h.time_step() == K
     assert fast.gpu_launches - n0 >= K
     assert torch.equal(fast.observations, slow.observations)
@@ -240,3 +247,30 @@ def test_step_host_single_call_path_equals_the_staged_path():
     assert term
     with pytest.raises(RuntimeError):
         short.step_host(np.zeros((4, 17), dtype='float32'))
+
+
+def test_split_phase_barrier_instantiation_is_bit_identical(monkeypatch):
+    """`CL_B200_DECOUPLE=1` selects the barrier-free step (arrive at step k, wait one step later, lagged district sums): an opt-in
+    experiment that must still give the same bits - observations, rewards, district sums, state - per step and inside one launch."""
+    from citylearn_b200 import CityLearnEnv
+    E, K = 300, 41                                           # several blocks, the last one partly filled
+    ref = CityLearnEnv(PALL, num_envs=E)
+    monkeypatch.setenv('CL_B200_DECOUPLE', '1')
+    dec = CityLearnEnv(PALL, num_envs=E)
+    dec2 = CityLearnEnv(PALL, num_envs=E)
+    monkeypatch.delenv('CL_B200_DECOUPLE')
+    g = torch.Generator(device='cuda').manual_seed(5)
+    acts = torch.rand((K, E, 17), device='cuda', generator=g) * 2 - 1
+    L = ref._obs_dim
+    bufs = [(torch.zeros((K, E, L), device='cuda'), torch.zeros((K, E, 17), device='cuda'), torch.zeros((K, E, 3), device='cuda')) for _ in range(2)]
+    ref.rollout(acts, *bufs[0])
+    dec.rollout(acts, *bufs[1])
+    for a, b in zip(bufs[0], bufs[1]):
+        assert torch.equal(a, b)
+    assert torch.equal(ref.state_dict()['state'], dec.state_dict()['state'])
+    for k in range(6):                                       # single-step launches (K = 1) and short blocks
+        o, r, _, _, _ = dec2.step(acts[k])
+        assert torch.equal(o, bufs[0][0][k]) and torch.equal(r, bufs[0][1][k]) and torch.equal(dec2.district, bufs[0][2][k])
+    o3 = torch.zeros((3, E, L), device='cuda'); r3 = torch.zeros((3, E, 17), device='cuda'); d3 = torch.zeros((3, E, 3), device='cuda')
+    dec2.rollout(acts[6:9].contiguous(), o3, r3, d3)
+    assert torch.equal(o3, bufs[0][0][6:9]) and torch.equal(r3, bufs[0][1][6:9]) and torch.equal(d3, bufs[0][2][6:9])
