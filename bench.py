@@ -572,9 +572,11 @@ def main():
     value = world * units_per_step * K / (ms_max * 1e-3)
 
     # ---------------- end to end through the public API with host buffers ----------------
+    env_host_mode = env._host_in_place
+
     def e2e_loop(full, in_place=True):
         env.reset()
-        env._host_in_place = 1 if in_place else 0
+        env._host_in_place = env_host_mode if in_place else 0
         # this step's actions wait in page-locked host memory (the contract's "host->device copy ... from pinned host memory"): a host-side
         # policy writes them there; every step copies ITS OWN [E, A] block to the device inside the timed region
         host_pinned = torch.empty((W + K, E, A), dtype=torch.float32).pin_memory()
@@ -601,7 +603,7 @@ def main():
     e2e_ms, e2e_sum = e2e_loop(None)                   # shared observation row (reference-parity rows are env-independent)
     e2e_full_ms, _ = e2e_loop(True)                    # full [E, L] copy, for comparison
     e2e_dma_ms, _ = e2e_loop(None, in_place=False)     # same as e2e, but DMA copies before / after the kernel instead of in-place access
-    env._host_in_place = 1
+    env._host_in_place = env_host_mode
     # K steps as ONE host call: one H2D of [K, E, A], one launch, one D2H of rewards + K rows
     env.reset()
     blk = np.random.RandomState(9 + rank).uniform(-1, 1, size=(K, E, A)).astype('float32')

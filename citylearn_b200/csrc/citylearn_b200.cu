@@ -1727,6 +1727,8 @@ struct cl_env {
     float* obs_tab_dev = nullptr;   // precomputed observation table (build_obs_table)
     double* kpi_unit = nullptr;     // online KPI accumulators (cl_kpi_enable)
     double* kpi_env = nullptr;
+    volatile int32_t* host_flag = nullptr;   // page-locked completion flag of cl_step_host (polled by the host)
+    int32_t host_seq = 0;
     bool decouple = false;          // CL_B200_DECOUPLE at cl_create: split-phase step barrier (advance_kernel<..., DEC>)
     bool kpi_fused = false;         // accumulated inside advance_kernel (else: cl_kpi_accumulate on the step's trace)
     float* dpart = nullptr;         // wide districts: per-tile partial district sums of one launch chunk
@@ -2323,6 +2325,7 @@ extern "C" int cl_destroy(cl_env* env) {
     if (env->x_buf) cudaFree(env->x_buf);
     if (env->x_peers_dev) cudaFree(env->x_peers_dev);
     if (env->x_err_dev) cudaFree(env->x_err_dev);
+    if (env->host_flag) cudaFreeHost(const_cast<int32_t*>(env->host_flag));
     delete env;
     return CL_OK;
 }
@@ -2540,6 +2543,13 @@ extern "C" int cl_step(cl_env* env, const float* actions, float* obs, float* rew
 // One step end to end from host buffers in ONE call: H2D of the actions, the step kernel, (optionally) the observation row all envs
 // share, ONE D2H of the caller's result range, stream synchronisation.  Every buffer is the caller's (pinned host memory makes both
 // copies asynchronous DMA transfers).
+// completion signal of cl_step_host: the last (one-thread) kernel of the call stores the call's sequence number into page-locked host
+// memory; the host polls it instead of paying cudaStreamSynchronize's wake-up latency
+__global__ void signal_kernel(volatile int32_t* flag, int32_t value) {
+    __threadfence_system();
+    *flag = value;
+}
+
 // page-locked host memory the device can address in place (cudaHostAlloc / cudaHostRegister under unified addressing)
 static bool device_addressable_host(const void* p, const void** dev_ptr) {
     cudaPointerAttributes a;
@@ -2564,10 +2574,10 @@ extern "C" int cl_step_host(cl_env* env, const float* actions_host, float* actio
     // ranges are device-addressable and the [E, L] observation slab is not requested (8 MB of stores belong on the copy engine).
     const float* act = actions_dev;
     const void *in_dev = nullptr, *out_dev = nullptr;
-    bool direct = in_place && obs_dev == nullptr && device_addressable_host(actions_host, &in_dev) &&
-                  (d2h_bytes == 0 || device_addressable_host(d2h_dst_host, &out_dev));
+    const bool read_in_place = (in_place & 1) && device_addressable_host(actions_host, &in_dev);
+    bool direct = (in_place & 2) && obs_dev == nullptr && d2h_bytes != 0 && device_addressable_host(d2h_dst_host, &out_dev);
+    if (read_in_place) act = static_cast<const float*>(in_dev);
     if (direct) {
-        act = static_cast<const float*>(in_dev);
         auto translate = [&](float* p) -> float* {
             const char* lo = static_cast<const char*>(d2h_src_dev);
             const char* q = reinterpret_cast<const char*>(p);
@@ -2577,9 +2587,9 @@ extern "C" int cl_step_host(cl_env* env, const float* actions_host, float* actio
         float* r2 = translate(reward_dev); float* w2 = translate(row_dev);
         // everything inside the range must be produced by this call, or the host range would miss it
         const size_t produced = (r2 != reward_dev ? sizeof(float) * (size_t)env->d.E * (env->d.central ? 1 : env->d.B) : 0) + (w2 != row_dev ? sizeof(float) * (size_t)env->d.L : 0);
-        if (produced == d2h_bytes) { reward_dev = r2; row_dev = w2; d2h_bytes = 0; } else { direct = false; act = actions_dev; }
+        if (produced == d2h_bytes) { reward_dev = r2; row_dev = w2; d2h_bytes = 0; } else direct = false;
     }
-    if (!direct) CUDA_TRY(cudaMemcpyAsync(actions_dev, actions_host, sizeof(float) * (size_t)env->d.E * (size_t)std::max(env->d.A, 1), cudaMemcpyHostToDevice, st));
+    if (!read_in_place) CUDA_TRY(cudaMemcpyAsync(actions_dev, actions_host, sizeof(float) * (size_t)env->d.E * (size_t)std::max(env->d.A, 1), cudaMemcpyHostToDevice, st));
     { const int rc = dispatch_advance(env, 1, act, obs_dev, reward_dev, district_dev, nullptr, st); if (rc) return rc; }
     if (row_dev) {
         const long total = env->d.L;
@@ -2590,6 +2600,24 @@ extern "C" int cl_step_host(cl_env* env, const float* actions_host, float* actio
     if (d2h_bytes) CUDA_TRY(cudaMemcpyAsync(d2h_dst_host, d2h_src_dev, d2h_bytes, cudaMemcpyDeviceToHost, st));
     env->t += 1;
     { const int rc = publish_time(env, st); if (rc) return rc; }
+    if ((in_place & 4) && env->host_flag == nullptr) {
+        void* hf = nullptr;
+        if (cudaHostAlloc(&hf, 64, cudaHostAllocMapped) != cudaSuccess) { cudaGetLastError(); hf = nullptr; }
+        env->host_flag = static_cast<volatile int32_t*>(hf);
+        if (env->host_flag) *env->host_flag = 0;
+    }
+    if ((in_place & 4) && env->host_flag != nullptr) {
+        const int32_t seq = ++env->host_seq;
+        signal_kernel<<<1, 1, 0, st>>>(env->host_flag, seq);
+        env->launches++;
+        CUDA_TRY(cudaGetLastError());
+        volatile int32_t* f = env->host_flag;
+        for (long spins = 0; *f != seq; ++spins) {
+            if ((spins & 0xFFFFF) == 0xFFFFF && cudaStreamQuery(st) != cudaErrorNotReady) break;     // finished, or failed: let the sync below report it
+        }
+        if (*f != seq) CUDA_TRY(cudaStreamSynchronize(st));
+        return CL_OK;
+    }
     CUDA_TRY(cudaStreamSynchronize(st));
     return CL_OK;
 }

@@ -324,7 +324,8 @@ class CityLearnEnv:
                                'district': self._district.data_ptr(), 'obs_host': self._obs_pinned.data_ptr(), 'reward_host': self._reward_pinned.data_ptr()}
             self._pinned_action_buffers: List[torch.Tensor] = []
             # in-place host step: actions read from / rewards + row written to page-locked host memory by the kernels themselves
-            self._host_in_place = 0 if os.environ.get('CL_B200_HOST_COPIES') else 1
+            # cl_step_host flags (include/citylearn_b200.h): 1 read actions in place, 2 write results in place, 4 polled completion flag
+            self._host_in_place = int(os.environ.get('CL_B200_HOST_MODE', '3'))
             self._reward_current = True
             self._roll = None                   # buffers of rollout_host, keyed by K
 
@@ -667,7 +668,7 @@ class CityLearnEnv:
             if shared:
                 self._h.step_host(src, p['act'], None, p['reward'], p['district'], p['row'], p['reward'], p['reward_host'], 4 * (E * R + L),
                                   self._host_in_place, st)
-                if self._host_in_place:
+                if self._host_in_place & 2:
                     self._reward_current = False            # the device reward buffer was bypassed (results went to the host range)
             else:
                 self._h.step_host(src, p['act'], p['obs'], p['reward'], p['district'], None, p['obs'], p['obs_host'], 4 * E * (L + R), 0, st)

@@ -302,10 +302,12 @@ int cl_set_state(cl_env* env, const void* src_dev, int32_t time_step, cl_stream 
  * observations and one episode window), copies d2h_bytes from d2h_src_dev to d2h_dst_host (the caller lays its result buffers out so
  * that ONE range covers what it wants back, e.g. [reward | row]) and synchronises the stream.  With pinned host memory both copies are
  * asynchronous DMA transfers; pageable memory works but is staged by the driver.
- * in_place != 0: when actions_host and d2h_dst_host are page-locked memory the device can address (cudaHostAlloc / cudaHostRegister),
- * obs_dev is NULL and the result range holds exactly reward_dev (+ row_dev), the kernels read the actions from and write those results
- * to the host memory directly - PCIe loads / posted stores inside the step instead of one DMA copy before and one after it (the
- * device buffers inside the range are then NOT written).  Falls back to the copies whenever a condition does not hold.
+ * in_place: bit flags, each honoured only when possible (else the copy / synchronisation is used):
+ *   1  the kernel reads the actions from actions_host directly (page-locked, device-addressable memory: cudaHostAlloc / cudaHostRegister)
+ *   2  the kernels write the results to d2h_dst_host directly (page-locked; obs_dev NULL; the result range holds exactly reward_dev
+ *      (+ row_dev)) - posted PCIe stores inside the step instead of a DMA copy after it; the device buffers of the range are NOT written
+ *   4  completion is a sequence number a final one-thread kernel stores into page-locked memory, polled by the host, instead of
+ *      cudaStreamSynchronize's wake-up
  */
 int cl_step_host(cl_env* env, const float* actions_host, float* actions_dev, float* obs_dev, float* reward_dev, float* district_dev,
                  float* row_dev, const void* d2h_src_dev, void* d2h_dst_host, size_t d2h_bytes, int32_t in_place, cl_stream stream);

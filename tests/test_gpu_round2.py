@@ -210,7 +210,10 @@ def test_step_host_single_call_path_equals_the_staged_path():
     copies = CityLearnEnv(PALL, num_envs=E)
     copies._host_in_place = 0                        # DMA copies before / after the kernel instead of in-place PCIe access
     slow = CityLearnEnv(PALL, num_envs=E, track_episode_rewards=True)
-    assert fast._host_fast and fast._host_in_place and copies._host_fast and not slow._host_fast
+    assert fast._host_fast and fast._host_in_place == 3 and copies._host_fast and not slow._host_fast
+    mixed = CityLearnEnv(PALL, num_envs=E)
+    mixed._host_in_place = 6                         # DMA in, in-place out, polled completion
+    mp = mixed.pinned_actions(1)[0]
     cp = copies.pinned_actions(1)[0]
     rng = np.random.RandomState(4)
     pinned = fast.pinned_actions(2)
@@ -232,6 +235,9 @@ def test_step_host_single_call_path_equals_the_staged_path():
         o3, r3, t3 = copies.step_host(cp, full_observations=full or None)
         assert np.array_equal(o1, o2) and np.array_equal(r1, r2) and t1 == t2, k
         assert np.array_equal(o3, o2) and np.array_equal(r3, r2) and t3 == t2, k
+        np.copyto(mp, a)
+        o4, r4, t4 = mixed.step_host(mp, full_observations=full or None)
+        assert np.array_equal(o4, o2) and np.array_equal(r4, r2) and t4 == t2, k
     assert fast.time_step == slow.time_step == K and fast._h.time_step() == K
     assert fast.gpu_launches - n0 >= K
     assert torch.equal(fast.observations, slow.observations)

@@ -54,10 +54,12 @@ env.reset()
 print('step_host, pinned in    %7.1f us' % wall(lambda: (fresh(), env.step_host(pin))))
 env.reset()
 print('step_host, pageable in  %7.1f us' % wall(lambda: (fresh(), env.step_host(page))))
-env.reset()
-env._host_in_place = 0
-print('step_host, pinned, DMA  %7.1f us' % wall(lambda: (fresh(), env.step_host(pin))))
-env._host_in_place = 1
+for mode, label in ((0, 'DMA both ways, sync'), (4, 'DMA both ways, flag'), (1, 'read in place'), (2, 'write in place'), (3, 'both in place'),
+                    (6, 'write in place, flag'), (7, 'both in place, flag'), (5, 'read in place, flag')):
+    env.reset()
+    env._host_in_place = mode
+    print('step_host mode %d %-22s %7.1f us' % (mode, label, wall(lambda: (fresh(), env.step_host(pin)))))
+env._host_in_place = 3
 env.reset()
 print('step_host, full obs     %7.1f us' % wall(lambda: (fresh(), env.step_host(pin, full_observations=True))))
 env.reset()
