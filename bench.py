@@ -624,6 +624,13 @@ def main():
     extra = {}
     want = args.extras
     fma_peak = None
+    def hard_exit():
+        # (multi-rank runs) leave without tearing the process group down: ranks finish at different times (rank 0 still times the CPU
+        # baseline), and a communicator teardown that waits for a peer which is already gone has hung a 2-GPU run for minutes AFTER
+        # the result line was out.  Everything is flushed; exit code 0.
+        sys.stdout.flush(); sys.stderr.flush()
+        os._exit(0)
+
     def guarded(name, fn):          # an extra must never take the headline (or another extra) down
         try:
             extra[name] = fn()
@@ -642,9 +649,7 @@ def main():
             guarded('building_sharded_district', lambda: extra_building_sharded(torch, dev, args.precision, world, dist, rank))
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        hard_exit()
 
     bpu = bytes_per_unit(args.precision, L / B, A / B, B, rollout=True)
     bpu_step = bytes_per_unit(args.precision, L / B, A / B, B, rollout=False)
@@ -707,7 +712,7 @@ def main():
     }
     print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        hard_exit()
 
 
 if __name__ == '__main__':

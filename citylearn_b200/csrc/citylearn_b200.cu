@@ -572,7 +572,7 @@ __device__ __forceinline__ void write_obs_general(const Dev& d, float* obs, int 
 // offsets in floats from the start of the dynamic shared memory (kept as plain ints so that every access is derived
 // directly from the `extern __shared__` array and compiles to LDS/STS with 32-bit addressing, not generic loads)
 struct SmemLayout {
-    int curves, clut, bsolar, rows, tcol, tmpl, red, rsum, dsum, wpart, rpart, lstm, lstm_pre, dynbuf, kpi_acc, kpi_nws, kpi_env, end, Lp;
+    int curves, clut, bsolar, rows, tcol, tmpl, red, rsum, dsum, wpart, rpart, lstm, lstm_pre, lstm_frag, dynbuf, kpi_acc, kpi_nws, kpi_env, end, Lp;
 };
 __host__ __device__ __forceinline__ SmemLayout smem_layout(int B, int Wp, int L, int epb, int nt, int rsize, int lstm_smem = 0, int tab_layout = 0, int fresh_slots = 0, int n_curves = 0, int kpi = 0) {
     SmemLayout o;
@@ -592,6 +592,7 @@ __host__ __device__ __forceinline__ SmemLayout smem_layout(int B, int Wp, int L,
     o.rpart = f; f += 2 * 32 * 2;                // wide districts, central agent: per-warp partial reward sums [2][32] doubles (8-byte aligned: f is even)
     o.lstm = f; f += lstm_smem ? B * kLstmStride : 0;      // kLstmStride is a multiple of 4 floats: 16-byte aligned rows
     o.lstm_pre = f; f += lstm_smem ? B * kLstmPreRing * 64 : 0;   // per-building ring of shared layer-0 input projections
+    o.lstm_frag = f; f += lstm_smem == 2 ? B * kLstmFragFloats : 0;   // tensor-core operand fragments of the recurrent / layer-1 matrices (lstm_update_mma)
     // with per-env row images the general writer's dynbuf is never live at the same time: it aliases them (cl_create checks the size)
     o.dynbuf = fresh_slots ? o.tmpl : f;
     // fused KPI accumulators (doubles; f is kept even): [CL_NKPI_UNIT][nt] running sums, [2][nt] baseline net of the step (by step
@@ -719,6 +720,163 @@ __device__ __forceinline__ float lstm_update(const Dev& d, const UnitCtx<R>& c, 
     }
     win_t[(size_t)(t % ring) * U] = y;                                       // the prediction replaces the slot (building.py:3027-3028)
     return y * c.tin_range + c.tin_min;                                      // de-normalised (building.py:3031-3037)
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// LSTM dynamics on the tensor cores (legacy warp-level path: mma.sync m16n8k8, TF32 operands, FP32 accumulate).
+// The scalar cell above is bound by shared-memory operand delivery (one 16-byte weight broadcast per 4 FMAs per lane).  Here a WARP
+// whose 32 lanes sit on ONE building treats 16 of its units as the M dimension of D[16 x 8] += A[16 x 8] B[8 x 8]: A = the units'
+// hidden vectors, B = an 8 x 8 block of the recurrent (or layer-1 input) matrix.  B fragments come from shared memory in fragment
+// order (conflict-free 8-byte loads, 12x fewer shared-memory wavefronts than the scalar cell); each product is done as 3 MMAs on
+// hi / lo TF32 splits of both operands (a_lo b_hi + a_hi b_lo + a_hi b_hi: float32-level accuracy, ~2^-21 relative).
+// Fragment layout (PTX ISA, m16n8k8 .tf32; g = lane / 4, t = lane % 4):
+//   A: a0 (row g, k t)  a1 (row g + 8, k t)  a2 (row g, k t + 4)  a3 (row g + 8, k t + 4)
+//   B: b0 (k t, col g)  b1 (k t + 4, col g)            C / D: c0 (g, 2t) c1 (g, 2t + 1) c2 (g + 8, 2t) c3 (g + 8, 2t + 1)
+// The K slots are permuted so that slot t of k-tile kt is hidden unit kt * 8 + 2t and slot t + 4 is kt * 8 + 2t + 1: lane (g, t)
+// then OWNS hidden units {2t, 2t + 1, 8 + 2t, 9 + 2t} of unit rows g and g + 8 both as producer (the C columns of the i / f / g / o
+// tiles of those hidden units) and as consumer (its A registers) - no shuffles between cell steps, h and c stay in registers.
+// Fed-back inputs, biases and the shared layer-0 projection `pre` are added in the epilogue in plain float32.
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t tf32_rna(float x) { uint32_t r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x)); return r; }
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// hi / lo TF32 split of the A registers {ra[j0], rb[j0], ra[j1], rb[j1]}
+__device__ __forceinline__ void lstm_a_frag(const float* ra, const float* rb, int j0, int j1, uint32_t (&hi)[4], uint32_t (&lo)[4]) {
+    const float v[4] = {ra[j0], rb[j0], ra[j1], rb[j1]};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { hi[i] = tf32_rna(v[i]); lo[i] = tf32_rna(v[i] - __uint_as_float(hi[i])); }
+}
+// acc[q] (gate type q = i, f, g, o; n-tile q * 2 + half) += A (one k-tile, hi / lo) x the fragments of block `blk` (matrix, k-tile)
+__device__ __forceinline__ void lstm_mma_ktile(float (&acc)[4][4], const uint32_t (&ahi)[4], const uint32_t (&alo)[4], uint32_t frag /* shared address of the block */,
+                                               int half, int lane) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int ntile = q * 2 + half;
+        uint32_t bh0, bh1, bl0, bl1;
+        asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(bh0), "=r"(bh1) : "r"(frag + 4u * (uint32_t)(((ntile * 2 + 0) * 32 + lane) * 2)));
+        asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(bl0), "=r"(bl1) : "r"(frag + 4u * (uint32_t)(((ntile * 2 + 1) * 32 + lane) * 2)));
+        mma_tf32(acc[q], alo, bh0, bh1);
+        mma_tf32(acc[q], ahi, bl0, bl1);
+        mma_tf32(acc[q], ahi, bh0, bh1);
+    }
+}
+// cell update of the hidden units (half * 8 + 2t, + 1) of rows a, b from the four gate accumulators (+ the epilogue terms already added)
+__device__ __forceinline__ void lstm_gate_update(const float (&acc)[4][4], int half, float* ha, float* hb, float* ca, float* cb) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {                       // e: 0 (row a, j0) 1 (row a, j1) 2 (row b, j0) 3 (row b, j1)
+        float* hh = (e < 2) ? ha : hb; float* cc = (e < 2) ? ca : cb;
+        const int j = half * 2 + (e & 1);               // slot in the lane's 4 owned hidden units: {2t, 2t + 1, 8 + 2t, 9 + 2t}
+        const float cn = fmaf(sigmoid_dev(acc[1][e]), cc[j], sigmoid_dev(acc[0][e]) * tanh_dev(acc[2][e]));
+        cc[j] = cn;
+        hh[j] = sigmoid_dev(acc[3][e]) * tanh_dev(cn);
+    }
+}
+
+// warp-collective: every lane of the warp sits on building b (units u0 + lane * B), all of them active.  Returns the lane's own
+// de-normalised prediction like lstm_update.
+template <typename R>
+__device__ __forceinline__ float lstm_update_mma(const Dev& d, const UnitCtx<R>& c, const float* Wb /* packed weights, shared */, uint32_t frag /* shared address */,
+                                                 const float* pre /* this building's projection ring, shared */, int u, int t, float obs_cool_dem,
+                                                 float t_in_dataset, int lane) {
+    const int U = d.U, B = d.B;
+    const int L = c.dyn_lookback, ring = L + 1;
+    float* lst = d.lst;
+    float* win_c = lst + (size_t)(4 * kLstmH) * U;                          // [ring][U]
+    float* win_t = lst + (size_t)(4 * kLstmH + kLstmMaxLookback + 1) * U;
+    // _update_dynamics_input: append the normalised observation of step t (float32 arithmetic), every lane for its own unit
+    if (c.dyn_slot_cdem >= 0) win_c[(size_t)(t % ring) * U + u] = (obs_cool_dem - c.cdem_min) / c.cdem_range;
+    win_t[(size_t)(t % ring) * U + u] = (t_in_dataset - c.tin_min) / c.tin_range;
+    if (t < L) return t_in_dataset;                                         // window not full yet (building.py:2996-2998)
+    __syncwarp();                                                           // the lanes read each other's window entries below
+    const int g = lane >> 2, tq = lane & 3;
+    const int u0 = __shfl_sync(0xffffffffu, u, 0);
+    const int jown[4] = {2 * tq, 2 * tq + 1, 8 + 2 * tq, 9 + 2 * tq};
+    const int sc = c.dyn_slot_cdem, stn = c.dyn_slot_tin;
+    const float* wl = Wb + 2 * kLstmLayerStride;
+    float y_mine = 0.f;
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+        const int ua = u0 + (pass * 16 + g) * B, ub = ua + 8 * B;           // the units of rows g and g + 8
+        float h0a[4], h0b[4], h1a[4], h1b[4], c0a[4], c0b[4], c1a[4], c1b[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const size_t j = (size_t)jown[i];
+            h0a[i] = lst[j * U + ua]; h0b[i] = lst[j * U + ub];
+            h1a[i] = lst[(kLstmH + j) * U + ua]; h1b[i] = lst[(kLstmH + j) * U + ub];
+            c0a[i] = lst[(2 * kLstmH + j) * U + ua]; c0b[i] = lst[(2 * kLstmH + j) * U + ub];
+            c1a[i] = lst[(3 * kLstmH + j) * U + ua]; c1b[i] = lst[(3 * kLstmH + j) * U + ub];
+        }
+#pragma unroll 1
+        for (int sidx = 0; sidx < L; ++sidx) {
+            const int tau = t - (L - 1) + sidx;
+            const float xca = sc >= 0 ? win_c[(size_t)(tau % ring) * U + ua] : 0.f, xcb = sc >= 0 ? win_c[(size_t)(tau % ring) * U + ub] : 0.f;
+            const float xta = win_t[(size_t)((tau - 1) % ring) * U + ua], xtb = win_t[(size_t)((tau - 1) % ring) * U + ub];   // lagged by one step (building.py:3044-3049)
+            const float* pr = pre + 64 * (tau % kLstmPreRing);
+            uint32_t ahi[4][4], alo[4][4];
+            // ---- layer 0: W_hh0 h0 + pre + the two fed-back input columns ----
+            lstm_a_frag(h0a, h0b, 0, 1, ahi[0], alo[0]);
+            lstm_a_frag(h0a, h0b, 2, 3, ahi[1], alo[1]);
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                float acc[4][4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int n0 = q * 16 + half * 8 + 2 * tq;
+                    const float p0 = pr[n0], p1 = pr[n0 + 1];
+                    const float wc0 = sc >= 0 ? Wb[n0 * 16 + sc] : 0.f, wc1 = sc >= 0 ? Wb[(n0 + 1) * 16 + sc] : 0.f;
+                    const float wt0 = Wb[n0 * 16 + stn], wt1 = Wb[(n0 + 1) * 16 + stn];
+                    acc[q][0] = fmaf(wt0, xta, fmaf(wc0, xca, p0)); acc[q][1] = fmaf(wt1, xta, fmaf(wc1, xca, p1));
+                    acc[q][2] = fmaf(wt0, xtb, fmaf(wc0, xcb, p0)); acc[q][3] = fmaf(wt1, xtb, fmaf(wc1, xcb, p1));
+                }
+                lstm_mma_ktile(acc, ahi[0], alo[0], frag + 4u * (uint32_t)(0 * kLstmFragBlock), half, lane);
+                lstm_mma_ktile(acc, ahi[1], alo[1], frag + 4u * (uint32_t)(1 * kLstmFragBlock), half, lane);
+                lstm_gate_update(acc, half, h0a, h0b, c0a, c0b);
+            }
+            // ---- layer 1: W_ih1 h0(new) + W_hh1 h1 + b1 ----
+            lstm_a_frag(h0a, h0b, 0, 1, ahi[0], alo[0]);
+            lstm_a_frag(h0a, h0b, 2, 3, ahi[1], alo[1]);
+            lstm_a_frag(h1a, h1b, 0, 1, ahi[2], alo[2]);
+            lstm_a_frag(h1a, h1b, 2, 3, ahi[3], alo[3]);
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                float acc[4][4];
+                const float* b1 = Wb + kLstmLayerStride + 64 * 32;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int n0 = q * 16 + half * 8 + 2 * tq;
+                    acc[q][0] = acc[q][2] = b1[n0]; acc[q][1] = acc[q][3] = b1[n0 + 1];
+                }
+#pragma unroll
+                for (int kt = 0; kt < 4; ++kt) lstm_mma_ktile(acc, ahi[kt], alo[kt], frag + 4u * (uint32_t)((2 + kt) * kLstmFragBlock), half, lane);
+                lstm_gate_update(acc, half, h1a, h1b, c1a, c1b);
+            }
+        }
+        // linear head: partial sums over the lane's hidden units, completed over the quad
+        float ya = 0.f, yb = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { ya = fmaf(wl[jown[i]], h1a[i], ya); yb = fmaf(wl[jown[i]], h1b[i], yb); }
+        ya += __shfl_xor_sync(0xffffffffu, ya, 1); yb += __shfl_xor_sync(0xffffffffu, yb, 1);
+        ya += __shfl_xor_sync(0xffffffffu, ya, 2); yb += __shfl_xor_sync(0xffffffffu, yb, 2);
+        ya += wl[16]; yb += wl[16];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const size_t j = (size_t)jown[i];
+            lst[j * U + ua] = h0a[i]; lst[j * U + ub] = h0b[i];
+            lst[(kLstmH + j) * U + ua] = h1a[i]; lst[(kLstmH + j) * U + ub] = h1b[i];
+            lst[(2 * kLstmH + j) * U + ua] = c0a[i]; lst[(2 * kLstmH + j) * U + ub] = c0b[i];
+            lst[(3 * kLstmH + j) * U + ua] = c1a[i]; lst[(3 * kLstmH + j) * U + ub] = c1b[i];
+        }
+        // the owner lane of unit row r (lane = pass * 16 + r) takes its prediction from lane 4 * (r % 8) of this pass
+        const int r = lane & 15;
+        const float va = __shfl_sync(0xffffffffu, ya, 4 * (r & 7)), vb = __shfl_sync(0xffffffffu, yb, 4 * (r & 7));
+        if ((lane >> 4) == pass) y_mine = (r < 8) ? va : vb;
+    }
+    __syncwarp();
+    win_t[(size_t)(t % ring) * U + u] = y_mine;                              // the prediction replaces the slot (building.py:3027-3028)
+    return y_mine * c.tin_range + c.tin_min;                                 // de-normalised (building.py:3031-3037)
 }
 
 __device__ __forceinline__ void kpi_push(double* a, double x);
@@ -919,10 +1077,30 @@ __global__ void __launch_bounds__(MAXT, (DYNAMICS && MAXT == CL_DYN_MAXT) ? CL_D
         for (int i = tid; i < n_env * 2 * CL_NKPI_ENV; i += nt) s_kenv[i] = d.kpi_env[(size_t)e0 * 2 * CL_NKPI_ENV + i];
     }
     __syncthreads();   // mbarriers initialised (visible to every waiter), curves / tcol / LSTM weights staged
+    if (DYNAMICS && d.lstm_smem == 2) {
+        // tensor-core operand fragments of W_hh0, W_ih1, W_hh1 (lstm_update_mma), from the packed weights staged above:
+        // block (matrix m, k-tile kt), n-tile, {hi, lo}, lane (g, t): {W[n-tile * 8 + g][kt * 8 + 2t], W[..][kt * 8 + 2t + 1]}
+        float* fr = smf + lo.lstm_frag;
+        for (int i = tid; i < B * 6 * 8 * 32; i += nt) {
+            const int ln = i & 31, ntile = (i >> 5) & 7, blk = (i >> 8) % 6, bb = i / (6 * 8 * 32);
+            const int m = blk >> 1, kt = blk & 1, gg = ln >> 2, tt = ln & 3;
+            const float* Wm = smf + lo.lstm + (size_t)bb * kLstmStride + (m == 0 ? 64 * 16 : kLstmLayerStride + (m == 2 ? 64 * 16 : 0));
+            const float w0 = Wm[(ntile * 8 + gg) * 16 + kt * 8 + 2 * tt], w1 = Wm[(ntile * 8 + gg) * 16 + kt * 8 + 2 * tt + 1];
+            const uint32_t h0 = tf32_rna(w0), h1 = tf32_rna(w1);
+            float* dst = fr + (size_t)bb * kLstmFragFloats + (size_t)blk * kLstmFragBlock;
+            dst[((ntile * 2 + 0) * 32 + ln) * 2] = __uint_as_float(h0); dst[((ntile * 2 + 0) * 32 + ln) * 2 + 1] = __uint_as_float(h1);
+            dst[((ntile * 2 + 1) * 32 + ln) * 2] = __uint_as_float(tf32_rna(w0 - __uint_as_float(h0)));
+            dst[((ntile * 2 + 1) * 32 + ln) * 2 + 1] = __uint_as_float(tf32_rna(w1 - __uint_as_float(h1)));
+        }
+        __syncthreads();
+    }
 
     // LSTM layer-0 input projections shared by all envs of the block (uniform episode windows, weights in shared memory):
     // pre[bb][tau % ring][r] = bias0[r] + W_ih0[r][:] . x(row of time step tau); fed-back slots hold 0 in the table
     const bool use_pre = DYNAMICS && uniform && d.lstm_smem;
+    // tensor-core cell: needs the fragments, the shared projections, and whole warps on one building (building-major mapping with a
+    // multiple of 32 envs in this block)
+    const bool lstm_mma = use_pre && d.lstm_smem == 2 && (n_env & 31) == 0;
     float* s_pre = smf + lo.lstm_pre;
     auto project_row = [&](int bb, int tau, const float* rowp, int r) {
         const float* Wb = smf + lo.lstm + (size_t)bb * kLstmStride;
@@ -1277,6 +1455,11 @@ __global__ void __launch_bounds__(MAXT, (DYNAMICS && MAXT == CL_DYN_MAXT) ? CL_D
 #else
                 constexpr bool kConstW = false;
 #endif
+                if (lstm_mma) {
+                    // (whole warps on one building, all lanes active: see lstm_mma above)
+                    t_in = lstm_update_mma<R>(d, c, lstm_w, smem_u32(smf + lo.lstm_frag + (size_t)b * kLstmFragFloats), s_pre + (size_t)b * kLstmPreRing * 64,
+                                              u, t, cd, t_in, lane);
+                } else
                 t_in = lstm_update<R, kConstW>(d, c, lstm_w, u, t, start_e, cd, t_in, use_pre ? s_pre + (size_t)b * kLstmPreRing * 64 : nullptr, b);
             }
             if (dec && k >= 2) mbar_wait(s_bar + 9 + pb, (uint32_t)(((k >> 1) - 1) & 1));   // S: the sums of step k - 2 have left red[pb]
@@ -1959,6 +2142,9 @@ extern "C" int cl_create(const cl_district_desc* desc, cl_env** out) {
         if (B <= kLstmConstBuildings && std::getenv("CL_B200_NO_LSTM_CONST") == nullptr) env->lstm_packed = packed;
 #endif
         d.lstm_smem = ((size_t)B * kLstmStride * sizeof(float) <= 120 * 1024) ? 1 : 0;
+        // + the tensor-core operand fragments when they fit next to everything else (3 LSTM buildings: 134 KB in all)
+        if (d.lstm_smem && (size_t)B * (kLstmStride + kLstmFragFloats + kLstmPreRing * 64) * sizeof(float) <= 150 * 1024 &&
+            std::getenv("CL_B200_NO_LSTM_MMA") == nullptr) d.lstm_smem = 2;
     }
     // padded table
     {

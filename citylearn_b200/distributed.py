@@ -104,8 +104,23 @@ class BuildingShardedEnv:
         if self.count == 0:
             raise ValueError(f'rank {rank} of {world} would own no building out of {len(names)}')
         self.n_buildings_total = len(names)
-        self.env = CityLearnEnv(schema, num_envs=num_envs, device=device, central_agent=False,
+        def make():
+            return CityLearnEnv(schema, num_envs=num_envs, device=device, central_agent=False,
                                 buildings=names[self.first:self.first + self.count], debug_trace=(exchange == 'nccl'), **kwargs)
+        self.env = make()
+        if world > 1 and exchange == 'p2p':
+            # ranks wait for each other INSIDE the step: every block of the launch must be resident (cl_exchange_create refuses more than
+            # one block per SM).  The default geometry minimises resident threads and may pick small blocks; take the largest ones instead
+            import os
+            g = self.env._h.geometry()
+            sms = torch.cuda.get_device_properties(self.env.device).multi_processor_count
+            if g['blocks'] > sms and 'CL_B200_BLOCK_THREADS' not in os.environ:
+                self.env.close()
+                os.environ['CL_B200_BLOCK_THREADS'] = '480'
+                try:
+                    self.env = make()
+                finally:
+                    del os.environ['CL_B200_BLOCK_THREADS']
         self.env.building_offset, self.env.total_buildings = self.first, len(names)
         self._handle_bytes, self._buffer = (None, None)
         if world > 1 and exchange == 'p2p':
