@@ -335,8 +335,14 @@ def extra_c3(torch, dev, precision, fma_peak):
     m = median(ms)
     flop_unit = 93696.0 + 150.0                                            # 46 848 LSTM MACs + device arithmetic
     tf = flop_unit * B * E * K / (m * 1e-3) / 1e12
+    geo = env._h.geometry()
+    tensor = os.environ.get('CL_B200_NO_LSTM_MMA') is None
     out = {'workload': f'citylearn_challenge_2023_phase_2_local_evaluation: {B} LSTM buildings x {E} envs, MARL, decentralised', 'ms_per_step': m / K,
-           'value': B * E * K / (m * 1e-3), 'unit': UNIT, 'timing': timing_summary(ms, K),
+           'value': B * E * K / (m * 1e-3), 'unit': UNIT, 'timing': timing_summary(ms, K), 'geometry': geo,
+           'lstm_cell': ('tensor cores: mma.sync m16n8k8 TF32 operands, FP32 accumulate, 3 MMAs per product on hi / lo splits (float32-level accuracy)'
+                         if tensor else 'scalar float32 FMAs, weights broadcast from shared memory'),
+           # algorithmic FLOPs of the float32 cell against the measured FP32-FMA throughput: what a scalar cell could reach at best;
+           # the tensor-core cell executes 3x the multiply-adds of the recurrent products on the (legacy) tensor path instead
            'roofline': {'bound': 'fp32_fma', 'achieved': tf, 'peak': fma_peak, 'unit': 'TFLOP/s', 'frac': tf / fma_peak if fma_peak else None,
                         'flop_per_unit': flop_unit, 'peak_source': 'cl_measure_fma_peak (independent FFMA chains, this device)'}}
     env.close()
