@@ -2362,6 +2362,7 @@ extern "C" int cl_create(const cl_district_desc* desc, cl_env** out) {
         for (int ci = 0; ci < 5; ++ci) {
             int epb_c = cand[ci] / BT;
             if (epb_c < 1) epb_c = 1;
+            if (d.lstm_smem == 2 && epb_c >= 32) epb_c &= ~31;       // tensor-core LSTM cell: whole warps on one building
             if (epb_c > d.E) epb_c = d.E;
             const int thr = ((epb_c * BT + 31) / 32) * 32 + 32;
             if (thr > (any_dyn ? kDynMaxT : 512) && ci > 0) continue;
@@ -2391,6 +2392,7 @@ extern "C" int cl_create(const cl_district_desc* desc, cl_env** out) {
     }
     int epb = target / BT;
     if (epb < 1) epb = 1;
+    if (d.lstm_smem == 2 && epb >= 32) epb &= ~31;
     if (epb > d.E) epb = d.E;
     d.envs_per_block = epb;
     d.tiles = 1; d.tile_b = B; d.Lt = d.L; d.tile_k = nullptr;

@@ -306,3 +306,31 @@ def test_lstm_tensor_core_cell_matches_the_scalar_cell(monkeypatch):
             assert torch.equal(t1[..., DYN[n]], t2[..., DYN[n]]), (n, k)
         assert torch.equal(o1, o2) and torch.equal(r1, r2), k
     assert 0.0 < worst < 4e-5, worst                     # two float32 evaluation orders, each within 3e-5 of the reference (0.0: the tensor-core path did not run)
+
+
+def test_multi_building_reward_function_matches_the_fused_rewards():
+    """Per-building reward functions from the schema (`MultiBuildingRewardFunction`, citylearn/reward_function.py:90-117; Python path
+    over the per-unit trace): every building's column equals the column of an env whose fused reward is that building's function."""
+    from citylearn_b200 import CityLearnEnv
+    from citylearn_b200 import reward_function as rf
+    from citylearn_b200.data import DataSet
+    src = DataSet.get_source('citylearn_challenge_2022_phase_1')
+    sch = src.schema()
+    names = list(sch['buildings'])
+    sch['reward_function'] = {'type': {'default': 'citylearn.reward_function.RewardFunction', names[1]: 'citylearn.reward_function.SolarPenaltyReward',
+                                       names[3]: 'citylearn.reward_function.IndependentSACReward'},
+                              'attributes': {}}
+    E = 24
+    multi = CityLearnEnv(sch, data_source=src, num_envs=E)
+    assert isinstance(multi.reward_function, rf.MultiBuildingRewardFunction) and multi._reward_id == -1
+    plain = {k: CityLearnEnv('citylearn_challenge_2022_phase_1', num_envs=E, reward_function=getattr(rf, k))
+             for k in ('RewardFunction', 'SolarPenaltyReward', 'IndependentSACReward')}
+    which = ['RewardFunction'] * len(names)
+    which[1], which[3] = 'SolarPenaltyReward', 'IndependentSACReward'
+    g = torch.Generator(device='cuda').manual_seed(12)
+    for k in range(15):
+        a = torch.rand((E, multi.spec.action_dim), device='cuda', generator=g) * 2 - 1
+        _, r, _, _, _ = multi.step(a)
+        cols = {n: e.step(a)[1] for n, e in plain.items()}
+        for b, n in enumerate(which):
+            assert max_abs_diff(r[:, b].cpu().numpy(), cols[n][:, b].cpu().numpy()) <= 2e-6 * max(1.0, float(cols[n][:, b].abs().max())), (k, b, n)
