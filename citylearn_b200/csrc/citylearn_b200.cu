@@ -2370,10 +2370,17 @@ extern "C" int cl_create(const cl_district_desc* desc, cl_env** out) {
             int bps = 65536 / (regs_alloc * thr);
             if (bps > 2048 / thr) bps = 2048 / thr;
             if (bps < 1) bps = 1;
+            if (d.lstm_smem == 2) {
+                // the operand fragments + packed weights + projections of the tensor-core LSTM cell are per block: shared memory, not
+                // registers, bounds the resident blocks (measured: 2 waves of 224-thread blocks at 3 x 16 384 took 0.31 ms/step)
+                const size_t fixed = (size_t)B * (kLstmStride + kLstmFragFloats + kLstmPreRing * 64) * sizeof(float) + 16 * 1024;
+                bps = std::max(1, std::min(bps, (int)((227 * 1024) / fixed)));
+            }
             const long blocks = (d.E + epb_c - 1) / epb_c;
             const long waves = (blocks + (long)n_sm * bps - 1) / ((long)n_sm * bps);
             const long resident = blocks < (long)n_sm * bps ? (blocks + n_sm - 1) / n_sm : bps;   // blocks per SM actually resident
-            const double cost = (double)waves * (double)resident * thr;
+            // (LSTM blocks are latency bound: a wave costs about the same whatever its width - fewest waves first, then the widest block)
+            const double cost = d.lstm_smem == 2 ? (double)waves * 1e6 - (double)cand[ci] : (double)waves * (double)resident * thr;
             // (ties go to the larger block: per-block staging - curves, LSTM weights - is amortised over more units; measured on the
             // LSTM district: 1.18 ms/step with 512-thread blocks against 1.35 with two 256-thread blocks per SM)
             if (cost < best - 1e-9 || (cost < best + 1e-9 && cand[ci] > target)) { best = cost; target = cand[ci]; }
