@@ -10,6 +10,8 @@
 //   start    int32  [E]               table row of time step 0 of every env
 //   state    float  [6][E*B]  (+ double [2][E*B] in CL_PRECISION_FP64)   unit index u = e * B + b (building fastest)
 //   lstm     float  [90][E*B]         h, c of both layers and the two fed-back input windows (LSTM dynamics districts)
+//   ev_*     float / double / u8      vehicles' soc[t-1] / soc[t], degraded capacity, efficiency, flags; washing-machine flags;
+//                                     charging-constraint headroom / violation [E][n_constrained * 6] (cl_ev_desc districts)
 //   obs_tab  float  [n_rows][L]       complete (wrapper-transformed) reference-parity observation row of every time step, built
 //                                     once; the step kernel only moves it (TMA load -> TMA stores)
 //   kpi_*    double [E][B][8], [E][2][15]   optional online KPI accumulators (cl_kpi_*)
@@ -22,6 +24,9 @@
 // Districts wider than one block (WIDE instantiation) split the buildings of an env into tiles, one CTA each: independent CTAs
 // with deferred district sums, or a thread-block cluster exchanging partial sums through distributed shared memory when a
 // reward reads the district sum inside the step.
+// LSTM dynamics: `lstm_update_mma` (warp-level tensor-core cell: mma.sync m16n8k8, 3xTF32, operand fragments in shared memory) where a
+// block's warps each sit on one building, else the scalar `lstm_update`.  Host steps: `cl_step_host` (one call per step; page-locked host
+// memory accessed in place by the kernels).  Building-sharded districts: `exchange_sum` (district sums completed over NVLink peer memory).
 #include <cuda_runtime.h>
 
 #include <cstdio>
