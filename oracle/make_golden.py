@@ -345,6 +345,67 @@ WRAPPER_CASES = {
 }
 
 
+CC_CONFIGS = {
+    'shipped': None,                                  # the dataset's own Building_15 block
+    'no_building_cap': {'Building_15': {'observations': {'headroom': True, 'violation': True, 'phase_encoding': True},
+                                        'phases': [{'name': 'phase_a', 'limit_kw': 6.0, 'chargers': ['charger_15_1']},
+                                                   {'name': 'phase_b', 'chargers': ['charger_15_2']}]}},
+    'nothing_exposed': {'Building_15': {'building_limit_kw': 9.0, 'observations': {'headroom': False, 'violation': False, 'phase_encoding': False},
+                                        'phases': [{'name': 'p1', 'limit_kw': 5.0, 'chargers': ['charger_15_1', 'charger_15_2']}]}},
+    'expose_flag': {'Building_15': {'building_limit_kw': 10.0, 'expose_observations': False,
+                                    'phases': [{'limit_kw': 4.0, 'chargers': ['charger_15_2']}]}},
+    'unassigned': {'Building_15': {'building_limit_kw': 11.0, 'observations': {'phase_encoding': True},
+                                   'phases': [{'name': 'only', 'limit_kw': 3.0, 'chargers': ['charger_15_1']}]}},
+    'two_buildings': {'Building_1': {'building_limit_kw': 5.0},
+                      'Building_15': {'building_limit_kw': 0.0, 'phases': [{'name': 'z', 'limit_kw': 0.0, 'chargers': ['charger_15_1']}]}},
+}
+
+
+def run_cc_meta(CityLearnEnv, steps=40, seed=5, np_seed=9):
+    """Charging-constraint configurations (building.py:764-833) on the demo dataset: the reference's names (both orders), spaces, and a
+    short trace of observations / rewards under random actions - loader and oracle fixture `tests/golden/ev/cc_meta.json.gz`."""
+    import gzip
+    sys.path.insert(0, str(HERE.parent))
+    from citylearn_b200.ev import _stable_unit
+    cases = []
+    for tag, cfg in CC_CONFIGS.items():
+        def hook(schema, cfg=cfg):
+            for n, e in (schema.get('electric_vehicles_def') or {}).items():
+                a = e['battery']['attributes']
+                if a.get('initial_soc') is None:
+                    a['initial_soc'] = _stable_unit(n)
+            if cfg is not None:
+                for b in schema['buildings'].values():
+                    b.pop('charging_constraints', None)
+                for bn, c in cfg.items():
+                    schema['buildings'][bn]['charging_constraints'] = c
+        np.random.seed(np_seed)
+        env = make_env(CityLearnEnv, 'citylearn_charging_constraints_demo', None, None, schema_hook=hook)
+        lo = np.concatenate([np.asarray(b.action_space.low, dtype='float64') for b in env.buildings])
+        hi = np.concatenate([np.asarray(b.action_space.high, dtype='float64') for b in env.buildings])
+        sizes = [b.action_space.shape[0] for b in env.buildings]
+        rng = np.random.RandomState(seed)
+        obs, _ = env.reset()
+        rec = {'tag': tag, 'constraints': cfg, 'np_seed': np_seed, 'observation_names': env.observation_names,
+               'active_observations': [b.active_observations for b in env.buildings],
+               'observation_low': [s.low.tolist() for s in env.observation_space], 'observation_high': [s.high.tolist() for s in env.observation_space],
+               'reset_obs': flat(obs).astype('float32').tolist(), 'actions': [], 'obs': [], 'reward': []}
+        for k in range(steps):
+            a = (lo + rng.uniform(0.0, 1.0, size=len(lo)) * (hi - lo)).astype('float32')
+            act, o = [], 0
+            for n in sizes:
+                act.append([float(x) for x in a[o:o + n]])
+                o += n
+            obs, rew, _, _, _ = env.step(act)
+            rec['actions'].append(a.tolist()); rec['obs'].append(flat(obs).astype('float32').tolist()); rec['reward'].append(flat(rew).astype('float32').tolist())
+        cases.append(rec)
+        print('cc_meta', tag, len(rec['observation_names'][14]))
+    (OUT / 'ev').mkdir(parents=True, exist_ok=True)
+    with gzip.open(OUT / 'ev' / 'cc_meta.json.gz', 'wt') as f:
+        json.dump(cases, f)
+    print('cc_meta', len(cases), (OUT / 'ev' / 'cc_meta.json.gz').stat().st_size)
+
+
 def run_meta_fuzz(CityLearnEnv, n=28, seed=123):
     """Loader fuzz: random combinations of the constructor overrides -> the reference's names, spaces and episode windows."""
     rng = np.random.RandomState(seed)
@@ -515,7 +576,7 @@ CASES = {
 
 if __name__ == '__main__':
     CityLearnEnv = import_reference()
-    todo = sys.argv[1:] or (list(CASES) + list(EV_CASES) + list(WRAPPER_CASES) + ['meta_fuzz', 'trace_fuzz', 'trace_datasets'])
+    todo = sys.argv[1:] or (list(CASES) + list(EV_CASES) + list(WRAPPER_CASES) + ['meta_fuzz', 'trace_fuzz', 'trace_datasets', 'cc_meta'])
     for n in todo:
         if n == 'trace_fuzz':
             run_trace_fuzz(CityLearnEnv)
@@ -526,6 +587,9 @@ if __name__ == '__main__':
                 ('citylearn_challenge_2022_phase_2', 60), ('citylearn_challenge_2023_phase_2_online_evaluation_1', 60),
                 ('citylearn_challenge_2023_phase_2_online_evaluation_2', 60), ('citylearn_challenge_2023_phase_2_online_evaluation_3', 60),
                 ('citylearn_challenge_2023_phase_3_2', 60), ('citylearn_challenge_2023_phase_3_3', 60)])
+            continue
+        if n == 'cc_meta':
+            run_cc_meta(CityLearnEnv)
             continue
         if n == 'meta_fuzz':
             run_meta_fuzz(CityLearnEnv)

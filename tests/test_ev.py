@@ -214,3 +214,60 @@ def test_gpu_unsupported_combinations_fail_loudly():
     from citylearn_b200.reward_function import Electric_Vehicles_Reward_Function
     with pytest.raises(ValueError, match='chargers'):
         CityLearnEnv('citylearn_challenge_2022_phase_all', num_envs=2, reward_function=Electric_Vehicles_Reward_Function)
+
+
+# ------------------------------------------------------------------------------------------ charging-constraint configurations
+def _cc_cases():
+    import gzip
+    p = GOLDEN / 'ev' / 'cc_meta.json.gz'
+    return json.load(gzip.open(p, 'rt')) if p.exists() else []
+
+
+CC_CASES = _cc_cases()
+
+
+def _cc_spec(rec):
+    src = DataSet.get_source('citylearn_charging_constraints_demo')
+    sch = src.schema()
+    if rec['constraints'] is not None:
+        for b in sch['buildings'].values():
+            b.pop('charging_constraints', None)
+        for bn, c in rec['constraints'].items():
+            sch['buildings'][bn]['charging_constraints'] = c
+    return S.load(sch, data_source=src, ev_random_seed=rec['np_seed'])
+
+
+@pytest.mark.parametrize('rec', CC_CASES, ids=[r['tag'] for r in CC_CASES])
+def test_charging_constraint_configurations_match_the_reference(rec):
+    """Six `charging_constraints` blocks run through the unmodified reference (oracle/make_golden.py cc_meta): caps with and without a
+    building limit, a phase without a cap, nothing exposed, `expose_observations`, an unassigned charger in the phase encoding, zero
+    caps on two buildings.  The loader reproduces both name orders and the spaces; the oracle the observations and rewards of 40 steps."""
+    spec = _cc_spec(rec)
+    assert [list(b.observation_value_order or b.active_observations) for b in spec.buildings] == rec['observation_names']
+    assert [list(b.active_observations) for b in spec.buildings] == rec['active_observations']
+    for b, lo, hi in zip(spec.buildings, rec['observation_low'], rec['observation_high']):
+        assert np.array_equal(b.observation_low, np.float32(lo)) and np.array_equal(b.observation_high, np.float32(hi)), b.name
+    env = OracleEnv(spec, 1, libm_pow=True)
+    assert np.array_equal(oracle_reset(env, spec)[0].astype('float32'), np.float32(rec['reset_obs']))
+    for k, a in enumerate(rec['actions']):
+        obs, rew, _, _ = env.step(np.float32(a)[None])
+        assert np.array_equal(obs[0], np.float32(rec['obs'][k])), k
+        assert np.array_equal(rew[0], np.float32(rec['reward'][k])), k
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('rec', CC_CASES, ids=[r['tag'] for r in CC_CASES])
+def test_gpu_charging_constraint_configurations_match_the_reference(rec):
+    from citylearn_b200 import CityLearnEnv
+    env = CityLearnEnv(_cc_spec(rec), num_envs=1)
+    obs, _ = env.reset()
+    assert np.array_equal(np.array([v for row in obs for v in row], dtype='float32'), np.float32(rec['reset_obs']))
+    sizes = [len(b.active_actions) for b in env.spec.buildings]
+    for k, a in enumerate(rec['actions']):
+        nested, o = [], 0
+        for s in sizes:
+            nested.append([float(x) for x in a[o:o + s]])
+            o += s
+        obs, rew, _, _, _ = env.step(nested)
+        assert np.array_equal(np.array([v for row in obs for v in row], dtype='float32'), np.float32(rec['obs'][k])), k
+        assert np.array_equal(np.array(rew, dtype='float32'), np.float32(rec['reward'][k])), k
