@@ -131,3 +131,32 @@ static int curve_check_impl(const double* xs, const double* ys, int n, const dou
 extern "C" int host_curve_check(int precision, const double* xs, const double* ys, int n, const double* x, int nx, int* first_bad) {
     return precision == CL_PRECISION_FP64 ? curve_check_impl<double>(xs, ys, n, x, nx, first_bad) : curve_check_impl<float>(xs, ys, n, x, nx, first_bad);
 }
+
+// One charger update with the device's `charger_step` (+ the vehicle battery's `battery_charge`): ev = the vehicle's parameter row
+// [CL_NPARAM], chp = the charger's [CL_NCHP]; state = {soc (soc[t-1] entry), degraded capacity, sqrt(efficiency of the last charge)}
+// in / out; out = {electricity consumption, commanded kWh}.  Returns 1 when the battery was charged / discharged.
+template <typename R>
+static int charger_impl(const double* chp, double action, int connected, const double* ev, int pe_n, int cp_n, int first_charge, double* state, double* out) {
+    ChargerParams<R> q;
+    q.max_c = (R)chp[CL_CH_MAX_C]; q.min_c = (R)chp[CL_CH_MIN_C]; q.max_d = (R)chp[CL_CH_MAX_D]; q.min_d = (R)chp[CL_CH_MIN_D]; q.eff = (R)chp[CL_CH_EFF];
+    q.c_n = (int)chp[CL_CH_C_N]; q.d_n = (int)chp[CL_CH_D_N]; q.curves = chp + CL_CH_C_X0;
+    BuildingParams<R> p;
+    p.bat_capacity = (R)ev[CL_P_BAT_CAPACITY]; p.bat_pnom = (R)ev[CL_P_BAT_NOMINAL_POWER]; p.bat_loss = (R)ev[CL_P_BAT_LOSS];
+    p.bat_clc = (R)ev[CL_P_BAT_CLC]; p.bat_dod = (R)ev[CL_P_BAT_DOD]; p.ratio = (R)ev[CL_P_TIME_STEP_RATIO]; p.hours = (R)ev[CL_P_HOURS_PER_STEP];
+    p.flags = 0; p.pe_n = pe_n; p.cp_n = cp_n;
+    derive_params(p);
+    R curves[4 * CL_MAX_CURVE];
+    for (int k = 0; k < 4 * CL_MAX_CURVE; ++k) curves[k] = (R)ev[CL_P_PE_X0 + k];
+    UnitState<R> s;
+    s.soc_b = (R)state[0]; s.cap_deg = (R)state[1]; s.rte_b = (R)state[2]; s.soc_cs = s.soc_hs = s.soc_ds = (R)0;
+    float kwh = 0.f; bool charged = false;
+    const float ec = charger_step<R>(q, action, connected != 0, p, StridedCurves<R, R>{curves, 1}, first_charge != 0, s, (double)p.hours, kwh, charged);
+    state[0] = (double)s.soc_b; state[1] = (double)s.cap_deg; state[2] = (double)s.rte_b;
+    out[0] = (double)ec; out[1] = (double)kwh;
+    return charged ? 1 : 0;
+}
+extern "C" int host_charger_step(int precision, const double* chp, double action, int connected, const double* ev, int pe_n, int cp_n, int first_charge,
+                                 double* state, double* out) {
+    return precision == CL_PRECISION_FP64 ? charger_impl<double>(chp, action, connected, ev, pe_n, cp_n, first_charge, state, out)
+                                          : charger_impl<float>(chp, action, connected, ev, pe_n, cp_n, first_charge, state, out);
+}

@@ -165,3 +165,52 @@ def test_curve_grid_search_matches_reference_scan(hostlib, precision):
         n_indexed += 1
         assert bad == 0, f'curve {xs}: {bad} mismatches, first at x = {x[first.value]!r}'
     assert n_indexed >= 20
+
+
+def test_charger_step_device_code_matches_the_oracle(hostlib):
+    """`charger_step` + the vehicle battery's `battery_charge` (the code the EV instantiation of the step kernel runs), compiled for the
+    host, against the oracle's charger update on the 300 reference actions of `c10_evs`: SOC entry, degraded capacity, the charger's
+    electricity consumption and the commanded energy bit for bit (fp64 flow), every charger update of the run."""
+    import json
+    from citylearn_b200.data import DataSet
+    from citylearn_b200.ev import CHARGER_PARAMS as CP
+    from helpers import GOLDEN
+    z = np.load(GOLDEN / 'ev' / 'c10_evs.npz')
+    cfg = json.loads(bytes(z['config']).decode())
+    src = DataSet.get_source(cfg['dataset'])
+    sch = src.schema()
+    sch['reward_function'] = {'type': cfg['reward']['type'], 'attributes': {}}
+    spec = S.load(sch, data_source=src, ev_random_seed=cfg['np_seed'])
+    ev = spec.ev
+    env = OracleEnv(spec, 1)                       # sqrt (not libm pow), like the device code
+    env.reset()
+    hostlib.host_charger_step.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_double, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
+                                          ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+    updates = 0
+    for k in range(len(z['actions'])):
+        t = env.t
+        row = int(env.start[0]) + t
+        pre = []
+        for c_i in range(len(ev['chargers'])):
+            conn = spec.table[row, ev['ch_cols'][c_i, 0]] > 0
+            v = max(int(spec.table[row, ev['ch_cols'][c_i, 1]]), 0)
+            soc = env.ev_soc_prev[0, v] if t > 0 else env.ev_soc[0, v]
+            pre.append((conn, v, float(np.float32(soc)), float(env.ev_cap_deg[0, v]), float(np.sqrt(env.ev_eff[0, v])), bool(env.ev_charged[0, v])))
+        env.step(z['actions'][k][None])
+        info = env.last_ev
+        for c_i, (conn, v, soc, cap, rte, was_charged) in enumerate(pre):
+            slot = int(ev['ch_action'][c_i])
+            act = float(z['actions'][k][slot]) if slot >= 0 else 0.0
+            state = np.array([soc, cap, rte], dtype='float64')
+            out = np.zeros(2, dtype='float64')
+            chp = np.ascontiguousarray(ev['ch_params'][c_i], dtype='float64')
+            evp = np.ascontiguousarray(ev['ev_params'][v], dtype='float64')
+            charged = hostlib.host_charger_step(1, ptr(chp), act, int(conn), ptr(evp), int(ev['ev_ip'][v, 0]), int(ev['ev_ip'][v, 1]), int(not was_charged),
+                                                ptr(state), ptr(out))
+            assert np.float32(out[0]) == info['ch_ec'][0, c_i], (k, c_i)
+            assert np.float32(out[1]) == info['past'][0, c_i], (k, c_i)
+            if charged:
+                updates += 1
+                assert np.float32(state[0]) == np.float32(env.ev_soc_prev[0, v]), (k, c_i)       # soc[t], one next_time_step later
+                assert state[1] == env.ev_cap_deg[0, v] and state[2] == np.sqrt(env.ev_eff[0, v]), (k, c_i)
+    assert updates > 300
