@@ -361,14 +361,53 @@ CC_CONFIGS = {
 }
 
 
-def run_cc_meta(CityLearnEnv, steps=40, seed=5, np_seed=9):
+def random_cc_configs(n, seed=77):
+    """Random `charging_constraints` blocks for the buildings of the demo dataset that have chargers."""
+    rng = np.random.RandomState(seed)
+    chargers = {'Building_1': ['charger_1_1'], 'Building_4': ['charger_4_1'], 'Building_5': ['charger_5_1'], 'Building_7': ['charger_7_1'],
+                'Building_10': ['charger_10_1'], 'Building_12': ['charger_12_1'], 'Building_15': ['charger_15_1', 'charger_15_2']}
+    out = {}
+    for i in range(n):
+        cfg = {}
+        names = ['Building_15'] + [b for b in chargers if b != 'Building_15' and rng.rand() < 0.35]
+        for bn in names:
+            ids = chargers[bn]
+            c = {}
+            if rng.rand() < 0.75:
+                c['building_limit_kw'] = float(np.round(rng.uniform(0.0, 14.0), 2)) if rng.rand() < 0.9 else 0.0
+            phases = []
+            for j in range(rng.randint(0, 4)):
+                ph = {'chargers': [cid for cid in ids if rng.rand() < 0.7]}
+                if rng.rand() < 0.8:
+                    ph['name'] = f'ph{j}' if rng.rand() < 0.8 else ''
+                if rng.rand() < 0.8:
+                    ph['limit_kw'] = float(np.round(rng.uniform(0.0, 9.0), 2))
+                phases.append(ph)
+            if phases:
+                c['phases'] = phases
+            obs = {}
+            for key in ('headroom', 'violation', 'phase_encoding'):
+                if rng.rand() < 0.6:
+                    obs[key] = bool(rng.rand() < 0.6)
+            if obs:
+                c['observations'] = obs
+            if rng.rand() < 0.2:
+                c['expose_observations'] = bool(rng.rand() < 0.5)
+            if not c:
+                c['building_limit_kw'] = 6.0
+            cfg[bn] = c
+        out[f'fuzz{i}'] = cfg
+    return out
+
+
+def run_cc_meta(CityLearnEnv, steps=40, seed=5, np_seed=9, configs=None, out_name='cc_meta.json.gz'):
     """Charging-constraint configurations (building.py:764-833) on the demo dataset: the reference's names (both orders), spaces, and a
     short trace of observations / rewards under random actions - loader and oracle fixture `tests/golden/ev/cc_meta.json.gz`."""
     import gzip
     sys.path.insert(0, str(HERE.parent))
     from citylearn_b200.ev import _stable_unit
     cases = []
-    for tag, cfg in CC_CONFIGS.items():
+    for tag, cfg in (configs or CC_CONFIGS).items():
         def hook(schema, cfg=cfg):
             for n, e in (schema.get('electric_vehicles_def') or {}).items():
                 a = e['battery']['attributes']
@@ -401,9 +440,9 @@ def run_cc_meta(CityLearnEnv, steps=40, seed=5, np_seed=9):
         cases.append(rec)
         print('cc_meta', tag, len(rec['observation_names'][14]))
     (OUT / 'ev').mkdir(parents=True, exist_ok=True)
-    with gzip.open(OUT / 'ev' / 'cc_meta.json.gz', 'wt') as f:
+    with gzip.open(OUT / 'ev' / out_name, 'wt') as f:
         json.dump(cases, f)
-    print('cc_meta', len(cases), (OUT / 'ev' / 'cc_meta.json.gz').stat().st_size)
+    print(out_name, len(cases), (OUT / 'ev' / out_name).stat().st_size)
 
 
 def run_meta_fuzz(CityLearnEnv, n=28, seed=123):
@@ -576,7 +615,7 @@ CASES = {
 
 if __name__ == '__main__':
     CityLearnEnv = import_reference()
-    todo = sys.argv[1:] or (list(CASES) + list(EV_CASES) + list(WRAPPER_CASES) + ['meta_fuzz', 'trace_fuzz', 'trace_datasets', 'cc_meta'])
+    todo = sys.argv[1:] or (list(CASES) + list(EV_CASES) + list(WRAPPER_CASES) + ['meta_fuzz', 'trace_fuzz', 'trace_datasets', 'cc_meta', 'cc_fuzz'])
     for n in todo:
         if n == 'trace_fuzz':
             run_trace_fuzz(CityLearnEnv)
@@ -590,6 +629,9 @@ if __name__ == '__main__':
             continue
         if n == 'cc_meta':
             run_cc_meta(CityLearnEnv)
+            continue
+        if n == 'cc_fuzz':
+            run_cc_meta(CityLearnEnv, steps=30, seed=6, np_seed=10, configs=random_cc_configs(12), out_name='cc_fuzz.json.gz')
             continue
         if n == 'meta_fuzz':
             run_meta_fuzz(CityLearnEnv)

@@ -271,3 +271,33 @@ def test_gpu_charging_constraint_configurations_match_the_reference(rec):
         obs, rew, _, _, _ = env.step(nested)
         assert np.array_equal(np.array([v for row in obs for v in row], dtype='float32'), np.float32(rec['obs'][k])), k
         assert np.array_equal(np.array(rew, dtype='float32'), np.float32(rec['reward'][k])), k
+
+
+def _cc_fuzz_cases():
+    import gzip
+    p = GOLDEN / 'ev' / 'cc_fuzz.json.gz'
+    return json.load(gzip.open(p, 'rt')) if p.exists() else []
+
+
+CC_FUZZ = _cc_fuzz_cases()
+
+
+@pytest.mark.parametrize('rec', CC_FUZZ, ids=[r['tag'] for r in CC_FUZZ])
+def test_random_charging_constraint_blocks_match_the_reference(rec):
+    """Twelve random `charging_constraints` blocks (1 - 4 constrained buildings, 0 - 3 phases with and without names / caps / members,
+    random observation flags) through the unmodified reference, 30 steps each: loader names (both orders), spaces, and the oracle's
+    observations and rewards."""
+    try:
+        spec = _cc_spec(rec)
+    except S.UnsupportedSchemaError:
+        pytest.skip('more phases / phase members than the device supports')
+    assert [list(b.observation_value_order or b.active_observations) for b in spec.buildings] == rec['observation_names']
+    assert [list(b.active_observations) for b in spec.buildings] == rec['active_observations']
+    for b, lo, hi in zip(spec.buildings, rec['observation_low'], rec['observation_high']):
+        assert np.array_equal(b.observation_low, np.float32(lo)) and np.array_equal(b.observation_high, np.float32(hi)), b.name
+    env = OracleEnv(spec, 1, libm_pow=True)
+    assert np.array_equal(oracle_reset(env, spec)[0].astype('float32'), np.float32(rec['reset_obs']))
+    for k, a in enumerate(rec['actions']):
+        obs, rew, _, _ = env.step(np.float32(a)[None])
+        assert np.array_equal(obs[0], np.float32(rec['obs'][k])), k
+        assert np.array_equal(rew[0], np.float32(rec['reward'][k])), k
