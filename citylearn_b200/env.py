@@ -233,6 +233,10 @@ class CityLearnEnv:
                 raise NotImplementedError('districts with electric vehicles / washing machines need stale_observations=True')
             if record_history or track_kpis or debug_trace:
                 raise NotImplementedError('record_history / track_kpis / debug_trace are not available for districts with electric vehicles / washing machines')
+            if self.central_agent:
+                # (loader and oracle are pinned against the reference for a central agent - tests/golden/ev_cpu - but the kernel's summed
+                #  reward of this instantiation has not run on hardware yet: refuse rather than return unverified numbers)
+                raise NotImplementedError('central_agent=True is not available for districts with electric vehicles / washing machines yet')
             record_history = False
         self._record = (self.num_envs == 1) if record_history is None else bool(record_history)
         self._history_env = int(history_env)

@@ -217,7 +217,7 @@ def run_case(CityLearnEnv, name, dataset, overrides=None, reward=None, steps=Non
     print(name, {k: v.shape for k, v in arrays.items() if k not in ('config', 'meta')}, (OUT / f'{name}.npz').stat().st_size)
 
 
-def run_ev_case(CityLearnEnv, name, dataset, overrides=None, reward=None, steps=200, seed=0, np_seed=5, hold=None):
+def run_ev_case(CityLearnEnv, name, dataset, overrides=None, reward=None, steps=200, seed=0, np_seed=5, hold=None, subdir='ev', episodes=1):
     """Electric vehicles / chargers / washing machines.  The reference draws the SOC drift of away vehicles from NumPy's
     GLOBAL generator (citylearn/citylearn.py:1473) and a missing vehicle `initial_soc` from Python's global `random`
     (citylearn.py:2564): the fixture seeds the former (`np_seed`, = `ev_random_seed` of the replacement) and writes the latter into the
@@ -238,6 +238,10 @@ def run_ev_case(CityLearnEnv, name, dataset, overrides=None, reward=None, steps=
     sizes = [b.action_space.shape[0] for b in env.buildings]
     rng = np.random.RandomState(seed)
     obs, _ = env.reset()
+    for _ in range(episodes - 1):          # later episode of a rolling split: finish the earlier ones with idle actions
+        while not env.terminated:
+            env.step([[0.0] * n for n in sizes] if not env.central_agent else [[0.0] * sum(sizes)])
+        obs, _ = env.reset()
     reset_obs = flat(obs)
     K = min(steps, env.time_steps - 1)
     actions = (lo + rng.uniform(0.0, 1.0, size=(K, len(lo))) * (hi - lo)).astype('float32')
@@ -272,13 +276,14 @@ def run_ev_case(CityLearnEnv, name, dataset, overrides=None, reward=None, steps=
               'trace': np.array(out['trace'], dtype='float32'), 'ev_soc': np.array(out['ev_soc'], dtype='float32'),
               'charger_ec': np.array(out['charger_ec'], dtype='float32'), 'charger_kwh': np.array(out['charger_kwh'], dtype='float32'),
               'wm_ec': np.array(out['wm_ec'], dtype='float32')}
-    config = {'dataset': dataset, 'overrides': overrides or {}, 'reward': reward, 'seed': seed, 'np_seed': np_seed, 'trace_names': TRACE_NAMES,
+    config = {'dataset': dataset, 'overrides': overrides or {}, 'reward': reward, 'seed': seed, 'np_seed': np_seed, 'trace_names': TRACE_NAMES, 'episodes': episodes,
+              'episode_window': [int(env.episode_tracker.episode_start_time_step), int(env.episode_tracker.episode_end_time_step)],
               'numpy': np.__version__, 'chargers': [c.charger_id for _, c in chargers], 'vehicles': [e.name for e in env.electric_vehicles]}
     arrays['config'] = np.frombuffer(json.dumps(config).encode(), dtype='uint8')
     arrays['meta'] = np.frombuffer(json.dumps(meta).encode(), dtype='uint8')
-    (OUT / 'ev').mkdir(parents=True, exist_ok=True)
-    np.savez_compressed(OUT / 'ev' / f'{name}.npz', **arrays)
-    print(name, {k: v.shape for k, v in arrays.items() if k not in ('config', 'meta')}, (OUT / 'ev' / f'{name}.npz').stat().st_size)
+    (OUT / subdir).mkdir(parents=True, exist_ok=True)
+    np.savez_compressed(OUT / subdir / f'{name}.npz', **arrays)
+    print(name, {k: v.shape for k, v in arrays.items() if k not in ('config', 'meta')}, (OUT / subdir / f'{name}.npz').stat().st_size)
 
 
 EV_CASES = {
@@ -292,6 +297,12 @@ EV_CASES = {
     # the constrained chargers are biased towards charging so that the caps bind (scaled actions, headroom / violation observations, reward
     # penalty)
     'c11_constraints': dict(dataset='citylearn_charging_constraints_demo', steps=240, seed=31, np_seed=8),
+    # CPU-side fixtures (tests/golden/ev_cpu: loader + oracle; recorded after the round's GPU budget was spent, so the GPU tests do not pick
+    # them up): an episode window in the middle of the year (vehicles already plugged in / away at the first step), a central agent
+    'c10_evs_window': dict(dataset='citylearn_challenge_2022_phase_all_plus_evs', steps=120, seed=24, np_seed=11, subdir='ev_cpu',
+                           overrides={'simulation_start_time_step': 1200, 'simulation_end_time_step': 1500, 'episode_time_steps': 121}),
+    'c10_evs_central': dict(dataset='citylearn_challenge_2022_phase_all_plus_evs', steps=100, seed=25, np_seed=12, subdir='ev_cpu',
+                            overrides={'central_agent': True}),
     'c10_evs_reward': dict(dataset='citylearn_challenge_2022_phase_all_plus_evs', steps=120, seed=22, np_seed=6),
 }
 

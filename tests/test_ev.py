@@ -205,6 +205,8 @@ def test_gpu_unsupported_combinations_fail_loudly():
         make_gpu_env(cfg, num_envs=4, stale_observations=False)
     with pytest.raises(NotImplementedError):
         make_gpu_env(cfg, num_envs=4, track_kpis=True)
+    with pytest.raises(NotImplementedError):
+        make_gpu_env(cfg, num_envs=4, central_agent=True)
     env = make_gpu_env(cfg, num_envs=4, episode_time_steps=48)
     with pytest.raises(NotImplementedError):
         env.reset(options={'episode_start': torch.tensor([0, 24, 48, 72])})
@@ -301,3 +303,34 @@ def test_random_charging_constraint_blocks_match_the_reference(rec):
         obs, rew, _, _ = env.step(np.float32(a)[None])
         assert np.array_equal(obs[0], np.float32(rec['obs'][k])), k
         assert np.array_equal(rew[0], np.float32(rec['reward'][k])), k
+
+
+CPU_CASES = sorted(p.stem for p in (GOLDEN / 'ev_cpu').glob('*.npz'))
+
+
+@pytest.mark.parametrize('case', CPU_CASES)
+def test_oracle_matches_reference_on_windows_and_central_agent(case):
+    """An episode window in the middle of the year (vehicles plugged in / away at its first step: the episode-start SOC columns) and a
+    central agent (shared observations dropped, one summed reward) - loader and oracle against the unmodified reference."""
+    z = np.load(GOLDEN / 'ev_cpu' / f'{case}.npz')
+    cfg = json.loads(bytes(z['config']).decode())
+    meta = json.loads(bytes(z['meta']).decode())
+    src = DataSet.get_source(cfg['dataset'])
+    sch = src.schema()
+    if cfg.get('reward') is not None:
+        sch['reward_function'] = {'type': cfg['reward']['type'], 'attributes': cfg['reward'].get('attributes', {})}
+    spec = S.load(sch, data_source=src, ev_random_seed=cfg['np_seed'], **(cfg.get('overrides') or {}))
+    env = OracleEnv(spec, 1, libm_pow=True)
+    assert env.entries is not None
+    names = [[n for bi2, n in env.entries if bi2 == bi] for bi in range(len(spec.buildings))] if not spec.central_agent else [[n for _, n in env.entries]]
+    assert names == meta['observation_names']
+    assert np.array_equal(oracle_reset(env, spec)[0].astype('float32'), z['reset_obs'])
+    assert [int(env.start[0]), int(env.start[0]) + env.T - 1] == cfg['episode_window']
+    for k in range(len(z['actions'])):
+        obs, rew, dist, dyn = env.step(z['actions'][k][None])
+        assert np.array_equal(obs[0], z['obs'][k]), k
+        assert np.array_equal(dist[0], z['district'][k]), k
+        assert np.array_equal(env.ev_soc_prev[0].astype('float32'), z['ev_soc'][k]), k
+        r = np.asarray(rew[0], dtype='float32').reshape(-1)
+        ok = np.array_equal(r, z['reward'][k]) if not spec.central_agent else bool(np.abs(r - z['reward'][k]).max() <= 2e-6 * max(1.0, float(np.abs(z['reward'][k]).max())))
+        assert ok, (k, r, z['reward'][k])
