@@ -217,7 +217,7 @@ def run_case(CityLearnEnv, name, dataset, overrides=None, reward=None, steps=Non
     print(name, {k: v.shape for k, v in arrays.items() if k not in ('config', 'meta')}, (OUT / f'{name}.npz').stat().st_size)
 
 
-def run_ev_case(CityLearnEnv, name, dataset, overrides=None, reward=None, steps=200, seed=0, np_seed=5, hold=None, subdir='ev', episodes=1):
+def run_ev_case(CityLearnEnv, name, dataset, overrides=None, reward=None, steps=200, seed=0, np_seed=5, hold=None, subdir='ev', episodes=1, obs_every=1):
     """Electric vehicles / chargers / washing machines.  The reference draws the SOC drift of away vehicles from NumPy's
     GLOBAL generator (citylearn/citylearn.py:1473) and a missing vehicle `initial_soc` from Python's global `random`
     (citylearn.py:2564): the fixture seeds the former (`np_seed`, = `ev_random_seed` of the replacement) and writes the latter into the
@@ -263,10 +263,13 @@ def run_ev_case(CityLearnEnv, name, dataset, overrides=None, reward=None, steps=
             act.append(a[o:o + n])
             o += n
         obs, rew, term, trunc, _ = env.step([a] if env.central_agent else act)
-        out['obs'].append(flat(obs)); out['reward'].append(flat(rew))
+        if k % obs_every == 0:
+            out['obs'].append(flat(obs))
+        out['reward'].append(flat(rew))
         out['district'].append([float(env.net_electricity_consumption[k]), float(env.net_electricity_consumption_cost[k]),
                                 float(env.net_electricity_consumption_emission[k])])
-        out['trace'].append([unit_trace(b, k) for b in env.buildings])
+        if obs_every == 1:
+            out['trace'].append([unit_trace(b, k) for b in env.buildings])
         out['ev_soc'].append([float(e.battery.soc[k]) for e in env.electric_vehicles])
         out['charger_ec'].append([float(c.electricity_consumption[k]) for _, c in chargers])
         out['charger_kwh'].append([float(c.past_charging_action_values_kwh[k]) for _, c in chargers])
@@ -277,6 +280,7 @@ def run_ev_case(CityLearnEnv, name, dataset, overrides=None, reward=None, steps=
               'charger_ec': np.array(out['charger_ec'], dtype='float32'), 'charger_kwh': np.array(out['charger_kwh'], dtype='float32'),
               'wm_ec': np.array(out['wm_ec'], dtype='float32')}
     config = {'dataset': dataset, 'overrides': overrides or {}, 'reward': reward, 'seed': seed, 'np_seed': np_seed, 'trace_names': TRACE_NAMES, 'episodes': episodes,
+              'obs_every': obs_every,
               'episode_window': [int(env.episode_tracker.episode_start_time_step), int(env.episode_tracker.episode_end_time_step)],
               'numpy': np.__version__, 'chargers': [c.charger_id for _, c in chargers], 'vehicles': [e.name for e in env.electric_vehicles]}
     arrays['config'] = np.frombuffer(json.dumps(config).encode(), dtype='uint8')
@@ -301,6 +305,8 @@ EV_CASES = {
     # them up): an episode window in the middle of the year (vehicles already plugged in / away at the first step), a central agent
     'c10_evs_window': dict(dataset='citylearn_challenge_2022_phase_all_plus_evs', steps=120, seed=24, np_seed=11, subdir='ev_cpu',
                            overrides={'simulation_start_time_step': 1200, 'simulation_end_time_step': 1500, 'episode_time_steps': 121}),
+    # the whole year (8 759 steps): every connection / departure of the schedule, a year of battery degradation; observations every 24th step
+    'c10_evs_year': dict(dataset='citylearn_challenge_2022_phase_all_plus_evs', steps=8759, seed=26, np_seed=13, subdir='ev_cpu', obs_every=24),
     'c10_evs_central': dict(dataset='citylearn_challenge_2022_phase_all_plus_evs', steps=100, seed=25, np_seed=12, subdir='ev_cpu',
                             overrides={'central_agent': True}),
     'c10_evs_reward': dict(dataset='citylearn_challenge_2022_phase_all_plus_evs', steps=120, seed=22, np_seed=6),
