@@ -11,17 +11,20 @@ observation at t+1 out.  Metric: building-env steps / s (whole job, all ranks).
             each launch bracketed by CUDA events on the launch stream; the launches are queued without host synchronisation, so
             host launch latency is outside the brackets of all but the first.  `value` / `ms_per_step` come from the MEDIAN
             launch (max over ranks); min / max / first are reported beside it.
-  e2e       the public API with HOST buffers, K steps: env.step_host(ndarray) -> pinned H2D of the actions, kernel, D2H of the
-            rewards + the observation row (reference-parity observation rows are identical for every env, so one row crosses
-            PCIe and the host gets a broadcast view; `e2e_full_observations` is the same loop with the full [E, L] copy).
+  e2e       the public API with HOST buffers, K steps: env.step_host(ndarray) -> ONE native call per step (cl_step_host): this step's
+            [E, A] actions wait in page-locked host memory and are read over PCIe by the step kernel, the rewards + the observation
+            row (reference-parity observation rows are identical for every env, so one row crosses PCIe and the host gets a
+            broadcast view) are written back to page-locked host memory by the kernels, then the stream is synchronised.
+            `e2e_dma_copies` is the same loop with cudaMemcpyAsync H2D / D2H around the kernel, `e2e_full_observations` the loop with
+            the full [E, L] observation copy, `e2e_rollout_host` K steps per call.
   roofline  HBM: bytes a rollout launch MOVES (actions + observations + rewards + district sums; the unit state stays in
             registers between the steps of a launch) / median launch duration.
   cpu_baseline  the UNMODIFIED reference (oracle/_ref, installed by oracle/build_ref.py) on one host core, when present; else the
             NumPy oracle port.
   extra     (N = 1, or --extras; C4 and C5 at every N) BASELINE configs[4] (C5: closed loop with an on-device policy, 32 768 envs in total),
-            BASELINE configs[2] (C3: 3 LSTM buildings x 65 536 envs, MARL, against a measured FP32-FMA
-            peak), configs[3] per-GPU share (C4: synthetic 1024 buildings x 1024 envs, full-year rollout) and configs[1] with
-            stale_observations=False (fresh observations) ride on the same JSON line under "extra".
+            BASELINE configs[2] (C3: 3 LSTM buildings x 65 536 envs, MARL; LSTM cell on the tensor cores), configs[3] per-GPU share (C4: synthetic 1024 buildings x 1024 envs, full-year rollout) and configs[1] with
+            stale_observations=False (fresh observations) ride on the same JSON line under "extra"; at N > 1 also the building-sharded
+            district (district sums completed inside the step kernel over NVLink peer memory vs the NCCL two-phase variant).
 
 `--impl reference` times the reference's own CPU step on all host cores (one process per core, one env each; oracle/_ref when it
 travelled with the snapshot, else the oracle port) and prints the same line with "impl": "reference".
